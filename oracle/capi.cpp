@@ -1,0 +1,190 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see orc_math.hpp header).
+// Flat C entry points for ctypes (oracle/binding.py). Not part of the product's C ABI.
+#include "orc_ipc.hpp"
+#include <chrono>
+
+using namespace orc;
+
+extern "C" {
+
+struct OrcMesh {
+    int nV; const double* X; const double* X0;
+    int nBN; const int* bnode; int nBE; const int* bedge; int nBT; const int* btri;
+    const uint8_t* dbc;
+};
+static Mesh to_mesh(const OrcMesh* m)
+{
+    Mesh r;
+    r.nV = m->nV; r.X = m->X; r.X0 = m->X0; r.nBN = m->nBN; r.bnode = m->bnode; r.nBE = m->nBE; r.bedge = m->bedge;
+    r.nBT = m->nBT; r.btri = m->btri; r.dbc = m->dbc;
+    return r;
+}
+static std::vector<Row> to_rows(long n, const int* rows)
+{
+    std::vector<Row> r(n);
+    for (long i = 0; i < n; ++i) r[i] = {rows[4 * i], rows[4 * i + 1], rows[4 * i + 2], rows[4 * i + 3]};
+    return r;
+}
+
+// ---- constraint set -------------------------------------------------------------------------
+void* orc_constraint_set(const OrcMesh* m, double dHat2, double thickness, int brute, int wantCand)
+{
+    auto* R = new ConstraintSetResult();
+    compute_constraint_set(to_mesh(m), dHat2, thickness, brute != 0, wantCand != 0, *R);
+    return R;
+}
+long orc_cs_count(void* h, int which)
+{
+    auto* R = (ConstraintSetResult*)h;
+    return which == 0 ? (long)R->rows.size() : (which == 1 ? (long)R->candPT.size() : (long)R->candEE.size());
+}
+void orc_cs_copy(void* h, int* rows, double* info, int* candPT, int* candEE)
+{
+    auto* R = (ConstraintSetResult*)h;
+    if (rows) for (size_t i = 0; i < R->rows.size(); ++i) for (int k = 0; k < 4; ++k) rows[4 * i + k] = R->rows[i][k];
+    if (info) for (size_t i = 0; i < R->info.size(); ++i) { info[2 * i] = R->info[i][0]; info[2 * i + 1] = R->info[i][1]; }
+    if (candPT) for (size_t i = 0; i < R->candPT.size(); ++i) { candPT[2 * i] = R->candPT[i][0]; candPT[2 * i + 1] = R->candPT[i][1]; }
+    if (candEE) for (size_t i = 0; i < R->candEE.size(); ++i) { candEE[2 * i] = R->candEE[i][0]; candEE[2 * i + 1] = R->candEE[i][1]; }
+}
+void orc_cs_free(void* h) { delete (ConstraintSetResult*)h; }
+
+// ---- barrier --------------------------------------------------------------------------------
+int orc_barrier(const OrcMesh* m, long n, const int* rows, const double* weight, double dHat2, double kappa,
+    double thickness, double* E)
+{
+    return compute_barrier(to_mesh(m), to_rows(n, rows), weight, dHat2, kappa, thickness, *E);
+}
+int orc_barrier_gradient(const OrcMesh* m, long n, const int* rows, const double* weight, double dHat2, double kappa,
+    double thickness, double* g)
+{
+    return compute_barrier_gradient(to_mesh(m), to_rows(n, rows), weight, dHat2, kappa, thickness, g);
+}
+struct HessHandle { Triplets T; CSR A; int status; };
+void* orc_barrier_hessian(const OrcMesh* m, long n, const int* rows, const double* weight, double dHat2, double kappa,
+    double thickness, int projectSPD, int buildCSR)
+{
+    auto* h = new HessHandle();
+    h->status = compute_barrier_hessian(to_mesh(m), to_rows(n, rows), weight, dHat2, kappa, thickness, projectSPD != 0, h->T);
+    if (buildCSR && h->status == OK) csr_from_triplets(3 * m->nV, h->T, h->A);
+    return h;
+}
+int orc_hess_status(void* h) { return ((HessHandle*)h)->status; }
+long orc_hess_count(void* h, int which) { auto* H = (HessHandle*)h; return which == 0 ? (long)H->T.v.size() : (long)H->A.col.size(); }
+void orc_hess_copy(void* h, int* tr, int* tc, double* tv, int* ptr, int* col, double* val)
+{
+    auto* H = (HessHandle*)h;
+    if (tr) std::copy(H->T.r.begin(), H->T.r.end(), tr);
+    if (tc) std::copy(H->T.c.begin(), H->T.c.end(), tc);
+    if (tv) std::copy(H->T.v.begin(), H->T.v.end(), tv);
+    if (ptr) std::copy(H->A.ptr.begin(), H->A.ptr.end(), ptr);
+    if (col) std::copy(H->A.col.begin(), H->A.col.end(), col);
+    if (val) std::copy(H->A.val.begin(), H->A.val.end(), val);
+}
+void orc_hess_free(void* h) { delete (HessHandle*)h; }
+
+// per-row local E / g / H (dense n x n, n = 3*nv) for one row; returns status, writes nv and stencil
+int orc_row_EgH(const OrcMesh* m, const int* row, double weight, double dHat2, double kappa, double thickness,
+    int projectSPD, double* E, double* g, double* H, int* nv, int* verts)
+{
+    Decoded d;
+    const Row r = {row[0], row[1], row[2], row[3]};
+    const int st = row_EgH(to_mesh(m), r, weight, adjusted_dhat2(dHat2, thickness), kappa, thickness * thickness,
+        projectSPD != 0, E, g, H, &d);
+    *nv = d.nv;
+    for (int i = 0; i < 4; ++i) verts[i] = d.v[i];
+    return st;
+}
+
+void orc_min_dist2(const OrcMesh* m, long n, const int* rows, double thickness, double* dist2, double* minDist2)
+{
+    std::vector<double> d;
+    compute_min_dist2(to_mesh(m), to_rows(n, rows), thickness, d, *minDist2);
+    if (dist2) std::copy(d.begin(), d.end(), dist2);
+}
+
+// ---- CCD ------------------------------------------------------------------------------------
+void* orc_ccd(const OrcMesh* m, const double* dir, double thickness, int brute, int wantCand, double* step,
+    double* step_after_clamp, long* iters, int* status)
+{
+    auto* R = new CCDResult();
+    R->step = *step;
+    *status = compute_intersection_free_stepsize(to_mesh(m), dir, thickness, brute != 0, wantCand != 0, *R);
+    *step = R->step;
+    *step_after_clamp = R->step_after_clamp;
+    *iters = R->iters;
+    return R;
+}
+long orc_ccd_count(void* h, int which) { auto* R = (CCDResult*)h; return which == 1 ? (long)R->candPT.size() : (long)R->candEE.size(); }
+void orc_ccd_copy(void* h, int* candPT, int* candEE)
+{
+    auto* R = (CCDResult*)h;
+    if (candPT) for (size_t i = 0; i < R->candPT.size(); ++i) { candPT[2 * i] = R->candPT[i][0]; candPT[2 * i + 1] = R->candPT[i][1]; }
+    if (candEE) for (size_t i = 0; i < R->candEE.size(); ++i) { candEE[2 * i] = R->candEE[i][0]; candEE[2 * i + 1] = R->candEE[i][1]; }
+}
+void orc_ccd_free(void* h) { delete (CCDResult*)h; }
+
+// ---- per-pair functions for unit tests --------------------------------------------------------
+// x: 4 points x 3 (or fewer for PE / PP)
+int orc_pt_type(const double* x) { return pt_type(ld3(x), ld3(x + 3), ld3(x + 6), ld3(x + 9)); }
+int orc_ee_type(const double* x) { return ee_type(ld3(x), ld3(x + 3), ld3(x + 6), ld3(x + 9)); }
+double orc_dist2(int kind, const double* x) // 0 PP, 1 PE, 2 PT, 3 EE, 4 PT unclassified, 5 EE unclassified, 6 EE cross norm2
+{
+    switch (kind) {
+    case 0: return dist2_pp(ld3(x), ld3(x + 3));
+    case 1: return dist2_pe(ld3(x), ld3(x + 3), ld3(x + 6));
+    case 2: return dist2_pt(ld3(x), ld3(x + 3), ld3(x + 6), ld3(x + 9));
+    case 3: return dist2_ee(ld3(x), ld3(x + 3), ld3(x + 6), ld3(x + 9));
+    case 4: return dist2_pt_unclassified(ld3(x), ld3(x + 3), ld3(x + 6), ld3(x + 9));
+    case 5: return dist2_ee_unclassified(ld3(x), ld3(x + 3), ld3(x + 6), ld3(x + 9));
+    default: return ee_cross_norm2(ld3(x), ld3(x + 3), ld3(x + 6), ld3(x + 9));
+    }
+}
+// closed-form (jet=0) or autodiff (jet=1) gradient/Hessian; kind: 0 PP, 1 PE, 2 PT, 3 EE, 6 EE cross norm2
+void orc_grad_hess(int kind, int jet, const double* x, double* g, double* H)
+{
+    const V3 a = ld3(x), b = ld3(x + 3);
+    switch (kind) {
+    case 0: pp_grad_hess(a, b, g, H); break;
+    case 1: if (jet) pe_jet(a, b, ld3(x + 6), g, H); else pe_grad_hess(a, b, ld3(x + 6), g, H); break;
+    case 2: if (jet) pt_jet(a, b, ld3(x + 6), ld3(x + 9), g, H); else pt_grad_hess(a, b, ld3(x + 6), ld3(x + 9), g, H); break;
+    case 3: if (jet) ee_jet(a, b, ld3(x + 6), ld3(x + 9), g, H); else ee_grad_hess(a, b, ld3(x + 6), ld3(x + 9), g, H); break;
+    default: if (jet) eecn2_jet(a, b, ld3(x + 6), ld3(x + 9), g, H); else ee_cross_norm2_grad_hess(a, b, ld3(x + 6), ld3(x + 9), g, H); break;
+    }
+}
+void orc_mollifier(const double* x, double eps_x, double* e, double* g, double* H)
+{
+    ee_mollifier_all(ld3(x), ld3(x + 3), ld3(x + 6), ld3(x + 9), eps_x, *e, g, H);
+}
+double orc_mollifier_threshold(const double* x0) { return ee_mollifier_threshold(ld3(x0), ld3(x0 + 3), ld3(x0 + 6), ld3(x0 + 9)); }
+void orc_barrier_scalar(double d, double dHat2, double kappa, double* b, double* g, double* h)
+{
+    *b = barrier(d, dHat2, kappa); *g = barrier_g(d, dHat2, kappa); *h = barrier_h(d, dHat2, kappa);
+}
+void orc_make_pd(int n, double* H) { make_pd(n, H); }
+void orc_sym_eig(int n, const double* A, double* lam, double* V) { sym_eig_jacobi(n, A, lam, V); }
+// ACCD: x = 4 points, d = 4 displacements; kind 0 PT, 1 EE. returns 1 if hit
+int orc_accd(int kind, const double* x, const double* d, double eta, double thickness, double* toc, long* iters)
+{
+    long it = 0;
+    bool r;
+    if (kind == 0) r = accd_pt(ld3(x), ld3(x + 3), ld3(x + 6), ld3(x + 9), ld3(d), ld3(d + 3), ld3(d + 6), ld3(d + 9), eta, thickness, *toc, &it);
+    else r = accd_ee(ld3(x), ld3(x + 3), ld3(x + 6), ld3(x + 9), ld3(d), ld3(d + 3), ld3(d + 6), ld3(d + 9), eta, thickness, *toc, &it);
+    if (iters) *iters = it;
+    return r ? 1 : 0;
+}
+int orc_aabb(int kind, const double* x, const double* d, double dist) // 0 PT static, 1 EE static, 2 PT swept, 3 EE swept
+{
+    switch (kind) {
+    case 0: return pt_cd_broadphase(ld3(x), ld3(x + 3), ld3(x + 6), ld3(x + 9), dist);
+    case 1: return ee_cd_broadphase(ld3(x), ld3(x + 3), ld3(x + 6), ld3(x + 9), dist);
+    case 2: return pt_ccd_broadphase(ld3(x), ld3(x + 3), ld3(x + 6), ld3(x + 9), ld3(d), ld3(d + 3), ld3(d + 6), ld3(d + 9), dist);
+    default: return ee_ccd_broadphase(ld3(x), ld3(x + 3), ld3(x + 6), ld3(x + 9), ld3(d), ld3(d + 3), ld3(d + 6), ld3(d + 9), dist);
+    }
+}
+double orc_tree_mean(const double* a, long n) { return tree_sum(a, n) / n; }
+double orc_mean_edge_length(const OrcMesh* m) { return SpatialHash::mean_edge_length(to_mesh(m)); }
+
+// wall-clock helper for the CPU-baseline leg of bench.py
+double orc_now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+} // extern "C"
