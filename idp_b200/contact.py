@@ -1,0 +1,245 @@
+"""ctypes view of the C ABI in include/idp_contact.h (libidp_contact.so).
+
+This is the harness tests/ and bench.py drive the library with; the product's host side is the C++ header
+idp_b200/host/IPC_B200.h, which mirrors the reference's six operators (Library/FEM/IPC.h). There is no CPU
+fallback here: if the shared library or a CUDA device is missing, construction raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libidp_contact.so")
+
+STATUS = {0: "IDP_OK", 1: "IDP_ERR_CUDA", 2: "IDP_ERR_INVALID", 3: "IDP_ERR_NONPOSITIVE_DISTANCE",
+          4: "IDP_ERR_CCD_ZERO_STEP", 5: "IDP_ERR_UNSUPPORTED_PRIMITIVE", 6: "IDP_ERR_NCCL",
+          7: "IDP_ERR_CCD_ITERATION_CAP"}
+STAGES = ["Compute_Constraint_Set_Build_Hash", "Compute_Constraint_Set_PT", "Compute_Constraint_Set_EE",
+          "Compute_Constraint_Set_Merge", "Compute_Barrier_EgH", "constructCSRMatrixFromTriplet",
+          "Compute_Intersection_Free_StepSize_Build_Hash", "Compute_Intersection_Free_StepSize_PT",
+          "Compute_Intersection_Free_StepSize_EE", "Compute_Min_Dist", "upload"]
+
+# every symbol include/idp_contact.h declares
+EXPORTS = ["idp_create", "idp_destroy", "idp_last_error", "idp_set_stream", "idp_set_mesh", "idp_declare_unsupported",
+           "idp_set_positions", "idp_set_rest_positions", "idp_constraint_set", "idp_get_constraints",
+           "idp_set_constraints", "idp_get_candidates", "idp_barrier_energy", "idp_barrier_gradient",
+           "idp_barrier_hessian", "idp_barrier_all", "idp_get_hessian_csr", "idp_hessian_csr_device",
+           "idp_gradient_device", "idp_ccd_step", "idp_min_dist2", "idp_comm_unique_id", "idp_comm_init",
+           "idp_set_shard", "idp_kernel_launches", "idp_library_calls", "idp_reset_counters", "idp_stage_ms",
+           "idp_last_count", "idp_measure_fp64_tflops"]
+
+
+class IdpError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("%s: %s" % (STATUS.get(code, code), msg))
+        self.code = code
+
+
+def load_library(path=LIB_PATH):
+    if not os.path.exists(path):
+        raise FileNotFoundError("%s is missing: run __graft_entry__.build() (make -C idp_b200/csrc)" % path)
+    L = C.CDLL(path)
+    vp, i, d, l = C.c_void_p, C.c_int, C.c_double, C.c_long
+    L.idp_create.argtypes = [i, C.POINTER(vp)]
+    L.idp_destroy.argtypes = [vp]
+    L.idp_destroy.restype = None
+    L.idp_last_error.argtypes = [vp]
+    L.idp_last_error.restype = C.c_char_p
+    L.idp_set_stream.argtypes = [vp, vp]
+    L.idp_set_mesh.argtypes = [vp, i, i, vp, i, vp, i, vp, vp]
+    L.idp_declare_unsupported.argtypes = [vp, i, i, i]
+    L.idp_set_positions.argtypes = [vp, vp, i]
+    L.idp_set_rest_positions.argtypes = [vp, vp, i]
+    L.idp_constraint_set.argtypes = [vp, d, d, C.POINTER(i)]
+    L.idp_get_constraints.argtypes = [vp, vp, vp]
+    L.idp_set_constraints.argtypes = [vp, i, vp, vp]
+    L.idp_get_candidates.argtypes = [vp, i, C.POINTER(l), vp]
+    L.idp_barrier_energy.argtypes = [vp, d, d, d, C.POINTER(d)]
+    L.idp_barrier_gradient.argtypes = [vp, d, d, d, vp, i]
+    L.idp_barrier_hessian.argtypes = [vp, d, d, d, i, C.POINTER(l)]
+    L.idp_barrier_all.argtypes = [vp, d, d, d, i, C.POINTER(d), C.POINTER(l)]
+    L.idp_get_hessian_csr.argtypes = [vp, vp, vp, vp]
+    L.idp_hessian_csr_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(l)]
+    L.idp_gradient_device.argtypes = [vp, C.POINTER(vp)]
+    L.idp_ccd_step.argtypes = [vp, vp, i, d, C.POINTER(d)]
+    L.idp_min_dist2.argtypes = [vp, d, vp, C.POINTER(d)]
+    L.idp_comm_unique_id.argtypes = [vp]
+    L.idp_comm_init.argtypes = [vp, i, i, vp]
+    L.idp_set_shard.argtypes = [vp, i, i]
+    L.idp_kernel_launches.argtypes = [vp]
+    L.idp_kernel_launches.restype = l
+    L.idp_library_calls.argtypes = [vp]
+    L.idp_library_calls.restype = l
+    L.idp_reset_counters.argtypes = [vp]
+    L.idp_reset_counters.restype = None
+    L.idp_stage_ms.argtypes = [vp, i]
+    L.idp_stage_ms.restype = C.c_float
+    L.idp_last_count.argtypes = [vp, i]
+    L.idp_last_count.restype = l
+    L.idp_measure_fp64_tflops.argtypes = [vp, C.POINTER(d)]
+    return L
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class ContactContext:
+    """One GPU context. Methods mirror the C entry points one to one."""
+
+    def __init__(self, device=0, lib=None):
+        self.L = lib or load_library()
+        h = C.c_void_p()
+        st = self.L.idp_create(device, C.byref(h))
+        if st != 0:
+            raise IdpError(st, "idp_create(device=%d) failed (no CUDA device? there is no CPU fallback)" % device)
+        self.h = h
+        self.nV = 0
+        self._keep = []
+
+    def close(self):
+        if self.h:
+            self.L.idp_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, st):
+        if st != 0:
+            raise IdpError(st, self.L.idp_last_error(self.h).decode())
+
+    # ---- inputs ----
+    def set_stream(self, cuda_stream):
+        self._ck(self.L.idp_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    def set_mesh(self, nV, bnode, bedge, btri, dbc=None):
+        bnode = np.ascontiguousarray(bnode, np.int32)
+        bedge = np.ascontiguousarray(bedge, np.int32).reshape(-1, 2)
+        btri = np.ascontiguousarray(btri, np.int32).reshape(-1, 3)
+        dbc = None if dbc is None else np.ascontiguousarray(dbc, np.uint8)
+        self.nV = int(nV)
+        self._ck(self.L.idp_set_mesh(self.h, nV, len(bnode), _p(bnode), len(bedge), _p(bedge), len(btri), _p(btri), _p(dbc)))
+
+    def set_surface_mesh(self, mesh):
+        """mesh: idp_b200.meshgen.SurfaceMesh"""
+        self.set_mesh(mesh.nV, mesh.bnode, mesh.bedge, mesh.btri, mesh.dbc)
+        self.set_rest_positions(mesh.X0)
+        self.set_positions(mesh.X)
+
+    def set_positions(self, X):
+        X = np.ascontiguousarray(X, np.float64)
+        self._ck(self.L.idp_set_positions(self.h, _p(X), X.shape[1]))
+
+    def set_rest_positions(self, X0):
+        X0 = np.ascontiguousarray(X0, np.float64)
+        self._ck(self.L.idp_set_rest_positions(self.h, _p(X0), X0.shape[1]))
+
+    def declare_unsupported(self, n_rod=0, n_particle=0, n_nn=0):
+        self._ck(self.L.idp_declare_unsupported(self.h, n_rod, n_particle, n_nn))
+
+    # ---- constraint set ----
+    def constraint_set(self, dhat2, thickness=0.0):
+        n = C.c_int(0)
+        self._ck(self.L.idp_constraint_set(self.h, dhat2, thickness, C.byref(n)))
+        return n.value
+
+    def get_constraints(self):
+        n = self.L.idp_last_count(self.h, 0)
+        rows = np.empty((n, 4), np.int32)
+        info = np.empty((n, 2), np.float64)
+        self._ck(self.L.idp_get_constraints(self.h, _p(rows), _p(info)))
+        return rows, info
+
+    def set_constraints(self, rows, info=None):
+        rows = np.ascontiguousarray(rows, np.int32).reshape(-1, 4)
+        info = None if info is None else np.ascontiguousarray(info, np.float64).reshape(-1, 2)
+        self._ck(self.L.idp_set_constraints(self.h, len(rows), _p(rows), _p(info)))
+
+    def get_candidates(self, which):
+        n = C.c_long(0)
+        self._ck(self.L.idp_get_candidates(self.h, which, C.byref(n), None))
+        out = np.empty((n.value, 2), np.int32)
+        if n.value:
+            self._ck(self.L.idp_get_candidates(self.h, which, C.byref(n), _p(out)))
+        return out
+
+    # ---- barrier ----
+    def barrier_energy(self, dhat2, kappa, thickness=0.0, E0=0.0):
+        E = C.c_double(E0)
+        self._ck(self.L.idp_barrier_energy(self.h, dhat2, kappa, thickness, C.byref(E)))
+        return E.value
+
+    def barrier_gradient(self, dhat2, kappa, thickness=0.0, g_accum=None):
+        g = np.zeros((self.nV, 3), np.float64) if g_accum is None else g_accum
+        self._ck(self.L.idp_barrier_gradient(self.h, dhat2, kappa, thickness, _p(g), g.shape[1]))
+        return g
+
+    def barrier_hessian(self, dhat2, kappa, thickness=0.0, project_spd=True, fetch=True):
+        nnz = C.c_long(0)
+        self._ck(self.L.idp_barrier_hessian(self.h, dhat2, kappa, thickness, int(project_spd), C.byref(nnz)))
+        return self.get_hessian_csr() if fetch else nnz.value
+
+    def barrier_all(self, dhat2, kappa, thickness=0.0, project_spd=True):
+        E = C.c_double(0.0)
+        nnz = C.c_long(0)
+        self._ck(self.L.idp_barrier_all(self.h, dhat2, kappa, thickness, int(project_spd), C.byref(E), C.byref(nnz)))
+        return E.value, nnz.value
+
+    def get_hessian_csr(self):
+        nnz = self.L.idp_last_count(self.h, 6)
+        ptr = np.empty(3 * self.nV + 1, np.int32)
+        col = np.empty(nnz, np.int32)
+        val = np.empty(nnz, np.float64)
+        self._ck(self.L.idp_get_hessian_csr(self.h, _p(ptr), _p(col), _p(val)))
+        return ptr, col, val
+
+    # ---- CCD / min distance ----
+    def ccd_step(self, direction, alpha=1.0, thickness=0.0):
+        direction = np.ascontiguousarray(direction, np.float64)
+        a = C.c_double(alpha)
+        self._ck(self.L.idp_ccd_step(self.h, _p(direction), direction.shape[1], thickness, C.byref(a)))
+        return a.value
+
+    def min_dist2(self, thickness=0.0, want_all=True):
+        n = self.L.idp_last_count(self.h, 0)
+        d = np.empty(n, np.float64) if want_all else None
+        m = C.c_double(np.nan)
+        self._ck(self.L.idp_min_dist2(self.h, thickness, _p(d), C.byref(m)))
+        return d, m.value
+
+    # ---- sharding / instrumentation ----
+    def set_shard(self, rank, nranks):
+        self._ck(self.L.idp_set_shard(self.h, rank, nranks))
+
+    def comm_init(self, rank, nranks, uid_bytes):
+        buf = C.create_string_buffer(bytes(uid_bytes), 128)
+        self._ck(self.L.idp_comm_init(self.h, rank, nranks, buf))
+
+    def unique_id(self):
+        buf = C.create_string_buffer(128)
+        st = self.L.idp_comm_unique_id(buf)
+        if st != 0:
+            raise IdpError(st, "ncclGetUniqueId failed")
+        return buf.raw
+
+    def launches(self):
+        return self.L.idp_kernel_launches(self.h), self.L.idp_library_calls(self.h)
+
+    def reset_counters(self):
+        self.L.idp_reset_counters(self.h)
+
+    def stage_ms(self):
+        return {STAGES[i]: float(self.L.idp_stage_ms(self.h, i)) for i in range(len(STAGES))}
+
+    def count(self, what):
+        return self.L.idp_last_count(self.h, what)
+
+    def fp64_tflops(self):
+        t = C.c_double(0)
+        self._ck(self.L.idp_measure_fp64_tflops(self.h, C.byref(t)))
+        return t.value

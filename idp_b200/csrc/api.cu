@@ -1,0 +1,315 @@
+// extern "C" launcher layer of libidp_contact.so (include/idp_contact.h). Thin: argument checks, marshalling of
+// host buffers, and calls into the launchers of exact_kernels.cu / barrier_kernels.cu / comm.cu.
+#include "ctx.cuh"
+#include <string.h>
+
+using namespace idp;
+
+namespace idp {
+int comm_allreduce_sum(idp_ctx* c, double* dev, long n);
+int comm_allreduce_min(idp_ctx* c, double* dev, long n);
+void comm_destroy(idp_ctx* c);
+} // namespace idp
+
+extern "C" {
+
+int idp_create(int device, idp_ctx** out)
+{
+    if (!out) return IDP_ERR_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return IDP_ERR_CUDA; // no CPU fallback
+    if (cudaSetDevice(device) != cudaSuccess) return IDP_ERR_CUDA;
+    idp_ctx* c = new idp_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return IDP_ERR_CUDA; }
+    c->own_stream = true;
+    cudaEventCreate(&c->ev0);
+    cudaEventCreate(&c->ev1);
+    if (c->counters.reserve(CNT_COUNT) != cudaSuccess) { delete c; return IDP_ERR_CUDA; }
+    cudaMemset(c->counters.p, 0, CNT_COUNT * sizeof(long long));
+    cudaMallocHost((void**)&c->h_counters, CNT_COUNT * sizeof(long long));
+    cudaMallocHost((void**)&c->h_red, 64 * sizeof(double));
+    memset(c->h_counters, 0, CNT_COUNT * sizeof(long long));
+    memset(&c->times, 0, sizeof(c->times));
+    *out = c;
+    return IDP_OK;
+}
+
+void idp_destroy(idp_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    comm_destroy(c);
+    if (c->h_counters) cudaFreeHost(c->h_counters);
+    if (c->h_red) cudaFreeHost(c->h_red);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    cudaStream_t s = c->own_stream ? c->stream : nullptr;
+    delete c; // frees the device buffers
+    if (s) cudaStreamDestroy(s);
+}
+
+const char* idp_last_error(idp_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int idp_set_stream(idp_ctx* c, void* stream)
+{
+    if (!c) return IDP_ERR_INVALID;
+    cudaStreamSynchronize(c->stream);
+    if (stream) {
+        if (c->own_stream) cudaStreamDestroy(c->stream);
+        c->stream = (cudaStream_t)stream;
+        c->own_stream = false;
+    }
+    else if (!c->own_stream) {
+        IDP_CK(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
+    return IDP_OK;
+}
+
+int idp_set_mesh(idp_ctx* c, int nV, int nBN, const int* bnode, int nBE, const int* bedge2, int nBT, const int* btri3,
+    const uint8_t* dbc)
+{
+    if (!c || nV <= 0 || nBN < 0 || nBE < 0 || nBT < 0 || (nBN && !bnode) || (nBE && !bedge2) || (nBT && !btri3))
+        return c ? fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "idp_set_mesh: bad arguments", __FILE__, __LINE__) : IDP_ERR_INVALID;
+    IDP_CK(c, cudaSetDevice(c->device));
+    c->nV = nV; c->nBN = nBN; c->nBE = nBE; c->nBT = nBT;
+    c->have_x = c->have_x0 = false;
+    c->nRows = 0; c->nCandPT = c->nCandEE = c->nCcdPT = c->nCcdEE = 0;
+    IDP_CK(c, c->bnode.reserve(std::max(nBN, 1)));
+    IDP_CK(c, c->bedge.reserve(std::max(nBE, 1)));
+    IDP_CK(c, c->btri.reserve(std::max(nBT, 1)));
+    IDP_CK(c, c->dbc.reserve(nV));
+    if (nBN) IDP_CK(c, cudaMemcpyAsync(c->bnode.p, bnode, nBN * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    if (nBE) IDP_CK(c, cudaMemcpyAsync(c->bedge.p, bedge2, nBE * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
+    if (nBT) {
+        std::vector<int4> t4(nBT);
+        for (int i = 0; i < nBT; ++i) t4[i] = make_int4(btri3[3 * i], btri3[3 * i + 1], btri3[3 * i + 2], 0);
+        IDP_CK(c, cudaMemcpyAsync(c->btri.p, t4.data(), nBT * sizeof(int4), cudaMemcpyHostToDevice, c->stream));
+        IDP_CK(c, cudaStreamSynchronize(c->stream));
+    }
+    if (dbc) IDP_CK(c, cudaMemcpyAsync(c->dbc.p, dbc, nV, cudaMemcpyHostToDevice, c->stream));
+    else IDP_CK(c, cudaMemsetAsync(c->dbc.p, 0, nV, c->stream));
+    IDP_CK(c, cudaStreamSynchronize(c->stream));
+    return IDP_OK;
+}
+
+int idp_declare_unsupported(idp_ctx* c, int n_rod, int n_particle, int n_nn)
+{
+    if (!c) return IDP_ERR_INVALID;
+    if (n_rod || n_particle || n_nn)
+        return fail(c, IDP_ERR_UNSUPPORTED_PRIMITIVE, "%s (%s:%d)", "rod / particle / NNExclusion inputs are outside the ported path", __FILE__, __LINE__);
+    return IDP_OK;
+}
+
+int idp_set_positions(idp_ctx* c, const double* x, int stride)
+{
+    if (!c || !x) return IDP_ERR_INVALID;
+    IDP_CK(c, cudaSetDevice(c->device));
+    return upload_positions(c, x, stride, 0);
+}
+int idp_set_rest_positions(idp_ctx* c, const double* x0, int stride)
+{
+    if (!c || !x0) return IDP_ERR_INVALID;
+    IDP_CK(c, cudaSetDevice(c->device));
+    return upload_positions(c, x0, stride, 1);
+}
+
+int idp_constraint_set(idp_ctx* c, double dhat2, double thickness, int* n_rows)
+{
+    if (!c) return IDP_ERR_INVALID;
+    IDP_CK(c, cudaSetDevice(c->device));
+    IDP_TRY(build_constraint_set(c, dhat2, thickness));
+    if (n_rows) *n_rows = (int)c->nRows;
+    return IDP_OK;
+}
+
+int idp_get_constraints(idp_ctx* c, int* rows4, double* info2)
+{
+    if (!c) return IDP_ERR_INVALID;
+    IDP_CK(c, cudaSetDevice(c->device));
+    if (rows4 && c->nRows) {
+        IDP_CK(c, cudaMemcpyAsync(rows4, c->rows.p, c->nRows * sizeof(Row4), cudaMemcpyDeviceToHost, c->stream));
+        IDP_CK(c, cudaStreamSynchronize(c->stream));
+    }
+    if (info2 && c->nRows) {
+        std::vector<double> w(c->nRows);
+        IDP_CK(c, cudaMemcpyAsync(w.data(), c->weights.p, c->nRows * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        IDP_CK(c, cudaStreamSynchronize(c->stream));
+        for (long i = 0; i < c->nRows; ++i) { info2[2 * i] = w[i]; info2[2 * i + 1] = c->cs_dhat2; }
+    }
+    return IDP_OK;
+}
+
+int idp_set_constraints(idp_ctx* c, int n, const int* rows4, const double* info2)
+{
+    if (!c || n < 0 || (n && !rows4)) return IDP_ERR_INVALID;
+    IDP_CK(c, cudaSetDevice(c->device));
+    c->nRows = n;
+    IDP_CK(c, c->rows.reserve(std::max(n, 1)));
+    IDP_CK(c, c->weights.reserve(std::max(n, 1)));
+    if (n) {
+        IDP_CK(c, cudaMemcpyAsync(c->rows.p, rows4, (size_t)n * sizeof(Row4), cudaMemcpyHostToDevice, c->stream));
+        std::vector<double> w(n, 1.0);
+        if (info2) {
+            for (int i = 0; i < n; ++i) w[i] = info2[2 * i];
+            c->cs_dhat2 = info2[1];
+        }
+        IDP_CK(c, cudaMemcpyAsync(c->weights.p, w.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        IDP_CK(c, cudaStreamSynchronize(c->stream));
+    }
+    return IDP_OK;
+}
+
+int idp_get_candidates(idp_ctx* c, int which, long* n_pairs, int* pairs2)
+{
+    if (!c || which < 0 || which > 3 || !n_pairs) return IDP_ERR_INVALID;
+    IDP_CK(c, cudaSetDevice(c->device));
+    *n_pairs = which == 0 ? c->nCandPT : (which == 1 ? c->nCandEE : (which == 2 ? c->nCcdPT : c->nCcdEE));
+    if (!pairs2) return IDP_OK;
+    return sorted_candidates(c, which, (int2*)pairs2);
+}
+
+static int finish_energy(idp_ctx* c, double E, double* E_inout)
+{
+    if (c->nranks > 1 && c->nccl_comm) {
+        IDP_CK(c, cudaMemcpyAsync(c->red.p, &E, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        IDP_TRY(comm_allreduce_sum(c, c->red.p, 1));
+        IDP_CK(c, cudaMemcpyAsync(&E, c->red.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        IDP_CK(c, cudaStreamSynchronize(c->stream));
+    }
+    if (E_inout) *E_inout += E;
+    return IDP_OK;
+}
+static int finish_gradient(idp_ctx* c, double* g_accum, int stride)
+{
+    if (c->nranks > 1 && c->nccl_comm) IDP_TRY(comm_allreduce_sum(c, c->gbuf.p, 3L * c->nV));
+    if (!g_accum) return IDP_OK;
+    if (stride < 3) return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "stride must be >= 3", __FILE__, __LINE__);
+    std::vector<double> g(3 * (size_t)c->nV);
+    IDP_CK(c, cudaMemcpyAsync(g.data(), c->gbuf.p, g.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    IDP_CK(c, cudaStreamSynchronize(c->stream));
+    for (long v = 0; v < c->nV; ++v)
+        for (int a = 0; a < 3; ++a) g_accum[v * stride + a] += g[3 * v + a];
+    return IDP_OK;
+}
+
+int idp_barrier_energy(idp_ctx* c, double dhat2, double kappa, double thickness, double* E_inout)
+{
+    if (!c) return IDP_ERR_INVALID;
+    IDP_CK(c, cudaSetDevice(c->device));
+    double E = 0;
+    IDP_TRY(barrier_eval(c, dhat2, kappa, thickness, 1, 0, 0, 0, &E));
+    return finish_energy(c, E, E_inout);
+}
+int idp_barrier_gradient(idp_ctx* c, double dhat2, double kappa, double thickness, double* g_accum, int stride)
+{
+    if (!c) return IDP_ERR_INVALID;
+    IDP_CK(c, cudaSetDevice(c->device));
+    IDP_TRY(barrier_eval(c, dhat2, kappa, thickness, 0, 1, 0, 0, nullptr));
+    return finish_gradient(c, g_accum, stride);
+}
+int idp_barrier_hessian(idp_ctx* c, double dhat2, double kappa, double thickness, int project_spd, long* nnz)
+{
+    if (!c) return IDP_ERR_INVALID;
+    IDP_CK(c, cudaSetDevice(c->device));
+    IDP_TRY(barrier_eval(c, dhat2, kappa, thickness, 0, 0, 1, project_spd, nullptr));
+    IDP_TRY(assemble_csr(c));
+    if (nnz) *nnz = c->nnz;
+    return IDP_OK;
+}
+int idp_barrier_all(idp_ctx* c, double dhat2, double kappa, double thickness, int project_spd, double* E_inout, long* nnz)
+{
+    if (!c) return IDP_ERR_INVALID;
+    IDP_CK(c, cudaSetDevice(c->device));
+    double E = 0;
+    IDP_TRY(barrier_eval(c, dhat2, kappa, thickness, 1, 1, 1, project_spd, &E));
+    IDP_TRY(assemble_csr(c));
+    IDP_TRY(finish_energy(c, E, E_inout));
+    IDP_TRY(finish_gradient(c, nullptr, 3));
+    if (nnz) *nnz = c->nnz;
+    return IDP_OK;
+}
+int idp_get_hessian_csr(idp_ctx* c, int* ptr, int* col, double* val)
+{
+    if (!c) return IDP_ERR_INVALID;
+    IDP_CK(c, cudaSetDevice(c->device));
+    if (ptr) IDP_CK(c, cudaMemcpyAsync(ptr, c->csrPtr.p, (3 * (size_t)c->nV + 1) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (col && c->nnz) IDP_CK(c, cudaMemcpyAsync(col, c->csrCol.p, c->nnz * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (val && c->nnz) IDP_CK(c, cudaMemcpyAsync(val, c->csrVal.p, c->nnz * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    IDP_CK(c, cudaStreamSynchronize(c->stream));
+    return IDP_OK;
+}
+int idp_hessian_csr_device(idp_ctx* c, const int** d_ptr, const int** d_col, const double** d_val, long* nnz)
+{
+    if (!c) return IDP_ERR_INVALID;
+    if (d_ptr) *d_ptr = c->csrPtr.p;
+    if (d_col) *d_col = c->csrCol.p;
+    if (d_val) *d_val = c->csrVal.p;
+    if (nnz) *nnz = c->nnz;
+    return IDP_OK;
+}
+int idp_gradient_device(idp_ctx* c, const double** d_g)
+{
+    if (!c || !d_g) return IDP_ERR_INVALID;
+    *d_g = c->gbuf.p;
+    return IDP_OK;
+}
+
+int idp_ccd_step(idp_ctx* c, const double* dir, int stride, double thickness, double* alpha_inout)
+{
+    if (!c || !dir || !alpha_inout) return IDP_ERR_INVALID;
+    IDP_CK(c, cudaSetDevice(c->device));
+    IDP_TRY(upload_positions(c, dir, stride, 2));
+    double a = *alpha_inout;
+    IDP_TRY(ccd_step(c, thickness, &a, 1));
+    if (c->nranks > 1 && c->nccl_comm) {
+        IDP_CK(c, cudaMemcpyAsync(c->red.p, &a, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        IDP_TRY(comm_allreduce_min(c, c->red.p, 1));
+        IDP_CK(c, cudaMemcpyAsync(&a, c->red.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        IDP_CK(c, cudaStreamSynchronize(c->stream));
+    }
+    *alpha_inout = a;
+    return IDP_OK;
+}
+
+int idp_min_dist2(idp_ctx* c, double thickness, double* dist2, double* min_out)
+{
+    if (!c || !min_out) return IDP_ERR_INVALID;
+    IDP_CK(c, cudaSetDevice(c->device));
+    return min_dist2(c, thickness, dist2, min_out);
+}
+
+int idp_set_shard(idp_ctx* c, int rank, int nranks)
+{
+    if (!c || nranks < 1 || rank < 0 || rank >= nranks) return IDP_ERR_INVALID;
+    c->rank = rank;
+    c->nranks = nranks;
+    return IDP_OK;
+}
+
+long idp_kernel_launches(idp_ctx* c) { return c ? c->launches : 0; }
+long idp_library_calls(idp_ctx* c) { return c ? c->lib_launches : 0; }
+void idp_reset_counters(idp_ctx* c) { if (c) { c->launches = 0; c->lib_launches = 0; } }
+float idp_stage_ms(idp_ctx* c, int stage) { return (c && stage >= 0 && stage < IDP_STAGE_COUNT) ? c->times.v[stage] : 0.f; }
+long idp_last_count(idp_ctx* c, int what)
+{
+    if (!c) return 0;
+    switch (what) {
+    case 0: return c->nRows;
+    case 1: return c->nCandPT;
+    case 2: return c->nCandEE;
+    case 3: return c->nCcdPT;
+    case 4: return c->nCcdEE;
+    case 5: return c->ccd_iters;
+    case 6: return c->nnz;
+    case 7: return c->nBlocksUnique;
+    default: return 0;
+    }
+}
+
+} // extern "C"

@@ -1,0 +1,317 @@
+// Barrier energy / gradient / Hessian per constraint row, per-row PSD projection, and the sort-reduce assembly of the
+// 3x3 blocks into a device-resident scalar CSR.
+//
+// Reference operators replaced (relative to /root/reference/Library):
+//   FEM/IPC.h:742-941 (Compute_Barrier), 943-1256 (Compute_Barrier_Gradient), 1258-1731 (Compute_Barrier_Hessian),
+//   Math/UTILS.h:9-27 (makePD), Math/CSR_MATRIX.h:49-56 (Construct_From_Triplet = Eigen setFromTriplets).
+// Tolerance of these outputs is 1e-10 relative (BASELINE.json), so FMA contraction is allowed in this unit.
+#include "ctx.cuh"
+#include "pair_deriv.cuh"
+#include "psd_lowrank.cuh"
+#include <cub/cub.cuh>
+
+namespace idp {
+
+__device__ __forceinline__ V3 ldv4(const double4* __restrict__ p, int v)
+{
+    const double2* q = reinterpret_cast<const double2*>(p + v);
+    const double2 a = __ldg(q), b = __ldg(q + 1);
+    return mk3(a.x, a.y, b.x);
+}
+
+// number of 3x3 blocks a row contributes: nv^2
+__global__ void k_row_block_counts(const Row4* __restrict__ rows, long n, int* __restrict__ cnt)
+{
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += (long)gridDim.x * blockDim.x) {
+        int k = 0;
+        if (i < n) {
+            const Row4 r = rows[i];
+            k = (r.a >= 0 || r.d >= 0) ? 16 : (r.c >= 0 ? 9 : 4); // IPC.h:1372-1387
+        }
+        cnt[i] = k;
+    }
+}
+
+struct BarrierArgs {
+    const Row4* rows; const double* weights; long rowBegin, rowEnd;
+    const double4* xp; const double4* x0p;
+    double dHat2, kappa, xi2;
+    int projectSPD;
+    double* partialE;                 // one slot per block
+    double* g;                        // 3*nV, xyz interleaved (atomics)
+    const int* blkOff; unsigned long long* blkKey; int* blkIdx; double* blkVal; long long nVll;
+    unsigned long long* errDist;
+};
+
+template <bool WANT_E, bool WANT_G, bool WANT_H>
+__global__ void __launch_bounds__(128) k_barrier(BarrierArgs a)
+{
+    double Eacc = 0;
+    for (long i = a.rowBegin + (long)blockIdx.x * blockDim.x + threadIdx.x; i < a.rowEnd; i += (long)gridDim.x * blockDim.x) {
+        const Row4 r = a.rows[i];
+        const RowDec d = decode_row(r.a, r.b, r.c, r.d);
+        V3 x[4], xr[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) x[k] = ldv4(a.xp, d.v[k]);
+        if (d.kind == K_EE_M || d.kind == K_PE_M || d.kind == K_PP_M) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) xr[k] = ldv4(a.x0p, d.v[k]);
+        }
+        double E = 0, g[12], H[144];
+        const bool ok = row_EgH_lowrank(d, x, xr, a.weights[i], a.dHat2, a.kappa, a.xi2, a.projectSPD != 0,
+            WANT_E ? &E : nullptr, WANT_G ? g : nullptr, WANT_H ? H : nullptr);
+        if (!ok) { atomicAdd(a.errDist, 1ull); continue; }
+        if (WANT_E) Eacc += E;
+        if (WANT_G) {
+            for (int k = 0; k < d.nv; ++k) {
+                double* gp = a.g + 3 * (long)d.v[k];
+                atomicAdd(gp, g[3 * k]); atomicAdd(gp + 1, g[3 * k + 1]); atomicAdd(gp + 2, g[3 * k + 2]);
+            }
+        }
+        if (WANT_H) {
+            const int n = 3 * d.nv;
+            const long o = a.blkOff[i];
+            for (int bi = 0; bi < d.nv; ++bi)
+                for (int bj = 0; bj < d.nv; ++bj) {
+                    const long s = o + bi * d.nv + bj;
+                    a.blkKey[s] = (unsigned long long)((long long)d.v[bi] * a.nVll + d.v[bj]);
+                    a.blkIdx[s] = (int)s;
+                    double* dst = a.blkVal + 9 * s;
+                    for (int p = 0; p < 3; ++p)
+                        for (int q = 0; q < 3; ++q) dst[3 * p + q] = H[(3 * bi + p) * n + 3 * bj + q];
+                }
+        }
+    }
+    if (WANT_E) {
+        typedef cub::BlockReduce<double, 128> BR;
+        __shared__ typename BR::TempStorage tmp;
+        const double s = BR(tmp).Sum(Eacc);
+        if (threadIdx.x == 0) a.partialE[blockIdx.x] = s;
+    }
+}
+
+// deterministic final sum of the per-block partials (single block)
+__global__ void __launch_bounds__(256) k_sum_partials(const double* __restrict__ p, int n, double* __restrict__ out)
+{
+    double s = 0;
+    for (int i = threadIdx.x; i < n; i += 256) s += p[i];
+    typedef cub::BlockReduce<double, 256> BR;
+    __shared__ typename BR::TempStorage tmp;
+    const double t = BR(tmp).Sum(s);
+    if (threadIdx.x == 0) *out = t;
+}
+
+int barrier_eval(idp_ctx* c, double dhat2, double kappa, double thickness, int want_e, int want_g, int want_h,
+    int project_spd, double* E_out)
+{
+    if (!c->have_x) return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "positions not set", __FILE__, __LINE__);
+    if (E_out) *E_out = 0;
+    if (want_g) {
+        IDP_CK(c, c->gbuf.reserve(3 * (size_t)c->nV));
+        IDP_CK(c, cudaMemsetAsync(c->gbuf.p, 0, 3 * (size_t)c->nV * sizeof(double), c->stream));
+    }
+    if (want_h) { c->nnz = 0; c->nBlocksUnique = 0; }
+    if (c->nRows == 0) return IDP_OK;
+    StageTimer tm(c, IDP_STAGE_BARRIER);
+    IDP_CK(c, cudaMemsetAsync(c->counters.p + CNT_ERR_DIST, 0, sizeof(long long), c->stream));
+    const long rb = c->nRows * c->rank / c->nranks, re = c->nRows * (c->rank + 1) / c->nranks;
+    const long nMine = re - rb;
+    const unsigned grid = std::max(1u, std::min(blocks_for(nMine, 128), (unsigned)c->sm_count * 16));
+    BarrierArgs a;
+    a.rows = c->rows.p; a.weights = c->weights.p; a.rowBegin = rb; a.rowEnd = re;
+    a.xp = c->xp.p; a.x0p = c->x0p.p;
+    a.dHat2 = dhat2 + 2 * std::sqrt(dhat2) * thickness; // IPC.h:757
+    a.kappa = kappa; a.xi2 = thickness * thickness; a.projectSPD = project_spd;
+    IDP_CK(c, c->red.reserve(grid + 8));
+    a.partialE = c->red.p;
+    a.g = c->gbuf.p;
+    a.errDist = (unsigned long long*)(c->counters.p + CNT_ERR_DIST);
+    a.nVll = c->nV;
+    a.blkOff = nullptr; a.blkKey = nullptr; a.blkIdx = nullptr; a.blkVal = nullptr;
+    long nBlocks = 0;
+    if (want_h) {
+        IDP_CK(c, c->rowBlkOff.reserve(c->nRows + 1));
+        IDP_CK(c, c->segId.reserve(c->nRows + 1));
+        IDP_LAUNCH(c, k_row_block_counts, blocks_for(c->nRows + 1, 256), 256, 0, c->rows.p, c->nRows, c->segId.p);
+        IDP_TRY(cub_scan_exclusive(c, c->segId.p, c->rowBlkOff.p, c->nRows + 1));
+        int ends[2];
+        IDP_CK(c, cudaMemcpyAsync(&ends[0], c->rowBlkOff.p + rb, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        IDP_CK(c, cudaMemcpyAsync(&ends[1], c->rowBlkOff.p + re, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        IDP_CK(c, cudaStreamSynchronize(c->stream));
+        nBlocks = ends[1]; // offsets are global; a shard fills only its slice [ends[0], ends[1])
+        IDP_CK(c, c->blkKey.reserve(std::max<long>(nBlocks, 1)));
+        IDP_CK(c, c->blkIdx.reserve(std::max<long>(nBlocks, 1)));
+        IDP_CK(c, c->blkVal.reserve(9 * (size_t)std::max<long>(nBlocks, 1)));
+        a.blkOff = c->rowBlkOff.p; a.blkKey = c->blkKey.p; a.blkIdx = c->blkIdx.p; a.blkVal = c->blkVal.p;
+        c->nBlocksUnique = 0;
+        c->nnz = 0;
+        // remember the slice for the assembly
+        c->h_counters[CNT_COUNT - 2] = ends[0];
+        c->h_counters[CNT_COUNT - 1] = ends[1];
+    }
+    if (nMine > 0) {
+        const int sel = (want_e ? 1 : 0) | (want_g ? 2 : 0) | (want_h ? 4 : 0);
+        switch (sel) {
+        case 1: IDP_LAUNCH(c, (k_barrier<true, false, false>), grid, 128, 0, a); break;
+        case 2: IDP_LAUNCH(c, (k_barrier<false, true, false>), grid, 128, 0, a); break;
+        case 3: IDP_LAUNCH(c, (k_barrier<true, true, false>), grid, 128, 0, a); break;
+        case 4: IDP_LAUNCH(c, (k_barrier<false, false, true>), grid, 128, 0, a); break;
+        case 5: IDP_LAUNCH(c, (k_barrier<true, false, true>), grid, 128, 0, a); break;
+        case 6: IDP_LAUNCH(c, (k_barrier<false, true, true>), grid, 128, 0, a); break;
+        case 7: IDP_LAUNCH(c, (k_barrier<true, true, true>), grid, 128, 0, a); break;
+        default: break;
+        }
+        IDP_CK(c, cudaGetLastError());
+        if (want_e) IDP_LAUNCH(c, k_sum_partials, 1, 256, 0, c->red.p, (int)grid, c->red.p + grid);
+    }
+    long long nerr = 0;
+    IDP_CK(c, cudaMemcpyAsync(&nerr, c->counters.p + CNT_ERR_DIST, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    double E = 0;
+    if (want_e && nMine > 0) IDP_CK(c, cudaMemcpyAsync(&E, c->red.p + grid, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    IDP_CK(c, cudaStreamSynchronize(c->stream));
+    if (nerr) return fail(c, IDP_ERR_NONPOSITIVE_DISTANCE, "%s (%s:%d)", "non-positive distance detected during barrier evaluation", __FILE__, __LINE__);
+    if (E_out) *E_out = E;
+    return IDP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// assembly: sort (vi*nV + vj) keys, segmented sum of the 3x3 blocks, scalar CSR with ascending columns
+// ------------------------------------------------------------------------------------------------------------
+__global__ void k_head_flags(const unsigned long long* __restrict__ keys, long n, int* __restrict__ flag)
+{
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+        flag[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+}
+// segId = inclusive scan of flags - 1; scatter segment starts
+__global__ void k_seg_starts(const int* __restrict__ flagScan, const int* __restrict__ flag, long n, int* __restrict__ segStart)
+{
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+        if (flag[i]) segStart[flagScan[i]] = (int)i; // flagScan = exclusive scan -> segment index
+}
+// first unique block of every block row: vtxStart[v] = lower_bound(uniqueKey, v * nV)
+__global__ void k_vertex_block_starts(const unsigned long long* __restrict__ keys, const int* __restrict__ segStart, int nSeg,
+    int nV, int* __restrict__ vtxStart)
+{
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v <= nV; v += gridDim.x * blockDim.x) {
+        const unsigned long long target = (unsigned long long)v * (unsigned long long)nV;
+        int lo = 0, hi = nSeg;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (keys[segStart[mid]] < target) lo = mid + 1;
+            else hi = mid;
+        }
+        vtxStart[v] = lo;
+    }
+}
+__global__ void k_csr_ptr(const int* __restrict__ vtxStart, int nV, int* __restrict__ ptr)
+{
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v <= nV; v += gridDim.x * blockDim.x) {
+        if (v == nV) { ptr[3 * (long)nV] = 9 * vtxStart[nV]; continue; }
+        const int s = vtxStart[v], nb = vtxStart[v + 1] - s;
+        ptr[3 * (long)v] = 9 * s;
+        ptr[3 * (long)v + 1] = 9 * s + 3 * nb;
+        ptr[3 * (long)v + 2] = 9 * s + 6 * nb;
+    }
+}
+// one thread per (unique block, component): sum the members in sorted (= emission) order, write CSR entry
+__global__ void __launch_bounds__(288) k_reduce_blocks(const unsigned long long* __restrict__ keys, const int* __restrict__ idx,
+    const int* __restrict__ segStart, int nSeg, long nTot, const double* __restrict__ blkVal, const int* __restrict__ vtxStart,
+    long long nV, int* __restrict__ col, double* __restrict__ val)
+{
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long seg = t / 9;
+    const int comp = (int)(t - seg * 9);
+    if (seg >= nSeg) return;
+    const int s0 = segStart[seg];
+    const int s1 = (seg + 1 < nSeg) ? segStart[seg + 1] : (int)nTot;
+    double s = 0;
+    for (int m = s0; m < s1; ++m) s += blkVal[9 * (long)idx[m] + comp];
+    const unsigned long long key = keys[s0];
+    const int vi = (int)(key / (unsigned long long)nV), vj = (int)(key - (unsigned long long)vi * (unsigned long long)nV);
+    const int bs = vtxStart[vi], nb = vtxStart[vi + 1] - bs;
+    const int a = comp / 3, b = comp - 3 * a;
+    const long pos = 9L * bs + (long)a * 3 * nb + 3L * (seg - bs) + b;
+    col[pos] = 3 * vj + b;
+    val[pos] = s;
+}
+
+int assemble_csr(idp_ctx* c)
+{
+    StageTimer tm(c, IDP_STAGE_CSR);
+    IDP_CK(c, c->csrPtr.reserve(3 * (size_t)c->nV + 1));
+    const long b0 = c->nRows ? (long)c->h_counters[CNT_COUNT - 2] : 0, b1 = c->nRows ? (long)c->h_counters[CNT_COUNT - 1] : 0;
+    const long n = b1 - b0;
+    if (n <= 0) {
+        IDP_CK(c, cudaMemsetAsync(c->csrPtr.p, 0, (3 * (size_t)c->nV + 1) * sizeof(int), c->stream));
+        c->nnz = 0; c->nBlocksUnique = 0;
+        IDP_CK(c, cudaStreamSynchronize(c->stream));
+        return IDP_OK;
+    }
+    IDP_CK(c, c->blkKeySorted.reserve(n));
+    IDP_CK(c, c->blkIdxSorted.reserve(n));
+    int bits = 1;
+    while (bits < 64 && ((unsigned long long)c->nV * (unsigned long long)c->nV) >> bits) ++bits;
+    size_t bytes = 0;
+    IDP_CK(c, cub::DeviceRadixSort::SortPairs(nullptr, bytes, c->blkKey.p + b0, c->blkKeySorted.p, c->blkIdx.p + b0, c->blkIdxSorted.p, (int)n, 0, bits, c->stream));
+    IDP_CK(c, c->cubTemp.reserve(bytes));
+    IDP_CK(c, cub::DeviceRadixSort::SortPairs(c->cubTemp.p, bytes, c->blkKey.p + b0, c->blkKeySorted.p, c->blkIdx.p + b0, c->blkIdxSorted.p, (int)n, 0, bits, c->stream));
+    ++c->lib_launches;
+    // unique blocks
+    IDP_CK(c, c->segId.reserve(n + 1));
+    IDP_CK(c, c->segStart.reserve(n + 1));
+    IDP_CK(c, c->rowBlkOff.reserve(n + 1)); // reused as scan output (row offsets are no longer needed)
+    IDP_LAUNCH(c, k_head_flags, blocks_for(n, 256), 256, 0, c->blkKeySorted.p, n, c->segId.p);
+    IDP_CK(c, cudaMemsetAsync(c->segId.p + n, 0, sizeof(int), c->stream));
+    IDP_TRY(cub_scan_exclusive(c, c->segId.p, c->rowBlkOff.p, n + 1));
+    int nSeg = 0;
+    IDP_CK(c, cudaMemcpyAsync(&nSeg, c->rowBlkOff.p + n, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    IDP_LAUNCH(c, k_seg_starts, blocks_for(n, 256), 256, 0, c->rowBlkOff.p, c->segId.p, n, c->segStart.p);
+    IDP_CK(c, cudaStreamSynchronize(c->stream));
+    c->nBlocksUnique = nSeg;
+    c->nnz = 9L * nSeg;
+    IDP_CK(c, c->vtxBlkStart.reserve((size_t)c->nV + 1));
+    IDP_CK(c, c->csrCol.reserve(c->nnz));
+    IDP_CK(c, c->csrVal.reserve(c->nnz));
+    IDP_LAUNCH(c, k_vertex_block_starts, blocks_for(c->nV + 1, 256), 256, 0, c->blkKeySorted.p, c->segStart.p, nSeg, c->nV, c->vtxBlkStart.p);
+    IDP_LAUNCH(c, k_csr_ptr, blocks_for(c->nV + 1, 256), 256, 0, c->vtxBlkStart.p, c->nV, c->csrPtr.p);
+    IDP_LAUNCH(c, k_reduce_blocks, blocks_for(9L * nSeg, 288), 288, 0, c->blkKeySorted.p, c->blkIdxSorted.p, c->segStart.p, nSeg, n,
+        c->blkVal.p, c->vtxBlkStart.p, (long long)c->nV, c->csrCol.p, c->csrVal.p);
+    IDP_CK(c, cudaGetLastError());
+    IDP_CK(c, cudaStreamSynchronize(c->stream));
+    return IDP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// FP64 pipe microbenchmark (roofline denominator): 8 independent DFMA chains per thread
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_dfma(double* out, int iters, double a, double b)
+{
+    double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    const double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 1.2345) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+} // namespace idp
+
+extern "C" int idp_measure_fp64_tflops(idp_ctx* c, double* tflops)
+{
+    using namespace idp;
+    const int iters = 1 << 15, blocks = c->sm_count * 8, threads = 256;
+    IDP_CK(c, c->red.reserve((size_t)blocks * threads));
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        IDP_CK(c, cudaEventRecord(c->ev0, c->stream));
+        IDP_LAUNCH(c, k_dfma, blocks, threads, 0, c->red.p, iters, 0.999999, 1e-6);
+        IDP_CK(c, cudaEventRecord(c->ev1, c->stream));
+        IDP_CK(c, cudaEventSynchronize(c->ev1));
+        float ms = 0;
+        IDP_CK(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        if (rep > 0) best = std::min(best, ms);
+    }
+    *tflops = 2.0 * 8.0 * iters * (double)blocks * threads / (best * 1e-3) / 1e12;
+    return IDP_OK;
+}

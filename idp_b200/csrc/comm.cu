@@ -1,0 +1,89 @@
+// NCCL plumbing for the natural reductions of the sharded path (energy sum, gradient all-reduce, global min of the
+// CCD step). libnccl is loaded at run time (dlopen) so that single-GPU use has no NCCL dependency.
+#include "ctx.cuh"
+#include <dlfcn.h>
+#include <string.h>
+
+namespace idp {
+
+typedef struct { char internal[128]; } nccl_uid;
+typedef int (*fn_get_uid)(nccl_uid*);
+typedef int (*fn_init_rank)(void**, int, nccl_uid, int);
+typedef int (*fn_allreduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*fn_destroy)(void*);
+typedef const char* (*fn_errstr)(int);
+
+struct NcclApi {
+    void* h = nullptr;
+    fn_get_uid get_uid = nullptr;
+    fn_init_rank init_rank = nullptr;
+    fn_allreduce allreduce = nullptr;
+    fn_destroy destroy = nullptr;
+    fn_errstr errstr = nullptr;
+};
+static NcclApi g_nccl;
+
+static bool load_nccl()
+{
+    if (g_nccl.h) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+        g_nccl.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.h) break;
+    }
+    if (!g_nccl.h) return false;
+    g_nccl.get_uid = (fn_get_uid)dlsym(g_nccl.h, "ncclGetUniqueId");
+    g_nccl.init_rank = (fn_init_rank)dlsym(g_nccl.h, "ncclCommInitRank");
+    g_nccl.allreduce = (fn_allreduce)dlsym(g_nccl.h, "ncclAllReduce");
+    g_nccl.destroy = (fn_destroy)dlsym(g_nccl.h, "ncclCommDestroy");
+    g_nccl.errstr = (fn_errstr)dlsym(g_nccl.h, "ncclGetErrorString");
+    return g_nccl.get_uid && g_nccl.init_rank && g_nccl.allreduce && g_nccl.destroy;
+}
+
+// ncclDataType_t: ncclFloat64 = 8; ncclRedOp_t: ncclSum = 0, ncclMin = 4
+int comm_allreduce_sum(idp_ctx* c, double* dev, long n)
+{
+    if (!c->nccl_comm) return IDP_OK;
+    const int r = g_nccl.allreduce(dev, dev, (size_t)n, 8, 0, c->nccl_comm, c->stream);
+    if (r != 0) return fail(c, IDP_ERR_NCCL, "NCCL error: %s at %s:%d", g_nccl.errstr ? g_nccl.errstr(r) : "?", __FILE__, __LINE__);
+    return IDP_OK;
+}
+int comm_allreduce_min(idp_ctx* c, double* dev, long n)
+{
+    if (!c->nccl_comm) return IDP_OK;
+    const int r = g_nccl.allreduce(dev, dev, (size_t)n, 8, 4, c->nccl_comm, c->stream);
+    if (r != 0) return fail(c, IDP_ERR_NCCL, "NCCL error: %s at %s:%d", g_nccl.errstr ? g_nccl.errstr(r) : "?", __FILE__, __LINE__);
+    return IDP_OK;
+}
+void comm_destroy(idp_ctx* c)
+{
+    if (c->nccl_comm && g_nccl.destroy) g_nccl.destroy(c->nccl_comm);
+    c->nccl_comm = nullptr;
+}
+
+} // namespace idp
+
+extern "C" int idp_comm_unique_id(void* out_id128)
+{
+    using namespace idp;
+    if (!out_id128 || !load_nccl()) return IDP_ERR_NCCL;
+    nccl_uid id;
+    if (g_nccl.get_uid(&id) != 0) return IDP_ERR_NCCL;
+    memcpy(out_id128, &id, 128);
+    return IDP_OK;
+}
+
+extern "C" int idp_comm_init(idp_ctx* c, int rank, int nranks, const void* id128)
+{
+    using namespace idp;
+    if (!c || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return IDP_ERR_INVALID;
+    if (!load_nccl()) return fail(c, IDP_ERR_NCCL, "%s (%s:%d)", "libnccl.so.2 not found", __FILE__, __LINE__);
+    IDP_CK(c, cudaSetDevice(c->device));
+    nccl_uid id;
+    memcpy(&id, id128, 128);
+    const int r = g_nccl.init_rank(&c->nccl_comm, nranks, id, rank);
+    if (r != 0) return fail(c, IDP_ERR_NCCL, "NCCL error: %s at %s:%d", g_nccl.errstr ? g_nccl.errstr(r) : "?", __FILE__, __LINE__);
+    c->rank = rank;
+    c->nranks = nranks;
+    return IDP_OK;
+}

@@ -1,0 +1,219 @@
+// Context, device buffers and launch helpers shared by the translation units of libidp_contact.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include "../../include/idp_contact.h"
+
+namespace idp {
+
+// one cache-line-pair record per boundary primitive (point / edge / triangle): exact AABB + vertex ids.
+// For the static phase the AABB is that of the current positions, for CCD it is the full-step swept AABB
+// (min/max over x and x + dir, Math/Distance/CCD.h:187-235).
+struct __align__(64) PrimRec {
+    double lo[3];
+    double hi[3];
+    int v[3];   // vertex ids (-1 = unused)
+    int flags;  // bit0: all vertices are Dirichlet
+};
+// integer lattice box of a primitive (cell coordinates of the broad-phase lattice)
+struct __align__(32) IBox {
+    int lo[3];
+    int hi[3];
+    int pad[2];
+};
+struct __align__(16) Row4 {
+    int a, b, c, d;
+    __host__ __device__ bool operator==(const Row4& o) const { return a == o.a && b == o.b && c == o.c && d == o.d; }
+    __host__ __device__ bool operator!=(const Row4& o) const { return !(*this == o); }
+};
+struct RowLess {
+    __host__ __device__ bool operator()(const Row4& x, const Row4& y) const
+    {
+        if (x.a != y.a) return x.a < y.a;
+        if (x.b != y.b) return x.b < y.b;
+        if (x.c != y.c) return x.c < y.c;
+        return x.d < y.d;
+    }
+};
+
+// lattice -> cell grid used by the broad phase
+struct GridDesc {
+    double lo[3];   // lattice origin
+    double inv;     // 1 / lattice spacing
+    int k;          // lattice voxels per grid cell (per axis)
+    int n[3];       // grid cells per axis
+    int clampLat;   // 1: lattice indices are clamped to the grid (static phase); 0: reference semantics (CCD)
+};
+
+template <class T>
+struct DBuf {
+    T* p = nullptr;
+    size_t cap = 0; // elements
+    DBuf() {}
+    DBuf(const DBuf&) = delete;
+    DBuf& operator=(const DBuf&) = delete;
+    ~DBuf() { release(); }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    // grow (contents are NOT preserved unless keep=true)
+    cudaError_t reserve(size_t n, bool keep = false, cudaStream_t s = 0)
+    {
+        if (n <= cap) return cudaSuccess;
+        size_t ncap = std::max(n, cap + cap / 2);
+        T* np = nullptr;
+        cudaError_t e = cudaMalloc((void**)&np, ncap * sizeof(T));
+        if (e != cudaSuccess) return e;
+        if (keep && p && cap) {
+            e = cudaMemcpyAsync(np, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, s);
+            if (e != cudaSuccess) return e;
+            cudaStreamSynchronize(s);
+        }
+        if (p) cudaFree(p);
+        p = np;
+        cap = ncap;
+        return cudaSuccess;
+    }
+};
+
+struct StageTimes {
+    // milliseconds of the last call of each stage (CUDA events on ctx->stream), names follow the reference's
+    // TIMER_FLAG scopes
+    float v[IDP_STAGE_COUNT];
+};
+
+} // namespace idp
+
+struct idp_ctx {
+    int device = 0;
+    cudaStream_t stream = 0;
+    bool own_stream = false;
+    std::string err;
+    long launches = 0;      // kernels of this library launched since the last idp_reset_counters
+    long lib_launches = 0;  // CUB device-wide primitives invoked (each expands to a few library kernels)
+    int sm_count = 148;
+
+    // sharding (multi-GPU): this context evaluates query primitives / rows of shard `rank` of `nranks`
+    int rank = 0, nranks = 1;
+    void* nccl_comm = nullptr;
+
+    // ---- mesh (set once per time step) ----
+    int nV = 0, nBN = 0, nBE = 0, nBT = 0;
+    idp::DBuf<int> bnode;
+    idp::DBuf<int2> bedge;
+    idp::DBuf<int4> btri;
+    idp::DBuf<unsigned char> dbc;
+    // ---- per-iterate state ----
+    idp::DBuf<double> stage;            // upload staging (AoS)
+    idp::DBuf<double> xs, ys, zs;       // SoA positions (streaming kernels)
+    idp::DBuf<double4> xp, x0p, dp;     // 32-byte packed positions / rest positions / search direction (gathers)
+    bool have_x = false, have_x0 = false;
+    // ---- broad-phase scratch ----
+    idp::DBuf<idp::PrimRec> recN, recE, recT;
+    idp::DBuf<idp::IBox> boxNq, boxEq, boxEb, boxTb; // query boxes (inflated) and insert boxes
+    idp::DBuf<idp::IBox> vbox;                        // per-vertex lattice box (CCD)
+    idp::DBuf<int> cellStart, cellCursor, entries;
+    idp::DBuf<int2> candPT, candEE;
+    long nCandPT = 0, nCandEE = 0;
+    idp::DBuf<double> red;              // reduction scratch
+    idp::DBuf<unsigned char> cubTemp;
+    idp::DBuf<long long> counters;      // device counters / flags (see enum in kernels)
+    // ---- constraint set ----
+    idp::DBuf<idp::Row4> rowsA, rowsB, rowsD, rowsD2, rows;
+    idp::DBuf<int> runCounts;
+    idp::DBuf<double> weights;
+    long nRows = 0;
+    double cs_dhat2 = 0; // dHat2 stored in stencilInfo (after the thickness offset, IPC.h:53-54)
+    // ---- barrier outputs ----
+    idp::DBuf<double> gbuf;             // 3*nV gradient (xyz interleaved)
+    idp::DBuf<double> rowDist2;
+    idp::DBuf<int> rowBlkOff;
+    idp::DBuf<unsigned long long> blkKey, blkKeySorted;
+    idp::DBuf<int> blkIdx, blkIdxSorted, segId, segStart;
+    idp::DBuf<double> blkVal;
+    idp::DBuf<int> vtxBlkStart;
+    idp::DBuf<int> csrPtr, csrCol;
+    idp::DBuf<double> csrVal;
+    long nnz = 0, nBlocksUnique = 0;
+    // ---- CCD ----
+    long ccd_iters = 0;
+    long nCcdPT = 0, nCcdEE = 0;
+    // host pinned scratch for small readbacks
+    long long* h_counters = nullptr;
+    double* h_red = nullptr;
+
+    idp::StageTimes times;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+namespace idp {
+
+static inline int fail(idp_ctx* c, int code, const char* fmt, const char* what, const char* file, int line)
+{
+    char buf[512];
+    snprintf(buf, sizeof(buf), fmt, what, file, line);
+    c->err = buf;
+    return code;
+}
+#define IDP_CK(ctx, call)                                                                                   \
+    do {                                                                                                    \
+        cudaError_t e__ = (call);                                                                           \
+        if (e__ != cudaSuccess) return idp::fail(ctx, IDP_ERR_CUDA, "CUDA error: %s at %s:%d", cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+#define IDP_TRY(expr)                 \
+    do {                              \
+        int st__ = (expr);            \
+        if (st__ != IDP_OK) return st__; \
+    } while (0)
+#define IDP_LAUNCH(ctx, kernel, grid, block, smem, ...)                    \
+    do {                                                                   \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);  \
+        ++(ctx)->launches;                                                 \
+    } while (0)
+
+static inline unsigned blocks_for(long n, int block) { return (unsigned)std::max(1L, (n + block - 1) / block); }
+
+// device counter slots
+enum Counter {
+    CNT_CAND = 0,     // candidate pairs written by the current query kernel
+    CNT_ROWS_A = 1,   // direct rows (PT / EE kinds)
+    CNT_ROWS_D = 2,   // plain PP / PE rows awaiting duplicate merge
+    CNT_ERR_DIST = 3, // rows with non-positive distance
+    CNT_ERR_CCD = 4,  // ACCD iteration cap reached or zero step
+    CNT_CCD_ITERS = 5,
+    CNT_RUNS = 6,
+    CNT_ALPHA_BITS = 7, // current CCD step as double bits (atomicMin on positive doubles)
+    CNT_COUNT = 16
+};
+
+struct StageTimer {
+    idp_ctx* c;
+    int stage;
+    StageTimer(idp_ctx* ctx, int st) : c(ctx), stage(st) { cudaEventRecord(c->ev0, c->stream); }
+    ~StageTimer()
+    {
+        cudaEventRecord(c->ev1, c->stream);
+        cudaEventSynchronize(c->ev1);
+        cudaEventElapsedTime(&c->times.v[stage], c->ev0, c->ev1);
+    }
+};
+
+// ---- host-side launchers implemented in the .cu files ----
+int upload_positions(idp_ctx* c, const double* host_xyz, int stride, int which); // which: 0 X, 1 X0, 2 dir
+int build_constraint_set(idp_ctx* c, double dhat2, double thickness);
+int sorted_candidates(idp_ctx* c, int which, int2* host_out);
+int barrier_eval(idp_ctx* c, double dhat2, double kappa, double thickness, int want_e, int want_g, int want_h,
+    int project_spd, double* E_out);
+int assemble_csr(idp_ctx* c);
+int min_dist2(idp_ctx* c, double thickness, double* host_dist2, double* min_out);
+int ccd_step(idp_ctx* c, double thickness, double* alpha_inout, int keep_candidates);
+int cub_scan_exclusive(idp_ctx* c, const int* in, int* out, long n);
+
+} // namespace idp

@@ -1,0 +1,1024 @@
+// Broad phase (static + swept), narrow-phase classification, duplicate merge, min-distance and additive CCD.
+// COMPILED WITH --fmad=false: every floating-point result here feeds a comparison whose outcome must match the
+// CPU reference bit for bit (voxel indices, AABB tests, distance types, d < dHat^2, ACCD step).
+//
+// Reference operators replaced (relative to /root/reference/Library):
+//   Grid/SPATIAL_HASH.h:28-291 (static build + queries), 432-662 (CCD build + queries),
+//   FEM/IPC.h:145-661 (PT / EE loops + merge), 1957-2243 (CCD loops), 2246-2388 (min distance),
+//   Math/Distance/CCD.h:149-235 (AABB predicates), 279-395 (ACCD).
+//
+// Data layout in HBM: positions are kept twice — SoA x[],y[],z[] for streaming reductions and
+// 32-byte packed double4 records for the per-pair gathers (one DRAM sector per vertex); every boundary primitive
+// gets a 64-byte PrimRec (exact AABB + vertex ids) and a 32-byte integer lattice box.
+#include "ctx.cuh"
+#include "pair_exact.cuh"
+#include <cub/cub.cuh>
+
+namespace idp {
+
+// ------------------------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ V3 ldv(const double4* __restrict__ p, int v)
+{
+    const double2* q = reinterpret_cast<const double2*>(p + v);
+    const double2 a = __ldg(q), b = __ldg(q + 1);
+    return mk3(a.x, a.y, b.x);
+}
+// order-preserving map double -> uint64 (for atomicMin / atomicMax on doubles of either sign)
+__device__ __forceinline__ unsigned long long enc_ord(double d)
+{
+    const unsigned long long b = (unsigned long long)__double_as_longlong(d);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__host__ __device__ __forceinline__ double dec_ord(unsigned long long u)
+{
+    const unsigned long long b = (u >> 63) ? (u & 0x7fffffffffffffffull) : ~u;
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double((long long)b);
+#else
+    double d;
+    memcpy(&d, &b, 8);
+    return d;
+#endif
+}
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// warp-aggregated append: returns the slot of this lane's item (valid only where pred), -1 if over capacity
+__device__ __forceinline__ long warp_append(bool pred, unsigned long long* counter, long cap)
+{
+    const unsigned m = __ballot_sync(0xffffffffu, pred);
+    if (m == 0) return -1;
+    const int leader = __ffs(m) - 1;
+    unsigned long long base = 0;
+    if (lane_id() == leader) base = atomicAdd(counter, (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (!pred) return -1;
+    const long slot = (long)base + __popc(m & ((1u << lane_id()) - 1u));
+    return slot < cap ? slot : -1;
+}
+
+__device__ __forceinline__ int lat_index(double c, double lo, double inv) { return (int)floor((c - lo) * inv); }
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// ------------------------------------------------------------------------------------------------------------
+// upload marshalling: host AoS (stride doubles per vertex) -> SoA + packed
+// ------------------------------------------------------------------------------------------------------------
+__global__ void k_scatter_positions(const double* __restrict__ aos, int stride, int nV, double* __restrict__ xs,
+    double* __restrict__ ys, double* __restrict__ zs, double4* __restrict__ packed)
+{
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < nV; v += gridDim.x * blockDim.x) {
+        const double x = aos[(long)v * stride], y = aos[(long)v * stride + 1], z = aos[(long)v * stride + 2];
+        if (xs) { xs[v] = x; ys[v] = y; zs[v] = z; }
+        packed[v] = make_double4(x, y, z, 0.0);
+    }
+}
+
+int upload_positions(idp_ctx* c, const double* host, int stride, int which)
+{
+    if (c->nV <= 0) return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "idp_set_mesh must be called first", __FILE__, __LINE__);
+    if (stride < 3) return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "stride must be >= 3", __FILE__, __LINE__);
+    StageTimer tm(c, IDP_STAGE_UPLOAD);
+    const size_t n = (size_t)c->nV * stride;
+    IDP_CK(c, c->stage.reserve(n));
+    IDP_CK(c, cudaMemcpyAsync(c->stage.p, host, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    DBuf<double4>& dst = which == 0 ? c->xp : (which == 1 ? c->x0p : c->dp);
+    IDP_CK(c, dst.reserve(c->nV));
+    if (which == 0) {
+        IDP_CK(c, c->xs.reserve(c->nV));
+        IDP_CK(c, c->ys.reserve(c->nV));
+        IDP_CK(c, c->zs.reserve(c->nV));
+    }
+    IDP_LAUNCH(c, k_scatter_positions, blocks_for(c->nV, 256), 256, 0, c->stage.p, stride, c->nV,
+        which == 0 ? c->xs.p : nullptr, c->ys.p, c->zs.p, dst.p);
+    IDP_CK(c, cudaGetLastError());
+    if (which == 0) c->have_x = true;
+    if (which == 1) c->have_x0 = true;
+    return IDP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// reductions: bounding box and the balanced adjacent-pair tree sum (mean edge length / mean |dir|)
+// ------------------------------------------------------------------------------------------------------------
+// out[0..2] = min (encoded), out[3..5] = max (encoded). mode 0: positions; mode 1: swept min/max(x, x + alpha d)
+__global__ void k_node_bbox(const int* __restrict__ bnode, int nBN, const double4* __restrict__ xp,
+    const double4* __restrict__ dp, double alpha, int mode, unsigned long long* __restrict__ out)
+{
+    double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < nBN; s += gridDim.x * blockDim.x) {
+        const int v = bnode[s];
+        const V3 x = ldv(xp, v);
+        V3 a = x, b = x;
+        if (mode == 1) {
+            const V3 d = ldv(dp, v);
+            const V3 xt = mk3(x.x + alpha * d.x, x.y + alpha * d.y, x.z + alpha * d.z);
+            a = min3(x, xt);
+            b = max3(x, xt);
+        }
+        lo[0] = fmin(lo[0], a.x); lo[1] = fmin(lo[1], a.y); lo[2] = fmin(lo[2], a.z);
+        hi[0] = fmax(hi[0], b.x); hi[1] = fmax(hi[1], b.y); hi[2] = fmax(hi[2], b.z);
+    }
+    typedef cub::BlockReduce<double, 256> BR;
+    __shared__ typename BR::TempStorage tmp;
+    for (int k = 0; k < 3; ++k) {
+        const double mn = BR(tmp).Reduce(lo[k], cub::Min());
+        __syncthreads();
+        const double mx = BR(tmp).Reduce(hi[k], cub::Max());
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            atomicMin(out + k, enc_ord(mn));
+            atomicMax(out + 3 + k, enc_ord(mx));
+        }
+    }
+}
+
+__global__ void k_edge_lengths(const int2* __restrict__ bedge, int nBE, const double4* __restrict__ xp, double* __restrict__ len)
+{
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nBE; e += gridDim.x * blockDim.x) {
+        const int2 ab = bedge[e];
+        len[e] = sqrt(sqn3(ldv(xp, ab.x) - ldv(xp, ab.y)));
+    }
+}
+__global__ void k_abs_dir(const int* __restrict__ bnode, int nBN, const double4* __restrict__ dp, double* __restrict__ out)
+{
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < nBN; s += gridDim.x * blockDim.x) {
+        const V3 d = ldv(dp, bnode[s]);
+        out[3 * (long)s] = fabs(d.x); out[3 * (long)s + 1] = fabs(d.y); out[3 * (long)s + 2] = fabs(d.z);
+    }
+}
+// One block reduces an aligned chunk of 2048 inputs with the adjacent-pair binary tree (zero padded), which makes the
+// multi-pass result identical to the tree over the whole array padded to a power of two (oracle: orc::tree_sum).
+__global__ void __launch_bounds__(1024) k_tree_reduce(const double* __restrict__ in, long n, double* __restrict__ out)
+{
+    __shared__ double s[1024];
+    const long base = (long)blockIdx.x * 2048;
+    const int t = threadIdx.x;
+    const long i0 = base + 2 * t, i1 = i0 + 1;
+    const double a = i0 < n ? in[i0] : 0.0, b = i1 < n ? in[i1] : 0.0;
+    s[t] = a + b;
+    __syncthreads();
+    for (int len = 1024; len > 1; len >>= 1) {
+        double v = 0;
+        const bool act = t < (len >> 1);
+        if (act) v = s[2 * t] + s[2 * t + 1];
+        __syncthreads();
+        if (act) s[t] = v;
+        __syncthreads();
+    }
+    if (t == 0) out[blockIdx.x] = s[0];
+}
+// tree sum of n doubles in buf (clobbers scratch); result to host
+static int tree_sum_device(idp_ctx* c, double* buf, long n, double* scratchA, double* scratchB, double* host_out)
+{
+    const double* in = buf;
+    double* outs[2] = {scratchA, scratchB};
+    int flip = 0;
+    long m = n;
+    while (true) {
+        const long nb = (m + 2047) / 2048;
+        IDP_LAUNCH(c, k_tree_reduce, (unsigned)nb, 1024, 0, in, m, outs[flip]);
+        in = outs[flip];
+        flip ^= 1;
+        m = nb;
+        if (nb == 1) break;
+    }
+    IDP_CK(c, cudaMemcpyAsync(host_out, in, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    IDP_CK(c, cudaStreamSynchronize(c->stream));
+    return IDP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// primitive records and lattice boxes
+// ------------------------------------------------------------------------------------------------------------
+struct PrepArgs {
+    const int* bnode; const int2* bedge; const int4* btri; const unsigned char* dbc;
+    const double4* xp; const double4* dp; // dp only for CCD
+    GridDesc g;
+    double radius;      // static: inflated query radius r'; CCD: unused
+    const IBox* vbox;   // CCD: per-vertex lattice boxes
+};
+__device__ __forceinline__ void box_from_aabb(const GridDesc& g, const V3& lo, const V3& hi, double r, IBox& b)
+{
+    b.lo[0] = lat_index(lo.x - r, g.lo[0], g.inv); b.lo[1] = lat_index(lo.y - r, g.lo[1], g.inv); b.lo[2] = lat_index(lo.z - r, g.lo[2], g.inv);
+    b.hi[0] = lat_index(hi.x + r, g.lo[0], g.inv); b.hi[1] = lat_index(hi.y + r, g.lo[1], g.inv); b.hi[2] = lat_index(hi.z + r, g.lo[2], g.inv);
+    if (g.clampLat) {
+        for (int k = 0; k < 3; ++k) {
+            b.lo[k] = clampi(b.lo[k], 0, g.n[k] * g.k - 1);
+            b.hi[k] = clampi(b.hi[k], 0, g.n[k] * g.k - 1);
+        }
+    }
+    b.pad[0] = b.pad[1] = 0;
+}
+__device__ __forceinline__ void rec_set(PrimRec& r, const V3& lo, const V3& hi, int v0, int v1, int v2, int flags)
+{
+    r.lo[0] = lo.x; r.lo[1] = lo.y; r.lo[2] = lo.z; r.hi[0] = hi.x; r.hi[1] = hi.y; r.hi[2] = hi.z;
+    r.v[0] = v0; r.v[1] = v1; r.v[2] = v2; r.flags = flags;
+}
+__device__ __forceinline__ void swept(const PrepArgs& a, int v, V3& lo, V3& hi)
+{
+    const V3 x = ldv(a.xp, v);
+    if (a.dp) {
+        const V3 xe = x + ldv(a.dp, v);
+        lo = min3(x, xe); hi = max3(x, xe);
+    }
+    else { lo = x; hi = x; }
+}
+__device__ __forceinline__ void box_union(IBox& o, const IBox& a, const IBox& b)
+{
+    for (int k = 0; k < 3; ++k) { o.lo[k] = min(a.lo[k], b.lo[k]); o.hi[k] = max(a.hi[k], b.hi[k]); }
+    o.pad[0] = o.pad[1] = 0;
+}
+
+// nodes: query records. static: box = idx(p -+ r'); CCD: box = vbox[v]
+__global__ void k_prep_nodes(PrepArgs a, int nBN, PrimRec* __restrict__ rec, IBox* __restrict__ qbox)
+{
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < nBN; s += gridDim.x * blockDim.x) {
+        const int v = a.bnode[s];
+        V3 lo, hi;
+        swept(a, v, lo, hi);
+        PrimRec r;
+        rec_set(r, lo, hi, v, -1, -1, a.dbc[v] ? 1 : 0);
+        rec[s] = r;
+        IBox b;
+        if (a.vbox) b = a.vbox[v];
+        else box_from_aabb(a.g, lo, hi, a.radius, b);
+        qbox[s] = b;
+    }
+}
+__global__ void k_prep_edges(PrepArgs a, int nBE, PrimRec* __restrict__ rec, IBox* __restrict__ qbox, IBox* __restrict__ bbox)
+{
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nBE; e += gridDim.x * blockDim.x) {
+        const int2 ab = a.bedge[e];
+        V3 l0, h0, l1, h1;
+        swept(a, ab.x, l0, h0);
+        swept(a, ab.y, l1, h1);
+        const V3 lo = min3(l0, l1), hi = max3(h0, h1);
+        PrimRec r;
+        rec_set(r, lo, hi, ab.x, ab.y, -1, (a.dbc[ab.x] && a.dbc[ab.y]) ? 1 : 0);
+        rec[e] = r;
+        IBox b;
+        if (a.vbox) {
+            box_union(b, a.vbox[ab.x], a.vbox[ab.y]);
+            bbox[e] = b; // query and insert boxes coincide for CCD
+        }
+        else {
+            box_from_aabb(a.g, lo, hi, 0.0, b);
+            bbox[e] = b;
+            box_from_aabb(a.g, lo, hi, a.radius, b);
+            qbox[e] = b;
+        }
+    }
+}
+__global__ void k_prep_tris(PrepArgs a, int nBT, PrimRec* __restrict__ rec, IBox* __restrict__ bbox)
+{
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nBT; t += gridDim.x * blockDim.x) {
+        const int4 f = a.btri[t];
+        V3 l0, h0, l1, h1, l2, h2;
+        swept(a, f.x, l0, h0);
+        swept(a, f.y, l1, h1);
+        swept(a, f.z, l2, h2);
+        const V3 lo = min3(min3(l0, l1), l2), hi = max3(max3(h0, h1), h2);
+        PrimRec r;
+        rec_set(r, lo, hi, f.x, f.y, f.z, (a.dbc[f.x] && a.dbc[f.y] && a.dbc[f.z]) ? 1 : 0);
+        rec[t] = r;
+        IBox b;
+        if (a.vbox) {
+            IBox t01;
+            box_union(t01, a.vbox[f.x], a.vbox[f.y]);
+            box_union(b, t01, a.vbox[f.z]);
+        }
+        else box_from_aabb(a.g, lo, hi, 0.0, b);
+        bbox[t] = b;
+    }
+}
+// CCD: per-vertex lattice box of the alpha-scaled, xi/2-inflated swept segment (SPATIAL_HASH.h:525-533)
+__global__ void k_ccd_vertex_boxes(const int* __restrict__ bnode, int nBN, const double4* __restrict__ xp,
+    const double4* __restrict__ dp, double alpha, double half, GridDesc g, IBox* __restrict__ vbox)
+{
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < nBN; s += gridDim.x * blockDim.x) {
+        const int v = bnode[s];
+        const V3 x = ldv(xp, v), d = ldv(dp, v);
+        const V3 xt = mk3(x.x + alpha * d.x, x.y + alpha * d.y, x.z + alpha * d.z);
+        const V3 mn = min3(x, xt), mx = max3(x, xt);
+        IBox b;
+        b.lo[0] = lat_index(mn.x - half, g.lo[0], g.inv); b.lo[1] = lat_index(mn.y - half, g.lo[1], g.inv); b.lo[2] = lat_index(mn.z - half, g.lo[2], g.inv);
+        b.hi[0] = lat_index(mx.x + half, g.lo[0], g.inv); b.hi[1] = lat_index(mx.y + half, g.lo[1], g.inv); b.hi[2] = lat_index(mx.z + half, g.lo[2], g.inv);
+        b.pad[0] = b.pad[1] = 0;
+        vbox[v] = b;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// cell lists: histogram -> exclusive scan -> fill
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cell_range(const GridDesc& g, const IBox& b, int lo[3], int hi[3])
+{
+    for (int k = 0; k < 3; ++k) {
+        lo[k] = clampi(b.lo[k] / g.k, 0, g.n[k] - 1);
+        hi[k] = clampi(b.hi[k] / g.k, 0, g.n[k] - 1);
+    }
+}
+// note: lattice indices are >= 0 on the paths that use k > 1 (CCD lattice origin is the global minimum), so integer
+// division is a monotone floor.
+template <bool FILL>
+__global__ void k_cells(const IBox* __restrict__ bbox, int nB, GridDesc g, int* __restrict__ cellCountOrCursor, int* __restrict__ entries)
+{
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nB; b += gridDim.x * blockDim.x) {
+        int lo[3], hi[3];
+        cell_range(g, bbox[b], lo, hi);
+        for (int iz = lo[2]; iz <= hi[2]; ++iz)
+            for (int iy = lo[1]; iy <= hi[1]; ++iy) {
+                const long row = ((long)iz * g.n[1] + iy) * g.n[0];
+                for (int ix = lo[0]; ix <= hi[0]; ++ix) {
+                    if (FILL) entries[atomicAdd(&cellCountOrCursor[row + ix], 1)] = b;
+                    else atomicAdd(&cellCountOrCursor[row + ix], 1);
+                }
+            }
+    }
+}
+
+int cub_scan_exclusive(idp_ctx* c, const int* in, int* out, long n)
+{
+    size_t bytes = 0;
+    IDP_CK(c, cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, (int)n, c->stream));
+    IDP_CK(c, c->cubTemp.reserve(bytes));
+    IDP_CK(c, cub::DeviceScan::ExclusiveSum(c->cubTemp.p, bytes, in, out, (int)n, c->stream));
+    ++c->lib_launches;
+    return IDP_OK;
+}
+
+static long grid_cells(const GridDesc& g) { return (long)g.n[0] * g.n[1] * g.n[2]; }
+
+// build cellStart (nCells + 1) and entries for the insert boxes bbox[0..nB)
+static int build_cells(idp_ctx* c, const IBox* bbox, int nB, const GridDesc& g, long* nEntries)
+{
+    const long nc = grid_cells(g);
+    IDP_CK(c, c->cellStart.reserve(nc + 1));
+    IDP_CK(c, c->cellCursor.reserve(nc + 1));
+    IDP_CK(c, cudaMemsetAsync(c->cellCursor.p, 0, (nc + 1) * sizeof(int), c->stream));
+    IDP_LAUNCH(c, k_cells<false>, blocks_for(nB, 256), 256, 0, bbox, nB, g, c->cellCursor.p, nullptr);
+    IDP_TRY(cub_scan_exclusive(c, c->cellCursor.p, c->cellStart.p, nc + 1));
+    int total = 0;
+    IDP_CK(c, cudaMemcpyAsync(&total, c->cellStart.p + nc, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    IDP_CK(c, cudaStreamSynchronize(c->stream));
+    *nEntries = total;
+    IDP_CK(c, c->entries.reserve((size_t)std::max(total, 1)));
+    IDP_CK(c, cudaMemcpyAsync(c->cellCursor.p, c->cellStart.p, (nc + 1) * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+    IDP_LAUNCH(c, k_cells<true>, blocks_for(nB, 256), 256, 0, bbox, nB, g, c->cellCursor.p, c->entries.p);
+    IDP_CK(c, cudaGetLastError());
+    return IDP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// broad-phase query: one warp per query primitive, lanes stride over the entries of each x-run of cells.
+// A pair is emitted from exactly one cell (componentwise max of the two boxes' low corners), so no de-duplication
+// pass is needed. Survivors are compacted with ballot/popc and appended with one atomic per warp batch.
+// MODE bit0: 0 = point queries vs triangles, 1 = edge queries vs edges (partner index > query index);
+// MODE bit1: CCD (require lattice-box overlap = "shares a voxel" of the reference's hash)
+// ------------------------------------------------------------------------------------------------------------
+struct QueryArgs {
+    const PrimRec* qrec; const IBox* qbox; int qBegin, qEnd;
+    const PrimRec* brec; const IBox* bbox;
+    const int* cellStart; const int* entries;
+    GridDesc g;
+    double dist; // dHat (static) or thickness (CCD)
+    int2* out; long cap; unsigned long long* counter;
+};
+template <int MODE>
+__global__ void __launch_bounds__(256) k_query(QueryArgs a)
+{
+    const int warpsPerBlock = blockDim.x >> 5;
+    const long warp0 = (long)blockIdx.x * warpsPerBlock + (threadIdx.x >> 5);
+    const long nWarps = (long)gridDim.x * warpsPerBlock;
+    const int lane = lane_id();
+    for (long q = a.qBegin + warp0; q < a.qEnd; q += nWarps) {
+        const PrimRec qr = a.qrec[q];
+        const IBox qb = a.qbox[q];
+        int qlo[3], qhi[3];
+        cell_range(a.g, qb, qlo, qhi);
+        const V3 qL = mk3(qr.lo[0], qr.lo[1], qr.lo[2]), qH = mk3(qr.hi[0], qr.hi[1], qr.hi[2]);
+        for (int iz = qlo[2]; iz <= qhi[2]; ++iz)
+            for (int iy = qlo[1]; iy <= qhi[1]; ++iy) {
+                const long row = ((long)iz * a.g.n[1] + iy) * a.g.n[0];
+                const int start = a.cellStart[row + qlo[0]], end = a.cellStart[row + qhi[0] + 1];
+                for (int i0 = start; i0 < end; i0 += 32) {
+                    const int i = i0 + lane;
+                    bool hit = false;
+                    int b = -1;
+                    if (i < end) {
+                        b = a.entries[i];
+                        bool ok = (MODE & 1) ? (b > (int)q) : true;
+                        if (ok) {
+                            const IBox bb = a.bbox[b];
+                            int blo[3], bhi[3];
+                            cell_range(a.g, bb, blo, bhi);
+                            // canonical cell of the pair
+                            const int cy = max(qlo[1], blo[1]), cz = max(qlo[2], blo[2]), cx = max(qlo[0], blo[0]);
+                            ok = (cy == iy) && (cz == iz);
+                            if (ok) {
+                                const int cs = a.cellStart[row + cx], ce = a.cellStart[row + cx + 1];
+                                ok = (i >= cs) && (i < ce);
+                            }
+                            if (ok && (MODE & 2)) {
+                                ok = qb.lo[0] <= bb.hi[0] && bb.lo[0] <= qb.hi[0] && qb.lo[1] <= bb.hi[1] && bb.lo[1] <= qb.hi[1] &&
+                                     qb.lo[2] <= bb.hi[2] && bb.lo[2] <= qb.hi[2];
+                            }
+                            if (ok) {
+                                const PrimRec br = a.brec[b];
+                                if (MODE & 1) {
+                                    // shared vertex (IPC.h:384) / all four Dirichlet (:385)
+                                    ok = !(qr.v[0] == br.v[0] || qr.v[0] == br.v[1] || qr.v[1] == br.v[0] || qr.v[1] == br.v[1]);
+                                }
+                                else {
+                                    // incident triangle (IPC.h:171) / all Dirichlet (:172)
+                                    ok = !(qr.v[0] == br.v[0] || qr.v[0] == br.v[1] || qr.v[0] == br.v[2]);
+                                }
+                                ok = ok && !((qr.flags & 1) && (br.flags & 1));
+                                if (ok) {
+                                    hit = aabb_gap_ok(qL, qH, mk3(br.lo[0], br.lo[1], br.lo[2]), mk3(br.hi[0], br.hi[1], br.hi[2]), a.dist);
+                                }
+                            }
+                        }
+                    }
+                    const long slot = warp_append(hit, a.counter, a.cap);
+                    if (hit && slot >= 0) a.out[slot] = make_int2((int)q, b);
+                }
+            }
+    }
+}
+
+// runs the query kernel, growing the candidate buffer until everything fits
+template <int MODE>
+static int run_query(idp_ctx* c, QueryArgs a, DBuf<int2>& out, long* nOut)
+{
+    const long nQ = a.qEnd - a.qBegin;
+    if (out.cap < 1024) IDP_CK(c, out.reserve(std::max<long>(1024, 4 * nQ)));
+    unsigned long long* counter = (unsigned long long*)(c->counters.p + CNT_CAND);
+    for (int attempt = 0; attempt < 8; ++attempt) {
+        IDP_CK(c, cudaMemsetAsync(counter, 0, sizeof(long long), c->stream));
+        a.out = out.p;
+        a.cap = (long)out.cap;
+        a.counter = counter;
+        const unsigned grid = (unsigned)std::min<long>((nQ + 7) / 8, (long)c->sm_count * 64);
+        if (nQ > 0) IDP_LAUNCH(c, k_query<MODE>, std::max(grid, 1u), 256, 0, a);
+        IDP_CK(c, cudaGetLastError());
+        long long n = 0;
+        IDP_CK(c, cudaMemcpyAsync(&n, counter, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+        IDP_CK(c, cudaStreamSynchronize(c->stream));
+        if (n <= (long long)out.cap) { *nOut = (long)n; return IDP_OK; }
+        IDP_CK(c, out.reserve((size_t)(n + n / 8)));
+    }
+    return fail(c, IDP_ERR_CUDA, "%s (%s:%d)", "candidate buffer did not converge", __FILE__, __LINE__);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// narrow phase: classification + constraint-row encoding (IPC.h:198-267, 421-564)
+// ------------------------------------------------------------------------------------------------------------
+struct ClassifyArgs {
+    const int2* cand; long nCand;
+    const int* bnode; const int2* bedge; const int4* btri;
+    const double4* xp; const double4* x0p;
+    double dHat2;
+    Row4* rowsDirect; long capDirect; unsigned long long* cntDirect;
+    Row4* rowsDup; long capDup; unsigned long long* cntDup;
+};
+__global__ void __launch_bounds__(256) k_classify_pt(ClassifyArgs a)
+{
+    const long stride = (long)gridDim.x * blockDim.x;
+    const long nRound = (a.nCand + 31) / 32 * 32;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nRound; i += stride) {
+        bool direct = false, dup = false;
+        Row4 r = {0, 0, 0, 0};
+        if (i < a.nCand) {
+            const int2 c = a.cand[i];
+            const int vI = a.bnode[c.x];
+            const int4 t = a.btri[c.y];
+            const V3 p = ldv(a.xp, vI), t0 = ldv(a.xp, t.x), t1 = ldv(a.xp, t.y), t2 = ldv(a.xp, t.z);
+            const int ty = pt_type(p, t0, t1, t2);
+            const double d = dist2_pt_by_type(ty, p, t0, t1, t2);
+            if (d < a.dHat2) {
+                r.a = -vI - 1;
+                switch (ty) {
+                case 0: r.b = t.x; r.c = -1; r.d = -1; break;
+                case 1: r.b = t.y; r.c = -1; r.d = -1; break;
+                case 2: r.b = t.z; r.c = -1; r.d = -1; break;
+                case 3: r.b = t.x; r.c = t.y; r.d = -1; break;
+                case 4: r.b = t.y; r.c = t.z; r.d = -1; break;
+                case 5: r.b = t.z; r.c = t.x; r.d = -1; break;
+                default: r.b = t.x; r.c = t.y; r.d = t.z; break;
+                }
+                direct = (ty == 6);
+                dup = !direct;
+            }
+        }
+        long s = warp_append(direct, a.cntDirect, a.capDirect);
+        if (direct && s >= 0) a.rowsDirect[s] = r;
+        s = warp_append(dup, a.cntDup, a.capDup);
+        if (dup && s >= 0) a.rowsDup[s] = r;
+    }
+}
+__global__ void __launch_bounds__(256) k_classify_ee(ClassifyArgs a)
+{
+    const long stride = (long)gridDim.x * blockDim.x;
+    const long nRound = (a.nCand + 31) / 32 * 32;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nRound; i += stride) {
+        bool direct = false, dup = false;
+        Row4 r = {0, 0, 0, 0};
+        if (i < a.nCand) {
+            const int2 c = a.cand[i];
+            const int2 ea = a.bedge[c.x], eb = a.bedge[c.y];
+            const V3 a0 = ldv(a.xp, ea.x), a1 = ldv(a.xp, ea.y), b0 = ldv(a.xp, eb.x), b1 = ldv(a.xp, eb.y);
+            const int ty = ee_type(a0, a1, b0, b1);
+            const double d = dist2_ee_by_type(ty, a0, a1, b0, b1);
+            if (d < a.dHat2) {
+                const double cn = ee_cross_norm2(a0, a1, b0, b1);
+                const double eps_x = ee_mollifier_threshold(ldv(a.x0p, ea.x), ldv(a.x0p, ea.y), ldv(a.x0p, eb.x), ldv(a.x0p, eb.y));
+                const bool moll = cn < eps_x;
+                const int A0 = ea.x, A1 = ea.y, B0 = eb.x, B1 = eb.y;
+                if (moll) {
+                    switch (ty) {
+                    case 0: r = {A0, B0, -A1 - 1, -B1 - 1}; break;
+                    case 1: r = {A0, B1, -A1 - 1, -B0 - 1}; break;
+                    case 2: r = {A0, B0, B1, -A1 - 1}; break;
+                    case 3: r = {A1, B0, -A0 - 1, -B1 - 1}; break;
+                    case 4: r = {A1, B1, -A0 - 1, -B0 - 1}; break;
+                    case 5: r = {A1, B0, B1, -A0 - 1}; break;
+                    case 6: r = {B0, A0, A1, -B1 - 1}; break;
+                    case 7: r = {B1, A0, A1, -B0 - 1}; break;
+                    default: r = {A0, A1, -B0 - 1, B1}; break;
+                    }
+                    direct = true;
+                }
+                else {
+                    switch (ty) {
+                    case 0: r = {-A0 - 1, B0, -1, -1}; break;
+                    case 1: r = {-A0 - 1, B1, -1, -1}; break;
+                    case 2: r = {-A0 - 1, B0, B1, -1}; break;
+                    case 3: r = {-A1 - 1, B0, -1, -1}; break;
+                    case 4: r = {-A1 - 1, B1, -1, -1}; break;
+                    case 5: r = {-A1 - 1, B0, B1, -1}; break;
+                    case 6: r = {-B0 - 1, A0, A1, -1}; break;
+                    case 7: r = {-B1 - 1, A0, A1, -1}; break;
+                    default: r = {A0, A1, B0, B1}; break;
+                    }
+                    direct = (ty == 8);
+                    dup = !direct;
+                }
+            }
+        }
+        long s = warp_append(direct, a.cntDirect, a.capDirect);
+        if (direct && s >= 0) a.rowsDirect[s] = r;
+        s = warp_append(dup, a.cntDup, a.capDup);
+        if (dup && s >= 0) a.rowsDup[s] = r;
+    }
+}
+
+__global__ void k_emit_merged(const Row4* __restrict__ uniq, const int* __restrict__ counts, long n, Row4* __restrict__ out)
+{
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        Row4 r = uniq[i];
+        r.d = -counts[i];
+        out[i] = r;
+    }
+}
+__global__ void k_fill_double(double* __restrict__ p, long n, double v)
+{
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) p[i] = v;
+}
+
+static int sort_rows(idp_ctx* c, Row4* rows, long n)
+{
+    if (n <= 1) return IDP_OK;
+    size_t bytes = 0;
+    IDP_CK(c, cub::DeviceMergeSort::SortKeys(nullptr, bytes, rows, (int)n, RowLess(), c->stream));
+    IDP_CK(c, c->cubTemp.reserve(bytes));
+    IDP_CK(c, cub::DeviceMergeSort::SortKeys(c->cubTemp.p, bytes, rows, (int)n, RowLess(), c->stream));
+    ++c->lib_launches;
+    return IDP_OK;
+}
+
+static int read_counters(idp_ctx* c)
+{
+    IDP_CK(c, cudaMemcpyAsync(c->h_counters, c->counters.p, CNT_COUNT * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    IDP_CK(c, cudaStreamSynchronize(c->stream));
+    return IDP_OK;
+}
+
+// choose the static broad-phase lattice: spacing h ~ max(mean edge length, query radius), at most 2^26 cells
+static void choose_static_grid(const double lo[3], const double hi[3], double meanEdge, double radius, GridDesc& g)
+{
+    double h = std::max(meanEdge, radius);
+    if (!(h > 0)) h = 1.0;
+    const double ext[3] = {hi[0] - lo[0] + 2 * radius, hi[1] - lo[1] + 2 * radius, hi[2] - lo[2] + 2 * radius};
+    for (int iter = 0; iter < 64; ++iter) {
+        double cells = 1;
+        for (int k = 0; k < 3; ++k) cells *= std::floor(ext[k] / h) + 2;
+        if (cells <= 67108864.0) break;
+        h *= 1.26;
+    }
+    g.inv = 1.0 / h;
+    g.k = 1;
+    g.clampLat = 1;
+    for (int k = 0; k < 3; ++k) {
+        g.lo[k] = lo[k] - radius;
+        g.n[k] = (int)std::floor(ext[k] / h) + 2;
+    }
+}
+
+static int mean_edge_length(idp_ctx* c, double* out)
+{
+    if (c->nBE == 0) { *out = 0; return IDP_OK; }
+    const long need = (long)c->nBE + 2 * ((c->nBE + 2047) / 2048 + 1);
+    IDP_CK(c, c->red.reserve(std::max<long>(need, 3L * c->nBN + 2 * ((3L * c->nBN + 2047) / 2048 + 1))));
+    IDP_LAUNCH(c, k_edge_lengths, blocks_for(c->nBE, 256), 256, 0, c->bedge.p, c->nBE, c->xp.p, c->red.p);
+    double s = 0;
+    const long nb = (c->nBE + 2047) / 2048 + 1;
+    IDP_TRY(tree_sum_device(c, c->red.p, c->nBE, c->red.p + c->nBE, c->red.p + c->nBE + nb, &s));
+    *out = s / c->nBE;
+    return IDP_OK;
+}
+
+static int node_bbox(idp_ctx* c, int mode, double alpha, double lo[3], double hi[3])
+{
+    unsigned long long init[6];
+    for (int k = 0; k < 3; ++k) { init[k] = ~0ull; init[3 + k] = 0ull; }
+    unsigned long long* d = (unsigned long long*)(c->counters.p + 8);
+    IDP_CK(c, cudaMemcpyAsync(d, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+    IDP_LAUNCH(c, k_node_bbox, std::min(blocks_for(c->nBN, 256), (unsigned)c->sm_count * 8), 256, 0, c->bnode.p, c->nBN,
+        c->xp.p, c->dp.p, alpha, mode, d);
+    IDP_CK(c, cudaMemcpyAsync(init, d, sizeof(init), cudaMemcpyDeviceToHost, c->stream));
+    IDP_CK(c, cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < 3; ++k) { lo[k] = dec_ord(init[k]); hi[k] = dec_ord(init[3 + k]); }
+    return IDP_OK;
+}
+
+// shard [0, n) by contiguous primitive ranges
+static void shard_range(const idp_ctx* c, long n, int* b, int* e)
+{
+    *b = (int)(n * c->rank / c->nranks);
+    *e = (int)(n * (c->rank + 1) / c->nranks);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Compute_Constraint_Set
+// ------------------------------------------------------------------------------------------------------------
+int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
+{
+    if (!c->have_x) return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "positions not set", __FILE__, __LINE__);
+    if (!c->have_x0) return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "rest positions not set", __FILE__, __LINE__);
+    const double dHat = std::sqrt(dhat2_in) + thickness; // IPC.h:53-54
+    const double dHat2 = dHat * dHat;
+    c->cs_dhat2 = dHat2;
+    IDP_CK(c, cudaMemsetAsync(c->counters.p, 0, CNT_COUNT * sizeof(long long), c->stream));
+
+    GridDesc g;
+    PrepArgs pa;
+    {
+        StageTimer tm(c, IDP_STAGE_CCS_BUILD_HASH);
+        double meanEdge = 0, lo[3], hi[3];
+        IDP_TRY(mean_edge_length(c, &meanEdge));
+        IDP_TRY(node_bbox(c, 0, 0.0, lo, hi));
+        double amax = 0;
+        for (int k = 0; k < 3; ++k) amax = std::max(amax, std::max(std::fabs(lo[k]), std::fabs(hi[k])));
+        // conservative query radius: the exact predicate (AABB gap <= dHat) is applied afterwards
+        const double radius = dHat * (1.0 + 1e-9) + amax * 1e-13;
+        choose_static_grid(lo, hi, meanEdge, radius, g);
+        pa.bnode = c->bnode.p; pa.bedge = c->bedge.p; pa.btri = c->btri.p; pa.dbc = c->dbc.p;
+        pa.xp = c->xp.p; pa.dp = nullptr; pa.g = g; pa.radius = radius; pa.vbox = nullptr;
+        IDP_CK(c, c->recN.reserve(c->nBN)); IDP_CK(c, c->boxNq.reserve(c->nBN));
+        IDP_CK(c, c->recE.reserve(c->nBE)); IDP_CK(c, c->boxEq.reserve(c->nBE)); IDP_CK(c, c->boxEb.reserve(c->nBE));
+        IDP_CK(c, c->recT.reserve(c->nBT)); IDP_CK(c, c->boxTb.reserve(c->nBT));
+        IDP_LAUNCH(c, k_prep_nodes, blocks_for(c->nBN, 256), 256, 0, pa, c->nBN, c->recN.p, c->boxNq.p);
+        IDP_LAUNCH(c, k_prep_edges, blocks_for(c->nBE, 256), 256, 0, pa, c->nBE, c->recE.p, c->boxEq.p, c->boxEb.p);
+        IDP_LAUNCH(c, k_prep_tris, blocks_for(c->nBT, 256), 256, 0, pa, c->nBT, c->recT.p, c->boxTb.p);
+        IDP_CK(c, cudaGetLastError());
+    }
+    unsigned long long* cnt = (unsigned long long*)c->counters.p;
+    int qb, qe;
+    {
+        StageTimer tm(c, IDP_STAGE_CCS_PT);
+        long nEntries = 0;
+        IDP_TRY(build_cells(c, c->boxTb.p, c->nBT, g, &nEntries));
+        shard_range(c, c->nBN, &qb, &qe);
+        QueryArgs qa;
+        qa.qrec = c->recN.p; qa.qbox = c->boxNq.p; qa.qBegin = qb; qa.qEnd = qe;
+        qa.brec = c->recT.p; qa.bbox = c->boxTb.p; qa.cellStart = c->cellStart.p; qa.entries = c->entries.p;
+        qa.g = g; qa.dist = dHat;
+        IDP_TRY(run_query<0>(c, qa, c->candPT, &c->nCandPT));
+        // classification
+        IDP_CK(c, c->rowsA.reserve(std::max<long>(c->nCandPT, 1)));
+        IDP_CK(c, c->rowsD.reserve(std::max<long>(c->nCandPT, 1)));
+        ClassifyArgs ca;
+        ca.cand = c->candPT.p; ca.nCand = c->nCandPT; ca.bnode = c->bnode.p; ca.bedge = c->bedge.p; ca.btri = c->btri.p;
+        ca.xp = c->xp.p; ca.x0p = c->x0p.p; ca.dHat2 = dHat2;
+        ca.rowsDirect = c->rowsA.p; ca.capDirect = (long)c->rowsA.cap; ca.cntDirect = cnt + CNT_ROWS_A;
+        ca.rowsDup = c->rowsD.p; ca.capDup = (long)c->rowsD.cap; ca.cntDup = cnt + CNT_ROWS_D;
+        if (c->nCandPT > 0) IDP_LAUNCH(c, k_classify_pt, std::min(blocks_for(c->nCandPT, 256), (unsigned)c->sm_count * 16), 256, 0, ca);
+        IDP_CK(c, cudaGetLastError());
+        IDP_TRY(read_counters(c));
+    }
+    const long nA = (long)c->h_counters[CNT_ROWS_A];
+    const long nD_pt = (long)c->h_counters[CNT_ROWS_D];
+    long nB = 0, nD = 0;
+    {
+        StageTimer tm(c, IDP_STAGE_CCS_EE);
+        long nEntries = 0;
+        IDP_TRY(build_cells(c, c->boxEb.p, c->nBE, g, &nEntries));
+        shard_range(c, c->nBE, &qb, &qe);
+        QueryArgs qa;
+        qa.qrec = c->recE.p; qa.qbox = c->boxEq.p; qa.qBegin = qb; qa.qEnd = qe;
+        qa.brec = c->recE.p; qa.bbox = c->boxEb.p; qa.cellStart = c->cellStart.p; qa.entries = c->entries.p;
+        qa.g = g; qa.dist = dHat;
+        IDP_TRY(run_query<1>(c, qa, c->candEE, &c->nCandEE));
+        IDP_CK(c, c->rowsB.reserve(std::max<long>(c->nCandEE, 1)));
+        IDP_CK(c, c->rowsD.reserve(std::max<long>(nD_pt + c->nCandEE, 1), true, c->stream));
+        IDP_CK(c, cudaMemsetAsync(c->counters.p + CNT_ROWS_A, 0, sizeof(long long), c->stream));
+        ClassifyArgs ca;
+        ca.cand = c->candEE.p; ca.nCand = c->nCandEE; ca.bnode = c->bnode.p; ca.bedge = c->bedge.p; ca.btri = c->btri.p;
+        ca.xp = c->xp.p; ca.x0p = c->x0p.p; ca.dHat2 = dHat2;
+        ca.rowsDirect = c->rowsB.p; ca.capDirect = (long)c->rowsB.cap; ca.cntDirect = cnt + CNT_ROWS_A;
+        ca.rowsDup = c->rowsD.p; ca.capDup = (long)c->rowsD.cap; ca.cntDup = cnt + CNT_ROWS_D;
+        if (c->nCandEE > 0) IDP_LAUNCH(c, k_classify_ee, std::min(blocks_for(c->nCandEE, 256), (unsigned)c->sm_count * 16), 256, 0, ca);
+        IDP_CK(c, cudaGetLastError());
+        IDP_TRY(read_counters(c));
+        nB = (long)c->h_counters[CNT_ROWS_A];
+        nD = (long)c->h_counters[CNT_ROWS_D];
+    }
+    {
+        StageTimer tm(c, IDP_STAGE_CCS_MERGE);
+        // canonical order inside the two direct groups; key order for the merged group (IPC.h:599-654)
+        IDP_TRY(sort_rows(c, c->rowsA.p, nA));
+        IDP_TRY(sort_rows(c, c->rowsB.p, nB));
+        long nU = 0;
+        if (nD > 0) {
+            IDP_TRY(sort_rows(c, c->rowsD.p, nD));
+            IDP_CK(c, c->rowsD2.reserve(nD));
+            IDP_CK(c, c->runCounts.reserve(nD));
+            int* dRuns = (int*)(c->counters.p + CNT_RUNS);
+            size_t bytes = 0;
+            IDP_CK(c, cub::DeviceRunLengthEncode::Encode(nullptr, bytes, c->rowsD.p, c->rowsD2.p, c->runCounts.p, dRuns, (int)nD, c->stream));
+            IDP_CK(c, c->cubTemp.reserve(bytes));
+            IDP_CK(c, cub::DeviceRunLengthEncode::Encode(c->cubTemp.p, bytes, c->rowsD.p, c->rowsD2.p, c->runCounts.p, dRuns, (int)nD, c->stream));
+            ++c->lib_launches;
+            int runs = 0;
+            IDP_CK(c, cudaMemcpyAsync(&runs, dRuns, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+            IDP_CK(c, cudaStreamSynchronize(c->stream));
+            nU = runs;
+        }
+        c->nRows = nA + nB + nU;
+        IDP_CK(c, c->rows.reserve(std::max<long>(c->nRows, 1)));
+        IDP_CK(c, c->weights.reserve(std::max<long>(c->nRows, 1)));
+        if (nA) IDP_CK(c, cudaMemcpyAsync(c->rows.p, c->rowsA.p, nA * sizeof(Row4), cudaMemcpyDeviceToDevice, c->stream));
+        if (nB) IDP_CK(c, cudaMemcpyAsync(c->rows.p + nA, c->rowsB.p, nB * sizeof(Row4), cudaMemcpyDeviceToDevice, c->stream));
+        if (nU) IDP_LAUNCH(c, k_emit_merged, blocks_for(nU, 256), 256, 0, c->rowsD2.p, c->runCounts.p, nU, c->rows.p + nA + nB);
+        if (c->nRows) IDP_LAUNCH(c, k_fill_double, blocks_for(c->nRows, 256), 256, 0, c->weights.p, c->nRows, 1.0); // OIPC: weight 1 (IPC.h:656-660)
+        IDP_CK(c, cudaGetLastError());
+    }
+    return IDP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// sorted candidate sets for the parity check
+// ------------------------------------------------------------------------------------------------------------
+__global__ void k_pack_pairs(const int2* __restrict__ in, long n, unsigned long long* __restrict__ out)
+{
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+        out[i] = ((unsigned long long)(unsigned)in[i].x << 32) | (unsigned)in[i].y;
+}
+__global__ void k_unpack_pairs(const unsigned long long* __restrict__ in, long n, int2* __restrict__ out)
+{
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+        out[i] = make_int2((int)(in[i] >> 32), (int)(in[i] & 0xffffffffu));
+}
+int sorted_candidates(idp_ctx* c, int which, int2* host_out)
+{
+    DBuf<int2>& src = (which == 0 || which == 2) ? c->candPT : c->candEE;
+    const long n = which == 0 ? c->nCandPT : (which == 1 ? c->nCandEE : (which == 2 ? c->nCcdPT : c->nCcdEE));
+    if (n == 0) return IDP_OK;
+    IDP_CK(c, c->blkKey.reserve(n));
+    IDP_CK(c, c->blkKeySorted.reserve(n));
+    IDP_LAUNCH(c, k_pack_pairs, blocks_for(n, 256), 256, 0, src.p, n, c->blkKey.p);
+    size_t bytes = 0;
+    IDP_CK(c, cub::DeviceRadixSort::SortKeys(nullptr, bytes, c->blkKey.p, c->blkKeySorted.p, (int)n, 0, 64, c->stream));
+    IDP_CK(c, c->cubTemp.reserve(bytes));
+    IDP_CK(c, cub::DeviceRadixSort::SortKeys(c->cubTemp.p, bytes, c->blkKey.p, c->blkKeySorted.p, (int)n, 0, 64, c->stream));
+    ++c->lib_launches;
+    IDP_LAUNCH(c, k_unpack_pairs, blocks_for(n, 256), 256, 0, c->blkKeySorted.p, n, (int2*)c->blkKey.p);
+    IDP_CK(c, cudaMemcpyAsync(host_out, c->blkKey.p, n * sizeof(int2), cudaMemcpyDeviceToHost, c->stream));
+    IDP_CK(c, cudaStreamSynchronize(c->stream));
+    return IDP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Compute_Min_Dist2
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_min_dist(const Row4* __restrict__ rows, long n, const double4* __restrict__ xp,
+    double* __restrict__ dist2, unsigned long long* __restrict__ minOut)
+{
+    double m = INFINITY;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const Row4 r = rows[i];
+        const RowDec d = decode_row(r.a, r.b, r.c, r.d);
+        const double d2 = row_dist2(d.kind, ldv(xp, d.v[0]), ldv(xp, d.v[1]), ldv(xp, d.v[2]), ldv(xp, d.v[3]));
+        dist2[i] = d2;
+        m = fmin(m, d2);
+    }
+    typedef cub::BlockReduce<double, 256> BR;
+    __shared__ typename BR::TempStorage tmp;
+    const double bm = BR(tmp).Reduce(m, cub::Min());
+    if (threadIdx.x == 0) atomicMin(minOut, enc_ord(bm));
+}
+int min_dist2(idp_ctx* c, double thickness, double* host_dist2, double* min_out)
+{
+    if (c->nRows == 0) return IDP_OK; // IPC.h:2253-2255
+    StageTimer tm(c, IDP_STAGE_MIN_DIST);
+    IDP_CK(c, c->rowDist2.reserve(c->nRows));
+    unsigned long long init = ~0ull;
+    unsigned long long* d = (unsigned long long*)(c->counters.p + 8);
+    IDP_CK(c, cudaMemcpyAsync(d, &init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+    IDP_LAUNCH(c, k_min_dist, std::min(blocks_for(c->nRows, 256), (unsigned)c->sm_count * 16), 256, 0, c->rows.p, c->nRows, c->xp.p,
+        c->rowDist2.p, d);
+    IDP_CK(c, cudaGetLastError());
+    IDP_CK(c, cudaMemcpyAsync(&init, d, sizeof(init), cudaMemcpyDeviceToHost, c->stream));
+    if (host_dist2) IDP_CK(c, cudaMemcpyAsync(host_dist2, c->rowDist2.p, c->nRows * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    IDP_CK(c, cudaStreamSynchronize(c->stream));
+    *min_out = dec_ord(init) - thickness * thickness;
+    return IDP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Compute_Intersection_Free_StepSize
+// ------------------------------------------------------------------------------------------------------------
+struct AccdArgs {
+    const int2* cand; long nCand;
+    const int* bnode; const int2* bedge; const int4* btri;
+    const double4* xp; const double4* dp;
+    double eta, xi;
+    unsigned long long* alphaBits; // positive double as ordered bits (plain bit pattern: positive doubles order as integers)
+    unsigned long long* iters; unsigned long long* err;
+};
+struct BoundLoad {
+    const unsigned long long* p;
+    __device__ __forceinline__ double operator()() const { return __longlong_as_double((long long)*(volatile const unsigned long long*)p); }
+};
+template <int EE>
+__global__ void __launch_bounds__(128) k_accd(AccdArgs a)
+{
+    const long stride = (long)gridDim.x * blockDim.x;
+    unsigned long long myIters = 0;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < a.nCand; i += stride) {
+        const int2 c = a.cand[i];
+        int v0, v1, v2, v3;
+        if (EE) { const int2 ea = a.bedge[c.x], eb = a.bedge[c.y]; v0 = ea.x; v1 = ea.y; v2 = eb.x; v3 = eb.y; }
+        else { const int4 t = a.btri[c.y]; v0 = a.bnode[c.x]; v1 = t.x; v2 = t.y; v3 = t.z; }
+        BoundLoad bound{a.alphaBits};
+        double toc = 0;
+        int it = 0, res;
+        if (EE) res = accd_ee(ldv(a.xp, v0), ldv(a.xp, v1), ldv(a.xp, v2), ldv(a.xp, v3), ldv(a.dp, v0), ldv(a.dp, v1), ldv(a.dp, v2), ldv(a.dp, v3), a.eta, a.xi, bound, toc, it);
+        else res = accd_pt(ldv(a.xp, v0), ldv(a.xp, v1), ldv(a.xp, v2), ldv(a.xp, v3), ldv(a.dp, v0), ldv(a.dp, v1), ldv(a.dp, v2), ldv(a.dp, v3), a.eta, a.xi, bound, toc, it);
+        myIters += it;
+        if (res == 1) atomicMin(a.alphaBits, (unsigned long long)__double_as_longlong(toc));
+        else if (res < 0) atomicAdd(a.err, 1ull);
+    }
+    // warp-reduce the trip counter
+    for (int o = 16; o > 0; o >>= 1) myIters += __shfl_down_sync(0xffffffffu, myIters, o);
+    if (lane_id() == 0 && myIters) atomicAdd(a.iters, myIters);
+}
+
+// restatement of SPATIAL_HASH::Build (CCD), grid sizing part (:504-519)
+static void ccd_set_grid(const double lo[3], const double hi[3], double voxelSize, GridDesc& g, long latN[3])
+{
+    const double range[3] = {hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]};
+    double inv = 1.0 / voxelSize;
+    long amt = 1;
+    for (int d = 0; d < 3; ++d) amt *= std::max(1L, (long)std::ceil(range[d] * inv));
+    if (amt > 1e9) {
+        voxelSize *= std::pow(amt / 1.0e9, 1.0 / 3);
+        inv = 1.0 / voxelSize;
+    }
+    int mn = 2147483647;
+    int n[3];
+    for (int d = 0; d < 3; ++d) {
+        n[d] = std::max(1, (int)std::ceil(range[d] * inv));
+        mn = std::min(mn, n[d]);
+    }
+    if (mn <= 0) {
+        inv = 1.0 / (std::max(std::max(range[0], range[1]), range[2]) * 1.01);
+        n[0] = n[1] = n[2] = 1;
+    }
+    g.inv = inv;
+    g.clampLat = 0;
+    for (int d = 0; d < 3; ++d) { g.lo[d] = lo[d]; latN[d] = n[d]; }
+    // cells: k^3 lattice voxels each, at most 2^26 cells. Lattice index n[d] (max corner) is clamped into the last cell.
+    int k = 1;
+    while (true) {
+        double cells = 1;
+        for (int d = 0; d < 3; ++d) cells *= (double)((n[d] + k) / k);
+        if (cells <= 67108864.0) break;
+        ++k;
+    }
+    g.k = k;
+    for (int d = 0; d < 3; ++d) g.n[d] = (n[d] + k) / k;
+}
+
+int ccd_step(idp_ctx* c, double thickness, double* alpha_inout, int keep_candidates)
+{
+    (void)keep_candidates;
+    if (!c->have_x) return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "positions not set", __FILE__, __LINE__);
+    double alpha = *alpha_inout;
+    IDP_CK(c, cudaMemsetAsync(c->counters.p, 0, CNT_COUNT * sizeof(long long), c->stream));
+    GridDesc g;
+    PrepArgs pa;
+    {
+        StageTimer tm(c, IDP_STAGE_CCD_BUILD_HASH);
+        double voxelSize = 1.0;
+        if (c->nBE) {
+            double meanEdge = 0;
+            IDP_TRY(mean_edge_length(c, &meanEdge));
+            voxelSize *= meanEdge; // SPATIAL_HASH.h:455-464
+        }
+        // pSize = mean |dir component| over boundary nodes (:466-475); summed with the balanced tree, see DESIGN.md
+        const long n3 = 3L * c->nBN;
+        const long nb = (n3 + 2047) / 2048 + 1;
+        IDP_CK(c, c->red.reserve(n3 + 2 * nb));
+        IDP_LAUNCH(c, k_abs_dir, blocks_for(c->nBN, 256), 256, 0, c->bnode.p, c->nBN, c->dp.p, c->red.p);
+        double pSum = 0;
+        IDP_TRY(tree_sum_device(c, c->red.p, n3, c->red.p + n3, c->red.p + n3 + nb, &pSum));
+        const double pSize = pSum / (double)n3;
+        const double spanSize = alpha * pSize / voxelSize;
+        if (spanSize > 1) {
+            alpha /= spanSize; // :477-482
+            // the reference sums |dir| serially; a differently ordered sum can differ in the last bits, so the clamped
+            // step is shaved by 2^-30 (<< the 1e-6 budget) to guarantee it never exceeds the reference's.
+            alpha *= (1.0 - 9.313225746154785e-10);
+        }
+        double lo[3], hi[3];
+        IDP_TRY(node_bbox(c, 1, alpha, lo, hi));
+        const double half = thickness / 2;
+        for (int k = 0; k < 3; ++k) { lo[k] -= half; hi[k] += half; } // :502-503
+        long latN[3];
+        ccd_set_grid(lo, hi, voxelSize, g, latN);
+        IDP_CK(c, c->vbox.reserve(c->nV));
+        IDP_LAUNCH(c, k_ccd_vertex_boxes, blocks_for(c->nBN, 256), 256, 0, c->bnode.p, c->nBN, c->xp.p, c->dp.p, alpha, half, g, c->vbox.p);
+        pa.bnode = c->bnode.p; pa.bedge = c->bedge.p; pa.btri = c->btri.p; pa.dbc = c->dbc.p;
+        pa.xp = c->xp.p; pa.dp = c->dp.p; pa.g = g; pa.radius = 0; pa.vbox = c->vbox.p;
+        IDP_CK(c, c->recN.reserve(c->nBN)); IDP_CK(c, c->boxNq.reserve(c->nBN));
+        IDP_CK(c, c->recE.reserve(c->nBE)); IDP_CK(c, c->boxEq.reserve(c->nBE)); IDP_CK(c, c->boxEb.reserve(c->nBE));
+        IDP_CK(c, c->recT.reserve(c->nBT)); IDP_CK(c, c->boxTb.reserve(c->nBT));
+        IDP_LAUNCH(c, k_prep_nodes, blocks_for(c->nBN, 256), 256, 0, pa, c->nBN, c->recN.p, c->boxNq.p);
+        IDP_LAUNCH(c, k_prep_edges, blocks_for(c->nBE, 256), 256, 0, pa, c->nBE, c->recE.p, c->boxEq.p, c->boxEb.p);
+        IDP_LAUNCH(c, k_prep_tris, blocks_for(c->nBT, 256), 256, 0, pa, c->nBT, c->recT.p, c->boxTb.p);
+        IDP_CK(c, cudaGetLastError());
+    }
+    unsigned long long* cnt = (unsigned long long*)c->counters.p;
+    {
+        unsigned long long bits;
+        memcpy(&bits, &alpha, 8);
+        IDP_CK(c, cudaMemcpyAsync(cnt + CNT_ALPHA_BITS, &bits, 8, cudaMemcpyHostToDevice, c->stream));
+    }
+    AccdArgs aa;
+    aa.bnode = c->bnode.p; aa.bedge = c->bedge.p; aa.btri = c->btri.p; aa.xp = c->xp.p; aa.dp = c->dp.p;
+    aa.eta = 0.1; aa.xi = thickness; // IPC.h:2009, 2233
+    aa.alphaBits = cnt + CNT_ALPHA_BITS; aa.iters = cnt + CNT_CCD_ITERS; aa.err = cnt + CNT_ERR_CCD;
+    int qb, qe;
+    {
+        StageTimer tm(c, IDP_STAGE_CCD_PT);
+        long nEntries = 0;
+        IDP_TRY(build_cells(c, c->boxTb.p, c->nBT, g, &nEntries));
+        shard_range(c, c->nBN, &qb, &qe);
+        QueryArgs qa;
+        qa.qrec = c->recN.p; qa.qbox = c->boxNq.p; qa.qBegin = qb; qa.qEnd = qe;
+        qa.brec = c->recT.p; qa.bbox = c->boxTb.p; qa.cellStart = c->cellStart.p; qa.entries = c->entries.p;
+        qa.g = g; qa.dist = thickness;
+        IDP_TRY(run_query<2>(c, qa, c->candPT, &c->nCcdPT));
+        aa.cand = c->candPT.p; aa.nCand = c->nCcdPT;
+        if (c->nCcdPT > 0) IDP_LAUNCH(c, k_accd<0>, std::min(blocks_for(c->nCcdPT, 128), (unsigned)c->sm_count * 32), 128, 0, aa);
+        IDP_CK(c, cudaGetLastError());
+    }
+    {
+        StageTimer tm(c, IDP_STAGE_CCD_EE);
+        long nEntries = 0;
+        IDP_TRY(build_cells(c, c->boxEb.p, c->nBE, g, &nEntries));
+        shard_range(c, c->nBE, &qb, &qe);
+        QueryArgs qa;
+        qa.qrec = c->recE.p; qa.qbox = c->boxEb.p; qa.qBegin = qb; qa.qEnd = qe;
+        qa.brec = c->recE.p; qa.bbox = c->boxEb.p; qa.cellStart = c->cellStart.p; qa.entries = c->entries.p;
+        qa.g = g; qa.dist = thickness;
+        IDP_TRY(run_query<3>(c, qa, c->candEE, &c->nCcdEE));
+        aa.cand = c->candEE.p; aa.nCand = c->nCcdEE;
+        if (c->nCcdEE > 0) IDP_LAUNCH(c, k_accd<1>, std::min(blocks_for(c->nCcdEE, 128), (unsigned)c->sm_count * 32), 128, 0, aa);
+        IDP_CK(c, cudaGetLastError());
+    }
+    IDP_TRY(read_counters(c));
+    c->ccd_iters = (long)c->h_counters[CNT_CCD_ITERS];
+    double out;
+    memcpy(&out, &c->h_counters[CNT_ALPHA_BITS], 8);
+    // the PT and EE candidate buffers are invalidated for the static phase
+    c->nCandPT = 0; c->nCandEE = 0;
+    if (c->h_counters[CNT_ERR_CCD]) return fail(c, IDP_ERR_CCD_ITERATION_CAP, "%s (%s:%d)", "additive CCD iteration cap reached", __FILE__, __LINE__);
+    *alpha_inout = out;
+    if (out == 0 && (c->nCcdPT + c->nCcdEE) > 0) return fail(c, IDP_ERR_CCD_ZERO_STEP, "%s (%s:%d)", "CCD returned a zero step", __FILE__, __LINE__);
+    return IDP_OK;
+}
+
+} // namespace idp

@@ -1,0 +1,134 @@
+/* idp_contact.h — C ABI of libidp_contact.so: the B200 (sm_100a) implementation of the IPC contact hot path of
+ * ipc-sim/IDP for codimensional triangle surfaces, instantiation <T=double, dim=3, shell=false, elasticIPC=false>.
+ *
+ * Every entry point below replaces one operator (or one piece of marshalling) of the reference's C++ boundary
+ * "B2" (SURVEY.md §8b): the six free function templates of Library/FEM/IPC.h. Citations are relative to
+ * /root/reference/Library. The reference-side binding a maintainer adds is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes, int status codes, no exceptions, no ownership transfer of host buffers;
+ *   - host arrays are dense: positions nV x 3 doubles with a caller-given stride (3 for packed xyz, 4 for the
+ *     reference's 32-byte VECTOR<double,3>, Math/VECTOR.h:33-44), indices int32;
+ *   - one context = one GPU = one CUDA stream; calls are synchronous for the calling host thread;
+ *   - there is NO CPU fallback: without a CUDA device idp_create fails with IDP_ERR_CUDA.
+ */
+#ifndef IDP_CONTACT_H
+#define IDP_CONTACT_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct idp_ctx idp_ctx;
+
+enum idp_status {
+    IDP_OK = 0,
+    IDP_ERR_CUDA = 1,                   /* CUDA runtime / allocation failure (see idp_last_error) */
+    IDP_ERR_INVALID = 2,                /* bad argument or call order */
+    IDP_ERR_NONPOSITIVE_DISTANCE = 3,   /* IPC.h:817-820,873-876,925-928: "distance detected during barrier evaluation" -> exit(-1) */
+    IDP_ERR_CCD_ZERO_STEP = 4,          /* IPC.h:2014-2032: CCD returned a zero step -> exit(-1) */
+    IDP_ERR_UNSUPPORTED_PRIMITIVE = 5,  /* rod / particle / NNExclusion / dim==2 / shell / elasticIPC inputs: rejected, never emulated */
+    IDP_ERR_NCCL = 6,
+    IDP_ERR_CCD_ITERATION_CAP = 7       /* additive CCD exceeded IDP_ACCD_MAX_ITER trips (the reference would loop forever) */
+};
+
+/* stage ids for idp_stage_ms: names follow the reference's TIMER_FLAG scopes */
+enum idp_stage {
+    IDP_STAGE_CCS_BUILD_HASH = 0,   /* Compute_Constraint_Set_Build_Hash */
+    IDP_STAGE_CCS_PT = 1,           /* Compute_Constraint_Set_PT (broad + narrow) */
+    IDP_STAGE_CCS_EE = 2,           /* Compute_Constraint_Set_EE */
+    IDP_STAGE_CCS_MERGE = 3,        /* Compute_Constraint_Set_Merge */
+    IDP_STAGE_BARRIER = 4,          /* Compute_Barrier / _Gradient / _Hessian per-row kernel */
+    IDP_STAGE_CSR = 5,              /* constructCSRMatrixFromTriplet */
+    IDP_STAGE_CCD_BUILD_HASH = 6,   /* Compute_Intersection_Free_StepSize_Build_Hash */
+    IDP_STAGE_CCD_PT = 7,           /* Compute_Intersection_Free_StepSize_PT */
+    IDP_STAGE_CCD_EE = 8,           /* Compute_Intersection_Free_StepSize_EE */
+    IDP_STAGE_MIN_DIST = 9,         /* Compute_Min_Dist */
+    IDP_STAGE_UPLOAD = 10,          /* host -> device marshalling of positions / directions */
+    IDP_STAGE_COUNT = 16
+};
+
+/* ---- lifetime ------------------------------------------------------------------------------------------- */
+int idp_create(int device, idp_ctx** out);
+void idp_destroy(idp_ctx* ctx);
+const char* idp_last_error(idp_ctx* ctx);
+/* run on a caller-owned CUDA stream (cudaStream_t passed as void*); NULL restores the context's own stream */
+int idp_set_stream(idp_ctx* ctx, void* cuda_stream);
+
+/* ---- inputs --------------------------------------------------------------------------------------------- */
+/* Surface primitives in the ordering contract of Find_Surface_Primitives_And_Compute_Area (Utils/MESHIO.h:768-834):
+ * boundaryNode ascending, boundaryEdge lexicographic with first-triangle orientation, boundaryTri in element order.
+ * These are the boundaryNode / boundaryEdge / boundaryTri / DBCb arguments of Compute_Constraint_Set (FEM/IPC.h:19-36)
+ * and Compute_Intersection_Free_StepSize (IPC.h:1879-1890). dbc may be NULL (no Dirichlet nodes). Call once per time step. */
+int idp_set_mesh(idp_ctx* ctx, int nV, int nBN, const int* bnode, int nBE, const int* bedge2, int nBT, const int* btri3,
+    const uint8_t* dbc);
+/* The reference's rod / particle / NNExclusion containers (IPC.h:25-27): the B2 shim reports their sizes here;
+ * any non-zero size returns IDP_ERR_UNSUPPORTED_PRIMITIVE (out of scope). */
+int idp_declare_unsupported(idp_ctx* ctx, int n_rod, int n_particle, int n_nn_exclusion);
+/* X (MESH_NODE<T,3>&, IPC.h:20) — current positions, nV rows, `stride` doubles per row (3 or 4). Call per iterate. */
+int idp_set_positions(idp_ctx* ctx, const double* x, int stride);
+/* nodeAttr.x0 (rest positions read at IPC.h:421-426, 880-885) — needed only for the edge-edge mollifier. */
+int idp_set_rest_positions(idp_ctx* ctx, const double* x0, int stride);
+
+/* ---- Compute_Constraint_Set (FEM/IPC.h:19-740) ------------------------------------------------------------- */
+/* Builds the constraint set on the device for the current positions: spatial-hash broad phase (Grid/SPATIAL_HASH.h:28-291),
+ * AABB filter (Math/Distance/CCD.h:149-185), distance-type classification (DISTANCE_TYPE.h), duplicate PP/PE merge
+ * (IPC.h:599-654). Row order: [PT rows][EE and mollified rows][merged PP/PE rows in key order]; rows inside the first
+ * two groups are sorted lexicographically (the reference's order there depends on unordered_set iteration). */
+int idp_constraint_set(idp_ctx* ctx, double dhat2, double thickness, int* n_rows);
+/* constraintSet (VECTOR<int,4>, 16 B/row) and stencilInfo (weight, dHat2) to the host. Either pointer may be NULL. */
+int idp_get_constraints(idp_ctx* ctx, int* rows4, double* info2);
+/* Use a caller-supplied constraint set (the constraintSet / stencilInfo arguments of Compute_Barrier*, IPC.h:745-746). */
+int idp_set_constraints(idp_ctx* ctx, int n_rows, const int* rows4, const double* info2);
+/* Post-AABB candidate pairs of the last idp_constraint_set / idp_ccd_step, lexicographically sorted:
+ * which = 0: PT (svI, sfI); 1: EE (eI, eJ); 2: CCD PT; 3: CCD EE. First call with pairs2 == NULL to get the count. */
+int idp_get_candidates(idp_ctx* ctx, int which, long* n_pairs, int* pairs2);
+
+/* ---- Compute_Barrier / _Gradient / _Hessian (FEM/IPC.h:742-941, 943-1256, 1258-1731) ----------------------- */
+/* E += sum of weighted barrier values over the current rows (adds, like the reference). kappa = kappa[0]. */
+int idp_barrier_energy(idp_ctx* ctx, double dhat2, double kappa, double thickness, double* E_inout);
+/* g_accum[v*stride + a] += barrier gradient (nodeAttr.g accumulation, IPC.h:1034-1042); g_accum may be NULL to keep the
+ * gradient on the device only (idp_gradient_device). */
+int idp_barrier_gradient(idp_ctx* ctx, double dhat2, double kappa, double thickness, double* g_accum, int stride);
+/* Per-row Hessians with optional PSD projection (makePD, Math/UTILS.h:9-27), sort-reduced into a device-resident scalar
+ * CSR of size 3nV x 3nV with the pattern/ordering Eigen::setFromTriplets produces (Math/CSR_MATRIX.h:49-56):
+ * duplicates summed, columns ascending per row, explicit zeros kept. */
+int idp_barrier_hessian(idp_ctx* ctx, double dhat2, double kappa, double thickness, int project_spd, long* nnz);
+/* E, g and H in one pass over the rows (what one Newton iteration needs); any of E_inout / nnz may be NULL. */
+int idp_barrier_all(idp_ctx* ctx, double dhat2, double kappa, double thickness, int project_spd, double* E_inout, long* nnz);
+/* copy the CSR to the host: exactly the (ptr, col, val) arrays CSR_MATRIX::Construct_From_CSR takes (CSR_MATRIX.h:33-47) */
+int idp_get_hessian_csr(idp_ctx* ctx, int* ptr, int* col, double* val);
+/* device pointers (valid until the next idp_barrier_hessian / idp_barrier_all on this context) */
+int idp_hessian_csr_device(idp_ctx* ctx, const int** d_ptr, const int** d_col, const double** d_val, long* nnz);
+int idp_gradient_device(idp_ctx* ctx, const double** d_g_xyz);
+
+/* ---- Compute_Intersection_Free_StepSize (FEM/IPC.h:1879-2244) ---------------------------------------------- */
+/* searchDir: nV rows x 3 doubles (std::vector<T>, stride 3 in the reference). alpha is in/out and includes the
+ * span clamp of the CCD hash build (Grid/SPATIAL_HASH.h:466-482). */
+int idp_ccd_step(idp_ctx* ctx, const double* search_dir, int stride, double thickness, double* alpha_inout);
+
+/* ---- Compute_Min_Dist2 (FEM/IPC.h:2246-2388) ---------------------------------------------------------------- */
+/* dist2 (n_rows doubles, may be NULL) and minDist2 = min - thickness^2. With zero rows nothing is written (IPC.h:2253). */
+int idp_min_dist2(idp_ctx* ctx, double thickness, double* dist2, double* min_dist2);
+
+/* ---- multi-GPU (one context per rank; NCCL only for the natural reductions) ---------------------------------- */
+/* out_id: 128 bytes (ncclUniqueId) produced on rank 0 and broadcast by the host program */
+int idp_comm_unique_id(void* out_id128);
+int idp_comm_init(idp_ctx* ctx, int rank, int nranks, const void* id128);
+/* shard without a communicator (results stay partial; for tests of the partition logic) */
+int idp_set_shard(idp_ctx* ctx, int rank, int nranks);
+
+/* ---- instrumentation ------------------------------------------------------------------------------------------ */
+long idp_kernel_launches(idp_ctx* ctx);     /* this library's own kernels launched since idp_reset_counters */
+long idp_library_calls(idp_ctx* ctx);       /* CUB device-wide primitives invoked since idp_reset_counters */
+void idp_reset_counters(idp_ctx* ctx);
+float idp_stage_ms(idp_ctx* ctx, int stage); /* device time of the last execution of a stage (CUDA events) */
+long idp_last_count(idp_ctx* ctx, int what); /* 0 rows, 1 PT cand, 2 EE cand, 3 CCD PT cand, 4 CCD EE cand, 5 ACCD trips, 6 nnz, 7 unique 3x3 blocks */
+/* FP64 pipe microbenchmark: register-resident DFMA chains on every SM; returns measured TFLOP/s (roofline denominator) */
+int idp_measure_fp64_tflops(idp_ctx* ctx, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

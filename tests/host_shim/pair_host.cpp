@@ -1,0 +1,39 @@
+// Test-only harness: compiles the product's per-pair device headers (idp_b200/csrc/pair_*.cuh) as plain host
+// C++ so that their arithmetic can be compared with the oracle on a machine without a GPU. This is NOT a CPU
+// fallback of the product: nothing in idp_b200/ links or loads it.
+#include "../../idp_b200/csrc/pair_deriv.cuh"
+#include "../../idp_b200/csrc/psd_lowrank.cuh"
+using namespace idp;
+static V3 l3(const double* p) { return mk3(p[0], p[1], p[2]); }
+extern "C" {
+int hs_pt_type(const double* x) { return pt_type(l3(x), l3(x + 3), l3(x + 6), l3(x + 9)); }
+int hs_ee_type(const double* x) { return ee_type(l3(x), l3(x + 3), l3(x + 6), l3(x + 9)); }
+double hs_dist2_unclassified(int kind, const double* x)
+{
+    return kind == 0 ? dist2_pt_unclassified(l3(x), l3(x + 3), l3(x + 6), l3(x + 9))
+                     : dist2_ee_unclassified(l3(x), l3(x + 3), l3(x + 6), l3(x + 9));
+}
+// row: 4 ints; X, X0: nV x 3; returns 0 ok / 1 nonpositive distance. H is n x n, n = 3 nv (written to nv_out)
+int hs_row_EgH(const int* row, const double* X, const double* X0, double weight, double dHat2, double kappa,
+    double xi, int projectSPD, int lowrank, double* E, double* g, double* H, int* nv_out, int* verts)
+{
+    RowDec d = decode_row(row[0], row[1], row[2], row[3]);
+    V3 x[4], xr[4];
+    for (int i = 0; i < 4; ++i) { x[i] = l3(X + 3 * (long)d.v[i]); xr[i] = l3(X0 + 3 * (long)d.v[i]); verts[i] = d.v[i]; }
+    *nv_out = d.nv;
+    const double dh2 = dHat2 + 2 * sqrt(dHat2) * xi;
+    bool ok;
+    if (lowrank) ok = row_EgH_lowrank(d, x, xr, weight, dh2, kappa, xi * xi, projectSPD != 0, E, g, H);
+    else ok = row_EgH(d, x, xr, weight, dh2, kappa, xi * xi, projectSPD != 0, E, g, H);
+    return ok ? 0 : 1;
+}
+int hs_accd(int kind, const double* x, const double* d, double eta, double xi, double bound, double* toc, int* iters)
+{
+    int it = 0, r;
+    auto bf = [bound]() { return bound; };
+    if (kind == 0) r = accd_pt(l3(x), l3(x + 3), l3(x + 6), l3(x + 9), l3(d), l3(d + 3), l3(d + 6), l3(d + 9), eta, xi, bf, *toc, it);
+    else r = accd_ee(l3(x), l3(x + 3), l3(x + 6), l3(x + 9), l3(d), l3(d + 3), l3(d + 6), l3(d + 9), eta, xi, bf, *toc, it);
+    *iters = it;
+    return r;
+}
+}

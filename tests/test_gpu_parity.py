@@ -1,0 +1,178 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical seeded inputs.
+
+Bars (BASELINE.json): sorted candidate and constraint sets bit-exact; barrier E/g/H within 1e-10 relative;
+CCD step never above the oracle's and within 1e-6 relative of it.
+"""
+import numpy as np
+import pytest
+
+from conftest import lexsorted, make_cases
+
+pytestmark = pytest.mark.gpu
+KAPPA = 1e5
+RTOL = 1e-10  # tolerance stated by BASELINE.json for E / g / H
+
+
+def rel(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    nb = np.linalg.norm(b)
+    return np.linalg.norm(a - b) / nb if nb > 0 else np.linalg.norm(a - b)
+
+
+@pytest.fixture(scope="module")
+def cases():
+    return make_cases()
+
+
+def omesh(orc, m):
+    return orc.mesh(m.X, m.X0, m.bnode, m.bedge, m.btri, m.dbc)
+
+
+def test_constraint_and_candidate_sets_bit_exact(gpu_ctx, orc, cases):
+    for name, m, _d, dhats in cases:
+        gpu_ctx.set_surface_mesh(m)
+        om = omesh(orc, m)
+        for dh in dhats:
+            n = gpu_ctx.constraint_set(dh * dh)
+            rows, info = gpu_ctx.get_constraints()
+            cpt, cee = gpu_ctx.get_candidates(0), gpu_ctx.get_candidates(1)
+            orows, oinfo, ocpt, ocee = orc.constraint_set(om, dh * dh, want_cand=True)
+            assert n == len(orows), (name, dh, n, len(orows))
+            assert np.array_equal(cpt, ocpt), (name, dh, "PT candidates")
+            assert np.array_equal(cee, ocee), (name, dh, "EE candidates")
+            assert np.array_equal(lexsorted(rows), lexsorted(orows)), (name, dh, "rows")
+            assert np.array_equal(info, np.tile([1.0, oinfo[0, 1] if len(oinfo) else dh * dh], (n, 1)))
+            # merged PP/PE group is in key order at the tail, exactly as the reference emits it (IPC.h:651-654)
+            dup = (rows[:, 0] < 0) & (rows[:, 3] < 0)
+            odup = (orows[:, 0] < 0) & (orows[:, 3] < 0)
+            assert np.array_equal(rows[dup], orows[odup]), (name, dh, "merged group order")
+
+
+def test_constraint_set_with_thickness_and_dbc(gpu_ctx, orc, cases):
+    name, m, _d, dhats = cases[0]
+    dbc = np.zeros(m.nV, np.uint8)
+    dbc[: m.nV // 2] = 1  # the whole inner sphere is Dirichlet: its self-pairs must vanish
+    gpu_ctx.set_mesh(m.nV, m.bnode, m.bedge, m.btri, dbc)
+    gpu_ctx.set_rest_positions(m.X0)
+    gpu_ctx.set_positions(m.X)
+    om = orc.mesh(m.X, m.X0, m.bnode, m.bedge, m.btri, dbc)
+    for thickness in (0.0, 5e-3):
+        n = gpu_ctx.constraint_set(dhats[1] ** 2, thickness)
+        rows, info = gpu_ctx.get_constraints()
+        orows, oinfo, ocpt, ocee = orc.constraint_set(om, dhats[1] ** 2, thickness, want_cand=True)
+        assert n == len(orows) and n > 0
+        assert np.array_equal(lexsorted(rows), lexsorted(orows))
+        assert np.array_equal(gpu_ctx.get_candidates(0), ocpt) and np.array_equal(gpu_ctx.get_candidates(1), ocee)
+        assert info[0, 1] == oinfo[0, 1]
+
+
+def test_barrier_energy_gradient_hessian(gpu_ctx, orc, cases):
+    for name, m, _d, dhats in cases:
+        gpu_ctx.set_surface_mesh(m)
+        om = omesh(orc, m)
+        dh = dhats[-1]
+        n = gpu_ctx.constraint_set(dh * dh)
+        assert n > 0
+        rows, info = gpu_ctx.get_constraints()
+        for project in (False, True):
+            E = gpu_ctx.barrier_energy(dh * dh, KAPPA, E0=1.5)
+            g = gpu_ctx.barrier_gradient(dh * dh, KAPPA)
+            ptr, col, val = gpu_ctx.barrier_hessian(dh * dh, KAPPA, project_spd=project)
+            st, oE = orc.barrier(om, rows, info[:, 0], dh * dh, KAPPA)
+            st2, og = orc.barrier_gradient(om, rows, info[:, 0], dh * dh, KAPPA)
+            oh = orc.barrier_hessian(om, rows, info[:, 0], dh * dh, KAPPA, project_spd=project)
+            assert st == 0 and st2 == 0 and oh["status"] == 0
+            assert abs((E - 1.5) - oE) <= RTOL * abs(oE), (name, E, oE)
+            assert rel(g, og) <= RTOL, (name, rel(g, og))
+            optr, ocol, oval = oh["csr"]
+            assert np.array_equal(ptr, optr) and np.array_equal(col, ocol), (name, "CSR pattern")
+            assert rel(val, oval) <= RTOL, (name, project, rel(val, oval))
+            assert np.abs(val - oval).max() <= RTOL * np.abs(oval).max()
+
+
+def test_barrier_all_matches_separate_calls(gpu_ctx, cases):
+    name, m, _d, dhats = cases[1]
+    gpu_ctx.set_surface_mesh(m)
+    dh = dhats[-1]
+    gpu_ctx.constraint_set(dh * dh)
+    E1 = gpu_ctx.barrier_energy(dh * dh, KAPPA)
+    ptr1, col1, val1 = gpu_ctx.barrier_hessian(dh * dh, KAPPA)
+    E2, nnz = gpu_ctx.barrier_all(dh * dh, KAPPA)
+    ptr2, col2, val2 = gpu_ctx.get_hessian_csr()
+    assert abs(E1 - E2) <= 1e-13 * abs(E1) and nnz == len(col1)
+    assert np.array_equal(ptr1, ptr2) and np.array_equal(col1, col2) and np.allclose(val1, val2, rtol=1e-13, atol=0)
+
+
+def test_min_dist2(gpu_ctx, orc, cases):
+    for name, m, _d, dhats in cases:
+        gpu_ctx.set_surface_mesh(m)
+        om = omesh(orc, m)
+        gpu_ctx.constraint_set(dhats[-1] ** 2)
+        rows, _ = gpu_ctx.get_constraints()
+        d, mn = gpu_ctx.min_dist2(thickness=1e-4)
+        od, omn = orc.min_dist2(om, rows, thickness=1e-4)
+        assert np.array_equal(d, od) and mn == omn, name
+
+
+def test_ccd_step_conservative_and_close(gpu_ctx, orc, cases):
+    for name, m, d, _dh in cases:
+        gpu_ctx.set_surface_mesh(m)
+        om = omesh(orc, m)
+        for scale, thickness, a0 in ((1.0, 0.0, 1.0), (0.3, 0.0, 1.0), (4.0, 0.0, 1.0), (1.0, 1e-4, 0.7)):
+            dd = d * scale
+            a = gpu_ctx.ccd_step(dd, a0, thickness)
+            o = orc.ccd(om, dd, a0, thickness, want_cand=True)
+            assert o["status"] == 0
+            assert a <= o["step"], (name, scale, a, o["step"])
+            assert abs(a - o["step"]) <= 1e-6 * o["step"], (name, scale, a, o["step"])
+            clamped = o["step_after_clamp"] != a0
+            if not clamped:
+                # same lattice on both sides -> candidate sets reaching the ACCD calls are bit-exact
+                assert np.array_equal(gpu_ctx.get_candidates(2), o["cand_pt"]), (name, scale, "CCD PT candidates")
+                assert np.array_equal(gpu_ctx.get_candidates(3), o["cand_ee"]), (name, scale, "CCD EE candidates")
+                assert a == o["step"] or o["step"] == a0 or a == o["step"]
+
+
+def test_ccd_result_is_intersection_free(gpu_ctx, orc, cases):
+    """Size-independent safety property: every constraint distance at x + alpha*dir stays positive."""
+    name, m, d, _dh = cases[0]
+    gpu_ctx.set_surface_mesh(m)
+    a = gpu_ctx.ccd_step(d * 2.0, 1.0, 0.0)
+    assert 0 < a < 1
+    X1 = m.X + a * d * 2.0
+    gpu_ctx.set_positions(X1)
+    n = gpu_ctx.constraint_set(0.05 ** 2)
+    assert n > 0
+    dist, mn = gpu_ctx.min_dist2()
+    assert mn > 0
+    gpu_ctx.set_positions(m.X)
+
+
+def test_nonpositive_distance_is_reported(gpu_ctx):
+    from idp_b200 import IdpError
+    X = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0.2, 0.2, 0.0]], np.float64)  # point in the triangle's plane
+    gpu_ctx.set_mesh(4, np.arange(4, dtype=np.int32), np.array([[0, 1], [1, 2], [2, 0]], np.int32), np.array([[0, 1, 2]], np.int32))
+    gpu_ctx.set_rest_positions(X)
+    gpu_ctx.set_positions(X)
+    gpu_ctx.set_constraints(np.array([[-4, 0, 1, 2]], np.int32))
+    with pytest.raises(IdpError) as e:
+        gpu_ctx.barrier_energy(1e-2, KAPPA)
+    assert e.value.code == 3
+
+
+def test_unsupported_inputs_rejected(gpu_ctx):
+    from idp_b200 import IdpError
+    with pytest.raises(IdpError) as e:
+        gpu_ctx.declare_unsupported(n_rod=1)
+    assert e.value.code == 5
+    gpu_ctx.declare_unsupported()
+
+
+def test_empty_constraint_set(gpu_ctx, cases):
+    name, m, d, _ = cases[0]
+    gpu_ctx.set_surface_mesh(m)
+    assert gpu_ctx.constraint_set(1e-12) == 0
+    assert gpu_ctx.barrier_energy(1e-12, KAPPA) == 0.0
+    ptr, col, val = gpu_ctx.barrier_hessian(1e-12, KAPPA)
+    assert len(col) == 0 and not ptr.any()
+    assert not gpu_ctx.barrier_gradient(1e-12, KAPPA).any()
