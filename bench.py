@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py — contact hot path throughput on B200 (BASELINE.json metric: barrier+CCD contact pairs/s).
+
+A "step" is one synthetic Newton iteration of the hot path over one batch of synthetic input:
+    1x Compute_Constraint_Set, 1x barrier E+g+H (+PSD, +CSR), 1x CCD step filter, 1x Compute_Min_Dist2
+(SURVEY.md §3.1 / §8d). Pairs per step = constraint rows + CCD candidates that reach an ACCD call.
+
+Workload (config.workload): BASELINE.json configs[3], "synthetic tangled multi-sheet surface, 4M triangles"
+(8 wavy sheets of 501x501 vertices, h=4e-3, A=1.5e-3, dHat=2e-3) — the configuration the
+8-GPU scaling target is quoted on; it fits one GPU, so it is also the N=1 workload. With N>1 the same mesh is sharded by
+primitive range across the ranks (strong scaling).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference ...                      # the reference's CPU algorithm (oracle port) on host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "barrier+CCD contact pairs/s"
+UNIT = "pairs/s"
+KAPPA = 1e5  # driver default, Python/Drivers/FEMDiscreteShellBase.py:45
+
+WORKLOADS = {
+    # name: (n_sheets, nx, ny, h, A, dHat)
+    "sheets8x500": dict(n_sheets=8, nx=500, ny=500, h=4e-3, A=1.5e-3, dhat=2e-3, extent=(1.0, 1.0)),
+    "sheets8x160": dict(n_sheets=8, nx=160, ny=160, h=4e-3, A=1.5e-3, dhat=2e-3, extent=(0.32, 0.32)),
+    "sheets8x100": dict(n_sheets=8, nx=100, ny=100, h=4e-3, A=1.5e-3, dhat=2e-3, extent=(0.2, 0.2)),
+}
+CPU_SAMPLE = "sheets8x100"  # crop of the same sheets (same waves, same spacing, same dHat): 160,000 triangles
+
+# algorithmic bytes / flops per constraint row
+ROW_BYTES = {"pt_ee": 1384.0, "moll": 1384.0 + 96.0, "pe": 832.0, "pp": 424.0}
+ROW_FLOPS = {"pt_ee": 21700.0, "moll": 24200.0, "pe": 9300.0, "pp": 2700.0}
+
+
+def build_workload(name):
+    from idp_b200 import meshgen
+    w = WORKLOADS[name]
+    mesh, direction = meshgen.sheet_stack(n_sheets=w["n_sheets"], nx=w["nx"], ny=w["ny"], h=w["h"], A=w["A"],
+                                          extent=w["extent"])
+    return mesh, direction, w["dhat"]
+
+
+def row_kind_counts(rows):
+    a, b, c, d = rows[:, 0], rows[:, 1], rows[:, 2], rows[:, 3]
+    ee = (a >= 0)
+    moll = ee & ~((c >= 0) & (d >= 0))
+    pt = (a < 0) & (d >= 0)
+    pe = (a < 0) & (d < 0) & (c >= 0)
+    pp = (a < 0) & (d < 0) & (c < 0)
+    return {"pt_ee": int((ee & ~moll).sum() + pt.sum()), "moll": int(moll.sum()), "pe": int(pe.sum()), "pp": int(pp.sum())}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+# ----------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's algorithm (oracle port, reference parallel structure) on the host cores
+# ----------------------------------------------------------------------------------------------------------
+def cpu_step(orc, om, direction, dhat2):
+    rows, info, _, _ = orc.constraint_set(om, dhat2)
+    st, E = orc.barrier(om, rows, info[:, 0], dhat2, KAPPA)
+    st, g = orc.barrier_gradient(om, rows, info[:, 0], dhat2, KAPPA)
+    h = orc.barrier_hessian(om, rows, info[:, 0], dhat2, KAPPA, project_spd=True, csr=True)
+    c = orc.ccd(om, direction, 1.0, want_cand=True)
+    orc.min_dist2(om, rows)
+    return len(rows) + len(c["cand_pt"]) + len(c["cand_ee"])
+
+
+def cpu_baseline(steps=1, warmup=0):
+    from oracle.binding import Oracle
+    orc = Oracle("fast")  # -O3 -mfma -mavx2: the reference's own flags (CMakeLists.txt:20)
+    mesh, direction, dhat = build_workload(CPU_SAMPLE)
+    om = orc.mesh(mesh.X, mesh.X0, mesh.bnode, mesh.bedge, mesh.btri, mesh.dbc)
+    for _ in range(warmup):
+        cpu_step(orc, om, direction, dhat * dhat)
+    t0 = time.perf_counter()
+    pairs = 0
+    for _ in range(steps):
+        pairs += cpu_step(orc, om, direction, dhat * dhat)
+    dt = time.perf_counter() - t0
+    cores = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
+    return {"value": pairs / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%s: crop of the bench sheets (%d triangles, same waves/spacing/dHat), %d step(s), %.1f s, %d pairs/step"
+                      % (CPU_SAMPLE, mesh.nF, steps, dt, pairs // max(steps, 1)),
+            "ms_per_step": 1e3 * dt / max(steps, 1), "pairs_per_step": pairs // max(steps, 1), "triangles": mesh.nF}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    cb = cpu_baseline(steps=args.steps, warmup=min(args.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "sheets8x500 (BASELINE configs[3]); each step = bounded sample %s" % CPU_SAMPLE},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="sheets8x500", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from idp_b200 import ContactContext
+
+    args.warmup = max(args.warmup, 3)
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    mesh, direction, dhat = build_workload(args.workload)
+    dhat2 = dhat * dhat
+    ctx = ContactContext(local_rank)  # raises without the CUDA library / a device: no CPU fallback
+    stream = torch.cuda.Stream()
+    ctx.set_stream(stream.cuda_stream)
+    if world > 1:
+        uid = [ctx.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(rank, world, uid[0])
+
+    # pinned host inputs
+    Xh = torch.from_numpy(mesh.X).pin_memory()
+    X0h = torch.from_numpy(mesh.X0).pin_memory()
+    Dh = torch.from_numpy(direction).pin_memory()
+    ctx.set_mesh(mesh.nV, mesh.bnode, mesh.bedge, mesh.btri, mesh.dbc)
+    ctx.set_rest_positions(X0h.numpy())
+    ctx.set_positions(Xh.numpy())
+    ctx.set_search_direction(Dh.numpy())
+
+    def step_resident():
+        n = ctx.constraint_set(dhat2)
+        E, nnz = ctx.barrier_all(dhat2, KAPPA)
+        a = ctx.ccd_step_resident(1.0)
+        _, mn = ctx.min_dist2(want_all=False)
+        return n + ctx.count(3) + ctx.count(4), (n, nnz, E, a, mn)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            pairs = 0
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                p, info = fn()
+                pairs += p
+            e1.record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device="cuda")
+        pr = torch.tensor([float(pairs)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t[0].item(), t[1].item(), pr.item(), info
+
+    for _ in range(args.warmup):
+        pairs_w, info_w = step_resident()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ctx.reset_counters()
+    ms, wall_ms, pairs, info = timed(step_resident, args.steps)
+    launches, lib_calls = ctx.launches()
+    clocks = sampler.stop()
+    stages = ctx.stage_ms()
+    n_rows, nnz, E, alpha, mind = info
+    # pairs are global: every rank sees the full row count; CCD candidates are per shard -> sum over ranks
+    ccd_local = torch.tensor([float(ctx.count(3) + ctx.count(4))], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ccd_local, op=dist.ReduceOp.SUM)
+    pairs_per_step = n_rows + int(ccd_local.item())
+    value = pairs_per_step * args.steps / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (k_barrier: E+g+H+PSD per row) ----
+    rows, _info = ctx.get_constraints()
+    kinds = row_kind_counts(rows)
+    share = (rows.shape[0] * (rank + 1) // world - rows.shape[0] * rank // world) / max(rows.shape[0], 1)
+    alg_bytes = sum(ROW_BYTES[k] * v for k, v in kinds.items()) * share
+    alg_flops = sum(ROW_FLOPS[k] * v for k, v in kinds.items()) * share
+    kb_ms = stages["k_barrier"]
+    peaks, peak_src = measured_peaks()
+    fp64_peak = ctx.fp64_tflops()
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("k_barrier_dram_bytes_per_launch")
+    roofline = {"kernel": "k_barrier<E,g,H> (per-row barrier E+g+H+PSD, FP64)", "bound": "hbm",
+                "achieved": alg_bytes / (kb_ms * 1e-3) / 1e9 if kb_ms > 0 else None, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": (alg_bytes / (kb_ms * 1e-3) / 1e9) / peaks["hbm_gbs"] if kb_ms > 0 else None, "traffic": traffic,
+                "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)", "launch_ms": kb_ms,
+                "algorithmic_bytes_per_launch": alg_bytes,
+                "fp64": {"achieved_tflops": alg_flops / (kb_ms * 1e-3) / 1e12 if kb_ms > 0 else None,
+                         "peak_tflops": fp64_peak, "peak_source": "measured live (idp_measure_fp64_tflops, DFMA chains)",
+                         "frac": (alg_flops / (kb_ms * 1e-3) / 1e12) / fp64_peak if kb_ms > 0 else None,
+                         "credited_flops_per_launch": alg_flops},
+                "row_kinds": kinds, "share_of_step": kb_ms * args.steps / ms if ms > 0 else None}
+
+    # ---- end to end through the C ABI with host buffers ----
+    e2e = None
+    if not args.no_e2e:
+        g_host = torch.zeros((mesh.nV, 3), dtype=torch.float64).pin_memory()
+        bufs = {}
+
+        def step_e2e():
+            ctx.set_positions(Xh.numpy())
+            n = ctx.constraint_set(dhat2)
+            if "rows" not in bufs or bufs["rows"].shape[0] < n:
+                bufs["rows"] = torch.empty((int(n * 1.1) + 16, 4), dtype=torch.int32).pin_memory()
+                bufs["info"] = torch.empty((int(n * 1.1) + 16, 2), dtype=torch.float64).pin_memory()
+            ctx._ck(ctx.L.idp_get_constraints(ctx.h, bufs["rows"].numpy().ctypes.data, bufs["info"].numpy().ctypes.data))
+            E, nnz = ctx.barrier_all(dhat2, KAPPA)
+            g_host.zero_()
+            # gradient accumulate + CSR to the host (what the reference's Newton solve consumes)
+            ctx._ck(ctx.L.idp_barrier_gradient(ctx.h, dhat2, KAPPA, 0.0, g_host.numpy().ctypes.data, 3))
+            if "col" not in bufs or bufs["col"].shape[0] < nnz:
+                bufs["ptr"] = torch.empty(3 * mesh.nV + 1, dtype=torch.int32).pin_memory()
+                bufs["col"] = torch.empty(int(nnz * 1.1) + 16, dtype=torch.int32).pin_memory()
+                bufs["val"] = torch.empty(int(nnz * 1.1) + 16, dtype=torch.float64).pin_memory()
+            ctx._ck(ctx.L.idp_get_hessian_csr(ctx.h, bufs["ptr"].numpy().ctypes.data, bufs["col"].numpy().ctypes.data,
+                                              bufs["val"].numpy().ctypes.data))
+            a = ctx.ccd_step(Dh.numpy(), 1.0)
+            _, mn = ctx.min_dist2(want_all=False)
+            return n + ctx.count(3) + ctx.count(4), (n, nnz, E, a, mn)
+
+        for _ in range(2):
+            step_e2e()
+        k2 = max(2, min(args.steps, 3))
+        ms2, wall2, pairs2, info2 = timed(step_e2e, k2)
+        n2, nnz2 = info2[0], info2[1]
+        h2d = 2 * mesh.nV * 3 * 8
+        d2h = n2 * (16 + 16) + mesh.nV * 3 * 8 + (3 * mesh.nV + 1) * 4 + nnz2 * 12 + 64
+        e2e = {"value": pairs_per_step * k2 / (wall2 * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": wall2 / k2, "steps": k2,
+               "timed_region": "wall clock around set_positions + constraint set + rows D2H + barrier E/g/H + g D2H + CSR D2H + "
+                               "search-direction H2D + CCD + min-dist, pinned host buffers"}
+
+    cb = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cb = cpu_baseline(steps=1, warmup=0)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "%s: BASELINE configs[3] synthetic tangled multi-sheet surface (%d triangles, %d vertices), "
+                                       "dHat=%g, kappa=%g, CCD alpha0=1" % (args.workload, mesh.nF, mesh.nV, dhat, KAPPA),
+                           "pairs_per_step": pairs_per_step, "constraint_rows": int(n_rows), "ccd_candidates": int(ccd_local.item()),
+                           "static_candidates": None, "nnz": int(nnz), "sharding": "primitive ranges x%d" % world,
+                           "l2": "working set per step (candidate lists, 3x3 blocks, CSR) is several GB >> 126 MB L2; no explicit flush"},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "library_primitive_calls": int(lib_calls),
+                "roofline": roofline, "cpu_baseline": ({k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")} if cb else None),
+                "stage_ms_last_step": stages, "wall_ms_per_step": wall_ms / args.steps,
+                "results": {"E": E, "alpha": alpha, "min_dist2": mind}}
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -18,14 +18,15 @@ STATUS = {0: "IDP_OK", 1: "IDP_ERR_CUDA", 2: "IDP_ERR_INVALID", 3: "IDP_ERR_NONP
 STAGES = ["Compute_Constraint_Set_Build_Hash", "Compute_Constraint_Set_PT", "Compute_Constraint_Set_EE",
           "Compute_Constraint_Set_Merge", "Compute_Barrier_EgH", "constructCSRMatrixFromTriplet",
           "Compute_Intersection_Free_StepSize_Build_Hash", "Compute_Intersection_Free_StepSize_PT",
-          "Compute_Intersection_Free_StepSize_EE", "Compute_Min_Dist", "upload"]
+          "Compute_Intersection_Free_StepSize_EE", "Compute_Min_Dist", "upload", "k_barrier", "k_query", "k_accd",
+          "k_classify"]
 
 # every symbol include/idp_contact.h declares
 EXPORTS = ["idp_create", "idp_destroy", "idp_last_error", "idp_set_stream", "idp_set_mesh", "idp_declare_unsupported",
            "idp_set_positions", "idp_set_rest_positions", "idp_constraint_set", "idp_get_constraints",
            "idp_set_constraints", "idp_get_candidates", "idp_barrier_energy", "idp_barrier_gradient",
            "idp_barrier_hessian", "idp_barrier_all", "idp_get_hessian_csr", "idp_hessian_csr_device",
-           "idp_gradient_device", "idp_ccd_step", "idp_min_dist2", "idp_comm_unique_id", "idp_comm_init",
+           "idp_gradient_device", "idp_ccd_step", "idp_set_search_direction", "idp_ccd_step_resident", "idp_min_dist2", "idp_comm_unique_id", "idp_comm_init",
            "idp_set_shard", "idp_kernel_launches", "idp_library_calls", "idp_reset_counters", "idp_stage_ms",
            "idp_last_count", "idp_measure_fp64_tflops"]
 
@@ -63,6 +64,8 @@ def load_library(path=LIB_PATH):
     L.idp_hessian_csr_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(l)]
     L.idp_gradient_device.argtypes = [vp, C.POINTER(vp)]
     L.idp_ccd_step.argtypes = [vp, vp, i, d, C.POINTER(d)]
+    L.idp_set_search_direction.argtypes = [vp, vp, i]
+    L.idp_ccd_step_resident.argtypes = [vp, d, C.POINTER(d)]
     L.idp_min_dist2.argtypes = [vp, d, vp, C.POINTER(d)]
     L.idp_comm_unique_id.argtypes = [vp]
     L.idp_comm_init.argtypes = [vp, i, i, vp]
@@ -203,6 +206,15 @@ class ContactContext:
         direction = np.ascontiguousarray(direction, np.float64)
         a = C.c_double(alpha)
         self._ck(self.L.idp_ccd_step(self.h, _p(direction), direction.shape[1], thickness, C.byref(a)))
+        return a.value
+
+    def set_search_direction(self, direction):
+        direction = np.ascontiguousarray(direction, np.float64)
+        self._ck(self.L.idp_set_search_direction(self.h, _p(direction), direction.shape[1]))
+
+    def ccd_step_resident(self, alpha=1.0, thickness=0.0):
+        a = C.c_double(alpha)
+        self._ck(self.L.idp_ccd_step_resident(self.h, thickness, C.byref(a)))
         return a.value
 
     def min_dist2(self, thickness=0.0, want_all=True):

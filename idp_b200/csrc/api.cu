@@ -28,6 +28,8 @@ int idp_create(int device, idp_ctx** out)
     c->own_stream = true;
     cudaEventCreate(&c->ev0);
     cudaEventCreate(&c->ev1);
+    cudaEventCreate(&c->kev0);
+    cudaEventCreate(&c->kev1);
     if (c->counters.reserve(CNT_COUNT) != cudaSuccess) { delete c; return IDP_ERR_CUDA; }
     cudaMemset(c->counters.p, 0, CNT_COUNT * sizeof(long long));
     cudaMallocHost((void**)&c->h_counters, CNT_COUNT * sizeof(long long));
@@ -48,6 +50,8 @@ void idp_destroy(idp_ctx* c)
     if (c->h_red) cudaFreeHost(c->h_red);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->kev0) cudaEventDestroy(c->kev0);
+    if (c->kev1) cudaEventDestroy(c->kev1);
     cudaStream_t s = c->own_stream ? c->stream : nullptr;
     delete c; // frees the device buffers
     if (s) cudaStreamDestroy(s);
@@ -78,7 +82,7 @@ int idp_set_mesh(idp_ctx* c, int nV, int nBN, const int* bnode, int nBE, const i
         return c ? fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "idp_set_mesh: bad arguments", __FILE__, __LINE__) : IDP_ERR_INVALID;
     IDP_CK(c, cudaSetDevice(c->device));
     c->nV = nV; c->nBN = nBN; c->nBE = nBE; c->nBT = nBT;
-    c->have_x = c->have_x0 = false;
+    c->have_x = c->have_x0 = c->have_dir = false;
     c->nRows = 0; c->nCandPT = c->nCandEE = c->nCcdPT = c->nCcdEE = 0;
     IDP_CK(c, c->bnode.reserve(std::max(nBN, 1)));
     IDP_CK(c, c->bedge.reserve(std::max(nBE, 1)));
@@ -260,11 +264,19 @@ int idp_gradient_device(idp_ctx* c, const double** d_g)
     return IDP_OK;
 }
 
-int idp_ccd_step(idp_ctx* c, const double* dir, int stride, double thickness, double* alpha_inout)
+int idp_set_search_direction(idp_ctx* c, const double* dir, int stride)
 {
-    if (!c || !dir || !alpha_inout) return IDP_ERR_INVALID;
+    if (!c || !dir) return IDP_ERR_INVALID;
     IDP_CK(c, cudaSetDevice(c->device));
     IDP_TRY(upload_positions(c, dir, stride, 2));
+    c->have_dir = true;
+    return IDP_OK;
+}
+int idp_ccd_step_resident(idp_ctx* c, double thickness, double* alpha_inout)
+{
+    if (!c || !alpha_inout) return IDP_ERR_INVALID;
+    IDP_CK(c, cudaSetDevice(c->device));
+    if (!c->have_dir) return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "search direction not set", __FILE__, __LINE__);
     double a = *alpha_inout;
     IDP_TRY(ccd_step(c, thickness, &a, 1));
     if (c->nranks > 1 && c->nccl_comm) {
@@ -275,6 +287,11 @@ int idp_ccd_step(idp_ctx* c, const double* dir, int stride, double thickness, do
     }
     *alpha_inout = a;
     return IDP_OK;
+}
+int idp_ccd_step(idp_ctx* c, const double* dir, int stride, double thickness, double* alpha_inout)
+{
+    IDP_TRY(idp_set_search_direction(c, dir, stride));
+    return idp_ccd_step_resident(c, thickness, alpha_inout);
 }
 
 int idp_min_dist2(idp_ctx* c, double thickness, double* dist2, double* min_out)

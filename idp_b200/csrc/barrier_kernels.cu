@@ -150,6 +150,7 @@ int barrier_eval(idp_ctx* c, double dhat2, double kappa, double thickness, int w
         c->h_counters[CNT_COUNT - 1] = ends[1];
     }
     if (nMine > 0) {
+        KernelTimer kt(c, IDP_STAGE_K_BARRIER);
         const int sel = (want_e ? 1 : 0) | (want_g ? 2 : 0) | (want_h ? 4 : 0);
         switch (sel) {
         case 1: IDP_LAUNCH(c, (k_barrier<true, false, false>), grid, 128, 0, a); break;
@@ -162,8 +163,8 @@ int barrier_eval(idp_ctx* c, double dhat2, double kappa, double thickness, int w
         default: break;
         }
         IDP_CK(c, cudaGetLastError());
-        if (want_e) IDP_LAUNCH(c, k_sum_partials, 1, 256, 0, c->red.p, (int)grid, c->red.p + grid);
     }
+    if (nMine > 0 && want_e) IDP_LAUNCH(c, k_sum_partials, 1, 256, 0, c->red.p, (int)grid, c->red.p + grid);
     long long nerr = 0;
     IDP_CK(c, cudaMemcpyAsync(&nerr, c->counters.p + CNT_ERR_DIST, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
     double E = 0;

@@ -114,7 +114,7 @@ struct idp_ctx {
     idp::DBuf<double> stage;            // upload staging (AoS)
     idp::DBuf<double> xs, ys, zs;       // SoA positions (streaming kernels)
     idp::DBuf<double4> xp, x0p, dp;     // 32-byte packed positions / rest positions / search direction (gathers)
-    bool have_x = false, have_x0 = false;
+    bool have_x = false, have_x0 = false, have_dir = false;
     // ---- broad-phase scratch ----
     idp::DBuf<idp::PrimRec> recN, recE, recT;
     idp::DBuf<idp::IBox> boxNq, boxEq, boxEb, boxTb; // query boxes (inflated) and insert boxes
@@ -150,7 +150,7 @@ struct idp_ctx {
     double* h_red = nullptr;
 
     idp::StageTimes times;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, kev0 = nullptr, kev1 = nullptr;
 };
 
 namespace idp {
@@ -202,6 +202,19 @@ struct StageTimer {
         cudaEventRecord(c->ev1, c->stream);
         cudaEventSynchronize(c->ev1);
         cudaEventElapsedTime(&c->times.v[stage], c->ev0, c->ev1);
+    }
+};
+
+// times a single launch with its own event pair (nested inside a StageTimer scope); read back lazily at scope end
+struct KernelTimer {
+    idp_ctx* c;
+    int stage;
+    KernelTimer(idp_ctx* ctx, int st) : c(ctx), stage(st) { cudaEventRecord(c->kev0, c->stream); }
+    ~KernelTimer()
+    {
+        cudaEventRecord(c->kev1, c->stream);
+        cudaEventSynchronize(c->kev1);
+        cudaEventElapsedTime(&c->times.v[stage], c->kev0, c->kev1);
     }
 };
 

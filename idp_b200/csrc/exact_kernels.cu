@@ -460,7 +460,10 @@ static int run_query(idp_ctx* c, QueryArgs a, DBuf<int2>& out, long* nOut)
         a.cap = (long)out.cap;
         a.counter = counter;
         const unsigned grid = (unsigned)std::min<long>((nQ + 7) / 8, (long)c->sm_count * 64);
-        if (nQ > 0) IDP_LAUNCH(c, k_query<MODE>, std::max(grid, 1u), 256, 0, a);
+        if (nQ > 0) {
+            KernelTimer kt(c, IDP_STAGE_K_QUERY);
+            IDP_LAUNCH(c, k_query<MODE>, std::max(grid, 1u), 256, 0, a);
+        }
         IDP_CK(c, cudaGetLastError());
         long long n = 0;
         IDP_CK(c, cudaMemcpyAsync(&n, counter, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
@@ -713,7 +716,10 @@ int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
         ca.xp = c->xp.p; ca.x0p = c->x0p.p; ca.dHat2 = dHat2;
         ca.rowsDirect = c->rowsA.p; ca.capDirect = (long)c->rowsA.cap; ca.cntDirect = cnt + CNT_ROWS_A;
         ca.rowsDup = c->rowsD.p; ca.capDup = (long)c->rowsD.cap; ca.cntDup = cnt + CNT_ROWS_D;
-        if (c->nCandPT > 0) IDP_LAUNCH(c, k_classify_pt, std::min(blocks_for(c->nCandPT, 256), (unsigned)c->sm_count * 16), 256, 0, ca);
+        if (c->nCandPT > 0) {
+            KernelTimer kt(c, IDP_STAGE_K_CLASSIFY);
+            IDP_LAUNCH(c, k_classify_pt, std::min(blocks_for(c->nCandPT, 256), (unsigned)c->sm_count * 16), 256, 0, ca);
+        }
         IDP_CK(c, cudaGetLastError());
         IDP_TRY(read_counters(c));
     }
@@ -738,7 +744,10 @@ int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
         ca.xp = c->xp.p; ca.x0p = c->x0p.p; ca.dHat2 = dHat2;
         ca.rowsDirect = c->rowsB.p; ca.capDirect = (long)c->rowsB.cap; ca.cntDirect = cnt + CNT_ROWS_A;
         ca.rowsDup = c->rowsD.p; ca.capDup = (long)c->rowsD.cap; ca.cntDup = cnt + CNT_ROWS_D;
-        if (c->nCandEE > 0) IDP_LAUNCH(c, k_classify_ee, std::min(blocks_for(c->nCandEE, 256), (unsigned)c->sm_count * 16), 256, 0, ca);
+        if (c->nCandEE > 0) {
+            KernelTimer kt(c, IDP_STAGE_K_CLASSIFY);
+            IDP_LAUNCH(c, k_classify_ee, std::min(blocks_for(c->nCandEE, 256), (unsigned)c->sm_count * 16), 256, 0, ca);
+        }
         IDP_CK(c, cudaGetLastError());
         IDP_TRY(read_counters(c));
         nB = (long)c->h_counters[CNT_ROWS_A];
@@ -1006,7 +1015,10 @@ int ccd_step(idp_ctx* c, double thickness, double* alpha_inout, int keep_candida
         qa.g = g; qa.dist = thickness;
         IDP_TRY(run_query<3>(c, qa, c->candEE, &c->nCcdEE));
         aa.cand = c->candEE.p; aa.nCand = c->nCcdEE;
-        if (c->nCcdEE > 0) IDP_LAUNCH(c, k_accd<1>, std::min(blocks_for(c->nCcdEE, 128), (unsigned)c->sm_count * 32), 128, 0, aa);
+        if (c->nCcdEE > 0) {
+            KernelTimer kt(c, IDP_STAGE_K_ACCD);
+            IDP_LAUNCH(c, k_accd<1>, std::min(blocks_for(c->nCcdEE, 128), (unsigned)c->sm_count * 32), 128, 0, aa);
+        }
         IDP_CK(c, cudaGetLastError());
     }
     IDP_TRY(read_counters(c));

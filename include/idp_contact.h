@@ -46,6 +46,10 @@ enum idp_stage {
     IDP_STAGE_CCD_EE = 8,           /* Compute_Intersection_Free_StepSize_EE */
     IDP_STAGE_MIN_DIST = 9,         /* Compute_Min_Dist */
     IDP_STAGE_UPLOAD = 10,          /* host -> device marshalling of positions / directions */
+    IDP_STAGE_K_BARRIER = 11,       /* the k_barrier launch alone (dominant FP64 kernel) */
+    IDP_STAGE_K_QUERY = 12,         /* the last broad-phase query launch alone */
+    IDP_STAGE_K_ACCD = 13,          /* the last additive-CCD launch alone */
+    IDP_STAGE_K_CLASSIFY = 14,      /* the last classification launch alone */
     IDP_STAGE_COUNT = 16
 };
 
@@ -107,6 +111,9 @@ int idp_gradient_device(idp_ctx* ctx, const double** d_g_xyz);
 /* searchDir: nV rows x 3 doubles (std::vector<T>, stride 3 in the reference). alpha is in/out and includes the
  * span clamp of the CCD hash build (Grid/SPATIAL_HASH.h:466-482). */
 int idp_ccd_step(idp_ctx* ctx, const double* search_dir, int stride, double thickness, double* alpha_inout);
+/* the same in two halves: upload the direction once, then filter steps against device-resident inputs */
+int idp_set_search_direction(idp_ctx* ctx, const double* search_dir, int stride);
+int idp_ccd_step_resident(idp_ctx* ctx, double thickness, double* alpha_inout);
 
 /* ---- Compute_Min_Dist2 (FEM/IPC.h:2246-2388) ---------------------------------------------------------------- */
 /* dist2 (n_rows doubles, may be NULL) and minDist2 = min - thickness^2. With zero rows nothing is written (IPC.h:2253). */
