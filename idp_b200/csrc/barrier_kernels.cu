@@ -43,43 +43,56 @@ struct BarrierArgs {
     unsigned long long* errDist;
 };
 
-template <bool WANT_E, bool WANT_G, bool WANT_H>
+// Hessian sink: writes the 3x3 block (i,j) of a row at its pre-scanned offset together with its (vi*nV+vj) sort key
+struct BlockEmit {
+    unsigned long long* key; int* idx; double* val;
+    long o; int nv; const int* v; long long nV;
+    __device__ __forceinline__ void operator()(int i, int j, const double* blk) const
+    {
+        const long s = o + i * nv + j;
+        key[s] = (unsigned long long)((long long)v[i] * nV + v[j]);
+        idx[s] = (int)s;
+        double* dst = val + 9 * s;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) dst[k] = blk[k];
+    }
+};
+
+// One thread per constraint row. PATH 0: four-vertex kinds (PT, EE and the three mollified kinds; 9x9 Jacobi with the
+// eigenvectors in shared memory), PATH 1: point-edge (6x6 Jacobi in registers), PATH 2: point-point (closed form).
+// Each launch walks all rows of the shard and skips the kinds of the other paths, so rows keep their positions and the
+// outputs (block offsets, partial sums) are deterministic.
+template <int PATH, bool WANT_E, bool WANT_G, bool WANT_H>
 __global__ void __launch_bounds__(128) k_barrier(BarrierArgs a)
 {
+    extern __shared__ double sV[];
     double Eacc = 0;
     for (long i = a.rowBegin + (long)blockIdx.x * blockDim.x + threadIdx.x; i < a.rowEnd; i += (long)gridDim.x * blockDim.x) {
         const Row4 r = a.rows[i];
         const RowDec d = decode_row(r.a, r.b, r.c, r.d);
+        const int path = (d.kind == K_PP) ? 2 : (d.kind == K_PE ? 1 : 0);
+        if (path != PATH) continue;
         V3 x[4], xr[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) x[k] = ldv4(a.xp, d.v[k]);
-        if (d.kind == K_EE_M || d.kind == K_PE_M || d.kind == K_PP_M) {
+        if (PATH == 0 && (d.kind == K_EE_M || d.kind == K_PE_M || d.kind == K_PP_M)) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) xr[k] = ldv4(a.x0p, d.v[k]);
         }
-        double E = 0, g[12], H[144];
-        const bool ok = row_EgH_lowrank(d, x, xr, a.weights[i], a.dHat2, a.kappa, a.xi2, a.projectSPD != 0,
-            WANT_E ? &E : nullptr, WANT_G ? g : nullptr, WANT_H ? H : nullptr);
+        RowOut out;
+        VShared<9> V9{sV + threadIdx.x, (int)blockDim.x, 0};
+        BlockEmit em{a.blkKey, a.blkIdx, a.blkVal, WANT_H ? (long)a.blkOff[i] : 0L, d.nv, d.v, a.nVll};
+        const bool ok = row_eval<PATH>(d, x, xr, a.weights[i], a.dHat2, a.kappa, a.xi2, a.projectSPD != 0, WANT_H, V9, out, em);
         if (!ok) { atomicAdd(a.errDist, 1ull); continue; }
-        if (WANT_E) Eacc += E;
+        if (WANT_E) Eacc += out.E;
         if (WANT_G) {
-            for (int k = 0; k < d.nv; ++k) {
-                double* gp = a.g + 3 * (long)d.v[k];
-                atomicAdd(gp, g[3 * k]); atomicAdd(gp + 1, g[3 * k + 1]); atomicAdd(gp + 2, g[3 * k + 2]);
-            }
-        }
-        if (WANT_H) {
-            const int n = 3 * d.nv;
-            const long o = a.blkOff[i];
-            for (int bi = 0; bi < d.nv; ++bi)
-                for (int bj = 0; bj < d.nv; ++bj) {
-                    const long s = o + bi * d.nv + bj;
-                    a.blkKey[s] = (unsigned long long)((long long)d.v[bi] * a.nVll + d.v[bj]);
-                    a.blkIdx[s] = (int)s;
-                    double* dst = a.blkVal + 9 * s;
-                    for (int p = 0; p < 3; ++p)
-                        for (int q = 0; q < 3; ++q) dst[3 * p + q] = H[(3 * bi + p) * n + 3 * bj + q];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (k < d.nv) {
+                    double* gp = a.g + 3 * (long)d.v[k];
+                    atomicAdd(gp, out.g[3 * k]); atomicAdd(gp + 1, out.g[3 * k + 1]); atomicAdd(gp + 2, out.g[3 * k + 2]);
                 }
+            }
         }
     }
     if (WANT_E) {
@@ -88,6 +101,30 @@ __global__ void __launch_bounds__(128) k_barrier(BarrierArgs a)
         const double s = BR(tmp).Sum(Eacc);
         if (threadIdx.x == 0) a.partialE[blockIdx.x] = s;
     }
+}
+
+template <int PATH>
+static int launch_barrier_path(idp_ctx* c, BarrierArgs a, unsigned grid, int sel)
+{
+    const size_t smem = PATH == 0 ? 81 * sizeof(double) * 128 : 0;
+#define IDP_BARRIER_CASE(E, G, H)                                                                                         \
+    do {                                                                                                                  \
+        if (smem) IDP_CK(c, cudaFuncSetAttribute(k_barrier<PATH, E, G, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        IDP_LAUNCH(c, (k_barrier<PATH, E, G, H>), grid, 128, smem, a);                                                  \
+    } while (0)
+    switch (sel) {
+    case 1: IDP_BARRIER_CASE(true, false, false); break;
+    case 2: IDP_BARRIER_CASE(false, true, false); break;
+    case 3: IDP_BARRIER_CASE(true, true, false); break;
+    case 4: IDP_BARRIER_CASE(false, false, true); break;
+    case 5: IDP_BARRIER_CASE(true, false, true); break;
+    case 6: IDP_BARRIER_CASE(false, true, true); break;
+    case 7: IDP_BARRIER_CASE(true, true, true); break;
+    default: break;
+    }
+#undef IDP_BARRIER_CASE
+    IDP_CK(c, cudaGetLastError());
+    return IDP_OK;
 }
 
 // deterministic final sum of the per-block partials (single block)
@@ -122,7 +159,7 @@ int barrier_eval(idp_ctx* c, double dhat2, double kappa, double thickness, int w
     a.xp = c->xp.p; a.x0p = c->x0p.p;
     a.dHat2 = dhat2 + 2 * std::sqrt(dhat2) * thickness; // IPC.h:757
     a.kappa = kappa; a.xi2 = thickness * thickness; a.projectSPD = project_spd;
-    IDP_CK(c, c->red.reserve(grid + 8));
+    IDP_CK(c, c->red.reserve(3 * (size_t)grid + 8));
     a.partialE = c->red.p;
     a.g = c->gbuf.p;
     a.errDist = (unsigned long long*)(c->counters.p + CNT_ERR_DIST);
@@ -152,23 +189,18 @@ int barrier_eval(idp_ctx* c, double dhat2, double kappa, double thickness, int w
     if (nMine > 0) {
         KernelTimer kt(c, IDP_STAGE_K_BARRIER);
         const int sel = (want_e ? 1 : 0) | (want_g ? 2 : 0) | (want_h ? 4 : 0);
-        switch (sel) {
-        case 1: IDP_LAUNCH(c, (k_barrier<true, false, false>), grid, 128, 0, a); break;
-        case 2: IDP_LAUNCH(c, (k_barrier<false, true, false>), grid, 128, 0, a); break;
-        case 3: IDP_LAUNCH(c, (k_barrier<true, true, false>), grid, 128, 0, a); break;
-        case 4: IDP_LAUNCH(c, (k_barrier<false, false, true>), grid, 128, 0, a); break;
-        case 5: IDP_LAUNCH(c, (k_barrier<true, false, true>), grid, 128, 0, a); break;
-        case 6: IDP_LAUNCH(c, (k_barrier<false, true, true>), grid, 128, 0, a); break;
-        case 7: IDP_LAUNCH(c, (k_barrier<true, true, true>), grid, 128, 0, a); break;
-        default: break;
-        }
-        IDP_CK(c, cudaGetLastError());
+        BarrierArgs a0 = a, a1 = a, a2 = a;
+        a1.partialE = a.partialE + grid;
+        a2.partialE = a.partialE + 2 * (size_t)grid;
+        IDP_TRY(launch_barrier_path<0>(c, a0, grid, sel));
+        IDP_TRY(launch_barrier_path<1>(c, a1, grid, sel));
+        IDP_TRY(launch_barrier_path<2>(c, a2, grid, sel));
     }
-    if (nMine > 0 && want_e) IDP_LAUNCH(c, k_sum_partials, 1, 256, 0, c->red.p, (int)grid, c->red.p + grid);
+    if (nMine > 0 && want_e) IDP_LAUNCH(c, k_sum_partials, 1, 256, 0, c->red.p, 3 * (int)grid, c->red.p + 3 * (size_t)grid);
     long long nerr = 0;
     IDP_CK(c, cudaMemcpyAsync(&nerr, c->counters.p + CNT_ERR_DIST, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
     double E = 0;
-    if (want_e && nMine > 0) IDP_CK(c, cudaMemcpyAsync(&E, c->red.p + grid, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (want_e && nMine > 0) IDP_CK(c, cudaMemcpyAsync(&E, c->red.p + 3 * (size_t)grid, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     IDP_CK(c, cudaStreamSynchronize(c->stream));
     if (nerr) return fail(c, IDP_ERR_NONPOSITIVE_DISTANCE, "%s (%s:%d)", "non-positive distance detected during barrier evaluation", __FILE__, __LINE__);
     if (E_out) *E_out = E;

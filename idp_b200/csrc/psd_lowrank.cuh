@@ -1,10 +1,570 @@
-// Structured (low-rank) evaluation of the projected barrier Hessian. Placeholder: forwards to the dense path.
+// Register-resident evaluation of one constraint row: energy, gradient and (PSD-projected) Hessian.
+//
+// Replaces the dense path of pair_deriv.cuh (kept as the straightforward formulation the tests compare against):
+//   * every quantity is formed in REDUCED (difference) coordinates: (w,u,v) in R^9 for four-vertex stencils, (w,u) in R^6
+//     for point-edge, because all distances and the mollifier are translation invariant;
+//   * the projection onto the PSD cone (makePD, Library/Math/UTILS.h:9-27) is done on the 9x9 / 6x6 matrix
+//     M = T^T H_r T, where T maps an ORTHONORMAL basis of the translation-free subspace (Hadamard basis of the stencil
+//     vertices) to the difference coordinates. Since H = Q M Q^T with Q orthonormal, eig(H) = eig(M) + three zeros and
+//     makePD(H) = Q makePD(M) Q^T exactly;
+//   * the symmetric eigen-decomposition is a cyclic Jacobi iteration on the packed upper triangle held in registers;
+//     the eigenvector matrix lives in shared memory (one column per thread, bank-conflict free) for 9x9 and in registers
+//     for 6x6; point-point rows have a closed form.
+// Reference semantics: FEM/IPC.h:801-938 (E), 1012-1254 (g), 1390-1729 (H); tolerance 1e-10 relative.
 #pragma once
 #include "pair_deriv.cuh"
+
 namespace idp {
+
+// packed upper triangle of a symmetric N x N matrix
+template <int N>
+IDP_HD constexpr int SI(int r, int c) { return r <= c ? (r * N - (r * (r - 1)) / 2 + (c - r)) : (c * N - (c * (c - 1)) / 2 + (r - c)); }
+
+// approximate reciprocal / reciprocal square root refined by Newton steps (no IEEE corner cases needed: inputs are
+// positive, finite and far from the subnormal range on this path)
+IDP_HD double rcp_nr2(double x)
+{
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    return r;
+#else
+    return 1.0 / x;
+#endif
+}
+template <int STEPS>
+IDP_HD double rsqrt_nr(double x)
+{
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double h = 0.5 * x;
+#pragma unroll
+    for (int i = 0; i < STEPS; ++i) y = fma(fma(-h * y, y, 0.5), y, y);
+    return y;
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
+
+// eigenvector storage policies -------------------------------------------------------------------------------
+// The Jacobi loop relabels the matrix indices cyclically after every round (see jacobi_packed); the storage follows
+// with advance(): registers are permuted, shared memory only moves a column offset.
+template <int N>
+struct VLocal {
+    static constexpr int M = (N % 2) ? N : N - 1;
+    double v[N * N];
+    IDP_HD void init()
+    {
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+#pragma unroll
+            for (int j = 0; j < N; ++j) v[i * N + j] = (i == j) ? 1.0 : 0.0;
+    }
+    IDP_HD double get(int r, int c) const { return v[r * N + c]; }
+    IDP_HD void set(int r, int c, double x) { v[r * N + c] = x; }
+    IDP_HD void advance()
+    {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const double t0 = v[i * N];
+#pragma unroll
+            for (int j = 0; j + 1 < M; ++j) v[i * N + j] = v[i * N + j + 1];
+            v[i * N + M - 1] = t0;
+        }
+    }
+};
+template <int N>
+struct VShared { // shared memory: element (r, physical column) of this thread at p[(r*N + col) * stride]
+    static constexpr int M = (N % 2) ? N : N - 1;
+    double* p;
+    int stride;
+    int off;
+    IDP_HD void init()
+    {
+        off = 0;
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+#pragma unroll
+            for (int j = 0; j < N; ++j) p[(i * N + j) * stride] = (i == j) ? 1.0 : 0.0;
+    }
+    IDP_HD int col(int c) const
+    {
+        if (c >= M) return c;
+        const int k = c + off;
+        return k >= M ? k - M : k;
+    }
+    IDP_HD double get(int r, int c) const { return p[(r * N + col(c)) * stride]; }
+    IDP_HD void set(int r, int c, double x) { p[(r * N + col(c)) * stride] = x; }
+    IDP_HD void advance() { off = (off + 1 == M) ? 0 : off + 1; }
+};
+
+// Jacobi eigenvalue iteration on the packed upper triangle a (N(N+1)/2 values); V receives the eigenvectors as
+// columns; on exit the diagonal of a holds the eigenvalues.
+// Pair order: round-robin tournament. The pairs of one round are disjoint, so their rotation parameters depend only on
+// their own 2x2 blocks and are computed together (independent rcp / rsqrt chains give the scheduler ILP), then applied.
+// Round r+1 of the circle method is round r with every index shifted by one, so instead of unrolling all rounds (a
+// 80 KB loop body that thrashes the instruction cache) the ROUND-0 code is executed M times and the matrix is relabelled
+// i -> i+1 (mod M) in between: a register permutation for a, a column offset for V. After M rounds (one sweep) the
+// labels are back in place. Converged when off-diagonal norm^2 <= 1e-26 * total norm^2.
+template <int N, class VS>
+IDP_HD void jacobi_packed(double* a, VS& V)
+{
+    constexpr int M = (N % 2) ? N : N - 1; // circle size; for even N index N-1 is the fixed player
+    constexpr int PAIRS = N / 2;
+    V.init();
+    for (int sweep = 0; sweep < 24; ++sweep) {
+        double off = 0, dia = 0;
+#pragma unroll
+        for (int p = 0; p < N; ++p)
+#pragma unroll
+            for (int q = p; q < N; ++q) {
+                const double x = a[SI<N>(p, q)];
+                if (p == q) dia += x * x;
+                else off += x * x;
+            }
+        if (off <= 1e-26 * (dia + 2.0 * off)) break;
+#pragma unroll 1
+        for (int round = 0; round < M; ++round) {
+            double cs[PAIRS], sn[PAIRS];
+#pragma unroll
+            for (int k = 0; k < PAIRS; ++k) {
+                // round-0 pairs: odd N: (k+1, M-1-k); even N: (0, N-1), (k, M-k)
+                const int p = (N % 2) ? (k + 1) : (k == 0 ? 0 : k);
+                const int q = (N % 2) ? (M - 1 - k) : (k == 0 ? N - 1 : M - k);
+                const double apq = a[SI<N>(p, q)], app = a[SI<N>(p, p)], aqq = a[SI<N>(q, q)];
+                const double delta = 0.5 * (aqq - app);
+                const double h2 = delta * delta + apq * apq;
+                double t = 0.0;
+                if (h2 > 1e-290 && apq != 0.0) {
+                    const double hyp = h2 * rsqrt_nr<1>(h2);                     // sqrt(delta^2 + apq^2)
+                    t = (delta >= 0 ? apq : -apq) * rcp_nr2(fabs(delta) + hyp); // tan of the rotation angle
+                }
+                const double c = rsqrt_nr<3>(t * t + 1.0), s = t * c;
+                cs[k] = c; sn[k] = s;
+                a[SI<N>(p, p)] = app - t * apq;
+                a[SI<N>(q, q)] = aqq + t * apq;
+                a[SI<N>(p, q)] = (t != 0.0) ? 0.0 : apq;
+            }
+#pragma unroll
+            for (int k = 0; k < PAIRS; ++k) {
+                const int p = (N % 2) ? (k + 1) : (k == 0 ? 0 : k);
+                const int q = (N % 2) ? (M - 1 - k) : (k == 0 ? N - 1 : M - k);
+                const double c = cs[k], s = sn[k];
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    if (i != p && i != q) {
+                        const double aip = a[SI<N>(i, p)], aiq = a[SI<N>(i, q)];
+                        a[SI<N>(i, p)] = c * aip - s * aiq;
+                        a[SI<N>(i, q)] = s * aip + c * aiq;
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    const double vip = V.get(i, p), viq = V.get(i, q);
+                    V.set(i, p, c * vip - s * viq);
+                    V.set(i, q, s * vip + c * viq);
+                }
+            }
+            // relabel: new(i, j) = old(sigma(i), sigma(j)), sigma(i) = i + 1 (mod M) on the circle, identity on the fixed player
+            {
+                double b[N * (N + 1) / 2];
+#pragma unroll
+                for (int i = 0; i < N; ++i)
+#pragma unroll
+                    for (int j = i; j < N; ++j) {
+                        const int si = (i < M) ? ((i + 1) % M) : i, sj = (j < M) ? ((j + 1) % M) : j;
+                        b[SI<N>(i, j)] = a[SI<N>(si, sj)];
+                    }
+#pragma unroll
+                for (int i = 0; i < N * (N + 1) / 2; ++i) a[i] = b[i];
+            }
+            V.advance();
+        }
+    }
+}
+
+// makePD on a packed symmetric matrix (in place). The matrix is always rebuilt as V diag(max(lambda,0)) V^T; when no
+// eigenvalue is negative this reproduces the input to rounding (the reference returns it untouched).
+template <int N, class VS>
+IDP_HD void make_pd_packed(double* m, VS& V)
+{
+    jacobi_packed<N>(m, V);
+    double lam[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const double l = m[SI<N>(i, i)];
+        lam[i] = l > 0 ? l : 0.0;
+    }
+#pragma unroll
+    for (int r = 0; r < N; ++r) {
+        double wr[N];
+#pragma unroll
+        for (int k = 0; k < N; ++k) wr[k] = V.get(r, k) * lam[k];
+#pragma unroll
+        for (int c = r; c < N; ++c) {
+            double s = 0;
+#pragma unroll
+            for (int k = 0; k < N; ++k) s += wr[k] * V.get(c, k);
+            m[SI<N>(r, c)] = s;
+        }
+    }
+}
+
+// ---- reduced-coordinate pieces ---------------------------------------------------------------------------------
+// adds to the packed 9x9 H (blocks w=0, u=1, v=2):  kg g g^T + kq q q^T + kA hess(A) + kB hess(B)
+// for d = A^2/B;  g = grad d, q = grad A - r grad B are returned in g9 / internally.
+IDP_HD void triple_quotient_packed(const V3& w, const V3& u, const V3& v, double kbh, double kbg, double* g9, double* H)
+{
+    const V3 n = cross3(u, v);
+    const double A = dot3(w, n), B = sqn3(n), iB = 1.0 / B, r = A * iB;
+    const V3 Au = cross3(v, w), Av = cross3(w, u);
+    const V3 Bu = 2.0 * cross3(v, n), Bv = 2.0 * cross3(n, u);
+    const double gA[9] = {n.x, n.y, n.z, Au.x, Au.y, Au.z, Av.x, Av.y, Av.z};
+    const double gB[9] = {0, 0, 0, Bu.x, Bu.y, Bu.z, Bv.x, Bv.y, Bv.z};
+    double q[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        g9[i] = 2.0 * r * gA[i] - r * r * gB[i];
+        q[i] = gA[i] - r * gB[i];
+    }
+    const double kq = kbg * 2.0 * iB, kA = kbg * 2.0 * r, kB = -kbg * r * r;
+#pragma unroll
+    for (int i = 0; i < 9; ++i)
+#pragma unroll
+        for (int j = i; j < 9; ++j) H[SI<9>(i, j)] += kbh * g9[i] * g9[j] + kq * q[i] * q[j];
+    const double uu = sqn3(u), vv = sqn3(v), uv = dot3(u, v);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const double dij = (i == j) ? 1.0 : 0.0;
+            H[SI<9>(i, 3 + j)] += kA * (-skew3(v, i, j));
+            H[SI<9>(i, 6 + j)] += kA * skew3(u, i, j);
+            H[SI<9>(3 + i, 6 + j)] += kA * (-skew3(w, i, j)) + kB * (2.0 * (comp3(u, i) * comp3(v, j) - uv * dij) - 2.0 * skew3(n, i, j));
+            if (j >= i) {
+                H[SI<9>(3 + i, 3 + j)] += kB * 2.0 * (vv * dij - comp3(v, i) * comp3(v, j));
+                H[SI<9>(6 + i, 6 + j)] += kB * 2.0 * (uu * dij - comp3(u, i) * comp3(u, j));
+            }
+        }
+}
+
+// N = |a x b|^2: value, gradient (ga, gb) and the three Hessian blocks as closures over (a, b, c = a x b)
+struct CrossN2 {
+    V3 a, b, c;
+    double N, aa, bb, ab;
+    V3 ga, gb;
+    IDP_HD void init(const V3& a_, const V3& b_)
+    {
+        a = a_; b = b_;
+        c = cross3(a, b);
+        N = sqn3(c); aa = sqn3(a); bb = sqn3(b); ab = dot3(a, b);
+        ga = 2.0 * cross3(b, c);
+        gb = 2.0 * cross3(c, a);
+    }
+    IDP_HD double Haa(int i, int j) const { return 2.0 * (bb * (i == j ? 1.0 : 0.0) - comp3(b, i) * comp3(b, j)); }
+    IDP_HD double Hbb(int i, int j) const { return 2.0 * (aa * (i == j ? 1.0 : 0.0) - comp3(a, i) * comp3(a, j)); }
+    IDP_HD double Hab(int i, int j) const { return 2.0 * (comp3(a, i) * comp3(b, j) - ab * (i == j ? 1.0 : 0.0)) - 2.0 * skew3(c, i, j); }
+};
+
+// d = |a x b|^2 / |b|^2 in coordinates (a, b) placed at block offsets oa, ob (oa < ob) of a packed NxN matrix:
+// H += kbh g g^T + kbg hess(d);  returns g (N-vector contributions written into gN at the two blocks)
+template <int N>
+IDP_HD void pe_quotient_packed(const V3& a, const V3& b, int oa, int ob, double kbh, double kbg, double* gN, double* H)
+{
+    CrossN2 cn;
+    cn.init(a, b);
+    const double B = cn.bb, iB = 1.0 / B, NB2 = cn.N * iB * iB;
+    const V3 gBb = 2.0 * b;
+    double g6[6];
+    const double gNn[6] = {cn.ga.x, cn.ga.y, cn.ga.z, cn.gb.x, cn.gb.y, cn.gb.z};
+    const double gBv[6] = {0, 0, 0, gBb.x, gBb.y, gBb.z};
+#pragma unroll
+    for (int i = 0; i < 6; ++i) g6[i] = gNn[i] * iB - NB2 * gBv[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { gN[oa + i] = g6[i]; gN[ob + i] = g6[3 + i]; }
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = i; j < 6; ++j) {
+            const int bi = i / 3, bj = j / 3, ii = i % 3, jj = j % 3;
+            const double hn = (bi == 0 && bj == 0) ? cn.Haa(ii, jj) : ((bi == 1 && bj == 1) ? cn.Hbb(ii, jj) : cn.Hab(ii, jj));
+            const double hb = (i >= 3 && i == j) ? 2.0 : 0.0;
+            const double hd = hn * iB - (gNn[i] * gBv[j] + gBv[i] * gNn[j]) * (iB * iB) - NB2 * hb + (2.0 * NB2 * iB) * gBv[i] * gBv[j];
+            const int R = (bi == 0 ? oa : ob) + ii, C = (bj == 0 ? oa : ob) + jj;
+            H[SI<N>(R, C)] += kbh * g6[i] * g6[j] + kbg * hd;
+        }
+}
+
+// M = T^T H T for a block matrix with scalar 3x3 coefficient matrix T (K x K), blocks of size 3: packed in / packed out
+template <int K>
+IDP_HD void congruence_blocks(const double (&T)[K][K], const double* H, double* M)
+{
+    constexpr int N = 3 * K;
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int l = k; l < K; ++l)
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = (k == l ? i : 0); j < 3; ++j) {
+                    double s = 0;
+#pragma unroll
+                    for (int m = 0; m < K; ++m)
+#pragma unroll
+                        for (int n = 0; n < K; ++n) {
+                            const double cf = T[m][k] * T[n][l];
+                            if (cf != 0.0) s += cf * H[SI<N>(3 * m + i, 3 * n + j)];
+                        }
+                    M[SI<N>(3 * k + i, 3 * l + j)] = s;
+                }
+}
+
+// dense block (i,j) of Q M Q^T for Q = Hm (x) I3, Hm: NV x K coefficients; writes 9 doubles row-major
+template <int NV, int K>
+IDP_HD void expand_block(const double (&Hm)[NV][K], const double* M, int i, int j, double* out9)
+{
+    constexpr int N = 3 * K;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            double s = 0;
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+#pragma unroll
+                for (int l = 0; l < K; ++l) s += (Hm[i][k] * Hm[j][l]) * M[SI<N>(3 * k + a, 3 * l + b)];
+            out9[3 * a + b] = s;
+        }
+}
+
+// ---- row evaluation ------------------------------------------------------------------------------------------------
+// Outputs: E (scalar), g (3*nv), and the Hessian through the sink `emit(i, j, block9)` called for all nv^2 blocks.
+// VS9 is the eigenvector storage used for the 9x9 problems.
+struct RowOut {
+    double E;
+    double g[12];
+};
+
+// PATH selects which kinds are compiled in: -1 all, 0 four-vertex kinds, 1 point-edge, 2 point-point
+template <int PATH, class VS9, class Emit>
+IDP_HD bool row_eval(const RowDec& d, const V3* x, const V3* xr, double weight, double dHat2, double kappa, double xi2,
+    bool projectSPD, bool wantH, VS9& V9, RowOut& out, Emit& emit)
+{
+    const double dist2 = row_dist2(d.kind, x[0], x[1], x[2], x[3]) - xi2;
+    if (!(dist2 > 0)) return false;
+    double b, bg, bh;
+    barrier_all(dist2, dHat2, kappa, b, bg, bh);
+    const double mu = (double)d.mult;
+
+    if ((PATH < 0 || PATH == 2) && d.kind == K_PP) {
+        // closed form: H = [[M,-M],[-M,M]], M = w mu (4 bh dd^T + 2 bg I); eigenvalues 2 w mu (4 bh |d|^2 + 2 bg), 2 w mu 2 bg (x2)
+        const V3 dd = x[0] - x[1];
+        out.E = b * (d.mult > 1 ? mu : 1.0) * weight;
+        const double kg = mu * weight * bg * 2.0;
+        out.g[0] = kg * dd.x; out.g[1] = kg * dd.y; out.g[2] = kg * dd.z;
+        out.g[3] = -out.g[0]; out.g[4] = -out.g[1]; out.g[5] = -out.g[2];
+        if (wantH) {
+            const double s = weight * mu;
+            const double l2 = sqn3(dd);
+            double kd = s * 4.0 * bh, ki = s * 2.0 * bg; // M = kd dd^T + ki I
+            if (projectSPD) {
+                const double lam1 = kd * l2 + ki, lam2 = ki;
+                if (fmin(lam1, lam2) < 0) {
+                    const double l1 = lam1 > 0 ? lam1 : 0.0, lp = lam2 > 0 ? lam2 : 0.0;
+                    // M+ = lp I + (l1 - lp) d d^T / |d|^2
+                    kd = (l1 - lp) / l2;
+                    ki = lp;
+                }
+            }
+            double Mb[9], Nb[9];
+            const double dv[3] = {dd.x, dd.y, dd.z};
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    Mb[3 * i + j] = kd * dv[i] * dv[j] + (i == j ? ki : 0.0);
+                    Nb[3 * i + j] = -Mb[3 * i + j];
+                }
+            emit(0, 0, Mb); emit(0, 1, Nb); emit(1, 0, Nb); emit(1, 1, Mb);
+        }
+        return true;
+    }
+
+    if ((PATH < 0 || PATH == 1) && d.kind == K_PE) {
+        // reduced (w,u) = (p - e0, e1 - e0); orthonormal basis of the translation-free subspace of 3 points:
+        // h1 = (1,-1,0)/sqrt2, h2 = (1,1,-2)/sqrt6
+        const V3 w = x[0] - x[1], u = x[2] - x[1];
+        double H6[21], g6[6];
+#pragma unroll
+        for (int i = 0; i < 21; ++i) H6[i] = 0;
+        const double s = weight * mu;
+        pe_quotient_packed<6>(w, u, 0, 3, wantH ? s * bh : 0.0, wantH ? s * bg : 0.0, g6, H6);
+        out.E = b * (d.mult > 1 ? mu : 1.0) * weight;
+        const double kg = s * bg;
+        // c_w = (1,-1,0), c_u = (0,-1,1)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            out.g[a] = kg * g6[a];
+            out.g[6 + a] = kg * g6[3 + a];
+            out.g[3 + a] = -kg * (g6[a] + g6[3 + a]);
+        }
+        if (wantH) {
+            const double r2 = 1.4142135623730951, ir2 = 0.70710678118654752, r32 = 1.2247448713915890, ir6 = 0.40824829046386302;
+            const double T[2][2] = {{r2, 0.0}, {ir2, -r32}};
+            double M[21];
+            congruence_blocks<2>(T, H6, M);
+            if (projectSPD) {
+                VLocal<6> V6;
+                make_pd_packed<6>(M, V6);
+            }
+            const double Hm[3][2] = {{ir2, ir6}, {-ir2, ir6}, {0.0, -2.0 * ir6}};
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    double blk[9];
+                    expand_block<3, 2>(Hm, M, i, j, blk);
+                    emit(i, j, blk);
+                }
+        }
+        return true;
+    }
+
+    if (!(PATH < 0 || PATH == 0) || d.kind == K_PP || d.kind == K_PE) return true;
+    // ---- four-vertex kinds: reduced (w,u,v)
+    const bool isPT = (d.kind == K_PT);
+    const bool moll = (d.kind == K_EE_M || d.kind == K_PE_M || d.kind == K_PP_M);
+    V3 w, u, v;
+    if (isPT) { w = x[0] - x[1]; u = x[2] - x[1]; v = x[3] - x[1]; }
+    else { w = x[2] - x[0]; u = x[1] - x[0]; v = x[3] - x[2]; }
+    double H[45], g9[9];
+#pragma unroll
+    for (int i = 0; i < 45; ++i) H[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) g9[i] = 0;
+    double e = 1.0, qg = 0, qh = 0;
+    CrossN2 cm;
+    if (moll) {
+        const double eps_x = ee_mollifier_threshold(xr[0], xr[1], xr[2], xr[3]);
+        cm.init(u, v);
+        if (cm.N < eps_x) {
+            const double ie = 1.0 / eps_x, qq = cm.N * ie;
+            e = (-qq + 2.0) * qq;
+            qg = 2.0 * ie * (-ie * cm.N + 1.0);
+            qh = -2.0 * ie * ie;
+        }
+    }
+    const double We = weight * e;
+    // distance part: H += We (bh g g^T + bg hess d), g9 = grad d
+    if (d.kind == K_PT || d.kind == K_EE || d.kind == K_EE_M) triple_quotient_packed(w, u, v, wantH ? We * bh : 0.0, wantH ? We * bg : 0.0, g9, H);
+    else if (d.kind == K_PE_M) pe_quotient_packed<9>(w, v, 0, 6, wantH ? We * bh : 0.0, wantH ? We * bg : 0.0, g9, H);
+    else { // K_PP_M: d = |w|^2
+        g9[0] = 2.0 * w.x; g9[1] = 2.0 * w.y; g9[2] = 2.0 * w.z;
+        if (wantH) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = i; j < 3; ++j) H[SI<9>(i, j)] += We * bh * g9[i] * g9[j] + (i == j ? We * bg * 2.0 : 0.0);
+        }
+    }
+    double gr[9]; // reduced gradient of the row energy
+    if (moll) {
+        out.E = b * e * weight;
+        const double gc[9] = {0, 0, 0, cm.ga.x, cm.ga.y, cm.ga.z, cm.gb.x, cm.gb.y, cm.gb.z};
+#pragma unroll
+        for (int i = 0; i < 9; ++i) gr[i] = weight * ((e * bg) * g9[i] + (b * qg) * gc[i]);
+        if (wantH && (qg != 0.0 || qh != 0.0)) {
+            // + w [ b (qg hess c + qh gc gc^T) + bg qg (g gc^T + gc g^T) ]
+            const double k1 = weight * b * qg, k2 = weight * b * qh, k3 = weight * bg * qg;
+#pragma unroll
+            for (int i = 0; i < 9; ++i)
+#pragma unroll
+                for (int j = i; j < 9; ++j) H[SI<9>(i, j)] += k2 * gc[i] * gc[j] + k3 * (g9[i] * gc[j] + gc[i] * g9[j]);
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    H[SI<9>(3 + i, 6 + j)] += k1 * cm.Hab(i, j);
+                    if (j >= i) {
+                        H[SI<9>(3 + i, 3 + j)] += k1 * cm.Haa(i, j);
+                        H[SI<9>(6 + i, 6 + j)] += k1 * cm.Hbb(i, j);
+                    }
+                }
+        }
+    }
+    else {
+        out.E = b * weight;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) gr[i] = (weight * bg) * g9[i];
+    }
+    // gradient embedding g_i = sum_m c[m][i] gr[m]
+    if (isPT) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            out.g[a] = gr[a];
+            out.g[6 + a] = gr[3 + a];
+            out.g[9 + a] = gr[6 + a];
+            out.g[3 + a] = -(gr[a] + gr[3 + a] + gr[6 + a]);
+        }
+    }
+    else {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            out.g[a] = -(gr[a] + gr[3 + a]);      // a0: -w -u
+            out.g[3 + a] = gr[3 + a];             // a1: +u
+            out.g[6 + a] = gr[a] - gr[6 + a];     // b0: +w -v
+            out.g[9 + a] = gr[6 + a];             // b1: +v
+        }
+    }
+    if (!wantH) return true;
+    // Hadamard basis rows Hm[i][k] (k = 1..3) and T = c Hm
+    double M[45];
+    if (isPT) {
+        const double T[3][3] = {{1, 0, 1}, {1, -1, 0}, {0, -1, 1}};
+        congruence_blocks<3>(T, H, M);
+    }
+    else {
+        const double T[3][3] = {{0, -1, -1}, {-1, 0, -1}, {-1, 0, 1}};
+        congruence_blocks<3>(T, H, M);
+    }
+    if (projectSPD) make_pd_packed<9>(M, V9);
+    const double Hm[4][3] = {{0.5, 0.5, 0.5}, {-0.5, 0.5, -0.5}, {0.5, -0.5, -0.5}, {-0.5, -0.5, 0.5}};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            double blk[9];
+            expand_block<4, 3>(Hm, M, i, j, blk);
+            emit(i, j, blk);
+        }
+    return true;
+}
+
+// dense adaptor with the signature of row_EgH (pair_deriv.cuh): used by the host-side test shim
+struct DenseEmit {
+    double* H;
+    int n;
+    IDP_HD void operator()(int i, int j, const double* blk)
+    {
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) H[(3 * i + a) * n + 3 * j + b] = blk[3 * a + b];
+    }
+};
 IDP_HD bool row_EgH_lowrank(const RowDec& d, const V3* x, const V3* xr, double weight, double dHat2, double kappa,
     double xi2, bool projectSPD, double* E, double* g, double* H)
 {
-    return row_EgH(d, x, xr, weight, dHat2, kappa, xi2, projectSPD, E, g, H);
+    VLocal<9> V9;
+    RowOut out;
+    DenseEmit em{H, 3 * d.nv};
+    const bool ok = row_eval<-1>(d, x, xr, weight, dHat2, kappa, xi2, projectSPD, H != nullptr, V9, out, em);
+    if (!ok) return false;
+    if (E) *E = out.E;
+    if (g) for (int i = 0; i < 3 * d.nv; ++i) g[i] = out.g[i];
+    return true;
 }
+
 } // namespace idp
