@@ -176,3 +176,50 @@ def test_empty_constraint_set(gpu_ctx, cases):
     ptr, col, val = gpu_ctx.barrier_hessian(1e-12, KAPPA)
     assert len(col) == 0 and not ptr.any()
     assert not gpu_ctx.barrier_gradient(1e-12, KAPPA).any()
+
+
+def test_b2_dropin_operators(lib_built, orc, cases):
+    """The six operators of idp_b200/host/IPC_B200.h (reference signatures, mock JGSL containers) against the oracle."""
+    import ctypes as C
+    import os
+    import subprocess
+    from conftest import ROOT
+    src = os.path.join(ROOT, "tests", "host_shim", "b2_driver.cpp")
+    out = os.path.join(ROOT, "tests", "host_shim", "libb2_driver.so")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-o", out, src, "-L", os.path.join(ROOT, "idp_b200"),
+                           "-lidp_contact", "-Wl,-rpath," + os.path.join(ROOT, "idp_b200")])
+    drv = C.CDLL(out)
+    name, m, d, dhats = cases[1]
+    dh, thickness = dhats[-1], 0.0
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    cap = 400000
+    rows = np.zeros((cap, 4), np.int32); g = np.zeros((m.nV, 3)); dist2 = np.zeros(cap)
+    tcap = 40000000
+    tr = np.zeros(tcap, np.int32); tc = np.zeros(tcap, np.int32); tv = np.zeros(tcap)
+    n = C.c_int(0); E = C.c_double(0); nt = C.c_long(0); alpha = C.c_double(0); mn = C.c_double(0)
+    drv.b2_run.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                           C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p]
+    X = np.ascontiguousarray(m.X); X0 = np.ascontiguousarray(m.X0); dd = np.ascontiguousarray(d)
+    st = drv.b2_run(m.nV, P(X), P(X0), len(m.bnode), P(m.bnode), len(m.bedge), P(m.bedge), len(m.btri), P(m.btri), P(dd),
+                    dh * dh, KAPPA, thickness, C.byref(n), P(rows), cap, C.byref(E), P(g), C.byref(nt), P(tr), P(tc), P(tv), tcap,
+                    C.byref(alpha), P(dist2), C.byref(mn))
+    assert st == 0 and 0 < n.value < cap and nt.value < tcap
+    rows = rows[: n.value]
+    om = omesh(orc, m)
+    orows, oinfo, _, _ = orc.constraint_set(om, dh * dh)
+    assert np.array_equal(lexsorted(rows), lexsorted(orows))
+    w = np.ones(len(rows))
+    _, oE = orc.barrier(om, rows, w, dh * dh, KAPPA)
+    _, og = orc.barrier_gradient(om, rows, w, dh * dh, KAPPA)
+    assert abs((E.value - 0.25) - oE) <= RTOL * abs(oE) and rel(g, og) <= RTOL
+    import scipy.sparse as sp
+    A = sp.coo_matrix((tv[1:nt.value], (tr[1:nt.value], tc[1:nt.value])), shape=(3 * m.nV, 3 * m.nV)).tocsr()
+    assert (tr[0], tc[0], tv[0]) == (0, 0, 1.0)  # appended, not overwritten
+    optr, ocol, oval = orc.barrier_hessian(om, rows, w, dh * dh, KAPPA)["csr"]
+    B = sp.csr_matrix((oval, ocol, optr), shape=A.shape)
+    assert abs(A - B).max() <= RTOL * abs(B).max()
+    oc = orc.ccd(om, dd, 1.0, thickness)
+    assert alpha.value <= oc["step"] and abs(alpha.value - oc["step"]) <= 1e-6 * oc["step"]
+    od, omn = orc.min_dist2(om, rows, thickness)
+    assert np.array_equal(dist2[: n.value], od) and mn.value == omn
