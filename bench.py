@@ -197,7 +197,8 @@ def main():
     dhat2 = dhat * dhat
     ctx = ContactContext(local_rank)  # raises without the CUDA library / a device: no CPU fallback
     stream = torch.cuda.Stream()
-    ctx.set_stream(stream.cuda_stream)
+    if not os.environ.get("IDP_BENCH_OWN_STREAM"):
+        ctx.set_stream(stream.cuda_stream)
     if world > 1:
         uid = [ctx.unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
@@ -248,7 +249,8 @@ def main():
     for _ in range(args.warmup):
         pairs_w, info_w = step_resident()
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if not os.environ.get("IDP_BENCH_NO_SAMPLER"):
+        sampler.start()
     ctx.reset_counters()
     ms, wall_ms, pairs, info = timed(step_resident, args.steps)
     launches, lib_calls = ctx.launches()

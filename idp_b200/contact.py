@@ -19,7 +19,7 @@ STAGES = ["Compute_Constraint_Set_Build_Hash", "Compute_Constraint_Set_PT", "Com
           "Compute_Constraint_Set_Merge", "Compute_Barrier_EgH", "constructCSRMatrixFromTriplet",
           "Compute_Intersection_Free_StepSize_Build_Hash", "Compute_Intersection_Free_StepSize_PT",
           "Compute_Intersection_Free_StepSize_EE", "Compute_Min_Dist", "upload", "k_barrier", "k_query", "k_accd",
-          "k_classify"]
+          "k_classify", "nccl_collectives"]
 
 # every symbol include/idp_contact.h declares
 EXPORTS = ["idp_create", "idp_destroy", "idp_last_error", "idp_set_stream", "idp_set_mesh", "idp_declare_unsupported",

@@ -20,11 +20,11 @@ __device__ __forceinline__ V3 ldv4(const double4* __restrict__ p, int v)
 }
 
 // number of 3x3 blocks a row contributes: nv^2
-__global__ void k_row_block_counts(const Row4* __restrict__ rows, long n, int* __restrict__ cnt)
+__global__ void k_row_block_counts(const Row4* __restrict__ rows, long n, int rank, int nranks, int* __restrict__ cnt)
 {
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += (long)gridDim.x * blockDim.x) {
         int k = 0;
-        if (i < n) {
+        if (i < n && (i % nranks) == rank) { // rows are dealt round-robin to the ranks (uniform mix of row kinds)
             const Row4 r = rows[i];
             k = (r.a >= 0 || r.d >= 0) ? 16 : (r.c >= 0 ? 9 : 4); // IPC.h:1372-1387
         }
@@ -33,7 +33,7 @@ __global__ void k_row_block_counts(const Row4* __restrict__ rows, long n, int* _
 }
 
 struct BarrierArgs {
-    const Row4* rows; const double* weights; long rowBegin, rowEnd;
+    const Row4* rows; const double* weights; long rowBegin, rowEnd, rowStride;
     const double4* xp; const double4* x0p;
     double dHat2, kappa, xi2;
     int projectSPD;
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(128) k_barrier(BarrierArgs a)
 {
     extern __shared__ double sV[];
     double Eacc = 0;
-    for (long i = a.rowBegin + (long)blockIdx.x * blockDim.x + threadIdx.x; i < a.rowEnd; i += (long)gridDim.x * blockDim.x) {
+    for (long i = a.rowBegin + a.rowStride * ((long)blockIdx.x * blockDim.x + threadIdx.x); i < a.rowEnd; i += a.rowStride * (long)gridDim.x * blockDim.x) {
         const Row4 r = a.rows[i];
         const RowDec d = decode_row(r.a, r.b, r.c, r.d);
         const int path = (d.kind == K_PP) ? 2 : (d.kind == K_PE ? 1 : 0);
@@ -151,11 +151,12 @@ int barrier_eval(idp_ctx* c, double dhat2, double kappa, double thickness, int w
     if (c->nRows == 0) return IDP_OK;
     StageTimer tm(c, IDP_STAGE_BARRIER);
     IDP_CK(c, cudaMemsetAsync(c->counters.p + CNT_ERR_DIST, 0, sizeof(long long), c->stream));
-    const long rb = c->nRows * c->rank / c->nranks, re = c->nRows * (c->rank + 1) / c->nranks;
-    const long nMine = re - rb;
+    // rows are dealt round-robin: rank r evaluates rows r, r + P, r + 2P, ...
+    const long rb = c->rank, re = c->nRows;
+    const long nMine = c->nRows > c->rank ? (c->nRows - c->rank + c->nranks - 1) / c->nranks : 0;
     const unsigned grid = std::max(1u, std::min(blocks_for(nMine, 128), (unsigned)c->sm_count * 16));
     BarrierArgs a;
-    a.rows = c->rows.p; a.weights = c->weights.p; a.rowBegin = rb; a.rowEnd = re;
+    a.rows = c->rows.p; a.weights = c->weights.p; a.rowBegin = rb; a.rowEnd = re; a.rowStride = c->nranks;
     a.xp = c->xp.p; a.x0p = c->x0p.p;
     a.dHat2 = dhat2 + 2 * std::sqrt(dhat2) * thickness; // IPC.h:757
     a.kappa = kappa; a.xi2 = thickness * thickness; a.projectSPD = project_spd;
@@ -169,13 +170,12 @@ int barrier_eval(idp_ctx* c, double dhat2, double kappa, double thickness, int w
     if (want_h) {
         IDP_CK(c, c->rowBlkOff.reserve(c->nRows + 1));
         IDP_CK(c, c->segId.reserve(c->nRows + 1));
-        IDP_LAUNCH(c, k_row_block_counts, blocks_for(c->nRows + 1, 256), 256, 0, c->rows.p, c->nRows, c->segId.p);
+        IDP_LAUNCH(c, k_row_block_counts, blocks_for(c->nRows + 1, 256), 256, 0, c->rows.p, c->nRows, c->rank, c->nranks, c->segId.p);
         IDP_TRY(cub_scan_exclusive(c, c->segId.p, c->rowBlkOff.p, c->nRows + 1));
-        int ends[2];
-        IDP_CK(c, cudaMemcpyAsync(&ends[0], c->rowBlkOff.p + rb, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        IDP_CK(c, cudaMemcpyAsync(&ends[1], c->rowBlkOff.p + re, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        int ends[2] = {0, 0};
+        IDP_CK(c, cudaMemcpyAsync(&ends[1], c->rowBlkOff.p + c->nRows, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         IDP_CK(c, cudaStreamSynchronize(c->stream));
-        nBlocks = ends[1]; // offsets are global; a shard fills only its slice [ends[0], ends[1])
+        nBlocks = ends[1]; // offsets count only this rank's rows, so its blocks are contiguous in [0, nBlocks)
         IDP_CK(c, c->blkKey.reserve(std::max<long>(nBlocks, 1)));
         IDP_CK(c, c->blkIdx.reserve(std::max<long>(nBlocks, 1)));
         IDP_CK(c, c->blkVal.reserve(9 * (size_t)std::max<long>(nBlocks, 1)));

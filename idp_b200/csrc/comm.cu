@@ -11,6 +11,9 @@ typedef int (*fn_get_uid)(nccl_uid*);
 typedef int (*fn_init_rank)(void**, int, nccl_uid, int);
 typedef int (*fn_allreduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
 typedef int (*fn_destroy)(void*);
+typedef int (*fn_allgather)(const void*, void*, size_t, int, void*, cudaStream_t);
+typedef int (*fn_broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*fn_group)(void);
 typedef const char* (*fn_errstr)(int);
 
 struct NcclApi {
@@ -20,8 +23,25 @@ struct NcclApi {
     fn_allreduce allreduce = nullptr;
     fn_destroy destroy = nullptr;
     fn_errstr errstr = nullptr;
+    fn_allgather allgather = nullptr;
+    fn_broadcast broadcast = nullptr;
+    fn_group group_start = nullptr, group_end = nullptr;
 };
 static NcclApi g_nccl;
+
+// accumulates the device time of the collectives of one step into IDP_STAGE_COMM
+struct CommTimer {
+    idp_ctx* c;
+    CommTimer(idp_ctx* ctx) : c(ctx) { cudaEventRecord(c->kev0, c->stream); }
+    ~CommTimer()
+    {
+        cudaEventRecord(c->kev1, c->stream);
+        cudaEventSynchronize(c->kev1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c->kev0, c->kev1);
+        c->times.v[IDP_STAGE_COMM] += ms;
+    }
+};
 
 static bool load_nccl()
 {
@@ -37,13 +57,19 @@ static bool load_nccl()
     g_nccl.allreduce = (fn_allreduce)dlsym(g_nccl.h, "ncclAllReduce");
     g_nccl.destroy = (fn_destroy)dlsym(g_nccl.h, "ncclCommDestroy");
     g_nccl.errstr = (fn_errstr)dlsym(g_nccl.h, "ncclGetErrorString");
-    return g_nccl.get_uid && g_nccl.init_rank && g_nccl.allreduce && g_nccl.destroy;
+    g_nccl.allgather = (fn_allgather)dlsym(g_nccl.h, "ncclAllGather");
+    g_nccl.broadcast = (fn_broadcast)dlsym(g_nccl.h, "ncclBroadcast");
+    g_nccl.group_start = (fn_group)dlsym(g_nccl.h, "ncclGroupStart");
+    g_nccl.group_end = (fn_group)dlsym(g_nccl.h, "ncclGroupEnd");
+    return g_nccl.get_uid && g_nccl.init_rank && g_nccl.allreduce && g_nccl.destroy && g_nccl.allgather && g_nccl.broadcast &&
+           g_nccl.group_start && g_nccl.group_end;
 }
 
-// ncclDataType_t: ncclFloat64 = 8; ncclRedOp_t: ncclSum = 0, ncclMin = 4
+// ncclDataType_t: ncclFloat64 = 8; ncclRedOp_t: ncclSum = 0, ncclProd = 1, ncclMax = 2, ncclMin = 3, ncclAvg = 4
 int comm_allreduce_sum(idp_ctx* c, double* dev, long n)
 {
     if (!c->nccl_comm) return IDP_OK;
+    CommTimer tm(c);
     const int r = g_nccl.allreduce(dev, dev, (size_t)n, 8, 0, c->nccl_comm, c->stream);
     if (r != 0) return fail(c, IDP_ERR_NCCL, "NCCL error: %s at %s:%d", g_nccl.errstr ? g_nccl.errstr(r) : "?", __FILE__, __LINE__);
     return IDP_OK;
@@ -51,10 +77,46 @@ int comm_allreduce_sum(idp_ctx* c, double* dev, long n)
 int comm_allreduce_min(idp_ctx* c, double* dev, long n)
 {
     if (!c->nccl_comm) return IDP_OK;
-    const int r = g_nccl.allreduce(dev, dev, (size_t)n, 8, 4, c->nccl_comm, c->stream);
+    CommTimer tm(c);
+    const int r = g_nccl.allreduce(dev, dev, (size_t)n, 8, 3, c->nccl_comm, c->stream);
     if (r != 0) return fail(c, IDP_ERR_NCCL, "NCCL error: %s at %s:%d", g_nccl.errstr ? g_nccl.errstr(r) : "?", __FILE__, __LINE__);
     return IDP_OK;
 }
+// variable-size all-gather of constraint rows: every rank ends with the concatenation (in rank order) of all ranks' rows
+#define IDP_NCCL(c, call)                                                                                              \
+    do {                                                                                                               \
+        const int r__ = (call);                                                                                        \
+        if (r__ != 0) return fail(c, IDP_ERR_NCCL, "NCCL error: %s at %s:%d", g_nccl.errstr ? g_nccl.errstr(r__) : "?", __FILE__, __LINE__); \
+    } while (0)
+int comm_allgather_rows(idp_ctx* c, DBuf<Row4>& local, long nLocal, DBuf<Row4>& out, long* nTotal)
+{
+    CommTimer tm(c);
+    const int P = c->nranks;
+    long long* dcnt = c->counters.p + 8; // scratch slots (P <= 8)
+    if (P > 8) return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "at most 8 ranks", __FILE__, __LINE__);
+    long long mine = nLocal;
+    IDP_CK(c, cudaMemcpyAsync(dcnt + c->rank, &mine, sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+    IDP_NCCL(c, g_nccl.allgather(dcnt + c->rank, dcnt, 1, 4 /*ncclInt64*/, c->nccl_comm, c->stream));
+    long long cnt[8];
+    IDP_CK(c, cudaMemcpyAsync(cnt, dcnt, P * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    IDP_CK(c, cudaStreamSynchronize(c->stream));
+    long total = 0;
+    long off[9];
+    for (int r = 0; r < P; ++r) { off[r] = total; total += (long)cnt[r]; }
+    off[P] = total;
+    IDP_CK(c, out.reserve(std::max<long>(total, 1)));
+    IDP_NCCL(c, g_nccl.group_start());
+    for (int r = 0; r < P; ++r) {
+        if (cnt[r] == 0) continue;
+        const int rc = g_nccl.broadcast(r == c->rank ? (const void*)local.p : (const void*)(out.p + off[r]), out.p + off[r],
+            (size_t)cnt[r] * sizeof(Row4), 0 /*ncclChar*/, r, c->nccl_comm, c->stream);
+        if (rc != 0) { g_nccl.group_end(); return fail(c, IDP_ERR_NCCL, "NCCL error: %s at %s:%d", g_nccl.errstr ? g_nccl.errstr(rc) : "?", __FILE__, __LINE__); }
+    }
+    IDP_NCCL(c, g_nccl.group_end());
+    *nTotal = total;
+    return IDP_OK;
+}
+
 void comm_destroy(idp_ctx* c)
 {
     if (c->nccl_comm && g_nccl.destroy) g_nccl.destroy(c->nccl_comm);

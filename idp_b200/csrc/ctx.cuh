@@ -126,7 +126,7 @@ struct idp_ctx {
     idp::DBuf<unsigned char> cubTemp;
     idp::DBuf<long long> counters;      // device counters / flags (see enum in kernels)
     // ---- constraint set ----
-    idp::DBuf<idp::Row4> rowsA, rowsB, rowsD, rowsD2, rows;
+    idp::DBuf<idp::Row4> rowsA, rowsB, rowsD, rowsD2, rows, rowsG;
     idp::DBuf<int> runCounts;
     idp::DBuf<double> weights;
     long nRows = 0;
@@ -228,5 +228,6 @@ int assemble_csr(idp_ctx* c);
 int min_dist2(idp_ctx* c, double thickness, double* host_dist2, double* min_out);
 int ccd_step(idp_ctx* c, double thickness, double* alpha_inout, int keep_candidates);
 int cub_scan_exclusive(idp_ctx* c, const int* in, int* out, long n);
+int comm_allgather_rows(idp_ctx* c, DBuf<Row4>& local, long nLocal, DBuf<Row4>& out, long* nTotal);
 
 } // namespace idp

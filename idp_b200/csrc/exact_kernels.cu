@@ -672,6 +672,7 @@ int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
     const double dHat = std::sqrt(dhat2_in) + thickness; // IPC.h:53-54
     const double dHat2 = dHat * dHat;
     c->cs_dhat2 = dHat2;
+    c->times.v[IDP_STAGE_COMM] = 0;
     IDP_CK(c, cudaMemsetAsync(c->counters.p, 0, CNT_COUNT * sizeof(long long), c->stream));
 
     GridDesc g;
@@ -753,7 +754,18 @@ int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
         nB = (long)c->h_counters[CNT_ROWS_A];
         nD = (long)c->h_counters[CNT_ROWS_D];
     }
+    long nAg = nA, nBg = nB, nDg = nD;
+    if (c->nranks > 1 && c->nccl_comm) {
+        // every rank classified its own query range; gather the three row groups so that all ranks hold the whole set
+        IDP_TRY(comm_allgather_rows(c, c->rowsA, nA, c->rowsG, &nAg));
+        std::swap(c->rowsA.p, c->rowsG.p); std::swap(c->rowsA.cap, c->rowsG.cap);
+        IDP_TRY(comm_allgather_rows(c, c->rowsB, nB, c->rowsG, &nBg));
+        std::swap(c->rowsB.p, c->rowsG.p); std::swap(c->rowsB.cap, c->rowsG.cap);
+        IDP_TRY(comm_allgather_rows(c, c->rowsD, nD, c->rowsG, &nDg));
+        std::swap(c->rowsD.p, c->rowsG.p); std::swap(c->rowsD.cap, c->rowsG.cap);
+    }
     {
+        const long nA = nAg, nB = nBg, nD = nDg;
         StageTimer tm(c, IDP_STAGE_CCS_MERGE);
         // canonical order inside the two direct groups; key order for the merged group (IPC.h:599-654)
         IDP_TRY(sort_rows(c, c->rowsA.p, nA));

@@ -50,6 +50,7 @@ enum idp_stage {
     IDP_STAGE_K_QUERY = 12,         /* the last broad-phase query launch alone */
     IDP_STAGE_K_ACCD = 13,          /* the last additive-CCD launch alone */
     IDP_STAGE_K_CLASSIFY = 14,      /* the last classification launch alone */
+    IDP_STAGE_COMM = 15,            /* NCCL collectives, accumulated since the last idp_constraint_set */
     IDP_STAGE_COUNT = 16
 };
 
