@@ -88,7 +88,8 @@ int comm_allreduce_min(idp_ctx* c, double* dev, long n)
         const int r__ = (call);                                                                                        \
         if (r__ != 0) return fail(c, IDP_ERR_NCCL, "NCCL error: %s at %s:%d", g_nccl.errstr ? g_nccl.errstr(r__) : "?", __FILE__, __LINE__); \
     } while (0)
-int comm_allgather_rows(idp_ctx* c, DBuf<Row4>& local, long nLocal, DBuf<Row4>& out, long* nTotal)
+template <class T>
+static int allgatherv(idp_ctx* c, DBuf<T>& local, long nLocal, DBuf<T>& out, long* nTotal)
 {
     CommTimer tm(c);
     const int P = c->nranks;
@@ -109,13 +110,15 @@ int comm_allgather_rows(idp_ctx* c, DBuf<Row4>& local, long nLocal, DBuf<Row4>& 
     for (int r = 0; r < P; ++r) {
         if (cnt[r] == 0) continue;
         const int rc = g_nccl.broadcast(r == c->rank ? (const void*)local.p : (const void*)(out.p + off[r]), out.p + off[r],
-            (size_t)cnt[r] * sizeof(Row4), 0 /*ncclChar*/, r, c->nccl_comm, c->stream);
+            (size_t)cnt[r] * sizeof(T), 0 /*ncclChar*/, r, c->nccl_comm, c->stream);
         if (rc != 0) { g_nccl.group_end(); return fail(c, IDP_ERR_NCCL, "NCCL error: %s at %s:%d", g_nccl.errstr ? g_nccl.errstr(rc) : "?", __FILE__, __LINE__); }
     }
     IDP_NCCL(c, g_nccl.group_end());
     *nTotal = total;
     return IDP_OK;
 }
+int comm_allgather_rows(idp_ctx* c, DBuf<Row4>& local, long nLocal, DBuf<Row4>& out, long* nTotal) { return allgatherv(c, local, nLocal, out, nTotal); }
+int comm_allgather_keys(idp_ctx* c, DBuf<unsigned long long>& local, long nLocal, DBuf<unsigned long long>& out, long* nTotal) { return allgatherv(c, local, nLocal, out, nTotal); }
 
 void comm_destroy(idp_ctx* c)
 {

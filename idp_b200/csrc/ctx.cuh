@@ -128,6 +128,7 @@ struct idp_ctx {
     // ---- constraint set ----
     idp::DBuf<idp::Row4> rowsA, rowsB, rowsD, rowsD2, rows, rowsG;
     idp::DBuf<int> runCounts;
+    idp::DBuf<unsigned long long> keyA, keyB, keyD, keyTmp; // sort keys of the row groups
     idp::DBuf<double> weights;
     long nRows = 0;
     double cs_dhat2 = 0; // dHat2 stored in stencilInfo (after the thickness offset, IPC.h:53-54)
@@ -229,5 +230,6 @@ int min_dist2(idp_ctx* c, double thickness, double* host_dist2, double* min_out)
 int ccd_step(idp_ctx* c, double thickness, double* alpha_inout, int keep_candidates);
 int cub_scan_exclusive(idp_ctx* c, const int* in, int* out, long n);
 int comm_allgather_rows(idp_ctx* c, DBuf<Row4>& local, long nLocal, DBuf<Row4>& out, long* nTotal);
+int comm_allgather_keys(idp_ctx* c, DBuf<unsigned long long>& local, long nLocal, DBuf<unsigned long long>& out, long* nTotal);
 
 } // namespace idp

@@ -484,7 +484,15 @@ struct ClassifyArgs {
     double dHat2;
     Row4* rowsDirect; long capDirect; unsigned long long* cntDirect;
     Row4* rowsDup; long capDup; unsigned long long* cntDup;
+    // sort keys: direct rows are ordered by their candidate pair (query * nPartner + partner) = the reference's loop
+    // order with ascending partners; duplicate rows by the std::map key order of (k0,k1,k2), packed when 3*dupBits <= 64
+    unsigned long long* keysDirect; unsigned long long* keysDup; long long nPartner; int dupBits; long long nV;
 };
+__device__ __forceinline__ unsigned long long dup_key(const Row4& r, int bits, long long nV)
+{
+    const unsigned long long p = (unsigned long long)(nV - 1 - (long long)(-r.a - 1)); // k0 = -p-1 ascending <=> p descending
+    return (p << (2 * bits)) | ((unsigned long long)r.b << bits) | (unsigned long long)(r.c + 1);
+}
 __global__ void __launch_bounds__(256) k_classify_pt(ClassifyArgs a)
 {
     const long stride = (long)gridDim.x * blockDim.x;
@@ -492,8 +500,10 @@ __global__ void __launch_bounds__(256) k_classify_pt(ClassifyArgs a)
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nRound; i += stride) {
         bool direct = false, dup = false;
         Row4 r = {0, 0, 0, 0};
+        long long ckey = 0;
         if (i < a.nCand) {
             const int2 c = a.cand[i];
+            ckey = (long long)c.x * a.nPartner + c.y;
             const int vI = a.bnode[c.x];
             const int4 t = a.btri[c.y];
             const V3 p = ldv(a.xp, vI), t0 = ldv(a.xp, t.x), t1 = ldv(a.xp, t.y), t2 = ldv(a.xp, t.z);
@@ -515,9 +525,9 @@ __global__ void __launch_bounds__(256) k_classify_pt(ClassifyArgs a)
             }
         }
         long s = warp_append(direct, a.cntDirect, a.capDirect);
-        if (direct && s >= 0) a.rowsDirect[s] = r;
+        if (direct && s >= 0) { a.rowsDirect[s] = r; a.keysDirect[s] = (unsigned long long)ckey; }
         s = warp_append(dup, a.cntDup, a.capDup);
-        if (dup && s >= 0) a.rowsDup[s] = r;
+        if (dup && s >= 0) { if (a.dupBits) a.keysDup[s] = dup_key(r, a.dupBits, a.nV); else a.rowsDup[s] = r; }
     }
 }
 __global__ void __launch_bounds__(256) k_classify_ee(ClassifyArgs a)
@@ -527,8 +537,10 @@ __global__ void __launch_bounds__(256) k_classify_ee(ClassifyArgs a)
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nRound; i += stride) {
         bool direct = false, dup = false;
         Row4 r = {0, 0, 0, 0};
+        long long ckey = 0;
         if (i < a.nCand) {
             const int2 c = a.cand[i];
+            ckey = (long long)c.x * a.nPartner + c.y;
             const int2 ea = a.bedge[c.x], eb = a.bedge[c.y];
             const V3 a0 = ldv(a.xp, ea.x), a1 = ldv(a.xp, ea.y), b0 = ldv(a.xp, eb.x), b1 = ldv(a.xp, eb.y);
             const int ty = ee_type(a0, a1, b0, b1);
@@ -570,9 +582,25 @@ __global__ void __launch_bounds__(256) k_classify_ee(ClassifyArgs a)
             }
         }
         long s = warp_append(direct, a.cntDirect, a.capDirect);
-        if (direct && s >= 0) a.rowsDirect[s] = r;
+        if (direct && s >= 0) { a.rowsDirect[s] = r; a.keysDirect[s] = (unsigned long long)ckey; }
         s = warp_append(dup, a.cntDup, a.capDup);
-        if (dup && s >= 0) a.rowsDup[s] = r;
+        if (dup && s >= 0) { if (a.dupBits) a.keysDup[s] = dup_key(r, a.dupBits, a.nV); else a.rowsDup[s] = r; }
+    }
+}
+
+__global__ void k_emit_merged_keys(const unsigned long long* __restrict__ uniq, const int* __restrict__ counts, long n, int bits,
+    long long nV, Row4* __restrict__ out)
+{
+    const unsigned long long mask = (1ull << bits) - 1ull;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const unsigned long long k = uniq[i];
+        const long long p = nV - 1 - (long long)(k >> (2 * bits));
+        Row4 r;
+        r.a = (int)(-p - 1);
+        r.b = (int)((k >> bits) & mask);
+        r.c = (int)(k & mask) - 1;
+        r.d = -counts[i];
+        out[i] = r;
     }
 }
 
@@ -596,6 +624,25 @@ static int sort_rows(idp_ctx* c, Row4* rows, long n)
     IDP_CK(c, cub::DeviceMergeSort::SortKeys(nullptr, bytes, rows, (int)n, RowLess(), c->stream));
     IDP_CK(c, c->cubTemp.reserve(bytes));
     IDP_CK(c, cub::DeviceMergeSort::SortKeys(c->cubTemp.p, bytes, rows, (int)n, RowLess(), c->stream));
+    ++c->lib_launches;
+    return IDP_OK;
+}
+
+static int bits_for(unsigned long long maxval)
+{
+    int b = 1;
+    while (b < 64 && (maxval >> b)) ++b;
+    return b;
+}
+// stable radix sort of rows by 64-bit keys (in: rows/keys, out: rowsOut); bits = significant key bits
+static int sort_rows_by_key(idp_ctx* c, unsigned long long* keys, Row4* rows, Row4* rowsOut, long n, int bits)
+{
+    if (n == 0) return IDP_OK;
+    IDP_CK(c, c->keyTmp.reserve(n));
+    size_t bytes = 0;
+    IDP_CK(c, cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys, c->keyTmp.p, rows, rowsOut, (int)n, 0, bits, c->stream));
+    IDP_CK(c, c->cubTemp.reserve(bytes));
+    IDP_CK(c, cub::DeviceRadixSort::SortPairs(c->cubTemp.p, bytes, keys, c->keyTmp.p, rows, rowsOut, (int)n, 0, bits, c->stream));
     ++c->lib_launches;
     return IDP_OK;
 }
@@ -699,6 +746,9 @@ int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
     }
     unsigned long long* cnt = (unsigned long long*)c->counters.p;
     int qb, qe;
+    // duplicate (PP / PE) rows are merged by sorting a packed (nV-1-p, k1, k2+1) key when it fits 64 bits
+    const int vbits = bits_for((unsigned long long)c->nV);
+    const int dupBits = (3 * vbits <= 64) ? vbits : 0;
     {
         StageTimer tm(c, IDP_STAGE_CCS_PT);
         long nEntries = 0;
@@ -717,6 +767,9 @@ int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
         ca.xp = c->xp.p; ca.x0p = c->x0p.p; ca.dHat2 = dHat2;
         ca.rowsDirect = c->rowsA.p; ca.capDirect = (long)c->rowsA.cap; ca.cntDirect = cnt + CNT_ROWS_A;
         ca.rowsDup = c->rowsD.p; ca.capDup = (long)c->rowsD.cap; ca.cntDup = cnt + CNT_ROWS_D;
+        IDP_CK(c, c->keyA.reserve(std::max<long>(c->nCandPT, 1)));
+        IDP_CK(c, c->keyD.reserve(std::max<long>(c->nCandPT, 1)));
+        ca.keysDirect = c->keyA.p; ca.keysDup = c->keyD.p; ca.nPartner = c->nBT; ca.dupBits = dupBits; ca.nV = c->nV;
         if (c->nCandPT > 0) {
             KernelTimer kt(c, IDP_STAGE_K_CLASSIFY);
             IDP_LAUNCH(c, k_classify_pt, std::min(blocks_for(c->nCandPT, 256), (unsigned)c->sm_count * 16), 256, 0, ca);
@@ -745,6 +798,9 @@ int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
         ca.xp = c->xp.p; ca.x0p = c->x0p.p; ca.dHat2 = dHat2;
         ca.rowsDirect = c->rowsB.p; ca.capDirect = (long)c->rowsB.cap; ca.cntDirect = cnt + CNT_ROWS_A;
         ca.rowsDup = c->rowsD.p; ca.capDup = (long)c->rowsD.cap; ca.cntDup = cnt + CNT_ROWS_D;
+        IDP_CK(c, c->keyB.reserve(std::max<long>(c->nCandEE, 1)));
+        IDP_CK(c, c->keyD.reserve(std::max<long>(nD_pt + c->nCandEE, 1), true, c->stream));
+        ca.keysDirect = c->keyB.p; ca.keysDup = c->keyD.p; ca.nPartner = c->nBE; ca.dupBits = dupBits; ca.nV = c->nV;
         if (c->nCandEE > 0) {
             KernelTimer kt(c, IDP_STAGE_K_CLASSIFY);
             IDP_LAUNCH(c, k_classify_ee, std::min(blocks_for(c->nCandEE, 256), (unsigned)c->sm_count * 16), 256, 0, ca);
@@ -755,27 +811,60 @@ int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
         nD = (long)c->h_counters[CNT_ROWS_D];
     }
     long nAg = nA, nBg = nB, nDg = nD;
+    float mergeSort = 0;
+    {
+        StageTimer tm(c, IDP_STAGE_CCS_MERGE);
+        // direct groups: order by candidate pair (query-major, partner ascending) with one radix sort each. A shard's
+        // rows come from its own contiguous query range, so concatenating the sorted shards in rank order is globally sorted.
+        IDP_CK(c, c->rowsG.reserve(std::max<long>(std::max(nA, nB), 1)));
+        IDP_TRY(sort_rows_by_key(c, c->keyA.p, c->rowsA.p, c->rowsG.p, nA, bits_for((unsigned long long)c->nBN * (unsigned long long)c->nBT)));
+        std::swap(c->rowsA.p, c->rowsG.p); std::swap(c->rowsA.cap, c->rowsG.cap);
+        IDP_CK(c, c->rowsG.reserve(std::max<long>(nB, 1)));
+        IDP_TRY(sort_rows_by_key(c, c->keyB.p, c->rowsB.p, c->rowsG.p, nB, bits_for((unsigned long long)c->nBE * (unsigned long long)c->nBE)));
+        std::swap(c->rowsB.p, c->rowsG.p); std::swap(c->rowsB.cap, c->rowsG.cap);
+    }
+    mergeSort = c->times.v[IDP_STAGE_CCS_MERGE];
     if (c->nranks > 1 && c->nccl_comm) {
-        // every rank classified its own query range; gather the three row groups so that all ranks hold the whole set
         IDP_TRY(comm_allgather_rows(c, c->rowsA, nA, c->rowsG, &nAg));
         std::swap(c->rowsA.p, c->rowsG.p); std::swap(c->rowsA.cap, c->rowsG.cap);
         IDP_TRY(comm_allgather_rows(c, c->rowsB, nB, c->rowsG, &nBg));
         std::swap(c->rowsB.p, c->rowsG.p); std::swap(c->rowsB.cap, c->rowsG.cap);
-        IDP_TRY(comm_allgather_rows(c, c->rowsD, nD, c->rowsG, &nDg));
-        std::swap(c->rowsD.p, c->rowsG.p); std::swap(c->rowsD.cap, c->rowsG.cap);
+        if (dupBits) {
+            IDP_TRY(comm_allgather_keys(c, c->keyD, nD, c->keyTmp, &nDg));
+            std::swap(c->keyD.p, c->keyTmp.p); std::swap(c->keyD.cap, c->keyTmp.cap);
+        }
+        else {
+            IDP_TRY(comm_allgather_rows(c, c->rowsD, nD, c->rowsG, &nDg));
+            std::swap(c->rowsD.p, c->rowsG.p); std::swap(c->rowsD.cap, c->rowsG.cap);
+        }
     }
     {
         const long nA = nAg, nB = nBg, nD = nDg;
         StageTimer tm(c, IDP_STAGE_CCS_MERGE);
-        // canonical order inside the two direct groups; key order for the merged group (IPC.h:599-654)
-        IDP_TRY(sort_rows(c, c->rowsA.p, nA));
-        IDP_TRY(sort_rows(c, c->rowsB.p, nB));
         long nU = 0;
-        if (nD > 0) {
+        int* dRuns = (int*)(c->counters.p + CNT_RUNS);
+        if (nD > 0 && dupBits) {
+            // merged group: sort the packed keys (key order == std::map<VECTOR<int,4>> order, IPC.h:599-654), run lengths = multiplicities
+            IDP_CK(c, c->keyTmp.reserve(nD));
+            IDP_CK(c, c->keyA.reserve(nD));
+            IDP_CK(c, c->runCounts.reserve(nD));
+            size_t bytes = 0;
+            IDP_CK(c, cub::DeviceRadixSort::SortKeys(nullptr, bytes, c->keyD.p, c->keyTmp.p, (int)nD, 0, 3 * dupBits, c->stream));
+            IDP_CK(c, c->cubTemp.reserve(bytes));
+            IDP_CK(c, cub::DeviceRadixSort::SortKeys(c->cubTemp.p, bytes, c->keyD.p, c->keyTmp.p, (int)nD, 0, 3 * dupBits, c->stream));
+            IDP_CK(c, cub::DeviceRunLengthEncode::Encode(nullptr, bytes, c->keyTmp.p, c->keyA.p, c->runCounts.p, dRuns, (int)nD, c->stream));
+            IDP_CK(c, c->cubTemp.reserve(bytes));
+            IDP_CK(c, cub::DeviceRunLengthEncode::Encode(c->cubTemp.p, bytes, c->keyTmp.p, c->keyA.p, c->runCounts.p, dRuns, (int)nD, c->stream));
+            c->lib_launches += 2;
+            int runs = 0;
+            IDP_CK(c, cudaMemcpyAsync(&runs, dRuns, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+            IDP_CK(c, cudaStreamSynchronize(c->stream));
+            nU = runs;
+        }
+        else if (nD > 0) {
             IDP_TRY(sort_rows(c, c->rowsD.p, nD));
             IDP_CK(c, c->rowsD2.reserve(nD));
             IDP_CK(c, c->runCounts.reserve(nD));
-            int* dRuns = (int*)(c->counters.p + CNT_RUNS);
             size_t bytes = 0;
             IDP_CK(c, cub::DeviceRunLengthEncode::Encode(nullptr, bytes, c->rowsD.p, c->rowsD2.p, c->runCounts.p, dRuns, (int)nD, c->stream));
             IDP_CK(c, c->cubTemp.reserve(bytes));
@@ -791,10 +880,12 @@ int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
         IDP_CK(c, c->weights.reserve(std::max<long>(c->nRows, 1)));
         if (nA) IDP_CK(c, cudaMemcpyAsync(c->rows.p, c->rowsA.p, nA * sizeof(Row4), cudaMemcpyDeviceToDevice, c->stream));
         if (nB) IDP_CK(c, cudaMemcpyAsync(c->rows.p + nA, c->rowsB.p, nB * sizeof(Row4), cudaMemcpyDeviceToDevice, c->stream));
-        if (nU) IDP_LAUNCH(c, k_emit_merged, blocks_for(nU, 256), 256, 0, c->rowsD2.p, c->runCounts.p, nU, c->rows.p + nA + nB);
+        if (nU && dupBits) IDP_LAUNCH(c, k_emit_merged_keys, blocks_for(nU, 256), 256, 0, c->keyA.p, c->runCounts.p, nU, dupBits, (long long)c->nV, c->rows.p + nA + nB);
+        else if (nU) IDP_LAUNCH(c, k_emit_merged, blocks_for(nU, 256), 256, 0, c->rowsD2.p, c->runCounts.p, nU, c->rows.p + nA + nB);
         if (c->nRows) IDP_LAUNCH(c, k_fill_double, blocks_for(c->nRows, 256), 256, 0, c->weights.p, c->nRows, 1.0); // OIPC: weight 1 (IPC.h:656-660)
         IDP_CK(c, cudaGetLastError());
     }
+    c->times.v[IDP_STAGE_CCS_MERGE] += mergeSort;
     return IDP_OK;
 }
 
