@@ -313,6 +313,15 @@ __global__ void k_ccd_vertex_boxes(const int* __restrict__ bnode, int nBN, const
 // ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void cell_range(const GridDesc& g, const IBox& b, int lo[3], int hi[3])
 {
+    if (g.k == 1) { // static phase and most CCD grids: no division
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            lo[k] = clampi(b.lo[k], 0, g.n[k] - 1);
+            hi[k] = clampi(b.hi[k], 0, g.n[k] - 1);
+        }
+        return;
+    }
+#pragma unroll
     for (int k = 0; k < 3; ++k) {
         lo[k] = clampi(b.lo[k] / g.k, 0, g.n[k] - 1);
         hi[k] = clampi(b.hi[k] / g.k, 0, g.n[k] - 1);
@@ -659,6 +668,7 @@ static void choose_static_grid(const double lo[3], const double hi[3], double me
 {
     double h = std::max(meanEdge, radius);
     if (!(h > 0)) h = 1.0;
+    if (const char* e = getenv("IDP_CELL_SCALE")) h *= atof(e); // tuning knob (results do not depend on the grid)
     const double ext[3] = {hi[0] - lo[0] + 2 * radius, hi[1] - lo[1] + 2 * radius, hi[2] - lo[2] + 2 * radius};
     for (int iter = 0; iter < 64; ++iter) {
         double cells = 1;
