@@ -30,7 +30,7 @@ int idp_create(int device, idp_ctx** out)
     cudaEventCreate(&c->ev1);
     cudaEventCreate(&c->kev0);
     cudaEventCreate(&c->kev1);
-    if (c->counters.reserve(CNT_COUNT) != cudaSuccess) { delete c; return IDP_ERR_CUDA; }
+    if (c->counters.reserve(CNT_COUNT) != cudaSuccess || c->histScratch.reserve(64) != cudaSuccess) { delete c; return IDP_ERR_CUDA; }
     cudaMemset(c->counters.p, 0, CNT_COUNT * sizeof(long long));
     cudaMallocHost((void**)&c->h_counters, CNT_COUNT * sizeof(long long));
     cudaMallocHost((void**)&c->h_red, 64 * sizeof(double));
@@ -325,6 +325,7 @@ long idp_last_count(idp_ctx* c, int what)
     case 5: return c->ccd_iters;
     case 6: return c->nnz;
     case 7: return c->nBlocksUnique;
+    case 8: return device_alloc_counter();
     default: return 0;
     }
 }

@@ -88,8 +88,7 @@ int comm_allreduce_min(idp_ctx* c, double* dev, long n)
         const int r__ = (call);                                                                                        \
         if (r__ != 0) return fail(c, IDP_ERR_NCCL, "NCCL error: %s at %s:%d", g_nccl.errstr ? g_nccl.errstr(r__) : "?", __FILE__, __LINE__); \
     } while (0)
-template <class T>
-static int allgatherv(idp_ctx* c, DBuf<T>& local, long nLocal, DBuf<T>& out, long* nTotal)
+int comm_allgatherv(idp_ctx* c, const void* local, long nLocal, size_t elemSize, void** outPtr, size_t* outCap, long outOffset, long* nTotal)
 {
     CommTimer tm(c);
     const int P = c->nranks;
@@ -105,20 +104,29 @@ static int allgatherv(idp_ctx* c, DBuf<T>& local, long nLocal, DBuf<T>& out, lon
     long off[9];
     for (int r = 0; r < P; ++r) { off[r] = total; total += (long)cnt[r]; }
     off[P] = total;
-    IDP_CK(c, out.reserve(std::max<long>(total, 1)));
+    const size_t need = (size_t)(outOffset + total);
+    if (need > *outCap) { // grow, keeping the first outOffset elements
+        const size_t ncap = need + need / 8;
+        void* np = nullptr;
+        IDP_CK(c, cudaMalloc(&np, ncap * elemSize));
+        if (*outPtr && outOffset > 0) IDP_CK(c, cudaMemcpyAsync(np, *outPtr, (size_t)outOffset * elemSize, cudaMemcpyDeviceToDevice, c->stream));
+        IDP_CK(c, cudaStreamSynchronize(c->stream));
+        if (*outPtr) cudaFree(*outPtr);
+        *outPtr = np;
+        *outCap = ncap;
+    }
+    char* out = (char*)*outPtr + (size_t)outOffset * elemSize;
     IDP_NCCL(c, g_nccl.group_start());
     for (int r = 0; r < P; ++r) {
         if (cnt[r] == 0) continue;
-        const int rc = g_nccl.broadcast(r == c->rank ? (const void*)local.p : (const void*)(out.p + off[r]), out.p + off[r],
-            (size_t)cnt[r] * sizeof(T), 0 /*ncclChar*/, r, c->nccl_comm, c->stream);
+        char* dst = out + (size_t)off[r] * elemSize;
+        const int rc = g_nccl.broadcast(r == c->rank ? local : (const void*)dst, dst, (size_t)cnt[r] * elemSize, 0 /*ncclChar*/, r, c->nccl_comm, c->stream);
         if (rc != 0) { g_nccl.group_end(); return fail(c, IDP_ERR_NCCL, "NCCL error: %s at %s:%d", g_nccl.errstr ? g_nccl.errstr(rc) : "?", __FILE__, __LINE__); }
     }
     IDP_NCCL(c, g_nccl.group_end());
     *nTotal = total;
     return IDP_OK;
 }
-int comm_allgather_rows(idp_ctx* c, DBuf<Row4>& local, long nLocal, DBuf<Row4>& out, long* nTotal) { return allgatherv(c, local, nLocal, out, nTotal); }
-int comm_allgather_keys(idp_ctx* c, DBuf<unsigned long long>& local, long nLocal, DBuf<unsigned long long>& out, long* nTotal) { return allgatherv(c, local, nLocal, out, nTotal); }
 
 void comm_destroy(idp_ctx* c)
 {

@@ -49,6 +49,8 @@ struct GridDesc {
     int clampLat;   // 1: lattice indices are clamped to the grid (static phase); 0: reference semantics (CCD)
 };
 
+inline long& device_alloc_counter() { static long n = 0; return n; } // cudaMalloc calls made by DBuf (steady state: 0 per step)
+
 template <class T>
 struct DBuf {
     T* p = nullptr;
@@ -71,6 +73,7 @@ struct DBuf {
         T* np = nullptr;
         cudaError_t e = cudaMalloc((void**)&np, ncap * sizeof(T));
         if (e != cudaSuccess) return e;
+        ++device_alloc_counter();
         if (keep && p && cap) {
             e = cudaMemcpyAsync(np, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, s);
             if (e != cudaSuccess) return e;
@@ -119,7 +122,7 @@ struct idp_ctx {
     idp::DBuf<idp::PrimRec> recN, recE, recT;
     idp::DBuf<idp::IBox> boxNq, boxEq, boxEb, boxTb; // query boxes (inflated) and insert boxes
     idp::DBuf<idp::IBox> vbox;                        // per-vertex lattice box (CCD)
-    idp::DBuf<int> cellStart, cellCursor, entries;
+    idp::DBuf<int> cellStart, cellCursor, entries, largeList, histScratch;
     idp::DBuf<int2> candPT, candEE;
     long nCandPT = 0, nCandEE = 0;
     idp::DBuf<double> red;              // reduction scratch
@@ -229,7 +232,8 @@ int assemble_csr(idp_ctx* c);
 int min_dist2(idp_ctx* c, double thickness, double* host_dist2, double* min_out);
 int ccd_step(idp_ctx* c, double thickness, double* alpha_inout, int keep_candidates);
 int cub_scan_exclusive(idp_ctx* c, const int* in, int* out, long n);
-int comm_allgather_rows(idp_ctx* c, DBuf<Row4>& local, long nLocal, DBuf<Row4>& out, long* nTotal);
-int comm_allgather_keys(idp_ctx* c, DBuf<unsigned long long>& local, long nLocal, DBuf<unsigned long long>& out, long* nTotal);
+// variable-size all-gather of nLocal elements of elemSize bytes into *outPtr (capacity *outCap elements, grown and
+// preserved when too small) starting at element outOffset; *nTotal = sum over ranks
+int comm_allgatherv(idp_ctx* c, const void* local, long nLocal, size_t elemSize, void** outPtr, size_t* outCap, long outOffset, long* nTotal);
 
 } // namespace idp

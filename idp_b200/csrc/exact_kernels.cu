@@ -329,8 +329,31 @@ __device__ __forceinline__ void cell_range(const GridDesc& g, const IBox& b, int
 }
 // note: lattice indices are >= 0 on the paths that use k > 1 (CCD lattice origin is the global minimum), so integer
 // division is a monotone floor.
+//
+// Cell lists with ANCHOR insertion: every primitive is stored once, in the cell of the low corner of its box, provided
+// its box spans at most `emax` cells beyond that corner on every axis; the (few) larger ones go to a "large" list that
+// every query scans. A query then visits the cells [qlo - emax, qhi]: each pair is met exactly once, so the traversal
+// needs no de-duplication and touches one 64-byte record per visited primitive.
+struct EMax { int e[3]; };
+__global__ void k_extent_hist(const IBox* __restrict__ bbox, int nB, GridDesc g, int* __restrict__ hist)
+{
+    __shared__ int sh[48]; // 16 bins per axis
+    if (threadIdx.x < 48) sh[threadIdx.x] = 0;
+    __syncthreads();
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nB; b += gridDim.x * blockDim.x) {
+        int lo[3], hi[3];
+        cell_range(g, bbox[b], lo, hi);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) atomicAdd(&sh[16 * k + min(hi[k] - lo[k], 15)], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < 48 && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
+}
+// MULTI insertion (used for the swept CCD boxes, whose extents vary too much for anchor insertion to pay off): a
+// primitive is stored in every cell its box overlaps and a pair is accepted only in the componentwise max of the two
+// boxes' low corners, which again meets every pair exactly once.
 template <bool FILL>
-__global__ void k_cells(const IBox* __restrict__ bbox, int nB, GridDesc g, int* __restrict__ cellCountOrCursor, int* __restrict__ entries)
+__global__ void k_cells_multi(const IBox* __restrict__ bbox, int nB, GridDesc g, int* __restrict__ cellCountOrCursor, int* __restrict__ entries)
 {
     for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nB; b += gridDim.x * blockDim.x) {
         int lo[3], hi[3];
@@ -343,6 +366,22 @@ __global__ void k_cells(const IBox* __restrict__ bbox, int nB, GridDesc g, int* 
                     else atomicAdd(&cellCountOrCursor[row + ix], 1);
                 }
             }
+    }
+}
+template <bool FILL>
+__global__ void k_cells(const IBox* __restrict__ bbox, int nB, GridDesc g, EMax emax, int* __restrict__ cellCountOrCursor,
+    int* __restrict__ entries, int* __restrict__ large, int* __restrict__ largeCount)
+{
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nB; b += gridDim.x * blockDim.x) {
+        int lo[3], hi[3];
+        cell_range(g, bbox[b], lo, hi);
+        if (hi[0] - lo[0] > emax.e[0] || hi[1] - lo[1] > emax.e[1] || hi[2] - lo[2] > emax.e[2]) {
+            if (FILL) large[atomicAdd(largeCount, 1)] = b;
+            continue;
+        }
+        const long cell = ((long)lo[2] * g.n[1] + lo[1]) * g.n[0] + lo[0];
+        if (FILL) entries[atomicAdd(&cellCountOrCursor[cell], 1)] = b;
+        else atomicAdd(&cellCountOrCursor[cell], 1);
     }
 }
 
@@ -358,30 +397,82 @@ int cub_scan_exclusive(idp_ctx* c, const int* in, int* out, long n)
 
 static long grid_cells(const GridDesc& g) { return (long)g.n[0] * g.n[1] * g.n[2]; }
 
-// build cellStart (nCells + 1) and entries for the insert boxes bbox[0..nB)
-static int build_cells(idp_ctx* c, const IBox* bbox, int nB, const GridDesc& g, long* nEntries)
+#define IDP_LARGE_CAP 4096
+// Build cellStart (nCells + 1), entries and the large list for the insert boxes bbox[0..nB). Chooses the smallest
+// emax <= 3 that leaves at most IDP_LARGE_CAP primitives on the large list; if there is none the cells are coarsened
+// (g.k doubled: a cell is k^3 lattice voxels) and the choice is repeated.
+static int build_cells_multi(idp_ctx* c, const IBox* bbox, int nB, const GridDesc& g)
 {
     const long nc = grid_cells(g);
     IDP_CK(c, c->cellStart.reserve(nc + 1));
     IDP_CK(c, c->cellCursor.reserve(nc + 1));
     IDP_CK(c, cudaMemsetAsync(c->cellCursor.p, 0, (nc + 1) * sizeof(int), c->stream));
-    IDP_LAUNCH(c, k_cells<false>, blocks_for(nB, 256), 256, 0, bbox, nB, g, c->cellCursor.p, nullptr);
+    IDP_CK(c, cudaMemsetAsync((int*)c->histScratch.p + 48, 0, sizeof(int), c->stream)); // empty large list
+    IDP_LAUNCH(c, k_cells_multi<false>, blocks_for(nB, 256), 256, 0, bbox, nB, g, c->cellCursor.p, nullptr);
     IDP_TRY(cub_scan_exclusive(c, c->cellCursor.p, c->cellStart.p, nc + 1));
     int total = 0;
     IDP_CK(c, cudaMemcpyAsync(&total, c->cellStart.p + nc, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     IDP_CK(c, cudaStreamSynchronize(c->stream));
-    *nEntries = total;
     IDP_CK(c, c->entries.reserve((size_t)std::max(total, 1)));
+    IDP_CK(c, c->largeList.reserve(IDP_LARGE_CAP + 1));
     IDP_CK(c, cudaMemcpyAsync(c->cellCursor.p, c->cellStart.p, (nc + 1) * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
-    IDP_LAUNCH(c, k_cells<true>, blocks_for(nB, 256), 256, 0, bbox, nB, g, c->cellCursor.p, c->entries.p);
+    IDP_LAUNCH(c, k_cells_multi<true>, blocks_for(nB, 256), 256, 0, bbox, nB, g, c->cellCursor.p, c->entries.p);
     IDP_CK(c, cudaGetLastError());
+    return IDP_OK;
+}
+static int build_cells(idp_ctx* c, const IBox* bbox, int nB, GridDesc& g, const int latN[3], EMax* emaxOut, int* nLargeOut)
+{
+    int* dHist = (int*)c->histScratch.p; // 48 ints
+    int hist[48];
+    EMax em;
+    int emax = -1, nLarge = 0;
+    for (int attempt = 0; attempt < 12 && emax < 0; ++attempt) {
+        IDP_CK(c, cudaMemsetAsync(dHist, 0, 48 * sizeof(int), c->stream));
+        IDP_LAUNCH(c, k_extent_hist, std::min(blocks_for(nB, 256), (unsigned)c->sm_count * 8), 256, 0, bbox, nB, g, dHist);
+        IDP_CK(c, cudaMemcpyAsync(hist, dHist, sizeof(hist), cudaMemcpyDeviceToHost, c->stream));
+        IDP_CK(c, cudaStreamSynchronize(c->stream));
+        // per axis: smallest extension that leaves at most a third of the large-list budget beyond it
+        bool ok = true;
+        nLarge = 0;
+        for (int k = 0; k < 3 && ok; ++k) {
+            long above = nB;
+            em.e[k] = -1;
+            for (int e = 0; e <= 4; ++e) {
+                above -= hist[16 * k + e];
+                if (above <= IDP_LARGE_CAP / 3) { em.e[k] = e; nLarge += (int)above; break; }
+            }
+            ok = em.e[k] >= 0;
+        }
+        if (ok) { emax = 0; break; }
+        if (g.n[0] <= 1 && g.n[1] <= 1 && g.n[2] <= 1) { em.e[0] = em.e[1] = em.e[2] = 0; emax = 0; nLarge = 0; break; } // one cell holds everything
+        g.k *= 2;
+        for (int d = 0; d < 3; ++d) g.n[d] = std::max(1, (latN[d] + g.k) / g.k);
+    }
+    if (emax < 0) return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "broad-phase grid could not be sized", __FILE__, __LINE__);
+    const long nc = grid_cells(g);
+    IDP_CK(c, c->cellStart.reserve(nc + 1));
+    IDP_CK(c, c->cellCursor.reserve(nc + 1));
+    IDP_CK(c, c->largeList.reserve(IDP_LARGE_CAP + 1));
+    int* dLargeCount = (int*)c->histScratch.p + 48;
+    IDP_CK(c, cudaMemsetAsync(c->cellCursor.p, 0, (nc + 1) * sizeof(int), c->stream));
+    IDP_CK(c, cudaMemsetAsync(dLargeCount, 0, sizeof(int), c->stream));
+    IDP_LAUNCH(c, (k_cells<false>), blocks_for(nB, 256), 256, 0, bbox, nB, g, em, c->cellCursor.p, nullptr, nullptr, nullptr);
+    IDP_TRY(cub_scan_exclusive(c, c->cellCursor.p, c->cellStart.p, nc + 1));
+    IDP_CK(c, c->entries.reserve((size_t)std::max(nB, 1)));
+    IDP_CK(c, cudaMemcpyAsync(c->cellCursor.p, c->cellStart.p, (nc + 1) * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+    IDP_LAUNCH(c, (k_cells<true>), blocks_for(nB, 256), 256, 0, bbox, nB, g, em, c->cellCursor.p, c->entries.p, c->largeList.p, dLargeCount);
+    IDP_CK(c, cudaGetLastError());
+    *emaxOut = em;
+    *nLargeOut = nLarge;
     return IDP_OK;
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// broad-phase query: one warp per query primitive, lanes stride over the entries of each x-run of cells.
-// A pair is emitted from exactly one cell (componentwise max of the two boxes' low corners), so no de-duplication
-// pass is needed. Survivors are compacted with ballot/popc and appended with one atomic per warp batch.
+// broad-phase query: one warp per query primitive. The (y,z) rows of the visited cell block are contiguous runs of
+// `entries`; their bounds are fetched by the lanes in parallel, prefix-summed with shuffles, and the concatenated runs
+// are then walked 32 entries at a time (warp-level load-balanced search), so no lane idles on short rows and the row
+// bounds cost one memory round trip instead of one per row. Survivors are compacted with ballot/popc and appended with
+// one atomic per warp batch.
 // MODE bit0: 0 = point queries vs triangles, 1 = edge queries vs edges (partner index > query index);
 // MODE bit1: CCD (require lattice-box overlap = "shares a voxel" of the reference's hash)
 // ------------------------------------------------------------------------------------------------------------
@@ -391,8 +482,34 @@ struct QueryArgs {
     const int* cellStart; const int* entries;
     GridDesc g;
     double dist; // dHat (static) or thickness (CCD)
+    EMax emax; const int* large; const int* nLargePtr; // device count of the large list
     int2* out; long cap; unsigned long long* counter;
 };
+// (iy, iz, i): row and entry slot the pair was met in (MULTI insertion only: canonical-cell test)
+template <int MODE>
+__device__ __forceinline__ bool pair_passes(const QueryArgs& a, long q, int b, const PrimRec& qr, const IBox& qb, const V3& qL, const V3& qH,
+    const int* qlo, int iy, int iz, int i)
+{
+    if ((MODE & 1) && b <= (int)q) return false; // eJ > eI (IPC.h:384, SPATIAL_HASH.h:265)
+    if (MODE & 2) {
+        const IBox bb = a.bbox[b];
+        if (i >= 0) {
+            int blo[3], bhi[3];
+            cell_range(a.g, bb, blo, bhi);
+            if (max(qlo[1], blo[1]) != iy || max(qlo[2], blo[2]) != iz) return false;
+            const long c = ((long)iz * a.g.n[1] + iy) * a.g.n[0] + max(qlo[0], blo[0]);
+            if (i < a.cellStart[c] || i >= a.cellStart[c + 1]) return false;
+        }
+        if (!(qb.lo[0] <= bb.hi[0] && bb.lo[0] <= qb.hi[0] && qb.lo[1] <= bb.hi[1] && bb.lo[1] <= qb.hi[1] &&
+              qb.lo[2] <= bb.hi[2] && bb.lo[2] <= qb.hi[2])) return false;
+    }
+    const PrimRec br = a.brec[b];
+    bool ok;
+    if (MODE & 1) ok = !(qr.v[0] == br.v[0] || qr.v[0] == br.v[1] || qr.v[1] == br.v[0] || qr.v[1] == br.v[1]); // shared vertex (IPC.h:384)
+    else ok = !(qr.v[0] == br.v[0] || qr.v[0] == br.v[1] || qr.v[0] == br.v[2]);                                   // incident triangle (IPC.h:171)
+    ok = ok && !((qr.flags & 1) && (br.flags & 1));                                                                  // all Dirichlet (:172, :385)
+    return ok && aabb_gap_ok(qL, qH, mk3(br.lo[0], br.lo[1], br.lo[2]), mk3(br.hi[0], br.hi[1], br.hi[2]), a.dist);
+}
 template <int MODE>
 __global__ void __launch_bounds__(256) k_query(QueryArgs a)
 {
@@ -405,54 +522,60 @@ __global__ void __launch_bounds__(256) k_query(QueryArgs a)
         const IBox qb = a.qbox[q];
         int qlo[3], qhi[3];
         cell_range(a.g, qb, qlo, qhi);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) qlo[k] = max(qlo[k] - a.emax.e[k], 0);
         const V3 qL = mk3(qr.lo[0], qr.lo[1], qr.lo[2]), qH = mk3(qr.hi[0], qr.hi[1], qr.hi[2]);
-        for (int iz = qlo[2]; iz <= qhi[2]; ++iz)
-            for (int iy = qlo[1]; iy <= qhi[1]; ++iy) {
+        const int ny = qhi[1] - qlo[1] + 1, nRows = ny * (qhi[2] - qlo[2] + 1);
+        for (int rbase = 0; rbase < nRows; rbase += 32) {
+            const int r = rbase + lane;
+            int start = 0, len = 0;
+            if (r < nRows) {
+                const int iy = qlo[1] + r % ny, iz = qlo[2] + r / ny;
                 const long row = ((long)iz * a.g.n[1] + iy) * a.g.n[0];
-                const int start = a.cellStart[row + qlo[0]], end = a.cellStart[row + qhi[0] + 1];
-                for (int i0 = start; i0 < end; i0 += 32) {
-                    const int i = i0 + lane;
-                    bool hit = false;
-                    int b = -1;
-                    if (i < end) {
-                        b = a.entries[i];
-                        bool ok = (MODE & 1) ? (b > (int)q) : true;
-                        if (ok) {
-                            const IBox bb = a.bbox[b];
-                            int blo[3], bhi[3];
-                            cell_range(a.g, bb, blo, bhi);
-                            // canonical cell of the pair
-                            const int cy = max(qlo[1], blo[1]), cz = max(qlo[2], blo[2]), cx = max(qlo[0], blo[0]);
-                            ok = (cy == iy) && (cz == iz);
-                            if (ok) {
-                                const int cs = a.cellStart[row + cx], ce = a.cellStart[row + cx + 1];
-                                ok = (i >= cs) && (i < ce);
-                            }
-                            if (ok && (MODE & 2)) {
-                                ok = qb.lo[0] <= bb.hi[0] && bb.lo[0] <= qb.hi[0] && qb.lo[1] <= bb.hi[1] && bb.lo[1] <= qb.hi[1] &&
-                                     qb.lo[2] <= bb.hi[2] && bb.lo[2] <= qb.hi[2];
-                            }
-                            if (ok) {
-                                const PrimRec br = a.brec[b];
-                                if (MODE & 1) {
-                                    // shared vertex (IPC.h:384) / all four Dirichlet (:385)
-                                    ok = !(qr.v[0] == br.v[0] || qr.v[0] == br.v[1] || qr.v[1] == br.v[0] || qr.v[1] == br.v[1]);
-                                }
-                                else {
-                                    // incident triangle (IPC.h:171) / all Dirichlet (:172)
-                                    ok = !(qr.v[0] == br.v[0] || qr.v[0] == br.v[1] || qr.v[0] == br.v[2]);
-                                }
-                                ok = ok && !((qr.flags & 1) && (br.flags & 1));
-                                if (ok) {
-                                    hit = aabb_gap_ok(qL, qH, mk3(br.lo[0], br.lo[1], br.lo[2]), mk3(br.hi[0], br.hi[1], br.hi[2]), a.dist);
-                                }
-                            }
-                        }
-                    }
-                    const long slot = warp_append(hit, a.counter, a.cap);
-                    if (hit && slot >= 0) a.out[slot] = make_int2((int)q, b);
-                }
+                start = a.cellStart[row + qlo[0]];
+                len = a.cellStart[row + qhi[0] + 1] - start;
             }
+            int scan = len; // inclusive prefix sum over the lanes
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, scan, o);
+                if (lane >= o) scan += v;
+            }
+            const int total = __shfl_sync(0xffffffffu, scan, 31);
+            const int excl = scan - len;
+            for (int t0 = 0; t0 < total; t0 += 32) {
+                const int t = t0 + lane;
+                int lo = 0, hi = 31; // first lane j with scan_j > t
+#pragma unroll
+                for (int step = 0; step < 5; ++step) {
+                    const int mid = (lo + hi) >> 1;
+                    const int sm = __shfl_sync(0xffffffffu, scan, mid);
+                    if (sm > t) hi = mid;
+                    else lo = mid + 1;
+                }
+                const int st = __shfl_sync(0xffffffffu, start, lo), ex = __shfl_sync(0xffffffffu, excl, lo);
+                bool hit = false;
+                int b = -1;
+                if (t < total) {
+                    const int i = st + (t - ex), rr = rbase + lo;
+                    b = a.entries[i];
+                    hit = pair_passes<MODE>(a, q, b, qr, qb, qL, qH, qlo, qlo[1] + rr % ny, qlo[2] + rr / ny, i);
+                }
+                const long slot = warp_append(hit, a.counter, a.cap);
+                if (hit && slot >= 0) a.out[slot] = make_int2((int)q, b);
+            }
+        }
+        const int nLarge = *a.nLargePtr;
+        for (int l0 = 0; l0 < nLarge; l0 += 32) { // primitives too large for anchor insertion
+            bool hit = false;
+            int b = -1;
+            if (l0 + lane < nLarge) {
+                b = a.large[l0 + lane];
+                hit = pair_passes<MODE>(a, q, b, qr, qb, qL, qH, qlo, 0, 0, -1);
+            }
+            const long slot = warp_append(hit, a.counter, a.cap);
+            if (hit && slot >= 0) a.out[slot] = make_int2((int)q, b);
+        }
     }
 }
 
@@ -734,6 +857,7 @@ int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
 
     GridDesc g;
     PrepArgs pa;
+    int latN[3] = {1, 1, 1};
     {
         StageTimer tm(c, IDP_STAGE_CCS_BUILD_HASH);
         double meanEdge = 0, lo[3], hi[3];
@@ -744,6 +868,7 @@ int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
         // conservative query radius: the exact predicate (AABB gap <= dHat) is applied afterwards
         const double radius = dHat * (1.0 + 1e-9) + amax * 1e-13;
         choose_static_grid(lo, hi, meanEdge, radius, g);
+        for (int k = 0; k < 3; ++k) latN[k] = g.n[k];
         pa.bnode = c->bnode.p; pa.bedge = c->bedge.p; pa.btri = c->btri.p; pa.dbc = c->dbc.p;
         pa.xp = c->xp.p; pa.dp = nullptr; pa.g = g; pa.radius = radius; pa.vbox = nullptr;
         IDP_CK(c, c->recN.reserve(c->nBN)); IDP_CK(c, c->boxNq.reserve(c->nBN));
@@ -761,17 +886,17 @@ int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
     const int dupBits = (3 * vbits <= 64) ? vbits : 0;
     {
         StageTimer tm(c, IDP_STAGE_CCS_PT);
-        long nEntries = 0;
-        IDP_TRY(build_cells(c, c->boxTb.p, c->nBT, g, &nEntries));
+        EMax emax; int nLarge = 0;
+        IDP_TRY(build_cells(c, c->boxTb.p, c->nBT, g, latN, &emax, &nLarge));
         shard_range(c, c->nBN, &qb, &qe);
         QueryArgs qa;
         qa.qrec = c->recN.p; qa.qbox = c->boxNq.p; qa.qBegin = qb; qa.qEnd = qe;
         qa.brec = c->recT.p; qa.bbox = c->boxTb.p; qa.cellStart = c->cellStart.p; qa.entries = c->entries.p;
-        qa.g = g; qa.dist = dHat;
+        qa.g = g; qa.dist = dHat; qa.emax = emax; qa.large = c->largeList.p; qa.nLargePtr = (const int*)c->histScratch.p + 48;
         IDP_TRY(run_query<0>(c, qa, c->candPT, &c->nCandPT));
         // classification
         IDP_CK(c, c->rowsA.reserve(std::max<long>(c->nCandPT, 1)));
-        IDP_CK(c, c->rowsD.reserve(std::max<long>(c->nCandPT, 1)));
+        if (!dupBits) IDP_CK(c, c->rowsD.reserve(std::max<long>(c->nCandPT, 1)));
         ClassifyArgs ca;
         ca.cand = c->candPT.p; ca.nCand = c->nCandPT; ca.bnode = c->bnode.p; ca.bedge = c->bedge.p; ca.btri = c->btri.p;
         ca.xp = c->xp.p; ca.x0p = c->x0p.p; ca.dHat2 = dHat2;
@@ -780,6 +905,7 @@ int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
         IDP_CK(c, c->keyA.reserve(std::max<long>(c->nCandPT, 1)));
         IDP_CK(c, c->keyD.reserve(std::max<long>(c->nCandPT, 1)));
         ca.keysDirect = c->keyA.p; ca.keysDup = c->keyD.p; ca.nPartner = c->nBT; ca.dupBits = dupBits; ca.nV = c->nV;
+        if (dupBits) ca.capDup = (long)c->keyD.cap;
         if (c->nCandPT > 0) {
             KernelTimer kt(c, IDP_STAGE_K_CLASSIFY);
             IDP_LAUNCH(c, k_classify_pt, std::min(blocks_for(c->nCandPT, 256), (unsigned)c->sm_count * 16), 256, 0, ca);
@@ -792,16 +918,16 @@ int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
     long nB = 0, nD = 0;
     {
         StageTimer tm(c, IDP_STAGE_CCS_EE);
-        long nEntries = 0;
-        IDP_TRY(build_cells(c, c->boxEb.p, c->nBE, g, &nEntries));
+        EMax emax; int nLarge = 0;
+        IDP_TRY(build_cells(c, c->boxEb.p, c->nBE, g, latN, &emax, &nLarge));
         shard_range(c, c->nBE, &qb, &qe);
         QueryArgs qa;
         qa.qrec = c->recE.p; qa.qbox = c->boxEq.p; qa.qBegin = qb; qa.qEnd = qe;
         qa.brec = c->recE.p; qa.bbox = c->boxEb.p; qa.cellStart = c->cellStart.p; qa.entries = c->entries.p;
-        qa.g = g; qa.dist = dHat;
+        qa.g = g; qa.dist = dHat; qa.emax = emax; qa.large = c->largeList.p; qa.nLargePtr = (const int*)c->histScratch.p + 48;
         IDP_TRY(run_query<1>(c, qa, c->candEE, &c->nCandEE));
         IDP_CK(c, c->rowsB.reserve(std::max<long>(c->nCandEE, 1)));
-        IDP_CK(c, c->rowsD.reserve(std::max<long>(nD_pt + c->nCandEE, 1), true, c->stream));
+        if (!dupBits) IDP_CK(c, c->rowsD.reserve(std::max<long>(nD_pt + c->nCandEE, 1), true, c->stream));
         IDP_CK(c, cudaMemsetAsync(c->counters.p + CNT_ROWS_A, 0, sizeof(long long), c->stream));
         ClassifyArgs ca;
         ca.cand = c->candEE.p; ca.nCand = c->nCandEE; ca.bnode = c->bnode.p; ca.bedge = c->bedge.p; ca.btri = c->btri.p;
@@ -811,6 +937,7 @@ int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
         IDP_CK(c, c->keyB.reserve(std::max<long>(c->nCandEE, 1)));
         IDP_CK(c, c->keyD.reserve(std::max<long>(nD_pt + c->nCandEE, 1), true, c->stream));
         ca.keysDirect = c->keyB.p; ca.keysDup = c->keyD.p; ca.nPartner = c->nBE; ca.dupBits = dupBits; ca.nV = c->nV;
+        if (dupBits) ca.capDup = (long)c->keyD.cap;
         if (c->nCandEE > 0) {
             KernelTimer kt(c, IDP_STAGE_K_CLASSIFY);
             IDP_LAUNCH(c, k_classify_ee, std::min(blocks_for(c->nCandEE, 256), (unsigned)c->sm_count * 16), 256, 0, ca);
@@ -820,33 +947,40 @@ int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
         nB = (long)c->h_counters[CNT_ROWS_A];
         nD = (long)c->h_counters[CNT_ROWS_D];
     }
+    // ---- merge (IPC.h:571-661). No buffer is swapped or re-sized here in the steady state: repeated calls reuse the same
+    // allocations (cudaMalloc / cudaFree of multi-GB buffers would dominate the step).
+    const bool sharded = c->nranks > 1 && c->nccl_comm;
     long nAg = nA, nBg = nB, nDg = nD;
     float mergeSort = 0;
+    IDP_CK(c, c->rows.reserve(std::max<long>(nA + nB + nD, 1)));
     {
         StageTimer tm(c, IDP_STAGE_CCS_MERGE);
-        // direct groups: order by candidate pair (query-major, partner ascending) with one radix sort each. A shard's
-        // rows come from its own contiguous query range, so concatenating the sorted shards in rank order is globally sorted.
-        IDP_CK(c, c->rowsG.reserve(std::max<long>(std::max(nA, nB), 1)));
-        IDP_TRY(sort_rows_by_key(c, c->keyA.p, c->rowsA.p, c->rowsG.p, nA, bits_for((unsigned long long)c->nBN * (unsigned long long)c->nBT)));
-        std::swap(c->rowsA.p, c->rowsG.p); std::swap(c->rowsA.cap, c->rowsG.cap);
-        IDP_CK(c, c->rowsG.reserve(std::max<long>(nB, 1)));
-        IDP_TRY(sort_rows_by_key(c, c->keyB.p, c->rowsB.p, c->rowsG.p, nB, bits_for((unsigned long long)c->nBE * (unsigned long long)c->nBE)));
-        std::swap(c->rowsB.p, c->rowsG.p); std::swap(c->rowsB.cap, c->rowsG.cap);
+        // direct groups: order by candidate pair (query-major, partner ascending = the reference's loop order) with one
+        // radix sort each, written straight into their final place when there is a single rank. A shard's rows come from
+        // its own contiguous query range, so concatenating the sorted shards in rank order is globally sorted.
+        Row4* dstA = c->rows.p;
+        Row4* dstB = c->rows.p + nA;
+        if (sharded) {
+            IDP_CK(c, c->rowsG.reserve(std::max<long>(nA + nB, 1)));
+            dstA = c->rowsG.p;
+            dstB = c->rowsG.p + nA;
+        }
+        IDP_TRY(sort_rows_by_key(c, c->keyA.p, c->rowsA.p, dstA, nA, bits_for((unsigned long long)c->nBN * (unsigned long long)c->nBT)));
+        IDP_TRY(sort_rows_by_key(c, c->keyB.p, c->rowsB.p, dstB, nB, bits_for((unsigned long long)c->nBE * (unsigned long long)c->nBE)));
     }
     mergeSort = c->times.v[IDP_STAGE_CCS_MERGE];
-    if (c->nranks > 1 && c->nccl_comm) {
-        IDP_TRY(comm_allgather_rows(c, c->rowsA, nA, c->rowsG, &nAg));
-        std::swap(c->rowsA.p, c->rowsG.p); std::swap(c->rowsA.cap, c->rowsG.cap);
-        IDP_TRY(comm_allgather_rows(c, c->rowsB, nB, c->rowsG, &nBg));
-        std::swap(c->rowsB.p, c->rowsG.p); std::swap(c->rowsB.cap, c->rowsG.cap);
+    unsigned long long* dupKeys = c->keyD.p;
+    if (sharded) {
+        IDP_TRY(comm_allgatherv(c, c->rowsG.p, nA, sizeof(Row4), (void**)&c->rows.p, &c->rows.cap, 0, &nAg));
+        IDP_TRY(comm_allgatherv(c, c->rowsG.p + nA, nB, sizeof(Row4), (void**)&c->rows.p, &c->rows.cap, nAg, &nBg));
         if (dupBits) {
-            IDP_TRY(comm_allgather_keys(c, c->keyD, nD, c->keyTmp, &nDg));
-            std::swap(c->keyD.p, c->keyTmp.p); std::swap(c->keyD.cap, c->keyTmp.cap);
+            IDP_TRY(comm_allgatherv(c, c->keyD.p, nD, sizeof(unsigned long long), (void**)&c->keyB.p, &c->keyB.cap, 0, &nDg));
+            dupKeys = c->keyB.p;
         }
         else {
-            IDP_TRY(comm_allgather_rows(c, c->rowsD, nD, c->rowsG, &nDg));
-            std::swap(c->rowsD.p, c->rowsG.p); std::swap(c->rowsD.cap, c->rowsG.cap);
+            IDP_TRY(comm_allgatherv(c, c->rowsD.p, nD, sizeof(Row4), (void**)&c->rowsG.p, &c->rowsG.cap, 0, &nDg));
         }
+        IDP_CK(c, c->rows.reserve(std::max<long>(nAg + nBg + nDg, 1), true, c->stream));
     }
     {
         const long nA = nAg, nB = nBg, nD = nDg;
@@ -859,9 +993,9 @@ int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
             IDP_CK(c, c->keyA.reserve(nD));
             IDP_CK(c, c->runCounts.reserve(nD));
             size_t bytes = 0;
-            IDP_CK(c, cub::DeviceRadixSort::SortKeys(nullptr, bytes, c->keyD.p, c->keyTmp.p, (int)nD, 0, 3 * dupBits, c->stream));
+            IDP_CK(c, cub::DeviceRadixSort::SortKeys(nullptr, bytes, dupKeys, c->keyTmp.p, (int)nD, 0, 3 * dupBits, c->stream));
             IDP_CK(c, c->cubTemp.reserve(bytes));
-            IDP_CK(c, cub::DeviceRadixSort::SortKeys(c->cubTemp.p, bytes, c->keyD.p, c->keyTmp.p, (int)nD, 0, 3 * dupBits, c->stream));
+            IDP_CK(c, cub::DeviceRadixSort::SortKeys(c->cubTemp.p, bytes, dupKeys, c->keyTmp.p, (int)nD, 0, 3 * dupBits, c->stream));
             IDP_CK(c, cub::DeviceRunLengthEncode::Encode(nullptr, bytes, c->keyTmp.p, c->keyA.p, c->runCounts.p, dRuns, (int)nD, c->stream));
             IDP_CK(c, c->cubTemp.reserve(bytes));
             IDP_CK(c, cub::DeviceRunLengthEncode::Encode(c->cubTemp.p, bytes, c->keyTmp.p, c->keyA.p, c->runCounts.p, dRuns, (int)nD, c->stream));
@@ -872,13 +1006,14 @@ int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
             nU = runs;
         }
         else if (nD > 0) {
-            IDP_TRY(sort_rows(c, c->rowsD.p, nD));
+            Row4* dupRows = sharded ? c->rowsG.p : c->rowsD.p;
+            IDP_TRY(sort_rows(c, dupRows, nD));
             IDP_CK(c, c->rowsD2.reserve(nD));
             IDP_CK(c, c->runCounts.reserve(nD));
             size_t bytes = 0;
-            IDP_CK(c, cub::DeviceRunLengthEncode::Encode(nullptr, bytes, c->rowsD.p, c->rowsD2.p, c->runCounts.p, dRuns, (int)nD, c->stream));
+            IDP_CK(c, cub::DeviceRunLengthEncode::Encode(nullptr, bytes, dupRows, c->rowsD2.p, c->runCounts.p, dRuns, (int)nD, c->stream));
             IDP_CK(c, c->cubTemp.reserve(bytes));
-            IDP_CK(c, cub::DeviceRunLengthEncode::Encode(c->cubTemp.p, bytes, c->rowsD.p, c->rowsD2.p, c->runCounts.p, dRuns, (int)nD, c->stream));
+            IDP_CK(c, cub::DeviceRunLengthEncode::Encode(c->cubTemp.p, bytes, dupRows, c->rowsD2.p, c->runCounts.p, dRuns, (int)nD, c->stream));
             ++c->lib_launches;
             int runs = 0;
             IDP_CK(c, cudaMemcpyAsync(&runs, dRuns, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -886,10 +1021,7 @@ int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
             nU = runs;
         }
         c->nRows = nA + nB + nU;
-        IDP_CK(c, c->rows.reserve(std::max<long>(c->nRows, 1)));
         IDP_CK(c, c->weights.reserve(std::max<long>(c->nRows, 1)));
-        if (nA) IDP_CK(c, cudaMemcpyAsync(c->rows.p, c->rowsA.p, nA * sizeof(Row4), cudaMemcpyDeviceToDevice, c->stream));
-        if (nB) IDP_CK(c, cudaMemcpyAsync(c->rows.p + nA, c->rowsB.p, nB * sizeof(Row4), cudaMemcpyDeviceToDevice, c->stream));
         if (nU && dupBits) IDP_LAUNCH(c, k_emit_merged_keys, blocks_for(nU, 256), 256, 0, c->keyA.p, c->runCounts.p, nU, dupBits, (long long)c->nV, c->rows.p + nA + nB);
         else if (nU) IDP_LAUNCH(c, k_emit_merged, blocks_for(nU, 256), 256, 0, c->rowsD2.p, c->runCounts.p, nU, c->rows.p + nA + nB);
         if (c->nRows) IDP_LAUNCH(c, k_fill_double, blocks_for(c->nRows, 256), 256, 0, c->weights.p, c->nRows, 1.0); // OIPC: weight 1 (IPC.h:656-660)
@@ -1051,6 +1183,7 @@ int ccd_step(idp_ctx* c, double thickness, double* alpha_inout, int keep_candida
     IDP_CK(c, cudaMemsetAsync(c->counters.p, 0, CNT_COUNT * sizeof(long long), c->stream));
     GridDesc g;
     PrepArgs pa;
+    int latN[3] = {1, 1, 1};
     {
         StageTimer tm(c, IDP_STAGE_CCD_BUILD_HASH);
         double voxelSize = 1.0;
@@ -1078,8 +1211,9 @@ int ccd_step(idp_ctx* c, double thickness, double* alpha_inout, int keep_candida
         IDP_TRY(node_bbox(c, 1, alpha, lo, hi));
         const double half = thickness / 2;
         for (int k = 0; k < 3; ++k) { lo[k] -= half; hi[k] += half; } // :502-503
-        long latN[3];
-        ccd_set_grid(lo, hi, voxelSize, g, latN);
+        long latNl[3];
+        ccd_set_grid(lo, hi, voxelSize, g, latNl);
+        for (int k = 0; k < 3; ++k) latN[k] = (int)latNl[k];
         IDP_CK(c, c->vbox.reserve(c->nV));
         IDP_LAUNCH(c, k_ccd_vertex_boxes, blocks_for(c->nBN, 256), 256, 0, c->bnode.p, c->nBN, c->xp.p, c->dp.p, alpha, half, g, c->vbox.p);
         pa.bnode = c->bnode.p; pa.bedge = c->bedge.p; pa.btri = c->btri.p; pa.dbc = c->dbc.p;
@@ -1105,13 +1239,13 @@ int ccd_step(idp_ctx* c, double thickness, double* alpha_inout, int keep_candida
     int qb, qe;
     {
         StageTimer tm(c, IDP_STAGE_CCD_PT);
-        long nEntries = 0;
-        IDP_TRY(build_cells(c, c->boxTb.p, c->nBT, g, &nEntries));
+        EMax emax = {{0, 0, 0}};
+        IDP_TRY(build_cells_multi(c, c->boxTb.p, c->nBT, g));
         shard_range(c, c->nBN, &qb, &qe);
         QueryArgs qa;
         qa.qrec = c->recN.p; qa.qbox = c->boxNq.p; qa.qBegin = qb; qa.qEnd = qe;
         qa.brec = c->recT.p; qa.bbox = c->boxTb.p; qa.cellStart = c->cellStart.p; qa.entries = c->entries.p;
-        qa.g = g; qa.dist = thickness;
+        qa.g = g; qa.dist = thickness; qa.emax = emax; qa.large = c->largeList.p; qa.nLargePtr = (const int*)c->histScratch.p + 48;
         IDP_TRY(run_query<2>(c, qa, c->candPT, &c->nCcdPT));
         aa.cand = c->candPT.p; aa.nCand = c->nCcdPT;
         if (c->nCcdPT > 0) IDP_LAUNCH(c, k_accd<0>, std::min(blocks_for(c->nCcdPT, 128), (unsigned)c->sm_count * 32), 128, 0, aa);
@@ -1119,13 +1253,13 @@ int ccd_step(idp_ctx* c, double thickness, double* alpha_inout, int keep_candida
     }
     {
         StageTimer tm(c, IDP_STAGE_CCD_EE);
-        long nEntries = 0;
-        IDP_TRY(build_cells(c, c->boxEb.p, c->nBE, g, &nEntries));
+        EMax emax = {{0, 0, 0}};
+        IDP_TRY(build_cells_multi(c, c->boxEb.p, c->nBE, g));
         shard_range(c, c->nBE, &qb, &qe);
         QueryArgs qa;
         qa.qrec = c->recE.p; qa.qbox = c->boxEb.p; qa.qBegin = qb; qa.qEnd = qe;
         qa.brec = c->recE.p; qa.bbox = c->boxEb.p; qa.cellStart = c->cellStart.p; qa.entries = c->entries.p;
-        qa.g = g; qa.dist = thickness;
+        qa.g = g; qa.dist = thickness; qa.emax = emax; qa.large = c->largeList.p; qa.nLargePtr = (const int*)c->histScratch.p + 48;
         IDP_TRY(run_query<3>(c, qa, c->candEE, &c->nCcdEE));
         aa.cand = c->candEE.p; aa.nCand = c->nCcdEE;
         if (c->nCcdEE > 0) {

@@ -132,7 +132,7 @@ long idp_kernel_launches(idp_ctx* ctx);     /* this library's own kernels launch
 long idp_library_calls(idp_ctx* ctx);       /* CUB device-wide primitives invoked since idp_reset_counters */
 void idp_reset_counters(idp_ctx* ctx);
 float idp_stage_ms(idp_ctx* ctx, int stage); /* device time of the last execution of a stage (CUDA events) */
-long idp_last_count(idp_ctx* ctx, int what); /* 0 rows, 1 PT cand, 2 EE cand, 3 CCD PT cand, 4 CCD EE cand, 5 ACCD trips, 6 nnz, 7 unique 3x3 blocks */
+long idp_last_count(idp_ctx* ctx, int what); /* 0 rows, 1 PT cand, 2 EE cand, 3 CCD PT cand, 4 CCD EE cand, 5 ACCD trips, 6 nnz, 7 unique 3x3 blocks, 8 device allocations made so far */
 /* FP64 pipe microbenchmark: register-resident DFMA chains on every SM; returns measured TFLOP/s (roofline denominator) */
 int idp_measure_fp64_tflops(idp_ctx* ctx, double* tflops);
 

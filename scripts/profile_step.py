@@ -22,6 +22,7 @@ dhat2 = dhat * dhat
 if args.only == "barrier":
     ctx.constraint_set(dhat2)
 for it in range(args.warmup + args.steps):
+    print('step', it, 'allocs so far', ctx.count(8))
     if args.only in ("all", "ccs"):
         n = ctx.constraint_set(dhat2)
     if args.only in ("all", "barrier"):
@@ -30,4 +31,4 @@ for it in range(args.warmup + args.steps):
         a = ctx.ccd_step_resident(1.0)
     if args.only == "all":
         ctx.min_dist2(want_all=False)
-print({k: round(v, 3) for k, v in ctx.stage_ms().items()}, ctx.count(0), ctx.launches())
+print({k: round(v, 3) for k, v in ctx.stage_ms().items()}, ctx.count(0), ctx.launches(), 'allocs', ctx.count(8))
