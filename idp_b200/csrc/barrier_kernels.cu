@@ -19,14 +19,14 @@ __device__ __forceinline__ V3 ldv4(const double4* __restrict__ p, int v)
     return mk3(a.x, a.y, b.x);
 }
 
-// number of 3x3 blocks a row contributes: nv^2
+// number of 3x3 blocks a row contributes: nv(nv+1)/2 — only blocks with vi <= vj are emitted, the assembly mirrors them
 __global__ void k_row_block_counts(const Row4* __restrict__ rows, long n, int rank, int nranks, int* __restrict__ cnt)
 {
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += (long)gridDim.x * blockDim.x) {
         int k = 0;
         if (i < n && (i % nranks) == rank) { // rows are dealt round-robin to the ranks (uniform mix of row kinds)
             const Row4 r = rows[i];
-            k = (r.a >= 0 || r.d >= 0) ? 16 : (r.c >= 0 ? 9 : 4); // IPC.h:1372-1387
+            k = (r.a >= 0 || r.d >= 0) ? 10 : (r.c >= 0 ? 6 : 3); // upper triangle of the nv x nv blocks (IPC.h:1372-1387 counts all nv^2)
         }
         cnt[i] = k;
     }
@@ -43,18 +43,24 @@ struct BarrierArgs {
     unsigned long long* errDist;
 };
 
-// Hessian sink: writes the 3x3 block (i,j) of a row at its pre-scanned offset together with its (vi*nV+vj) sort key
+// Hessian sink: the local Hessian is symmetric, so only one block per unordered vertex pair is stored, keyed (vlo, vhi)
+// with vlo <= vhi; block (i,j) with v[i] > v[j] is stored transposed. Slot = upper-triangle index of (min(i,j), max(i,j)).
 struct BlockEmit {
     unsigned long long* key; int* idx; double* val;
     long o; int nv; const int* v; long long nV;
+    __device__ __forceinline__ bool wants(int i, int j) const { return i <= j; }
     __device__ __forceinline__ void operator()(int i, int j, const double* blk) const
     {
-        const long s = o + i * nv + j;
-        key[s] = (unsigned long long)((long long)v[i] * nV + v[j]);
+        const long s = o + (i * nv - (i * (i - 1)) / 2 + (j - i));
+        const bool tr = v[i] > v[j];
+        const long long vlo = tr ? v[j] : v[i], vhi = tr ? v[i] : v[j];
+        key[s] = (unsigned long long)(vlo * nV + vhi);
         idx[s] = (int)s;
         double* dst = val + 9 * s;
 #pragma unroll
-        for (int k = 0; k < 9; ++k) dst[k] = blk[k];
+        for (int p = 0; p < 3; ++p)
+#pragma unroll
+            for (int q = 0; q < 3; ++q) dst[3 * p + q] = tr ? blk[3 * q + p] : blk[3 * p + q];
     }
 };
 
@@ -221,7 +227,7 @@ __global__ void k_seg_starts(const int* __restrict__ flagScan, const int* __rest
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
         if (flag[i]) segStart[flagScan[i]] = (int)i; // flagScan = exclusive scan -> segment index
 }
-// first unique block of every block row: vtxStart[v] = lower_bound(uniqueKey, v * nV)
+// first unique (upper) block of every block row: vtxStart[v] = lower_bound(uniqueKey, v * nV)
 __global__ void k_vertex_block_starts(const unsigned long long* __restrict__ keys, const int* __restrict__ segStart, int nSeg,
     int nV, int* __restrict__ vtxStart)
 {
@@ -236,20 +242,11 @@ __global__ void k_vertex_block_starts(const unsigned long long* __restrict__ key
         vtxStart[v] = lo;
     }
 }
-__global__ void k_csr_ptr(const int* __restrict__ vtxStart, int nV, int* __restrict__ ptr)
-{
-    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v <= nV; v += gridDim.x * blockDim.x) {
-        if (v == nV) { ptr[3 * (long)nV] = 9 * vtxStart[nV]; continue; }
-        const int s = vtxStart[v], nb = vtxStart[v + 1] - s;
-        ptr[3 * (long)v] = 9 * s;
-        ptr[3 * (long)v + 1] = 9 * s + 3 * nb;
-        ptr[3 * (long)v + 2] = 9 * s + 6 * nb;
-    }
-}
-// one thread per (unique block, component): sum the members in sorted (= emission) order, write CSR entry
+// one thread per (unique upper block, component): sum the members in sorted (= emission) order into ublk[seg][9];
+// component 0 also records the block's column vertex and counts the strictly-upper blocks per column (= lower blocks per row)
 __global__ void __launch_bounds__(288) k_reduce_blocks(const unsigned long long* __restrict__ keys, const int* __restrict__ idx,
-    const int* __restrict__ segStart, int nSeg, long nTot, const double* __restrict__ blkVal, const int* __restrict__ vtxStart,
-    long long nV, int* __restrict__ col, double* __restrict__ val)
+    const int* __restrict__ segStart, int nSeg, long nTot, const double* __restrict__ blkVal, long long nV,
+    double* __restrict__ ublk, int* __restrict__ ucol, int* __restrict__ urow, int* __restrict__ lowerCount)
 {
     const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const long seg = t / 9;
@@ -259,13 +256,89 @@ __global__ void __launch_bounds__(288) k_reduce_blocks(const unsigned long long*
     const int s1 = (seg + 1 < nSeg) ? segStart[seg + 1] : (int)nTot;
     double s = 0;
     for (int m = s0; m < s1; ++m) s += blkVal[9 * (long)idx[m] + comp];
-    const unsigned long long key = keys[s0];
-    const int vi = (int)(key / (unsigned long long)nV), vj = (int)(key - (unsigned long long)vi * (unsigned long long)nV);
-    const int bs = vtxStart[vi], nb = vtxStart[vi + 1] - bs;
+    ublk[9 * seg + comp] = s;
+    if (comp == 0) {
+        const unsigned long long key = keys[s0];
+        const int vi = (int)(key / (unsigned long long)nV), vj = (int)(key - (unsigned long long)vi * (unsigned long long)nV);
+        urow[seg] = vi;
+        ucol[seg] = vj;
+        if (vi != vj) atomicAdd(&lowerCount[vj], 1);
+    }
+}
+// block-row layout: [lower blocks (mirrors, ascending column)] [upper blocks incl. diagonal (ascending column)]
+// cnt[v] = lowerCount[v] + upperCount[v]
+__global__ void k_row_totals(const int* __restrict__ vtxStart, const int* __restrict__ lowerCount, int nV, int* __restrict__ cnt)
+{
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v <= nV; v += gridDim.x * blockDim.x)
+        cnt[v] = (v < nV) ? lowerCount[v] + (vtxStart[v + 1] - vtxStart[v]) : 0;
+}
+__global__ void k_csr_ptr(const int* __restrict__ rowStart, int nV, int* __restrict__ ptr)
+{
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v <= nV; v += gridDim.x * blockDim.x) {
+        if (v == nV) { ptr[3 * (long)nV] = 9 * rowStart[nV]; continue; }
+        const int s = rowStart[v], nb = rowStart[v + 1] - s;
+        ptr[3 * (long)v] = 9 * s;
+        ptr[3 * (long)v + 1] = 9 * s + 3 * nb;
+        ptr[3 * (long)v + 2] = 9 * s + 6 * nb;
+    }
+}
+// upper (and diagonal) blocks: one thread per (unique block, component)
+__global__ void __launch_bounds__(288) k_write_upper(const double* __restrict__ ublk, const int* __restrict__ urow, const int* __restrict__ ucol,
+    int nSeg, const int* __restrict__ vtxStart, const int* __restrict__ rowStart, const int* __restrict__ lowerCount,
+    int* __restrict__ col, double* __restrict__ val)
+{
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long seg = t / 9;
+    const int comp = (int)(t - seg * 9);
+    if (seg >= nSeg) return;
+    const int vi = urow[seg], vj = ucol[seg];
+    const int bs = rowStart[vi], nb = rowStart[vi + 1] - bs;
+    const int slot = lowerCount[vi] + (int)(seg - vtxStart[vi]);
     const int a = comp / 3, b = comp - 3 * a;
-    const long pos = 9L * bs + (long)a * 3 * nb + 3L * (seg - bs) + b;
+    const long pos = 9L * bs + (long)a * 3 * nb + 3L * slot + b;
     col[pos] = 3 * vj + b;
-    val[pos] = s;
+    val[pos] = ublk[9 * seg + comp];
+}
+// mirrored blocks: `order` lists the strictly-upper unique blocks stably sorted by their column vertex, so the members
+// of one block row appear with ascending row vertex = ascending column in the mirror. lstart[v] = first entry of row v.
+__global__ void __launch_bounds__(288) k_write_lower(const double* __restrict__ ublk, const int* __restrict__ urow, const int* __restrict__ order,
+    const int* __restrict__ sortedCol, long nLower, const int* __restrict__ lstart, const int* __restrict__ rowStart,
+    int* __restrict__ col, double* __restrict__ val)
+{
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long e = t / 9;
+    const int comp = (int)(t - e * 9);
+    if (e >= nLower) return;
+    const int seg = order[e];
+    const int row = sortedCol[e], cv = urow[seg]; // mirror: row vertex = original column, column vertex = original row
+    const int bs = rowStart[row], nb = rowStart[row + 1] - bs;
+    const int slot = (int)(e - lstart[row]);
+    const int a = comp / 3, b = comp - 3 * a;
+    const long pos = 9L * bs + (long)a * 3 * nb + 3L * slot + b;
+    col[pos] = 3 * cv + b;
+    val[pos] = ublk[9 * seg + 3 * b + a]; // transposed block
+}
+__global__ void k_lower_keys(const int* __restrict__ urow, const int* __restrict__ ucol, int nSeg, int* __restrict__ keyOut, int* __restrict__ segOut,
+    unsigned long long* __restrict__ counter)
+{
+    // compacts the strictly-upper blocks in segment order (deterministic: slot = exclusive count of earlier ones is not
+    // needed because the following sort is stable on (column) and the input order here is by segment via the scan below)
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < nSeg; s += gridDim.x * blockDim.x) {
+        keyOut[s] = (urow[s] != ucol[s]) ? ucol[s] : 0x7fffffff; // diagonal blocks sort to the end and are ignored
+        segOut[s] = s;
+    }
+}
+__global__ void k_lower_starts(const int* __restrict__ sortedCol, long nLower, int nV, int* __restrict__ lstart)
+{
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v <= nV; v += gridDim.x * blockDim.x) {
+        long lo = 0, hi = nLower;
+        while (lo < hi) {
+            const long mid = (lo + hi) >> 1;
+            if (sortedCol[mid] < v) lo = mid + 1;
+            else hi = mid;
+        }
+        lstart[v] = (int)lo;
+    }
 }
 
 int assemble_csr(idp_ctx* c)
@@ -280,19 +353,20 @@ int assemble_csr(idp_ctx* c)
         IDP_CK(c, cudaStreamSynchronize(c->stream));
         return IDP_OK;
     }
+    const int nV = c->nV;
     IDP_CK(c, c->blkKeySorted.reserve(n));
     IDP_CK(c, c->blkIdxSorted.reserve(n));
     int bits = 1;
-    while (bits < 64 && ((unsigned long long)c->nV * (unsigned long long)c->nV) >> bits) ++bits;
+    while (bits < 64 && ((unsigned long long)nV * (unsigned long long)nV) >> bits) ++bits;
     size_t bytes = 0;
     IDP_CK(c, cub::DeviceRadixSort::SortPairs(nullptr, bytes, c->blkKey.p + b0, c->blkKeySorted.p, c->blkIdx.p + b0, c->blkIdxSorted.p, (int)n, 0, bits, c->stream));
     IDP_CK(c, c->cubTemp.reserve(bytes));
     IDP_CK(c, cub::DeviceRadixSort::SortPairs(c->cubTemp.p, bytes, c->blkKey.p + b0, c->blkKeySorted.p, c->blkIdx.p + b0, c->blkIdxSorted.p, (int)n, 0, bits, c->stream));
     ++c->lib_launches;
-    // unique blocks
-    IDP_CK(c, c->segId.reserve(n + 1));
+    // unique upper blocks
+    IDP_CK(c, c->segId.reserve(std::max<long>(n + 1, nV + 2)));
     IDP_CK(c, c->segStart.reserve(n + 1));
-    IDP_CK(c, c->rowBlkOff.reserve(n + 1)); // reused as scan output (row offsets are no longer needed)
+    IDP_CK(c, c->rowBlkOff.reserve(std::max<long>(n + 1, nV + 2))); // reused as scan output (row offsets are no longer needed)
     IDP_LAUNCH(c, k_head_flags, blocks_for(n, 256), 256, 0, c->blkKeySorted.p, n, c->segId.p);
     IDP_CK(c, cudaMemsetAsync(c->segId.p + n, 0, sizeof(int), c->stream));
     IDP_TRY(cub_scan_exclusive(c, c->segId.p, c->rowBlkOff.p, n + 1));
@@ -300,15 +374,42 @@ int assemble_csr(idp_ctx* c)
     IDP_CK(c, cudaMemcpyAsync(&nSeg, c->rowBlkOff.p + n, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     IDP_LAUNCH(c, k_seg_starts, blocks_for(n, 256), 256, 0, c->rowBlkOff.p, c->segId.p, n, c->segStart.p);
     IDP_CK(c, cudaStreamSynchronize(c->stream));
-    c->nBlocksUnique = nSeg;
-    c->nnz = 9L * nSeg;
-    IDP_CK(c, c->vtxBlkStart.reserve((size_t)c->nV + 1));
-    IDP_CK(c, c->csrCol.reserve(c->nnz));
-    IDP_CK(c, c->csrVal.reserve(c->nnz));
-    IDP_LAUNCH(c, k_vertex_block_starts, blocks_for(c->nV + 1, 256), 256, 0, c->blkKeySorted.p, c->segStart.p, nSeg, c->nV, c->vtxBlkStart.p);
-    IDP_LAUNCH(c, k_csr_ptr, blocks_for(c->nV + 1, 256), 256, 0, c->vtxBlkStart.p, c->nV, c->csrPtr.p);
+    // reduce duplicates -> dense unique upper blocks
+    IDP_CK(c, c->ublk.reserve(9 * (size_t)nSeg));
+    IDP_CK(c, c->urow.reserve(nSeg)); IDP_CK(c, c->ucol.reserve(nSeg));
+    IDP_CK(c, c->lowerCount.reserve((size_t)nV + 2)); IDP_CK(c, c->lstart.reserve((size_t)nV + 2));
+    IDP_CK(c, c->vtxBlkStart.reserve((size_t)nV + 2)); IDP_CK(c, c->rowStart.reserve((size_t)nV + 2));
+    IDP_CK(c, cudaMemsetAsync(c->lowerCount.p, 0, ((size_t)nV + 2) * sizeof(int), c->stream));
     IDP_LAUNCH(c, k_reduce_blocks, blocks_for(9L * nSeg, 288), 288, 0, c->blkKeySorted.p, c->blkIdxSorted.p, c->segStart.p, nSeg, n,
-        c->blkVal.p, c->vtxBlkStart.p, (long long)c->nV, c->csrCol.p, c->csrVal.p);
+        c->blkVal.p, (long long)nV, c->ublk.p, c->ucol.p, c->urow.p, c->lowerCount.p);
+    IDP_LAUNCH(c, k_vertex_block_starts, blocks_for(nV + 1, 256), 256, 0, c->blkKeySorted.p, c->segStart.p, nSeg, nV, c->vtxBlkStart.p);
+    // block-row sizes and starts
+    IDP_LAUNCH(c, k_row_totals, blocks_for(nV + 1, 256), 256, 0, c->vtxBlkStart.p, c->lowerCount.p, nV, c->segId.p);
+    IDP_TRY(cub_scan_exclusive(c, c->segId.p, c->rowStart.p, (long)nV + 1));
+    int nBlkTotal = 0;
+    IDP_CK(c, cudaMemcpyAsync(&nBlkTotal, c->rowStart.p + nV, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    // mirrored (lower) blocks: stable sort of the unique blocks by column vertex
+    IDP_CK(c, c->lkey.reserve(nSeg)); IDP_CK(c, c->lkeySorted.reserve(nSeg)); IDP_CK(c, c->lseg.reserve(nSeg)); IDP_CK(c, c->lsegSorted.reserve(nSeg));
+    IDP_LAUNCH(c, k_lower_keys, blocks_for(nSeg, 256), 256, 0, c->urow.p, c->ucol.p, nSeg, c->lkey.p, c->lseg.p, (unsigned long long*)nullptr);
+    int vbits = 1;
+    while (vbits < 31 && (nV >> vbits)) ++vbits;
+    IDP_CK(c, cub::DeviceRadixSort::SortPairs(nullptr, bytes, c->lkey.p, c->lkeySorted.p, c->lseg.p, c->lsegSorted.p, nSeg, 0, 31, c->stream));
+    IDP_CK(c, c->cubTemp.reserve(bytes));
+    IDP_CK(c, cub::DeviceRadixSort::SortPairs(c->cubTemp.p, bytes, c->lkey.p, c->lkeySorted.p, c->lseg.p, c->lsegSorted.p, nSeg, 0, 31, c->stream));
+    ++c->lib_launches;
+    IDP_CK(c, cudaStreamSynchronize(c->stream));
+    const long nLower = (long)nBlkTotal - nSeg; // every strictly-upper block has one mirror
+    c->nBlocksUnique = nBlkTotal;
+    c->nnz = 9L * nBlkTotal;
+    IDP_CK(c, c->csrCol.reserve(std::max<long>(c->nnz, 1)));
+    IDP_CK(c, c->csrVal.reserve(std::max<long>(c->nnz, 1)));
+    IDP_LAUNCH(c, k_lower_starts, blocks_for(nV + 1, 256), 256, 0, c->lkeySorted.p, nLower, nV, c->lstart.p);
+    IDP_LAUNCH(c, k_csr_ptr, blocks_for(nV + 1, 256), 256, 0, c->rowStart.p, nV, c->csrPtr.p);
+    IDP_LAUNCH(c, k_write_upper, blocks_for(9L * nSeg, 288), 288, 0, c->ublk.p, c->urow.p, c->ucol.p, nSeg, c->vtxBlkStart.p, c->rowStart.p,
+        c->lowerCount.p, c->csrCol.p, c->csrVal.p);
+    if (nLower > 0)
+        IDP_LAUNCH(c, k_write_lower, blocks_for(9L * nLower, 288), 288, 0, c->ublk.p, c->urow.p, c->lsegSorted.p, c->lkeySorted.p, nLower, c->lstart.p,
+            c->rowStart.p, c->csrCol.p, c->csrVal.p);
     IDP_CK(c, cudaGetLastError());
     IDP_CK(c, cudaStreamSynchronize(c->stream));
     return IDP_OK;

@@ -142,7 +142,8 @@ struct idp_ctx {
     idp::DBuf<unsigned long long> blkKey, blkKeySorted;
     idp::DBuf<int> blkIdx, blkIdxSorted, segId, segStart;
     idp::DBuf<double> blkVal;
-    idp::DBuf<int> vtxBlkStart;
+    idp::DBuf<int> vtxBlkStart, rowStart, lowerCount, lstart, urow, ucol, lkey, lkeySorted, lseg, lsegSorted;
+    idp::DBuf<double> ublk;              // unique upper 3x3 blocks after the segmented sum
     idp::DBuf<int> csrPtr, csrCol;
     idp::DBuf<double> csrVal;
     long nnz = 0, nBlocksUnique = 0;

@@ -404,7 +404,8 @@ IDP_HD bool row_eval(const RowDec& d, const V3* x, const V3* xr, double weight, 
                     Mb[3 * i + j] = kd * dv[i] * dv[j] + (i == j ? ki : 0.0);
                     Nb[3 * i + j] = -Mb[3 * i + j];
                 }
-            emit(0, 0, Mb); emit(0, 1, Nb); emit(1, 0, Nb); emit(1, 1, Mb);
+            emit(0, 0, Mb); emit(0, 1, Nb); emit(1, 1, Mb);
+            if (emit.wants(1, 0)) emit(1, 0, Nb);
         }
         return true;
     }
@@ -441,6 +442,7 @@ IDP_HD bool row_eval(const RowDec& d, const V3* x, const V3* xr, double weight, 
             for (int i = 0; i < 3; ++i)
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
+                    if (!emit.wants(i, j)) continue;
                     double blk[9];
                     expand_block<3, 2>(Hm, M, i, j, blk);
                     emit(i, j, blk);
@@ -552,6 +554,7 @@ IDP_HD bool row_eval(const RowDec& d, const V3* x, const V3* xr, double weight, 
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
+            if (!emit.wants(i, j)) continue;
             double blk[9];
             expand_block<4, 3>(Hm, M, i, j, blk);
             emit(i, j, blk);
@@ -563,6 +566,7 @@ IDP_HD bool row_eval(const RowDec& d, const V3* x, const V3* xr, double weight, 
 struct DenseEmit {
     double* H;
     int n;
+    IDP_HD bool wants(int, int) const { return true; }
     IDP_HD void operator()(int i, int j, const double* blk)
     {
         for (int a = 0; a < 3; ++a)
