@@ -14,6 +14,8 @@ typedef int (*fn_destroy)(void*);
 typedef int (*fn_allgather)(const void*, void*, size_t, int, void*, cudaStream_t);
 typedef int (*fn_broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t);
 typedef int (*fn_group)(void);
+typedef int (*fn_send)(const void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*fn_recv)(void*, size_t, int, int, void*, cudaStream_t);
 typedef const char* (*fn_errstr)(int);
 
 struct NcclApi {
@@ -26,6 +28,8 @@ struct NcclApi {
     fn_allgather allgather = nullptr;
     fn_broadcast broadcast = nullptr;
     fn_group group_start = nullptr, group_end = nullptr;
+    fn_send send = nullptr;
+    fn_recv recv = nullptr;
 };
 static NcclApi g_nccl;
 
@@ -61,8 +65,10 @@ static bool load_nccl()
     g_nccl.broadcast = (fn_broadcast)dlsym(g_nccl.h, "ncclBroadcast");
     g_nccl.group_start = (fn_group)dlsym(g_nccl.h, "ncclGroupStart");
     g_nccl.group_end = (fn_group)dlsym(g_nccl.h, "ncclGroupEnd");
+    g_nccl.send = (fn_send)dlsym(g_nccl.h, "ncclSend");
+    g_nccl.recv = (fn_recv)dlsym(g_nccl.h, "ncclRecv");
     return g_nccl.get_uid && g_nccl.init_rank && g_nccl.allreduce && g_nccl.destroy && g_nccl.allgather && g_nccl.broadcast &&
-           g_nccl.group_start && g_nccl.group_end;
+           g_nccl.group_start && g_nccl.group_end && g_nccl.send && g_nccl.recv;
 }
 
 // ncclDataType_t: ncclFloat64 = 8; ncclRedOp_t: ncclSum = 0, ncclProd = 1, ncclMax = 2, ncclMin = 3, ncclAvg = 4
@@ -125,6 +131,36 @@ int comm_allgatherv(idp_ctx* c, const void* local, long nLocal, size_t elemSize,
     }
     IDP_NCCL(c, g_nccl.group_end());
     *nTotal = total;
+    return IDP_OK;
+}
+
+// all-to-all of 64-bit keys: rank r receives, from every rank s, the slice [sendOff_s[r], sendOff_s[r+1]) of s's array.
+// Used to route the duplicate-merge keys to the rank that owns their key range (halo-free: keys, not geometry, move).
+int comm_exchange_keys(idp_ctx* c, const unsigned long long* keys, const long sendOff[9], DBuf<unsigned long long>& recv, long* nRecv)
+{
+    CommTimer tm(c);
+    const int P = c->nranks;
+    IDP_CK(c, c->commCounts.reserve(64)); // P send counts of this rank, gathered into a P x P matrix (P <= 8)
+    long long mine[8];
+    for (int r = 0; r < P; ++r) mine[r] = sendOff[r + 1] - sendOff[r];
+    IDP_CK(c, cudaMemcpyAsync(c->commCounts.p + (size_t)c->rank * P, mine, P * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+    IDP_NCCL(c, g_nccl.allgather(c->commCounts.p + (size_t)c->rank * P, c->commCounts.p, (size_t)P, 4 /*ncclInt64*/, c->nccl_comm, c->stream));
+    long long all[64];
+    IDP_CK(c, cudaMemcpyAsync(all, c->commCounts.p, (size_t)P * P * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    IDP_CK(c, cudaStreamSynchronize(c->stream));
+    long roff[9];
+    long total = 0;
+    for (int s2 = 0; s2 < P; ++s2) { roff[s2] = total; total += (long)all[s2 * P + c->rank]; }
+    roff[P] = total;
+    IDP_CK(c, recv.reserve(std::max<long>(total, 1)));
+    IDP_NCCL(c, g_nccl.group_start());
+    for (int r = 0; r < P; ++r) {
+        const long ns = sendOff[r + 1] - sendOff[r], nr = roff[r + 1] - roff[r];
+        if (ns > 0) { const int rc = g_nccl.send(keys + sendOff[r], (size_t)ns, 5 /*ncclUint64*/, r, c->nccl_comm, c->stream); if (rc) { g_nccl.group_end(); return fail(c, IDP_ERR_NCCL, "NCCL error: %s at %s:%d", g_nccl.errstr ? g_nccl.errstr(rc) : "?", __FILE__, __LINE__); } }
+        if (nr > 0) { const int rc = g_nccl.recv(recv.p + roff[r], (size_t)nr, 5, r, c->nccl_comm, c->stream); if (rc) { g_nccl.group_end(); return fail(c, IDP_ERR_NCCL, "NCCL error: %s at %s:%d", g_nccl.errstr ? g_nccl.errstr(rc) : "?", __FILE__, __LINE__); } }
+    }
+    IDP_NCCL(c, g_nccl.group_end());
+    *nRecv = total;
     return IDP_OK;
 }
 

@@ -127,6 +127,7 @@ struct idp_ctx {
     long nCandPT = 0, nCandEE = 0;
     idp::DBuf<double> red;              // reduction scratch
     idp::DBuf<unsigned char> cubTemp;
+    idp::DBuf<long long> commCounts;    // P x P exchange counts
     idp::DBuf<long long> counters;      // device counters / flags (see enum in kernels)
     // ---- constraint set ----
     idp::DBuf<idp::Row4> rowsA, rowsB, rowsD, rowsD2, rows, rowsG;
@@ -235,6 +236,7 @@ int ccd_step(idp_ctx* c, double thickness, double* alpha_inout, int keep_candida
 int cub_scan_exclusive(idp_ctx* c, const int* in, int* out, long n);
 // variable-size all-gather of nLocal elements of elemSize bytes into *outPtr (capacity *outCap elements, grown and
 // preserved when too small) starting at element outOffset; *nTotal = sum over ranks
+int comm_exchange_keys(idp_ctx* c, const unsigned long long* keys, const long sendOff[9], DBuf<unsigned long long>& recv, long* nRecv);
 int comm_allgatherv(idp_ctx* c, const void* local, long nLocal, size_t elemSize, void** outPtr, size_t* outCap, long outOffset, long* nTotal);
 
 } // namespace idp

@@ -736,6 +736,21 @@ __global__ void k_emit_merged_keys(const unsigned long long* __restrict__ uniq, 
     }
 }
 
+// lower_bound of P+1 thresholds in a sorted key array (one thread each)
+__global__ void k_key_splits(const unsigned long long* __restrict__ sorted, long n, const unsigned long long* __restrict__ thr, int nThr, long long* __restrict__ out)
+{
+    const int t = threadIdx.x;
+    if (t >= nThr) return;
+    long lo = 0, hi = n;
+    const unsigned long long target = thr[t];
+    while (lo < hi) {
+        const long mid = (lo + hi) >> 1;
+        if (sorted[mid] < target) lo = mid + 1;
+        else hi = mid;
+    }
+    out[t] = lo;
+}
+
 __global__ void k_emit_merged(const Row4* __restrict__ uniq, const int* __restrict__ counts, long n, Row4* __restrict__ out)
 {
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
@@ -970,15 +985,42 @@ int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
     }
     mergeSort = c->times.v[IDP_STAGE_CCS_MERGE];
     unsigned long long* dupKeys = c->keyD.p;
+    bool distributedDup = false;
     if (sharded) {
         IDP_TRY(comm_allgatherv(c, c->rowsG.p, nA, sizeof(Row4), (void**)&c->rows.p, &c->rows.cap, 0, &nAg));
         IDP_TRY(comm_allgatherv(c, c->rowsG.p + nA, nB, sizeof(Row4), (void**)&c->rows.p, &c->rows.cap, nAg, &nBg));
         if (dupBits) {
-            IDP_TRY(comm_allgatherv(c, c->keyD.p, nD, sizeof(unsigned long long), (void**)&c->keyB.p, &c->keyB.cap, 0, &nDg));
+            // distributed duplicate merge: sort the local keys, route every key to the rank owning its range of the leading
+            // field (nV-1-p), merge there; the merged rows are gathered below in rank order = key order.
+            const int P = c->nranks;
+            long sendOff[9];
+            {
+            StageTimer tm2(c, IDP_STAGE_CCS_MERGE);
+            IDP_CK(c, c->keyTmp.reserve(std::max<long>(nD, 1)));
+            size_t bytes = 0;
+            if (nD > 0) {
+                IDP_CK(c, cub::DeviceRadixSort::SortKeys(nullptr, bytes, c->keyD.p, c->keyTmp.p, (int)nD, 0, 3 * dupBits, c->stream));
+                IDP_CK(c, c->cubTemp.reserve(bytes));
+                IDP_CK(c, cub::DeviceRadixSort::SortKeys(c->cubTemp.p, bytes, c->keyD.p, c->keyTmp.p, (int)nD, 0, 3 * dupBits, c->stream));
+                ++c->lib_launches;
+            }
+            unsigned long long thr[9];
+            for (int r = 0; r <= P; ++r) thr[r] = (r == P) ? ~0ull : (((unsigned long long)((long long)c->nV * r / P)) << (2 * dupBits));
+            thr[0] = 0;
+            unsigned long long* dThr = (unsigned long long*)c->histScratch.p; // 64 ints = 32 ull of scratch
+            long long* dSplit = (long long*)(dThr + 12);
+            IDP_CK(c, cudaMemcpyAsync(dThr, thr, (P + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
+            IDP_LAUNCH(c, k_key_splits, 1, 32, 0, c->keyTmp.p, nD, dThr, P + 1, dSplit);
+            long long split[9];
+            IDP_CK(c, cudaMemcpyAsync(split, dSplit, (P + 1) * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+            IDP_CK(c, cudaStreamSynchronize(c->stream));
+            for (int r = 0; r <= P; ++r) sendOff[r] = (long)split[r];
+            sendOff[P] = nD;
+            }
+            mergeSort += c->times.v[IDP_STAGE_CCS_MERGE]; // (the exchange itself is accounted to nccl_collectives)
+            IDP_TRY(comm_exchange_keys(c, c->keyTmp.p, sendOff, c->keyB, &nDg));
             dupKeys = c->keyB.p;
-        }
-        else {
-            IDP_TRY(comm_allgatherv(c, c->rowsD.p, nD, sizeof(Row4), (void**)&c->rowsG.p, &c->rowsG.cap, 0, &nDg));
+            distributedDup = true;
         }
         IDP_CK(c, c->rows.reserve(std::max<long>(nAg + nBg + nDg, 1), true, c->stream));
     }
@@ -1020,7 +1062,16 @@ int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
             IDP_CK(c, cudaStreamSynchronize(c->stream));
             nU = runs;
         }
-        c->nRows = nA + nB + nU;
+        if (distributedDup) {
+            // this rank merged its own key range: emit its rows, then all-gather them behind the direct groups
+            IDP_CK(c, c->rowsG.reserve(std::max<long>(nU, 1)));
+            if (nU) IDP_LAUNCH(c, k_emit_merged_keys, blocks_for(nU, 256), 256, 0, c->keyA.p, c->runCounts.p, nU, dupBits, (long long)c->nV, c->rowsG.p);
+            long nUg = 0;
+            IDP_TRY(comm_allgatherv(c, c->rowsG.p, nU, sizeof(Row4), (void**)&c->rows.p, &c->rows.cap, nA + nB, &nUg));
+            nU = 0;        // already in place
+            c->nRows = nA + nB + nUg;
+        }
+        else c->nRows = nA + nB + nU;
         IDP_CK(c, c->weights.reserve(std::max<long>(c->nRows, 1)));
         if (nU && dupBits) IDP_LAUNCH(c, k_emit_merged_keys, blocks_for(nU, 256), 256, 0, c->keyA.p, c->runCounts.p, nU, dupBits, (long long)c->nV, c->rows.p + nA + nB);
         else if (nU) IDP_LAUNCH(c, k_emit_merged, blocks_for(nU, 256), 256, 0, c->rowsD2.p, c->runCounts.p, nU, c->rows.p + nA + nB);
