@@ -2,8 +2,33 @@
 // host buffers, and calls into the launchers of exact_kernels.cu / barrier_kernels.cu / comm.cu.
 #include "ctx.cuh"
 #include <string.h>
+#include <thread>
 
 using namespace idp;
+
+// run f(begin, end) over [0, n) on a few host threads (marshalling loops over tens of millions of rows)
+template <class F>
+static void host_parallel(long n, F f)
+{
+    const int T = (int)std::max(1L, std::min<long>(8, n / 65536));
+    if (T == 1) { f(0, n); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < T; ++t) th.emplace_back([=]() { f(n * t / T, n * (t + 1) / T); });
+    for (auto& x : th) x.join();
+}
+// pinned host staging owned by the context (grown on demand)
+static int host_stage(idp_ctx* c, size_t bytes, void** out)
+{
+    if (bytes > c->h_stage_bytes) {
+        if (c->h_stage) cudaFreeHost(c->h_stage);
+        c->h_stage = nullptr;
+        c->h_stage_bytes = 0;
+        IDP_CK(c, cudaMallocHost(&c->h_stage, bytes + bytes / 8));
+        c->h_stage_bytes = bytes + bytes / 8;
+    }
+    *out = c->h_stage;
+    return IDP_OK;
+}
 
 namespace idp {
 int comm_allreduce_sum(idp_ctx* c, double* dev, long n);
@@ -48,6 +73,7 @@ void idp_destroy(idp_ctx* c)
     comm_destroy(c);
     if (c->h_counters) cudaFreeHost(c->h_counters);
     if (c->h_red) cudaFreeHost(c->h_red);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->kev0) cudaEventDestroy(c->kev0);
@@ -141,10 +167,18 @@ int idp_get_constraints(idp_ctx* c, int* rows4, double* info2)
         IDP_CK(c, cudaStreamSynchronize(c->stream));
     }
     if (info2 && c->nRows) {
-        std::vector<double> w(c->nRows);
-        IDP_CK(c, cudaMemcpyAsync(w.data(), c->weights.p, c->nRows * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-        IDP_CK(c, cudaStreamSynchronize(c->stream));
-        for (long i = 0; i < c->nRows; ++i) { info2[2 * i] = w[i]; info2[2 * i + 1] = c->cs_dhat2; }
+        const long n = c->nRows;
+        const double dh2 = c->cs_dhat2;
+        if (c->weights_all_one) { // set by idp_constraint_set (OIPC: weight 1, IPC.h:656-660): nothing to copy back
+            host_parallel(n, [=](long b, long e) { for (long i = b; i < e; ++i) { info2[2 * i] = 1.0; info2[2 * i + 1] = dh2; } });
+        }
+        else {
+            double* w = nullptr;
+            IDP_TRY(host_stage(c, (size_t)n * sizeof(double), (void**)&w));
+            IDP_CK(c, cudaMemcpyAsync(w, c->weights.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            IDP_CK(c, cudaStreamSynchronize(c->stream));
+            host_parallel(n, [=](long b, long e) { for (long i = b; i < e; ++i) { info2[2 * i] = w[i]; info2[2 * i + 1] = dh2; } });
+        }
     }
     return IDP_OK;
 }
@@ -154,6 +188,7 @@ int idp_set_constraints(idp_ctx* c, int n, const int* rows4, const double* info2
     if (!c || n < 0 || (n && !rows4)) return IDP_ERR_INVALID;
     IDP_CK(c, cudaSetDevice(c->device));
     c->nRows = n;
+    c->weights_all_one = false;
     IDP_CK(c, c->rows.reserve(std::max(n, 1)));
     IDP_CK(c, c->weights.reserve(std::max(n, 1)));
     if (n) {
@@ -194,11 +229,15 @@ static int finish_gradient(idp_ctx* c, double* g_accum, int stride)
     if (c->nranks > 1 && c->nccl_comm) IDP_TRY(comm_allreduce_sum(c, c->gbuf.p, 3L * c->nV));
     if (!g_accum) return IDP_OK;
     if (stride < 3) return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "stride must be >= 3", __FILE__, __LINE__);
-    std::vector<double> g(3 * (size_t)c->nV);
-    IDP_CK(c, cudaMemcpyAsync(g.data(), c->gbuf.p, g.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    double* g = nullptr;
+    const long nV = c->nV;
+    IDP_TRY(host_stage(c, 3 * (size_t)nV * sizeof(double), (void**)&g));
+    IDP_CK(c, cudaMemcpyAsync(g, c->gbuf.p, 3 * (size_t)nV * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     IDP_CK(c, cudaStreamSynchronize(c->stream));
-    for (long v = 0; v < c->nV; ++v)
-        for (int a = 0; a < 3; ++a) g_accum[v * stride + a] += g[3 * v + a];
+    host_parallel(nV, [=](long b, long e) {
+        for (long v = b; v < e; ++v)
+            for (int a = 0; a < 3; ++a) g_accum[v * stride + a] += g[3 * v + a];
+    });
     return IDP_OK;
 }
 

@@ -154,6 +154,9 @@ struct idp_ctx {
     // host pinned scratch for small readbacks
     long long* h_counters = nullptr;
     double* h_red = nullptr;
+    void* h_stage = nullptr;            // pinned staging for gradient / weight read-backs
+    size_t h_stage_bytes = 0;
+    bool weights_all_one = false;
 
     idp::StageTimes times;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, kev0 = nullptr, kev1 = nullptr;

@@ -1076,6 +1076,7 @@ int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
         if (nU && dupBits) IDP_LAUNCH(c, k_emit_merged_keys, blocks_for(nU, 256), 256, 0, c->keyA.p, c->runCounts.p, nU, dupBits, (long long)c->nV, c->rows.p + nA + nB);
         else if (nU) IDP_LAUNCH(c, k_emit_merged, blocks_for(nU, 256), 256, 0, c->rowsD2.p, c->runCounts.p, nU, c->rows.p + nA + nB);
         if (c->nRows) IDP_LAUNCH(c, k_fill_double, blocks_for(c->nRows, 256), 256, 0, c->weights.p, c->nRows, 1.0); // OIPC: weight 1 (IPC.h:656-660)
+        c->weights_all_one = true;
         IDP_CK(c, cudaGetLastError());
     }
     c->times.v[IDP_STAGE_CCS_MERGE] += mergeSort;
