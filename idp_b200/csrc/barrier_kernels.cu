@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(128) k_barrier(BarrierArgs a)
             for (int k = 0; k < 4; ++k) xr[k] = ldv4(a.x0p, d.v[k]);
         }
         RowOut out;
-        VShared<9> V9{sV + threadIdx.x, (int)blockDim.x, 0};
+        QlStore<9, 128> V9{sV + threadIdx.x};
         BlockEmit em{a.blkKey, a.blkIdx, a.blkVal, WANT_H ? (long)a.blkOff[i] : 0L, d.nv, d.v, a.nVll};
         const bool ok = row_eval<PATH>(d, x, xr, a.weights[i], a.dHat2, a.kappa, a.xi2, a.projectSPD != 0, WANT_H, V9, out, em);
         if (!ok) { atomicAdd(a.errDist, 1ull); continue; }
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(128) k_barrier(BarrierArgs a)
 template <int PATH>
 static int launch_barrier_path(idp_ctx* c, BarrierArgs a, unsigned grid, int sel)
 {
-    const size_t smem = PATH == 0 ? 81 * sizeof(double) * 128 : 0;
+    const size_t smem = PATH == 0 ? QlStore<9, 128>::WORDS * sizeof(double) * 128 : 0;
 #define IDP_BARRIER_CASE(E, G, H)                                                                                         \
     do {                                                                                                                  \
         if (smem) IDP_CK(c, cudaFuncSetAttribute(k_barrier<PATH, E, G, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \

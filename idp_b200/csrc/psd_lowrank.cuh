@@ -76,31 +76,6 @@ struct VLocal {
         }
     }
 };
-template <int N>
-struct VShared { // shared memory: element (r, physical column) of this thread at p[(r*N + col) * stride]
-    static constexpr int M = (N % 2) ? N : N - 1;
-    double* p;
-    int stride;
-    int off;
-    IDP_HD void init()
-    {
-        off = 0;
-#pragma unroll
-        for (int i = 0; i < N; ++i)
-#pragma unroll
-            for (int j = 0; j < N; ++j) p[(i * N + j) * stride] = (i == j) ? 1.0 : 0.0;
-    }
-    IDP_HD int col(int c) const
-    {
-        if (c >= M) return c;
-        const int k = c + off;
-        return k >= M ? k - M : k;
-    }
-    IDP_HD double get(int r, int c) const { return p[(r * N + col(c)) * stride]; }
-    IDP_HD void set(int r, int c, double x) { p[(r * N + col(c)) * stride] = x; }
-    IDP_HD void advance() { off = (off + 1 == M) ? 0 : off + 1; }
-};
-
 // Jacobi eigenvalue iteration on the packed upper triangle a (N(N+1)/2 values); V receives the eigenvectors as
 // columns; on exit the diagonal of a holds the eigenvalues.
 // Pair order: round-robin tournament. The pairs of one round are disjoint, so their rotation parameters depend only on
@@ -224,6 +199,236 @@ IDP_HD void make_pd_packed(double* m, VS& V)
 #pragma unroll
             for (int k = 0; k < N; ++k) s += wr[k] * V.get(c, k);
             m[SI<N>(r, c)] = s;
+        }
+    }
+}
+
+
+// ---- makePD through Householder tridiagonalisation + implicit QL ----------------------------------------------------------
+// Same result as make_pd_packed (V max(lambda,0) V^T) at roughly a third of the arithmetic of cyclic Jacobi:
+//   1. Householder reduction of the packed matrix to tridiagonal form T = Q^T M Q: fixed control flow, fully unrolled,
+//      every index static -> registers only;
+//   2. Q is formed explicitly in the work store S (shared memory on the device);
+//   3. implicit-shift QL on (d, e) with the Givens rotations accumulated into the columns of S. Every lane of a warp
+//      performs ONE QL iteration per trip (deflation scan, Wilkinson shift, bulge chase from its own m down to its own l),
+//      so lanes stay in the chase together and a trip costs the longest chase in the warp. The chase is software
+//      pipelined: the column rotation of step i+1 (9 independent rows) is issued together with the scalar dependency
+//      chain that produces the rotation of step i, and the column shared by consecutive rotations is carried in
+//      registers (one column load + one column store per step);
+//   4. reconstruction V max(lambda,0) V^T into the packed matrix.
+// Deflation threshold: |e| <= 2e-15 * (max|d_i| + max|e_i|). Dropping such an e perturbs T by that much; the projection
+// onto the PSD cone is non-expansive, so the result moves by no more than the sum of the dropped values (<= ~2e-14 ||M||).
+//
+// QlStore: per-row work store of N*N eigenvector entries, N diagonal and N sub-diagonal values; element w of the row
+// lives at p[w * STRIDE] (device: STRIDE = threads per block, p = shared base + threadIdx.x -> conflict-free 64-bit accesses
+// whatever the per-lane column index is; host: STRIDE = 1 over a local buffer).
+template <int N, int STRIDE>
+struct QlStore {
+    static constexpr int WORDS = N * N + 2 * N;
+    static constexpr int STRIDE_V = STRIDE;
+    double* p;
+    // entry (r, c) of the eigenvector matrix relative to a column pointer col(c)
+    IDP_HD double* col(int c) const { return p + c * STRIDE; }
+    static IDP_HD double z(const double* colp, int r) { return colp[r * N * STRIDE]; }
+    static IDP_HD void zset(double* colp, int r, double x) { colp[r * N * STRIDE] = x; }
+    static IDP_HD double d(const double* colp) { return colp[N * N * STRIDE]; }
+    static IDP_HD void dset(double* colp, double x) { colp[N * N * STRIDE] = x; }
+    static IDP_HD double e(const double* colp) { return colp[(N * N + N) * STRIDE]; }
+    static IDP_HD void eset(double* colp, double x) { colp[(N * N + N) * STRIDE] = x; }
+};
+IDP_HD int first_set_bit(unsigned x) // 1-based, 0 when x == 0
+{
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)x);
+#else
+    return __builtin_ffs((int)x);
+#endif
+}
+#ifdef IDP_QL_STATS
+struct QlStats { long rows, trips, givens; int n; int chase[512]; };
+static QlStats g_ql_stats = {0, 0, 0, 0, {0}};
+#endif
+template <int N, class ST>
+IDP_HD void make_pd_ql(double* a, ST& S)
+{
+    // ---- 1. Householder: for column k annihilate a(k+2.., k); v is stored over a(k, k+1..), beta kept
+    double beta[N - 2];
+    double emax = 0;
+#pragma unroll
+    for (int k = 0; k < N - 2; ++k) {
+        const double x0 = a[SI<N>(k, k + 1)];
+        double sigma = 0;
+#pragma unroll
+        for (int i = k + 2; i < N; ++i) sigma += a[SI<N>(k, i)] * a[SI<N>(k, i)];
+        const double n2 = x0 * x0 + sigma;
+        const bool act = sigma > 0.0 && n2 > 1e-280;
+        double alpha = x0, bt = 0.0;
+        if (act) {
+            const double nrm = n2 * rsqrt_nr<3>(n2);
+            alpha = x0 >= 0 ? -nrm : nrm;
+            bt = rcp_nr2(nrm * (fabs(x0) + nrm)); // 2 / v^T v with v0 = x0 - alpha
+            a[SI<N>(k, k + 1)] = x0 - alpha;
+        }
+        beta[k] = bt;
+        // p = beta A22 v, K = beta/2 v.p, w = p - K v, A22 -= v w^T + w v^T
+        double pv[N];
+        double vp = 0;
+#pragma unroll
+        for (int i = k + 1; i < N; ++i) {
+            double s = 0;
+#pragma unroll
+            for (int j = k + 1; j < N; ++j) s += a[SI<N>(i, j)] * a[SI<N>(k, j)];
+            pv[i] = bt * s;
+            vp += pv[i] * a[SI<N>(k, i)];
+        }
+        const double K = 0.5 * bt * vp;
+#pragma unroll
+        for (int i = k + 1; i < N; ++i) pv[i] -= K * a[SI<N>(k, i)];
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+#pragma unroll
+            for (int j = 0; j < N; ++j)
+                if (i > k && j >= i) a[SI<N>(i, j)] -= a[SI<N>(k, i)] * pv[j] + pv[i] * a[SI<N>(k, j)];
+        ST::eset(S.col(k), alpha);
+        emax = fmax(emax, fabs(alpha));
+    }
+    ST::eset(S.col(N - 2), a[SI<N>(N - 2, N - 1)]);
+    ST::eset(S.col(N - 1), 0.0);
+    double dmax = 0;
+    emax = fmax(emax, fabs(a[SI<N>(N - 2, N - 1)]));
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        ST::dset(S.col(i), a[SI<N>(i, i)]);
+        dmax = fmax(dmax, fabs(a[SI<N>(i, i)]));
+    }
+    const double tol = 2e-15 * (dmax + emax);
+    // ---- 2. Q = H_0 H_1 ... H_{N-3} (backward accumulation; rows/columns <= k stay those of the identity)
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+            if (i == 0 || j == 0 || (i == N - 1 && j == N - 1)) ST::zset(S.col(j), i, i == j ? 1.0 : 0.0);
+#pragma unroll
+    for (int k = N - 3; k >= 0; --k) {
+        const double bt = beta[k];
+        { // column k+1 of the current block is e_{k+1}: s = beta v_{k+1}
+            const double s = bt * a[SI<N>(k, k + 1)];
+#pragma unroll
+            for (int i = k + 1; i < N; ++i) ST::zset(S.col(k + 1), i, (i == k + 1 ? 1.0 : 0.0) - s * a[SI<N>(k, i)]);
+        }
+#pragma unroll
+        for (int j = k + 2; j < N; ++j) {
+            double cj[N];
+            double s = 0;
+#pragma unroll
+            for (int i = k + 2; i < N; ++i) {
+                cj[i] = ST::z(S.col(j), i);
+                s += a[SI<N>(k, i)] * cj[i];
+            }
+            s *= bt;
+            ST::zset(S.col(j), k + 1, -s * a[SI<N>(k, k + 1)]);
+#pragma unroll
+            for (int i = k + 2; i < N; ++i) ST::zset(S.col(j), i, cj[i] - s * a[SI<N>(k, i)]);
+        }
+    }
+    // ---- 3. implicit QL with Wilkinson shift (tql2 / tqli structure), rotations accumulated into S
+    int l = 0;
+#ifdef IDP_QL_STATS
+    ++g_ql_stats.rows; g_ql_stats.n = 0;
+#endif
+    for (int trip = 0; trip < 30 * N; ++trip) {
+        // deflation scan: bit i set <=> e_i negligible (all loads independent, static offsets)
+        unsigned negl = 0;
+#pragma unroll
+        for (int i = 0; i < N - 1; ++i) negl |= (fabs(ST::e(S.col(i))) <= tol) ? (1u << i) : 0u;
+        l += first_set_bit(~(negl >> l)) - 1;                                 // skip converged eigenvalues
+        if (l >= N - 1) break;
+        const int m = l + first_set_bit((negl | (1u << (N - 1))) >> (l + 1)); // first negligible e above l (or the end)
+        double* cl = S.col(l);
+        const double* cm = S.col(m);
+        double zc[N]; // column carried between consecutive rotations (starts as column m)
+#pragma unroll
+        for (int k = 0; k < N; ++k) zc[k] = ST::z(cm, k);
+        const double dl = ST::d(cl), el = ST::e(cl);
+        double g = (ST::d(cl + ST::STRIDE_V) - dl) * 0.5 * rcp_nr2(fabs(el));
+        if (el < 0) g = -g;
+        const double r0 = (g * g + 1.0) * rsqrt_nr<2>(g * g + 1.0);
+        g = ST::d(cm) - dl + el * (g >= 0 ? rcp_nr2(g + r0) : -rcp_nr2(r0 - g));
+        double s = 1.0, c = 1.0, p = 0.0;
+        double cp = 1.0, sp = 0.0; // rotation whose column update is still pending
+        bool pend = false, underflow = false;
+#ifdef IDP_QL_STATS
+        ++g_ql_stats.trips; g_ql_stats.givens += m - l; if (g_ql_stats.n < 512) g_ql_stats.chase[g_ql_stats.n++] = m - l;
+#endif
+        double* ci = S.col(m - 1);
+        for (int i = m - 1; i >= l; --i, ci -= ST::STRIDE_V) {
+            // loads first: scalars of this step and the column needed by the pending rotation (columns i+1, i+2)
+            const double ei = ST::e(ci), di = ST::d(ci), di1 = ST::d(ci + ST::STRIDE_V);
+            double z0[N];
+            if (pend) {
+#pragma unroll
+                for (int k = 0; k < N; ++k) z0[k] = ST::z(ci + ST::STRIDE_V, k);
+            }
+            const double f = s * ei, b = c * ei;
+            const double r2 = f * f + g * g;
+            const bool ok = r2 > 1e-290;
+            if (ok) {
+                const double ir = rsqrt_nr<3>(r2);
+                ST::eset(ci + ST::STRIDE_V, r2 * ir);
+                s = f * ir; c = g * ir;
+                g = di1 - p;
+                const double rr = (di - g) * s + 2.0 * c * b;
+                p = s * rr;
+                ST::dset(ci + ST::STRIDE_V, g + p);
+                g = c * rr - b;
+            }
+            if (pend) {
+#pragma unroll
+                for (int k = 0; k < N; ++k) {
+                    ST::zset(ci + 2 * ST::STRIDE_V, k, sp * z0[k] + cp * zc[k]);
+                    zc[k] = cp * z0[k] - sp * zc[k];
+                }
+            }
+            if (!ok) { // recover from underflow (tqli): split here; the carried column is the current column i+1
+                ST::dset(ci + ST::STRIDE_V, di1 - p);
+                ST::eset(ci + ST::STRIDE_V, 0.0);
+#pragma unroll
+                for (int k = 0; k < N; ++k) ST::zset(ci + ST::STRIDE_V, k, zc[k]);
+                underflow = true;
+                break;
+            }
+            cp = c; sp = s; pend = true;
+        }
+        ST::eset(S.col(m), 0.0);
+        if (underflow) continue;
+        // flush the last rotation (columns l, l+1)
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            const double z0 = ST::z(cl, k);
+            ST::zset(cl + ST::STRIDE_V, k, sp * z0 + cp * zc[k]);
+            ST::zset(cl, k, cp * z0 - sp * zc[k]);
+        }
+        ST::dset(cl, dl - p);
+        ST::eset(cl, g);
+    }
+    // ---- 4. V max(lambda, 0) V^T
+    double lam[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const double x = ST::d(S.col(i));
+        lam[i] = x > 0 ? x : 0.0;
+    }
+#pragma unroll
+    for (int r = 0; r < N; ++r) {
+        double wr[N];
+#pragma unroll
+        for (int k = 0; k < N; ++k) wr[k] = ST::z(S.col(k), r) * lam[k];
+#pragma unroll
+        for (int c = r; c < N; ++c) {
+            double s = 0;
+#pragma unroll
+            for (int k = 0; k < N; ++k) s += wr[k] * ST::z(S.col(k), c);
+            a[SI<N>(r, c)] = s;
         }
     }
 }
@@ -548,7 +753,7 @@ IDP_HD bool row_eval(const RowDec& d, const V3* x, const V3* xr, double weight, 
         const double T[3][3] = {{0, -1, -1}, {-1, 0, -1}, {-1, 0, 1}};
         congruence_blocks<3>(T, H, M);
     }
-    if (projectSPD) make_pd_packed<9>(M, V9);
+    if (projectSPD) make_pd_ql<9>(M, V9);
     const double Hm[4][3] = {{0.5, 0.5, 0.5}, {-0.5, 0.5, -0.5}, {0.5, -0.5, -0.5}, {-0.5, -0.5, 0.5}};
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -576,7 +781,8 @@ struct DenseEmit {
 IDP_HD bool row_EgH_lowrank(const RowDec& d, const V3* x, const V3* xr, double weight, double dHat2, double kappa,
     double xi2, bool projectSPD, double* E, double* g, double* H)
 {
-    VLocal<9> V9;
+    double work[QlStore<9, 1>::WORDS];
+    QlStore<9, 1> V9{work};
     RowOut out;
     DenseEmit em{H, 3 * d.nv};
     const bool ok = row_eval<-1>(d, x, xr, weight, dHat2, kappa, xi2, projectSPD, H != nullptr, V9, out, em);
