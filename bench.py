@@ -278,16 +278,39 @@ def main():
     if os.path.exists(tpath):
         with open(tpath) as f:
             traffic = json.load(f).get("k_barrier_dram_bytes_per_launch")
-    roofline = {"kernel": "k_barrier<E,g,H> (per-row barrier E+g+H+PSD, FP64)", "bound": "hbm",
-                "achieved": alg_bytes / (kb_ms * 1e-3) / 1e9 if kb_ms > 0 else None, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": (alg_bytes / (kb_ms * 1e-3) / 1e9) / peaks["hbm_gbs"] if kb_ms > 0 else None, "traffic": traffic,
-                "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)", "launch_ms": kb_ms,
-                "algorithmic_bytes_per_launch": alg_bytes,
-                "fp64": {"achieved_tflops": alg_flops / (kb_ms * 1e-3) / 1e12 if kb_ms > 0 else None,
-                         "peak_tflops": fp64_peak, "peak_source": "measured live (idp_measure_fp64_tflops, DFMA chains)",
-                         "frac": (alg_flops / (kb_ms * 1e-3) / 1e12) / fp64_peak if kb_ms > 0 else None,
-                         "credited_flops_per_launch": alg_flops},
-                "row_kinds": kinds, "share_of_step": kb_ms * args.steps / ms if ms > 0 else None}
+    hbm_gbs = peaks["hbm_gbs"]
+    kb_s = kb_ms * 1e-3
+    # composite roofline of the whole step: T_roof = sum over stages of max(bytes / BW, flops / FP64 peak)
+    nV, nE, nF = mesh.nV, len(mesh.bedge), len(mesh.btri)
+    c_static = ctx.count(1) + ctx.count(2)
+    c_ccd = ctx.count(3) + ctx.count(4)
+    n_moll_pt = kinds["pt_ee"] + kinds["moll"]
+    blocks_row = {"pt_ee": 16, "moll": 16, "pe": 9, "pp": 4}
+    stage_alg = {
+        "broad_phase_static": (24.0 * nV + 12.0 * nF + 8.0 * nE + 16.0 * (nV + nE + nF) + 8.0 * c_static, 0.0),
+        "narrow_phase": (8.0 * c_static + 32.0 * n_rows, 0.0),
+        "barrier_EgH_psd": (alg_bytes, alg_flops),
+        "csr_assembly": (sum((72.0 + 8.0) * blocks_row[k] * v for k, v in kinds.items()) * share + 12.0 * nnz, 0.0),
+        "ccd": (24.0 * nV * 2 + 12.0 * nF + 8.0 * nE + 16.0 * (nV + nE + nF) + 200.0 * c_ccd + 8.0 * (nV + nE) / world,
+                60.0 * c_ccd + 300.0 * ctx.count(5)),
+        "min_dist": (120.0 * n_rows, 0.0),
+    }
+    t_roof = {k: max(b / (hbm_gbs * 1e9), f / (fp64_peak * 1e12)) for k, (b, f) in stage_alg.items()}
+    step_s = ms * 1e-3 / args.steps
+    composite = {"t_roof_ms": {k: 1e3 * v for k, v in t_roof.items()}, "t_roof_total_ms": 1e3 * sum(t_roof.values()),
+                 "t_measured_ms": 1e3 * step_s, "frac": sum(t_roof.values()) / step_s if step_s > 0 else None,
+                 "note": "per-rank algorithmic bytes/flops of SURVEY.md 8(d); static/CCD candidate counts of this rank"}
+    # the dominant kernel is bound by the FP64 pipe (arithmetic intensity ~16 flop/B >> machine balance ~5 flop/B), so the
+    # headline fraction is credited FP64 flops / measured FP64 peak; the HBM view of the same launch is kept beside it
+    roofline = {"kernel": "k_barrier<E,g,H> (per-row barrier E+g+H+PSD, FP64; three launches by row kind)", "bound": "fp64",
+                "achieved": alg_flops / kb_s / 1e12 if kb_ms > 0 else None, "peak": fp64_peak, "unit": "TFLOP/s",
+                "frac": (alg_flops / kb_s / 1e12) / fp64_peak if kb_ms > 0 else None, "traffic": traffic,
+                "peak_source": "measured live (idp_measure_fp64_tflops, register-resident DFMA chains; FP64 is not in MEASURED_PEAKS.json)",
+                "launch_ms": kb_ms, "credited_flops_per_launch": alg_flops, "algorithmic_bytes_per_launch": alg_bytes,
+                "hbm": {"achieved": alg_bytes / kb_s / 1e9 if kb_ms > 0 else None, "peak": hbm_gbs, "unit": "GB/s",
+                        "frac": (alg_bytes / kb_s / 1e9) / hbm_gbs if kb_ms > 0 else None,
+                        "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)"},
+                "row_kinds": kinds, "share_of_step": kb_ms * args.steps / ms if ms > 0 else None, "composite": composite}
 
     # ---- end to end through the C ABI with host buffers ----
     e2e = None
@@ -339,7 +362,7 @@ def main():
                 "config": {"workload": "%s: BASELINE configs[3] synthetic tangled multi-sheet surface (%d triangles, %d vertices), "
                                        "dHat=%g, kappa=%g, CCD alpha0=1" % (args.workload, mesh.nF, mesh.nV, dhat, KAPPA),
                            "pairs_per_step": pairs_per_step, "constraint_rows": int(n_rows), "ccd_candidates": int(ccd_local.item()),
-                           "static_candidates": None, "nnz": int(nnz), "sharding": "primitive ranges x%d" % world,
+                           "static_candidates": int(ctx.count(1) + ctx.count(2)), "nnz": int(nnz), "sharding": "primitive ranges x%d" % world,
                            "l2": "working set per step (candidate lists, 3x3 blocks, CSR) is several GB >> 126 MB L2; no explicit flush"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "library_primitive_calls": int(lib_calls),
                 "roofline": roofline, "cpu_baseline": ({k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")} if cb else None),

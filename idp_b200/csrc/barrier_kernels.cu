@@ -87,8 +87,9 @@ __global__ void __launch_bounds__(128) k_barrier(BarrierArgs a)
         }
         RowOut out;
         QlStore<9, 128> V9{sV + threadIdx.x};
+        QlStore<6, 128> V6{sV + threadIdx.x};
         BlockEmit em{a.blkKey, a.blkIdx, a.blkVal, WANT_H ? (long)a.blkOff[i] : 0L, d.nv, d.v, a.nVll};
-        const bool ok = row_eval<PATH>(d, x, xr, a.weights[i], a.dHat2, a.kappa, a.xi2, a.projectSPD != 0, WANT_H, V9, out, em);
+        const bool ok = row_eval<PATH>(d, x, xr, a.weights[i], a.dHat2, a.kappa, a.xi2, a.projectSPD != 0, WANT_H, V9, V6, out, em);
         if (!ok) { atomicAdd(a.errDist, 1ull); continue; }
         if (WANT_E) Eacc += out.E;
         if (WANT_G) {
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(128) k_barrier(BarrierArgs a)
 template <int PATH>
 static int launch_barrier_path(idp_ctx* c, BarrierArgs a, unsigned grid, int sel)
 {
-    const size_t smem = PATH == 0 ? QlStore<9, 128>::WORDS * sizeof(double) * 128 : 0;
+    const size_t smem = PATH == 0 ? QlStore<9, 128>::WORDS * sizeof(double) * 128 : (PATH == 1 ? QlStore<6, 128>::WORDS * sizeof(double) * 128 : 0);
 #define IDP_BARRIER_CASE(E, G, H)                                                                                         \
     do {                                                                                                                  \
         if (smem) IDP_CK(c, cudaFuncSetAttribute(k_barrier<PATH, E, G, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \

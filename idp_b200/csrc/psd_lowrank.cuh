@@ -7,9 +7,8 @@
 //     M = T^T H_r T, where T maps an ORTHONORMAL basis of the translation-free subspace (Hadamard basis of the stencil
 //     vertices) to the difference coordinates. Since H = Q M Q^T with Q orthonormal, eig(H) = eig(M) + three zeros and
 //     makePD(H) = Q makePD(M) Q^T exactly;
-//   * the symmetric eigen-decomposition is a cyclic Jacobi iteration on the packed upper triangle held in registers;
-//     the eigenvector matrix lives in shared memory (one column per thread, bank-conflict free) for 9x9 and in registers
-//     for 6x6; point-point rows have a closed form.
+//   * the symmetric eigen-decomposition is Householder tridiagonalisation (registers, fully unrolled) followed by
+//     implicit-shift QL with the eigenvector matrix in shared memory (make_pd_ql below); point-point rows have a closed form.
 // Reference semantics: FEM/IPC.h:801-938 (E), 1012-1254 (g), 1390-1729 (H); tolerance 1e-10 relative.
 #pragma once
 #include "pair_deriv.cuh"
@@ -48,164 +47,23 @@ IDP_HD double rsqrt_nr(double x)
     return 1.0 / sqrt(x);
 #endif
 }
-
-// eigenvector storage policies -------------------------------------------------------------------------------
-// The Jacobi loop relabels the matrix indices cyclically after every round (see jacobi_packed); the storage follows
-// with advance(): registers are permuted, shared memory only moves a column offset.
-template <int N>
-struct VLocal {
-    static constexpr int M = (N % 2) ? N : N - 1;
-    double v[N * N];
-    IDP_HD void init()
-    {
-#pragma unroll
-        for (int i = 0; i < N; ++i)
-#pragma unroll
-            for (int j = 0; j < N; ++j) v[i * N + j] = (i == j) ? 1.0 : 0.0;
-    }
-    IDP_HD double get(int r, int c) const { return v[r * N + c]; }
-    IDP_HD void set(int r, int c, double x) { v[r * N + c] = x; }
-    IDP_HD void advance()
-    {
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-            const double t0 = v[i * N];
-#pragma unroll
-            for (int j = 0; j + 1 < M; ++j) v[i * N + j] = v[i * N + j + 1];
-            v[i * N + M - 1] = t0;
-        }
-    }
-};
-// Jacobi eigenvalue iteration on the packed upper triangle a (N(N+1)/2 values); V receives the eigenvectors as
-// columns; on exit the diagonal of a holds the eigenvalues.
-// Pair order: round-robin tournament. The pairs of one round are disjoint, so their rotation parameters depend only on
-// their own 2x2 blocks and are computed together (independent rcp / rsqrt chains give the scheduler ILP), then applied.
-// Round r+1 of the circle method is round r with every index shifted by one, so instead of unrolling all rounds (a
-// 80 KB loop body that thrashes the instruction cache) the ROUND-0 code is executed M times and the matrix is relabelled
-// i -> i+1 (mod M) in between: a register permutation for a, a column offset for V. After M rounds (one sweep) the
-// labels are back in place. Converged when off-diagonal norm^2 <= 1e-24 * total norm^2: the PSD projection is
-// non-expansive, so the Frobenius error of the projected matrix is bounded by the remaining off-diagonal norm (1e-12 relative).
-template <int N, class VS>
-IDP_HD void jacobi_packed(double* a, VS& V)
+// one third-order step on the ~2^-20 hardware approximation (MUFU.RSQ64H works on the high word): with e = 1 - x y^2,
+// y (1 + e/2 + 3e^2/8) has relative error ~(5/16) e^3 < 2^-60, i.e. correctly rounded up to the last FMA. Four dependent
+// operations instead of the nine of three Newton steps: this sits on the serial chain of every Givens rotation.
+IDP_HD double rsqrt_h3(double x)
 {
-    constexpr int M = (N % 2) ? N : N - 1; // circle size; for even N index N-1 is the fixed player
-    constexpr int PAIRS = N / 2;
-    V.init();
-    for (int sweep = 0; sweep < 24; ++sweep) {
-        double off = 0, dia = 0;
-#pragma unroll
-        for (int p = 0; p < N; ++p)
-#pragma unroll
-            for (int q = p; q < N; ++q) {
-                const double x = a[SI<N>(p, q)];
-                if (p == q) dia += x * x;
-                else off += x * x;
-            }
-        if (off <= 1e-24 * (dia + 2.0 * off)) break;
-#pragma unroll 1
-        for (int round = 0; round < M; ++round) {
-            double cs[PAIRS], sn[PAIRS];
-#pragma unroll
-            for (int k = 0; k < PAIRS; ++k) {
-                // round-0 pairs: odd N: (k+1, M-1-k); even N: (0, N-1), (k, M-k)
-                const int p = (N % 2) ? (k + 1) : (k == 0 ? 0 : k);
-                const int q = (N % 2) ? (M - 1 - k) : (k == 0 ? N - 1 : M - k);
-                const double apq = a[SI<N>(p, q)], app = a[SI<N>(p, p)], aqq = a[SI<N>(q, q)];
-                const double delta = 0.5 * (aqq - app);
-                const double h2 = delta * delta + apq * apq;
-                double t = 0.0;
-                if (h2 > 1e-290 && apq != 0.0) {
-                    const double hyp = h2 * rsqrt_nr<1>(h2);                     // sqrt(delta^2 + apq^2)
-                    t = (delta >= 0 ? apq : -apq) * rcp_nr2(fabs(delta) + hyp); // tan of the rotation angle
-                }
-                const double c = rsqrt_nr<3>(t * t + 1.0), s = t * c;
-                cs[k] = c; sn[k] = s;
-                a[SI<N>(p, p)] = app - t * apq;
-                a[SI<N>(q, q)] = aqq + t * apq;
-                a[SI<N>(p, q)] = (t != 0.0) ? 0.0 : apq;
-            }
-#pragma unroll
-            for (int k = 0; k < PAIRS; ++k) {
-                const int p = (N % 2) ? (k + 1) : (k == 0 ? 0 : k);
-                const int q = (N % 2) ? (M - 1 - k) : (k == 0 ? N - 1 : M - k);
-                const double c = cs[k], s = sn[k];
-#pragma unroll
-                for (int i = 0; i < N; ++i) {
-                    if (i != p && i != q) {
-                        const double aip = a[SI<N>(i, p)], aiq = a[SI<N>(i, q)];
-                        a[SI<N>(i, p)] = c * aip - s * aiq;
-                        a[SI<N>(i, q)] = s * aip + c * aiq;
-                    }
-                }
-            }
-            // eigenvectors: the rotations of one round touch disjoint column pairs, so each row of V is loaded once
-            // (all loads of a row are independent and overlap), rotated, and stored
-#pragma unroll
-            for (int i = 0; i < N; ++i) {
-                double vp[PAIRS], vq[PAIRS];
-#pragma unroll
-                for (int k = 0; k < PAIRS; ++k) {
-                    const int p = (N % 2) ? (k + 1) : (k == 0 ? 0 : k);
-                    const int q = (N % 2) ? (M - 1 - k) : (k == 0 ? N - 1 : M - k);
-                    vp[k] = V.get(i, p);
-                    vq[k] = V.get(i, q);
-                }
-#pragma unroll
-                for (int k = 0; k < PAIRS; ++k) {
-                    const int p = (N % 2) ? (k + 1) : (k == 0 ? 0 : k);
-                    const int q = (N % 2) ? (M - 1 - k) : (k == 0 ? N - 1 : M - k);
-                    V.set(i, p, cs[k] * vp[k] - sn[k] * vq[k]);
-                    V.set(i, q, sn[k] * vp[k] + cs[k] * vq[k]);
-                }
-            }
-            // relabel: new(i, j) = old(sigma(i), sigma(j)), sigma(i) = i + 1 (mod M) on the circle, identity on the fixed player
-            {
-                double b[N * (N + 1) / 2];
-#pragma unroll
-                for (int i = 0; i < N; ++i)
-#pragma unroll
-                    for (int j = i; j < N; ++j) {
-                        const int si = (i < M) ? ((i + 1) % M) : i, sj = (j < M) ? ((j + 1) % M) : j;
-                        b[SI<N>(i, j)] = a[SI<N>(si, sj)];
-                    }
-#pragma unroll
-                for (int i = 0; i < N * (N + 1) / 2; ++i) a[i] = b[i];
-            }
-            V.advance();
-        }
-    }
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x * y, y, 1.0);
+    return fma(y * e, fma(0.375, e, 0.5), y);
+#else
+    return 1.0 / sqrt(x);
+#endif
 }
-
-// makePD on a packed symmetric matrix (in place). The matrix is always rebuilt as V diag(max(lambda,0)) V^T; when no
-// eigenvalue is negative this reproduces the input to rounding (the reference returns it untouched).
-template <int N, class VS>
-IDP_HD void make_pd_packed(double* m, VS& V)
-{
-    jacobi_packed<N>(m, V);
-    double lam[N];
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-        const double l = m[SI<N>(i, i)];
-        lam[i] = l > 0 ? l : 0.0;
-    }
-#pragma unroll
-    for (int r = 0; r < N; ++r) {
-        double wr[N];
-#pragma unroll
-        for (int k = 0; k < N; ++k) wr[k] = V.get(r, k) * lam[k];
-#pragma unroll
-        for (int c = r; c < N; ++c) {
-            double s = 0;
-#pragma unroll
-            for (int k = 0; k < N; ++k) s += wr[k] * V.get(c, k);
-            m[SI<N>(r, c)] = s;
-        }
-    }
-}
-
 
 // ---- makePD through Householder tridiagonalisation + implicit QL ----------------------------------------------------------
-// Same result as make_pd_packed (V max(lambda,0) V^T) at roughly a third of the arithmetic of cyclic Jacobi:
+// Result V max(lambda,0) V^T at roughly a third of the arithmetic of a cyclic Jacobi iteration:
 //   1. Householder reduction of the packed matrix to tridiagonal form T = Q^T M Q: fixed control flow, fully unrolled,
 //      every index static -> registers only;
 //   2. Q is formed explicitly in the work store S (shared memory on the device);
@@ -346,9 +204,10 @@ IDP_HD void make_pd_ql(double* a, ST& S)
         const int m = l + first_set_bit((negl | (1u << (N - 1))) >> (l + 1)); // first negligible e above l (or the end)
         double* cl = S.col(l);
         const double* cm = S.col(m);
-        double zc[N]; // column carried between consecutive rotations (starts as column m)
+        double zc[N], zl[N]; // zc: column carried between consecutive rotations (starts as column m); zl: column l,
+                             // only touched by the last rotation of the chase, fetched here so its latency is hidden
 #pragma unroll
-        for (int k = 0; k < N; ++k) zc[k] = ST::z(cm, k);
+        for (int k = 0; k < N; ++k) { zc[k] = ST::z(cm, k); zl[k] = ST::z(cl, k); }
         const double dl = ST::d(cl), el = ST::e(cl);
         double g = (ST::d(cl + ST::STRIDE_V) - dl) * 0.5 * rcp_nr2(fabs(el));
         if (el < 0) g = -g;
@@ -373,7 +232,7 @@ IDP_HD void make_pd_ql(double* a, ST& S)
             const double r2 = f * f + g * g;
             const bool ok = r2 > 1e-290;
             if (ok) {
-                const double ir = rsqrt_nr<3>(r2);
+                const double ir = rsqrt_h3(r2);
                 ST::eset(ci + ST::STRIDE_V, r2 * ir);
                 s = f * ir; c = g * ir;
                 g = di1 - p;
@@ -404,9 +263,8 @@ IDP_HD void make_pd_ql(double* a, ST& S)
         // flush the last rotation (columns l, l+1)
 #pragma unroll
         for (int k = 0; k < N; ++k) {
-            const double z0 = ST::z(cl, k);
-            ST::zset(cl + ST::STRIDE_V, k, sp * z0 + cp * zc[k]);
-            ST::zset(cl, k, cp * z0 - sp * zc[k]);
+            ST::zset(cl + ST::STRIDE_V, k, sp * zl[k] + cp * zc[k]);
+            ST::zset(cl, k, cp * zl[k] - sp * zc[k]);
         }
         ST::dset(cl, dl - p);
         ST::eset(cl, g);
@@ -563,16 +421,16 @@ IDP_HD void expand_block(const double (&Hm)[NV][K], const double* M, int i, int 
 
 // ---- row evaluation ------------------------------------------------------------------------------------------------
 // Outputs: E (scalar), g (3*nv), and the Hessian through the sink `emit(i, j, block9)` called for all nv^2 blocks.
-// VS9 is the eigenvector storage used for the 9x9 problems.
+// VS9 / VS6 are the QL work stores (QlStore) of the 9x9 / 6x6 projections.
 struct RowOut {
     double E;
     double g[12];
 };
 
 // PATH selects which kinds are compiled in: -1 all, 0 four-vertex kinds, 1 point-edge, 2 point-point
-template <int PATH, class VS9, class Emit>
+template <int PATH, class VS9, class VS6, class Emit>
 IDP_HD bool row_eval(const RowDec& d, const V3* x, const V3* xr, double weight, double dHat2, double kappa, double xi2,
-    bool projectSPD, bool wantH, VS9& V9, RowOut& out, Emit& emit)
+    bool projectSPD, bool wantH, VS9& V9, VS6& V6, RowOut& out, Emit& emit)
 {
     const double dist2 = row_dist2(d.kind, x[0], x[1], x[2], x[3]) - xi2;
     if (!(dist2 > 0)) return false;
@@ -638,10 +496,7 @@ IDP_HD bool row_eval(const RowDec& d, const V3* x, const V3* xr, double weight, 
             const double T[2][2] = {{r2, 0.0}, {ir2, -r32}};
             double M[21];
             congruence_blocks<2>(T, H6, M);
-            if (projectSPD) {
-                VLocal<6> V6;
-                make_pd_packed<6>(M, V6);
-            }
+            if (projectSPD) make_pd_ql<6>(M, V6);
             const double Hm[3][2] = {{ir2, ir6}, {-ir2, ir6}, {0.0, -2.0 * ir6}};
 #pragma unroll
             for (int i = 0; i < 3; ++i)
@@ -783,9 +638,10 @@ IDP_HD bool row_EgH_lowrank(const RowDec& d, const V3* x, const V3* xr, double w
 {
     double work[QlStore<9, 1>::WORDS];
     QlStore<9, 1> V9{work};
+    QlStore<6, 1> V6{work};
     RowOut out;
     DenseEmit em{H, 3 * d.nv};
-    const bool ok = row_eval<-1>(d, x, xr, weight, dHat2, kappa, xi2, projectSPD, H != nullptr, V9, out, em);
+    const bool ok = row_eval<-1>(d, x, xr, weight, dHat2, kappa, xi2, projectSPD, H != nullptr, V9, V6, out, em);
     if (!ok) return false;
     if (E) *E = out.E;
     if (g) for (int i = 0; i < 3 * d.nv; ++i) g[i] = out.g[i];
