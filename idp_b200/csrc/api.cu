@@ -110,6 +110,7 @@ int idp_set_mesh(idp_ctx* c, int nV, int nBN, const int* bnode, int nBE, const i
     c->nV = nV; c->nBN = nBN; c->nBE = nBE; c->nBT = nBT;
     c->have_x = c->have_x0 = c->have_dir = false;
     c->nRows = 0; c->nCandPT = c->nCandEE = c->nCcdPT = c->nCcdEE = 0;
+    c->permValid = false;
     IDP_CK(c, c->bnode.reserve(std::max(nBN, 1)));
     IDP_CK(c, c->bedge.reserve(std::max(nBE, 1)));
     IDP_CK(c, c->btri.reserve(std::max(nBT, 1)));
@@ -188,6 +189,7 @@ int idp_set_constraints(idp_ctx* c, int n, const int* rows4, const double* info2
     if (!c || n < 0 || (n && !rows4)) return IDP_ERR_INVALID;
     IDP_CK(c, cudaSetDevice(c->device));
     c->nRows = n;
+    c->permValid = false;
     c->weights_all_one = false;
     IDP_CK(c, c->rows.reserve(std::max(n, 1)));
     IDP_CK(c, c->weights.reserve(std::max(n, 1)));
@@ -345,6 +347,7 @@ int idp_set_shard(idp_ctx* c, int rank, int nranks)
     if (!c || nranks < 1 || rank < 0 || rank >= nranks) return IDP_ERR_INVALID;
     c->rank = rank;
     c->nranks = nranks;
+    c->permValid = false;
     return IDP_OK;
 }
 

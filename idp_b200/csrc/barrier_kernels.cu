@@ -10,6 +10,11 @@
 #include "psd_lowrank.cuh"
 #include <cub/cub.cuh>
 
+#ifndef IDP_BARRIER_T0
+#define IDP_BARRIER_T0 128
+#define IDP_BARRIER_B0 2
+#endif
+
 namespace idp {
 
 __device__ __forceinline__ V3 ldv4(const double4* __restrict__ p, int v)
@@ -31,9 +36,30 @@ __global__ void k_row_block_counts(const Row4* __restrict__ rows, long n, int ra
         cnt[i] = k;
     }
 }
+// kind of every row of this rank (7 = row of another rank) + identity permutation; kinds are counted per block and added
+// once (counts are order independent, so the result is deterministic)
+__global__ void __launch_bounds__(256) k_row_kinds(const Row4* __restrict__ rows, long n, int rank, int nranks, unsigned char* __restrict__ kind,
+    int* __restrict__ iota, unsigned long long* __restrict__ kindCount)
+{
+    __shared__ int sh[8];
+    if (threadIdx.x < 8) sh[threadIdx.x] = 0;
+    __syncthreads();
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        int k = 7;
+        if ((i % nranks) == rank) {
+            const Row4 r = rows[i];
+            k = decode_row(r.a, r.b, r.c, r.d).kind;
+        }
+        kind[i] = (unsigned char)k;
+        iota[i] = (int)i;
+        atomicAdd(&sh[k], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < 8 && sh[threadIdx.x]) atomicAdd(&kindCount[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
+}
 
 struct BarrierArgs {
-    const Row4* rows; const double* weights; long rowBegin, rowEnd, rowStride;
+    const Row4* rows; const double* weights; const int* perm; long jBegin, jEnd; // rows perm[jBegin..jEnd): one path, sorted by kind
     const double4* xp; const double4* x0p;
     double dHat2, kappa, xi2;
     int projectSPD;
@@ -64,20 +90,24 @@ struct BlockEmit {
     }
 };
 
-// One thread per constraint row. PATH 0: four-vertex kinds (PT, EE and the three mollified kinds; 9x9 Jacobi with the
-// eigenvectors in shared memory), PATH 1: point-edge (6x6 Jacobi in registers), PATH 2: point-point (closed form).
-// Each launch walks all rows of the shard and skips the kinds of the other paths, so rows keep their positions and the
-// outputs (block offsets, partial sums) are deterministic.
+// One thread per constraint row. PATH 0: four-vertex kinds (PT, EE and the three mollified kinds; 9x9 QL with the work
+// store in shared memory), PATH 1: point-edge (6x6 QL), PATH 2: point-point (closed form).
+// Rows are visited through a permutation that groups them by kind (stable, so memory locality of the constraint order is
+// kept inside a kind): the lanes of a warp run the same distance formulas and the three launches see only their own
+// rows. Outputs keep their positions (block offsets by row index), so the results do not depend on the visiting order.
+// Threads per block / resident blocks per SM by path. PATH 0 is limited by the 99-word shared work store per row
+// (792 B): 2 blocks x 128 rows = 8 warps per SM at 255 registers (9 warps would need 96-thread blocks, but registers are
+// allocated per 4 warps, which caps them at 168 and spills 1.4 KB per row).
+template <int PATH> struct BarrierCfg { static constexpr int T = PATH == 0 ? IDP_BARRIER_T0 : 128; static constexpr int MINB = PATH == 0 ? IDP_BARRIER_B0 : (PATH == 1 ? 3 : 4); };
 template <int PATH, bool WANT_E, bool WANT_G, bool WANT_H>
-__global__ void __launch_bounds__(128) k_barrier(BarrierArgs a)
+__global__ void __launch_bounds__(BarrierCfg<PATH>::T, BarrierCfg<PATH>::MINB) k_barrier(BarrierArgs a)
 {
     extern __shared__ double sV[];
     double Eacc = 0;
-    for (long i = a.rowBegin + a.rowStride * ((long)blockIdx.x * blockDim.x + threadIdx.x); i < a.rowEnd; i += a.rowStride * (long)gridDim.x * blockDim.x) {
+    for (long j = a.jBegin + (long)blockIdx.x * blockDim.x + threadIdx.x; j < a.jEnd; j += (long)gridDim.x * blockDim.x) {
+        const long i = a.perm[j];
         const Row4 r = a.rows[i];
         const RowDec d = decode_row(r.a, r.b, r.c, r.d);
-        const int path = (d.kind == K_PP) ? 2 : (d.kind == K_PE ? 1 : 0);
-        if (path != PATH) continue;
         V3 x[4], xr[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) x[k] = ldv4(a.xp, d.v[k]);
@@ -86,8 +116,8 @@ __global__ void __launch_bounds__(128) k_barrier(BarrierArgs a)
             for (int k = 0; k < 4; ++k) xr[k] = ldv4(a.x0p, d.v[k]);
         }
         RowOut out;
-        QlStore<9, 128> V9{sV + threadIdx.x};
-        QlStore<6, 128> V6{sV + threadIdx.x};
+        QlStore<9, BarrierCfg<PATH>::T> V9{sV + threadIdx.x};
+        QlStore<6, BarrierCfg<PATH>::T> V6{sV + threadIdx.x};
         BlockEmit em{a.blkKey, a.blkIdx, a.blkVal, WANT_H ? (long)a.blkOff[i] : 0L, d.nv, d.v, a.nVll};
         const bool ok = row_eval<PATH>(d, x, xr, a.weights[i], a.dHat2, a.kappa, a.xi2, a.projectSPD != 0, WANT_H, V9, V6, out, em);
         if (!ok) { atomicAdd(a.errDist, 1ull); continue; }
@@ -103,7 +133,7 @@ __global__ void __launch_bounds__(128) k_barrier(BarrierArgs a)
         }
     }
     if (WANT_E) {
-        typedef cub::BlockReduce<double, 128> BR;
+        typedef cub::BlockReduce<double, BarrierCfg<PATH>::T> BR;
         __shared__ typename BR::TempStorage tmp;
         const double s = BR(tmp).Sum(Eacc);
         if (threadIdx.x == 0) a.partialE[blockIdx.x] = s;
@@ -113,11 +143,12 @@ __global__ void __launch_bounds__(128) k_barrier(BarrierArgs a)
 template <int PATH>
 static int launch_barrier_path(idp_ctx* c, BarrierArgs a, unsigned grid, int sel)
 {
-    const size_t smem = PATH == 0 ? QlStore<9, 128>::WORDS * sizeof(double) * 128 : (PATH == 1 ? QlStore<6, 128>::WORDS * sizeof(double) * 128 : 0);
+    constexpr int T = BarrierCfg<PATH>::T;
+    const size_t smem = PATH == 0 ? QlStore<9, T>::WORDS * sizeof(double) * T : (PATH == 1 ? QlStore<6, T>::WORDS * sizeof(double) * T : 0);
 #define IDP_BARRIER_CASE(E, G, H)                                                                                         \
     do {                                                                                                                  \
         if (smem) IDP_CK(c, cudaFuncSetAttribute(k_barrier<PATH, E, G, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        IDP_LAUNCH(c, (k_barrier<PATH, E, G, H>), grid, 128, smem, a);                                                  \
+        IDP_LAUNCH(c, (k_barrier<PATH, E, G, H>), grid, T, smem, a);                                                  \
     } while (0)
     switch (sel) {
     case 1: IDP_BARRIER_CASE(true, false, false); break;
@@ -158,12 +189,31 @@ int barrier_eval(idp_ctx* c, double dhat2, double kappa, double thickness, int w
     if (c->nRows == 0) return IDP_OK;
     StageTimer tm(c, IDP_STAGE_BARRIER);
     IDP_CK(c, cudaMemsetAsync(c->counters.p + CNT_ERR_DIST, 0, sizeof(long long), c->stream));
-    // rows are dealt round-robin: rank r evaluates rows r, r + P, r + 2P, ...
-    const long rb = c->rank, re = c->nRows;
+    // rows are dealt round-robin: rank r evaluates rows r, r + P, r + 2P, ... in an order grouped by kind
     const long nMine = c->nRows > c->rank ? (c->nRows - c->rank + c->nranks - 1) / c->nranks : 0;
-    const unsigned grid = std::max(1u, std::min(blocks_for(nMine, 128), (unsigned)c->sm_count * 16));
+    if (!c->permValid) {
+        IDP_CK(c, c->rowKind.reserve(c->nRows)); IDP_CK(c, c->rowKindSorted.reserve(c->nRows));
+        IDP_CK(c, c->rowIota.reserve(c->nRows)); IDP_CK(c, c->rowPerm.reserve(c->nRows));
+        unsigned long long* dKind = (unsigned long long*)(c->counters.p + CNT_KINDS);
+        IDP_CK(c, cudaMemsetAsync(dKind, 0, 8 * sizeof(long long), c->stream));
+        IDP_LAUNCH(c, k_row_kinds, std::min(blocks_for(c->nRows, 256), (unsigned)c->sm_count * 16), 256, 0, c->rows.p, c->nRows, c->rank, c->nranks,
+            c->rowKind.p, c->rowIota.p, dKind);
+        size_t bytes = 0;
+        IDP_CK(c, cub::DeviceRadixSort::SortPairs(nullptr, bytes, c->rowKind.p, c->rowKindSorted.p, c->rowIota.p, c->rowPerm.p, (int)c->nRows, 0, 3, c->stream));
+        IDP_CK(c, c->cubTemp.reserve(bytes));
+        IDP_CK(c, cub::DeviceRadixSort::SortPairs(c->cubTemp.p, bytes, c->rowKind.p, c->rowKindSorted.p, c->rowIota.p, c->rowPerm.p, (int)c->nRows, 0, 3, c->stream));
+        ++c->lib_launches;
+        long long hk[8];
+        IDP_CK(c, cudaMemcpyAsync(hk, dKind, sizeof(hk), cudaMemcpyDeviceToHost, c->stream));
+        IDP_CK(c, cudaStreamSynchronize(c->stream));
+        for (int k = 0; k < 8; ++k) c->kindCount[k] = hk[k];
+        c->permValid = true;
+    }
+    const long nPath[3] = {c->kindCount[K_EE] + c->kindCount[K_EE_M] + c->kindCount[K_PE_M] + c->kindCount[K_PP_M] + c->kindCount[K_PT],
+        c->kindCount[K_PE], c->kindCount[K_PP]};
+    const unsigned grid = std::max(1u, std::min(blocks_for(std::max(nPath[0], std::max(nPath[1], nPath[2])), 128), (unsigned)c->sm_count * 16));
     BarrierArgs a;
-    a.rows = c->rows.p; a.weights = c->weights.p; a.rowBegin = rb; a.rowEnd = re; a.rowStride = c->nranks;
+    a.rows = c->rows.p; a.weights = c->weights.p; a.perm = c->rowPerm.p; a.jBegin = 0; a.jEnd = 0;
     a.xp = c->xp.p; a.x0p = c->x0p.p;
     a.dHat2 = dhat2 + 2 * std::sqrt(dhat2) * thickness; // IPC.h:757
     a.kappa = kappa; a.xi2 = thickness * thickness; a.projectSPD = project_spd;
@@ -197,11 +247,17 @@ int barrier_eval(idp_ctx* c, double dhat2, double kappa, double thickness, int w
         KernelTimer kt(c, IDP_STAGE_K_BARRIER);
         const int sel = (want_e ? 1 : 0) | (want_g ? 2 : 0) | (want_h ? 4 : 0);
         BarrierArgs a0 = a, a1 = a, a2 = a;
+        a0.jBegin = 0; a0.jEnd = nPath[0];
+        a1.jBegin = nPath[0]; a1.jEnd = nPath[0] + nPath[1];
+        a2.jBegin = nPath[0] + nPath[1]; a2.jEnd = nPath[0] + nPath[1] + nPath[2];
         a1.partialE = a.partialE + grid;
         a2.partialE = a.partialE + 2 * (size_t)grid;
-        IDP_TRY(launch_barrier_path<0>(c, a0, grid, sel));
-        IDP_TRY(launch_barrier_path<1>(c, a1, grid, sel));
-        IDP_TRY(launch_barrier_path<2>(c, a2, grid, sel));
+        if (want_e) IDP_CK(c, cudaMemsetAsync(c->red.p, 0, 3 * (size_t)grid * sizeof(double), c->stream));
+        const unsigned g0 = std::max(1u, std::min(blocks_for(nPath[0], BarrierCfg<0>::T), grid)), g1 = std::max(1u, std::min(blocks_for(nPath[1], 128), grid)),
+                       g2 = std::max(1u, std::min(blocks_for(nPath[2], 128), grid));
+        if (nPath[0] > 0) IDP_TRY(launch_barrier_path<0>(c, a0, g0, sel));
+        if (nPath[1] > 0) IDP_TRY(launch_barrier_path<1>(c, a1, g1, sel));
+        if (nPath[2] > 0) IDP_TRY(launch_barrier_path<2>(c, a2, g2, sel));
     }
     if (nMine > 0 && want_e) IDP_LAUNCH(c, k_sum_partials, 1, 256, 0, c->red.p, 3 * (int)grid, c->red.p + 3 * (size_t)grid);
     long long nerr = 0;

@@ -194,5 +194,6 @@ extern "C" int idp_comm_init(idp_ctx* c, int rank, int nranks, const void* id128
     if (r != 0) return fail(c, IDP_ERR_NCCL, "NCCL error: %s at %s:%d", g_nccl.errstr ? g_nccl.errstr(r) : "?", __FILE__, __LINE__);
     c->rank = rank;
     c->nranks = nranks;
+    c->permValid = false;
     return IDP_OK;
 }

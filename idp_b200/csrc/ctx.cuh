@@ -140,6 +140,11 @@ struct idp_ctx {
     idp::DBuf<double> gbuf;             // 3*nV gradient (xyz interleaved)
     idp::DBuf<double> rowDist2;
     idp::DBuf<int> rowBlkOff;
+    // evaluation order of this rank's rows: stable sort by row kind (uniform warps); rebuilt when the rows change
+    idp::DBuf<unsigned char> rowKind, rowKindSorted;
+    idp::DBuf<int> rowIota, rowPerm;
+    long kindCount[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    bool permValid = false;
     idp::DBuf<unsigned long long> blkKey, blkKeySorted;
     idp::DBuf<int> blkIdx, blkIdxSorted, segId, segStart;
     idp::DBuf<double> blkVal;
@@ -199,7 +204,8 @@ enum Counter {
     CNT_CCD_ITERS = 5,
     CNT_RUNS = 6,
     CNT_ALPHA_BITS = 7, // current CCD step as double bits (atomicMin on positive doubles)
-    CNT_COUNT = 16
+    CNT_KINDS = 16,     // 8 slots: rows of this rank per kind (k_row_kinds)
+    CNT_COUNT = 24
 };
 
 struct StageTimer {

@@ -862,6 +862,7 @@ static void shard_range(const idp_ctx* c, long n, int* b, int* e)
 // ------------------------------------------------------------------------------------------------------------
 int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
 {
+    c->permValid = false;
     if (!c->have_x) return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "positions not set", __FILE__, __LINE__);
     if (!c->have_x0) return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "rest positions not set", __FILE__, __LINE__);
     const double dHat = std::sqrt(dhat2_in) + thickness; // IPC.h:53-54
