@@ -25,6 +25,14 @@ struct __align__(32) IBox {
     int hi[3];
     int pad[2];
 };
+// compact cell-sorted filter record (32 B) read by the broad-phase traversal instead of chasing entries[] -> PrimRec:
+// static phase: the primitive's AABB rounded OUTWARD to float (a conservative pre-filter, the exact FP64 predicate is
+// applied to the survivors); CCD: its integer lattice box (the reference's "shares a voxel" test is exact on these).
+struct __align__(32) CRec {
+    union { float f[6]; int i[6]; } box; // lo[3], hi[3]
+    int b;    // primitive index
+    int aux;  // CCD (multi insertion): x index of the cell this copy lives in
+};
 struct __align__(16) Row4 {
     int a, b, c, d;
     __host__ __device__ bool operator==(const Row4& o) const { return a == o.a && b == o.b && c == o.c && d == o.d; }
@@ -122,7 +130,8 @@ struct idp_ctx {
     idp::DBuf<idp::PrimRec> recN, recE, recT;
     idp::DBuf<idp::IBox> boxNq, boxEq, boxEb, boxTb; // query boxes (inflated) and insert boxes
     idp::DBuf<idp::IBox> vbox;                        // per-vertex lattice box (CCD)
-    idp::DBuf<int> cellStart, cellCursor, entries, largeList, histScratch;
+    idp::DBuf<int> cellStart, cellCursor, largeList, histScratch;
+    idp::DBuf<idp::CRec> crec;          // cell-sorted compact records (one per stored (cell, primitive) entry)
     idp::DBuf<int2> candPT, candEE;
     long nCandPT = 0, nCandEE = 0;
     idp::DBuf<double> red;              // reduction scratch

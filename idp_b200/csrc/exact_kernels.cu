@@ -353,24 +353,32 @@ __global__ void k_extent_hist(const IBox* __restrict__ bbox, int nB, GridDesc g,
 // primitive is stored in every cell its box overlaps and a pair is accepted only in the componentwise max of the two
 // boxes' low corners, which again meets every pair exactly once.
 template <bool FILL>
-__global__ void k_cells_multi(const IBox* __restrict__ bbox, int nB, GridDesc g, int* __restrict__ cellCountOrCursor, int* __restrict__ entries)
+__global__ void k_cells_multi(const IBox* __restrict__ bbox, int nB, GridDesc g, int* __restrict__ cellCountOrCursor, CRec* __restrict__ crec)
 {
     for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nB; b += gridDim.x * blockDim.x) {
         int lo[3], hi[3];
-        cell_range(g, bbox[b], lo, hi);
+        const IBox bb = bbox[b];
+        cell_range(g, bb, lo, hi);
+        CRec rc;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { rc.box.i[k] = bb.lo[k]; rc.box.i[3 + k] = bb.hi[k]; }
+        rc.b = b;
         for (int iz = lo[2]; iz <= hi[2]; ++iz)
             for (int iy = lo[1]; iy <= hi[1]; ++iy) {
                 const long row = ((long)iz * g.n[1] + iy) * g.n[0];
                 for (int ix = lo[0]; ix <= hi[0]; ++ix) {
-                    if (FILL) entries[atomicAdd(&cellCountOrCursor[row + ix], 1)] = b;
+                    if (FILL) {
+                        rc.aux = ix;
+                        crec[atomicAdd(&cellCountOrCursor[row + ix], 1)] = rc;
+                    }
                     else atomicAdd(&cellCountOrCursor[row + ix], 1);
                 }
             }
     }
 }
 template <bool FILL>
-__global__ void k_cells(const IBox* __restrict__ bbox, int nB, GridDesc g, EMax emax, int* __restrict__ cellCountOrCursor,
-    int* __restrict__ entries, int* __restrict__ large, int* __restrict__ largeCount)
+__global__ void k_cells(const IBox* __restrict__ bbox, const PrimRec* __restrict__ rec, int nB, GridDesc g, EMax emax,
+    int* __restrict__ cellCountOrCursor, CRec* __restrict__ crec, int* __restrict__ large, int* __restrict__ largeCount)
 {
     for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nB; b += gridDim.x * blockDim.x) {
         int lo[3], hi[3];
@@ -380,7 +388,14 @@ __global__ void k_cells(const IBox* __restrict__ bbox, int nB, GridDesc g, EMax 
             continue;
         }
         const long cell = ((long)lo[2] * g.n[1] + lo[1]) * g.n[0] + lo[0];
-        if (FILL) entries[atomicAdd(&cellCountOrCursor[cell], 1)] = b;
+        if (FILL) {
+            const PrimRec r = rec[b];
+            CRec rc;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { rc.box.f[k] = __double2float_rd(r.lo[k]); rc.box.f[3 + k] = __double2float_ru(r.hi[k]); }
+            rc.b = b; rc.aux = 0;
+            crec[atomicAdd(&cellCountOrCursor[cell], 1)] = rc;
+        }
         else atomicAdd(&cellCountOrCursor[cell], 1);
     }
 }
@@ -398,7 +413,7 @@ int cub_scan_exclusive(idp_ctx* c, const int* in, int* out, long n)
 static long grid_cells(const GridDesc& g) { return (long)g.n[0] * g.n[1] * g.n[2]; }
 
 #define IDP_LARGE_CAP 4096
-// Build cellStart (nCells + 1), entries and the large list for the insert boxes bbox[0..nB). Chooses the smallest
+// Build cellStart (nCells + 1), the cell-sorted records and the large list for the insert boxes bbox[0..nB). Chooses the smallest
 // emax <= 3 that leaves at most IDP_LARGE_CAP primitives on the large list; if there is none the cells are coarsened
 // (g.k doubled: a cell is k^3 lattice voxels) and the choice is repeated.
 static int build_cells_multi(idp_ctx* c, const IBox* bbox, int nB, const GridDesc& g)
@@ -408,19 +423,19 @@ static int build_cells_multi(idp_ctx* c, const IBox* bbox, int nB, const GridDes
     IDP_CK(c, c->cellCursor.reserve(nc + 1));
     IDP_CK(c, cudaMemsetAsync(c->cellCursor.p, 0, (nc + 1) * sizeof(int), c->stream));
     IDP_CK(c, cudaMemsetAsync((int*)c->histScratch.p + 48, 0, sizeof(int), c->stream)); // empty large list
-    IDP_LAUNCH(c, k_cells_multi<false>, blocks_for(nB, 256), 256, 0, bbox, nB, g, c->cellCursor.p, nullptr);
+    IDP_LAUNCH(c, k_cells_multi<false>, blocks_for(nB, 256), 256, 0, bbox, nB, g, c->cellCursor.p, (CRec*)nullptr);
     IDP_TRY(cub_scan_exclusive(c, c->cellCursor.p, c->cellStart.p, nc + 1));
     int total = 0;
     IDP_CK(c, cudaMemcpyAsync(&total, c->cellStart.p + nc, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     IDP_CK(c, cudaStreamSynchronize(c->stream));
-    IDP_CK(c, c->entries.reserve((size_t)std::max(total, 1)));
+    IDP_CK(c, c->crec.reserve((size_t)std::max(total, 1)));
     IDP_CK(c, c->largeList.reserve(IDP_LARGE_CAP + 1));
     IDP_CK(c, cudaMemcpyAsync(c->cellCursor.p, c->cellStart.p, (nc + 1) * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
-    IDP_LAUNCH(c, k_cells_multi<true>, blocks_for(nB, 256), 256, 0, bbox, nB, g, c->cellCursor.p, c->entries.p);
+    IDP_LAUNCH(c, k_cells_multi<true>, blocks_for(nB, 256), 256, 0, bbox, nB, g, c->cellCursor.p, c->crec.p);
     IDP_CK(c, cudaGetLastError());
     return IDP_OK;
 }
-static int build_cells(idp_ctx* c, const IBox* bbox, int nB, GridDesc& g, const int latN[3], EMax* emaxOut, int* nLargeOut)
+static int build_cells(idp_ctx* c, const IBox* bbox, const PrimRec* rec, int nB, GridDesc& g, const int latN[3], EMax* emaxOut, int* nLargeOut)
 {
     int* dHist = (int*)c->histScratch.p; // 48 ints
     int hist[48];
@@ -456,11 +471,11 @@ static int build_cells(idp_ctx* c, const IBox* bbox, int nB, GridDesc& g, const 
     int* dLargeCount = (int*)c->histScratch.p + 48;
     IDP_CK(c, cudaMemsetAsync(c->cellCursor.p, 0, (nc + 1) * sizeof(int), c->stream));
     IDP_CK(c, cudaMemsetAsync(dLargeCount, 0, sizeof(int), c->stream));
-    IDP_LAUNCH(c, (k_cells<false>), blocks_for(nB, 256), 256, 0, bbox, nB, g, em, c->cellCursor.p, nullptr, nullptr, nullptr);
+    IDP_LAUNCH(c, (k_cells<false>), blocks_for(nB, 256), 256, 0, bbox, rec, nB, g, em, c->cellCursor.p, (CRec*)nullptr, (int*)nullptr, (int*)nullptr);
     IDP_TRY(cub_scan_exclusive(c, c->cellCursor.p, c->cellStart.p, nc + 1));
-    IDP_CK(c, c->entries.reserve((size_t)std::max(nB, 1)));
+    IDP_CK(c, c->crec.reserve((size_t)std::max(nB, 1)));
     IDP_CK(c, cudaMemcpyAsync(c->cellCursor.p, c->cellStart.p, (nc + 1) * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
-    IDP_LAUNCH(c, (k_cells<true>), blocks_for(nB, 256), 256, 0, bbox, nB, g, em, c->cellCursor.p, c->entries.p, c->largeList.p, dLargeCount);
+    IDP_LAUNCH(c, (k_cells<true>), blocks_for(nB, 256), 256, 0, bbox, rec, nB, g, em, c->cellCursor.p, c->crec.p, c->largeList.p, dLargeCount);
     IDP_CK(c, cudaGetLastError());
     *emaxOut = em;
     *nLargeOut = nLarge;
@@ -468,41 +483,30 @@ static int build_cells(idp_ctx* c, const IBox* bbox, int nB, GridDesc& g, const 
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// broad-phase query: one warp per query primitive. The (y,z) rows of the visited cell block are contiguous runs of
-// `entries`; their bounds are fetched by the lanes in parallel, prefix-summed with shuffles, and the concatenated runs
-// are then walked 32 entries at a time (warp-level load-balanced search), so no lane idles on short rows and the row
-// bounds cost one memory round trip instead of one per row. Survivors are compacted with ballot/popc and appended with
-// one atomic per warp batch.
+// broad-phase query: one warp per query primitive.
+// The (y,z) rows of the visited cell block are contiguous runs of the cell-sorted compact records (CRec). Every lane
+// takes one run -- or one slice of a run when the block has fewer than 17 rows, so that all 32 lanes are busy -- and
+// scans it sequentially: two 16-byte loads and a handful of float / integer compares per record (the coarse filter:
+// index order, outward-rounded float AABB for the static phase; canonical cell + lattice-box overlap, both exact, for
+// CCD). Survivors are pushed to a per-warp queue in shared memory with ballot/popc; whenever 32 are waiting the whole
+// warp runs the exact predicate on them (one 64-byte PrimRec each: shared vertices, Dirichlet flags, FP64 AABB gap) and
+// appends the hits with one atomic. The exact test therefore always runs on full warps, and the scan loop stays short.
 // MODE bit0: 0 = point queries vs triangles, 1 = edge queries vs edges (partner index > query index);
-// MODE bit1: CCD (require lattice-box overlap = "shares a voxel" of the reference's hash)
+// MODE bit1: CCD (multi insertion; require lattice-box overlap = "shares a voxel" of the reference's hash)
 // ------------------------------------------------------------------------------------------------------------
 struct QueryArgs {
     const PrimRec* qrec; const IBox* qbox; int qBegin, qEnd;
     const PrimRec* brec; const IBox* bbox;
-    const int* cellStart; const int* entries;
+    const int* cellStart; const CRec* crec;
     GridDesc g;
     double dist; // dHat (static) or thickness (CCD)
     EMax emax; const int* large; const int* nLargePtr; // device count of the large list
     int2* out; long cap; unsigned long long* counter;
 };
-// (iy, iz, i): row and entry slot the pair was met in (MULTI insertion only: canonical-cell test)
+// exact predicate on a (query, partner) pair that passed the coarse filter (IPC.h:171-172, 384-385; CCD.h:149-235)
 template <int MODE>
-__device__ __forceinline__ bool pair_passes(const QueryArgs& a, long q, int b, const PrimRec& qr, const IBox& qb, const V3& qL, const V3& qH,
-    const int* qlo, int iy, int iz, int i)
+__device__ __forceinline__ bool pair_exact(const QueryArgs& a, int b, const PrimRec& qr, const V3& qL, const V3& qH)
 {
-    if ((MODE & 1) && b <= (int)q) return false; // eJ > eI (IPC.h:384, SPATIAL_HASH.h:265)
-    if (MODE & 2) {
-        const IBox bb = a.bbox[b];
-        if (i >= 0) {
-            int blo[3], bhi[3];
-            cell_range(a.g, bb, blo, bhi);
-            if (max(qlo[1], blo[1]) != iy || max(qlo[2], blo[2]) != iz) return false;
-            const long c = ((long)iz * a.g.n[1] + iy) * a.g.n[0] + max(qlo[0], blo[0]);
-            if (i < a.cellStart[c] || i >= a.cellStart[c + 1]) return false;
-        }
-        if (!(qb.lo[0] <= bb.hi[0] && bb.lo[0] <= qb.hi[0] && qb.lo[1] <= bb.hi[1] && bb.lo[1] <= qb.hi[1] &&
-              qb.lo[2] <= bb.hi[2] && bb.lo[2] <= qb.hi[2])) return false;
-    }
     const PrimRec br = a.brec[b];
     bool ok;
     if (MODE & 1) ok = !(qr.v[0] == br.v[0] || qr.v[0] == br.v[1] || qr.v[1] == br.v[0] || qr.v[1] == br.v[1]); // shared vertex (IPC.h:384)
@@ -510,60 +514,114 @@ __device__ __forceinline__ bool pair_passes(const QueryArgs& a, long q, int b, c
     ok = ok && !((qr.flags & 1) && (br.flags & 1));                                                                  // all Dirichlet (:172, :385)
     return ok && aabb_gap_ok(qL, qH, mk3(br.lo[0], br.lo[1], br.lo[2]), mk3(br.hi[0], br.hi[1], br.hi[2]), a.dist);
 }
+// large-list entries (static phase only): index order + exact predicate
 template <int MODE>
-__global__ void __launch_bounds__(256) k_query(QueryArgs a)
+__device__ __forceinline__ bool pair_large(const QueryArgs& a, long q, int b, const PrimRec& qr, const V3& qL, const V3& qH)
 {
-    const int warpsPerBlock = blockDim.x >> 5;
-    const long warp0 = (long)blockIdx.x * warpsPerBlock + (threadIdx.x >> 5);
-    const long nWarps = (long)gridDim.x * warpsPerBlock;
+    if ((MODE & 1) && b <= (int)q) return false; // eJ > eI (IPC.h:384, SPATIAL_HASH.h:265)
+    return pair_exact<MODE>(a, b, qr, qL, qH);
+}
+#define IDP_QUERY_WARPS 8
+template <int MODE>
+__global__ void __launch_bounds__(32 * IDP_QUERY_WARPS) k_query(QueryArgs a)
+{
+    __shared__ int squeue[IDP_QUERY_WARPS][64];
+    const int wib = threadIdx.x >> 5;
+    const long warp0 = (long)blockIdx.x * IDP_QUERY_WARPS + wib;
+    const long nWarps = (long)gridDim.x * IDP_QUERY_WARPS;
     const int lane = lane_id();
+    const unsigned lt = (1u << lane) - 1u;
+    int* sq = squeue[wib];
     for (long q = a.qBegin + warp0; q < a.qEnd; q += nWarps) {
         const PrimRec qr = a.qrec[q];
         const IBox qb = a.qbox[q];
         int qlo[3], qhi[3];
         cell_range(a.g, qb, qlo, qhi);
+        int clo[3]; // cell-space low corner of the query box (canonical-cell rule of the multi insertion)
 #pragma unroll
-        for (int k = 0; k < 3; ++k) qlo[k] = max(qlo[k] - a.emax.e[k], 0);
+        for (int k = 0; k < 3; ++k) { clo[k] = qlo[k]; qlo[k] = max(qlo[k] - a.emax.e[k], 0); }
         const V3 qL = mk3(qr.lo[0], qr.lo[1], qr.lo[2]), qH = mk3(qr.hi[0], qr.hi[1], qr.hi[2]);
+        // coarse float thresholds: a record is dropped only if its outward-rounded box lies beyond qL - dist - eps (or
+        // qH + dist + eps) on some axis, which implies the exact FP64 gap test (aabb_gap_ok) fails too
+        float loT[3], hiT[3];
+        if (!(MODE & 2)) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const double eps = 1e-12 * (fabs(qr.lo[k]) + fabs(qr.hi[k]) + a.dist) + 1e-300;
+                loT[k] = __double2float_rd(qr.lo[k] - a.dist - eps);
+                hiT[k] = __double2float_ru(qr.hi[k] + a.dist + eps);
+            }
+        }
+        int nq = 0; // survivors waiting in the queue (warp-uniform)
         const int ny = qhi[1] - qlo[1] + 1, nRows = ny * (qhi[2] - qlo[2] + 1);
-        for (int rbase = 0; rbase < nRows; rbase += 32) {
-            const int r = rbase + lane;
-            int start = 0, len = 0;
+        int lg = 0; // 2^lg slices per run
+        while (lg < 3 && (nRows << (lg + 1)) <= 32) ++lg;
+        const int rowsPerBatch = 32 >> lg;
+        for (int rbase = 0; rbase < nRows; rbase += rowsPerBatch) {
+            const int r = rbase + (lane >> lg), sl = lane & ((1 << lg) - 1);
+            int my = 0, iy = 0, iz = 0;
+            long first = 0;
             if (r < nRows) {
-                const int iy = qlo[1] + r % ny, iz = qlo[2] + r / ny;
+                const int rz = r / ny;
+                iy = qlo[1] + (r - rz * ny); iz = qlo[2] + rz;
                 const long row = ((long)iz * a.g.n[1] + iy) * a.g.n[0];
-                start = a.cellStart[row + qlo[0]];
-                len = a.cellStart[row + qhi[0] + 1] - start;
+                const int start = a.cellStart[row + qlo[0]];
+                const int len = a.cellStart[row + qhi[0] + 1] - start;
+                const int slen = (len + (1 << lg) - 1) >> lg;
+                first = start + (long)sl * slen;
+                my = max(0, min(slen, len - sl * slen));
             }
-            int scan = len; // inclusive prefix sum over the lanes
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, scan, o);
-                if (lane >= o) scan += v;
-            }
-            const int total = __shfl_sync(0xffffffffu, scan, 31);
-            const int excl = scan - len;
-            for (int t0 = 0; t0 < total; t0 += 32) {
-                const int t = t0 + lane;
-                int lo = 0, hi = 31; // first lane j with scan_j > t
-#pragma unroll
-                for (int step = 0; step < 5; ++step) {
-                    const int mid = (lo + hi) >> 1;
-                    const int sm = __shfl_sync(0xffffffffu, scan, mid);
-                    if (sm > t) hi = mid;
-                    else lo = mid + 1;
-                }
-                const int st = __shfl_sync(0xffffffffu, start, lo), ex = __shfl_sync(0xffffffffu, excl, lo);
-                bool hit = false;
+            const int maxLen = __reduce_max_sync(0xffffffffu, my);
+            for (int k = 0; k < maxLen; ++k) {
+                bool cand = false;
                 int b = -1;
-                if (t < total) {
-                    const int i = st + (t - ex), rr = rbase + lo;
-                    b = a.entries[i];
-                    hit = pair_passes<MODE>(a, q, b, qr, qb, qL, qH, qlo, qlo[1] + rr % ny, qlo[2] + rr / ny, i);
+                if (k < my) {
+                    const int4* rp = reinterpret_cast<const int4*>(a.crec + first + k);
+                    const int4 w0 = __ldg(rp), w1 = __ldg(rp + 1); // box[0..3] | box[4], box[5], b, aux
+                    b = w1.z;
+                    cand = !(MODE & 1) || b > (int)q; // eJ > eI (IPC.h:384, SPATIAL_HASH.h:265)
+                    if (MODE & 2) {
+                        // canonical cell of the pair: componentwise max of the two low corners (every pair is met once)
+                        const int bl[3] = {w0.x, w0.y, w0.z}, bh[3] = {w0.w, w1.x, w1.y};
+                        int cl[3];
+#pragma unroll
+                        for (int d = 0; d < 3; ++d) cl[d] = clampi(a.g.k == 1 ? bl[d] : bl[d] / a.g.k, 0, a.g.n[d] - 1);
+                        cand = cand && max(clo[0], cl[0]) == w1.w && max(clo[1], cl[1]) == iy && max(clo[2], cl[2]) == iz;
+                        cand = cand && qb.lo[0] <= bh[0] && bl[0] <= qb.hi[0] && qb.lo[1] <= bh[1] && bl[1] <= qb.hi[1] &&
+                               qb.lo[2] <= bh[2] && bl[2] <= qb.hi[2];
+                    }
+                    else {
+                        const float fl0 = __int_as_float(w0.x), fl1 = __int_as_float(w0.y), fl2 = __int_as_float(w0.z);
+                        const float fh0 = __int_as_float(w0.w), fh1 = __int_as_float(w1.x), fh2 = __int_as_float(w1.y);
+                        cand = cand && !(fh0 < loT[0] || fh1 < loT[1] || fh2 < loT[2] || fl0 > hiT[0] || fl1 > hiT[1] || fl2 > hiT[2]);
+                    }
                 }
-                const long slot = warp_append(hit, a.counter, a.cap);
-                if (hit && slot >= 0) a.out[slot] = make_int2((int)q, b);
+                const unsigned m = __ballot_sync(0xffffffffu, cand);
+                if (m) {
+                    if (cand) sq[nq + __popc(m & lt)] = b;
+                    nq += __popc(m);
+                    if (nq >= 32) { // a full warp of survivors: exact predicate, append
+                        __syncwarp();
+                        const int bb = sq[lane];
+                        const bool hit = pair_exact<MODE>(a, bb, qr, qL, qH);
+                        const long slot = warp_append(hit, a.counter, a.cap);
+                        if (hit && slot >= 0) a.out[slot] = make_int2((int)q, bb);
+                        const int rest = (lane < nq - 32) ? sq[32 + lane] : 0;
+                        __syncwarp();
+                        if (lane < nq - 32) sq[lane] = rest;
+                        nq -= 32;
+                        __syncwarp();
+                    }
+                }
             }
+        }
+        if (nq > 0) { // remaining survivors
+            __syncwarp();
+            const int bb = lane < nq ? sq[lane] : -1;
+            const bool hit = lane < nq && pair_exact<MODE>(a, bb, qr, qL, qH);
+            const long slot = warp_append(hit, a.counter, a.cap);
+            if (hit && slot >= 0) a.out[slot] = make_int2((int)q, bb);
+            __syncwarp();
         }
         const int nLarge = *a.nLargePtr;
         for (int l0 = 0; l0 < nLarge; l0 += 32) { // primitives too large for anchor insertion
@@ -571,7 +629,7 @@ __global__ void __launch_bounds__(256) k_query(QueryArgs a)
             int b = -1;
             if (l0 + lane < nLarge) {
                 b = a.large[l0 + lane];
-                hit = pair_passes<MODE>(a, q, b, qr, qb, qL, qH, qlo, 0, 0, -1);
+                hit = pair_large<MODE>(a, q, b, qr, qL, qH);
             }
             const long slot = warp_append(hit, a.counter, a.cap);
             if (hit && slot >= 0) a.out[slot] = make_int2((int)q, b);
@@ -594,7 +652,7 @@ static int run_query(idp_ctx* c, QueryArgs a, DBuf<int2>& out, long* nOut)
         const unsigned grid = (unsigned)std::min<long>((nQ + 7) / 8, (long)c->sm_count * 64);
         if (nQ > 0) {
             KernelTimer kt(c, IDP_STAGE_K_QUERY);
-            IDP_LAUNCH(c, k_query<MODE>, std::max(grid, 1u), 256, 0, a);
+            IDP_LAUNCH(c, k_query<MODE>, std::max(grid, 1u), 32 * IDP_QUERY_WARPS, 0, a);
         }
         IDP_CK(c, cudaGetLastError());
         long long n = 0;
@@ -903,11 +961,11 @@ int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
     {
         StageTimer tm(c, IDP_STAGE_CCS_PT);
         EMax emax; int nLarge = 0;
-        IDP_TRY(build_cells(c, c->boxTb.p, c->nBT, g, latN, &emax, &nLarge));
+        IDP_TRY(build_cells(c, c->boxTb.p, c->recT.p, c->nBT, g, latN, &emax, &nLarge));
         shard_range(c, c->nBN, &qb, &qe);
         QueryArgs qa;
         qa.qrec = c->recN.p; qa.qbox = c->boxNq.p; qa.qBegin = qb; qa.qEnd = qe;
-        qa.brec = c->recT.p; qa.bbox = c->boxTb.p; qa.cellStart = c->cellStart.p; qa.entries = c->entries.p;
+        qa.brec = c->recT.p; qa.bbox = c->boxTb.p; qa.cellStart = c->cellStart.p; qa.crec = c->crec.p;
         qa.g = g; qa.dist = dHat; qa.emax = emax; qa.large = c->largeList.p; qa.nLargePtr = (const int*)c->histScratch.p + 48;
         IDP_TRY(run_query<0>(c, qa, c->candPT, &c->nCandPT));
         // classification
@@ -935,11 +993,11 @@ int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
     {
         StageTimer tm(c, IDP_STAGE_CCS_EE);
         EMax emax; int nLarge = 0;
-        IDP_TRY(build_cells(c, c->boxEb.p, c->nBE, g, latN, &emax, &nLarge));
+        IDP_TRY(build_cells(c, c->boxEb.p, c->recE.p, c->nBE, g, latN, &emax, &nLarge));
         shard_range(c, c->nBE, &qb, &qe);
         QueryArgs qa;
         qa.qrec = c->recE.p; qa.qbox = c->boxEq.p; qa.qBegin = qb; qa.qEnd = qe;
-        qa.brec = c->recE.p; qa.bbox = c->boxEb.p; qa.cellStart = c->cellStart.p; qa.entries = c->entries.p;
+        qa.brec = c->recE.p; qa.bbox = c->boxEb.p; qa.cellStart = c->cellStart.p; qa.crec = c->crec.p;
         qa.g = g; qa.dist = dHat; qa.emax = emax; qa.large = c->largeList.p; qa.nLargePtr = (const int*)c->histScratch.p + 48;
         IDP_TRY(run_query<1>(c, qa, c->candEE, &c->nCandEE));
         IDP_CK(c, c->rowsB.reserve(std::max<long>(c->nCandEE, 1)));
@@ -1297,7 +1355,7 @@ int ccd_step(idp_ctx* c, double thickness, double* alpha_inout, int keep_candida
         shard_range(c, c->nBN, &qb, &qe);
         QueryArgs qa;
         qa.qrec = c->recN.p; qa.qbox = c->boxNq.p; qa.qBegin = qb; qa.qEnd = qe;
-        qa.brec = c->recT.p; qa.bbox = c->boxTb.p; qa.cellStart = c->cellStart.p; qa.entries = c->entries.p;
+        qa.brec = c->recT.p; qa.bbox = c->boxTb.p; qa.cellStart = c->cellStart.p; qa.crec = c->crec.p;
         qa.g = g; qa.dist = thickness; qa.emax = emax; qa.large = c->largeList.p; qa.nLargePtr = (const int*)c->histScratch.p + 48;
         IDP_TRY(run_query<2>(c, qa, c->candPT, &c->nCcdPT));
         aa.cand = c->candPT.p; aa.nCand = c->nCcdPT;
@@ -1311,7 +1369,7 @@ int ccd_step(idp_ctx* c, double thickness, double* alpha_inout, int keep_candida
         shard_range(c, c->nBE, &qb, &qe);
         QueryArgs qa;
         qa.qrec = c->recE.p; qa.qbox = c->boxEb.p; qa.qBegin = qb; qa.qEnd = qe;
-        qa.brec = c->recE.p; qa.bbox = c->boxEb.p; qa.cellStart = c->cellStart.p; qa.entries = c->entries.p;
+        qa.brec = c->recE.p; qa.bbox = c->boxEb.p; qa.cellStart = c->cellStart.p; qa.crec = c->crec.p;
         qa.g = g; qa.dist = thickness; qa.emax = emax; qa.large = c->largeList.p; qa.nLargePtr = (const int*)c->histScratch.p + 48;
         IDP_TRY(run_query<3>(c, qa, c->candEE, &c->nCcdEE));
         aa.cand = c->candEE.p; aa.nCand = c->nCcdEE;
