@@ -53,8 +53,7 @@ int idp_create(int device, idp_ctx** out)
     c->own_stream = true;
     cudaEventCreate(&c->ev0);
     cudaEventCreate(&c->ev1);
-    cudaEventCreate(&c->kev0);
-    cudaEventCreate(&c->kev1);
+    for (int i = 0; i < 2 * IDP_EVENT_POOL; ++i) cudaEventCreate(&c->evPool[i]);
     if (c->counters.reserve(CNT_COUNT) != cudaSuccess || c->histScratch.reserve(64) != cudaSuccess) { delete c; return IDP_ERR_CUDA; }
     cudaMemset(c->counters.p, 0, CNT_COUNT * sizeof(long long));
     cudaMallocHost((void**)&c->h_counters, CNT_COUNT * sizeof(long long));
@@ -76,8 +75,7 @@ void idp_destroy(idp_ctx* c)
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
-    if (c->kev0) cudaEventDestroy(c->kev0);
-    if (c->kev1) cudaEventDestroy(c->kev1);
+    for (int i = 0; i < 2 * IDP_EVENT_POOL; ++i) if (c->evPool[i]) cudaEventDestroy(c->evPool[i]);
     cudaStream_t s = c->own_stream ? c->stream : nullptr;
     delete c; // frees the device buffers
     if (s) cudaStreamDestroy(s);
@@ -320,12 +318,6 @@ int idp_ccd_step_resident(idp_ctx* c, double thickness, double* alpha_inout)
     if (!c->have_dir) return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "search direction not set", __FILE__, __LINE__);
     double a = *alpha_inout;
     IDP_TRY(ccd_step(c, thickness, &a, 1));
-    if (c->nranks > 1 && c->nccl_comm) {
-        IDP_CK(c, cudaMemcpyAsync(c->red.p, &a, sizeof(double), cudaMemcpyHostToDevice, c->stream));
-        IDP_TRY(comm_allreduce_min(c, c->red.p, 1));
-        IDP_CK(c, cudaMemcpyAsync(&a, c->red.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-        IDP_CK(c, cudaStreamSynchronize(c->stream));
-    }
     *alpha_inout = a;
     return IDP_OK;
 }
@@ -354,7 +346,12 @@ int idp_set_shard(idp_ctx* c, int rank, int nranks)
 long idp_kernel_launches(idp_ctx* c) { return c ? c->launches : 0; }
 long idp_library_calls(idp_ctx* c) { return c ? c->lib_launches : 0; }
 void idp_reset_counters(idp_ctx* c) { if (c) { c->launches = 0; c->lib_launches = 0; } }
-float idp_stage_ms(idp_ctx* c, int stage) { return (c && stage >= 0 && stage < IDP_STAGE_COUNT) ? c->times.v[stage] : 0.f; }
+float idp_stage_ms(idp_ctx* c, int stage)
+{
+    if (!c || stage < 0 || stage >= IDP_STAGE_COUNT) return 0.f;
+    idp::timers_resolve(c);
+    return c->times.v[stage];
+}
 long idp_last_count(idp_ctx* c, int what)
 {
     if (!c) return 0;

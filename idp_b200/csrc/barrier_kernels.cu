@@ -24,32 +24,43 @@ __device__ __forceinline__ V3 ldv4(const double4* __restrict__ p, int v)
     return mk3(a.x, a.y, b.x);
 }
 
-// number of 3x3 blocks a row contributes: nv(nv+1)/2 — only blocks with vi <= vj are emitted, the assembly mirrors them
-__global__ void k_row_block_counts(const Row4* __restrict__ rows, long n, int rank, int nranks, int* __restrict__ cnt)
+// Row -> rank assignment of the sharded path: the rank that owns the vertex chunk of the row's smallest vertex, chunks of
+// 2^shift consecutive vertices dealt round-robin. Rows that touch the same vertices land on the same rank, so the
+// per-rank partial CSRs are nearly disjoint (only chunk borders overlap; their sum is the global Hessian either way),
+// while the round-robin over ~16 chunks per rank keeps the mix of cheap and expensive row kinds balanced.
+__device__ __forceinline__ int row_owner(const Row4& r, int shift, int nranks)
+{
+    const RowDec d = decode_row(r.a, r.b, r.c, r.d);
+    int mv = d.v[0];
+#pragma unroll
+    for (int k = 1; k < 4; ++k) mv = (k < d.nv && d.v[k] < mv) ? d.v[k] : mv;
+    return (mv >> shift) % nranks;
+}
+// number of 3x3 blocks a row contributes: nv(nv+1)/2 -- only blocks with vi <= vj are emitted, the assembly mirrors them
+__global__ void k_row_block_counts(const Row4* __restrict__ rows, long n, int rank, int nranks, int shift, int* __restrict__ cnt)
 {
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += (long)gridDim.x * blockDim.x) {
         int k = 0;
-        if (i < n && (i % nranks) == rank) { // rows are dealt round-robin to the ranks (uniform mix of row kinds)
+        if (i < n) {
             const Row4 r = rows[i];
-            k = (r.a >= 0 || r.d >= 0) ? 10 : (r.c >= 0 ? 6 : 3); // upper triangle of the nv x nv blocks (IPC.h:1372-1387 counts all nv^2)
+            if (nranks == 1 || row_owner(r, shift, nranks) == rank)
+                k = (r.a >= 0 || r.d >= 0) ? 10 : (r.c >= 0 ? 6 : 3); // upper triangle of the nv x nv blocks (IPC.h:1372-1387 counts all nv^2)
         }
         cnt[i] = k;
     }
 }
 // kind of every row of this rank (7 = row of another rank) + identity permutation; kinds are counted per block and added
 // once (counts are order independent, so the result is deterministic)
-__global__ void __launch_bounds__(256) k_row_kinds(const Row4* __restrict__ rows, long n, int rank, int nranks, unsigned char* __restrict__ kind,
-    int* __restrict__ iota, unsigned long long* __restrict__ kindCount)
+__global__ void __launch_bounds__(256) k_row_kinds(const Row4* __restrict__ rows, long n, int rank, int nranks, int shift,
+    unsigned char* __restrict__ kind, int* __restrict__ iota, unsigned long long* __restrict__ kindCount)
 {
     __shared__ int sh[8];
     if (threadIdx.x < 8) sh[threadIdx.x] = 0;
     __syncthreads();
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const Row4 r = rows[i];
         int k = 7;
-        if ((i % nranks) == rank) {
-            const Row4 r = rows[i];
-            k = decode_row(r.a, r.b, r.c, r.d).kind;
-        }
+        if (nranks == 1 || row_owner(r, shift, nranks) == rank) k = decode_row(r.a, r.b, r.c, r.d).kind;
         kind[i] = (unsigned char)k;
         iota[i] = (int)i;
         atomicAdd(&sh[k], 1);
@@ -189,14 +200,15 @@ int barrier_eval(idp_ctx* c, double dhat2, double kappa, double thickness, int w
     if (c->nRows == 0) return IDP_OK;
     StageTimer tm(c, IDP_STAGE_BARRIER);
     IDP_CK(c, cudaMemsetAsync(c->counters.p + CNT_ERR_DIST, 0, sizeof(long long), c->stream));
-    // rows are dealt round-robin: rank r evaluates rows r, r + P, r + 2P, ... in an order grouped by kind
-    const long nMine = c->nRows > c->rank ? (c->nRows - c->rank + c->nranks - 1) / c->nranks : 0;
+    // this rank's rows (row_owner) in an order grouped by kind
+    int ownerShift = 8;
+    while (ownerShift < 14 && (c->nV >> ownerShift) > 16 * c->nranks) ++ownerShift;
     if (!c->permValid) {
         IDP_CK(c, c->rowKind.reserve(c->nRows)); IDP_CK(c, c->rowKindSorted.reserve(c->nRows));
         IDP_CK(c, c->rowIota.reserve(c->nRows)); IDP_CK(c, c->rowPerm.reserve(c->nRows));
         unsigned long long* dKind = (unsigned long long*)(c->counters.p + CNT_KINDS);
         IDP_CK(c, cudaMemsetAsync(dKind, 0, 8 * sizeof(long long), c->stream));
-        IDP_LAUNCH(c, k_row_kinds, std::min(blocks_for(c->nRows, 256), (unsigned)c->sm_count * 16), 256, 0, c->rows.p, c->nRows, c->rank, c->nranks,
+        IDP_LAUNCH(c, k_row_kinds, std::min(blocks_for(c->nRows, 256), (unsigned)c->sm_count * 16), 256, 0, c->rows.p, c->nRows, c->rank, c->nranks, ownerShift,
             c->rowKind.p, c->rowIota.p, dKind);
         size_t bytes = 0;
         IDP_CK(c, cub::DeviceRadixSort::SortPairs(nullptr, bytes, c->rowKind.p, c->rowKindSorted.p, c->rowIota.p, c->rowPerm.p, (int)c->nRows, 0, 3, c->stream));
@@ -211,6 +223,7 @@ int barrier_eval(idp_ctx* c, double dhat2, double kappa, double thickness, int w
     }
     const long nPath[3] = {c->kindCount[K_EE] + c->kindCount[K_EE_M] + c->kindCount[K_PE_M] + c->kindCount[K_PP_M] + c->kindCount[K_PT],
         c->kindCount[K_PE], c->kindCount[K_PP]};
+    const long nMine = nPath[0] + nPath[1] + nPath[2];
     const unsigned grid = std::max(1u, std::min(blocks_for(std::max(nPath[0], std::max(nPath[1], nPath[2])), 128), (unsigned)c->sm_count * 16));
     BarrierArgs a;
     a.rows = c->rows.p; a.weights = c->weights.p; a.perm = c->rowPerm.p; a.jBegin = 0; a.jEnd = 0;
@@ -227,7 +240,7 @@ int barrier_eval(idp_ctx* c, double dhat2, double kappa, double thickness, int w
     if (want_h) {
         IDP_CK(c, c->rowBlkOff.reserve(c->nRows + 1));
         IDP_CK(c, c->segId.reserve(c->nRows + 1));
-        IDP_LAUNCH(c, k_row_block_counts, blocks_for(c->nRows + 1, 256), 256, 0, c->rows.p, c->nRows, c->rank, c->nranks, c->segId.p);
+        IDP_LAUNCH(c, k_row_block_counts, blocks_for(c->nRows + 1, 256), 256, 0, c->rows.p, c->nRows, c->rank, c->nranks, ownerShift, c->segId.p);
         IDP_TRY(cub_scan_exclusive(c, c->segId.p, c->rowBlkOff.p, c->nRows + 1));
         int ends[2] = {0, 0};
         IDP_CK(c, cudaMemcpyAsync(&ends[1], c->rowBlkOff.p + c->nRows, sizeof(int), cudaMemcpyDeviceToHost, c->stream));

@@ -33,18 +33,9 @@ struct NcclApi {
 };
 static NcclApi g_nccl;
 
-// accumulates the device time of the collectives of one step into IDP_STAGE_COMM
-struct CommTimer {
-    idp_ctx* c;
-    CommTimer(idp_ctx* ctx) : c(ctx) { cudaEventRecord(c->kev0, c->stream); }
-    ~CommTimer()
-    {
-        cudaEventRecord(c->kev1, c->stream);
-        cudaEventSynchronize(c->kev1);
-        float ms = 0;
-        cudaEventElapsedTime(&ms, c->kev0, c->kev1);
-        c->times.v[IDP_STAGE_COMM] += ms;
-    }
+// accumulates the device time of the collectives of one step into IDP_STAGE_COMM (resolved lazily, no host sync)
+struct CommTimer : ScopeTimer {
+    CommTimer(idp_ctx* ctx) : ScopeTimer(ctx, IDP_STAGE_COMM, true) {}
 };
 
 static bool load_nccl()
@@ -85,6 +76,15 @@ int comm_allreduce_min(idp_ctx* c, double* dev, long n)
     if (!c->nccl_comm) return IDP_OK;
     CommTimer tm(c);
     const int r = g_nccl.allreduce(dev, dev, (size_t)n, 8, 3, c->nccl_comm, c->stream);
+    if (r != 0) return fail(c, IDP_ERR_NCCL, "NCCL error: %s at %s:%d", g_nccl.errstr ? g_nccl.errstr(r) : "?", __FILE__, __LINE__);
+    return IDP_OK;
+}
+// min over ranks of order-encoded 64-bit keys (ncclUint64 = 5)
+int comm_allreduce_min_u64(idp_ctx* c, unsigned long long* dev, long n)
+{
+    if (!c->nccl_comm) return IDP_OK;
+    CommTimer tm(c);
+    const int r = g_nccl.allreduce(dev, dev, (size_t)n, 5, 3, c->nccl_comm, c->stream);
     if (r != 0) return fail(c, IDP_ERR_NCCL, "NCCL error: %s at %s:%d", g_nccl.errstr ? g_nccl.errstr(r) : "?", __FILE__, __LINE__);
     return IDP_OK;
 }

@@ -8,6 +8,8 @@
 #include <algorithm>
 #include "../../include/idp_contact.h"
 
+#define IDP_EVENT_POOL 512
+
 namespace idp {
 
 // one cache-line-pair record per boundary primitive (point / edge / triangle): exact AABB + vertex ids.
@@ -173,7 +175,11 @@ struct idp_ctx {
     bool weights_all_one = false;
 
     idp::StageTimes times;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, kev0 = nullptr, kev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr; // microbenchmark timing
+    cudaEvent_t evPool[2 * IDP_EVENT_POOL] = {};
+    int pendStage[IDP_EVENT_POOL] = {};
+    bool pendAccum[IDP_EVENT_POOL] = {};
+    int nPending = 0, timerDepth = 0;
 };
 
 namespace idp {
@@ -217,29 +223,47 @@ enum Counter {
     CNT_COUNT = 24
 };
 
-struct StageTimer {
+// Device-side timers that never block the host: a scope records an event pair from a small pool and the elapsed times
+// are resolved lazily (idp_stage_ms, or when the pool wraps). Synchronising inside the destructors, as a first version
+// did, cost one host round trip per stage, kernel and collective -- visible at 8 GPUs where a step is ~20 ms.
+inline void timers_resolve(idp_ctx* c)
+{
+    if (c->nPending == 0) return;
+    for (int i = 0; i < c->nPending; ++i) {
+        float ms = 0;
+        if (cudaEventSynchronize(c->evPool[2 * i + 1]) != cudaSuccess) continue;
+        if (cudaEventElapsedTime(&ms, c->evPool[2 * i], c->evPool[2 * i + 1]) != cudaSuccess) continue;
+        const int st = c->pendStage[i];
+        if (c->pendAccum[i]) c->times.v[st] += ms;
+        else c->times.v[st] = ms;
+    }
+    c->nPending = 0;
+}
+struct ScopeTimer {
     idp_ctx* c;
-    int stage;
-    StageTimer(idp_ctx* ctx, int st) : c(ctx), stage(st) { cudaEventRecord(c->ev0, c->stream); }
-    ~StageTimer()
+    int slot;
+    ScopeTimer(idp_ctx* ctx, int stage, bool accumulate) : c(ctx), slot(-1)
     {
-        cudaEventRecord(c->ev1, c->stream);
-        cudaEventSynchronize(c->ev1);
-        cudaEventElapsedTime(&c->times.v[stage], c->ev0, c->ev1);
+        if (c->nPending == IDP_EVENT_POOL && c->timerDepth == 0) timers_resolve(c); // only between top-level scopes
+        ++c->timerDepth;
+        if (c->nPending == IDP_EVENT_POOL) return; // pool exhausted inside a nested scope: this one goes untimed
+        slot = c->nPending++;
+        c->pendStage[slot] = stage;
+        c->pendAccum[slot] = accumulate;
+        cudaEventRecord(c->evPool[2 * slot], c->stream);
+    }
+    ~ScopeTimer()
+    {
+        --c->timerDepth;
+        if (slot >= 0) cudaEventRecord(c->evPool[2 * slot + 1], c->stream);
     }
 };
-
-// times a single launch with its own event pair (nested inside a StageTimer scope); read back lazily at scope end
-struct KernelTimer {
-    idp_ctx* c;
-    int stage;
-    KernelTimer(idp_ctx* ctx, int st) : c(ctx), stage(st) { cudaEventRecord(c->kev0, c->stream); }
-    ~KernelTimer()
-    {
-        cudaEventRecord(c->kev1, c->stream);
-        cudaEventSynchronize(c->kev1);
-        cudaEventElapsedTime(&c->times.v[stage], c->kev0, c->kev1);
-    }
+struct StageTimer : ScopeTimer {
+    StageTimer(idp_ctx* ctx, int st) : ScopeTimer(ctx, st, false) {}
+};
+// times a single launch (nested inside a StageTimer scope)
+struct KernelTimer : ScopeTimer {
+    KernelTimer(idp_ctx* ctx, int st) : ScopeTimer(ctx, st, false) {}
 };
 
 // ---- host-side launchers implemented in the .cu files ----
@@ -254,6 +278,8 @@ int ccd_step(idp_ctx* c, double thickness, double* alpha_inout, int keep_candida
 int cub_scan_exclusive(idp_ctx* c, const int* in, int* out, long n);
 // variable-size all-gather of nLocal elements of elemSize bytes into *outPtr (capacity *outCap elements, grown and
 // preserved when too small) starting at element outOffset; *nTotal = sum over ranks
+int comm_allreduce_min(idp_ctx* c, double* dev, long n);
+int comm_allreduce_min_u64(idp_ctx* c, unsigned long long* dev, long n);
 int comm_exchange_keys(idp_ctx* c, const unsigned long long* keys, const long sendOff[9], DBuf<unsigned long long>& recv, long* nRecv);
 int comm_allgatherv(idp_ctx* c, const void* local, long nLocal, size_t elemSize, void** outPtr, size_t* outCap, long outOffset, long* nTotal);
 

@@ -926,7 +926,9 @@ int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
     const double dHat = std::sqrt(dhat2_in) + thickness; // IPC.h:53-54
     const double dHat2 = dHat * dHat;
     c->cs_dhat2 = dHat2;
+    timers_resolve(c);
     c->times.v[IDP_STAGE_COMM] = 0;
+    c->times.v[IDP_STAGE_CCS_MERGE] = 0; // accumulated over the scopes of the merge stage
     IDP_CK(c, cudaMemsetAsync(c->counters.p, 0, CNT_COUNT * sizeof(long long), c->stream));
 
     GridDesc g;
@@ -1025,10 +1027,9 @@ int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
     // allocations (cudaMalloc / cudaFree of multi-GB buffers would dominate the step).
     const bool sharded = c->nranks > 1 && c->nccl_comm;
     long nAg = nA, nBg = nB, nDg = nD;
-    float mergeSort = 0;
     IDP_CK(c, c->rows.reserve(std::max<long>(nA + nB + nD, 1)));
     {
-        StageTimer tm(c, IDP_STAGE_CCS_MERGE);
+        ScopeTimer tm(c, IDP_STAGE_CCS_MERGE, true);
         // direct groups: order by candidate pair (query-major, partner ascending = the reference's loop order) with one
         // radix sort each, written straight into their final place when there is a single rank. A shard's rows come from
         // its own contiguous query range, so concatenating the sorted shards in rank order is globally sorted.
@@ -1042,7 +1043,6 @@ int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
         IDP_TRY(sort_rows_by_key(c, c->keyA.p, c->rowsA.p, dstA, nA, bits_for((unsigned long long)c->nBN * (unsigned long long)c->nBT)));
         IDP_TRY(sort_rows_by_key(c, c->keyB.p, c->rowsB.p, dstB, nB, bits_for((unsigned long long)c->nBE * (unsigned long long)c->nBE)));
     }
-    mergeSort = c->times.v[IDP_STAGE_CCS_MERGE];
     unsigned long long* dupKeys = c->keyD.p;
     bool distributedDup = false;
     if (sharded) {
@@ -1054,7 +1054,7 @@ int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
             const int P = c->nranks;
             long sendOff[9];
             {
-            StageTimer tm2(c, IDP_STAGE_CCS_MERGE);
+            ScopeTimer tm2(c, IDP_STAGE_CCS_MERGE, true);
             IDP_CK(c, c->keyTmp.reserve(std::max<long>(nD, 1)));
             size_t bytes = 0;
             if (nD > 0) {
@@ -1076,7 +1076,6 @@ int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
             for (int r = 0; r <= P; ++r) sendOff[r] = (long)split[r];
             sendOff[P] = nD;
             }
-            mergeSort += c->times.v[IDP_STAGE_CCS_MERGE]; // (the exchange itself is accounted to nccl_collectives)
             IDP_TRY(comm_exchange_keys(c, c->keyTmp.p, sendOff, c->keyB, &nDg));
             dupKeys = c->keyB.p;
             distributedDup = true;
@@ -1085,7 +1084,7 @@ int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
     }
     {
         const long nA = nAg, nB = nBg, nD = nDg;
-        StageTimer tm(c, IDP_STAGE_CCS_MERGE);
+        ScopeTimer tm(c, IDP_STAGE_CCS_MERGE, true);
         long nU = 0;
         int* dRuns = (int*)(c->counters.p + CNT_RUNS);
         if (nD > 0 && dupBits) {
@@ -1138,7 +1137,6 @@ int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
         c->weights_all_one = true;
         IDP_CK(c, cudaGetLastError());
     }
-    c->times.v[IDP_STAGE_CCS_MERGE] += mergeSort;
     return IDP_OK;
 }
 
@@ -1177,11 +1175,11 @@ int sorted_candidates(idp_ctx* c, int which, int2* host_out)
 // ------------------------------------------------------------------------------------------------------------
 // Compute_Min_Dist2
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_min_dist(const Row4* __restrict__ rows, long n, const double4* __restrict__ xp,
+__global__ void __launch_bounds__(256) k_min_dist(const Row4* __restrict__ rows, long begin, long n, const double4* __restrict__ xp,
     double* __restrict__ dist2, unsigned long long* __restrict__ minOut)
 {
     double m = INFINITY;
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    for (long i = begin + (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
         const Row4 r = rows[i];
         const RowDec d = decode_row(r.a, r.b, r.c, r.d);
         const double d2 = row_dist2(d.kind, ldv(xp, d.v[0]), ldv(xp, d.v[1]), ldv(xp, d.v[2]), ldv(xp, d.v[3]));
@@ -1201,9 +1199,14 @@ int min_dist2(idp_ctx* c, double thickness, double* host_dist2, double* min_out)
     unsigned long long init = ~0ull;
     unsigned long long* d = (unsigned long long*)(c->counters.p + 8);
     IDP_CK(c, cudaMemcpyAsync(d, &init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
-    IDP_LAUNCH(c, k_min_dist, std::min(blocks_for(c->nRows, 256), (unsigned)c->sm_count * 16), 256, 0, c->rows.p, c->nRows, c->xp.p,
+    // sharded: when only the minimum is wanted every rank scans a contiguous slice of the (replicated) rows and the
+    // order-encoded minima are combined with one all-reduce; the per-row vector needs all rows on the asking rank
+    const bool slice = c->nranks > 1 && c->nccl_comm && !host_dist2;
+    const long rb = slice ? c->nRows * c->rank / c->nranks : 0, re = slice ? c->nRows * (c->rank + 1) / c->nranks : c->nRows;
+    IDP_LAUNCH(c, k_min_dist, std::min(blocks_for(std::max(re - rb, 1L), 256), (unsigned)c->sm_count * 16), 256, 0, c->rows.p, rb, re, c->xp.p,
         c->rowDist2.p, d);
     IDP_CK(c, cudaGetLastError());
+    if (slice) IDP_TRY(comm_allreduce_min_u64(c, d, 1));
     IDP_CK(c, cudaMemcpyAsync(&init, d, sizeof(init), cudaMemcpyDeviceToHost, c->stream));
     if (host_dist2) IDP_CK(c, cudaMemcpyAsync(host_dist2, c->rowDist2.p, c->nRows * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     IDP_CK(c, cudaStreamSynchronize(c->stream));
@@ -1379,6 +1382,8 @@ int ccd_step(idp_ctx* c, double thickness, double* alpha_inout, int keep_candida
         }
         IDP_CK(c, cudaGetLastError());
     }
+    // positive doubles order like their bit patterns, so the device cell is a valid double for the min all-reduce
+    if (c->nranks > 1 && c->nccl_comm) IDP_TRY(comm_allreduce_min(c, (double*)(cnt + CNT_ALPHA_BITS), 1));
     IDP_TRY(read_counters(c));
     c->ccd_iters = (long)c->h_counters[CNT_CCD_ITERS];
     double out;

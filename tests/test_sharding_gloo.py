@@ -21,24 +21,25 @@ def _worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from idp_b200.sharding import shard_range
+    from idp_b200.sharding import row_owner, shard_range
     from oracle.binding import Oracle
     orc = Oracle()
     name, m, d, dhats = make_cases()[1]
     dh = dhats[-1]
     om = orc.mesh(m.X, m.X0, m.bnode, m.bedge, m.btri, m.dbc)
     rows, info, _, _ = orc.constraint_set(om, dh * dh)
-    # rows are replicated after the all-gather; each rank evaluates its slice
+    # rows are replicated after the all-gather; each rank evaluates the rows it owns (vertex-chunk ownership)
     b, e = shard_range(len(rows), rank, world)
-    st, E = orc.barrier(om, rows[b:e], info[b:e, 0], dh * dh, 1e5)
-    st, g = orc.barrier_gradient(om, rows[b:e], info[b:e, 0], dh * dh, 1e5)
+    mine = row_owner(rows, m.nV, world) == rank
+    st, E = orc.barrier(om, rows[mine], info[mine, 0], dh * dh, 1e5)
+    st, g = orc.barrier_gradient(om, rows[mine], info[mine, 0], dh * dh, 1e5)
     Et = torch.tensor([E], dtype=torch.float64); gt = torch.from_numpy(g.copy())
     dist.all_reduce(Et, op=dist.ReduceOp.SUM)
     dist.all_reduce(gt, op=dist.ReduceOp.SUM)
     # CCD: the step is the min over query shards; emulate a shard by masking the other half of the search direction
     nb, ne = shard_range(m.nV, rank, world)
     ranges = [None] * world
-    dist.all_gather_object(ranges, (b, e, nb, ne))
+    dist.all_gather_object(ranges, (b, e, nb, ne, int(mine.sum())))
     a_part = torch.tensor([0.3 + 0.1 * rank], dtype=torch.float64)
     dist.all_reduce(a_part, op=dist.ReduceOp.MIN)
     if rank == 0:
@@ -63,8 +64,20 @@ def test_sharded_reductions_world2():
     # the slices tile [0, n) and [0, nV) exactly, in rank order
     assert ranges[0][0] == 0 and ranges[0][1] == ranges[1][0] and ranges[1][1] == n
     assert ranges[0][2] == 0 and ranges[0][3] == ranges[1][2] and ranges[1][3] == nV
+    assert ranges[0][4] + ranges[1][4] == n and min(ranges[0][4], ranges[1][4]) > 0.2 * n  # every row owned once, both busy
     assert abs(E - E0) <= 1e-12 * abs(E0) and gerr <= 1e-12
     assert amin == 0.3
+
+
+def test_row_owner_decodes_every_row_kind():
+    from idp_b200.sharding import owner_shift, row_owner, row_vertices
+    rows = np.array([[5, 6, 7, 8], [5, 6, -8, 9], [5, 7, 8, -10], [5, 7, -9, -10],
+                     [-4, 10, 11, 12], [-4, 10, 11, -2], [-4, 10, -1, -3]], np.int32)
+    v = row_vertices(rows)
+    assert v.tolist() == [[5, 6, 7, 8], [5, 6, 7, 9], [5, 7, 8, 9], [5, 7, 8, 9], [3, 10, 11, 12], [3, 10, 11, -1], [3, 10, -1, -1]]
+    assert owner_shift(2008008, 8) == 14 and owner_shift(12000, 2) == 9 and owner_shift(100, 8) == 8
+    own = row_owner(np.array([[70000, 70001, 70002, 70003], [-1, 5, 6, 7]], np.int32), 2008008, 8)
+    assert own.tolist() == [(70000 >> 14) % 8, 0]
 
 
 def test_shard_range_tiles_exactly():
