@@ -1,0 +1,189 @@
+"""Full-size GPU checks on the BASELINE.json configurations.
+
+* config 3 (two nested icospheres, 501,760 triangles, dHat sweep): the oracle finishes this size in seconds, so the
+  comparison is the full one -- candidate and constraint sets bit-exact at every dHat, E/g/H within 1e-10, CCD step
+  conservative and within 1e-6;
+* config 4 (8 sheets, 4,000,000 triangles) and config 5 (16 sheets, 16,000,000 triangles, CCD only) are beyond the
+  oracle's reach in a test, so they are checked through size-independent properties: translation invariance of the
+  gradient, parity of E/g/H with the oracle on a random subset of the real rows, a step that never exceeds the input
+  step, determinism, and a rigorous per-pair proof (independent numpy distances + the Lipschitz bound of the linear
+  trajectories) that the closest candidate pairs never touch along the returned step.
+"""
+import numpy as np
+import pytest
+
+from conftest import lexsorted
+from geometry_np import point_triangle_distance, segment_segment_distance
+
+pytestmark = pytest.mark.gpu
+KAPPA = 1e5
+RTOL = 1e-10  # BASELINE.json tolerance for E / g / H
+
+
+def rel(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    nb = np.linalg.norm(b)
+    return np.linalg.norm(a - b) / nb if nb > 0 else np.linalg.norm(a - b)
+
+
+def omesh(orc, m):
+    return orc.mesh(m.X, m.X0, m.bnode, m.bedge, m.btri, m.dbc)
+
+
+def test_config3_icospheres_dhat_sweep_full_parity(gpu_ctx, orc):
+    from idp_b200 import meshgen
+    m, d = meshgen.nested_icospheres()  # nu=112: 501,760 triangles
+    assert m.nF == 501760
+    gpu_ctx.set_surface_mesh(m)
+    om = omesh(orc, m)
+    counts = []
+    for dh in (1e-3, 2e-3, 5e-3, 1e-2):
+        n = gpu_ctx.constraint_set(dh * dh)
+        rows, info = gpu_ctx.get_constraints()
+        orows, oinfo, ocpt, ocee = orc.constraint_set(om, dh * dh, want_cand=True)
+        assert n == len(orows), (dh, n, len(orows))
+        assert np.array_equal(gpu_ctx.get_candidates(0), ocpt) and np.array_equal(gpu_ctx.get_candidates(1), ocee), dh
+        assert np.array_equal(lexsorted(rows), lexsorted(orows)), dh
+        dup = (rows[:, 0] < 0) & (rows[:, 3] < 0)
+        odup = (orows[:, 0] < 0) & (orows[:, 3] < 0)
+        assert np.array_equal(rows[dup], orows[odup]), dh
+        counts.append(n)
+        if dh == 5e-3:
+            E = gpu_ctx.barrier_energy(dh * dh, KAPPA)
+            g = gpu_ctx.barrier_gradient(dh * dh, KAPPA)
+            _, oE = orc.barrier(om, rows, info[:, 0], dh * dh, KAPPA)
+            _, og = orc.barrier_gradient(om, rows, info[:, 0], dh * dh, KAPPA)
+            assert abs(E - oE) <= RTOL * abs(oE) and rel(g, og) <= RTOL
+            dist, mn = gpu_ctx.min_dist2()
+            od, omn = orc.min_dist2(om, rows)
+            assert np.array_equal(dist, od) and mn == omn
+            # projected Hessian: every 12th row (the oracle stores 144 triplets per row on the host)
+            sub = np.ascontiguousarray(rows[::12])
+            gpu_ctx.set_constraints(sub)
+            ptr, col, val = gpu_ctx.barrier_hessian(dh * dh, KAPPA, project_spd=True)
+            optr, ocol, oval = orc.barrier_hessian(om, sub, np.ones(len(sub)), dh * dh, KAPPA, project_spd=True)["csr"]
+            assert np.array_equal(ptr, optr) and np.array_equal(col, ocol)
+            assert rel(val, oval) <= RTOL and np.abs(val - oval).max() <= RTOL * np.abs(oval).max()
+    assert counts[0] == 0 and counts == sorted(counts) and counts[-1] > 1000000  # below the gap nothing is in contact
+    for a0, scale, xi in ((1.0, 1.0, 0.0), (0.5, 2.0, 1e-4)):
+        a = gpu_ctx.ccd_step(d * scale, a0, xi)
+        o = orc.ccd(om, d * scale, a0, xi, want_cand=True)
+        assert o["status"] == 0 and a <= o["step"] and abs(a - o["step"]) <= 1e-6 * o["step"], (a, o["step"])
+        if o["step_after_clamp"] == a0:
+            assert np.array_equal(gpu_ctx.get_candidates(2), o["cand_pt"]) and np.array_equal(gpu_ctx.get_candidates(3), o["cand_ee"])
+            assert a == o["step"]
+
+
+def _closest_pairs_never_touch(m, d, alpha, cpt, cee, n_check=200000, k_samples=48, n_pool=12000000):
+    """Rigorous for the checked pairs: min over the samples of the true distance minus the Lipschitz slack of one
+    sub-interval must stay positive. The pairs checked are the n_check/2 closest at t=0 of a random pool of at most
+    n_pool candidates per kind (numpy distances over every candidate of the 16M-triangle case would take minutes) plus
+    n_check/2 random ones."""
+    rng = np.random.default_rng(7)
+
+    def pick(d0, n):
+        idx = np.argsort(d0)[: n // 2]
+        return np.unique(np.concatenate([idx, rng.integers(0, len(d0), n // 2)]))
+
+    worst = np.inf
+    for kind, cand in (("pt", cpt), ("ee", cee)):
+        if len(cand) == 0:
+            continue
+        if len(cand) > n_pool:
+            cand = cand[np.unique(rng.integers(0, len(cand), n_pool))]
+        if kind == "pt":
+            v = np.stack([m.bnode[cand[:, 0]], m.btri[cand[:, 1], 0], m.btri[cand[:, 1], 1], m.btri[cand[:, 1], 2]], axis=1)
+            fn = point_triangle_distance
+        else:
+            v = np.stack([m.bedge[cand[:, 0], 0], m.bedge[cand[:, 0], 1], m.bedge[cand[:, 1], 0], m.bedge[cand[:, 1], 1]], axis=1)
+            fn = segment_segment_distance
+        d0 = np.empty(len(v))
+        for c0 in range(0, len(v), 2000000):   # chunked: the full (n, 4, 3) gather would be several GB
+            xc = m.X[v[c0:c0 + 2000000]]
+            d0[c0:c0 + 2000000] = fn(xc[:, 0], xc[:, 1], xc[:, 2], xc[:, 3])
+        sel = pick(d0, min(n_check, 2 * len(d0)))
+        x, dd = m.X[v[sel]], d[v[sel]]
+        speed = np.linalg.norm(dd, axis=2)
+        lip = (speed[:, 0] + speed[:, 1:].max(axis=1)) if kind == "pt" else (speed[:, :2].max(axis=1) + speed[:, 2:].max(axis=1))
+        slack = lip * (alpha / k_samples) * 0.5
+        dmin = np.full(len(sel), np.inf)
+        for k in range(k_samples + 1):
+            xt = x + (alpha * k / k_samples) * dd
+            dmin = np.minimum(dmin, fn(xt[:, 0], xt[:, 1], xt[:, 2], xt[:, 3]))
+        margin = dmin - slack
+        worst = min(worst, float(margin.min()))
+        assert (margin > 0).all(), (kind, float(margin.min()))
+    return worst
+
+
+def test_config4_sheets_4m_properties(gpu_ctx, orc):
+    import bench
+    m, d, dh = bench.build_workload("sheets8x500")
+    assert m.nF == 4000000
+    gpu_ctx.set_surface_mesh(m)
+    n = gpu_ctx.constraint_set(dh * dh)
+    rows, info = gpu_ctx.get_constraints()
+    assert n == len(rows) > 20000000
+    # group layout of the reference: [PT rows][EE / mollified rows][merged PP / PE rows], each group sorted
+    pt = (rows[:, 0] < 0) & (rows[:, 3] >= 0)
+    ee = rows[:, 0] >= 0
+    du = (rows[:, 0] < 0) & (rows[:, 3] < 0)
+    npt, nee = int(pt.sum()), int(ee.sum())
+    assert pt[:npt].all() and ee[npt:npt + nee].all() and du[npt + nee:].all()
+    key = (-rows[npt + nee:, 0].astype(np.int64) - 1)
+    assert (np.diff(key) <= 0).all()  # std::map order of (k0 = -p-1, ...): ascending k0 = descending p
+    E = gpu_ctx.barrier_energy(dh * dh, KAPPA)
+    g = gpu_ctx.barrier_gradient(dh * dh, KAPPA)
+    assert E > 0 and np.isfinite(g).all()
+    assert np.abs(g.sum(axis=0)).max() <= 1e-9 * np.abs(g).sum()  # translation invariance: the row gradients sum to zero
+    # parity with the oracle on a random subset of the real rows (E, g, projected Hessian)
+    rng = np.random.default_rng(3)
+    sel = np.sort(rng.choice(n, 100000, replace=False))
+    sub = np.ascontiguousarray(rows[sel])
+    om = omesh(orc, m)
+    gpu_ctx.set_constraints(sub)
+    Es = gpu_ctx.barrier_energy(dh * dh, KAPPA)
+    gs = gpu_ctx.barrier_gradient(dh * dh, KAPPA)
+    ptr, col, val = gpu_ctx.barrier_hessian(dh * dh, KAPPA, project_spd=True)
+    w = np.ones(len(sub))
+    _, oE = orc.barrier(om, sub, w, dh * dh, KAPPA)
+    _, og = orc.barrier_gradient(om, sub, w, dh * dh, KAPPA)
+    optr, ocol, oval = orc.barrier_hessian(om, sub, w, dh * dh, KAPPA, project_spd=True)["csr"]
+    assert abs(Es - oE) <= RTOL * abs(oE) and rel(gs, og) <= RTOL
+    assert np.array_equal(ptr, optr) and np.array_equal(col, ocol)
+    assert rel(val, oval) <= RTOL and np.abs(val - oval).max() <= RTOL * np.abs(oval).max()
+    ds, mns = gpu_ctx.min_dist2()
+    ods, omns = orc.min_dist2(om, sub)
+    assert np.array_equal(ds, ods) and mns == omns
+    # CCD: deterministic, never above the input step, and the closest pairs provably never touch along it
+    a = gpu_ctx.ccd_step(d, 1.0)
+    cpt, cee = gpu_ctx.get_candidates(2), gpu_ctx.get_candidates(3)
+    assert 0 < a <= 1.0 and a == gpu_ctx.ccd_step(d, 1.0)
+    assert len(cpt) + len(cee) > 40000000
+    worst = _closest_pairs_never_touch(m, d, a, cpt, cee)
+    assert worst > 0
+
+
+def test_config5_ccd_only_16m_step_filter_sweep(gpu_ctx):
+    from idp_b200 import meshgen
+    h = 2e-3
+    m, d = meshgen.sheet_stack(n_sheets=16, nx=1000, ny=500, h=h, A=0.75e-3, seed=20260104, dir_sigma=1.0, dir_seed=20260105,
+                               extent=(2.0, 1.0))
+    assert m.nF == 16000000
+    d[:, 2] -= np.where((np.arange(len(d)) // (1001 * 501)) % 2 == 1, -1.0, 1.0) * 0.25 * h  # keep only the unit Gaussian part
+    gpu_ctx.set_surface_mesh(m)
+    first = None
+    for sigma, a0s, xis in ((0.5 * h, (1.0, 0.25), (0.0, 1e-4)), (1.0 * h, (1.0,), (0.0, 1e-4)), (4.0 * h, (1.0,), (0.0,))):
+        dd = np.ascontiguousarray(d * sigma)      # sigma = 4h triggers the span clamp (SPATIAL_HASH.h:477-482)
+        for a0 in a0s:
+            for xi in xis:
+                a = gpu_ctx.ccd_step(dd, a0, xi)
+                assert 0 < a <= a0, (sigma, a0, xi, a)
+                if first is None:
+                    first = (dd, a0, xi, a)
+    assert gpu_ctx.ccd_step(first[0], first[1], first[2]) == first[3]  # deterministic
+    dd = first[0]
+    a = gpu_ctx.ccd_step(dd, 1.0, 0.0)
+    cpt, cee = gpu_ctx.get_candidates(2), gpu_ctx.get_candidates(3)
+    assert len(cpt) > 0 and len(cee) > 0
+    assert _closest_pairs_never_touch(m, dd, a, cpt, cee, n_check=100000, k_samples=32, n_pool=6000000) > 0
