@@ -349,16 +349,44 @@ __global__ void k_extent_hist(const IBox* __restrict__ bbox, int nB, GridDesc g,
     __syncthreads();
     if (threadIdx.x < 48 && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
 }
+// Shards only look at the cells their own queries visit: the bounding box (in cell coordinates) of the query ranges of
+// this rank is reduced on the device and the fill kernels skip everything outside it, so the cost of building the cell
+// lists shrinks with the shard instead of being replicated on every GPU. region = {lo[3], hi[3]}; one rank: whole grid.
+__global__ void k_query_region(const IBox* __restrict__ qbox, int qBegin, int qEnd, GridDesc g, int* __restrict__ region)
+{
+    int lo[3] = {2147483647, 2147483647, 2147483647}, hi[3] = {-1, -1, -1};
+    for (int q = qBegin + blockIdx.x * blockDim.x + threadIdx.x; q < qEnd; q += gridDim.x * blockDim.x) {
+        int l[3], h[3];
+        cell_range(g, qbox[q], l, h);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { lo[k] = min(lo[k], l[k]); hi[k] = max(hi[k], h[k]); }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        lo[k] = __reduce_min_sync(0xffffffffu, lo[k]);
+        hi[k] = __reduce_max_sync(0xffffffffu, hi[k]);
+    }
+    if (lane_id() == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { atomicMin(&region[k], lo[k]); atomicMax(&region[3 + k], hi[k]); }
+    }
+}
 // MULTI insertion (used for the swept CCD boxes, whose extents vary too much for anchor insertion to pay off): a
 // primitive is stored in every cell its box overlaps and a pair is accepted only in the componentwise max of the two
 // boxes' low corners, which again meets every pair exactly once.
 template <bool FILL>
-__global__ void k_cells_multi(const IBox* __restrict__ bbox, int nB, GridDesc g, int* __restrict__ cellCountOrCursor, CRec* __restrict__ crec)
+__global__ void k_cells_multi(const IBox* __restrict__ bbox, int nB, GridDesc g, const int* __restrict__ region,
+    int* __restrict__ cellCountOrCursor, CRec* __restrict__ crec)
 {
+    int rg[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) rg[k] = region[k];
     for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nB; b += gridDim.x * blockDim.x) {
         int lo[3], hi[3];
         const IBox bb = bbox[b];
         cell_range(g, bb, lo, hi);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { lo[k] = max(lo[k], rg[k]); hi[k] = min(hi[k], rg[3 + k]); } // cells no query of this shard visits
         CRec rc;
 #pragma unroll
         for (int k = 0; k < 3; ++k) { rc.box.i[k] = bb.lo[k]; rc.box.i[3 + k] = bb.hi[k]; }
@@ -378,8 +406,12 @@ __global__ void k_cells_multi(const IBox* __restrict__ bbox, int nB, GridDesc g,
 }
 template <bool FILL>
 __global__ void k_cells(const IBox* __restrict__ bbox, const PrimRec* __restrict__ rec, int nB, GridDesc g, EMax emax,
-    int* __restrict__ cellCountOrCursor, CRec* __restrict__ crec, int* __restrict__ large, int* __restrict__ largeCount)
+    const int* __restrict__ region, int* __restrict__ cellCountOrCursor, CRec* __restrict__ crec, int* __restrict__ large,
+    int* __restrict__ largeCount)
 {
+    int rg[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) rg[k] = region[k];
     for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nB; b += gridDim.x * blockDim.x) {
         int lo[3], hi[3];
         cell_range(g, bbox[b], lo, hi);
@@ -387,6 +419,9 @@ __global__ void k_cells(const IBox* __restrict__ bbox, const PrimRec* __restrict
             if (FILL) large[atomicAdd(largeCount, 1)] = b;
             continue;
         }
+        // queries visit the anchors in [qlo - emax, qhi]: anchors outside the shard's region (grown by emax) are never met
+        if (lo[0] < rg[0] - emax.e[0] || lo[0] > rg[3] || lo[1] < rg[1] - emax.e[1] || lo[1] > rg[4] || lo[2] < rg[2] - emax.e[2] || lo[2] > rg[5])
+            continue;
         const long cell = ((long)lo[2] * g.n[1] + lo[1]) * g.n[0] + lo[0];
         if (FILL) {
             const PrimRec r = rec[b];
@@ -413,17 +448,31 @@ int cub_scan_exclusive(idp_ctx* c, const int* in, int* out, long n)
 static long grid_cells(const GridDesc& g) { return (long)g.n[0] * g.n[1] * g.n[2]; }
 
 #define IDP_LARGE_CAP 4096
+// device region of the cells visited by the queries [qb, qe) of this shard (6 ints behind the histogram scratch)
+static int set_query_region(idp_ctx* c, const IBox* qbox, int qb, int qe, const GridDesc& g, int** regionOut)
+{
+    int* dRegion = (int*)c->histScratch.p + 50;
+    int init[6] = {0, 0, 0, g.n[0] - 1, g.n[1] - 1, g.n[2] - 1};
+    const bool shard = c->nranks > 1;
+    if (shard) { init[0] = init[1] = init[2] = 2147483647; init[3] = init[4] = init[5] = -1; }
+    IDP_CK(c, cudaMemcpyAsync(dRegion, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+    if (shard && qe > qb) IDP_LAUNCH(c, k_query_region, std::min(blocks_for(qe - qb, 256), (unsigned)c->sm_count * 4), 256, 0, qbox, qb, qe, g, dRegion);
+    *regionOut = dRegion;
+    return IDP_OK;
+}
 // Build cellStart (nCells + 1), the cell-sorted records and the large list for the insert boxes bbox[0..nB). Chooses the smallest
 // emax <= 3 that leaves at most IDP_LARGE_CAP primitives on the large list; if there is none the cells are coarsened
 // (g.k doubled: a cell is k^3 lattice voxels) and the choice is repeated.
-static int build_cells_multi(idp_ctx* c, const IBox* bbox, int nB, const GridDesc& g)
+static int build_cells_multi(idp_ctx* c, const IBox* bbox, int nB, const GridDesc& g, const IBox* qbox, int qb, int qe)
 {
+    int* dRegion = nullptr;
+    IDP_TRY(set_query_region(c, qbox, qb, qe, g, &dRegion));
     const long nc = grid_cells(g);
     IDP_CK(c, c->cellStart.reserve(nc + 1));
     IDP_CK(c, c->cellCursor.reserve(nc + 1));
     IDP_CK(c, cudaMemsetAsync(c->cellCursor.p, 0, (nc + 1) * sizeof(int), c->stream));
     IDP_CK(c, cudaMemsetAsync((int*)c->histScratch.p + 48, 0, sizeof(int), c->stream)); // empty large list
-    IDP_LAUNCH(c, k_cells_multi<false>, blocks_for(nB, 256), 256, 0, bbox, nB, g, c->cellCursor.p, (CRec*)nullptr);
+    IDP_LAUNCH(c, k_cells_multi<false>, blocks_for(nB, 256), 256, 0, bbox, nB, g, dRegion, c->cellCursor.p, (CRec*)nullptr);
     IDP_TRY(cub_scan_exclusive(c, c->cellCursor.p, c->cellStart.p, nc + 1));
     int total = 0;
     IDP_CK(c, cudaMemcpyAsync(&total, c->cellStart.p + nc, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -431,11 +480,12 @@ static int build_cells_multi(idp_ctx* c, const IBox* bbox, int nB, const GridDes
     IDP_CK(c, c->crec.reserve((size_t)std::max(total, 1)));
     IDP_CK(c, c->largeList.reserve(IDP_LARGE_CAP + 1));
     IDP_CK(c, cudaMemcpyAsync(c->cellCursor.p, c->cellStart.p, (nc + 1) * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
-    IDP_LAUNCH(c, k_cells_multi<true>, blocks_for(nB, 256), 256, 0, bbox, nB, g, c->cellCursor.p, c->crec.p);
+    IDP_LAUNCH(c, k_cells_multi<true>, blocks_for(nB, 256), 256, 0, bbox, nB, g, dRegion, c->cellCursor.p, c->crec.p);
     IDP_CK(c, cudaGetLastError());
     return IDP_OK;
 }
-static int build_cells(idp_ctx* c, const IBox* bbox, const PrimRec* rec, int nB, GridDesc& g, const int latN[3], EMax* emaxOut, int* nLargeOut)
+static int build_cells(idp_ctx* c, const IBox* bbox, const PrimRec* rec, int nB, GridDesc& g, const int latN[3], EMax* emaxOut, int* nLargeOut,
+    const IBox* qbox, int qb, int qe)
 {
     int* dHist = (int*)c->histScratch.p; // 48 ints
     int hist[48];
@@ -464,6 +514,8 @@ static int build_cells(idp_ctx* c, const IBox* bbox, const PrimRec* rec, int nB,
         for (int d = 0; d < 3; ++d) g.n[d] = std::max(1, (latN[d] + g.k) / g.k);
     }
     if (emax < 0) return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "broad-phase grid could not be sized", __FILE__, __LINE__);
+    int* dRegion = nullptr;
+    IDP_TRY(set_query_region(c, qbox, qb, qe, g, &dRegion)); // after the grid is final (it may have been coarsened above)
     const long nc = grid_cells(g);
     IDP_CK(c, c->cellStart.reserve(nc + 1));
     IDP_CK(c, c->cellCursor.reserve(nc + 1));
@@ -471,11 +523,11 @@ static int build_cells(idp_ctx* c, const IBox* bbox, const PrimRec* rec, int nB,
     int* dLargeCount = (int*)c->histScratch.p + 48;
     IDP_CK(c, cudaMemsetAsync(c->cellCursor.p, 0, (nc + 1) * sizeof(int), c->stream));
     IDP_CK(c, cudaMemsetAsync(dLargeCount, 0, sizeof(int), c->stream));
-    IDP_LAUNCH(c, (k_cells<false>), blocks_for(nB, 256), 256, 0, bbox, rec, nB, g, em, c->cellCursor.p, (CRec*)nullptr, (int*)nullptr, (int*)nullptr);
+    IDP_LAUNCH(c, (k_cells<false>), blocks_for(nB, 256), 256, 0, bbox, rec, nB, g, em, dRegion, c->cellCursor.p, (CRec*)nullptr, (int*)nullptr, (int*)nullptr);
     IDP_TRY(cub_scan_exclusive(c, c->cellCursor.p, c->cellStart.p, nc + 1));
     IDP_CK(c, c->crec.reserve((size_t)std::max(nB, 1)));
     IDP_CK(c, cudaMemcpyAsync(c->cellCursor.p, c->cellStart.p, (nc + 1) * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
-    IDP_LAUNCH(c, (k_cells<true>), blocks_for(nB, 256), 256, 0, bbox, rec, nB, g, em, c->cellCursor.p, c->crec.p, c->largeList.p, dLargeCount);
+    IDP_LAUNCH(c, (k_cells<true>), blocks_for(nB, 256), 256, 0, bbox, rec, nB, g, em, dRegion, c->cellCursor.p, c->crec.p, c->largeList.p, dLargeCount);
     IDP_CK(c, cudaGetLastError());
     *emaxOut = em;
     *nLargeOut = nLarge;
@@ -963,8 +1015,8 @@ int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
     {
         StageTimer tm(c, IDP_STAGE_CCS_PT);
         EMax emax; int nLarge = 0;
-        IDP_TRY(build_cells(c, c->boxTb.p, c->recT.p, c->nBT, g, latN, &emax, &nLarge));
         shard_range(c, c->nBN, &qb, &qe);
+        IDP_TRY(build_cells(c, c->boxTb.p, c->recT.p, c->nBT, g, latN, &emax, &nLarge, c->boxNq.p, qb, qe));
         QueryArgs qa;
         qa.qrec = c->recN.p; qa.qbox = c->boxNq.p; qa.qBegin = qb; qa.qEnd = qe;
         qa.brec = c->recT.p; qa.bbox = c->boxTb.p; qa.cellStart = c->cellStart.p; qa.crec = c->crec.p;
@@ -995,8 +1047,8 @@ int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
     {
         StageTimer tm(c, IDP_STAGE_CCS_EE);
         EMax emax; int nLarge = 0;
-        IDP_TRY(build_cells(c, c->boxEb.p, c->recE.p, c->nBE, g, latN, &emax, &nLarge));
         shard_range(c, c->nBE, &qb, &qe);
+        IDP_TRY(build_cells(c, c->boxEb.p, c->recE.p, c->nBE, g, latN, &emax, &nLarge, c->boxEq.p, qb, qe));
         QueryArgs qa;
         qa.qrec = c->recE.p; qa.qbox = c->boxEq.p; qa.qBegin = qb; qa.qEnd = qe;
         qa.brec = c->recE.p; qa.bbox = c->boxEb.p; qa.cellStart = c->cellStart.p; qa.crec = c->crec.p;
@@ -1058,9 +1110,11 @@ int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
             IDP_CK(c, c->keyTmp.reserve(std::max<long>(nD, 1)));
             size_t bytes = 0;
             if (nD > 0) {
-                IDP_CK(c, cub::DeviceRadixSort::SortKeys(nullptr, bytes, c->keyD.p, c->keyTmp.p, (int)nD, 0, 3 * dupBits, c->stream));
+                // routing only needs the keys grouped by destination: order them by the leading field alone (3 radix passes
+                // instead of 8); the owner sorts what it receives completely
+                IDP_CK(c, cub::DeviceRadixSort::SortKeys(nullptr, bytes, c->keyD.p, c->keyTmp.p, (int)nD, 2 * dupBits, 3 * dupBits, c->stream));
                 IDP_CK(c, c->cubTemp.reserve(bytes));
-                IDP_CK(c, cub::DeviceRadixSort::SortKeys(c->cubTemp.p, bytes, c->keyD.p, c->keyTmp.p, (int)nD, 0, 3 * dupBits, c->stream));
+                IDP_CK(c, cub::DeviceRadixSort::SortKeys(c->cubTemp.p, bytes, c->keyD.p, c->keyTmp.p, (int)nD, 2 * dupBits, 3 * dupBits, c->stream));
                 ++c->lib_launches;
             }
             unsigned long long thr[9];
@@ -1354,8 +1408,8 @@ int ccd_step(idp_ctx* c, double thickness, double* alpha_inout, int keep_candida
     {
         StageTimer tm(c, IDP_STAGE_CCD_PT);
         EMax emax = {{0, 0, 0}};
-        IDP_TRY(build_cells_multi(c, c->boxTb.p, c->nBT, g));
         shard_range(c, c->nBN, &qb, &qe);
+        IDP_TRY(build_cells_multi(c, c->boxTb.p, c->nBT, g, c->boxNq.p, qb, qe));
         QueryArgs qa;
         qa.qrec = c->recN.p; qa.qbox = c->boxNq.p; qa.qBegin = qb; qa.qEnd = qe;
         qa.brec = c->recT.p; qa.bbox = c->boxTb.p; qa.cellStart = c->cellStart.p; qa.crec = c->crec.p;
@@ -1368,8 +1422,8 @@ int ccd_step(idp_ctx* c, double thickness, double* alpha_inout, int keep_candida
     {
         StageTimer tm(c, IDP_STAGE_CCD_EE);
         EMax emax = {{0, 0, 0}};
-        IDP_TRY(build_cells_multi(c, c->boxEb.p, c->nBE, g));
         shard_range(c, c->nBE, &qb, &qe);
+        IDP_TRY(build_cells_multi(c, c->boxEb.p, c->nBE, g, c->boxEb.p, qb, qe));
         QueryArgs qa;
         qa.qrec = c->recE.p; qa.qbox = c->boxEb.p; qa.qBegin = qb; qa.qEnd = qe;
         qa.brec = c->recE.p; qa.bbox = c->boxEb.p; qa.cellStart = c->cellStart.p; qa.crec = c->crec.p;
