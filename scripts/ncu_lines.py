@@ -21,8 +21,12 @@ for l in dis[start + 1:]:
         lines.append((int(m.group(1), 16), cur, m.group(2).strip()))
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
-hdr = rows[1]; ix = {h: i for i, h in enumerate(hdr)}
-body = rows[2:]
+# the page holds one section per captured launch: take the first one (pass -k / -c to ncu to choose the kernel)
+sec = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+end = sec[1] if len(sec) > 1 else len(rows)
+print("kernel:", rows[sec[0]][1])
+hdr = rows[sec[0] + 1]; ix = {h: i for i, h in enumerate(hdr)}
+body = rows[sec[0] + 2:end]
 base = int(body[0][0], 16)
 off2line = {o: (ln, t) for o, ln, t in lines}
 agg = collections.defaultdict(lambda: [0, 0, collections.Counter()])
