@@ -153,7 +153,7 @@ int idp_constraint_set(idp_ctx* c, double dhat2, double thickness, int* n_rows)
     if (!c) return IDP_ERR_INVALID;
     IDP_CK(c, cudaSetDevice(c->device));
     IDP_TRY(build_constraint_set(c, dhat2, thickness));
-    if (n_rows) *n_rows = (int)c->nRows;
+    if (n_rows) *n_rows = (int)(c->rowsLocal ? c->nRowsGlobal : c->nRows);
     return IDP_OK;
 }
 
@@ -161,6 +161,22 @@ int idp_get_constraints(idp_ctx* c, int* rows4, double* info2)
 {
     if (!c) return IDP_ERR_INVALID;
     IDP_CK(c, cudaSetDevice(c->device));
+    if (c->rowsLocal) {
+        // sharded LOCAL-ROWS mode: collective -- every rank must call it; the global list (order of the unsharded path) is
+        // gathered on the device and copied out. Weights are all one here (set by idp_constraint_set).
+        const long n = c->nRowsGlobal;
+        if (rows4 && n) {
+            IDP_CK(c, c->rowsGlobal.reserve(n));
+            IDP_TRY(comm_gather_groups(c, c->rows.p, sizeof(Row4), c->rowsGlobal.p));
+            IDP_CK(c, cudaMemcpyAsync(rows4, c->rowsGlobal.p, n * sizeof(Row4), cudaMemcpyDeviceToHost, c->stream));
+            IDP_CK(c, cudaStreamSynchronize(c->stream));
+        }
+        if (info2 && n) {
+            const double dh2 = c->cs_dhat2;
+            host_parallel(n, [=](long b, long e) { for (long i = b; i < e; ++i) { info2[2 * i] = 1.0; info2[2 * i + 1] = dh2; } });
+        }
+        return IDP_OK;
+    }
     if (rows4 && c->nRows) {
         IDP_CK(c, cudaMemcpyAsync(rows4, c->rows.p, c->nRows * sizeof(Row4), cudaMemcpyDeviceToHost, c->stream));
         IDP_CK(c, cudaStreamSynchronize(c->stream));
@@ -187,6 +203,7 @@ int idp_set_constraints(idp_ctx* c, int n, const int* rows4, const double* info2
     if (!c || n < 0 || (n && !rows4)) return IDP_ERR_INVALID;
     IDP_CK(c, cudaSetDevice(c->device));
     c->nRows = n;
+    c->rowsLocal = false;
     c->permValid = false;
     c->weights_all_one = false;
     IDP_CK(c, c->rows.reserve(std::max(n, 1)));
@@ -356,7 +373,7 @@ long idp_last_count(idp_ctx* c, int what)
 {
     if (!c) return 0;
     switch (what) {
-    case 0: return c->nRows;
+    case 0: return c->rowsLocal ? c->nRowsGlobal : c->nRows;
     case 1: return c->nCandPT;
     case 2: return c->nCandEE;
     case 3: return c->nCcdPT;

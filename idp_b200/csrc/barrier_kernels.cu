@@ -201,6 +201,7 @@ int barrier_eval(idp_ctx* c, double dhat2, double kappa, double thickness, int w
     StageTimer tm(c, IDP_STAGE_BARRIER);
     IDP_CK(c, cudaMemsetAsync(c->counters.p + CNT_ERR_DIST, 0, sizeof(long long), c->stream));
     // this rank's rows (row_owner) in an order grouped by kind
+    const int ownRanks = c->rowsLocal ? 1 : c->nranks; // LOCAL-ROWS mode: every row in c->rows is this rank's
     int ownerShift = 8;
     while (ownerShift < 14 && (c->nV >> ownerShift) > 16 * c->nranks) ++ownerShift;
     if (!c->permValid) {
@@ -208,7 +209,7 @@ int barrier_eval(idp_ctx* c, double dhat2, double kappa, double thickness, int w
         IDP_CK(c, c->rowIota.reserve(c->nRows)); IDP_CK(c, c->rowPerm.reserve(c->nRows));
         unsigned long long* dKind = (unsigned long long*)(c->counters.p + CNT_KINDS);
         IDP_CK(c, cudaMemsetAsync(dKind, 0, 8 * sizeof(long long), c->stream));
-        IDP_LAUNCH(c, k_row_kinds, std::min(blocks_for(c->nRows, 256), (unsigned)c->sm_count * 16), 256, 0, c->rows.p, c->nRows, c->rank, c->nranks, ownerShift,
+        IDP_LAUNCH(c, k_row_kinds, std::min(blocks_for(c->nRows, 256), (unsigned)c->sm_count * 16), 256, 0, c->rows.p, c->nRows, c->rank, ownRanks, ownerShift,
             c->rowKind.p, c->rowIota.p, dKind);
         size_t bytes = 0;
         IDP_CK(c, cub::DeviceRadixSort::SortPairs(nullptr, bytes, c->rowKind.p, c->rowKindSorted.p, c->rowIota.p, c->rowPerm.p, (int)c->nRows, 0, 3, c->stream));
@@ -240,7 +241,7 @@ int barrier_eval(idp_ctx* c, double dhat2, double kappa, double thickness, int w
     if (want_h) {
         IDP_CK(c, c->rowBlkOff.reserve(c->nRows + 1));
         IDP_CK(c, c->segId.reserve(c->nRows + 1));
-        IDP_LAUNCH(c, k_row_block_counts, blocks_for(c->nRows + 1, 256), 256, 0, c->rows.p, c->nRows, c->rank, c->nranks, ownerShift, c->segId.p);
+        IDP_LAUNCH(c, k_row_block_counts, blocks_for(c->nRows + 1, 256), 256, 0, c->rows.p, c->nRows, c->rank, ownRanks, ownerShift, c->segId.p);
         IDP_TRY(cub_scan_exclusive(c, c->segId.p, c->rowBlkOff.p, c->nRows + 1));
         int ends[2] = {0, 0};
         IDP_CK(c, cudaMemcpyAsync(&ends[1], c->rowBlkOff.p + c->nRows, sizeof(int), cudaMemcpyDeviceToHost, c->stream));

@@ -79,6 +79,8 @@ int comm_allreduce_min(idp_ctx* c, double* dev, long n)
     if (r != 0) return fail(c, IDP_ERR_NCCL, "NCCL error: %s at %s:%d", g_nccl.errstr ? g_nccl.errstr(r) : "?", __FILE__, __LINE__);
     return IDP_OK;
 }
+#define IDP_NCCL_BEGIN(c) do { const int r__ = g_nccl.group_start(); if (r__ != 0) return fail(c, IDP_ERR_NCCL, "NCCL error: %s at %s:%d", g_nccl.errstr ? g_nccl.errstr(r__) : "?", __FILE__, __LINE__); } while (0)
+#define IDP_NCCL_END(c) do { const int r__ = g_nccl.group_end(); if (r__ != 0) return fail(c, IDP_ERR_NCCL, "NCCL error: %s at %s:%d", g_nccl.errstr ? g_nccl.errstr(r__) : "?", __FILE__, __LINE__); } while (0)
 // min over ranks of order-encoded 64-bit keys (ncclUint64 = 5)
 int comm_allreduce_min_u64(idp_ctx* c, unsigned long long* dev, long n)
 {
@@ -86,6 +88,42 @@ int comm_allreduce_min_u64(idp_ctx* c, unsigned long long* dev, long n)
     CommTimer tm(c);
     const int r = g_nccl.allreduce(dev, dev, (size_t)n, 5, 3, c->nccl_comm, c->stream);
     if (r != 0) return fail(c, IDP_ERR_NCCL, "NCCL error: %s at %s:%d", g_nccl.errstr ? g_nccl.errstr(r) : "?", __FILE__, __LINE__);
+    return IDP_OK;
+}
+int comm_allgather_i64(idp_ctx* c, long long* dev, long perRank)
+{
+    if (!c->nccl_comm) return IDP_OK;
+    CommTimer tm(c);
+    const int r = g_nccl.allgather(dev + (size_t)c->rank * perRank, dev, (size_t)perRank, 4 /*ncclInt64*/, c->nccl_comm, c->stream);
+    if (r != 0) return fail(c, IDP_ERR_NCCL, "NCCL error: %s at %s:%d", g_nccl.errstr ? g_nccl.errstr(r) : "?", __FILE__, __LINE__);
+    return IDP_OK;
+}
+// LOCAL-ROWS mode: assemble the global per-row array [all direct PT | all direct EE | all merged], each group in rank
+// order (the merged group in descending rank order: its owner ranges follow the vertex slabs) = the order of the
+// unsharded path, from every rank's local [A|B|U] segments. Counts are already known
+// (ctx.shardCnt), so this is three grouped broadcasts without any host round trip. Collective: every rank must call it.
+int comm_gather_groups(idp_ctx* c, const void* local, size_t elemSize, void* globalOut)
+{
+    CommTimer tm(c);
+    const int P = c->nranks;
+    long goff = 0;
+    IDP_NCCL_BEGIN(c);
+    for (int k = 0; k < 3; ++k) {
+        long loff = 0;
+        for (int kk = 0; kk < k; ++kk) loff += c->shardCnt[c->rank][kk];
+        for (int rr = 0; rr < P; ++rr) {
+            const int r = (k == 2) ? P - 1 - rr : rr; // merged group: ascending key = descending leading vertex = descending rank
+            const long n = c->shardCnt[r][k];
+            if (n > 0) {
+                char* dst = (char*)globalOut + (size_t)goff * elemSize;
+                const void* src = (r == c->rank) ? (const void*)((const char*)local + (size_t)loff * elemSize) : (const void*)dst;
+                const int rc = g_nccl.broadcast(src, dst, (size_t)n * elemSize, 0 /*ncclChar*/, r, c->nccl_comm, c->stream);
+                if (rc != 0) { g_nccl.group_end(); return fail(c, IDP_ERR_NCCL, "NCCL error: %s at %s:%d", g_nccl.errstr ? g_nccl.errstr(rc) : "?", __FILE__, __LINE__); }
+            }
+            goff += n;
+        }
+    }
+    IDP_NCCL_END(c);
     return IDP_OK;
 }
 // variable-size all-gather of constraint rows: every rank ends with the concatenation (in rank order) of all ranks' rows
@@ -134,15 +172,16 @@ int comm_allgatherv(idp_ctx* c, const void* local, long nLocal, size_t elemSize,
     return IDP_OK;
 }
 
-// all-to-all of 64-bit keys: rank r receives, from every rank s, the slice [sendOff_s[r], sendOff_s[r+1]) of s's array.
-// Used to route the duplicate-merge keys to the rank that owns their key range (halo-free: keys, not geometry, move).
-int comm_exchange_keys(idp_ctx* c, const unsigned long long* keys, const long sendOff[9], DBuf<unsigned long long>& recv, long* nRecv)
+// all-to-all of 64-bit keys: this rank sends keys[sendBegin[r] .. +sendCount[r]) to rank r and receives every rank's
+// slice for it, concatenated in rank order. Used to route the duplicate-merge keys to the rank that owns their key range
+// (halo-free: keys, not geometry, move).
+int comm_exchange_keys(idp_ctx* c, const unsigned long long* keys, const long sendBegin[8], const long sendCount[8], DBuf<unsigned long long>& recv, long* nRecv)
 {
     CommTimer tm(c);
     const int P = c->nranks;
     IDP_CK(c, c->commCounts.reserve(64)); // P send counts of this rank, gathered into a P x P matrix (P <= 8)
     long long mine[8];
-    for (int r = 0; r < P; ++r) mine[r] = sendOff[r + 1] - sendOff[r];
+    for (int r = 0; r < P; ++r) mine[r] = sendCount[r];
     IDP_CK(c, cudaMemcpyAsync(c->commCounts.p + (size_t)c->rank * P, mine, P * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
     IDP_NCCL(c, g_nccl.allgather(c->commCounts.p + (size_t)c->rank * P, c->commCounts.p, (size_t)P, 4 /*ncclInt64*/, c->nccl_comm, c->stream));
     long long all[64];
@@ -155,8 +194,8 @@ int comm_exchange_keys(idp_ctx* c, const unsigned long long* keys, const long se
     IDP_CK(c, recv.reserve(std::max<long>(total, 1)));
     IDP_NCCL(c, g_nccl.group_start());
     for (int r = 0; r < P; ++r) {
-        const long ns = sendOff[r + 1] - sendOff[r], nr = roff[r + 1] - roff[r];
-        if (ns > 0) { const int rc = g_nccl.send(keys + sendOff[r], (size_t)ns, 5 /*ncclUint64*/, r, c->nccl_comm, c->stream); if (rc) { g_nccl.group_end(); return fail(c, IDP_ERR_NCCL, "NCCL error: %s at %s:%d", g_nccl.errstr ? g_nccl.errstr(rc) : "?", __FILE__, __LINE__); } }
+        const long ns = sendCount[r], nr = roff[r + 1] - roff[r];
+        if (ns > 0) { const int rc = g_nccl.send(keys + sendBegin[r], (size_t)ns, 5 /*ncclUint64*/, r, c->nccl_comm, c->stream); if (rc) { g_nccl.group_end(); return fail(c, IDP_ERR_NCCL, "NCCL error: %s at %s:%d", g_nccl.errstr ? g_nccl.errstr(rc) : "?", __FILE__, __LINE__); } }
         if (nr > 0) { const int rc = g_nccl.recv(recv.p + roff[r], (size_t)nr, 5, r, c->nccl_comm, c->stream); if (rc) { g_nccl.group_end(); return fail(c, IDP_ERR_NCCL, "NCCL error: %s at %s:%d", g_nccl.errstr ? g_nccl.errstr(rc) : "?", __FILE__, __LINE__); } }
     }
     IDP_NCCL(c, g_nccl.group_end());

@@ -146,6 +146,12 @@ struct idp_ctx {
     idp::DBuf<unsigned long long> keyA, keyB, keyD, keyTmp; // sort keys of the row groups
     idp::DBuf<double> weights;
     long nRows = 0;
+    // sharded LOCAL-ROWS mode (set by build_constraint_set): rows holds only this rank's [direct PT][direct EE][merged] rows
+    bool rowsLocal = false;
+    long nRowsGlobal = 0;
+    long shardCnt[8][3] = {};
+    idp::DBuf<idp::Row4> rowsGlobal;     // gathered list (idp_get_constraints)
+    idp::DBuf<double> dist2Global;
     double cs_dhat2 = 0; // dHat2 stored in stencilInfo (after the thickness offset, IPC.h:53-54)
     // ---- barrier outputs ----
     idp::DBuf<double> gbuf;             // 3*nV gradient (xyz interleaved)
@@ -220,7 +226,8 @@ enum Counter {
     CNT_RUNS = 6,
     CNT_ALPHA_BITS = 7, // current CCD step as double bits (atomicMin on positive doubles)
     CNT_KINDS = 16,     // 8 slots: rows of this rank per kind (k_row_kinds)
-    CNT_COUNT = 24
+    CNT_SHARD = 24,     // 3 x 8 slots: (direct PT, direct EE, merged) row counts of every rank
+    CNT_COUNT = 48
 };
 
 // Device-side timers that never block the host: a scope records an event pair from a small pool and the elapsed times
@@ -279,8 +286,10 @@ int cub_scan_exclusive(idp_ctx* c, const int* in, int* out, long n);
 // variable-size all-gather of nLocal elements of elemSize bytes into *outPtr (capacity *outCap elements, grown and
 // preserved when too small) starting at element outOffset; *nTotal = sum over ranks
 int comm_allreduce_min(idp_ctx* c, double* dev, long n);
+int comm_allgather_i64(idp_ctx* c, long long* dev, long perRank); // in place: rank r's perRank values at dev + r*perRank
+int comm_gather_groups(idp_ctx* c, const void* local, size_t elemSize, void* globalOut); // local [A|B|U] -> global [A..|B..|U..]
 int comm_allreduce_min_u64(idp_ctx* c, unsigned long long* dev, long n);
-int comm_exchange_keys(idp_ctx* c, const unsigned long long* keys, const long sendOff[9], DBuf<unsigned long long>& recv, long* nRecv);
+int comm_exchange_keys(idp_ctx* c, const unsigned long long* keys, const long sendBegin[8], const long sendCount[8], DBuf<unsigned long long>& recv, long* nRecv);
 int comm_allgatherv(idp_ctx* c, const void* local, long nLocal, size_t elemSize, void** outPtr, size_t* outCap, long outOffset, long* nTotal);
 
 } // namespace idp

@@ -1087,7 +1087,7 @@ int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
         // its own contiguous query range, so concatenating the sorted shards in rank order is globally sorted.
         Row4* dstA = c->rows.p;
         Row4* dstB = c->rows.p + nA;
-        if (sharded) {
+        if (sharded && !dupBits) { // fallback (keys wider than 64 bits): the row groups are all-gathered below
             IDP_CK(c, c->rowsG.reserve(std::max<long>(nA + nB, 1)));
             dstA = c->rowsG.p;
             dstB = c->rowsG.p + nA;
@@ -1097,10 +1097,17 @@ int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
     }
     unsigned long long* dupKeys = c->keyD.p;
     bool distributedDup = false;
+    c->rowsLocal = false;
     if (sharded) {
-        IDP_TRY(comm_allgatherv(c, c->rowsG.p, nA, sizeof(Row4), (void**)&c->rows.p, &c->rows.cap, 0, &nAg));
-        IDP_TRY(comm_allgatherv(c, c->rowsG.p + nA, nB, sizeof(Row4), (void**)&c->rows.p, &c->rows.cap, nAg, &nBg));
+        if (!dupBits) {
+            IDP_TRY(comm_allgatherv(c, c->rowsG.p, nA, sizeof(Row4), (void**)&c->rows.p, &c->rows.cap, 0, &nAg));
+            IDP_TRY(comm_allgatherv(c, c->rowsG.p + nA, nB, sizeof(Row4), (void**)&c->rows.p, &c->rows.cap, nAg, &nBg));
+        }
         if (dupBits) {
+            // LOCAL-ROWS mode: every rank keeps (and later evaluates) the rows it produced -- its own direct rows and the
+            // merged rows of its key range -- so nothing is replicated; the global list is only materialised on request
+            // (idp_get_constraints). Rows born from a contiguous primitive range touch a contiguous vertex range, which
+            // keeps the per-rank partial CSRs nearly disjoint.
             // distributed duplicate merge: sort the local keys, route every key to the rank owning its range of the leading
             // field (nV-1-p), merge there; the merged rows are gathered below in rank order = key order.
             const int P = c->nranks;
@@ -1130,11 +1137,15 @@ int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
             for (int r = 0; r <= P; ++r) sendOff[r] = (long)split[r];
             sendOff[P] = nD;
             }
-            IDP_TRY(comm_exchange_keys(c, c->keyTmp.p, sendOff, c->keyB, &nDg));
+            // segment s of the leading field (nV-1-p ascending) holds the vertices of slab P-1-s: send it to that rank, so the
+            // merged rows a rank evaluates touch the same vertex slab as its direct rows (near-disjoint partial CSRs)
+            long sendBegin[8], sendCount[8];
+            for (int r = 0; r < P; ++r) { sendBegin[r] = sendOff[P - 1 - r]; sendCount[r] = sendOff[P - r] - sendOff[P - 1 - r]; }
+            IDP_TRY(comm_exchange_keys(c, c->keyTmp.p, sendBegin, sendCount, c->keyB, &nDg));
             dupKeys = c->keyB.p;
             distributedDup = true;
         }
-        IDP_CK(c, c->rows.reserve(std::max<long>(nAg + nBg + nDg, 1), true, c->stream));
+        if (!distributedDup) IDP_CK(c, c->rows.reserve(std::max<long>(nAg + nBg + nDg, 1), true, c->stream));
     }
     {
         const long nA = nAg, nB = nBg, nD = nDg;
@@ -1175,15 +1186,21 @@ int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
             nU = runs;
         }
         if (distributedDup) {
-            // this rank merged its own key range: emit its rows, then all-gather them behind the direct groups
-            IDP_CK(c, c->rowsG.reserve(std::max<long>(nU, 1)));
-            if (nU) IDP_LAUNCH(c, k_emit_merged_keys, blocks_for(nU, 256), 256, 0, c->keyA.p, c->runCounts.p, nU, dupBits, (long long)c->nV, c->rowsG.p);
-            long nUg = 0;
-            IDP_TRY(comm_allgatherv(c, c->rowsG.p, nU, sizeof(Row4), (void**)&c->rows.p, &c->rows.cap, nA + nB, &nUg));
-            nU = 0;        // already in place
-            c->nRows = nA + nB + nUg;
+            // this rank merged its own key range: its rows go behind its direct groups; only the counts are exchanged
+            IDP_CK(c, c->rows.reserve(std::max<long>(nA + nB + nU, 1), true, c->stream));
+            long long mine[3] = {nA, nB, nU};
+            long long* dcnt = c->counters.p + CNT_SHARD; // 3 x P slots
+            IDP_CK(c, cudaMemcpyAsync(dcnt + 3 * c->rank, mine, sizeof(mine), cudaMemcpyHostToDevice, c->stream));
+            IDP_TRY(comm_allgather_i64(c, dcnt, 3));
+            long long all[24];
+            IDP_CK(c, cudaMemcpyAsync(all, dcnt, 3 * c->nranks * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+            IDP_CK(c, cudaStreamSynchronize(c->stream));
+            c->nRowsGlobal = 0;
+            for (int r = 0; r < c->nranks; ++r)
+                for (int k = 0; k < 3; ++k) { c->shardCnt[r][k] = (long)all[3 * r + k]; c->nRowsGlobal += (long)all[3 * r + k]; }
+            c->rowsLocal = true;
         }
-        else c->nRows = nA + nB + nU;
+        c->nRows = nA + nB + nU;
         IDP_CK(c, c->weights.reserve(std::max<long>(c->nRows, 1)));
         if (nU && dupBits) IDP_LAUNCH(c, k_emit_merged_keys, blocks_for(nU, 256), 256, 0, c->keyA.p, c->runCounts.p, nU, dupBits, (long long)c->nV, c->rows.p + nA + nB);
         else if (nU) IDP_LAUNCH(c, k_emit_merged, blocks_for(nU, 256), 256, 0, c->rowsD2.p, c->runCounts.p, nU, c->rows.p + nA + nB);
@@ -1247,22 +1264,28 @@ __global__ void __launch_bounds__(256) k_min_dist(const Row4* __restrict__ rows,
 }
 int min_dist2(idp_ctx* c, double thickness, double* host_dist2, double* min_out)
 {
-    if (c->nRows == 0) return IDP_OK; // IPC.h:2253-2255
+    if ((c->rowsLocal ? c->nRowsGlobal : c->nRows) == 0) return IDP_OK; // IPC.h:2253-2255 (a shard without rows still joins the collectives)
     StageTimer tm(c, IDP_STAGE_MIN_DIST);
-    IDP_CK(c, c->rowDist2.reserve(c->nRows));
+    IDP_CK(c, c->rowDist2.reserve(std::max<long>(c->nRows, 1)));
     unsigned long long init = ~0ull;
     unsigned long long* d = (unsigned long long*)(c->counters.p + 8);
     IDP_CK(c, cudaMemcpyAsync(d, &init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
-    // sharded: when only the minimum is wanted every rank scans a contiguous slice of the (replicated) rows and the
-    // order-encoded minima are combined with one all-reduce; the per-row vector needs all rows on the asking rank
-    const bool slice = c->nranks > 1 && c->nccl_comm && !host_dist2;
+    // sharded: in LOCAL-ROWS mode every rank scans its own rows; with replicated rows (idp_set_constraints) and only the
+    // minimum wanted, a contiguous slice each. The order-encoded minima are combined with one all-reduce.
+    const bool sharded = c->nranks > 1 && c->nccl_comm;
+    const bool slice = sharded && !c->rowsLocal && !host_dist2;
     const long rb = slice ? c->nRows * c->rank / c->nranks : 0, re = slice ? c->nRows * (c->rank + 1) / c->nranks : c->nRows;
     IDP_LAUNCH(c, k_min_dist, std::min(blocks_for(std::max(re - rb, 1L), 256), (unsigned)c->sm_count * 16), 256, 0, c->rows.p, rb, re, c->xp.p,
         c->rowDist2.p, d);
     IDP_CK(c, cudaGetLastError());
-    if (slice) IDP_TRY(comm_allreduce_min_u64(c, d, 1));
+    if (slice || (sharded && c->rowsLocal)) IDP_TRY(comm_allreduce_min_u64(c, d, 1));
     IDP_CK(c, cudaMemcpyAsync(&init, d, sizeof(init), cudaMemcpyDeviceToHost, c->stream));
-    if (host_dist2) IDP_CK(c, cudaMemcpyAsync(host_dist2, c->rowDist2.p, c->nRows * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (host_dist2 && c->rowsLocal) { // per-row vector in the order of the global list (collective)
+        IDP_CK(c, c->dist2Global.reserve(std::max<long>(c->nRowsGlobal, 1)));
+        IDP_TRY(comm_gather_groups(c, c->rowDist2.p, sizeof(double), c->dist2Global.p));
+        IDP_CK(c, cudaMemcpyAsync(host_dist2, c->dist2Global.p, c->nRowsGlobal * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    }
+    else if (host_dist2) IDP_CK(c, cudaMemcpyAsync(host_dist2, c->rowDist2.p, c->nRows * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     IDP_CK(c, cudaStreamSynchronize(c->stream));
     *min_out = dec_ord(init) - thickness * thickness;
     return IDP_OK;

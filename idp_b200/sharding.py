@@ -2,9 +2,14 @@
 (tests/test_sharding_gloo.py):
 
 * query primitives: rank r of P owns the contiguous slice [n*r//P, n*(r+1)//P) (shard_range() in csrc/exact_kernels.cu);
-* constraint rows (barrier E/g/H): the rank that owns the vertex chunk of the row's smallest vertex, chunks of 2^shift
-  consecutive vertices dealt round-robin (row_owner() in csrc/barrier_kernels.cu). Rows touching the same vertices land on
-  the same rank, so the per-rank partial CSRs are nearly disjoint; their sum is the global Hessian.
+* constraint rows built by idp_constraint_set stay on the rank that produced them (LOCAL-ROWS mode): its own direct PT /
+  EE rows plus the merged PP / PE rows whose leading vertex lies in its vertex slab; the global list is only gathered on
+  request (comm_gather_groups() in csrc/comm.cu: direct groups in rank order, merged group in descending rank order);
+* rows handed in by the caller (idp_set_constraints) are replicated, and each is evaluated by the rank that owns the
+  vertex chunk of its smallest vertex, chunks of 2^shift consecutive vertices dealt round-robin (row_owner() in
+  csrc/barrier_kernels.cu).
+Either way rows touching the same vertices land on the same rank, so the per-rank partial CSRs are nearly disjoint; their
+sum is the global Hessian.
 """
 import numpy as np
 

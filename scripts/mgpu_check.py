@@ -23,6 +23,7 @@ rows0, _ = ref.get_constraints()
 E0 = ref.barrier_energy(dh2, kappa); g0 = ref.barrier_gradient(dh2, kappa)
 ptr0, col0, val0 = ref.barrier_hessian(dh2, kappa)
 a0 = ref.ccd_step(direction, 1.0)
+d0, m0 = ref.min_dist2()
 ctx = ContactContext(lr)
 uid = [ctx.unique_id() if rank == 0 else None]
 dist.broadcast_object_list(uid, src=0)
@@ -33,6 +34,8 @@ rows, _ = ctx.get_constraints()
 E = ctx.barrier_energy(dh2, kappa); g = ctx.barrier_gradient(dh2, kappa)
 ptr, col, val = ctx.barrier_hessian(dh2, kappa)
 a = ctx.ccd_step(direction, 1.0)
+d1, m1 = ctx.min_dist2()               # collective in the sharded path: per-row vector in the global order
+_, m2 = ctx.min_dist2(want_all=False)  # min only: local rows + all-reduce
 N = 3 * mesh.nV
 parts = [None] * world
 dist.all_gather_object(parts, sp.csr_matrix((val, col, ptr), shape=(N, N)))
@@ -42,7 +45,7 @@ if rank == 0:
     H0 = sp.csr_matrix((val0, col0, ptr0), shape=(N, N))
     checks = {"rows": n == n0 and np.array_equal(rows, rows0), "E": abs(E - E0) <= 1e-12 * abs(E0),
               "g": np.abs(g - g0).max() <= 1e-12 * np.abs(g0).max(), "H": abs(H - H0).max() <= 1e-12 * abs(H0).max(),
-              "alpha": a == a0}
+              "alpha": a == a0, "dist2": np.array_equal(d1, d0) and m1 == m0 and m2 == m0}
     print("mgpu_check world=%d rows=%d/%d E=%.15e/%.15e alpha=%.15e/%.15e %s" % (world, n, n0, E, E0, a, a0, checks), flush=True)
     ok = all(checks.values())
 dist.barrier()
