@@ -213,8 +213,11 @@ def main():
     ctx.set_positions(Xh.numpy())
     ctx.set_search_direction(Dh.numpy())
 
+    state = {"static_candidates": 0}
+
     def step_resident():
         n = ctx.constraint_set(dhat2)
+        state["static_candidates"] = ctx.count(1) + ctx.count(2)  # the CCD stage reuses (and invalidates) these buffers
         E, nnz = ctx.barrier_all(dhat2, KAPPA)
         a = ctx.ccd_step_resident(1.0)
         _, mn = ctx.min_dist2(want_all=False)
@@ -282,7 +285,7 @@ def main():
     kb_s = kb_ms * 1e-3
     # composite roofline of the whole step: T_roof = sum over stages of max(bytes / BW, flops / FP64 peak)
     nV, nE, nF = mesh.nV, len(mesh.bedge), len(mesh.btri)
-    c_static = ctx.count(1) + ctx.count(2)
+    c_static = state["static_candidates"]
     c_ccd = ctx.count(3) + ctx.count(4)
     n_moll_pt = kinds["pt_ee"] + kinds["moll"]
     blocks_row = {"pt_ee": 16, "moll": 16, "pe": 9, "pp": 4}
@@ -362,7 +365,7 @@ def main():
                 "config": {"workload": "%s: BASELINE configs[3] synthetic tangled multi-sheet surface (%d triangles, %d vertices), "
                                        "dHat=%g, kappa=%g, CCD alpha0=1" % (args.workload, mesh.nF, mesh.nV, dhat, KAPPA),
                            "pairs_per_step": pairs_per_step, "constraint_rows": int(n_rows), "ccd_candidates": int(ccd_local.item()),
-                           "static_candidates": int(ctx.count(1) + ctx.count(2)), "nnz": int(nnz), "sharding": "primitive ranges x%d" % world,
+                           "static_candidates": int(state["static_candidates"]), "nnz": int(nnz), "sharding": "primitive ranges x%d" % world,
                            "l2": "working set per step (candidate lists, 3x3 blocks, CSR) is several GB >> 126 MB L2; no explicit flush"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "library_primitive_calls": int(lib_calls),
                 "roofline": roofline, "cpu_baseline": ({k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")} if cb else None),

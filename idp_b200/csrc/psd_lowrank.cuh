@@ -103,8 +103,8 @@ IDP_HD int first_set_bit(unsigned x) // 1-based, 0 when x == 0
 #endif
 }
 #ifdef IDP_QL_STATS
-struct QlStats { long rows, trips, givens; int n; int chase[512]; };
-static QlStats g_ql_stats = {0, 0, 0, 0, {0}};
+struct QlStats { long rows, trips, givens; int n; int chase[512]; int negcount; };
+static QlStats g_ql_stats = {0, 0, 0, 0, {0}, 0};
 #endif
 template <int N, class ST>
 IDP_HD void make_pd_ql(double* a, ST& S)
@@ -271,10 +271,16 @@ IDP_HD void make_pd_ql(double* a, ST& S)
     }
     // ---- 4. V max(lambda, 0) V^T
     double lam[N];
+#ifdef IDP_QL_STATS
+    g_ql_stats.negcount = 0;
+#endif
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         const double x = ST::d(S.col(i));
         lam[i] = x > 0 ? x : 0.0;
+#ifdef IDP_QL_STATS
+        if (x < 0) ++g_ql_stats.negcount;
+#endif
     }
 #pragma unroll
     for (int r = 0; r < N; ++r) {

@@ -121,6 +121,16 @@ int idp_ccd_step_resident(idp_ctx* ctx, double thickness, double* alpha_inout);
 int idp_min_dist2(idp_ctx* ctx, double thickness, double* dist2, double* min_dist2);
 
 /* ---- multi-GPU (one context per rank; NCCL only for the natural reductions) ---------------------------------- */
+/* Sharded semantics (after idp_comm_init): every entry point is called by ALL ranks with the same arguments.
+ *   idp_constraint_set      queries split by contiguous primitive ranges; each rank keeps the rows it produced (direct PT /
+ *                           EE rows of its range + the merged PP/PE rows of its vertex slab); *n_rows is the GLOBAL count;
+ *   idp_get_constraints     collective: gathers the global list, bit-identical to the single-GPU one, on every rank;
+ *   idp_barrier_*           E and the gradient are all-reduced (every rank returns the global values); the Hessian CSR of a
+ *                           rank holds the partial sums of its rows -- the global Hessian is the sum of the P CSRs (their
+ *                           patterns are nearly disjoint: a primitive range touches a vertex slab);
+ *   idp_ccd_step*           sharded queries, all-reduce(min) of the step;
+ *   idp_min_dist2           all-reduce(min); with dist2 != NULL collective gather of the per-row values in global order;
+ *   idp_set_constraints     rows are replicated and evaluated by the owner of the vertex chunk of their smallest vertex. */
 /* out_id: 128 bytes (ncclUniqueId) produced on rank 0 and broadcast by the host program */
 int idp_comm_unique_id(void* out_id128);
 int idp_comm_init(idp_ctx* ctx, int rank, int nranks, const void* id128);

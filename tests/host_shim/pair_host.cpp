@@ -38,6 +38,7 @@ int hs_accd(int kind, const double* x, const double* d, double eta, double xi, d
 }
 #ifdef IDP_QL_STATS
 // development aid (scripts/ql_stats.py): chase lengths of the QL trips of the last 9x9 projection
+int hs_ql_negcount() { return g_ql_stats.negcount; }
 int hs_ql_trace(int* out) { for (int i = 0; i < g_ql_stats.n; ++i) out[i] = g_ql_stats.chase[i]; return g_ql_stats.n; }
 #endif
 }
