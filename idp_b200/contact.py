@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libidp_contact.so")
 
 STATUS = {0: "IDP_OK", 1: "IDP_ERR_CUDA", 2: "IDP_ERR_INVALID", 3: "IDP_ERR_NONPOSITIVE_DISTANCE",
           4: "IDP_ERR_CCD_ZERO_STEP", 5: "IDP_ERR_UNSUPPORTED_PRIMITIVE", 6: "IDP_ERR_NCCL",
-          7: "IDP_ERR_CCD_ITERATION_CAP"}
+          7: "IDP_ERR_CCD_ITERATION_CAP", 8: "IDP_ERR_EIGEN_NO_CONVERGENCE"}
 STAGES = ["Compute_Constraint_Set_Build_Hash", "Compute_Constraint_Set_PT", "Compute_Constraint_Set_EE",
           "Compute_Constraint_Set_Merge", "Compute_Barrier_EgH", "constructCSRMatrixFromTriplet",
           "Compute_Intersection_Free_StepSize_Build_Hash", "Compute_Intersection_Free_StepSize_PT",

@@ -78,6 +78,7 @@ struct BarrierArgs {
     double* g;                        // 3*nV, xyz interleaved (atomics)
     const int* blkOff; unsigned long long* blkKey; int* blkIdx; double* blkVal; long long nVll;
     unsigned long long* errDist;
+    unsigned long long* errEig;
 };
 
 // Hessian sink: the local Hessian is symmetric, so only one block per unordered vertex pair is stored, keyed (vlo, vhi)
@@ -132,6 +133,7 @@ __global__ void __launch_bounds__(BarrierCfg<PATH>::T, BarrierCfg<PATH>::MINB) k
         BlockEmit em{a.blkKey, a.blkIdx, a.blkVal, WANT_H ? (long)a.blkOff[i] : 0L, d.nv, d.v, a.nVll};
         const bool ok = row_eval<PATH>(d, x, xr, a.weights[i], a.dHat2, a.kappa, a.xi2, a.projectSPD != 0, WANT_H, V9, V6, out, em);
         if (!ok) { atomicAdd(a.errDist, 1ull); continue; }
+        if (WANT_H && out.eigFail) atomicAdd(a.errEig, 1ull);
         if (WANT_E) Eacc += out.E;
         if (WANT_G) {
 #pragma unroll
@@ -200,6 +202,7 @@ int barrier_eval(idp_ctx* c, double dhat2, double kappa, double thickness, int w
     if (c->nRows == 0) return IDP_OK;
     StageTimer tm(c, IDP_STAGE_BARRIER);
     IDP_CK(c, cudaMemsetAsync(c->counters.p + CNT_ERR_DIST, 0, sizeof(long long), c->stream));
+    IDP_CK(c, cudaMemsetAsync(c->counters.p + CNT_ERR_EIG, 0, sizeof(long long), c->stream));
     // this rank's rows (row_owner) in an order grouped by kind
     const int ownRanks = c->rowsLocal ? 1 : c->nranks; // LOCAL-ROWS mode: every row in c->rows is this rank's
     int ownerShift = 8;
@@ -235,6 +238,7 @@ int barrier_eval(idp_ctx* c, double dhat2, double kappa, double thickness, int w
     a.partialE = c->red.p;
     a.g = c->gbuf.p;
     a.errDist = (unsigned long long*)(c->counters.p + CNT_ERR_DIST);
+    a.errEig = (unsigned long long*)(c->counters.p + CNT_ERR_EIG);
     a.nVll = c->nV;
     a.blkOff = nullptr; a.blkKey = nullptr; a.blkIdx = nullptr; a.blkVal = nullptr;
     long nBlocks = 0;
@@ -274,12 +278,14 @@ int barrier_eval(idp_ctx* c, double dhat2, double kappa, double thickness, int w
         if (nPath[2] > 0) IDP_TRY(launch_barrier_path<2>(c, a2, g2, sel));
     }
     if (nMine > 0 && want_e) IDP_LAUNCH(c, k_sum_partials, 1, 256, 0, c->red.p, 3 * (int)grid, c->red.p + 3 * (size_t)grid);
-    long long nerr = 0;
+    long long nerr = 0, neig = 0;
     IDP_CK(c, cudaMemcpyAsync(&nerr, c->counters.p + CNT_ERR_DIST, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    IDP_CK(c, cudaMemcpyAsync(&neig, c->counters.p + CNT_ERR_EIG, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
     double E = 0;
     if (want_e && nMine > 0) IDP_CK(c, cudaMemcpyAsync(&E, c->red.p + 3 * (size_t)grid, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     IDP_CK(c, cudaStreamSynchronize(c->stream));
     if (nerr) return fail(c, IDP_ERR_NONPOSITIVE_DISTANCE, "%s (%s:%d)", "non-positive distance detected during barrier evaluation", __FILE__, __LINE__);
+    if (neig) return fail(c, IDP_ERR_EIGEN_NO_CONVERGENCE, "%s (%s:%d)", "PSD projection: QL iteration cap reached", __FILE__, __LINE__);
     if (E_out) *E_out = E;
     return IDP_OK;
 }

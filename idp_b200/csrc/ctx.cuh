@@ -227,7 +227,8 @@ enum Counter {
     CNT_ALPHA_BITS = 7, // current CCD step as double bits (atomicMin on positive doubles)
     CNT_KINDS = 16,     // 8 slots: rows of this rank per kind (k_row_kinds)
     CNT_SHARD = 24,     // 3 x 8 slots: (direct PT, direct EE, merged) row counts of every rank
-    CNT_COUNT = 48
+    CNT_ERR_EIG = 48,   // rows whose PSD projection hit the QL iteration cap
+    CNT_COUNT = 52
 };
 
 // Device-side timers that never block the host: a scope records an event pair from a small pool and the elapsed times

@@ -107,7 +107,7 @@ struct QlStats { long rows, trips, givens; int n; int chase[512]; int negcount; 
 static QlStats g_ql_stats = {0, 0, 0, 0, {0}, 0};
 #endif
 template <int N, class ST>
-IDP_HD void make_pd_ql(double* a, ST& S)
+IDP_HD bool make_pd_ql(double* a, ST& S) // false: the QL iteration cap was reached (never observed; reported, not ignored)
 {
     // ---- 1. Householder: for column k annihilate a(k+2.., k); v is stored over a(k, k+1..), beta kept
     double beta[N - 2];
@@ -269,6 +269,7 @@ IDP_HD void make_pd_ql(double* a, ST& S)
         ST::dset(cl, dl - p);
         ST::eset(cl, g);
     }
+    const bool converged = l >= N - 1;
     // ---- 4. V max(lambda, 0) V^T
     double lam[N];
 #ifdef IDP_QL_STATS
@@ -295,6 +296,7 @@ IDP_HD void make_pd_ql(double* a, ST& S)
             a[SI<N>(r, c)] = s;
         }
     }
+    return converged;
 }
 
 // ---- reduced-coordinate pieces ---------------------------------------------------------------------------------
@@ -431,6 +433,7 @@ IDP_HD void expand_block(const double (&Hm)[NV][K], const double* M, int i, int 
 struct RowOut {
     double E;
     double g[12];
+    bool eigFail; // the PSD projection did not converge (QL iteration cap)
 };
 
 // PATH selects which kinds are compiled in: -1 all, 0 four-vertex kinds, 1 point-edge, 2 point-point
@@ -438,6 +441,7 @@ template <int PATH, class VS9, class VS6, class Emit>
 IDP_HD bool row_eval(const RowDec& d, const V3* x, const V3* xr, double weight, double dHat2, double kappa, double xi2,
     bool projectSPD, bool wantH, VS9& V9, VS6& V6, RowOut& out, Emit& emit)
 {
+    out.eigFail = false;
     const double dist2 = row_dist2(d.kind, x[0], x[1], x[2], x[3]) - xi2;
     if (!(dist2 > 0)) return false;
     double b, bg, bh;
@@ -502,7 +506,7 @@ IDP_HD bool row_eval(const RowDec& d, const V3* x, const V3* xr, double weight, 
             const double T[2][2] = {{r2, 0.0}, {ir2, -r32}};
             double M[21];
             congruence_blocks<2>(T, H6, M);
-            if (projectSPD) make_pd_ql<6>(M, V6);
+            if (projectSPD && !make_pd_ql<6>(M, V6)) out.eigFail = true;
             const double Hm[3][2] = {{ir2, ir6}, {-ir2, ir6}, {0.0, -2.0 * ir6}};
 #pragma unroll
             for (int i = 0; i < 3; ++i)
@@ -614,7 +618,7 @@ IDP_HD bool row_eval(const RowDec& d, const V3* x, const V3* xr, double weight, 
         const double T[3][3] = {{0, -1, -1}, {-1, 0, -1}, {-1, 0, 1}};
         congruence_blocks<3>(T, H, M);
     }
-    if (projectSPD) make_pd_ql<9>(M, V9);
+    if (projectSPD && !make_pd_ql<9>(M, V9)) out.eigFail = true;
     const double Hm[4][3] = {{0.5, 0.5, 0.5}, {-0.5, 0.5, -0.5}, {0.5, -0.5, -0.5}, {-0.5, -0.5, 0.5}};
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -648,7 +652,7 @@ IDP_HD bool row_EgH_lowrank(const RowDec& d, const V3* x, const V3* xr, double w
     RowOut out;
     DenseEmit em{H, 3 * d.nv};
     const bool ok = row_eval<-1>(d, x, xr, weight, dHat2, kappa, xi2, projectSPD, H != nullptr, V9, V6, out, em);
-    if (!ok) return false;
+    if (!ok || out.eigFail) return false;
     if (E) *E = out.E;
     if (g) for (int i = 0; i < 3 * d.nv; ++i) g[i] = out.g[i];
     return true;

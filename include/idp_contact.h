@@ -30,7 +30,8 @@ enum idp_status {
     IDP_ERR_CCD_ZERO_STEP = 4,          /* IPC.h:2014-2032: CCD returned a zero step -> exit(-1) */
     IDP_ERR_UNSUPPORTED_PRIMITIVE = 5,  /* rod / particle / NNExclusion / dim==2 / shell / elasticIPC inputs: rejected, never emulated */
     IDP_ERR_NCCL = 6,
-    IDP_ERR_CCD_ITERATION_CAP = 7       /* additive CCD exceeded IDP_ACCD_MAX_ITER trips (the reference would loop forever) */
+    IDP_ERR_CCD_ITERATION_CAP = 7,      /* additive CCD exceeded IDP_ACCD_MAX_ITER trips (the reference would loop forever) */
+    IDP_ERR_EIGEN_NO_CONVERGENCE = 8    /* makePD (Math/UTILS.h:9-27): the symmetric eigen-solver hit its iteration cap for some row */
 };
 
 /* stage ids for idp_stage_ms: names follow the reference's TIMER_FLAG scopes */
