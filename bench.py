@@ -37,6 +37,7 @@ WORKLOADS = {
     "sheets8x100": dict(n_sheets=8, nx=100, ny=100, h=4e-3, A=1.5e-3, dhat=2e-3, extent=(0.2, 0.2)),
 }
 CPU_SAMPLE = "sheets8x100"  # crop of the same sheets (same waves, same spacing, same dHat): 160,000 triangles
+CPU_SAMPLE_REF = "sheets8x100"  # same crop for the reference's own loops (they keep 144 16-byte triplets per row: ~5 GB of host memory)
 
 # algorithmic bytes / flops per constraint row
 ROW_BYTES = {"pt_ee": 1384.0, "moll": 1384.0 + 96.0, "pe": 832.0, "pp": 424.0}
@@ -131,22 +132,56 @@ def cpu_step(orc, om, direction, dhat2):
     return len(rows) + len(c["cand_pt"]) + len(c["cand_ee"])
 
 
+def ref_step(ref, mesh, direction, dhat2):
+    """One synthetic Newton iteration through the REFERENCE's own operators (FEM/IPC.h compiled into oracle/_ref); the
+    triplet -> CSR step (Eigen setFromTriplets in the reference, Math/CSR_MATRIX.h:49-56) is scipy's coo -> csr."""
+    import scipy.sparse as sp
+    rows, info = ref.constraint_set(mesh, dhat2, cap=max(4000000, 12 * mesh.nF))
+    E, g, (tr, tc, tv) = ref.barrier(mesh, rows, info[:, 0], dhat2, KAPPA, project_spd=True)
+    N = 3 * mesh.nV
+    sp.coo_matrix((tv, (tr, tc)), shape=(N, N)).tocsr()
+    ref.ccd(mesh, direction, 1.0)
+    ref.min_dist2(mesh, rows)
+    return len(rows)
+
+
 def cpu_baseline(steps=1, warmup=0):
+    """CPU arm on the host cores: the reference's own loops when oracle/_ref/libidp_ref_ipc.so was built (kind
+    "reference"), else the oracle port (kind "port"). Both run the reference's parallel structure on all host threads."""
+    from oracle import ref_binding
     from oracle.binding import Oracle
     orc = Oracle("fast")  # -O3 -mfma -mavx2: the reference's own flags (CMakeLists.txt:20)
-    mesh, direction, dhat = build_workload(CPU_SAMPLE)
+    use_ref = ref_binding.ipc_available() and not os.environ.get("IDP_BENCH_CPU_PORT")
+    sample = CPU_SAMPLE_REF if use_ref else CPU_SAMPLE
+    mesh, direction, dhat = build_workload(sample)
     om = orc.mesh(mesh.X, mesh.X0, mesh.bnode, mesh.bedge, mesh.btri, mesh.dbc)
-    for _ in range(warmup):
-        cpu_step(orc, om, direction, dhat * dhat)
-    t0 = time.perf_counter()
-    pairs = 0
-    for _ in range(steps):
-        pairs += cpu_step(orc, om, direction, dhat * dhat)
-    dt = time.perf_counter() - t0
+    pairs_ref = 0
+    if use_ref:
+        ref = ref_binding.ReferenceIPC()
+        c = orc.ccd(om, direction, 1.0, want_cand=True)  # the reference does not report its candidate count; the sets are identical
+        pairs_ref = len(c["cand_pt"]) + len(c["cand_ee"])
+        devnull, saved = os.open(os.devnull, os.O_WRONLY), os.dup(1)  # the reference prints voxel counts to stdout
+        sys.stdout.flush()
+        os.dup2(devnull, 1)
+    try:
+        for _ in range(warmup):
+            ref_step(ref, mesh, direction, dhat * dhat) if use_ref else cpu_step(orc, om, direction, dhat * dhat)
+        t0 = time.perf_counter()
+        pairs = 0
+        for _ in range(steps):
+            pairs += (ref_step(ref, mesh, direction, dhat * dhat) + pairs_ref) if use_ref else cpu_step(orc, om, direction, dhat * dhat)
+        dt = time.perf_counter() - t0
+    finally:
+        if use_ref:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(devnull)
     cores = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
-    return {"value": pairs / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%s: crop of the bench sheets (%d triangles, same waves/spacing/dHat), %d step(s), %.1f s, %d pairs/step"
-                      % (CPU_SAMPLE, mesh.nF, steps, dt, pairs // max(steps, 1)),
+    what = ("the reference's own FEM/IPC.h + Grid/SPATIAL_HASH.h compiled into oracle/_ref (OpenMP Par_Each)" if use_ref
+            else "oracle port with the reference's parallel structure")
+    return {"value": pairs / dt, "unit": UNIT, "cores": cores, "kind": "reference" if use_ref else "port",
+            "sample": "%s: crop of the bench sheets (%d triangles, same waves/spacing/dHat), %d step(s), %.1f s, %d pairs/step; %s"
+                      % (sample, mesh.nF, steps, dt, pairs // max(steps, 1), what),
             "ms_per_step": 1e3 * dt / max(steps, 1), "pairs_per_step": pairs // max(steps, 1), "triangles": mesh.nF}
 
 
@@ -157,7 +192,7 @@ def run_reference(args, rank):
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "sheets8x500 (BASELINE configs[3]); each step = bounded sample %s" % CPU_SAMPLE},
+            "config": {"workload": "sheets8x500 (BASELINE configs[3]); each step = bounded sample %s" % cb["sample"].split(":")[0]},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))

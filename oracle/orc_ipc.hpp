@@ -5,7 +5,9 @@
 // (SURVEY.md F8), and of the two SPATIAL_HASH builds they use (Library/Grid/SPATIAL_HASH.h).
 // The parallel structure mirrors the reference: `omp parallel for` where the
 // reference uses Par_Each, serial where the reference is serial (hash inserts, merge, E, g, min-dist),
-// because the same code is timed as the CPU baseline ("port").
+// because the same code can be timed as the CPU baseline ("port").
+// Checked against the reference's own FEM/IPC.h + Grid/SPATIAL_HASH.h compiled into oracle/_ref/libidp_ref_ipc.so:
+// constraint sets, merged-group order, E, per-row distances and CCD steps bit for bit, g / H to 1e-12 (tests/test_ref_loops.py).
 #pragma once
 #include "orc_deriv.hpp"
 #include <vector>

@@ -1,11 +1,13 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY. Nothing under idp_b200/ may include, link or call this.
 //
 // CPU restatement of the per-pair math of the IPC contact hot path of ipc-sim/IDP ("JGSL").
-// Parity status: the reference ships no golden vectors and its arithmetic runs
-// through an unpinned Eigen; the pieces below that are taken from Eigen semantics (3-term
-// reduction order, pivoted 2x2 LDLT) are therefore "parity unpinned" at the Eigen boundary.
-// The scalar derivative code of the reference (g_PT/H_PT/... generated by MATLAB) is checked
-// against this file through oracle/_ref (see oracle/ref_shim/) and tests/golden/.
+// Parity status: PINNED AGAINST THE REFERENCE'S OWN CODE, with one stated exception. The reference ships no golden
+// vectors, so the pins are produced here: its per-pair headers (Math/Distance/*.h, BARRIER.h, UTILS.h) AND
+// its loops (FEM/IPC.h, Grid/SPATIAL_HASH.h) are compiled from /root/reference into oracle/_ref (oracle/ref_shim/) and this
+// restatement is checked against them bit for bit / to 1e-12 (tests/test_golden.py, tests/test_ref_loops.py and the
+// fixtures under tests/golden/). The exception: Eigen itself is not installed, so the reference code runs on the repo's
+// Eigen subset; what is taken from Eigen semantics there (3-term reduction order, pivoted 2x2 LDLT, VectorXd::mean()
+// order, the symmetric eigen-solver) remains "parity unpinned" at the Eigen boundary.
 //
 // All citations are relative to /root/reference/Library.
 //

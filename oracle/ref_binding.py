@@ -8,10 +8,15 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(_HERE, "_ref", "libidp_ref.so")
+LIB_IPC = os.path.join(_HERE, "_ref", "libidp_ref_ipc.so")
 
 
 def available():
     return os.path.exists(LIB)
+
+
+def ipc_available():
+    return os.path.exists(LIB_IPC)
 
 
 def build():
@@ -79,3 +84,56 @@ class Reference:
         x = np.ascontiguousarray(x, np.float64)
         d = np.ascontiguousarray(d if d is not None else np.zeros_like(x), np.float64)
         return bool(self.lib.ref_aabb(kind, _p(x), _p(d), dist))
+
+
+class ReferenceIPC:
+    """The reference's own six contact operators (FEM/IPC.h + Grid/SPATIAL_HASH.h compiled from /root/reference on
+    std::vector storage stand-ins, oracle/ref_shim/ref_ipc_capi.cpp): <double, 3, shell=false, elasticIPC=false>."""
+
+    def __init__(self):
+        L = self.lib = C.CDLL(LIB_IPC)
+        L.refipc_constraint_set.restype = C.c_int
+        L.refipc_constraint_set.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                            C.c_void_p, C.c_double, C.c_double, C.c_long, C.c_void_p, C.c_void_p]
+        L.refipc_barrier.restype = C.c_long
+        L.refipc_barrier.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double,
+                                     C.c_int, C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.refipc_ccd.restype = C.c_double
+        L.refipc_ccd.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_double, C.c_double]
+        L.refipc_min_dist2.restype = C.c_double
+        L.refipc_min_dist2.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_void_p]
+
+    @staticmethod
+    def _mesh(m):
+        return (np.ascontiguousarray(m.X, np.float64), np.ascontiguousarray(m.X0, np.float64), np.ascontiguousarray(m.bnode, np.int32),
+                np.ascontiguousarray(m.bedge, np.int32), np.ascontiguousarray(m.btri, np.int32), np.ascontiguousarray(m.dbc, np.uint8))
+
+    def constraint_set(self, m, dHat2, thickness=0.0, cap=4000000):
+        X, X0, bn, be, bt, dbc = self._mesh(m)
+        rows = np.zeros((cap, 4), np.int32); info = np.zeros((cap, 2))
+        n = self.lib.refipc_constraint_set(len(X), _p(X), _p(X0), len(bn), _p(bn), len(be), _p(be), len(bt), _p(bt), _p(dbc), dHat2, thickness,
+                                           cap, _p(rows), _p(info))
+        assert n <= cap
+        return rows[:n].copy(), info[:n].copy()
+
+    def barrier(self, m, rows, weights, dHat2, kappa, thickness=0.0, project_spd=True, want_h=True):
+        X, X0 = np.ascontiguousarray(m.X, np.float64), np.ascontiguousarray(m.X0, np.float64)
+        rows = np.ascontiguousarray(rows, np.int32); w = np.ascontiguousarray(weights, np.float64)
+        E = C.c_double(0.0); g = np.zeros((len(X), 3))
+        cap = 144 * len(rows) + 1
+        tr = np.zeros(cap, np.int32); tc = np.zeros(cap, np.int32); tv = np.zeros(cap)
+        nt = self.lib.refipc_barrier(len(X), _p(X), _p(X0), len(rows), _p(rows), _p(w), dHat2, kappa, thickness, int(project_spd), C.byref(E), _p(g),
+                                     cap, _p(tr) if want_h else None, _p(tc) if want_h else None, _p(tv) if want_h else None)
+        return E.value, g, (tr[:nt], tc[:nt], tv[:nt])
+
+    def ccd(self, m, direction, step=1.0, thickness=0.0):
+        X, X0, bn, be, bt, dbc = self._mesh(m)
+        d = np.ascontiguousarray(direction, np.float64)
+        return self.lib.refipc_ccd(len(X), _p(X), len(bn), _p(bn), len(be), _p(be), len(bt), _p(bt), _p(dbc), _p(d), thickness, step)
+
+    def min_dist2(self, m, rows, thickness=0.0):
+        X = np.ascontiguousarray(m.X, np.float64); rows = np.ascontiguousarray(rows, np.int32)
+        d = np.zeros(len(rows))
+        mn = self.lib.refipc_min_dist2(len(X), _p(X), len(rows), _p(rows), thickness, _p(d))
+        return d, mn

@@ -3,8 +3,12 @@
 // Semantics transcribed from Eigen that affect results:
 //   * 3-term reductions (dot / squaredNorm) associate as x0 + (x1 + x2); n-term ones split in halves recursively;
 //   * LDLT is the pivoted in-place algorithm (largest |diagonal| first), solve zeroes pivots <= numeric_limits::min;
-//   * SelfAdjointEigenSolver: eigenvalues ascending, lower triangle read (implemented with cyclic Jacobi).
+//   * SelfAdjointEigenSolver: eigenvalues ascending, lower triangle read (Householder tridiagonalisation + implicit QL).
 // Expressions are evaluated eagerly, coefficient by coefficient, which matches Eigen's lazy coefficient-wise order.
+// For FEM/IPC.h and Grid/SPATIAL_HASH.h (ref_ipc_capi.cpp) it also has: run-time sized Matrix<T, Dynamic, C> (row(),
+// colwise().minCoeff()/maxCoeff(), mean() = zero-padded power-of-two tree sum / n, the order the oracle and the CUDA path
+// use -- Eigen's own vectorised order is not recoverable offline), coefficient-wise Array<T,R,C> with Matrix <-> Array and
+// row <-> column vector conversions, Triplet, and a 3x3 fullPivLu().solve (only used by dead code of IPC.h).
 #pragma once
 #include <cmath>
 #include <cstring>
@@ -12,6 +16,9 @@
 #include <algorithm>
 #include <limits>
 #include <iostream>
+#include <cassert>
+#include <numeric>
+#include <type_traits>
 
 namespace Eigen {
 
@@ -38,6 +45,8 @@ struct Matrix {
     template <int R2, int C2, class = typename std::enable_if<(R2 == C && C2 == R && (R == 1 || C == 1) && R != C)>::type>
     Matrix(const Matrix<T, R2, C2>& o) { for (int i = 0; i < R * C; ++i) d[i] = o.d[i]; }
     Matrix(const Array<T, R, C>& a);
+    template <int R2, int C2, class = typename std::enable_if<(R2 == C && C2 == R && R != C)>::type>
+    Matrix(const Array<T, R2, C2>& a) { for (int i = 0; i < R * C; ++i) d[i] = a.d[i]; }
     static Matrix Zero() { Matrix m; m.setZero(); return m; }
     T& operator()(int i, int j) { return d[i + j * R]; }
     const T& operator()(int i, int j) const { return d[i + j * R]; }
@@ -90,6 +99,32 @@ struct Matrix {
         return redux_sum(t, 0, R * C);
     }
     T norm() const { return std::sqrt(squaredNorm()); }
+    T prod() const { T p = d[0]; for (int i = 1; i < R * C; ++i) p *= d[i]; return p; }
+    // Gaussian elimination with full pivoting (3x3 use in dead code of FEM/IPC.h; not result relevant)
+    struct FullPivLU {
+        Matrix A;
+        Matrix<T, R, 1> solve(const Matrix<T, R, 1>& b) const
+        {
+            Matrix M = A; Matrix<T, R, 1> x = b; int perm[R];
+            for (int i = 0; i < R; ++i) perm[i] = i;
+            for (int k = 0; k < R; ++k) {
+                int pi = k, pj = k; T best = -1;
+                for (int i = k; i < R; ++i) for (int j = k; j < R; ++j) if (std::fabs(M(i, j)) > best) { best = std::fabs(M(i, j)); pi = i; pj = j; }
+                for (int j = 0; j < R; ++j) std::swap(M(k, j), M(pi, j));
+                std::swap(x.d[k], x.d[pi]);
+                for (int i = 0; i < R; ++i) std::swap(M(i, k), M(i, pj));
+                std::swap(perm[k], perm[pj]);
+                if (M(k, k) == T(0)) continue;
+                for (int i = k + 1; i < R; ++i) { const T f = M(i, k) / M(k, k); for (int j = k; j < R; ++j) M(i, j) -= f * M(k, j); x.d[i] -= f * x.d[k]; }
+            }
+            Matrix<T, R, 1> y;
+            for (int i = R - 1; i >= 0; --i) { T t = x.d[i]; for (int j = i + 1; j < R; ++j) t -= M(i, j) * y.d[j]; y.d[i] = (M(i, i) != T(0)) ? t / M(i, i) : T(0); }
+            Matrix<T, R, 1> out;
+            for (int i = 0; i < R; ++i) out.d[perm[i]] = y.d[i];
+            return out;
+        }
+    };
+    FullPivLU fullPivLu() const { return FullPivLU{*this}; }
     template <int R2, int C2> Matrix cross(const Matrix<T, R2, C2>& o) const
     {
         static_assert(R * C == 3 && R2 * C2 == 3, "cross needs 3-vectors");
@@ -114,7 +149,16 @@ struct Matrix {
         Matrix& m; int j;
         operator Matrix<T, R, 1>() const { Matrix<T, R, 1> r; for (int i = 0; i < R; ++i) r.d[i] = m(i, j); return r; }
         ColRef& operator=(const Matrix<T, R, 1>& r) { for (int i = 0; i < R; ++i) m(i, j) = r.d[i]; return *this; }
+        template <int R2, int C2> ColRef& operator=(const Matrix<T, R2, C2>& r) { static_assert(R2 * C2 == R, "size"); for (int i = 0; i < R; ++i) m(i, j) = r.d[i]; return *this; }
+        Matrix<T, R, 1> cross(const ColRef& o) const { return ((Matrix<T, R, 1>)*this).cross((Matrix<T, R, 1>)o); }
+        template <int R2, int C2> Matrix<T, R, 1> cross(const Matrix<T, R2, C2>& o) const { return ((Matrix<T, R, 1>)*this).cross(o); }
     };
+    T determinant() const
+    {
+        static_assert(R == 3 && C == 3, "3x3 only");
+        const Matrix& a = *this;
+        return a(0, 0) * (a(1, 1) * a(2, 2) - a(1, 2) * a(2, 1)) - a(0, 1) * (a(1, 0) * a(2, 2) - a(1, 2) * a(2, 0)) + a(0, 2) * (a(1, 0) * a(2, 1) - a(1, 1) * a(2, 0));
+    }
     RowRef row(int i) { return RowRef{*this, i}; }
     ColRef col(int j) { return ColRef{*this, j}; }
     template <int N> struct SegRef {
@@ -124,6 +168,14 @@ struct Matrix {
         Matrix<T, N, 1> operator-() const { return -((Matrix<T, N, 1>)*this); }
     };
     template <int N> SegRef<N> segment(int s) { return SegRef<N>{*this, s}; }
+    template <int BR, int BC> struct BlockRef {
+        Matrix& m; int i0, j0;
+        operator Matrix<T, BR, BC>() const { Matrix<T, BR, BC> r; for (int i = 0; i < BR; ++i) for (int j = 0; j < BC; ++j) r(i, j) = m(i0 + i, j0 + j); return r; }
+        template <class O> BlockRef& operator+=(const O& o) { const Matrix<T, BR, BC> v = o; for (int i = 0; i < BR; ++i) for (int j = 0; j < BC; ++j) m(i0 + i, j0 + j) += v(i, j); return *this; }
+        template <class O> BlockRef& operator=(const O& o) { const Matrix<T, BR, BC> v = o; for (int i = 0; i < BR; ++i) for (int j = 0; j < BC; ++j) m(i0 + i, j0 + j) = v(i, j); return *this; }
+        Matrix<T, BC, BR> transpose() const { return ((Matrix<T, BR, BC>)*this).transpose(); }
+    };
+    template <int BR, int BC> BlockRef<BR, BC> block(int i, int j) { return BlockRef<BR, BC>{*this, i, j}; }
     struct DiagRef {
         Matrix& m;
         void setConstant(T v) { for (int i = 0; i < (R < C ? R : C); ++i) m(i, i) = v; }
@@ -177,18 +229,96 @@ template <class T, int R, int C> inline std::ostream& operator<<(std::ostream& o
 template <class T, int R, int C>
 struct Array {
     T d[R * C];
+    Array() {}
+    // vectors convert between orientations; matrices convert to arrays implicitly (Eigen: MatrixBase -> Array assignment)
+    template <int R2, int C2, class = typename std::enable_if<(R2 * C2 == R * C)>::type>
+    Array(const Matrix<T, R2, C2>& m) { for (int i = 0; i < R * C; ++i) d[i] = m.d[i]; }
+    template <int R2, int C2, class = typename std::enable_if<(R2 == C && C2 == R && R != C)>::type>
+    Array(const Array<T, R2, C2>& o) { for (int i = 0; i < R * C; ++i) d[i] = o.d[i]; }
+    static Array Zero() { Array a; for (int i = 0; i < R * C; ++i) a.d[i] = T(0); return a; }
+    static Array Ones() { Array a; for (int i = 0; i < R * C; ++i) a.d[i] = T(1); return a; }
+    void setOnes() { for (int i = 0; i < R * C; ++i) d[i] = T(1); }
+    void setZero() { for (int i = 0; i < R * C; ++i) d[i] = T(0); }
+    T& operator[](int i) { return d[i]; }
+    const T& operator[](int i) const { return d[i]; }
+    T& operator()(int i) { return d[i]; }
+    const T& operator()(int i) const { return d[i]; }
     Array max(const Array& o) const { Array a; for (int i = 0; i < R * C; ++i) a.d[i] = std::max(d[i], o.d[i]); return a; }
     Array min(const Array& o) const { Array a; for (int i = 0; i < R * C; ++i) a.d[i] = std::min(d[i], o.d[i]); return a; }
     Array operator-(const Array& o) const { Array a; for (int i = 0; i < R * C; ++i) a.d[i] = d[i] - o.d[i]; return a; }
+    Array operator+(const Array& o) const { Array a; for (int i = 0; i < R * C; ++i) a.d[i] = d[i] + o.d[i]; return a; }
     Array operator-(T s) const { Array a; for (int i = 0; i < R * C; ++i) a.d[i] = d[i] - s; return a; }
     Array operator+(T s) const { Array a; for (int i = 0; i < R * C; ++i) a.d[i] = d[i] + s; return a; }
+    Array operator*(T s) const { Array a; for (int i = 0; i < R * C; ++i) a.d[i] = d[i] * s; return a; }
     Array<bool, R, C> operator>(T s) const { Array<bool, R, C> a; for (int i = 0; i < R * C; ++i) a.d[i] = d[i] > s; return a; }
     bool any() const { for (int i = 0; i < R * C; ++i) if (d[i]) return true; return false; }
+    Array ceil() const { Array a; for (int i = 0; i < R * C; ++i) a.d[i] = std::ceil(d[i]); return a; }
+    Array floor() const { Array a; for (int i = 0; i < R * C; ++i) a.d[i] = std::floor(d[i]); return a; }
+    template <class U> Array<U, R, C> cast() const { Array<U, R, C> a; for (int i = 0; i < R * C; ++i) a.d[i] = static_cast<U>(d[i]); return a; }
+    T prod() const { T p = d[0]; for (int i = 1; i < R * C; ++i) p *= d[i]; return p; }
+    T minCoeff() const { T m = d[0]; for (int i = 1; i < R * C; ++i) m = std::min(m, d[i]); return m; }
+    T maxCoeff() const { T m = d[0]; for (int i = 1; i < R * C; ++i) m = std::max(m, d[i]); return m; }
+    Matrix<T, R, C> matrix() const { Matrix<T, R, C> m; for (int i = 0; i < R * C; ++i) m.d[i] = d[i]; return m; }
+    Array<T, C, R> transpose() const { Array<T, C, R> a; for (int i = 0; i < R * C; ++i) a.d[i] = d[i]; return a; } // vectors only
 };
 template <class T, int R, int C> Array<T, R, C> Matrix<T, R, C>::array() const { Array<T, R, C> a; for (int i = 0; i < R * C; ++i) a.d[i] = d[i]; return a; }
 template <class T, int R, int C> Matrix<T, R, C>::Matrix(const Array<T, R, C>& a) { for (int i = 0; i < R * C; ++i) d[i] = a.d[i]; }
 
+// run-time sized matrix with a fixed number of columns (column major)
+template <class T, int C>
+struct Matrix<T, Dynamic, C> {
+    std::vector<T> d;
+    int nr = 0;
+    Matrix() {}
+    Matrix(long rows, long cols) : d((size_t)rows * cols), nr((int)rows) { (void)cols; }
+    T& operator()(int i, int j) { return d[i + (size_t)j * nr]; }
+    const T& operator()(int i, int j) const { return d[i + (size_t)j * nr]; }
+    T& operator[](int i) { return d[i]; }
+    const T& operator[](int i) const { return d[i]; }
+    T& operator()(int i) { return d[i]; }
+    const T& operator()(int i) const { return d[i]; }
+    int rows() const { return nr; }
+    int cols() const { return C; }
+    Matrix<T, 1, C> row(int i) const { Matrix<T, 1, C> r; for (int j = 0; j < C; ++j) r.d[j] = (*this)(i, j); return r; }
+    struct Colwise {
+        const Matrix& m;
+        Matrix<T, 1, C> minCoeff() const
+        {
+            Matrix<T, 1, C> r;
+            for (int j = 0; j < C; ++j) { T v = m(0, j); for (int i = 1; i < m.nr; ++i) v = std::min(v, m(i, j)); r.d[j] = v; }
+            return r;
+        }
+        Matrix<T, 1, C> maxCoeff() const
+        {
+            Matrix<T, 1, C> r;
+            for (int j = 0; j < C; ++j) { T v = m(0, j); for (int i = 1; i < m.nr; ++i) v = std::max(v, m(i, j)); r.d[j] = v; }
+            return r;
+        }
+    };
+    Colwise colwise() const { return Colwise{*this}; }
+    static T tree(const T* a, long n, long lo, long len)
+    {
+        if (lo >= n) return T(0);
+        if (len == 1) return a[lo];
+        return tree(a, n, lo, len / 2) + tree(a, n, lo + len / 2, len / 2);
+    }
+    T sum() const { const long n = (long)d.size(); if (n <= 0) return T(0); long P = 1; while (P < n) P <<= 1; return tree(d.data(), n, 0, P); }
+    T mean() const { return sum() / T(d.size()); }
+};
+
+template <class T>
+struct Triplet {
+    int r, c; T v;
+    Triplet() : r(0), c(0), v(0) {}
+    Triplet(int i, int j, const T& x) : r(i), c(j), v(x) {}
+    int row() const { return r; }
+    int col() const { return c; }
+    const T& value() const { return v; }
+};
+
 typedef Matrix<double, 1, 3> RowVector3d;
+typedef Matrix<double, 3, 1> Vector3d;
+typedef Matrix<double, 3, 3> Matrix3d;
 
 template <class T, int N>
 struct DiagonalMatrix {
@@ -204,33 +334,122 @@ template <class T, int N> inline Matrix<T, N, N> operator*(const Matrix<T, N, N>
 }
 
 template <class MatT> struct SelfAdjointEigenSolver;
+// Symmetric eigen-decomposition the way Eigen does it: Householder reduction to tridiagonal form followed by implicit
+// shifted QL/QR iterations on the tridiagonal matrix with the rotations accumulated (classic tred2 / tql2 structure),
+// eigenvalues ascending, lower triangle read. (A first version used cyclic Jacobi; it was 5x slower than this, which made
+// the reference loops compiled against this subset an unfairly slow CPU baseline.)
 template <class T, int N>
 struct SelfAdjointEigenSolver<Matrix<T, N, N>> {
     Matrix<T, N, 1> lam;
     Matrix<T, N, N> vec;
     explicit SelfAdjointEigenSolver(const Matrix<T, N, N>& Ain)
     {
-        T A[N][N], V[N][N];
-        for (int i = 0; i < N; ++i) for (int j = 0; j < N; ++j) { A[i][j] = (i >= j) ? Ain(i, j) : Ain(j, i); V[i][j] = (i == j); }
-        for (int sweep = 0; sweep < 100; ++sweep) {
-            T off = 0, tot = 0;
-            for (int i = 0; i < N; ++i) for (int j = 0; j < N; ++j) { tot += A[i][j] * A[i][j]; if (i != j) off += A[i][j] * A[i][j]; }
-            if (off <= 1e-34 * tot || off == 0) break;
-            for (int p = 0; p < N - 1; ++p)
-                for (int q = p + 1; q < N; ++q) {
-                    if (A[p][q] == 0) continue;
-                    const T th = (A[q][q] - A[p][p]) / (2 * A[p][q]);
-                    const T t = (th >= 0 ? 1 : -1) / (std::fabs(th) + std::sqrt(th * th + 1));
-                    const T c = 1 / std::sqrt(t * t + 1), s = t * c;
-                    for (int k = 0; k < N; ++k) { const T a = A[k][p], b = A[k][q]; A[k][p] = c * a - s * b; A[k][q] = s * a + c * b; }
-                    for (int k = 0; k < N; ++k) { const T a = A[p][k], b = A[q][k]; A[p][k] = c * a - s * b; A[q][k] = s * a + c * b; }
-                    for (int k = 0; k < N; ++k) { const T a = V[k][p], b = V[k][q]; V[k][p] = c * a - s * b; V[k][q] = s * a + c * b; }
+        T V[N][N], d[N], e[N];
+        for (int i = 0; i < N; ++i) for (int j = 0; j < N; ++j) V[i][j] = (i >= j) ? Ain(i, j) : Ain(j, i);
+        // ---- Householder tridiagonalisation (rows from the bottom up), V accumulates the transformation
+        for (int j = 0; j < N; ++j) d[j] = V[N - 1][j];
+        for (int i = N - 1; i > 0; --i) {
+            T scale = 0, h = 0;
+            for (int k = 0; k < i; ++k) scale += std::fabs(d[k]);
+            if (scale == T(0)) {
+                e[i] = d[i - 1];
+                for (int j = 0; j < i; ++j) { d[j] = V[i - 1][j]; V[i][j] = 0; V[j][i] = 0; }
+            }
+            else {
+                for (int k = 0; k < i; ++k) { d[k] /= scale; h += d[k] * d[k]; }
+                T f = d[i - 1], g = std::sqrt(h);
+                if (f > 0) g = -g;
+                e[i] = scale * g;
+                h -= f * g;
+                d[i - 1] = f - g;
+                for (int j = 0; j < i; ++j) e[j] = 0;
+                for (int j = 0; j < i; ++j) {
+                    f = d[j];
+                    V[j][i] = f;
+                    g = e[j] + V[j][j] * f;
+                    for (int k = j + 1; k <= i - 1; ++k) { g += V[k][j] * d[k]; e[k] += V[k][j] * f; }
+                    e[j] = g;
                 }
+                f = 0;
+                for (int j = 0; j < i; ++j) { e[j] /= h; f += e[j] * d[j]; }
+                const T hh = f / (h + h);
+                for (int j = 0; j < i; ++j) e[j] -= hh * d[j];
+                for (int j = 0; j < i; ++j) {
+                    f = d[j]; g = e[j];
+                    for (int k = j; k <= i - 1; ++k) V[k][j] -= (f * e[k] + g * d[k]);
+                    d[j] = V[i - 1][j];
+                    V[i][j] = 0;
+                }
+            }
+            d[i] = h;
+        }
+        for (int i = 0; i < N - 1; ++i) {
+            V[N - 1][i] = V[i][i];
+            V[i][i] = 1;
+            const T h = d[i + 1];
+            if (h != T(0)) {
+                for (int k = 0; k <= i; ++k) d[k] = V[k][i + 1] / h;
+                for (int j = 0; j <= i; ++j) {
+                    T g = 0;
+                    for (int k = 0; k <= i; ++k) g += V[k][i + 1] * V[k][j];
+                    for (int k = 0; k <= i; ++k) V[k][j] -= g * d[k];
+                }
+            }
+            for (int k = 0; k <= i; ++k) V[k][i + 1] = 0;
+        }
+        for (int j = 0; j < N; ++j) { d[j] = V[N - 1][j]; V[N - 1][j] = 0; }
+        V[N - 1][N - 1] = 1;
+        e[0] = 0;
+        // ---- implicit QL on the tridiagonal matrix
+        for (int i = 1; i < N; ++i) e[i - 1] = e[i];
+        e[N - 1] = 0;
+        T f = 0, tst1 = 0;
+        const T eps = std::numeric_limits<T>::epsilon();
+        for (int l = 0; l < N; ++l) {
+            tst1 = std::max(tst1, std::fabs(d[l]) + std::fabs(e[l]));
+            int m = l;
+            while (m < N) { if (std::fabs(e[m]) <= eps * tst1) break; ++m; }
+            if (m > l) {
+                int iter = 0;
+                do {
+                    ++iter;
+                    T g = d[l];
+                    T p = (d[l + 1] - g) / (2 * e[l]);
+                    T r = std::hypot(p, T(1));
+                    if (p < 0) r = -r;
+                    d[l] = e[l] / (p + r);
+                    d[l + 1] = e[l] * (p + r);
+                    const T dl1 = d[l + 1];
+                    T h = g - d[l];
+                    for (int i = l + 2; i < N; ++i) d[i] -= h;
+                    f += h;
+                    p = d[m];
+                    T c = 1, c2 = c, c3 = c, s = 0, s2 = 0;
+                    const T el1 = e[l + 1];
+                    for (int i = m - 1; i >= l; --i) {
+                        c3 = c2; c2 = c; s2 = s;
+                        g = c * e[i];
+                        h = c * p;
+                        r = std::hypot(p, e[i]);
+                        e[i + 1] = s * r;
+                        s = e[i] / r;
+                        c = p / r;
+                        p = c * d[i] - s * g;
+                        d[i + 1] = h + s * (c * g + s * d[i]);
+                        for (int k = 0; k < N; ++k) { h = V[k][i + 1]; V[k][i + 1] = s * V[k][i] + c * h; V[k][i] = c * V[k][i] - s * h; }
+                    }
+                    p = -s * s2 * c3 * el1 * e[l] / dl1;
+                    e[l] = s * p;
+                    d[l] = c * p;
+                } while (std::fabs(e[l]) > eps * tst1 && iter < 60);
+            }
+            d[l] += f;
+            e[l] = 0;
         }
         int idx[N];
         for (int i = 0; i < N; ++i) idx[i] = i;
-        std::sort(idx, idx + N, [&](int a, int b) { return A[a][a] < A[b][b]; });
-        for (int j = 0; j < N; ++j) { lam.d[j] = A[idx[j]][idx[j]]; for (int k = 0; k < N; ++k) vec(k, j) = V[k][idx[j]]; }
+        std::sort(idx, idx + N, [&](int a, int b) { return d[a] < d[b]; });
+        for (int j = 0; j < N; ++j) { lam.d[j] = d[idx[j]]; for (int k = 0; k < N; ++k) vec(k, j) = V[k][idx[j]]; }
     }
     const Matrix<T, N, 1>& eigenvalues() const { return lam; }
     const Matrix<T, N, N>& eigenvectors() const { return vec; }

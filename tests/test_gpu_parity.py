@@ -90,6 +90,48 @@ def test_barrier_energy_gradient_hessian(gpu_ctx, orc, cases):
             assert np.abs(val - oval).max() <= RTOL * np.abs(oval).max()
 
 
+def test_cuda_path_matches_reference_golden(gpu_ctx, cases):
+    """Directly against what the REFERENCE's own loops returned (tests/golden/ref_loops.npz, produced from FEM/IPC.h and
+    Grid/SPATIAL_HASH.h compiled from /root/reference; see tests/test_ref_loops.py), without the oracle in between."""
+    import hashlib
+    import os
+    import scipy.sparse as sp
+    from conftest import ROOT
+    G = np.load(os.path.join(ROOT, "tests", "golden", "ref_loops.npz"))
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    for name, m, d, dhats in cases:
+        gpu_ctx.set_surface_mesh(m)
+        for k, dh in enumerate(dhats):
+            n = gpu_ctx.constraint_set(dh * dh)
+            rows, info = gpu_ctx.get_constraints()
+            assert n == int(G["%s/cs%d/n" % (name, k)]), (name, dh)
+            assert sha(lexsorted(rows).astype(np.int32)) == str(G["%s/cs%d/sorted_sha" % (name, k)]), (name, dh)
+            dup = (rows[:, 0] < 0) & (rows[:, 3] < 0)
+            assert sha(rows[dup].astype(np.int32)) == str(G["%s/cs%d/merged_sha" % (name, k)]), (name, dh)
+            if n:
+                assert np.array_equal(info[0], G["%s/cs%d/info" % (name, k)])
+        dh = dhats[-1]
+        grows = G["%s/rows" % name]
+        gpu_ctx.set_constraints(grows)
+        E = gpu_ctx.barrier_energy(dh * dh, KAPPA)
+        g = gpu_ctx.barrier_gradient(dh * dh, KAPPA)
+        assert abs(E - float(G["%s/E" % name])) <= RTOL * abs(float(G["%s/E" % name]))
+        assert rel(g, G["%s/g" % name]) <= RTOL
+        N = 3 * m.nV
+        probe = np.random.default_rng(20260118).normal(size=N)
+        for spd in (0, 1):
+            ptr, col, val = gpu_ctx.barrier_hessian(dh * dh, KAPPA, project_spd=bool(spd))
+            H = sp.csr_matrix((val, col, ptr), shape=(N, N))
+            assert rel(H @ probe, G["%s/H%d_probe" % (name, spd)]) <= RTOL, (name, spd)
+            assert abs(np.sqrt((val ** 2).sum()) - float(G["%s/H%d_fro" % (name, spd)])) <= RTOL * float(G["%s/H%d_fro" % (name, spd)])
+            assert H.nnz == int(G["%s/H%d_nnz" % (name, spd)])
+        d2, mn = gpu_ctx.min_dist2(thickness=1e-4)
+        assert sha(d2) == str(G["%s/dist2_sha" % name]) and mn == float(G["%s/min_dist2" % name])
+        for (scale, xi, a0), ref_step in zip(((1.0, 0.0, 1.0), (0.3, 0.0, 1.0), (4.0, 0.0, 1.0), (1.0, 1e-4, 0.7)), G["%s/ccd" % name]):
+            a = gpu_ctx.ccd_step(d * scale, a0, xi)
+            assert a <= ref_step and abs(a - ref_step) <= 1e-6 * ref_step, (name, scale, xi, a, ref_step)
+
+
 def test_barrier_all_matches_separate_calls(gpu_ctx, cases):
     name, m, _d, dhats = cases[1]
     gpu_ctx.set_surface_mesh(m)

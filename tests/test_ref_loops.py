@@ -1,0 +1,110 @@
+"""The oracle against the REFERENCE's own contact loops.
+
+FEM/IPC.h and Grid/SPATIAL_HASH.h themselves -- not a restatement -- are compiled from /root/reference/Library into
+oracle/_ref/libidp_ref_ipc.so (oracle/ref_shim: std::vector stand-ins for the Cabana storages, the repo's Eigen subset, an
+inert pybind11). tests/golden/ref_loops.npz holds what the reference's six operators return on the small test meshes
+(made by tests/golden/make_golden_loops.py); it travels to machines without /root/reference. Where the library is present
+the comparison is also made live, including a Dirichlet mask and a thickness offset.
+
+Bars: constraint sets (sorted) and the merged PP/PE group in the reference's own order bit for bit; energy, per-row
+distances and the CCD step bit for bit (same expressions, same rounding); gradient and projected Hessian to 1e-12
+(summation order / eigen-solver differ)."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import ROOT, lexsorted, make_cases
+
+G = np.load(os.path.join(ROOT, "tests", "golden", "ref_loops.npz"))
+KAPPA = 1e5
+CCD_CONFIGS = ((1.0, 0.0, 1.0), (0.3, 0.0, 1.0), (4.0, 0.0, 1.0), (1.0, 1e-4, 0.7))
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def probe_vector(n):
+    return np.random.default_rng(20260118).normal(size=n)
+
+
+def omesh(orc, m):
+    return orc.mesh(m.X, m.X0, m.bnode, m.bedge, m.btri, m.dbc)
+
+
+@pytest.fixture(scope="module")
+def cases():
+    return make_cases()
+
+
+def test_oracle_constraint_sets_match_reference_golden(orc, cases):
+    for name, m, d, dhats in cases:
+        om = omesh(orc, m)
+        for k, dh in enumerate(dhats):
+            rows, info, _, _ = orc.constraint_set(om, dh * dh)
+            assert len(rows) == int(G["%s/cs%d/n" % (name, k)]), (name, dh)
+            assert sha(lexsorted(rows).astype(np.int32)) == str(G["%s/cs%d/sorted_sha" % (name, k)]), (name, dh)
+            dup = (rows[:, 0] < 0) & (rows[:, 3] < 0)
+            assert sha(rows[dup].astype(np.int32)) == str(G["%s/cs%d/merged_sha" % (name, k)]), (name, dh)
+            if len(info):
+                assert np.array_equal(info[0], G["%s/cs%d/info" % (name, k)])
+
+
+def test_oracle_barrier_min_dist_ccd_match_reference_golden(orc, cases):
+    for name, m, d, dhats in cases:
+        om = omesh(orc, m)
+        dh = dhats[-1]
+        rows = G["%s/rows" % name]
+        w = np.ones(len(rows))
+        _, E = orc.barrier(om, rows, w, dh * dh, KAPPA)
+        _, g = orc.barrier_gradient(om, rows, w, dh * dh, KAPPA)
+        assert E == float(G["%s/E" % name]), name                      # same row order, same serial accumulation (IPC.h:940)
+        assert np.abs(g - G["%s/g" % name]).max() <= 1e-12 * np.abs(G["%s/g" % name]).max()
+        N = 3 * m.nV
+        for spd in (0, 1):
+            ptr, col, val = orc.barrier_hessian(om, rows, w, dh * dh, KAPPA, project_spd=bool(spd))["csr"]
+            H = sp.csr_matrix((val, col, ptr), shape=(N, N))
+            ref = G["%s/H%d_probe" % (name, spd)]
+            assert np.abs(H @ probe_vector(N) - ref).max() <= 1e-12 * np.abs(ref).max(), (name, spd)
+            assert abs(np.sqrt((val ** 2).sum()) - float(G["%s/H%d_fro" % (name, spd)])) <= 1e-12 * float(G["%s/H%d_fro" % (name, spd)])
+            assert H.nnz == int(G["%s/H%d_nnz" % (name, spd)])        # Eigen setFromTriplets keeps explicit zeros, as does the oracle
+        d2, mn = orc.min_dist2(om, rows, 1e-4)
+        assert sha(d2) == str(G["%s/dist2_sha" % name]) and mn == float(G["%s/min_dist2" % name])
+        steps = np.array([orc.ccd(om, d * s, a0, xi)["step"] for s, xi, a0 in CCD_CONFIGS])
+        assert np.array_equal(steps, G["%s/ccd" % name]), (name, steps, G["%s/ccd" % name])
+
+
+def test_oracle_matches_reference_loops_live(orc, cases):
+    from oracle import ref_binding
+    if not ref_binding.ipc_available():
+        pytest.skip("oracle/_ref/libidp_ref_ipc.so not built (needs /root/reference at build time)")
+    ref = ref_binding.ReferenceIPC()
+    name, m, d, dhats = cases[1]
+    dbc = np.zeros(m.nV, np.uint8)
+    dbc[: m.nV // 3] = 1
+    m.dbc = dbc
+    try:
+        om = omesh(orc, m)
+        for thickness in (0.0, 2e-3):
+            rrows, rinfo = ref.constraint_set(m, dhats[-1] ** 2, thickness)
+            orows, oinfo, _, _ = orc.constraint_set(om, dhats[-1] ** 2, thickness)
+            assert len(rrows) == len(orows) > 0 and np.array_equal(lexsorted(rrows), lexsorted(orows))
+            dup = (rrows[:, 0] < 0) & (rrows[:, 3] < 0)
+            assert np.array_equal(rrows[dup], orows[(orows[:, 0] < 0) & (orows[:, 3] < 0)]) and np.array_equal(rinfo, oinfo)
+            E, g, (tr, tc, tv) = ref.barrier(m, orows, oinfo[:, 0], dhats[-1] ** 2, KAPPA, thickness)
+            _, oE = orc.barrier(om, orows, oinfo[:, 0], dhats[-1] ** 2, KAPPA, thickness)
+            _, og = orc.barrier_gradient(om, orows, oinfo[:, 0], dhats[-1] ** 2, KAPPA, thickness)
+            optr, ocol, oval = orc.barrier_hessian(om, orows, oinfo[:, 0], dhats[-1] ** 2, KAPPA, thickness)["csr"]
+            N = 3 * m.nV
+            A = sp.coo_matrix((tv, (tr, tc)), shape=(N, N)).tocsr()
+            B = sp.csr_matrix((oval, ocol, optr), shape=(N, N))
+            assert E == oE and np.abs(g - og).max() <= 1e-12 * np.abs(og).max() and abs(A - B).max() <= 1e-12 * abs(B).max()
+            rd, rmn = ref.min_dist2(m, orows, thickness)
+            od, omn = orc.min_dist2(om, orows, thickness)
+            assert np.array_equal(rd, od) and rmn == omn
+            assert ref.ccd(m, d, 1.0, thickness) == orc.ccd(om, d, 1.0, thickness)["step"]
+    finally:
+        m.dbc = np.zeros(m.nV, np.uint8)
