@@ -132,6 +132,41 @@ def test_cuda_path_matches_reference_golden(gpu_ctx, cases):
             assert a <= ref_step and abs(a - ref_step) <= 1e-6 * ref_step, (name, scale, xi, a, ref_step)
 
 
+@pytest.mark.parametrize("name", ["bunny3K", "hand"])
+def test_cuda_path_matches_reference_on_paper_meshes(gpu_ctx, name):
+    """Real geometry of the paper examples against what the reference's own loops returned (tests/golden/
+    ref_paper_meshes.npz; configuration and generator: tests/golden/make_golden_paper.py)."""
+    import hashlib
+    import os
+    import scipy.sparse as sp
+    from conftest import ROOT
+    from test_ref_loops import paper_case
+    P = np.load(os.path.join(ROOT, "tests", "golden", "ref_paper_meshes.npz"))
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    m, d, e = paper_case(P, name)
+    gpu_ctx.set_surface_mesh(m)
+    for k, f in enumerate((0.6, 1.2)):
+        dh = f * e
+        n = gpu_ctx.constraint_set(dh * dh)
+        rows, info = gpu_ctx.get_constraints()
+        assert n == int(P["%s/cs%d/n" % (name, k)])
+        assert sha(lexsorted(rows).astype(np.int32)) == str(P["%s/cs%d/sorted_sha" % (name, k)])
+        dup = (rows[:, 0] < 0) & (rows[:, 3] < 0)
+        assert sha(rows[dup].astype(np.int32)) == str(P["%s/cs%d/merged_sha" % (name, k)])
+    E = gpu_ctx.barrier_energy(dh * dh, KAPPA)
+    g = gpu_ctx.barrier_gradient(dh * dh, KAPPA)
+    ptr, col, val = gpu_ctx.barrier_hessian(dh * dh, KAPPA, project_spd=True)
+    assert abs(E - float(P[name + "/E"])) <= RTOL * abs(float(P[name + "/E"])) and rel(g, P[name + "/g"]) <= RTOL
+    N = 3 * m.nV
+    probe = np.random.default_rng(20260118).normal(size=N)
+    assert rel(sp.csr_matrix((val, col, ptr), shape=(N, N)) @ probe, P[name + "/H_probe"]) <= RTOL
+    _, mn = gpu_ctx.min_dist2()
+    assert mn == float(P[name + "/min_dist2"])
+    for (scale, a0), ref_step in zip(((1.0, 1.0), (0.25, 0.5)), P[name + "/ccd"]):
+        a = gpu_ctx.ccd_step(d * scale, a0, 0.0)
+        assert a <= ref_step and abs(a - ref_step) <= 1e-6 * ref_step, (name, a, ref_step)
+
+
 def test_barrier_all_matches_separate_calls(gpu_ctx, cases):
     name, m, _d, dhats = cases[1]
     gpu_ctx.set_surface_mesh(m)

@@ -108,3 +108,40 @@ def test_oracle_matches_reference_loops_live(orc, cases):
             assert ref.ccd(m, d, 1.0, thickness) == orc.ccd(om, d, 1.0, thickness)["step"]
     finally:
         m.dbc = np.zeros(m.nV, np.uint8)
+
+
+# ---- real geometry of the paper examples: bunny3K and hand in a normal-flow-like configuration ----------
+def paper_case(P, name):
+    from idp_b200 import meshgen
+    V, F, e = P[name + "/V"], P[name + "/F"], float(P[name + "/edge"])
+    m0 = meshgen.SurfaceMesh(V, F)
+    n = m0.vertex_normals()
+    m = meshgen.SurfaceMesh(V - 0.2 * e * n, F, X0=V)
+    return m, np.ascontiguousarray(-2.0 * e * n), e
+
+
+@pytest.mark.parametrize("name", ["bunny3K", "hand"])
+def test_oracle_matches_reference_on_paper_meshes(orc, name):
+    P = np.load(os.path.join(ROOT, "tests", "golden", "ref_paper_meshes.npz"))
+    m, d, e = paper_case(P, name)
+    om = omesh(orc, m)
+    for k, f in enumerate((0.6, 1.2)):
+        dh = f * e
+        rows, info, _, _ = orc.constraint_set(om, dh * dh)
+        assert len(rows) == int(P["%s/cs%d/n" % (name, k)])
+        assert sha(lexsorted(rows).astype(np.int32)) == str(P["%s/cs%d/sorted_sha" % (name, k)])
+        dup = (rows[:, 0] < 0) & (rows[:, 3] < 0)
+        assert sha(rows[dup].astype(np.int32)) == str(P["%s/cs%d/merged_sha" % (name, k)])
+    # rows inside the PT / EE groups are in a different (sorted) order here, so sums agree to rounding, not bit for bit
+    _, E = orc.barrier(om, rows, info[:, 0], dh * dh, KAPPA)
+    _, g = orc.barrier_gradient(om, rows, info[:, 0], dh * dh, KAPPA)
+    assert abs(E - float(P[name + "/E"])) <= 1e-12 * abs(float(P[name + "/E"]))
+    assert np.abs(g - P[name + "/g"]).max() <= 1e-12 * np.abs(P[name + "/g"]).max()
+    N = 3 * m.nV
+    ptr, col, val = orc.barrier_hessian(om, rows, info[:, 0], dh * dh, KAPPA, project_spd=True)["csr"]
+    ref = P[name + "/H_probe"]
+    assert np.abs(sp.csr_matrix((val, col, ptr), shape=(N, N)) @ probe_vector(N) - ref).max() <= 1e-11 * np.abs(ref).max()
+    d2, mn = orc.min_dist2(om, rows)
+    assert mn == float(P[name + "/min_dist2"])
+    steps = np.array([orc.ccd(om, d, 1.0, 0.0)["step"], orc.ccd(om, 0.25 * d, 0.5, 0.0)["step"]])
+    assert np.array_equal(steps, P[name + "/ccd"]), (steps, P[name + "/ccd"])
