@@ -300,3 +300,30 @@ def test_b2_dropin_operators(lib_built, orc, cases):
     assert alpha.value <= oc["step"] and abs(alpha.value - oc["step"]) <= 1e-6 * oc["step"]
     od, omn = orc.min_dist2(om, rows, thickness)
     assert np.array_equal(dist2[: n.value], od) and mn.value == omn
+
+
+def test_b2_side_by_side_with_reference_types(lib_built, cases):
+    """tests/host_shim/b2_side_by_side.cpp: the reference's own FEM/IPC.h operators and JGSL::B200::Compute_* called with
+    the SAME argument objects (reference VECTOR / storage stand-ins / Eigen::Triplet) in one translation unit."""
+    import ctypes as C
+    import os
+    from conftest import ROOT
+    so = os.path.join(ROOT, "tests", "host_shim", "libb2_side_by_side.so")
+    if not os.path.exists(so):
+        pytest.skip("libb2_side_by_side.so is built where /root/reference exists (make -C tests/host_shim)")
+    drv = C.CDLL(so)
+    drv.b2_side_by_side.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                    C.c_double, C.c_double, C.c_double, C.c_void_p]
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    for name, m, d, dhats in cases[:2]:
+        dh = dhats[-1]
+        X = np.ascontiguousarray(m.X); X0 = np.ascontiguousarray(m.X0); dd = np.ascontiguousarray(d)
+        rep = np.zeros(16)
+        assert drv.b2_side_by_side(m.nV, P(X), P(X0), len(m.bnode), P(m.bnode), len(m.bedge), P(m.bedge), len(m.btri), P(m.btri), P(dd),
+                                   dh * dh, KAPPA, 0.0, P(rep)) == 0
+        n_ref, n_new, same, e_ref, e_new, gmax, gdiff, hmax, hdiff, pattern, nnz, a_ref, a_new, m_ref, m_new, deq = rep
+        assert n_ref == n_new > 0 and same == 1.0, (name, n_ref, n_new)
+        assert abs(e_new - e_ref) <= RTOL * abs(e_ref - 0.25)          # E is accumulated onto the caller's value (0.25)
+        assert gdiff <= RTOL * gmax and hdiff <= RTOL * hmax and pattern == 1.0 and nnz > 0
+        assert a_new <= a_ref and abs(a_new - a_ref) <= 1e-6 * a_ref
+        assert m_new == m_ref and deq == 1.0
