@@ -12,6 +12,7 @@
 // Reference semantics: FEM/IPC.h:801-938 (E), 1012-1254 (g), 1390-1729 (H); tolerance 1e-10 relative.
 #pragma once
 #include "pair_deriv.cuh"
+#include <string.h>
 
 namespace idp {
 
@@ -94,6 +95,26 @@ struct QlStore {
     static IDP_HD double e(const double* colp) { return colp[(N * N + N) * STRIDE]; }
     static IDP_HD void eset(double* colp, double x) { colp[(N * N + N) * STRIDE] = x; }
 };
+IDP_HD long long pun_double_bits(double x)
+{
+#if defined(__CUDA_ARCH__)
+    return __double_as_longlong(x);
+#else
+    long long b;
+    memcpy(&b, &x, 8);
+    return b;
+#endif
+}
+IDP_HD double pun_bits_double(long long b)
+{
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double(b);
+#else
+    double x;
+    memcpy(&x, &b, 8);
+    return x;
+#endif
+}
 IDP_HD int first_set_bit(unsigned x) // 1-based, 0 when x == 0
 {
 #if defined(__CUDA_ARCH__)
@@ -109,6 +130,26 @@ static QlStats g_ql_stats = {0, 0, 0, 0, {0}, 0};
 template <int N, class ST>
 IDP_HD bool make_pd_ql(double* a, ST& S) // false: the QL iteration cap was reached (never observed; reported, not ignored)
 {
+    // ---- 0. exact power-of-two scaling to [0.5, 1): the squares formed below neither underflow nor overflow whatever the
+    // magnitude of the row (mollified rows near e = 0 are tiny, rows at contact are huge); the result is scaled back
+    double am[4] = {0, 0, 0, 0}; // four independent chains: a single fmax chain over 45 entries is pure latency
+#pragma unroll
+    for (int i = 0; i < N * (N + 1) / 2; ++i) am[i & 3] = fmax(am[i & 3], fabs(a[i]));
+    const double amax = fmax(fmax(am[0], am[1]), fmax(am[2], am[3]));
+    if (!(amax >= 2.3e-308)) { // zero (or denormal) matrix: its projection is zero
+#pragma unroll
+        for (int i = 0; i < N * (N + 1) / 2; ++i) a[i] = 0.0;
+        return true;
+    }
+    long long ebits = (pun_double_bits(amax) >> 52) & 0x7ffLL;                 // biased exponent of the largest entry
+    if (ebits > 2044) ebits = 2044;                                            // (keeps both scale factors finite)
+    const double fscale = pun_bits_double((2045LL - ebits) << 52);            // 2^(1022 - e): amax * fscale in [0.5, 1)
+    const double funscale = pun_bits_double((ebits + 1LL) << 52);             // its inverse 2^(e - 1022)
+    const double unscale = (ebits < 723 || ebits > 1323) ? funscale : 1.0;
+    if (ebits < 723 || ebits > 1323) { // |entries| outside [2^-300, 2^300]: only then can a square leave the double range
+#pragma unroll
+        for (int i = 0; i < N * (N + 1) / 2; ++i) a[i] *= fscale;
+    }
     // ---- 1. Householder: for column k annihilate a(k+2.., k); v is stored over a(k, k+1..), beta kept
     double beta[N - 2];
     double emax = 0;
@@ -270,7 +311,7 @@ IDP_HD bool make_pd_ql(double* a, ST& S) // false: the QL iteration cap was reac
         ST::eset(cl, g);
     }
     const bool converged = l >= N - 1;
-    // ---- 4. V max(lambda, 0) V^T
+    // ---- 4. V max(lambda, 0) V^T (eigenvalues scaled back by the exact power of two)
     double lam[N];
 #ifdef IDP_QL_STATS
     g_ql_stats.negcount = 0;
@@ -278,7 +319,7 @@ IDP_HD bool make_pd_ql(double* a, ST& S) // false: the QL iteration cap was reac
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         const double x = ST::d(S.col(i));
-        lam[i] = x > 0 ? x : 0.0;
+        lam[i] = x > 0 ? x * unscale : 0.0;
 #ifdef IDP_QL_STATS
         if (x < 0) ++g_ql_stats.negcount;
 #endif

@@ -36,6 +36,28 @@ int hs_accd(int kind, const double* x, const double* d, double eta, double xi, d
     *iters = it;
     return r;
 }
+// make_pd_ql on a dense symmetric N x N matrix (row-major in / out); N = 6 or 9. Returns 0 when the QL iteration converged.
+int hs_make_pd(int n, const double* A, double* out)
+{
+    double work[QlStore<9, 1>::WORDS];
+    bool ok = false;
+    if (n == 9) {
+        double m[45];
+        for (int i = 0; i < 9; ++i) for (int j = i; j < 9; ++j) m[SI<9>(i, j)] = A[i * 9 + j];
+        QlStore<9, 1> S{work};
+        ok = make_pd_ql<9>(m, S);
+        for (int i = 0; i < 9; ++i) for (int j = 0; j < 9; ++j) out[i * 9 + j] = m[SI<9>(i, j)];
+    }
+    else if (n == 6) {
+        double m[21];
+        for (int i = 0; i < 6; ++i) for (int j = i; j < 6; ++j) m[SI<6>(i, j)] = A[i * 6 + j];
+        QlStore<6, 1> S{work};
+        ok = make_pd_ql<6>(m, S);
+        for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) out[i * 6 + j] = m[SI<6>(i, j)];
+    }
+    else return -1;
+    return ok ? 0 : 1;
+}
 #ifdef IDP_QL_STATS
 // development aid (scripts/ql_stats.py): chase lengths of the QL trips of the last 9x9 projection
 int hs_ql_negcount() { return g_ql_stats.negcount; }

@@ -57,6 +57,7 @@ def host_shim():
     hs.hs_dist2_unclassified.restype = C.c_double
     hs.hs_row_EgH.argtypes = [C.c_void_p] * 3 + [C.c_double] * 4 + [C.c_int, C.c_int] + [C.c_void_p] * 5
     hs.hs_accd.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
+    hs.hs_make_pd.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
     return hs
 
 
@@ -117,6 +118,48 @@ def test_device_row_math_matches_oracle_on_host(orc, host_shim, lowrank):
                 assert np.abs(g2[:n] - g).max() <= 1e-10 * np.abs(g).max()
                 assert np.linalg.norm(H2[:n * n].reshape(n, n) - H) <= 1e-10 * np.linalg.norm(H)
         assert len(seen) >= 4, seen
+
+
+@pytest.mark.parametrize("n", [6, 9])
+def test_device_psd_projection_on_hard_spectra(host_shim, n):
+    """make_pd_ql (psd_lowrank.cuh: Householder + pipelined implicit QL, compiled for the host) against numpy's eigh
+    projection on spectra the mesh tests do not guarantee: repeated and clustered eigenvalues, exact zeros, rank one,
+    already block-diagonal / diagonal input, 1e16 dynamic range, definite matrices, tiny and huge scales."""
+    rng = np.random.default_rng(12)
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+
+    def check(A):
+        A = 0.5 * (A + A.T)
+        out = np.zeros((n, n))
+        assert host_shim.hs_make_pd(n, P(np.ascontiguousarray(A)), P(out)) == 0
+        lam, V = np.linalg.eigh(A)
+        ref = (V * np.maximum(lam, 0.0)) @ V.T
+        scale = max(np.abs(lam).max(), 1e-300)
+        assert np.abs(out - ref).max() <= 1e-12 * scale, (np.abs(out - ref).max() / scale, lam)
+        assert np.abs(out - out.T).max() == 0.0
+
+    def with_spectrum(lam):
+        Q, _ = np.linalg.qr(rng.normal(size=(n, n)))
+        return (Q * np.asarray(lam, float)) @ Q.T
+
+    for _ in range(300):
+        check(rng.normal(size=(n, n)))
+    check(np.zeros((n, n)))
+    check(np.eye(n)); check(-np.eye(n))
+    check(np.diag(np.arange(n) - n / 2.0))                                  # already diagonal
+    v = rng.normal(size=n); check(np.outer(v, v)); check(-np.outer(v, v))    # rank one
+    for _ in range(60):
+        lam = rng.normal(size=n)
+        lam[1] = lam[0]; lam[3] = lam[2] * (1 + 1e-13)                       # exact and near-exact pairs
+        check(with_spectrum(lam))
+        lam = np.concatenate([[-1.0] * (n // 2), [2.0] * (n - n // 2)])      # two clusters of multiplicity n/2
+        check(with_spectrum(lam))
+        lam = np.concatenate([[1e8], rng.normal(size=n - 3) * 1e-8, [0.0, -1e-8]])  # 1e16 range, exact zero
+        check(with_spectrum(lam))
+        check(with_spectrum(np.abs(rng.normal(size=n))))                     # definite: returned unchanged up to rounding
+        check(with_spectrum(rng.normal(size=n)) * 1e-150); check(with_spectrum(rng.normal(size=n)) * 1e120)
+    B = np.zeros((n, n)); B[:3, :3] = with_spectrum(rng.normal(size=n))[:3, :3]; B[3:, 3:] = with_spectrum(rng.normal(size=n))[3:, 3:]
+    check(B)                                                                 # block diagonal: interior split from the start
 
 
 def test_surface_primitive_ordering_contract():
