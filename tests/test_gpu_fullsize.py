@@ -65,6 +65,17 @@ def test_config3_icospheres_dhat_sweep_full_parity(gpu_ctx, orc):
             assert np.array_equal(ptr, optr) and np.array_equal(col, ocol)
             assert rel(val, oval) <= RTOL and np.abs(val - oval).max() <= RTOL * np.abs(oval).max()
     assert counts[0] == 0 and counts == sorted(counts) and counts[-1] > 1000000  # below the gap nothing is in contact
+    # where the reference's own loops were compiled (oracle/_ref/libidp_ref_ipc.so travels with the repository), the same
+    # full-size comparison is made against them directly
+    from oracle import ref_binding
+    ref = ref_binding.ReferenceIPC() if ref_binding.ipc_available() else None
+    if ref is not None:
+        dh = 5e-3
+        n = gpu_ctx.constraint_set(dh * dh)
+        rows, _ = gpu_ctx.get_constraints()
+        rrows, _ = ref.constraint_set(m, dh * dh, cap=2000000)
+        assert n == len(rrows) and np.array_equal(lexsorted(rows), lexsorted(rrows))
+        assert np.array_equal(rows[(rows[:, 0] < 0) & (rows[:, 3] < 0)], rrows[(rrows[:, 0] < 0) & (rrows[:, 3] < 0)])
     for a0, scale, xi in ((1.0, 1.0, 0.0), (0.5, 2.0, 1e-4)):
         a = gpu_ctx.ccd_step(d * scale, a0, xi)
         o = orc.ccd(om, d * scale, a0, xi, want_cand=True)
@@ -72,6 +83,9 @@ def test_config3_icospheres_dhat_sweep_full_parity(gpu_ctx, orc):
         if o["step_after_clamp"] == a0:
             assert np.array_equal(gpu_ctx.get_candidates(2), o["cand_pt"]) and np.array_equal(gpu_ctx.get_candidates(3), o["cand_ee"])
             assert a == o["step"]
+        if ref is not None:
+            ra = ref.ccd(m, d * scale, a0, xi)
+            assert a <= ra and abs(a - ra) <= 1e-6 * ra, (a, ra)
 
 
 def _closest_pairs_never_touch(m, d, alpha, cpt, cee, n_check=200000, k_samples=48, n_pool=12000000):
