@@ -1011,7 +1011,8 @@ int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
     int qb, qe;
     // duplicate (PP / PE) rows are merged by sorting a packed (nV-1-p, k1, k2+1) key when it fits 64 bits
     const int vbits = bits_for((unsigned long long)c->nV);
-    const int dupBits = (3 * vbits <= 64) ? vbits : 0;
+    // IDP_FORCE_ROW_MERGE=1 selects the 16-byte row merge sort that meshes with more than 2^21 vertices need (tests)
+    const int dupBits = (3 * vbits <= 64 && !getenv("IDP_FORCE_ROW_MERGE")) ? vbits : 0;
     {
         StageTimer tm(c, IDP_STAGE_CCS_PT);
         EMax emax; int nLarge = 0;
@@ -1102,6 +1103,8 @@ int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
         if (!dupBits) {
             IDP_TRY(comm_allgatherv(c, c->rowsG.p, nA, sizeof(Row4), (void**)&c->rows.p, &c->rows.cap, 0, &nAg));
             IDP_TRY(comm_allgatherv(c, c->rowsG.p + nA, nB, sizeof(Row4), (void**)&c->rows.p, &c->rows.cap, nAg, &nBg));
+            // the unmerged PP / PE rows of every rank are gathered too (rowsG is free again) and merged on every rank
+            IDP_TRY(comm_allgatherv(c, c->rowsD.p, nD, sizeof(Row4), (void**)&c->rowsG.p, &c->rowsG.cap, 0, &nDg));
         }
         if (dupBits) {
             // LOCAL-ROWS mode: every rank keeps (and later evaluates) the rows it produced -- its own direct rows and the

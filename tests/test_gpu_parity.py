@@ -327,3 +327,23 @@ def test_b2_side_by_side_with_reference_types(lib_built, cases):
         assert gdiff <= RTOL * gmax and hdiff <= RTOL * hmax and pattern == 1.0 and nnz > 0
         assert a_new <= a_ref and abs(a_new - a_ref) <= 1e-6 * a_ref
         assert m_new == m_ref and deq == 1.0
+
+
+def test_row_merge_fallback_for_large_vertex_counts(lib_built, orc, cases, monkeypatch):
+    """Meshes with more than 2^21 vertices cannot pack a PP/PE row into one 64-bit key; the 16-byte row merge sort they fall
+    back to is forced here on a small mesh (IDP_FORCE_ROW_MERGE) and must give the identical constraint set."""
+    from idp_b200 import ContactContext
+    monkeypatch.setenv("IDP_FORCE_ROW_MERGE", "1")
+    ctx = ContactContext(0)
+    try:
+        for name, m, d, dhats in cases[:2]:
+            ctx.set_surface_mesh(m)
+            om = omesh(orc, m)
+            n = ctx.constraint_set(dhats[-1] ** 2)
+            rows, _ = ctx.get_constraints()
+            orows, _, _, _ = orc.constraint_set(om, dhats[-1] ** 2)
+            assert n == len(orows) and np.array_equal(lexsorted(rows), lexsorted(orows)), name
+            dup = (rows[:, 0] < 0) & (rows[:, 3] < 0)
+            assert np.array_equal(rows[dup], orows[(orows[:, 0] < 0) & (orows[:, 3] < 0)]), name
+    finally:
+        ctx.close()
