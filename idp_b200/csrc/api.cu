@@ -161,7 +161,7 @@ int idp_get_constraints(idp_ctx* c, int* rows4, double* info2)
 {
     if (!c) return IDP_ERR_INVALID;
     IDP_CK(c, cudaSetDevice(c->device));
-    if (c->rowsLocal) {
+    if (c->rowsLocal && c->nccl_comm) {
         // sharded LOCAL-ROWS mode: collective -- every rank must call it; the global list (order of the unsharded path) is
         // gathered on the device and copied out. Weights are all one here (set by idp_constraint_set).
         const long n = c->nRowsGlobal;

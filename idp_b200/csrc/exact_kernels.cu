@@ -1204,6 +1204,10 @@ int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
             c->rowsLocal = true;
         }
         c->nRows = nA + nB + nU;
+        if (c->nranks > 1 && !sharded) { // idp_set_shard without a communicator: the rows of this shard only, all evaluated here
+            c->rowsLocal = true;
+            c->nRowsGlobal = c->nRows;
+        }
         IDP_CK(c, c->weights.reserve(std::max<long>(c->nRows, 1)));
         if (nU && dupBits) IDP_LAUNCH(c, k_emit_merged_keys, blocks_for(nU, 256), 256, 0, c->keyA.p, c->runCounts.p, nU, dupBits, (long long)c->nV, c->rows.p + nA + nB);
         else if (nU) IDP_LAUNCH(c, k_emit_merged, blocks_for(nU, 256), 256, 0, c->rowsD2.p, c->runCounts.p, nU, c->rows.p + nA + nB);
@@ -1283,7 +1287,7 @@ int min_dist2(idp_ctx* c, double thickness, double* host_dist2, double* min_out)
     IDP_CK(c, cudaGetLastError());
     if (slice || (sharded && c->rowsLocal)) IDP_TRY(comm_allreduce_min_u64(c, d, 1));
     IDP_CK(c, cudaMemcpyAsync(&init, d, sizeof(init), cudaMemcpyDeviceToHost, c->stream));
-    if (host_dist2 && c->rowsLocal) { // per-row vector in the order of the global list (collective)
+    if (host_dist2 && c->rowsLocal && sharded) { // per-row vector in the order of the global list (collective)
         IDP_CK(c, c->dist2Global.reserve(std::max<long>(c->nRowsGlobal, 1)));
         IDP_TRY(comm_gather_groups(c, c->rowDist2.p, sizeof(double), c->dist2Global.p));
         IDP_CK(c, cudaMemcpyAsync(host_dist2, c->dist2Global.p, c->nRowsGlobal * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
