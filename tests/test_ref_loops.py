@@ -145,3 +145,32 @@ def test_oracle_matches_reference_on_paper_meshes(orc, name):
     assert mn == float(P[name + "/min_dist2"])
     steps = np.array([orc.ccd(om, d, 1.0, 0.0)["step"], orc.ccd(om, 0.25 * d, 0.5, 0.0)["step"]])
     assert np.array_equal(steps, P[name + "/ccd"]), (steps, P[name + "/ccd"])
+
+
+def test_oracle_matches_reference_loops_on_bench_geometry(orc):
+    """A crop of the bench sheets (same spacing, waves and dHat as BASELINE configs[3]): the regime where 98 % of the
+    four-vertex rows are mollified PE / PP rows of parallel in-sheet edges. Live only (needs oracle/_ref)."""
+    from idp_b200 import meshgen
+    from oracle import ref_binding
+    if not ref_binding.ipc_available():
+        pytest.skip("oracle/_ref/libidp_ref_ipc.so not built (needs /root/reference at build time)")
+    ref = ref_binding.ReferenceIPC()
+    m, d = meshgen.sheet_stack(n_sheets=8, nx=24, ny=24, h=4e-3, A=1.5e-3, extent=(0.048, 0.048))
+    dh = 2e-3
+    om = omesh(orc, m)
+    rrows, rinfo = ref.constraint_set(m, dh * dh)
+    orows, oinfo, _, _ = orc.constraint_set(om, dh * dh)
+    assert len(rrows) == len(orows) > 20000 and np.array_equal(lexsorted(rrows), lexsorted(orows))
+    moll = (orows[:, 0] >= 0) & ((orows[:, 2] < 0) | (orows[:, 3] < 0))
+    assert moll.sum() > 0.3 * len(orows)
+    dup = (rrows[:, 0] < 0) & (rrows[:, 3] < 0)
+    assert np.array_equal(rrows[dup], orows[(orows[:, 0] < 0) & (orows[:, 3] < 0)])
+    E, g, (tr, tc, tv) = ref.barrier(m, orows, oinfo[:, 0], dh * dh, KAPPA)
+    _, oE = orc.barrier(om, orows, oinfo[:, 0], dh * dh, KAPPA)
+    _, og = orc.barrier_gradient(om, orows, oinfo[:, 0], dh * dh, KAPPA)
+    optr, ocol, oval = orc.barrier_hessian(om, orows, oinfo[:, 0], dh * dh, KAPPA)["csr"]
+    N = 3 * m.nV
+    A = sp.coo_matrix((tv, (tr, tc)), shape=(N, N)).tocsr()
+    B = sp.csr_matrix((oval, ocol, optr), shape=(N, N))
+    assert E == oE and np.abs(g - og).max() <= 1e-12 * np.abs(og).max() and abs(A - B).max() <= 1e-12 * abs(B).max()
+    assert ref.ccd(m, d, 1.0, 0.0) == orc.ccd(om, d, 1.0, 0.0)["step"]
