@@ -24,6 +24,7 @@ STAGES = ["Compute_Constraint_Set_Build_Hash", "Compute_Constraint_Set_PT", "Com
 # every symbol include/idp_contact.h declares
 EXPORTS = ["idp_create", "idp_destroy", "idp_last_error", "idp_set_stream", "idp_set_mesh", "idp_declare_unsupported",
            "idp_set_positions", "idp_set_rest_positions", "idp_constraint_set", "idp_get_constraints",
+           "idp_gather_constraints", "idp_comm_init_local", "idp_comm_abort",
            "idp_set_constraints", "idp_get_candidates", "idp_barrier_energy", "idp_barrier_gradient",
            "idp_barrier_hessian", "idp_barrier_all", "idp_get_hessian_csr", "idp_hessian_csr_device",
            "idp_gradient_device", "idp_ccd_step", "idp_set_search_direction", "idp_ccd_step_resident", "idp_min_dist2", "idp_comm_unique_id", "idp_comm_init",
@@ -54,6 +55,9 @@ def load_library(path=LIB_PATH):
     L.idp_set_rest_positions.argtypes = [vp, vp, i]
     L.idp_constraint_set.argtypes = [vp, d, d, C.POINTER(i)]
     L.idp_get_constraints.argtypes = [vp, vp, vp]
+    L.idp_gather_constraints.argtypes = [vp, vp, vp, vp]
+    L.idp_comm_init_local.argtypes = [C.POINTER(vp), i]
+    L.idp_comm_abort.argtypes = [vp]
     L.idp_set_constraints.argtypes = [vp, i, vp, vp]
     L.idp_get_candidates.argtypes = [vp, i, C.POINTER(l), vp]
     L.idp_barrier_energy.argtypes = [vp, d, d, d, C.POINTER(d)]
@@ -152,11 +156,21 @@ class ContactContext:
         return n.value
 
     def get_constraints(self):
-        n = self.L.idp_last_count(self.h, 0)
+        """The rows this context holds (sharded: this rank's rows only)."""
+        n = self.L.idp_last_count(self.h, 9)
         rows = np.empty((n, 4), np.int32)
         info = np.empty((n, 2), np.float64)
         self._ck(self.L.idp_get_constraints(self.h, _p(rows), _p(info)))
         return rows, info
+
+    def gather_constraints(self, want_dist2=False):
+        """The global list in the order of the unsharded path (sharded: a collective)."""
+        n = self.L.idp_last_count(self.h, 0)
+        rows = np.empty((n, 4), np.int32)
+        info = np.empty((n, 2), np.float64)
+        d = np.empty(n, np.float64) if want_dist2 else None
+        self._ck(self.L.idp_gather_constraints(self.h, _p(rows), _p(info), _p(d)))
+        return (rows, info, d) if want_dist2 else (rows, info)
 
     def set_constraints(self, rows, info=None):
         rows = np.ascontiguousarray(rows, np.int32).reshape(-1, 4)
@@ -218,7 +232,7 @@ class ContactContext:
         return a.value
 
     def min_dist2(self, thickness=0.0, want_all=True):
-        n = self.L.idp_last_count(self.h, 0)
+        n = self.L.idp_last_count(self.h, 9)
         d = np.empty(n, np.float64) if want_all else None
         m = C.c_double(np.nan)
         self._ck(self.L.idp_min_dist2(self.h, thickness, _p(d), C.byref(m)))
@@ -227,6 +241,17 @@ class ContactContext:
     # ---- sharding / instrumentation ----
     def set_shard(self, rank, nranks):
         self._ck(self.L.idp_set_shard(self.h, rank, nranks))
+
+    @staticmethod
+    def comm_init_local(ctxs):
+        """Make ctxs[r] rank r of an in-process group (each context must then be driven by its own thread)."""
+        arr = (C.c_void_p * len(ctxs))(*[c.h for c in ctxs])
+        st = ctxs[0].L.idp_comm_init_local(arr, len(ctxs))
+        if st != 0:
+            raise IdpError(st, ctxs[0].L.idp_last_error(ctxs[0].h).decode())
+
+    def comm_abort(self):
+        self.L.idp_comm_abort(self.h)
 
     def comm_init(self, rank, nranks, uid_bytes):
         buf = C.create_string_buffer(bytes(uid_bytes), 128)

@@ -31,8 +31,6 @@ static int host_stage(idp_ctx* c, size_t bytes, void** out)
 }
 
 namespace idp {
-int comm_allreduce_sum(idp_ctx* c, double* dev, long n);
-int comm_allreduce_min(idp_ctx* c, double* dev, long n);
 void comm_destroy(idp_ctx* c);
 } // namespace idp
 
@@ -157,43 +155,67 @@ int idp_constraint_set(idp_ctx* c, double dhat2, double thickness, int* n_rows)
     return IDP_OK;
 }
 
+// fills info2 = (weight, dHat2) for n rows whose weights live at dW (or are all one)
+static int fill_info(idp_ctx* c, long n, const double* dW, bool allOne, double* info2)
+{
+    const double dh2 = c->cs_dhat2;
+    if (allOne) { // set by idp_constraint_set (OIPC: weight 1, IPC.h:656-660): nothing to copy back
+        host_parallel(n, [=](long b, long e) { for (long i = b; i < e; ++i) { info2[2 * i] = 1.0; info2[2 * i + 1] = dh2; } });
+        return IDP_OK;
+    }
+    double* w = nullptr;
+    IDP_TRY(host_stage(c, (size_t)n * sizeof(double), (void**)&w));
+    IDP_CK(c, cudaMemcpyAsync(w, dW, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    IDP_CK(c, cudaStreamSynchronize(c->stream));
+    host_parallel(n, [=](long b, long e) { for (long i = b; i < e; ++i) { info2[2 * i] = w[i]; info2[2 * i + 1] = dh2; } });
+    return IDP_OK;
+}
+
 int idp_get_constraints(idp_ctx* c, int* rows4, double* info2)
 {
     if (!c) return IDP_ERR_INVALID;
     IDP_CK(c, cudaSetDevice(c->device));
-    if (c->rowsLocal && c->nccl_comm) {
-        // sharded LOCAL-ROWS mode: collective -- every rank must call it; the global list (order of the unsharded path) is
-        // gathered on the device and copied out. Weights are all one here (set by idp_constraint_set).
-        const long n = c->nRowsGlobal;
-        if (rows4 && n) {
-            IDP_CK(c, c->rowsGlobal.reserve(n));
-            IDP_TRY(comm_gather_groups(c, c->rows.p, sizeof(Row4), c->rowsGlobal.p));
-            IDP_CK(c, cudaMemcpyAsync(rows4, c->rowsGlobal.p, n * sizeof(Row4), cudaMemcpyDeviceToHost, c->stream));
-            IDP_CK(c, cudaStreamSynchronize(c->stream));
-        }
-        if (info2 && n) {
-            const double dh2 = c->cs_dhat2;
-            host_parallel(n, [=](long b, long e) { for (long i = b; i < e; ++i) { info2[2 * i] = 1.0; info2[2 * i + 1] = dh2; } });
-        }
-        return IDP_OK;
-    }
+    // sharded: the rows THIS rank holds (idp_last_count(ctx, 9) of them) -- not a collective; the global list is
+    // idp_gather_constraints
     if (rows4 && c->nRows) {
         IDP_CK(c, cudaMemcpyAsync(rows4, c->rows.p, c->nRows * sizeof(Row4), cudaMemcpyDeviceToHost, c->stream));
         IDP_CK(c, cudaStreamSynchronize(c->stream));
     }
-    if (info2 && c->nRows) {
-        const long n = c->nRows;
-        const double dh2 = c->cs_dhat2;
-        if (c->weights_all_one) { // set by idp_constraint_set (OIPC: weight 1, IPC.h:656-660): nothing to copy back
-            host_parallel(n, [=](long b, long e) { for (long i = b; i < e; ++i) { info2[2 * i] = 1.0; info2[2 * i + 1] = dh2; } });
-        }
-        else {
-            double* w = nullptr;
-            IDP_TRY(host_stage(c, (size_t)n * sizeof(double), (void**)&w));
-            IDP_CK(c, cudaMemcpyAsync(w, c->weights.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (info2 && c->nRows) IDP_TRY(fill_info(c, c->nRows, c->weights.p, c->weights_all_one, info2));
+    return IDP_OK;
+}
+
+int idp_gather_constraints(idp_ctx* c, int* rows4, double* info2, double* dist2)
+{
+    if (!c) return IDP_ERR_INVALID;
+    IDP_CK(c, cudaSetDevice(c->device));
+    if (!(c->rowsLocal && comm_on(c))) { // unsharded (or replicated rows): the local list is the global one
+        IDP_TRY(idp_get_constraints(c, rows4, info2));
+        if (dist2 && c->nRows) {
+            if (!c->dist2Valid) return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "idp_gather_constraints: dist2 wanted but idp_min_dist2 has not run on these rows", __FILE__, __LINE__);
+            IDP_CK(c, cudaMemcpyAsync(dist2, c->rowDist2.p, c->nRows * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
             IDP_CK(c, cudaStreamSynchronize(c->stream));
-            host_parallel(n, [=](long b, long e) { for (long i = b; i < e; ++i) { info2[2 * i] = w[i]; info2[2 * i + 1] = dh2; } });
         }
+        return IDP_OK;
+    }
+    // sharded LOCAL-ROWS mode: collective -- every rank must call it with the same non-NULL pattern; the global list (order
+    // of the unsharded path) is gathered on the device and copied out. Weights are all one here (idp_constraint_set).
+    const long n = c->nRowsGlobal;
+    if (rows4 && n) {
+        IDP_CK(c, c->rowsGlobal.reserve(n));
+        IDP_TRY(comm_gather_groups(c, c->rows.p, sizeof(Row4), c->rowsGlobal.p));
+        IDP_CK(c, cudaMemcpyAsync(rows4, c->rowsGlobal.p, n * sizeof(Row4), cudaMemcpyDeviceToHost, c->stream));
+        IDP_CK(c, cudaStreamSynchronize(c->stream));
+    }
+    if (info2 && n) IDP_TRY(fill_info(c, n, nullptr, true, info2));
+    if (dist2 && n) {
+        int st = c->dist2Valid ? IDP_OK : IDP_ERR_INVALID;
+        st = comm_agree_status(c, st);
+        if (st != IDP_OK) return fail(c, st, "%s (%s:%d)", "idp_gather_constraints: dist2 wanted but idp_min_dist2 has not run on these rows", __FILE__, __LINE__);
+        IDP_CK(c, c->dist2Global.reserve(n));
+        IDP_TRY(comm_gather_groups(c, c->rowDist2.p, sizeof(double), c->dist2Global.p));
+        IDP_CK(c, cudaMemcpyAsync(dist2, c->dist2Global.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        IDP_CK(c, cudaStreamSynchronize(c->stream));
     }
     return IDP_OK;
 }
@@ -205,6 +227,7 @@ int idp_set_constraints(idp_ctx* c, int n, const int* rows4, const double* info2
     c->nRows = n;
     c->rowsLocal = false;
     c->permValid = false;
+    c->dist2Valid = false;
     c->weights_all_one = false;
     IDP_CK(c, c->rows.reserve(std::max(n, 1)));
     IDP_CK(c, c->weights.reserve(std::max(n, 1)));
@@ -232,7 +255,7 @@ int idp_get_candidates(idp_ctx* c, int which, long* n_pairs, int* pairs2)
 
 static int finish_energy(idp_ctx* c, double E, double* E_inout)
 {
-    if (c->nranks > 1 && c->nccl_comm) {
+    if (comm_on(c)) {
         IDP_CK(c, cudaMemcpyAsync(c->red.p, &E, sizeof(double), cudaMemcpyHostToDevice, c->stream));
         IDP_TRY(comm_allreduce_sum(c, c->red.p, 1));
         IDP_CK(c, cudaMemcpyAsync(&E, c->red.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -243,7 +266,7 @@ static int finish_energy(idp_ctx* c, double E, double* E_inout)
 }
 static int finish_gradient(idp_ctx* c, double* g_accum, int stride)
 {
-    if (c->nranks > 1 && c->nccl_comm) IDP_TRY(comm_allreduce_sum(c, c->gbuf.p, 3L * c->nV));
+    if (comm_on(c)) IDP_TRY(comm_allreduce_sum(c, c->gbuf.p, 3L * c->nV));
     if (!g_accum) return IDP_OK;
     if (stride < 3) return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "stride must be >= 3", __FILE__, __LINE__);
     double* g = nullptr;
@@ -263,21 +286,21 @@ int idp_barrier_energy(idp_ctx* c, double dhat2, double kappa, double thickness,
     if (!c) return IDP_ERR_INVALID;
     IDP_CK(c, cudaSetDevice(c->device));
     double E = 0;
-    IDP_TRY(barrier_eval(c, dhat2, kappa, thickness, 1, 0, 0, 0, &E));
+    IDP_TRY(comm_agree_status(c, barrier_eval(c, dhat2, kappa, thickness, 1, 0, 0, 0, &E)));
     return finish_energy(c, E, E_inout);
 }
 int idp_barrier_gradient(idp_ctx* c, double dhat2, double kappa, double thickness, double* g_accum, int stride)
 {
     if (!c) return IDP_ERR_INVALID;
     IDP_CK(c, cudaSetDevice(c->device));
-    IDP_TRY(barrier_eval(c, dhat2, kappa, thickness, 0, 1, 0, 0, nullptr));
+    IDP_TRY(comm_agree_status(c, barrier_eval(c, dhat2, kappa, thickness, 0, 1, 0, 0, nullptr)));
     return finish_gradient(c, g_accum, stride);
 }
 int idp_barrier_hessian(idp_ctx* c, double dhat2, double kappa, double thickness, int project_spd, long* nnz)
 {
     if (!c) return IDP_ERR_INVALID;
     IDP_CK(c, cudaSetDevice(c->device));
-    IDP_TRY(barrier_eval(c, dhat2, kappa, thickness, 0, 0, 1, project_spd, nullptr));
+    IDP_TRY(comm_agree_status(c, barrier_eval(c, dhat2, kappa, thickness, 0, 0, 1, project_spd, nullptr)));
     IDP_TRY(assemble_csr(c));
     if (nnz) *nnz = c->nnz;
     return IDP_OK;
@@ -287,7 +310,7 @@ int idp_barrier_all(idp_ctx* c, double dhat2, double kappa, double thickness, in
     if (!c) return IDP_ERR_INVALID;
     IDP_CK(c, cudaSetDevice(c->device));
     double E = 0;
-    IDP_TRY(barrier_eval(c, dhat2, kappa, thickness, 1, 1, 1, project_spd, &E));
+    IDP_TRY(comm_agree_status(c, barrier_eval(c, dhat2, kappa, thickness, 1, 1, 1, project_spd, &E)));
     IDP_TRY(assemble_csr(c));
     IDP_TRY(finish_energy(c, E, E_inout));
     IDP_TRY(finish_gradient(c, nullptr, 3));
@@ -354,6 +377,8 @@ int idp_min_dist2(idp_ctx* c, double thickness, double* dist2, double* min_out)
 int idp_set_shard(idp_ctx* c, int rank, int nranks)
 {
     if (!c || nranks < 1 || rank < 0 || rank >= nranks) return IDP_ERR_INVALID;
+    if (nranks > IDP_MAX_RANKS) return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "at most IDP_MAX_RANKS (8) shards", __FILE__, __LINE__);
+    if (c->nccl_comm || c->local_group) return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "context belongs to a communicator", __FILE__, __LINE__);
     c->rank = rank;
     c->nranks = nranks;
     c->permValid = false;
@@ -382,6 +407,7 @@ long idp_last_count(idp_ctx* c, int what)
     case 6: return c->nnz;
     case 7: return c->nBlocksUnique;
     case 8: return device_alloc_counter();
+    case 9: return c->nRows;
     default: return 0;
     }
 }

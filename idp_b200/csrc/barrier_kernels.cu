@@ -228,6 +228,8 @@ int barrier_eval(idp_ctx* c, double dhat2, double kappa, double thickness, int w
     const long nPath[3] = {c->kindCount[K_EE] + c->kindCount[K_EE_M] + c->kindCount[K_PE_M] + c->kindCount[K_PP_M] + c->kindCount[K_PT],
         c->kindCount[K_PE], c->kindCount[K_PP]};
     const long nMine = nPath[0] + nPath[1] + nPath[2];
+    if (!c->have_x0 && c->kindCount[K_EE_M] + c->kindCount[K_PE_M] + c->kindCount[K_PP_M] > 0)
+        return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "mollified rows need the rest positions (idp_set_rest_positions)", __FILE__, __LINE__);
     const unsigned grid = std::max(1u, std::min(blocks_for(std::max(nPath[0], std::max(nPath[1], nPath[2])), 128), (unsigned)c->sm_count * 16));
     BarrierArgs a;
     a.rows = c->rows.p; a.weights = c->weights.p; a.perm = c->rowPerm.p; a.jBegin = 0; a.jEnd = 0;

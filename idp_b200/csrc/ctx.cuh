@@ -9,6 +9,8 @@
 #include "../../include/idp_contact.h"
 
 #define IDP_EVENT_POOL 512
+// the sharded path keeps per-rank counts, thresholds and exchange matrices in fixed-size host / device arrays
+#define IDP_MAX_RANKS 8
 
 namespace idp {
 
@@ -116,6 +118,7 @@ struct idp_ctx {
     // sharding (multi-GPU): this context evaluates query primitives / rows of shard `rank` of `nranks`
     int rank = 0, nranks = 1;
     void* nccl_comm = nullptr;
+    void* local_group = nullptr; // in-process group (idp_comm_init_local): same sharded code path, peer-memory transport
 
     // ---- mesh (set once per time step) ----
     int nV = 0, nBN = 0, nBE = 0, nBT = 0;
@@ -139,6 +142,7 @@ struct idp_ctx {
     idp::DBuf<double> red;              // reduction scratch
     idp::DBuf<unsigned char> cubTemp;
     idp::DBuf<long long> commCounts;    // P x P exchange counts
+    idp::DBuf<double> commTmp;          // in-process group: reduction result before it replaces the input
     idp::DBuf<long long> counters;      // device counters / flags (see enum in kernels)
     // ---- constraint set ----
     idp::DBuf<idp::Row4> rowsA, rowsB, rowsD, rowsD2, rows, rowsG;
@@ -149,13 +153,14 @@ struct idp_ctx {
     // sharded LOCAL-ROWS mode (set by build_constraint_set): rows holds only this rank's [direct PT][direct EE][merged] rows
     bool rowsLocal = false;
     long nRowsGlobal = 0;
-    long shardCnt[8][3] = {};
+    long shardCnt[IDP_MAX_RANKS][3] = {};
     idp::DBuf<idp::Row4> rowsGlobal;     // gathered list (idp_get_constraints)
     idp::DBuf<double> dist2Global;
     double cs_dhat2 = 0; // dHat2 stored in stencilInfo (after the thickness offset, IPC.h:53-54)
     // ---- barrier outputs ----
     idp::DBuf<double> gbuf;             // 3*nV gradient (xyz interleaved)
     idp::DBuf<double> rowDist2;
+    bool dist2Valid = false;            // rowDist2 holds the values of the current rows (set by idp_min_dist2)
     idp::DBuf<int> rowBlkOff;
     // evaluation order of this rank's rows: stable sort by row kind (uniform warps); rebuilt when the rows change
     idp::DBuf<unsigned char> rowKind, rowKindSorted;
@@ -228,6 +233,7 @@ enum Counter {
     CNT_KINDS = 16,     // 8 slots: rows of this rank per kind (k_row_kinds)
     CNT_SHARD = 24,     // 3 x 8 slots: (direct PT, direct EE, merged) row counts of every rank
     CNT_ERR_EIG = 48,   // rows whose PSD projection hit the QL iteration cap
+    CNT_STATUS = 49,    // status agreement cell (comm_agree_status)
     CNT_COUNT = 52
 };
 
@@ -286,11 +292,14 @@ int ccd_step(idp_ctx* c, double thickness, double* alpha_inout, int keep_candida
 int cub_scan_exclusive(idp_ctx* c, const int* in, int* out, long n);
 // variable-size all-gather of nLocal elements of elemSize bytes into *outPtr (capacity *outCap elements, grown and
 // preserved when too small) starting at element outOffset; *nTotal = sum over ranks
+inline bool comm_on(const idp_ctx* c) { return c->nranks > 1 && (c->nccl_comm || c->local_group); }
 int comm_allreduce_min(idp_ctx* c, double* dev, long n);
+int comm_allreduce_sum(idp_ctx* c, double* dev, long n);
+int comm_agree_status(idp_ctx* c, int status); // max over ranks of a status code (collective; identity when unsharded)
 int comm_allgather_i64(idp_ctx* c, long long* dev, long perRank); // in place: rank r's perRank values at dev + r*perRank
 int comm_gather_groups(idp_ctx* c, const void* local, size_t elemSize, void* globalOut); // local [A|B|U] -> global [A..|B..|U..]
 int comm_allreduce_min_u64(idp_ctx* c, unsigned long long* dev, long n);
-int comm_exchange_keys(idp_ctx* c, const unsigned long long* keys, const long sendBegin[8], const long sendCount[8], DBuf<unsigned long long>& recv, long* nRecv);
+int comm_exchange_keys(idp_ctx* c, const unsigned long long* keys, const long sendBegin[IDP_MAX_RANKS], const long sendCount[IDP_MAX_RANKS], DBuf<unsigned long long>& recv, long* nRecv);
 int comm_allgatherv(idp_ctx* c, const void* local, long nLocal, size_t elemSize, void** outPtr, size_t* outCap, long outOffset, long* nTotal);
 
 } // namespace idp

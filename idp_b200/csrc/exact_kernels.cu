@@ -170,6 +170,7 @@ __global__ void __launch_bounds__(1024) k_tree_reduce(const double* __restrict__
 // tree sum of n doubles in buf (clobbers scratch); result to host
 static int tree_sum_device(idp_ctx* c, double* buf, long n, double* scratchA, double* scratchB, double* host_out)
 {
+    if (n <= 0) { *host_out = 0.0; return IDP_OK; }
     const double* in = buf;
     double* outs[2] = {scratchA, scratchB};
     int flip = 0;
@@ -973,6 +974,7 @@ static void shard_range(const idp_ctx* c, long n, int* b, int* e)
 int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
 {
     c->permValid = false;
+    c->dist2Valid = false;
     if (!c->have_x) return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "positions not set", __FILE__, __LINE__);
     if (!c->have_x0) return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "rest positions not set", __FILE__, __LINE__);
     const double dHat = std::sqrt(dhat2_in) + thickness; // IPC.h:53-54
@@ -1078,7 +1080,7 @@ int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
     }
     // ---- merge (IPC.h:571-661). No buffer is swapped or re-sized here in the steady state: repeated calls reuse the same
     // allocations (cudaMalloc / cudaFree of multi-GB buffers would dominate the step).
-    const bool sharded = c->nranks > 1 && c->nccl_comm;
+    const bool sharded = comm_on(c);
     long nAg = nA, nBg = nB, nDg = nD;
     IDP_CK(c, c->rows.reserve(std::max<long>(nA + nB + nD, 1)));
     {
@@ -1114,7 +1116,7 @@ int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
             // distributed duplicate merge: sort the local keys, route every key to the rank owning its range of the leading
             // field (nV-1-p), merge there; the merged rows are gathered below in rank order = key order.
             const int P = c->nranks;
-            long sendOff[9];
+            long sendOff[IDP_MAX_RANKS + 1];
             {
             ScopeTimer tm2(c, IDP_STAGE_CCS_MERGE, true);
             IDP_CK(c, c->keyTmp.reserve(std::max<long>(nD, 1)));
@@ -1127,14 +1129,14 @@ int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
                 IDP_CK(c, cub::DeviceRadixSort::SortKeys(c->cubTemp.p, bytes, c->keyD.p, c->keyTmp.p, (int)nD, 2 * dupBits, 3 * dupBits, c->stream));
                 ++c->lib_launches;
             }
-            unsigned long long thr[9];
+            unsigned long long thr[IDP_MAX_RANKS + 1];
             for (int r = 0; r <= P; ++r) thr[r] = (r == P) ? ~0ull : (((unsigned long long)((long long)c->nV * r / P)) << (2 * dupBits));
             thr[0] = 0;
             unsigned long long* dThr = (unsigned long long*)c->histScratch.p; // 64 ints = 32 ull of scratch
             long long* dSplit = (long long*)(dThr + 12);
             IDP_CK(c, cudaMemcpyAsync(dThr, thr, (P + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
             IDP_LAUNCH(c, k_key_splits, 1, 32, 0, c->keyTmp.p, nD, dThr, P + 1, dSplit);
-            long long split[9];
+            long long split[IDP_MAX_RANKS + 1];
             IDP_CK(c, cudaMemcpyAsync(split, dSplit, (P + 1) * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
             IDP_CK(c, cudaStreamSynchronize(c->stream));
             for (int r = 0; r <= P; ++r) sendOff[r] = (long)split[r];
@@ -1142,7 +1144,7 @@ int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
             }
             // segment s of the leading field (nV-1-p ascending) holds the vertices of slab P-1-s: send it to that rank, so the
             // merged rows a rank evaluates touch the same vertex slab as its direct rows (near-disjoint partial CSRs)
-            long sendBegin[8], sendCount[8];
+            long sendBegin[IDP_MAX_RANKS], sendCount[IDP_MAX_RANKS];
             for (int r = 0; r < P; ++r) { sendBegin[r] = sendOff[P - 1 - r]; sendCount[r] = sendOff[P - r] - sendOff[P - 1 - r]; }
             IDP_TRY(comm_exchange_keys(c, c->keyTmp.p, sendBegin, sendCount, c->keyB, &nDg));
             dupKeys = c->keyB.p;
@@ -1195,7 +1197,7 @@ int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
             long long* dcnt = c->counters.p + CNT_SHARD; // 3 x P slots
             IDP_CK(c, cudaMemcpyAsync(dcnt + 3 * c->rank, mine, sizeof(mine), cudaMemcpyHostToDevice, c->stream));
             IDP_TRY(comm_allgather_i64(c, dcnt, 3));
-            long long all[24];
+            long long all[3 * IDP_MAX_RANKS];
             IDP_CK(c, cudaMemcpyAsync(all, dcnt, 3 * c->nranks * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
             IDP_CK(c, cudaStreamSynchronize(c->stream));
             c->nRowsGlobal = 0;
@@ -1272,28 +1274,27 @@ __global__ void __launch_bounds__(256) k_min_dist(const Row4* __restrict__ rows,
 int min_dist2(idp_ctx* c, double thickness, double* host_dist2, double* min_out)
 {
     if ((c->rowsLocal ? c->nRowsGlobal : c->nRows) == 0) return IDP_OK; // IPC.h:2253-2255 (a shard without rows still joins the collectives)
+    if (!c->have_x) return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "positions not set", __FILE__, __LINE__);
     StageTimer tm(c, IDP_STAGE_MIN_DIST);
     IDP_CK(c, c->rowDist2.reserve(std::max<long>(c->nRows, 1)));
     unsigned long long init = ~0ull;
     unsigned long long* d = (unsigned long long*)(c->counters.p + 8);
     IDP_CK(c, cudaMemcpyAsync(d, &init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
     // sharded: in LOCAL-ROWS mode every rank scans its own rows; with replicated rows (idp_set_constraints) and only the
-    // minimum wanted, a contiguous slice each. The order-encoded minima are combined with one all-reduce.
-    const bool sharded = c->nranks > 1 && c->nccl_comm;
+    // minimum wanted, a contiguous slice each. The order-encoded minima are combined with one all-reduce. The per-row
+    // vector is the one of the rows this rank holds (idp_get_constraints order; idp_gather_constraints for the global one).
+    const bool sharded = comm_on(c);
     const bool slice = sharded && !c->rowsLocal && !host_dist2;
     const long rb = slice ? c->nRows * c->rank / c->nranks : 0, re = slice ? c->nRows * (c->rank + 1) / c->nranks : c->nRows;
-    IDP_LAUNCH(c, k_min_dist, std::min(blocks_for(std::max(re - rb, 1L), 256), (unsigned)c->sm_count * 16), 256, 0, c->rows.p, rb, re, c->xp.p,
-        c->rowDist2.p, d);
+    if (re > rb)
+        IDP_LAUNCH(c, k_min_dist, std::min(blocks_for(re - rb, 256), (unsigned)c->sm_count * 16), 256, 0, c->rows.p, rb, re, c->xp.p, c->rowDist2.p, d);
     IDP_CK(c, cudaGetLastError());
+    c->dist2Valid = !slice;
     if (slice || (sharded && c->rowsLocal)) IDP_TRY(comm_allreduce_min_u64(c, d, 1));
-    IDP_CK(c, cudaMemcpyAsync(&init, d, sizeof(init), cudaMemcpyDeviceToHost, c->stream));
-    if (host_dist2 && c->rowsLocal && sharded) { // per-row vector in the order of the global list (collective)
-        IDP_CK(c, c->dist2Global.reserve(std::max<long>(c->nRowsGlobal, 1)));
-        IDP_TRY(comm_gather_groups(c, c->rowDist2.p, sizeof(double), c->dist2Global.p));
-        IDP_CK(c, cudaMemcpyAsync(host_dist2, c->dist2Global.p, c->nRowsGlobal * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    }
-    else if (host_dist2) IDP_CK(c, cudaMemcpyAsync(host_dist2, c->rowDist2.p, c->nRows * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    IDP_CK(c, cudaMemcpyAsync(c->h_red, d, sizeof(init), cudaMemcpyDeviceToHost, c->stream));
+    if (host_dist2 && c->nRows) IDP_CK(c, cudaMemcpyAsync(host_dist2, c->rowDist2.p, c->nRows * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     IDP_CK(c, cudaStreamSynchronize(c->stream));
+    memcpy(&init, c->h_red, sizeof(init));
     *min_out = dec_ord(init) - thickness * thickness;
     return IDP_OK;
 }
@@ -1378,6 +1379,9 @@ int ccd_step(idp_ctx* c, double thickness, double* alpha_inout, int keep_candida
     (void)keep_candidates;
     if (!c->have_x) return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "positions not set", __FILE__, __LINE__);
     double alpha = *alpha_inout;
+    c->nCcdPT = c->nCcdEE = 0;
+    c->ccd_iters = 0;
+    if (c->nBN == 0 || (c->nBT == 0 && c->nBE == 0)) return IDP_OK; // nothing can collide: the step is returned unchanged (IPC.h:1957-2243 loops are empty)
     IDP_CK(c, cudaMemsetAsync(c->counters.p, 0, CNT_COUNT * sizeof(long long), c->stream));
     GridDesc g;
     PrepArgs pa;
@@ -1467,16 +1471,18 @@ int ccd_step(idp_ctx* c, double thickness, double* alpha_inout, int keep_candida
         IDP_CK(c, cudaGetLastError());
     }
     // positive doubles order like their bit patterns, so the device cell is a valid double for the min all-reduce
-    if (c->nranks > 1 && c->nccl_comm) IDP_TRY(comm_allreduce_min(c, (double*)(cnt + CNT_ALPHA_BITS), 1));
+    if (comm_on(c)) IDP_TRY(comm_allreduce_min(c, (double*)(cnt + CNT_ALPHA_BITS), 1));
     IDP_TRY(read_counters(c));
     c->ccd_iters = (long)c->h_counters[CNT_CCD_ITERS];
     double out;
     memcpy(&out, &c->h_counters[CNT_ALPHA_BITS], 8);
     // the PT and EE candidate buffers are invalidated for the static phase
     c->nCandPT = 0; c->nCandEE = 0;
-    if (c->h_counters[CNT_ERR_CCD]) return fail(c, IDP_ERR_CCD_ITERATION_CAP, "%s (%s:%d)", "additive CCD iteration cap reached", __FILE__, __LINE__);
+    // every rank leaves with the same verdict (the step itself is already the global minimum)
+    const int st = comm_agree_status(c, c->h_counters[CNT_ERR_CCD] ? IDP_ERR_CCD_ITERATION_CAP : IDP_OK);
+    if (st != IDP_OK) return fail(c, st, "%s (%s:%d)", "additive CCD iteration cap reached", __FILE__, __LINE__);
     *alpha_inout = out;
-    if (out == 0 && (c->nCcdPT + c->nCcdEE) > 0) return fail(c, IDP_ERR_CCD_ZERO_STEP, "%s (%s:%d)", "CCD returned a zero step", __FILE__, __LINE__);
+    if (out == 0 && alpha > 0) return fail(c, IDP_ERR_CCD_ZERO_STEP, "%s (%s:%d)", "CCD returned a zero step", __FILE__, __LINE__);
     return IDP_OK;
 }
 

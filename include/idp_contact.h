@@ -83,8 +83,13 @@ int idp_set_rest_positions(idp_ctx* ctx, const double* x0, int stride);
  * (IPC.h:599-654). Row order: [PT rows][EE and mollified rows][merged PP/PE rows in key order]; rows inside the first
  * two groups are sorted lexicographically (the reference's order there depends on unordered_set iteration). */
 int idp_constraint_set(idp_ctx* ctx, double dhat2, double thickness, int* n_rows);
-/* constraintSet (VECTOR<int,4>, 16 B/row) and stencilInfo (weight, dHat2) to the host. Either pointer may be NULL. */
+/* constraintSet (VECTOR<int,4>, 16 B/row) and stencilInfo (weight, dHat2) to the host. Either pointer may be NULL.
+ * Sharded: the rows THIS rank holds (idp_last_count(ctx, 9) of them), not a collective. */
 int idp_get_constraints(idp_ctx* ctx, int* rows4, double* info2);
+/* The GLOBAL list (idp_last_count(ctx, 0) rows) in the order of the unsharded path, on every rank; dist2 = the per-row
+ * values of the last idp_min_dist2 in the same order. Any pointer may be NULL. Sharded: a collective (all ranks call it
+ * with the same NULL pattern); unsharded: the same as idp_get_constraints. */
+int idp_gather_constraints(idp_ctx* ctx, int* rows4, double* info2, double* dist2);
 /* Use a caller-supplied constraint set (the constraintSet / stencilInfo arguments of Compute_Barrier*, IPC.h:745-746). */
 int idp_set_constraints(idp_ctx* ctx, int n_rows, const int* rows4, const double* info2);
 /* Post-AABB candidate pairs of the last idp_constraint_set / idp_ccd_step, lexicographically sorted:
@@ -125,17 +130,25 @@ int idp_min_dist2(idp_ctx* ctx, double thickness, double* dist2, double* min_dis
 /* Sharded semantics (after idp_comm_init): every entry point is called by ALL ranks with the same arguments.
  *   idp_constraint_set      queries split by contiguous primitive ranges; each rank keeps the rows it produced (direct PT /
  *                           EE rows of its range + the merged PP/PE rows of its vertex slab); *n_rows is the GLOBAL count;
- *   idp_get_constraints     collective: gathers the global list, bit-identical to the single-GPU one, on every rank;
+ *   idp_get_constraints     NOT a collective: the rows of this rank ([its direct PT][its direct EE][its merged PP/PE] rows);
+ *   idp_gather_constraints  collective: gathers the global list, bit-identical to the single-GPU one, on every rank;
  *   idp_barrier_*           E and the gradient are all-reduced (every rank returns the global values); the Hessian CSR of a
  *                           rank holds the partial sums of its rows -- the global Hessian is the sum of the P CSRs (their
  *                           patterns are nearly disjoint: a primitive range touches a vertex slab);
  *   idp_ccd_step*           sharded queries, all-reduce(min) of the step;
- *   idp_min_dist2           all-reduce(min); with dist2 != NULL collective gather of the per-row values in global order;
+ *   idp_min_dist2           all-reduce(min); dist2 = the values of this rank's rows (global order: idp_gather_constraints);
  *   idp_set_constraints     rows are replicated and evaluated by the owner of the vertex chunk of their smallest vertex. */
 /* out_id: 128 bytes (ncclUniqueId) produced on rank 0 and broadcast by the host program */
 int idp_comm_unique_id(void* out_id128);
 int idp_comm_init(idp_ctx* ctx, int rank, int nranks, const void* id128);
-/* shard without a communicator (results stay partial; for tests of the partition logic) */
+/* In-process group: ctxs[r] becomes rank r of nranks (<= 8) contexts of THIS process, on the same or on different GPUs.
+ * Same sharded semantics as idp_comm_init, but the exchanges go over peer memory (device-to-device copies and a
+ * rank-ordered reduction kernel that loads the peers' buffers) instead of NCCL. Every context must then be driven by
+ * its own host thread (the collectives meet at a host barrier). Used by the sharding parity tests on one GPU. */
+int idp_comm_init_local(idp_ctx** ctxs, int nranks);
+/* in-process group only: wake every rank waiting in a collective with IDP_ERR_INVALID (a host thread gave up) */
+int idp_comm_abort(idp_ctx* ctx);
+/* shard without a communicator (results stay partial; for tests of the partition logic). nranks <= 8. */
 int idp_set_shard(idp_ctx* ctx, int rank, int nranks);
 
 /* ---- instrumentation ------------------------------------------------------------------------------------------ */
@@ -143,7 +156,7 @@ long idp_kernel_launches(idp_ctx* ctx);     /* this library's own kernels launch
 long idp_library_calls(idp_ctx* ctx);       /* CUB device-wide primitives invoked since idp_reset_counters */
 void idp_reset_counters(idp_ctx* ctx);
 float idp_stage_ms(idp_ctx* ctx, int stage); /* device time of the last execution of a stage (CUDA events) */
-long idp_last_count(idp_ctx* ctx, int what); /* 0 rows, 1 PT cand, 2 EE cand, 3 CCD PT cand, 4 CCD EE cand, 5 ACCD trips, 6 nnz, 7 unique 3x3 blocks, 8 device allocations made so far */
+long idp_last_count(idp_ctx* ctx, int what); /* 0 rows, 1 PT cand, 2 EE cand, 3 CCD PT cand, 4 CCD EE cand, 5 ACCD trips, 6 nnz, 7 unique 3x3 blocks, 8 device allocations made so far, 9 rows held by this rank */
 /* FP64 pipe microbenchmark: register-resident DFMA chains on every SM; returns measured TFLOP/s (roofline denominator) */
 int idp_measure_fp64_tflops(idp_ctx* ctx, double* tflops);
 

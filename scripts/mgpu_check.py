@@ -30,11 +30,12 @@ dist.broadcast_object_list(uid, src=0)
 ctx.comm_init(rank, world, uid[0])
 ctx.set_surface_mesh(mesh)
 n = ctx.constraint_set(dh2)
-rows, _ = ctx.get_constraints()
+rows, _ = ctx.gather_constraints()
 E = ctx.barrier_energy(dh2, kappa); g = ctx.barrier_gradient(dh2, kappa)
 ptr, col, val = ctx.barrier_hessian(dh2, kappa)
 a = ctx.ccd_step(direction, 1.0)
-d1, m1 = ctx.min_dist2()               # collective in the sharded path: per-row vector in the global order
+_, m1 = ctx.min_dist2()
+_, _, d1 = ctx.gather_constraints(want_dist2=True)  # collective: per-row vector in the global order
 _, m2 = ctx.min_dist2(want_all=False)  # min only: local rows + all-reduce
 N = 3 * mesh.nV
 parts = [None] * world

@@ -9,11 +9,18 @@
   step, determinism, and a rigorous per-pair proof (independent numpy distances + the Lipschitz bound of the linear
   trajectories) that the closest candidate pairs never touch along the returned step.
 """
+import json
+import os
+
 import numpy as np
 import pytest
 
 from conftest import lexsorted
+from digests import pairs_digest, rows_digest
 from geometry_np import point_triangle_distance, segment_segment_distance
+
+with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_fullsize.json")) as _f:
+    GOLD = json.load(_f)  # digests of the REFERENCE's own loops run offline at full size (tests/golden/make_golden_fullsize.py)
 
 pytestmark = pytest.mark.gpu
 KAPPA = 1e5
@@ -138,6 +145,16 @@ def test_config4_sheets_4m_properties(gpu_ctx, orc):
     n = gpu_ctx.constraint_set(dh * dh)
     rows, info = gpu_ctx.get_constraints()
     assert n == len(rows) > 20000000
+    # the whole constraint set, the per-row distances and both static candidate sets against the digests of the reference's
+    # own loops (FEM/IPC.h compiled into oracle/_ref) run offline on this very mesh
+    gold = GOLD["sheets8x500"]
+    assert gold["triangles"] == m.nF and gold["dhat"] == dh
+    dist_all, mn_all = gpu_ctx.min_dist2()
+    assert rows_digest(rows, dist_all) == gold["constraint_set"]
+    assert mn_all == gold["min_dist2"]
+    assert (info[:, 0] == gold["info_all"][0]).all() and (info[:, 1] == gold["info_all"][1]).all()
+    assert pairs_digest(gpu_ctx.get_candidates(0)) == gold["static_candidates"]["pt"]
+    assert pairs_digest(gpu_ctx.get_candidates(1)) == gold["static_candidates"]["ee"]
     # group layout of the reference: [PT rows][EE / mollified rows][merged PP / PE rows], each group sorted
     pt = (rows[:, 0] < 0) & (rows[:, 3] >= 0)
     ee = rows[:, 0] >= 0
@@ -174,8 +191,49 @@ def test_config4_sheets_4m_properties(gpu_ctx, orc):
     cpt, cee = gpu_ctx.get_candidates(2), gpu_ctx.get_candidates(3)
     assert 0 < a <= 1.0 and a == gpu_ctx.ccd_step(d, 1.0)
     assert len(cpt) + len(cee) > 40000000
+    ra = gold["ccd"]["alpha_reference"]
+    assert a <= ra and abs(a - ra) <= 1e-6 * ra, (a, ra)  # never above the reference's step, within 1e-6 of it
+    assert pairs_digest(cpt) == gold["ccd"]["candidates"]["pt"] and pairs_digest(cee) == gold["ccd"]["candidates"]["ee"]
     worst = _closest_pairs_never_touch(m, d, a, cpt, cee)
     assert worst > 0
+
+
+def test_config4_crop_and_config5_crop_against_reference_digests(gpu_ctx):
+    """sheets8x160 (409,600 triangles) and a 1,000,000-triangle crop of the config-5 CCD stress sheets: constraint set,
+    candidates and CCD steps of the step-filter sweep against the reference-loop digests."""
+    import bench
+    sys_path_golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_fullsize", os.path.join(sys_path_golden, "make_golden_fullsize.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    m, d, dh = bench.build_workload("sheets8x160")
+    gold = GOLD["sheets8x160"]
+    gpu_ctx.set_surface_mesh(m)
+    gpu_ctx.constraint_set(dh * dh)
+    rows, info = gpu_ctx.get_constraints()
+    dist_all, mn_all = gpu_ctx.min_dist2()
+    assert rows_digest(rows, dist_all) == gold["constraint_set"] and mn_all == gold["min_dist2"]
+    assert pairs_digest(gpu_ctx.get_candidates(0)) == gold["static_candidates"]["pt"]
+    assert pairs_digest(gpu_ctx.get_candidates(1)) == gold["static_candidates"]["ee"]
+    a = gpu_ctx.ccd_step(d, 1.0)
+    assert a == gold["ccd"]["alpha_reference"]
+    assert pairs_digest(gpu_ctx.get_candidates(2)) == gold["ccd"]["candidates"]["pt"]
+    assert pairs_digest(gpu_ctx.get_candidates(3)) == gold["ccd"]["candidates"]["ee"]
+    # config 5 crop: CCD only
+    gold = GOLD["ccd_stress_16x250x125"]
+    m, d, h = gen.config5_mesh(250, 125, (0.5, 0.25))
+    assert m.nF == gold["triangles"]
+    gpu_ctx.set_surface_mesh(m)
+    for rec in gold["sweep"]:
+        dd = np.ascontiguousarray(d * (rec["sigma_over_h"] * h))
+        a = gpu_ctx.ccd_step(dd, rec["alpha0"], rec["thickness"])
+        ra = rec["alpha_reference"]
+        assert a <= ra and abs(a - ra) <= 1e-6 * ra, (rec, a)
+        if rec["step_after_clamp"] == rec["alpha0"]:  # no span clamp: identical grid, identical candidates, identical step
+            assert a == ra
+            assert pairs_digest(gpu_ctx.get_candidates(2)) == rec["candidates"]["pt"]
+            assert pairs_digest(gpu_ctx.get_candidates(3)) == rec["candidates"]["ee"]
 
 
 def test_config5_ccd_only_16m_step_filter_sweep(gpu_ctx):
