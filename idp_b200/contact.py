@@ -27,7 +27,7 @@ EXPORTS = ["idp_create", "idp_destroy", "idp_last_error", "idp_set_stream", "idp
            "idp_gather_constraints", "idp_comm_init_local", "idp_comm_abort",
            "idp_set_constraints", "idp_get_candidates", "idp_barrier_energy", "idp_barrier_gradient",
            "idp_barrier_hessian", "idp_barrier_all", "idp_get_hessian_csr", "idp_hessian_csr_device",
-           "idp_gradient_device", "idp_ccd_step", "idp_set_search_direction", "idp_ccd_step_resident", "idp_min_dist2", "idp_comm_unique_id", "idp_comm_init",
+           "idp_gradient_device", "idp_get_gradient", "idp_ccd_step", "idp_set_search_direction", "idp_ccd_step_resident", "idp_min_dist2", "idp_comm_unique_id", "idp_comm_init",
            "idp_set_shard", "idp_kernel_launches", "idp_library_calls", "idp_reset_counters", "idp_stage_ms",
            "idp_last_count", "idp_measure_fp64_tflops"]
 
@@ -67,6 +67,7 @@ def load_library(path=LIB_PATH):
     L.idp_get_hessian_csr.argtypes = [vp, vp, vp, vp]
     L.idp_hessian_csr_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(l)]
     L.idp_gradient_device.argtypes = [vp, C.POINTER(vp)]
+    L.idp_get_gradient.argtypes = [vp, vp, i]
     L.idp_ccd_step.argtypes = [vp, vp, i, d, C.POINTER(d)]
     L.idp_set_search_direction.argtypes = [vp, vp, i]
     L.idp_ccd_step_resident.argtypes = [vp, d, C.POINTER(d)]

@@ -52,7 +52,7 @@ int idp_create(int device, idp_ctx** out)
     cudaEventCreate(&c->ev0);
     cudaEventCreate(&c->ev1);
     for (int i = 0; i < 2 * IDP_EVENT_POOL; ++i) cudaEventCreate(&c->evPool[i]);
-    if (c->counters.reserve(CNT_COUNT) != cudaSuccess || c->histScratch.reserve(64) != cudaSuccess) { delete c; return IDP_ERR_CUDA; }
+    if (c->counters.reserve(CNT_COUNT) != cudaSuccess || c->histScratch.reserve(256) != cudaSuccess) { delete c; return IDP_ERR_CUDA; }
     cudaMemset(c->counters.p, 0, CNT_COUNT * sizeof(long long));
     cudaMallocHost((void**)&c->h_counters, CNT_COUNT * sizeof(long long));
     cudaMallocHost((void**)&c->h_red, 64 * sizeof(double));
@@ -268,17 +268,7 @@ static int finish_gradient(idp_ctx* c, double* g_accum, int stride)
 {
     if (comm_on(c)) IDP_TRY(comm_allreduce_sum(c, c->gbuf.p, 3L * c->nV));
     if (!g_accum) return IDP_OK;
-    if (stride < 3) return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "stride must be >= 3", __FILE__, __LINE__);
-    double* g = nullptr;
-    const long nV = c->nV;
-    IDP_TRY(host_stage(c, 3 * (size_t)nV * sizeof(double), (void**)&g));
-    IDP_CK(c, cudaMemcpyAsync(g, c->gbuf.p, 3 * (size_t)nV * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    IDP_CK(c, cudaStreamSynchronize(c->stream));
-    host_parallel(nV, [=](long b, long e) {
-        for (long v = b; v < e; ++v)
-            for (int a = 0; a < 3; ++a) g_accum[v * stride + a] += g[3 * v + a];
-    });
-    return IDP_OK;
+    return idp_get_gradient(c, g_accum, stride);
 }
 
 int idp_barrier_energy(idp_ctx* c, double dhat2, double kappa, double thickness, double* E_inout)
@@ -334,6 +324,23 @@ int idp_hessian_csr_device(idp_ctx* c, const int** d_ptr, const int** d_col, con
     if (d_col) *d_col = c->csrCol.p;
     if (d_val) *d_val = c->csrVal.p;
     if (nnz) *nnz = c->nnz;
+    return IDP_OK;
+}
+int idp_get_gradient(idp_ctx* c, double* g_accum, int stride)
+{
+    if (!c || !g_accum) return IDP_ERR_INVALID;
+    IDP_CK(c, cudaSetDevice(c->device));
+    if (stride < 3) return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "stride must be >= 3", __FILE__, __LINE__);
+    if (c->gbuf.cap < 3 * (size_t)c->nV) return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "no gradient has been computed", __FILE__, __LINE__);
+    double* g = nullptr;
+    const long nV = c->nV;
+    IDP_TRY(host_stage(c, 3 * (size_t)nV * sizeof(double), (void**)&g));
+    IDP_CK(c, cudaMemcpyAsync(g, c->gbuf.p, 3 * (size_t)nV * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    IDP_CK(c, cudaStreamSynchronize(c->stream));
+    host_parallel(nV, [=](long b, long e) {
+        for (long v = b; v < e; ++v)
+            for (int a = 0; a < 3; ++a) g_accum[v * stride + a] += g[3 * v + a];
+    });
     return IDP_OK;
 }
 int idp_gradient_device(idp_ctx* c, const double** d_g)

@@ -36,17 +36,23 @@ __device__ __forceinline__ int row_owner(const Row4& r, int shift, int nranks)
     for (int k = 1; k < 4; ++k) mv = (k < d.nv && d.v[k] < mv) ? d.v[k] : mv;
     return (mv >> shift) % nranks;
 }
-// number of 3x3 blocks a row contributes: nv(nv+1)/2 -- only blocks with vi <= vj are emitted, the assembly mirrors them
-__global__ void k_row_block_counts(const Row4* __restrict__ rows, long n, int rank, int nranks, int shift, int* __restrict__ cnt)
+// Hessian blocks are bucketed by their LOWER vertex: the local Hessian is symmetric, so one block per unordered vertex pair
+// (vlo <= vhi) is emitted, nv(nv+1)/2 per row (IPC.h:1372-1387 emits all nv^2 x 9 scalars), and vertex v collects the blocks
+// whose lower vertex it is. This pass counts them: vertex v[k] of a row receives 1 + #{m : v[m] > v[k]} blocks.
+__global__ void k_vertex_block_counts(const Row4* __restrict__ rows, long n, int rank, int nranks, int shift, int* __restrict__ cnt)
 {
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += (long)gridDim.x * blockDim.x) {
-        int k = 0;
-        if (i < n) {
-            const Row4 r = rows[i];
-            if (nranks == 1 || row_owner(r, shift, nranks) == rank)
-                k = (r.a >= 0 || r.d >= 0) ? 10 : (r.c >= 0 ? 6 : 3); // upper triangle of the nv x nv blocks (IPC.h:1372-1387 counts all nv^2)
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const Row4 r = rows[i];
+        if (nranks != 1 && row_owner(r, shift, nranks) != rank) continue;
+        const RowDec d = decode_row(r.a, r.b, r.c, r.d);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (k >= d.nv) break;
+            int m = 1;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) m += (j < d.nv && d.v[j] > d.v[k]) ? 1 : 0;
+            atomicAdd(&cnt[d.v[k]], m);
         }
-        cnt[i] = k;
     }
 }
 // kind of every row of this rank (7 = row of another rank) + identity permutation; kinds are counted per block and added
@@ -76,29 +82,50 @@ struct BarrierArgs {
     int projectSPD;
     double* partialE;                 // one slot per block
     double* g;                        // 3*nV, xyz interleaved (atomics)
-    const int* blkOff; unsigned long long* blkKey; int* blkIdx; double* blkVal; long long nVll;
+    const int* vtxOff; int* vtxCursor; unsigned long long* bktKey; double* bktVal8; double* bktVal1; // Hessian block buckets
     unsigned long long* errDist;
     unsigned long long* errEig;
 };
 
-// Hessian sink: the local Hessian is symmetric, so only one block per unordered vertex pair is stored, keyed (vlo, vhi)
-// with vlo <= vhi; block (i,j) with v[i] > v[j] is stored transposed. Slot = upper-triangle index of (min(i,j), max(i,j)).
-struct BlockEmit {
-    unsigned long long* key; int* idx; double* val;
-    long o; int nv; const int* v; long long nV;
+// Hessian sink: block (i,j), i <= j, of a row goes to the bucket of its lower vertex vlo = min(v[i], v[j]) (stored transposed
+// when v[i] > v[j]). A row reserves its slots in the (up to four) buckets with one atomic each; inside the reservation the
+// blocks are ordered by the stencil index of the higher vertex. Bucket entry: key (vhi << 32 | row << 4 | 4 i + j) -- the
+// low word is a deterministic origin tag that fixes the summation order of duplicates -- and the 3x3 values split 64 + 8
+// bytes (the 64-byte part is written as two full 32-byte sectors).
+struct BucketEmit {
+    unsigned long long* key; double* val8; double* val1;
+    int base[4]; int nv; const int* v; unsigned rowTag;
+    __device__ __forceinline__ void reserve(const int* vtxOff, int* cursor)
+    {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            base[k] = 0;
+            if (k < nv) {
+                int m = 1;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) m += (j < nv && v[j] > v[k]) ? 1 : 0;
+                base[k] = __ldg(vtxOff + v[k]) + atomicAdd(cursor + v[k], m);
+            }
+        }
+    }
     __device__ __forceinline__ bool wants(int i, int j) const { return i <= j; }
     __device__ __forceinline__ void operator()(int i, int j, const double* blk) const
     {
-        const long s = o + (i * nv - (i * (i - 1)) / 2 + (j - i));
         const bool tr = v[i] > v[j];
-        const long long vlo = tr ? v[j] : v[i], vhi = tr ? v[i] : v[j];
-        key[s] = (unsigned long long)(vlo * nV + vhi);
-        idx[s] = (int)s;
-        double* dst = val + 9 * s;
+        const int a = tr ? j : i, b = tr ? i : j; // a: lower vertex, b: higher (a == b on the diagonal)
+        int rnk = 0;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) rnk += (m < b && m < nv && (v[m] > v[a] || m == a)) ? 1 : 0;
+        const long s = (long)base[a] + rnk;
+        key[s] = ((unsigned long long)(unsigned)v[b] << 32) | (unsigned long long)(rowTag | (unsigned)(4 * i + j));
+        double t[9];
 #pragma unroll
         for (int p = 0; p < 3; ++p)
 #pragma unroll
-            for (int q = 0; q < 3; ++q) dst[3 * p + q] = tr ? blk[3 * q + p] : blk[3 * p + q];
+            for (int q = 0; q < 3; ++q) t[3 * p + q] = tr ? blk[3 * q + p] : blk[3 * p + q];
+        double2* d8 = reinterpret_cast<double2*>(val8 + 8 * s);
+        d8[0] = make_double2(t[0], t[1]); d8[1] = make_double2(t[2], t[3]); d8[2] = make_double2(t[4], t[5]); d8[3] = make_double2(t[6], t[7]);
+        val1[s] = t[8];
     }
 };
 
@@ -130,7 +157,9 @@ __global__ void __launch_bounds__(BarrierCfg<PATH>::T, BarrierCfg<PATH>::MINB) k
         RowOut out;
         QlStore<9, BarrierCfg<PATH>::T> V9{sV + threadIdx.x};
         QlStore<6, BarrierCfg<PATH>::T> V6{sV + threadIdx.x};
-        BlockEmit em{a.blkKey, a.blkIdx, a.blkVal, WANT_H ? (long)a.blkOff[i] : 0L, d.nv, d.v, a.nVll};
+        BucketEmit em;
+        em.key = a.bktKey; em.val8 = a.bktVal8; em.val1 = a.bktVal1; em.nv = d.nv; em.v = d.v; em.rowTag = (unsigned)i << 4;
+        if (WANT_H) em.reserve(a.vtxOff, a.vtxCursor);
         const bool ok = row_eval<PATH>(d, x, xr, a.weights[i], a.dHat2, a.kappa, a.xi2, a.projectSPD != 0, WANT_H, V9, V6, out, em);
         if (!ok) { atomicAdd(a.errDist, 1ull); continue; }
         if (WANT_H && out.eigFail) atomicAdd(a.errEig, 1ull);
@@ -241,27 +270,27 @@ int barrier_eval(idp_ctx* c, double dhat2, double kappa, double thickness, int w
     a.g = c->gbuf.p;
     a.errDist = (unsigned long long*)(c->counters.p + CNT_ERR_DIST);
     a.errEig = (unsigned long long*)(c->counters.p + CNT_ERR_EIG);
-    a.nVll = c->nV;
-    a.blkOff = nullptr; a.blkKey = nullptr; a.blkIdx = nullptr; a.blkVal = nullptr;
+    a.vtxOff = nullptr; a.vtxCursor = nullptr; a.bktKey = nullptr; a.bktVal8 = nullptr; a.bktVal1 = nullptr;
     long nBlocks = 0;
     if (want_h) {
-        IDP_CK(c, c->rowBlkOff.reserve(c->nRows + 1));
-        IDP_CK(c, c->segId.reserve(c->nRows + 1));
-        IDP_LAUNCH(c, k_row_block_counts, blocks_for(c->nRows + 1, 256), 256, 0, c->rows.p, c->nRows, c->rank, ownRanks, ownerShift, c->segId.p);
-        IDP_TRY(cub_scan_exclusive(c, c->segId.p, c->rowBlkOff.p, c->nRows + 1));
-        int ends[2] = {0, 0};
-        IDP_CK(c, cudaMemcpyAsync(&ends[1], c->rowBlkOff.p + c->nRows, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        if (c->nRows >= (1L << 28)) return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "more than 2^28 constraint rows on one rank", __FILE__, __LINE__);
+        const size_t nV1 = (size_t)c->nV + 1;
+        IDP_CK(c, c->vtxCnt.reserve(nV1)); IDP_CK(c, c->vtxOff.reserve(nV1)); IDP_CK(c, c->vtxCursor.reserve(nV1));
+        IDP_CK(c, cudaMemsetAsync(c->vtxCnt.p, 0, nV1 * sizeof(int), c->stream));
+        IDP_CK(c, cudaMemsetAsync(c->vtxCursor.p, 0, nV1 * sizeof(int), c->stream));
+        IDP_LAUNCH(c, k_vertex_block_counts, std::min(blocks_for(c->nRows, 256), (unsigned)c->sm_count * 16), 256, 0, c->rows.p, c->nRows, c->rank, ownRanks, ownerShift, c->vtxCnt.p);
+        IDP_TRY(cub_scan_exclusive(c, c->vtxCnt.p, c->vtxOff.p, (long)nV1));
+        int total = 0;
+        IDP_CK(c, cudaMemcpyAsync(&total, c->vtxOff.p + c->nV, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         IDP_CK(c, cudaStreamSynchronize(c->stream));
-        nBlocks = ends[1]; // offsets count only this rank's rows, so its blocks are contiguous in [0, nBlocks)
-        IDP_CK(c, c->blkKey.reserve(std::max<long>(nBlocks, 1)));
-        IDP_CK(c, c->blkIdx.reserve(std::max<long>(nBlocks, 1)));
-        IDP_CK(c, c->blkVal.reserve(9 * (size_t)std::max<long>(nBlocks, 1)));
-        a.blkOff = c->rowBlkOff.p; a.blkKey = c->blkKey.p; a.blkIdx = c->blkIdx.p; a.blkVal = c->blkVal.p;
+        nBlocks = total; // only this rank's rows are counted
+        IDP_CK(c, c->bktKey.reserve(std::max<long>(nBlocks, 1)));
+        IDP_CK(c, c->bktVal8.reserve(8 * (size_t)std::max<long>(nBlocks, 1)));
+        IDP_CK(c, c->bktVal1.reserve(std::max<long>(nBlocks, 1)));
+        a.vtxOff = c->vtxOff.p; a.vtxCursor = c->vtxCursor.p; a.bktKey = c->bktKey.p; a.bktVal8 = c->bktVal8.p; a.bktVal1 = c->bktVal1.p;
         c->nBlocksUnique = 0;
         c->nnz = 0;
-        // remember the slice for the assembly
-        c->h_counters[CNT_COUNT - 2] = ends[0];
-        c->h_counters[CNT_COUNT - 1] = ends[1];
+        c->nBlocksEmitted = nBlocks;
     }
     if (nMine > 0) {
         KernelTimer kt(c, IDP_STAGE_K_BARRIER);
@@ -293,63 +322,151 @@ int barrier_eval(idp_ctx* c, double dhat2, double kappa, double thickness, int w
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// assembly: sort (vi*nV + vj) keys, segmented sum of the 3x3 blocks, scalar CSR with ascending columns
+// assembly (replaces Eigen's setFromTriplets, Math/CSR_MATRIX.h:49-56): the blocks arrive bucketed by lower vertex
+// (k_barrier / BucketEmit). One warp per vertex sorts its bucket's keys (vhi, origin) in shared memory, finds the unique
+// upper neighbours and sums the duplicates in origin order -- deterministic although the slots inside a bucket were handed
+// out by atomics -- reading the 3x3 values from the bucket's own contiguous region. No global sort of the ~10 blocks per
+// row is needed (the first version radix-sorted 200 M 64-bit keys and then gathered 72-byte values from all over HBM).
+// The unique upper blocks are mirrored (a small stable sort by column vertex) and every block row is written as
+// [mirrors ascending][diagonal + upper ascending] -> exactly Eigen's pattern: columns ascending, duplicates summed.
 // ------------------------------------------------------------------------------------------------------------
-__global__ void k_head_flags(const unsigned long long* __restrict__ keys, long n, int* __restrict__ flag)
+// ascending bitonic network without direction flags ("flip" merge): elements past n behave as +inf and are never touched
+template <class SyncF>
+__device__ __forceinline__ void bitonic_sort_kp(unsigned long long* key, unsigned* pay, int n, int tid, int nthreads, SyncF sync)
 {
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
-        flag[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
-}
-// segId = inclusive scan of flags - 1; scatter segment starts
-__global__ void k_seg_starts(const int* __restrict__ flagScan, const int* __restrict__ flag, long n, int* __restrict__ segStart)
-{
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
-        if (flag[i]) segStart[flagScan[i]] = (int)i; // flagScan = exclusive scan -> segment index
-}
-// first unique (upper) block of every block row: vtxStart[v] = lower_bound(uniqueKey, v * nV)
-__global__ void k_vertex_block_starts(const unsigned long long* __restrict__ keys, const int* __restrict__ segStart, int nSeg,
-    int nV, int* __restrict__ vtxStart)
-{
-    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v <= nV; v += gridDim.x * blockDim.x) {
-        const unsigned long long target = (unsigned long long)v * (unsigned long long)nV;
-        int lo = 0, hi = nSeg;
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (keys[segStart[mid]] < target) lo = mid + 1;
-            else hi = mid;
+    int P = 1;
+    while (P < n) P <<= 1;
+    for (int k = 2; k <= P; k <<= 1) {
+        const int half = k >> 1;
+        for (int t = tid; t < (P >> 1); t += nthreads) { // flip stage: i <-> mirror inside its block of k
+            const int grp = t / half, idx = t - grp * half;
+            const int i = grp * k + idx, l = grp * k + (k - 1 - idx);
+            if (l < n) {
+                const unsigned long long a = key[i], b = key[l];
+                if (a > b) { key[i] = b; key[l] = a; const unsigned pa = pay[i]; pay[i] = pay[l]; pay[l] = pa; }
+            }
         }
-        vtxStart[v] = lo;
+        sync();
+        for (int j = k >> 2; j > 0; j >>= 1) {
+            for (int t = tid; t < (P >> 1); t += nthreads) {
+                const int i = 2 * j * (t / j) + (t % j), l = i + j;
+                if (l < n) {
+                    const unsigned long long a = key[i], b = key[l];
+                    if (a > b) { key[i] = b; key[l] = a; const unsigned pa = pay[i]; pay[i] = pay[l]; pay[l] = pa; }
+                }
+            }
+            sync();
+        }
     }
 }
-// one thread per (unique upper block, component): sum the members in sorted (= emission) order into ublk[seg][9];
-// component 0 also records the block's column vertex and counts the strictly-upper blocks per column (= lower blocks per row)
-__global__ void __launch_bounds__(288) k_reduce_blocks(const unsigned long long* __restrict__ keys, const int* __restrict__ idx,
-    const int* __restrict__ segStart, int nSeg, long nTot, const double* __restrict__ blkVal, long long nV,
-    double* __restrict__ ublk, int* __restrict__ ucol, int* __restrict__ urow, int* __restrict__ lowerCount)
+struct ReduceArgs {
+    const int* vtxOff; const unsigned long long* bktKey; const double* bktVal8; const double* bktVal1;
+    int nV;
+    int* uCount; int* uCol; double* uVal; int* lowerCount; // unique blocks of vertex v at sparse slots vtxOff[v] + u
+    int* bigList; int* bigCount;                           // vertices whose bucket exceeds the shared-memory capacity
+    unsigned long long* bigKey; unsigned* bigPay; unsigned* bigStart; // global scratch for those (aligned with the bucket slots)
+};
+// after the sort: unique upper neighbours and their sums. key/pay/ustart may live in shared or global memory.
+template <class SyncF>
+__device__ __forceinline__ void reduce_sorted_bucket(const ReduceArgs& a, int v, int off, int n, const unsigned long long* key, const unsigned* pay,
+    unsigned* ustart, int tid, int nthreads, int* sCounter, SyncF sync)
 {
-    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long seg = t / 9;
-    const int comp = (int)(t - seg * 9);
-    if (seg >= nSeg) return;
-    const int s0 = segStart[seg];
-    const int s1 = (seg + 1 < nSeg) ? segStart[seg + 1] : (int)nTot;
-    double s = 0;
-    for (int m = s0; m < s1; ++m) s += blkVal[9 * (long)idx[m] + comp];
-    ublk[9 * seg + comp] = s;
-    if (comp == 0) {
-        const unsigned long long key = keys[s0];
-        const int vi = (int)(key / (unsigned long long)nV), vj = (int)(key - (unsigned long long)vi * (unsigned long long)nV);
-        urow[seg] = vi;
-        ucol[seg] = vj;
-        if (vi != vj) atomicAdd(&lowerCount[vj], 1);
+    // heads of the runs of equal vhi -> ustart[u] (order preserved: a block-wide pass in chunks with a running base)
+    if (tid == 0) *sCounter = 0;
+    sync();
+    for (int p0 = 0; p0 < n; p0 += nthreads) {
+        const int p = p0 + tid;
+        const bool head = p < n && (p == 0 || (unsigned)(key[p] >> 32) != (unsigned)(key[p - 1] >> 32));
+        // order-preserving compaction inside the chunk: warp ballots + per-warp bases taken in warp order
+        const unsigned m = __ballot_sync(0xffffffffu, head);
+        const int lane = tid & 31, wid = tid >> 5, nw = (nthreads + 31) >> 5;
+        for (int w = 0; w < nw; ++w) { // warps take their turn (nw = 1 for the warp-per-vertex path)
+            if (w == wid) {
+                int base = 0;
+                if (lane == 0) { base = *sCounter; *sCounter = base + __popc(m); }
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (head) ustart[base + __popc(m & ((1u << lane) - 1u))] = (unsigned)p;
+            }
+            sync();
+        }
+    }
+    const int U = *sCounter;
+    sync();
+    for (int t = tid; t < 9 * U; t += nthreads) {
+        const int u = t / 9, comp = t - 9 * u;
+        const int s0 = (int)ustart[u], s1 = (u + 1 < U) ? (int)ustart[u + 1] : n;
+        double sum = 0;
+        for (int p = s0; p < s1; ++p) {
+            const long slot = (long)off + pay[p];
+            sum += comp < 8 ? a.bktVal8[8 * slot + comp] : a.bktVal1[slot];
+        }
+        a.uVal[9 * ((long)off + u) + comp] = sum;
+        if (comp == 0) {
+            const int vj = (int)(unsigned)(key[s0] >> 32);
+            a.uCol[off + u] = vj;
+            if (vj != v) atomicAdd(&a.lowerCount[vj], 1);
+        }
+    }
+    if (tid == 0) a.uCount[v] = U;
+    sync();
+}
+#define IDP_REDUCE_WARPS 4
+#define IDP_REDUCE_CAP 512 // bucket entries a warp sorts in shared memory
+__global__ void __launch_bounds__(32 * IDP_REDUCE_WARPS) k_vertex_reduce(ReduceArgs a)
+{
+    __shared__ unsigned long long sKey[IDP_REDUCE_WARPS][IDP_REDUCE_CAP];
+    __shared__ unsigned sPay[IDP_REDUCE_WARPS][IDP_REDUCE_CAP];
+    __shared__ unsigned sStart[IDP_REDUCE_WARPS][IDP_REDUCE_CAP];
+    __shared__ int sCnt[IDP_REDUCE_WARPS];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    auto sync = [] { __syncwarp(); };
+    for (int v = blockIdx.x * IDP_REDUCE_WARPS + wib; v < a.nV; v += gridDim.x * IDP_REDUCE_WARPS) {
+        const int off = a.vtxOff[v], n = a.vtxOff[v + 1] - off;
+        if (n == 0) { if (lane == 0) a.uCount[v] = 0; continue; }
+        if (n > IDP_REDUCE_CAP) {
+            if (lane == 0) { a.bigList[atomicAdd(a.bigCount, 1)] = v; a.uCount[v] = 0; }
+            continue;
+        }
+        for (int p = lane; p < n; p += 32) { sKey[wib][p] = a.bktKey[off + p]; sPay[wib][p] = (unsigned)p; }
+        __syncwarp();
+        bitonic_sort_kp(sKey[wib], sPay[wib], n, lane, 32, sync);
+        reduce_sorted_bucket(a, v, off, n, sKey[wib], sPay[wib], sStart[wib], lane, 32, &sCnt[wib], sync);
+    }
+}
+// oversized buckets: one CTA per vertex, the same network on global scratch (correct for any size; only pathological
+// inputs -- one vertex within dHat of thousands of primitives -- get here)
+__global__ void __launch_bounds__(256) k_vertex_reduce_big(ReduceArgs a)
+{
+    __shared__ int sCnt;
+    auto sync = [] { __threadfence_block(); __syncthreads(); };
+    const int nBig = *a.bigCount;
+    for (int b = blockIdx.x; b < nBig; b += gridDim.x) {
+        const int v = a.bigList[b];
+        const int off = a.vtxOff[v], n = a.vtxOff[v + 1] - off;
+        unsigned long long* key = a.bigKey + off;
+        unsigned* pay = a.bigPay + off;
+        for (int p = threadIdx.x; p < n; p += blockDim.x) { key[p] = a.bktKey[off + p]; pay[p] = (unsigned)p; }
+        sync();
+        bitonic_sort_kp(key, pay, n, (int)threadIdx.x, (int)blockDim.x, sync);
+        reduce_sorted_bucket(a, v, off, n, key, pay, a.bigStart + off, (int)threadIdx.x, (int)blockDim.x, &sCnt, sync);
+    }
+}
+// compact list of the unique upper blocks in (row vertex, column vertex) order
+__global__ void __launch_bounds__(256) k_compact_unique(const int* __restrict__ vtxOff, const int* __restrict__ uCount, const int* __restrict__ vtxBlkStart,
+    const int* __restrict__ uCol, int nV, int* __restrict__ urow, int* __restrict__ ucol, int* __restrict__ usrc)
+{
+    const int lane = threadIdx.x & 31;
+    for (int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < nV; v += (gridDim.x * blockDim.x) >> 5) {
+        const int U = uCount[v], off = vtxOff[v], seg0 = vtxBlkStart[v];
+        for (int u = lane; u < U; u += 32) { urow[seg0 + u] = v; ucol[seg0 + u] = uCol[off + u]; usrc[seg0 + u] = off + u; }
     }
 }
 // block-row layout: [lower blocks (mirrors, ascending column)] [upper blocks incl. diagonal (ascending column)]
 // cnt[v] = lowerCount[v] + upperCount[v]
-__global__ void k_row_totals(const int* __restrict__ vtxStart, const int* __restrict__ lowerCount, int nV, int* __restrict__ cnt)
+__global__ void k_row_totals(const int* __restrict__ uCount, const int* __restrict__ lowerCount, int nV, int* __restrict__ cnt)
 {
     for (int v = blockIdx.x * blockDim.x + threadIdx.x; v <= nV; v += gridDim.x * blockDim.x)
-        cnt[v] = (v < nV) ? lowerCount[v] + (vtxStart[v + 1] - vtxStart[v]) : 0;
+        cnt[v] = (v < nV) ? lowerCount[v] + uCount[v] : 0;
 }
 __global__ void k_csr_ptr(const int* __restrict__ rowStart, int nV, int* __restrict__ ptr)
 {
@@ -362,8 +479,8 @@ __global__ void k_csr_ptr(const int* __restrict__ rowStart, int nV, int* __restr
     }
 }
 // upper (and diagonal) blocks: one thread per (unique block, component)
-__global__ void __launch_bounds__(288) k_write_upper(const double* __restrict__ ublk, const int* __restrict__ urow, const int* __restrict__ ucol,
-    int nSeg, const int* __restrict__ vtxStart, const int* __restrict__ rowStart, const int* __restrict__ lowerCount,
+__global__ void __launch_bounds__(288) k_write_upper(const double* __restrict__ uVal, const int* __restrict__ usrc, const int* __restrict__ urow,
+    const int* __restrict__ ucol, int nSeg, const int* __restrict__ vtxBlkStart, const int* __restrict__ rowStart, const int* __restrict__ lowerCount,
     int* __restrict__ col, double* __restrict__ val)
 {
     const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -372,16 +489,16 @@ __global__ void __launch_bounds__(288) k_write_upper(const double* __restrict__ 
     if (seg >= nSeg) return;
     const int vi = urow[seg], vj = ucol[seg];
     const int bs = rowStart[vi], nb = rowStart[vi + 1] - bs;
-    const int slot = lowerCount[vi] + (int)(seg - vtxStart[vi]);
+    const int slot = lowerCount[vi] + (int)(seg - vtxBlkStart[vi]);
     const int a = comp / 3, b = comp - 3 * a;
     const long pos = 9L * bs + (long)a * 3 * nb + 3L * slot + b;
     col[pos] = 3 * vj + b;
-    val[pos] = ublk[9 * seg + comp];
+    val[pos] = uVal[9L * usrc[seg] + comp];
 }
 // mirrored blocks: `order` lists the strictly-upper unique blocks stably sorted by their column vertex, so the members
 // of one block row appear with ascending row vertex = ascending column in the mirror. lstart[v] = first entry of row v.
-__global__ void __launch_bounds__(288) k_write_lower(const double* __restrict__ ublk, const int* __restrict__ urow, const int* __restrict__ order,
-    const int* __restrict__ sortedCol, long nLower, const int* __restrict__ lstart, const int* __restrict__ rowStart,
+__global__ void __launch_bounds__(288) k_write_lower(const double* __restrict__ uVal, const int* __restrict__ usrc, const int* __restrict__ urow,
+    const int* __restrict__ order, const int* __restrict__ sortedCol, long nLower, const int* __restrict__ lstart, const int* __restrict__ rowStart,
     int* __restrict__ col, double* __restrict__ val)
 {
     const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -395,13 +512,10 @@ __global__ void __launch_bounds__(288) k_write_lower(const double* __restrict__ 
     const int a = comp / 3, b = comp - 3 * a;
     const long pos = 9L * bs + (long)a * 3 * nb + 3L * slot + b;
     col[pos] = 3 * cv + b;
-    val[pos] = ublk[9 * seg + 3 * b + a]; // transposed block
+    val[pos] = uVal[9L * usrc[seg] + 3 * b + a]; // transposed block
 }
-__global__ void k_lower_keys(const int* __restrict__ urow, const int* __restrict__ ucol, int nSeg, int* __restrict__ keyOut, int* __restrict__ segOut,
-    unsigned long long* __restrict__ counter)
+__global__ void k_lower_keys(const int* __restrict__ urow, const int* __restrict__ ucol, int nSeg, int* __restrict__ keyOut, int* __restrict__ segOut)
 {
-    // compacts the strictly-upper blocks in segment order (deterministic: slot = exclusive count of earlier ones is not
-    // needed because the following sort is stable on (column) and the input order here is by segment via the scan below)
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < nSeg; s += gridDim.x * blockDim.x) {
         keyOut[s] = (urow[s] != ucol[s]) ? ucol[s] : 0x7fffffff; // diagonal blocks sort to the end and are ignored
         segOut[s] = s;
@@ -424,8 +538,7 @@ int assemble_csr(idp_ctx* c)
 {
     StageTimer tm(c, IDP_STAGE_CSR);
     IDP_CK(c, c->csrPtr.reserve(3 * (size_t)c->nV + 1));
-    const long b0 = c->nRows ? (long)c->h_counters[CNT_COUNT - 2] : 0, b1 = c->nRows ? (long)c->h_counters[CNT_COUNT - 1] : 0;
-    const long n = b1 - b0;
+    const long n = c->nRows ? c->nBlocksEmitted : 0;
     if (n <= 0) {
         IDP_CK(c, cudaMemsetAsync(c->csrPtr.p, 0, (3 * (size_t)c->nV + 1) * sizeof(int), c->stream));
         c->nnz = 0; c->nBlocksUnique = 0;
@@ -433,50 +546,43 @@ int assemble_csr(idp_ctx* c)
         return IDP_OK;
     }
     const int nV = c->nV;
-    IDP_CK(c, c->blkKeySorted.reserve(n));
-    IDP_CK(c, c->blkIdxSorted.reserve(n));
-    int bits = 1;
-    while (bits < 64 && ((unsigned long long)nV * (unsigned long long)nV) >> bits) ++bits;
-    size_t bytes = 0;
-    IDP_CK(c, cub::DeviceRadixSort::SortPairs(nullptr, bytes, c->blkKey.p + b0, c->blkKeySorted.p, c->blkIdx.p + b0, c->blkIdxSorted.p, (int)n, 0, bits, c->stream));
-    IDP_CK(c, c->cubTemp.reserve(bytes));
-    IDP_CK(c, cub::DeviceRadixSort::SortPairs(c->cubTemp.p, bytes, c->blkKey.p + b0, c->blkKeySorted.p, c->blkIdx.p + b0, c->blkIdxSorted.p, (int)n, 0, bits, c->stream));
-    ++c->lib_launches;
-    // unique upper blocks
-    IDP_CK(c, c->segId.reserve(std::max<long>(n + 1, nV + 2)));
-    IDP_CK(c, c->segStart.reserve(n + 1));
-    IDP_CK(c, c->rowBlkOff.reserve(std::max<long>(n + 1, nV + 2))); // reused as scan output (row offsets are no longer needed)
-    IDP_LAUNCH(c, k_head_flags, blocks_for(n, 256), 256, 0, c->blkKeySorted.p, n, c->segId.p);
-    IDP_CK(c, cudaMemsetAsync(c->segId.p + n, 0, sizeof(int), c->stream));
-    IDP_TRY(cub_scan_exclusive(c, c->segId.p, c->rowBlkOff.p, n + 1));
+    const size_t nV2 = (size_t)nV + 2;
+    // per-vertex sort / unique / sum
+    IDP_CK(c, c->uCount.reserve(nV2)); IDP_CK(c, c->uCol.reserve(n)); IDP_CK(c, c->uVal.reserve(9 * (size_t)n));
+    IDP_CK(c, c->lowerCount.reserve(nV2)); IDP_CK(c, c->lstart.reserve(nV2));
+    IDP_CK(c, c->vtxBlkStart.reserve(nV2)); IDP_CK(c, c->rowStart.reserve(nV2)); IDP_CK(c, c->segId.reserve(nV2));
+    IDP_CK(c, c->bigList.reserve(nV2)); IDP_CK(c, c->bigKey.reserve(n)); IDP_CK(c, c->bigPay.reserve(n)); IDP_CK(c, c->bigStart.reserve(n));
+    IDP_CK(c, cudaMemsetAsync(c->lowerCount.p, 0, nV2 * sizeof(int), c->stream));
+    IDP_CK(c, cudaMemsetAsync(c->uCount.p + nV, 0, 2 * sizeof(int), c->stream));
+    int* dBigCount = c->bigList.p + nV + 1;
+    IDP_CK(c, cudaMemsetAsync(dBigCount, 0, sizeof(int), c->stream));
+    ReduceArgs ra;
+    ra.vtxOff = c->vtxOff.p; ra.bktKey = c->bktKey.p; ra.bktVal8 = c->bktVal8.p; ra.bktVal1 = c->bktVal1.p; ra.nV = nV;
+    ra.uCount = c->uCount.p; ra.uCol = c->uCol.p; ra.uVal = c->uVal.p; ra.lowerCount = c->lowerCount.p;
+    ra.bigList = c->bigList.p; ra.bigCount = dBigCount; ra.bigKey = c->bigKey.p; ra.bigPay = c->bigPay.p; ra.bigStart = c->bigStart.p;
+    IDP_LAUNCH(c, k_vertex_reduce, std::min(blocks_for(nV, IDP_REDUCE_WARPS), (unsigned)c->sm_count * 64), 32 * IDP_REDUCE_WARPS, 0, ra);
+    IDP_LAUNCH(c, k_vertex_reduce_big, (unsigned)c->sm_count * 2, 256, 0, ra);
+    IDP_TRY(cub_scan_exclusive(c, c->uCount.p, c->vtxBlkStart.p, (long)nV + 1));
     int nSeg = 0;
-    IDP_CK(c, cudaMemcpyAsync(&nSeg, c->rowBlkOff.p + n, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    IDP_LAUNCH(c, k_seg_starts, blocks_for(n, 256), 256, 0, c->rowBlkOff.p, c->segId.p, n, c->segStart.p);
-    IDP_CK(c, cudaStreamSynchronize(c->stream));
-    // reduce duplicates -> dense unique upper blocks
-    IDP_CK(c, c->ublk.reserve(9 * (size_t)nSeg));
-    IDP_CK(c, c->urow.reserve(nSeg)); IDP_CK(c, c->ucol.reserve(nSeg));
-    IDP_CK(c, c->lowerCount.reserve((size_t)nV + 2)); IDP_CK(c, c->lstart.reserve((size_t)nV + 2));
-    IDP_CK(c, c->vtxBlkStart.reserve((size_t)nV + 2)); IDP_CK(c, c->rowStart.reserve((size_t)nV + 2));
-    IDP_CK(c, cudaMemsetAsync(c->lowerCount.p, 0, ((size_t)nV + 2) * sizeof(int), c->stream));
-    IDP_LAUNCH(c, k_reduce_blocks, blocks_for(9L * nSeg, 288), 288, 0, c->blkKeySorted.p, c->blkIdxSorted.p, c->segStart.p, nSeg, n,
-        c->blkVal.p, (long long)nV, c->ublk.p, c->ucol.p, c->urow.p, c->lowerCount.p);
-    IDP_LAUNCH(c, k_vertex_block_starts, blocks_for(nV + 1, 256), 256, 0, c->blkKeySorted.p, c->segStart.p, nSeg, nV, c->vtxBlkStart.p);
+    IDP_CK(c, cudaMemcpyAsync(&nSeg, c->vtxBlkStart.p + nV, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     // block-row sizes and starts
-    IDP_LAUNCH(c, k_row_totals, blocks_for(nV + 1, 256), 256, 0, c->vtxBlkStart.p, c->lowerCount.p, nV, c->segId.p);
+    IDP_LAUNCH(c, k_row_totals, blocks_for(nV + 1, 256), 256, 0, c->uCount.p, c->lowerCount.p, nV, c->segId.p);
     IDP_TRY(cub_scan_exclusive(c, c->segId.p, c->rowStart.p, (long)nV + 1));
     int nBlkTotal = 0;
     IDP_CK(c, cudaMemcpyAsync(&nBlkTotal, c->rowStart.p + nV, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    IDP_CK(c, cudaStreamSynchronize(c->stream));
+    IDP_CK(c, c->urow.reserve(std::max(nSeg, 1))); IDP_CK(c, c->ucol.reserve(std::max(nSeg, 1))); IDP_CK(c, c->usrc.reserve(std::max(nSeg, 1)));
+    IDP_LAUNCH(c, k_compact_unique, std::min(blocks_for(32L * nV, 256), (unsigned)c->sm_count * 32), 256, 0, c->vtxOff.p, c->uCount.p, c->vtxBlkStart.p, c->uCol.p, nV,
+        c->urow.p, c->ucol.p, c->usrc.p);
     // mirrored (lower) blocks: stable sort of the unique blocks by column vertex
-    IDP_CK(c, c->lkey.reserve(nSeg)); IDP_CK(c, c->lkeySorted.reserve(nSeg)); IDP_CK(c, c->lseg.reserve(nSeg)); IDP_CK(c, c->lsegSorted.reserve(nSeg));
-    IDP_LAUNCH(c, k_lower_keys, blocks_for(nSeg, 256), 256, 0, c->urow.p, c->ucol.p, nSeg, c->lkey.p, c->lseg.p, (unsigned long long*)nullptr);
-    int vbits = 1;
-    while (vbits < 31 && (nV >> vbits)) ++vbits;
+    IDP_CK(c, c->lkey.reserve(std::max(nSeg, 1))); IDP_CK(c, c->lkeySorted.reserve(std::max(nSeg, 1)));
+    IDP_CK(c, c->lseg.reserve(std::max(nSeg, 1))); IDP_CK(c, c->lsegSorted.reserve(std::max(nSeg, 1)));
+    IDP_LAUNCH(c, k_lower_keys, blocks_for(nSeg, 256), 256, 0, c->urow.p, c->ucol.p, nSeg, c->lkey.p, c->lseg.p);
+    size_t bytes = 0;
     IDP_CK(c, cub::DeviceRadixSort::SortPairs(nullptr, bytes, c->lkey.p, c->lkeySorted.p, c->lseg.p, c->lsegSorted.p, nSeg, 0, 31, c->stream));
     IDP_CK(c, c->cubTemp.reserve(bytes));
     IDP_CK(c, cub::DeviceRadixSort::SortPairs(c->cubTemp.p, bytes, c->lkey.p, c->lkeySorted.p, c->lseg.p, c->lsegSorted.p, nSeg, 0, 31, c->stream));
     ++c->lib_launches;
-    IDP_CK(c, cudaStreamSynchronize(c->stream));
     const long nLower = (long)nBlkTotal - nSeg; // every strictly-upper block has one mirror
     c->nBlocksUnique = nBlkTotal;
     c->nnz = 9L * nBlkTotal;
@@ -484,10 +590,11 @@ int assemble_csr(idp_ctx* c)
     IDP_CK(c, c->csrVal.reserve(std::max<long>(c->nnz, 1)));
     IDP_LAUNCH(c, k_lower_starts, blocks_for(nV + 1, 256), 256, 0, c->lkeySorted.p, nLower, nV, c->lstart.p);
     IDP_LAUNCH(c, k_csr_ptr, blocks_for(nV + 1, 256), 256, 0, c->rowStart.p, nV, c->csrPtr.p);
-    IDP_LAUNCH(c, k_write_upper, blocks_for(9L * nSeg, 288), 288, 0, c->ublk.p, c->urow.p, c->ucol.p, nSeg, c->vtxBlkStart.p, c->rowStart.p,
-        c->lowerCount.p, c->csrCol.p, c->csrVal.p);
+    if (nSeg > 0)
+        IDP_LAUNCH(c, k_write_upper, blocks_for(9L * nSeg, 288), 288, 0, c->uVal.p, c->usrc.p, c->urow.p, c->ucol.p, nSeg, c->vtxBlkStart.p, c->rowStart.p,
+            c->lowerCount.p, c->csrCol.p, c->csrVal.p);
     if (nLower > 0)
-        IDP_LAUNCH(c, k_write_lower, blocks_for(9L * nLower, 288), 288, 0, c->ublk.p, c->urow.p, c->lsegSorted.p, c->lkeySorted.p, nLower, c->lstart.p,
+        IDP_LAUNCH(c, k_write_lower, blocks_for(9L * nLower, 288), 288, 0, c->uVal.p, c->usrc.p, c->urow.p, c->lsegSorted.p, c->lkeySorted.p, nLower, c->lstart.p,
             c->rowStart.p, c->csrCol.p, c->csrVal.p);
     IDP_CK(c, cudaGetLastError());
     IDP_CK(c, cudaStreamSynchronize(c->stream));

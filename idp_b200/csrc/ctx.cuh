@@ -29,14 +29,6 @@ struct __align__(32) IBox {
     int hi[3];
     int pad[2];
 };
-// compact cell-sorted filter record (32 B) read by the broad-phase traversal instead of chasing entries[] -> PrimRec:
-// static phase: the primitive's AABB rounded OUTWARD to float (a conservative pre-filter, the exact FP64 predicate is
-// applied to the survivors); CCD: its integer lattice box (the reference's "shares a voxel" test is exact on these).
-struct __align__(32) CRec {
-    union { float f[6]; int i[6]; } box; // lo[3], hi[3]
-    int b;    // primitive index
-    int aux;  // CCD (multi insertion): x index of the cell this copy lives in
-};
 struct __align__(16) Row4 {
     int a, b, c, d;
     __host__ __device__ bool operator==(const Row4& o) const { return a == o.a && b == o.b && c == o.c && d == o.d; }
@@ -136,7 +128,7 @@ struct idp_ctx {
     idp::DBuf<idp::IBox> boxNq, boxEq, boxEb, boxTb; // query boxes (inflated) and insert boxes
     idp::DBuf<idp::IBox> vbox;                        // per-vertex lattice box (CCD)
     idp::DBuf<int> cellStart, cellCursor, largeList, histScratch;
-    idp::DBuf<idp::CRec> crec;          // cell-sorted compact records (one per stored (cell, primitive) entry)
+    idp::DBuf<int4> crec0, crec1;       // cell-sorted filter records, SoA 2 x 16 B (see k_cells)
     idp::DBuf<int2> candPT, candEE;
     long nCandPT = 0, nCandEE = 0;
     idp::DBuf<double> red;              // reduction scratch
@@ -161,17 +153,21 @@ struct idp_ctx {
     idp::DBuf<double> gbuf;             // 3*nV gradient (xyz interleaved)
     idp::DBuf<double> rowDist2;
     bool dist2Valid = false;            // rowDist2 holds the values of the current rows (set by idp_min_dist2)
-    idp::DBuf<int> rowBlkOff;
     // evaluation order of this rank's rows: stable sort by row kind (uniform warps); rebuilt when the rows change
     idp::DBuf<unsigned char> rowKind, rowKindSorted;
     idp::DBuf<int> rowIota, rowPerm;
     long kindCount[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     bool permValid = false;
-    idp::DBuf<unsigned long long> blkKey, blkKeySorted;
-    idp::DBuf<int> blkIdx, blkIdxSorted, segId, segStart;
-    idp::DBuf<double> blkVal;
+    // Hessian blocks bucketed by lower vertex (BucketEmit) and their per-vertex reduction (assemble_csr)
+    idp::DBuf<int> vtxCnt, vtxOff, vtxCursor;
+    idp::DBuf<unsigned long long> bktKey, bigKey;
+    idp::DBuf<double> bktVal8, bktVal1, uVal;
+    idp::DBuf<int> uCount, uCol, usrc, bigList;
+    idp::DBuf<unsigned> bigPay, bigStart;
+    long nBlocksEmitted = 0;
+    idp::DBuf<unsigned long long> blkKey, blkKeySorted; // scratch of idp_get_candidates
+    idp::DBuf<int> segId;
     idp::DBuf<int> vtxBlkStart, rowStart, lowerCount, lstart, urow, ucol, lkey, lkeySorted, lseg, lsegSorted;
-    idp::DBuf<double> ublk;              // unique upper 3x3 blocks after the segmented sum
     idp::DBuf<int> csrPtr, csrCol;
     idp::DBuf<double> csrVal;
     long nnz = 0, nBlocksUnique = 0;

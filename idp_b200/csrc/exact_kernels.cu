@@ -331,24 +331,55 @@ __device__ __forceinline__ void cell_range(const GridDesc& g, const IBox& b, int
 // note: lattice indices are >= 0 on the paths that use k > 1 (CCD lattice origin is the global minimum), so integer
 // division is a monotone floor.
 //
-// Cell lists with ANCHOR insertion: every primitive is stored once, in the cell of the low corner of its box, provided
-// its box spans at most `emax` cells beyond that corner on every axis; the (few) larger ones go to a "large" list that
-// every query scans. A query then visits the cells [qlo - emax, qhi]: each pair is met exactly once, so the traversal
-// needs no de-duplication and touches one 64-byte record per visited primitive.
-struct EMax { int e[3]; };
-__global__ void k_extent_hist(const IBox* __restrict__ bbox, int nB, GridDesc g, int* __restrict__ hist)
+// Cell lists with ANCHOR insertion in LEVELS: a primitive is stored once, in the cell of the low corner of its box, in the
+// first level that covers its extent. Bins 0 and 1 use the base cells and hold the primitives that span at most 1 / exactly
+// 2 cells beyond their corner; bin j >= 2 has cells of 2^j base cells and holds what spans at most two of those per axis.
+// A query visits, per non-empty level, the cells [qlo - ext, qhi] (ext = the largest span of the level per axis): every
+// pair is met exactly once -- no de-duplication, no per-cell copies -- and the neighbourhood of a query does not grow with
+// the largest primitive in the scene (the swept CCD boxes have a long-tailed extent distribution: a single level either
+// visits 6^3 cells for everybody or parks the tail on a list that every query scans). The tail levels are sparse and have
+// few, large cells, so they cost a query a handful of rows. A thinly populated bin 1 is folded into bin 2 (useBin1 = 0).
+#define IDP_MAX_LEVELS 12   // active (non-empty) levels
+#define IDP_LEVEL_BINS 28
+struct Levels {
+    int n;                          // active levels
+    int useBin1;
+    int shift[IDP_MAX_LEVELS];      // cell = base cell >> shift
+    int ext[IDP_MAX_LEVELS][3];     // largest span (in level cells) of the level's primitives per axis
+    int dim[IDP_MAX_LEVELS][3];     // cells per axis
+    long off[IDP_MAX_LEVELS];       // first cell of the level in the concatenated cellStart array
+    signed char slot[IDP_LEVEL_BINS]; // level bin -> active index (-1: empty)
+};
+__host__ __device__ __forceinline__ int level_shift(int bin) { return bin < 2 ? 0 : bin; }
+__device__ __forceinline__ int level_of(const int lo[3], const int hi[3], int useBin1)
 {
-    __shared__ int sh[48]; // 16 bins per axis
-    if (threadIdx.x < 48) sh[threadIdx.x] = 0;
+    const int m = max(hi[0] - lo[0], max(hi[1] - lo[1], hi[2] - lo[2]));
+    if (m <= 1) return 0;
+    if (m == 2 && useBin1) return 1;
+    int s = 2;
+    while (s < IDP_LEVEL_BINS - 1 && (((hi[0] >> s) - (lo[0] >> s)) > 1 || ((hi[1] >> s) - (lo[1] >> s)) > 1 || ((hi[2] >> s) - (lo[2] >> s)) > 1)) ++s;
+    return s;
+}
+// hist[bin] = primitives of the level; hist[IDP_LEVEL_BINS + 3 bin + k] = their largest span on axis k
+__global__ void k_level_hist(const IBox* __restrict__ bbox, int nB, GridDesc g, int* __restrict__ hist)
+{
+    __shared__ int sh[4 * IDP_LEVEL_BINS];
+    for (int i = threadIdx.x; i < 4 * IDP_LEVEL_BINS; i += blockDim.x) sh[i] = 0;
     __syncthreads();
     for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nB; b += gridDim.x * blockDim.x) {
         int lo[3], hi[3];
         cell_range(g, bbox[b], lo, hi);
+        const int l = level_of(lo, hi, 1), s = level_shift(l);
+        atomicAdd(&sh[l], 1);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) atomicAdd(&sh[16 * k + min(hi[k] - lo[k], 15)], 1);
+        for (int k = 0; k < 3; ++k) {
+            const int e = (hi[k] >> s) - (lo[k] >> s);
+            if (e > sh[IDP_LEVEL_BINS + 3 * l + k]) atomicMax(&sh[IDP_LEVEL_BINS + 3 * l + k], e);
+        }
     }
     __syncthreads();
-    if (threadIdx.x < 48 && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
+    for (int i = threadIdx.x; i < 4 * IDP_LEVEL_BINS; i += blockDim.x)
+        if (sh[i]) { if (i < IDP_LEVEL_BINS) atomicAdd(&hist[i], sh[i]); else atomicMax(&hist[i], sh[i]); }
 }
 // Shards only look at the cells their own queries visit: the bounding box (in cell coordinates) of the query ranges of
 // this rank is reduced on the device and the fill kernels skip everything outside it, so the cost of building the cell
@@ -372,43 +403,13 @@ __global__ void k_query_region(const IBox* __restrict__ qbox, int qBegin, int qE
         for (int k = 0; k < 3; ++k) { atomicMin(&region[k], lo[k]); atomicMax(&region[3 + k], hi[k]); }
     }
 }
-// MULTI insertion (used for the swept CCD boxes, whose extents vary too much for anchor insertion to pay off): a
-// primitive is stored in every cell its box overlaps and a pair is accepted only in the componentwise max of the two
-// boxes' low corners, which again meets every pair exactly once.
+// Cell-sorted filter records, SoA: rec0[i] = (lo.x, lo.y, lo.z, hi.x), rec1[i] = (hi.y, hi.z, primitive, 0): the primitive's
+// AABB (static phase) or full-step swept AABB (CCD) rounded OUTWARD to float -- a conservative pre-filter; the exact
+// predicate (FP64 AABB gap; for CCD also the integer "shares a voxel" test of the reference's hash) is applied to the
+// survivors. Consecutive lanes of the query kernel read consecutive records, so both 16-byte streams are fully coalesced.
 template <bool FILL>
-__global__ void k_cells_multi(const IBox* __restrict__ bbox, int nB, GridDesc g, const int* __restrict__ region,
-    int* __restrict__ cellCountOrCursor, CRec* __restrict__ crec)
-{
-    int rg[6];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) rg[k] = region[k];
-    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nB; b += gridDim.x * blockDim.x) {
-        int lo[3], hi[3];
-        const IBox bb = bbox[b];
-        cell_range(g, bb, lo, hi);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) { lo[k] = max(lo[k], rg[k]); hi[k] = min(hi[k], rg[3 + k]); } // cells no query of this shard visits
-        CRec rc;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) { rc.box.i[k] = bb.lo[k]; rc.box.i[3 + k] = bb.hi[k]; }
-        rc.b = b;
-        for (int iz = lo[2]; iz <= hi[2]; ++iz)
-            for (int iy = lo[1]; iy <= hi[1]; ++iy) {
-                const long row = ((long)iz * g.n[1] + iy) * g.n[0];
-                for (int ix = lo[0]; ix <= hi[0]; ++ix) {
-                    if (FILL) {
-                        rc.aux = ix;
-                        crec[atomicAdd(&cellCountOrCursor[row + ix], 1)] = rc;
-                    }
-                    else atomicAdd(&cellCountOrCursor[row + ix], 1);
-                }
-            }
-    }
-}
-template <bool FILL>
-__global__ void k_cells(const IBox* __restrict__ bbox, const PrimRec* __restrict__ rec, int nB, GridDesc g, EMax emax,
-    const int* __restrict__ region, int* __restrict__ cellCountOrCursor, CRec* __restrict__ crec, int* __restrict__ large,
-    int* __restrict__ largeCount)
+__global__ void k_cells(const IBox* __restrict__ bbox, const PrimRec* __restrict__ rec, int nB, GridDesc g, Levels lv,
+    const int* __restrict__ region, int* __restrict__ cellCountOrCursor, int4* __restrict__ rec0, int4* __restrict__ rec1)
 {
     int rg[6];
 #pragma unroll
@@ -416,21 +417,21 @@ __global__ void k_cells(const IBox* __restrict__ bbox, const PrimRec* __restrict
     for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nB; b += gridDim.x * blockDim.x) {
         int lo[3], hi[3];
         cell_range(g, bbox[b], lo, hi);
-        if (hi[0] - lo[0] > emax.e[0] || hi[1] - lo[1] > emax.e[1] || hi[2] - lo[2] > emax.e[2]) {
-            if (FILL) large[atomicAdd(largeCount, 1)] = b;
-            continue;
-        }
-        // queries visit the anchors in [qlo - emax, qhi]: anchors outside the shard's region (grown by emax) are never met
-        if (lo[0] < rg[0] - emax.e[0] || lo[0] > rg[3] || lo[1] < rg[1] - emax.e[1] || lo[1] > rg[4] || lo[2] < rg[2] - emax.e[2] || lo[2] > rg[5])
-            continue;
-        const long cell = ((long)lo[2] * g.n[1] + lo[1]) * g.n[0] + lo[0];
+        const int li = lv.slot[level_of(lo, hi, lv.useBin1)], l = lv.shift[li];
+        // queries visit the anchors in [qlo - ext, qhi] (level cells): anchors outside the shard's region are never met
+        bool skip = false;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) skip = skip || (lo[k] >> l) < (rg[k] >> l) - lv.ext[li][k] || (lo[k] >> l) > (rg[3 + k] >> l);
+        if (skip) continue;
+        const long cell = lv.off[li] + ((long)(lo[2] >> l) * lv.dim[li][1] + (lo[1] >> l)) * lv.dim[li][0] + (lo[0] >> l);
         if (FILL) {
             const PrimRec r = rec[b];
-            CRec rc;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) { rc.box.f[k] = __double2float_rd(r.lo[k]); rc.box.f[3 + k] = __double2float_ru(r.hi[k]); }
-            rc.b = b; rc.aux = 0;
-            crec[atomicAdd(&cellCountOrCursor[cell], 1)] = rc;
+            const int4 r0 = make_int4(__float_as_int(__double2float_rd(r.lo[0])), __float_as_int(__double2float_rd(r.lo[1])),
+                __float_as_int(__double2float_rd(r.lo[2])), __float_as_int(__double2float_ru(r.hi[0])));
+            const int4 r1 = make_int4(__float_as_int(__double2float_ru(r.hi[1])), __float_as_int(__double2float_ru(r.hi[2])), b, 0);
+            const int slot = atomicAdd(&cellCountOrCursor[cell], 1);
+            rec0[slot] = r0;
+            rec1[slot] = r1;
         }
         else atomicAdd(&cellCountOrCursor[cell], 1);
     }
@@ -448,11 +449,10 @@ int cub_scan_exclusive(idp_ctx* c, const int* in, int* out, long n)
 
 static long grid_cells(const GridDesc& g) { return (long)g.n[0] * g.n[1] * g.n[2]; }
 
-#define IDP_LARGE_CAP 4096
 // device region of the cells visited by the queries [qb, qe) of this shard (6 ints behind the histogram scratch)
 static int set_query_region(idp_ctx* c, const IBox* qbox, int qb, int qe, const GridDesc& g, int** regionOut)
 {
-    int* dRegion = (int*)c->histScratch.p + 50;
+    int* dRegion = (int*)c->histScratch.p + 4 * IDP_LEVEL_BINS + 2;
     int init[6] = {0, 0, 0, g.n[0] - 1, g.n[1] - 1, g.n[2] - 1};
     const bool shard = c->nranks > 1;
     if (shard) { init[0] = init[1] = init[2] = 2147483647; init[3] = init[4] = init[5] = -1; }
@@ -461,231 +461,247 @@ static int set_query_region(idp_ctx* c, const IBox* qbox, int qb, int qe, const 
     *regionOut = dRegion;
     return IDP_OK;
 }
-// Build cellStart (nCells + 1), the cell-sorted records and the large list for the insert boxes bbox[0..nB). Chooses the smallest
-// emax <= 3 that leaves at most IDP_LARGE_CAP primitives on the large list; if there is none the cells are coarsened
-// (g.k doubled: a cell is k^3 lattice voxels) and the choice is repeated.
-static int build_cells_multi(idp_ctx* c, const IBox* bbox, int nB, const GridDesc& g, const IBox* qbox, int qb, int qe)
+// Build the level table, cellStart (all levels concatenated, + 1) and the cell-sorted records for the insert boxes
+// bbox[0..nB). If the primitives spread over more than IDP_MAX_LEVELS levels the base cells are coarsened (g.k doubled: a
+// cell is k^3 lattice voxels) and the choice is repeated.
+static int build_cells(idp_ctx* c, const IBox* bbox, const PrimRec* rec, int nB, GridDesc& g, const int latN[3], Levels* levelsOut,
+    const IBox* qbox, int qb, int qe, bool ccd)
 {
-    int* dRegion = nullptr;
-    IDP_TRY(set_query_region(c, qbox, qb, qe, g, &dRegion));
-    const long nc = grid_cells(g);
-    IDP_CK(c, c->cellStart.reserve(nc + 1));
-    IDP_CK(c, c->cellCursor.reserve(nc + 1));
-    IDP_CK(c, cudaMemsetAsync(c->cellCursor.p, 0, (nc + 1) * sizeof(int), c->stream));
-    IDP_CK(c, cudaMemsetAsync((int*)c->histScratch.p + 48, 0, sizeof(int), c->stream)); // empty large list
-    IDP_LAUNCH(c, k_cells_multi<false>, blocks_for(nB, 256), 256, 0, bbox, nB, g, dRegion, c->cellCursor.p, (CRec*)nullptr);
-    IDP_TRY(cub_scan_exclusive(c, c->cellCursor.p, c->cellStart.p, nc + 1));
-    int total = 0;
-    IDP_CK(c, cudaMemcpyAsync(&total, c->cellStart.p + nc, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    IDP_CK(c, cudaStreamSynchronize(c->stream));
-    IDP_CK(c, c->crec.reserve((size_t)std::max(total, 1)));
-    IDP_CK(c, c->largeList.reserve(IDP_LARGE_CAP + 1));
-    IDP_CK(c, cudaMemcpyAsync(c->cellCursor.p, c->cellStart.p, (nc + 1) * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
-    IDP_LAUNCH(c, k_cells_multi<true>, blocks_for(nB, 256), 256, 0, bbox, nB, g, dRegion, c->cellCursor.p, c->crec.p);
-    IDP_CK(c, cudaGetLastError());
-    return IDP_OK;
-}
-static int build_cells(idp_ctx* c, const IBox* bbox, const PrimRec* rec, int nB, GridDesc& g, const int latN[3], EMax* emaxOut, int* nLargeOut,
-    const IBox* qbox, int qb, int qe)
-{
-    int* dHist = (int*)c->histScratch.p; // 48 ints
-    int hist[48];
-    EMax em;
-    int emax = -1, nLarge = 0;
-    for (int attempt = 0; attempt < 12 && emax < 0; ++attempt) {
-        IDP_CK(c, cudaMemsetAsync(dHist, 0, 48 * sizeof(int), c->stream));
-        IDP_LAUNCH(c, k_extent_hist, std::min(blocks_for(nB, 256), (unsigned)c->sm_count * 8), 256, 0, bbox, nB, g, dHist);
+    int* dHist = (int*)c->histScratch.p; // 4 * IDP_LEVEL_BINS ints
+    int hist[4 * IDP_LEVEL_BINS];
+    Levels lv;
+    bool ok = false;
+    for (int attempt = 0; attempt < 16 && !ok; ++attempt) {
+        IDP_CK(c, cudaMemsetAsync(dHist, 0, sizeof(hist), c->stream));
+        IDP_LAUNCH(c, k_level_hist, std::min(blocks_for(nB, 256), (unsigned)c->sm_count * 8), 256, 0, bbox, nB, g, dHist);
         IDP_CK(c, cudaMemcpyAsync(hist, dHist, sizeof(hist), cudaMemcpyDeviceToHost, c->stream));
         IDP_CK(c, cudaStreamSynchronize(c->stream));
-        // per axis: smallest extension that leaves at most a third of the large-list budget beyond it
-        bool ok = true;
-        nLarge = 0;
-        for (int k = 0; k < 3 && ok; ++k) {
-            long above = nB;
-            em.e[k] = -1;
-            for (int e = 0; e <= 4; ++e) {
-                above -= hist[16 * k + e];
-                if (above <= IDP_LARGE_CAP / 3) { em.e[k] = e; nLarge += (int)above; break; }
-            }
-            ok = em.e[k] >= 0;
+        lv.n = 0;
+        lv.useBin1 = 1;
+        if (hist[1] > 0 && (long)hist[1] * 32 < nB && !getenv("IDP_KEEP_BIN1")) { // thin bin 1: its rows cost every query more than its records
+            lv.useBin1 = 0;
+            hist[2] += hist[1];
+            hist[1] = 0;
+            for (int k = 0; k < 3; ++k) hist[IDP_LEVEL_BINS + 6 + k] = std::max(hist[IDP_LEVEL_BINS + 6 + k], hist[IDP_LEVEL_BINS + 3 + k] ? 1 : 0);
         }
-        if (ok) { emax = 0; break; }
-        if (g.n[0] <= 1 && g.n[1] <= 1 && g.n[2] <= 1) { em.e[0] = em.e[1] = em.e[2] = 0; emax = 0; nLarge = 0; break; } // one cell holds everything
+        long off = 0;
+        ok = true;
+        for (int l = 0; l < IDP_LEVEL_BINS; ++l) {
+            lv.slot[l] = -1;
+            if (hist[l] == 0 && !(l == 0 && nB == 0)) continue;
+            if (lv.n == IDP_MAX_LEVELS) { ok = false; break; }
+            const int i = lv.n++;
+            lv.slot[l] = (signed char)i;
+            lv.shift[i] = level_shift(l);
+            for (int k = 0; k < 3; ++k) {
+                lv.ext[i][k] = hist[IDP_LEVEL_BINS + 3 * l + k];
+                lv.dim[i][k] = ((g.n[k] - 1) >> lv.shift[i]) + 1;
+            }
+            lv.off[i] = off;
+            off += (long)lv.dim[i][0] * lv.dim[i][1] * lv.dim[i][2];
+        }
+        if (lv.n == 0) { lv.n = 1; lv.slot[0] = 0; lv.shift[0] = 0; lv.off[0] = 0; for (int k = 0; k < 3; ++k) { lv.ext[0][k] = 0; lv.dim[0][k] = g.n[k]; } }
+        if (ok) break;
         g.k *= 2;
         for (int d = 0; d < 3; ++d) g.n[d] = std::max(1, (latN[d] + g.k) / g.k);
     }
-    if (emax < 0) return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "broad-phase grid could not be sized", __FILE__, __LINE__);
+    if (!ok) return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "broad-phase grid could not be sized", __FILE__, __LINE__);
+    for (int i = lv.n; i < IDP_MAX_LEVELS; ++i) { lv.shift[i] = 0; lv.off[i] = 0; for (int k = 0; k < 3; ++k) { lv.ext[i][k] = 0; lv.dim[i][k] = 1; } }
+    const int last = lv.n - 1;
+    const long ncAll = lv.off[last] + (long)lv.dim[last][0] * lv.dim[last][1] * lv.dim[last][2];
+    if (getenv("IDP_DEBUG")) {
+        fprintf(stderr, "[idp] build_cells(%s) nB=%d base grid %dx%dx%d k=%d, %d level(s):", ccd ? "ccd" : "static", nB, g.n[0], g.n[1], g.n[2], g.k, lv.n);
+        for (int l = 0; l < IDP_LEVEL_BINS; ++l)
+            if (lv.slot[l] >= 0) fprintf(stderr, " [shift=%d n=%d ext=%d%d%d]", level_shift(l), hist[l], lv.ext[lv.slot[l]][0], lv.ext[lv.slot[l]][1], lv.ext[lv.slot[l]][2]);
+        fprintf(stderr, "\n");
+    }
     int* dRegion = nullptr;
     IDP_TRY(set_query_region(c, qbox, qb, qe, g, &dRegion)); // after the grid is final (it may have been coarsened above)
-    const long nc = grid_cells(g);
-    IDP_CK(c, c->cellStart.reserve(nc + 1));
-    IDP_CK(c, c->cellCursor.reserve(nc + 1));
-    IDP_CK(c, c->largeList.reserve(IDP_LARGE_CAP + 1));
-    int* dLargeCount = (int*)c->histScratch.p + 48;
-    IDP_CK(c, cudaMemsetAsync(c->cellCursor.p, 0, (nc + 1) * sizeof(int), c->stream));
-    IDP_CK(c, cudaMemsetAsync(dLargeCount, 0, sizeof(int), c->stream));
-    IDP_LAUNCH(c, (k_cells<false>), blocks_for(nB, 256), 256, 0, bbox, rec, nB, g, em, dRegion, c->cellCursor.p, (CRec*)nullptr, (int*)nullptr, (int*)nullptr);
-    IDP_TRY(cub_scan_exclusive(c, c->cellCursor.p, c->cellStart.p, nc + 1));
-    IDP_CK(c, c->crec.reserve((size_t)std::max(nB, 1)));
-    IDP_CK(c, cudaMemcpyAsync(c->cellCursor.p, c->cellStart.p, (nc + 1) * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
-    IDP_LAUNCH(c, (k_cells<true>), blocks_for(nB, 256), 256, 0, bbox, rec, nB, g, em, dRegion, c->cellCursor.p, c->crec.p, c->largeList.p, dLargeCount);
+    IDP_CK(c, c->cellStart.reserve(ncAll + 1));
+    IDP_CK(c, c->cellCursor.reserve(ncAll + 1));
+    IDP_CK(c, cudaMemsetAsync(c->cellCursor.p, 0, (ncAll + 1) * sizeof(int), c->stream));
+    IDP_CK(c, c->crec0.reserve((size_t)std::max(nB, 1)));
+    IDP_CK(c, c->crec1.reserve((size_t)std::max(nB, 1)));
+    const unsigned grid = blocks_for(nB, 256);
+    IDP_LAUNCH(c, (k_cells<false>), grid, 256, 0, bbox, rec, nB, g, lv, dRegion, c->cellCursor.p, (int4*)nullptr, (int4*)nullptr);
+    IDP_TRY(cub_scan_exclusive(c, c->cellCursor.p, c->cellStart.p, ncAll + 1));
+    IDP_CK(c, cudaMemcpyAsync(c->cellCursor.p, c->cellStart.p, (ncAll + 1) * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+    IDP_LAUNCH(c, (k_cells<true>), grid, 256, 0, bbox, rec, nB, g, lv, dRegion, c->cellCursor.p, c->crec0.p, c->crec1.p);
     IDP_CK(c, cudaGetLastError());
-    *emaxOut = em;
-    *nLargeOut = nLarge;
+    *levelsOut = lv;
     return IDP_OK;
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// broad-phase query: one warp per query primitive.
-// The (y,z) rows of the visited cell block are contiguous runs of the cell-sorted compact records (CRec). Every lane
-// takes one run -- or one slice of a run when the block has fewer than 17 rows, so that all 32 lanes are busy -- and
-// scans it sequentially: two 16-byte loads and a handful of float / integer compares per record (the coarse filter:
-// index order, outward-rounded float AABB for the static phase; canonical cell + lattice-box overlap, both exact, for
-// CCD). Survivors are pushed to a per-warp queue in shared memory with ballot/popc; whenever 32 are waiting the whole
-// warp runs the exact predicate on them (one 64-byte PrimRec each: shared vertices, Dirichlet flags, FP64 AABB gap) and
-// appends the hits with one atomic. The exact test therefore always runs on full warps, and the scan loop stays short.
+// broad-phase query: one warp per query primitive, records streamed in FLAT order.
+// With anchor insertion the records a query must look at are the (y,z) rows of the cell block [qlo - emax, qhi]; each row
+// is one contiguous run of the cell-sorted record arrays. The warp lists the non-empty runs (one lane per row: two
+// cellStart loads), prefix-sums their lengths and then walks the concatenation of the runs 32 records at a time: lane j
+// takes flat index i + j, finds its run from a 32-bit mask of the run starts inside the chunk (one REDUX.OR + popc) and
+// reads record start[run] + (flat - offset[run]). Consecutive lanes read consecutive records, so the two 16-byte record
+// streams are coalesced and every lane is busy except in the last chunk (the first version gave every lane its own run:
+// 32 different cache lines per warp load and lanes idling on short runs -- 85x the algorithmic bytes through L1).
+// Coarse filter per record: index order, then outward-rounded float AABB (static) or lattice-box overlap (CCD, exact).
+// Survivors are pushed to a per-warp queue in shared memory with ballot/popc; whenever 32 are waiting the whole warp runs
+// the exact predicate on them (one 64-byte PrimRec each: shared vertices, Dirichlet flags, FP64 AABB gap) and appends the
+// hits with one atomic. Every pair is met exactly once, so there is no de-duplication.
 // MODE bit0: 0 = point queries vs triangles, 1 = edge queries vs edges (partner index > query index);
-// MODE bit1: CCD (multi insertion; require lattice-box overlap = "shares a voxel" of the reference's hash)
+// MODE bit1: CCD (lattice-box overlap = "shares a voxel" of the reference's hash; swept AABBs)
 // ------------------------------------------------------------------------------------------------------------
 struct QueryArgs {
     const PrimRec* qrec; const IBox* qbox; int qBegin, qEnd;
     const PrimRec* brec; const IBox* bbox;
-    const int* cellStart; const CRec* crec;
+    const int* cellStart; const int4* rec0; const int4* rec1;
     GridDesc g;
     double dist; // dHat (static) or thickness (CCD)
-    EMax emax; const int* large; const int* nLargePtr; // device count of the large list
+    Levels lv;
     int2* out; long cap; unsigned long long* counter;
 };
 // exact predicate on a (query, partner) pair that passed the coarse filter (IPC.h:171-172, 384-385; CCD.h:149-235)
 template <int MODE>
-__device__ __forceinline__ bool pair_exact(const QueryArgs& a, int b, const PrimRec& qr, const V3& qL, const V3& qH)
+__device__ __forceinline__ bool pair_exact(const QueryArgs& a, int b, const IBox& qb, const PrimRec& qr, const V3& qL, const V3& qH)
 {
     const PrimRec br = a.brec[b];
     bool ok;
+    if (MODE & 2) { // the reference's CCD hash only pairs primitives that share a voxel: lattice boxes of the alpha-scaled sweeps overlap
+        const IBox bb = a.bbox[b];
+        if (!(qb.lo[0] <= bb.hi[0] && bb.lo[0] <= qb.hi[0] && qb.lo[1] <= bb.hi[1] && bb.lo[1] <= qb.hi[1] && qb.lo[2] <= bb.hi[2] && bb.lo[2] <= qb.hi[2]))
+            return false;
+    }
     if (MODE & 1) ok = !(qr.v[0] == br.v[0] || qr.v[0] == br.v[1] || qr.v[1] == br.v[0] || qr.v[1] == br.v[1]); // shared vertex (IPC.h:384)
     else ok = !(qr.v[0] == br.v[0] || qr.v[0] == br.v[1] || qr.v[0] == br.v[2]);                                   // incident triangle (IPC.h:171)
     ok = ok && !((qr.flags & 1) && (br.flags & 1));                                                                  // all Dirichlet (:172, :385)
     return ok && aabb_gap_ok(qL, qH, mk3(br.lo[0], br.lo[1], br.lo[2]), mk3(br.hi[0], br.hi[1], br.hi[2]), a.dist);
 }
-// large-list entries (static phase only): index order + exact predicate
-template <int MODE>
-__device__ __forceinline__ bool pair_large(const QueryArgs& a, long q, int b, const PrimRec& qr, const V3& qL, const V3& qH)
-{
-    if ((MODE & 1) && b <= (int)q) return false; // eJ > eI (IPC.h:384, SPATIAL_HASH.h:265)
-    return pair_exact<MODE>(a, b, qr, qL, qH);
-}
 #define IDP_QUERY_WARPS 8
+// per-warp table of the rows a query visits, one entry per active level
+struct LevelRows { int rowEnd; int x0, x1, y0, ny, z0; int nx, nyDim; long off; };
 template <int MODE>
 __global__ void __launch_bounds__(32 * IDP_QUERY_WARPS) k_query(QueryArgs a)
 {
-    __shared__ int squeue[IDP_QUERY_WARPS][64];
+    __shared__ int squeue[IDP_QUERY_WARPS][96];
+    __shared__ int2 sruns[IDP_QUERY_WARPS][32];
+    __shared__ LevelRows slev[IDP_QUERY_WARPS][IDP_MAX_LEVELS];
     const int wib = threadIdx.x >> 5;
     const long warp0 = (long)blockIdx.x * IDP_QUERY_WARPS + wib;
     const long nWarps = (long)gridDim.x * IDP_QUERY_WARPS;
     const int lane = lane_id();
-    const unsigned lt = (1u << lane) - 1u;
+    const unsigned lt = (1u << lane) - 1u, le = lt | (1u << lane);
     int* sq = squeue[wib];
+    int2* sr = sruns[wib];
+    LevelRows* sl = slev[wib];
+    const int nLev = a.lv.n;
     for (long q = a.qBegin + warp0; q < a.qEnd; q += nWarps) {
         const PrimRec qr = a.qrec[q];
         const IBox qb = a.qbox[q];
-        int qlo[3], qhi[3];
-        cell_range(a.g, qb, qlo, qhi);
-        int clo[3]; // cell-space low corner of the query box (canonical-cell rule of the multi insertion)
-#pragma unroll
-        for (int k = 0; k < 3; ++k) { clo[k] = qlo[k]; qlo[k] = max(qlo[k] - a.emax.e[k], 0); }
+        int qlo0[3], qhi0[3];
+        cell_range(a.g, qb, qlo0, qhi0);
         const V3 qL = mk3(qr.lo[0], qr.lo[1], qr.lo[2]), qH = mk3(qr.hi[0], qr.hi[1], qr.hi[2]);
         // coarse float thresholds: a record is dropped only if its outward-rounded box lies beyond qL - dist - eps (or
         // qH + dist + eps) on some axis, which implies the exact FP64 gap test (aabb_gap_ok) fails too
         float loT[3], hiT[3];
-        if (!(MODE & 2)) {
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const double eps = 1e-12 * (fabs(qr.lo[k]) + fabs(qr.hi[k]) + a.dist) + 1e-300;
-                loT[k] = __double2float_rd(qr.lo[k] - a.dist - eps);
-                hiT[k] = __double2float_ru(qr.hi[k] + a.dist + eps);
-            }
+        for (int k = 0; k < 3; ++k) {
+            const double eps = 1e-12 * (fabs(qr.lo[k]) + fabs(qr.hi[k]) + a.dist) + 1e-300;
+            loT[k] = __double2float_rd(qr.lo[k] - a.dist - eps);
+            hiT[k] = __double2float_ru(qr.hi[k] + a.dist + eps);
         }
-        int nq = 0; // survivors waiting in the queue (warp-uniform)
-        const int ny = qhi[1] - qlo[1] + 1, nRows = ny * (qhi[2] - qlo[2] + 1);
-        int lg = 0; // 2^lg slices per run
-        while (lg < 3 && (nRows << (lg + 1)) <= 32) ++lg;
-        const int rowsPerBatch = 32 >> lg;
-        for (int rbase = 0; rbase < nRows; rbase += rowsPerBatch) {
-            const int r = rbase + (lane >> lg), sl = lane & ((1 << lg) - 1);
-            int my = 0, iy = 0, iz = 0;
-            long first = 0;
-            if (r < nRows) {
-                const int rz = r / ny;
-                iy = qlo[1] + (r - rz * ny); iz = qlo[2] + rz;
-                const long row = ((long)iz * a.g.n[1] + iy) * a.g.n[0];
-                const int start = a.cellStart[row + qlo[0]];
-                const int len = a.cellStart[row + qhi[0] + 1] - start;
-                const int slen = (len + (1 << lg) - 1) >> lg;
-                first = start + (long)sl * slen;
-                my = max(0, min(slen, len - sl * slen));
-            }
-            const int maxLen = __reduce_max_sync(0xffffffffu, my);
-            for (int k = 0; k < maxLen; ++k) {
-                bool cand = false;
-                int b = -1;
-                if (k < my) {
-                    const int4* rp = reinterpret_cast<const int4*>(a.crec + first + k);
-                    const int4 w0 = __ldg(rp), w1 = __ldg(rp + 1); // box[0..3] | box[4], box[5], b, aux
-                    b = w1.z;
-                    cand = !(MODE & 1) || b > (int)q; // eJ > eI (IPC.h:384, SPATIAL_HASH.h:265)
-                    if (MODE & 2) {
-                        // canonical cell of the pair: componentwise max of the two low corners (every pair is met once)
-                        const int bl[3] = {w0.x, w0.y, w0.z}, bh[3] = {w0.w, w1.x, w1.y};
-                        int cl[3];
+        // lane l < nLev describes level l: the block of cells [qlo - ext, qhi] in level cells, rows = (y, z) pairs
+        int myRows = 0;
+        LevelRows lr;
+        if (lane < nLev) {
+            const int sh = a.lv.shift[lane];
+            lr.x0 = max((qlo0[0] >> sh) - a.lv.ext[lane][0], 0); lr.x1 = qhi0[0] >> sh;
+            lr.y0 = max((qlo0[1] >> sh) - a.lv.ext[lane][1], 0); lr.ny = (qhi0[1] >> sh) - lr.y0 + 1;
+            lr.z0 = max((qlo0[2] >> sh) - a.lv.ext[lane][2], 0);
+            lr.nx = a.lv.dim[lane][0]; lr.nyDim = a.lv.dim[lane][1]; lr.off = a.lv.off[lane];
+            myRows = lr.ny * ((qhi0[2] >> sh) - lr.z0 + 1);
+        }
+        int rowEnd = myRows; // inclusive prefix over the levels
 #pragma unroll
-                        for (int d = 0; d < 3; ++d) cl[d] = clampi(a.g.k == 1 ? bl[d] : bl[d] / a.g.k, 0, a.g.n[d] - 1);
-                        cand = cand && max(clo[0], cl[0]) == w1.w && max(clo[1], cl[1]) == iy && max(clo[2], cl[2]) == iz;
-                        cand = cand && qb.lo[0] <= bh[0] && bl[0] <= qb.hi[0] && qb.lo[1] <= bh[1] && bl[1] <= qb.hi[1] &&
-                               qb.lo[2] <= bh[2] && bl[2] <= qb.hi[2];
-                    }
-                    else {
-                        const float fl0 = __int_as_float(w0.x), fl1 = __int_as_float(w0.y), fl2 = __int_as_float(w0.z);
-                        const float fh0 = __int_as_float(w0.w), fh1 = __int_as_float(w1.x), fh2 = __int_as_float(w1.y);
-                        cand = cand && !(fh0 < loT[0] || fh1 < loT[1] || fh2 < loT[2] || fl0 > hiT[0] || fl1 > hiT[1] || fl2 > hiT[2]);
-                    }
+        for (int o = 1; o < IDP_MAX_LEVELS; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, rowEnd, o);
+            if (lane >= o) rowEnd += t;
+        }
+        const int nRows = __shfl_sync(0xffffffffu, rowEnd, nLev - 1);
+        __syncwarp();
+        if (lane < nLev) { lr.rowEnd = rowEnd; sl[lane] = lr; }
+        __syncwarp();
+        int nq = 0; // survivors waiting in the queue (warp-uniform)
+        for (int rbase = 0; rbase < nRows; rbase += 32) {
+            // one lane per row: its run of records (rows of all levels in one list)
+            const int r = rbase + lane;
+            int start = 0, len = 0;
+            if (r < nRows) {
+                int L = 0;
+                while (r >= sl[L].rowEnd) ++L;
+                const LevelRows v = sl[L];
+                const int rr = r - (L ? sl[L - 1].rowEnd : 0);
+                const int rz = rr / v.ny;
+                const int* cs = a.cellStart + v.off + ((long)(v.z0 + rz) * v.nyDim + (v.y0 + (rr - rz * v.ny))) * v.nx;
+                start = __ldg(cs + v.x0);
+                len = __ldg(cs + v.x1 + 1) - start;
+            }
+            int off = len; // inclusive prefix sum of the run lengths
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, off, o);
+                if (lane >= o) off += t;
+            }
+            const int total = __shfl_sync(0xffffffffu, off, 31);
+            off -= len; // exclusive
+            const unsigned ne = __ballot_sync(0xffffffffu, len > 0);
+            __syncwarp();
+            if (len > 0) sr[__popc(ne & lt)] = make_int2(start, off); // non-empty runs, offsets strictly increasing
+            __syncwarp();
+            int runsBefore = 0;
+            for (int i = 0; i < total; i += 64) { // 64 records per trip: two per lane, four 16-byte loads in flight
+                const unsigned bit = len > 0 ? (unsigned)(off - i) : 64u;
+                const unsigned m0 = __reduce_or_sync(0xffffffffu, bit < 32u ? (1u << bit) : 0u);
+                const unsigned m1 = __reduce_or_sync(0xffffffffu, (bit >= 32u && bit < 64u) ? (1u << (bit - 32u)) : 0u);
+                const int f0 = i + lane, f1 = f0 + 32;
+                int4 w0 = make_int4(0, 0, 0, 0), w1 = w0, w2 = w0, w3 = w0;
+                if (f0 < total) {
+                    const int2 run = sr[runsBefore + __popc(m0 & le) - 1];
+                    const int rec = run.x + (f0 - run.y);
+                    w0 = __ldg(a.rec0 + rec); w1 = __ldg(a.rec1 + rec); // lo.xyz hi.x | hi.y hi.z b 0
                 }
-                const unsigned m = __ballot_sync(0xffffffffu, cand);
-                if (m) {
-                    if (cand) sq[nq + __popc(m & lt)] = b;
-                    nq += __popc(m);
-                    if (nq >= 32) { // a full warp of survivors: exact predicate, append
+                if (f1 < total) {
+                    const int2 run = sr[runsBefore + __popc(m0) + __popc(m1 & le) - 1];
+                    const int rec = run.x + (f1 - run.y);
+                    w2 = __ldg(a.rec0 + rec); w3 = __ldg(a.rec1 + rec);
+                }
+                runsBefore += __popc(m0) + __popc(m1);
+                bool c0 = f0 < total && (!(MODE & 1) || w1.z > (int)q); // eJ > eI (IPC.h:384, SPATIAL_HASH.h:265)
+                bool c1 = f1 < total && (!(MODE & 1) || w3.z > (int)q);
+                c0 = c0 && !(__int_as_float(w0.w) < loT[0] || __int_as_float(w1.x) < loT[1] || __int_as_float(w1.y) < loT[2] ||
+                             __int_as_float(w0.x) > hiT[0] || __int_as_float(w0.y) > hiT[1] || __int_as_float(w0.z) > hiT[2]);
+                c1 = c1 && !(__int_as_float(w2.w) < loT[0] || __int_as_float(w3.x) < loT[1] || __int_as_float(w3.y) < loT[2] ||
+                             __int_as_float(w2.x) > hiT[0] || __int_as_float(w2.y) > hiT[1] || __int_as_float(w2.z) > hiT[2]);
+                const unsigned b0 = __ballot_sync(0xffffffffu, c0), b1 = __ballot_sync(0xffffffffu, c1);
+                if (b0 | b1) {
+                    if (c0) sq[nq + __popc(b0 & lt)] = w1.z;
+                    if (c1) sq[nq + __popc(b0) + __popc(b1 & lt)] = w3.z;
+                    nq += __popc(b0) + __popc(b1);
+                    while (nq >= 32) { // a full warp of survivors: exact predicate, append
                         __syncwarp();
-                        const int bb = sq[lane];
-                        const bool hit = pair_exact<MODE>(a, bb, qr, qL, qH);
+                        const int bb = sq[nq - 32 + lane];
+                        const bool hit = pair_exact<MODE>(a, bb, qb, qr, qL, qH);
                         const long slot = warp_append(hit, a.counter, a.cap);
                         if (hit && slot >= 0) a.out[slot] = make_int2((int)q, bb);
-                        const int rest = (lane < nq - 32) ? sq[32 + lane] : 0;
-                        __syncwarp();
-                        if (lane < nq - 32) sq[lane] = rest;
                         nq -= 32;
-                        __syncwarp();
                     }
+                    __syncwarp();
                 }
             }
         }
         if (nq > 0) { // remaining survivors
             __syncwarp();
             const int bb = lane < nq ? sq[lane] : -1;
-            const bool hit = lane < nq && pair_exact<MODE>(a, bb, qr, qL, qH);
+            const bool hit = lane < nq && pair_exact<MODE>(a, bb, qb, qr, qL, qH);
             const long slot = warp_append(hit, a.counter, a.cap);
             if (hit && slot >= 0) a.out[slot] = make_int2((int)q, bb);
             __syncwarp();
-        }
-        const int nLarge = *a.nLargePtr;
-        for (int l0 = 0; l0 < nLarge; l0 += 32) { // primitives too large for anchor insertion
-            bool hit = false;
-            int b = -1;
-            if (l0 + lane < nLarge) {
-                b = a.large[l0 + lane];
-                hit = pair_large<MODE>(a, q, b, qr, qL, qH);
-            }
-            const long slot = warp_append(hit, a.counter, a.cap);
-            if (hit && slot >= 0) a.out[slot] = make_int2((int)q, b);
         }
     }
 }
@@ -1017,13 +1033,13 @@ int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
     const int dupBits = (3 * vbits <= 64 && !getenv("IDP_FORCE_ROW_MERGE")) ? vbits : 0;
     {
         StageTimer tm(c, IDP_STAGE_CCS_PT);
-        EMax emax; int nLarge = 0;
+        Levels lv;
         shard_range(c, c->nBN, &qb, &qe);
-        IDP_TRY(build_cells(c, c->boxTb.p, c->recT.p, c->nBT, g, latN, &emax, &nLarge, c->boxNq.p, qb, qe));
+        IDP_TRY(build_cells(c, c->boxTb.p, c->recT.p, c->nBT, g, latN, &lv, c->boxNq.p, qb, qe, false));
         QueryArgs qa;
         qa.qrec = c->recN.p; qa.qbox = c->boxNq.p; qa.qBegin = qb; qa.qEnd = qe;
-        qa.brec = c->recT.p; qa.bbox = c->boxTb.p; qa.cellStart = c->cellStart.p; qa.crec = c->crec.p;
-        qa.g = g; qa.dist = dHat; qa.emax = emax; qa.large = c->largeList.p; qa.nLargePtr = (const int*)c->histScratch.p + 48;
+        qa.brec = c->recT.p; qa.bbox = c->boxTb.p; qa.cellStart = c->cellStart.p; qa.rec0 = c->crec0.p; qa.rec1 = c->crec1.p;
+        qa.g = g; qa.dist = dHat; qa.lv = lv;
         IDP_TRY(run_query<0>(c, qa, c->candPT, &c->nCandPT));
         // classification
         IDP_CK(c, c->rowsA.reserve(std::max<long>(c->nCandPT, 1)));
@@ -1049,13 +1065,13 @@ int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
     long nB = 0, nD = 0;
     {
         StageTimer tm(c, IDP_STAGE_CCS_EE);
-        EMax emax; int nLarge = 0;
+        Levels lv;
         shard_range(c, c->nBE, &qb, &qe);
-        IDP_TRY(build_cells(c, c->boxEb.p, c->recE.p, c->nBE, g, latN, &emax, &nLarge, c->boxEq.p, qb, qe));
+        IDP_TRY(build_cells(c, c->boxEb.p, c->recE.p, c->nBE, g, latN, &lv, c->boxEq.p, qb, qe, false));
         QueryArgs qa;
         qa.qrec = c->recE.p; qa.qbox = c->boxEq.p; qa.qBegin = qb; qa.qEnd = qe;
-        qa.brec = c->recE.p; qa.bbox = c->boxEb.p; qa.cellStart = c->cellStart.p; qa.crec = c->crec.p;
-        qa.g = g; qa.dist = dHat; qa.emax = emax; qa.large = c->largeList.p; qa.nLargePtr = (const int*)c->histScratch.p + 48;
+        qa.brec = c->recE.p; qa.bbox = c->boxEb.p; qa.cellStart = c->cellStart.p; qa.rec0 = c->crec0.p; qa.rec1 = c->crec1.p;
+        qa.g = g; qa.dist = dHat; qa.lv = lv;
         IDP_TRY(run_query<1>(c, qa, c->candEE, &c->nCandEE));
         IDP_CK(c, c->rowsB.reserve(std::max<long>(c->nCandEE, 1)));
         if (!dupBits) IDP_CK(c, c->rowsD.reserve(std::max<long>(nD_pt + c->nCandEE, 1), true, c->stream));
@@ -1441,13 +1457,13 @@ int ccd_step(idp_ctx* c, double thickness, double* alpha_inout, int keep_candida
     int qb, qe;
     {
         StageTimer tm(c, IDP_STAGE_CCD_PT);
-        EMax emax = {{0, 0, 0}};
+        Levels lv;
         shard_range(c, c->nBN, &qb, &qe);
-        IDP_TRY(build_cells_multi(c, c->boxTb.p, c->nBT, g, c->boxNq.p, qb, qe));
+        IDP_TRY(build_cells(c, c->boxTb.p, c->recT.p, c->nBT, g, latN, &lv, c->boxNq.p, qb, qe, true));
         QueryArgs qa;
         qa.qrec = c->recN.p; qa.qbox = c->boxNq.p; qa.qBegin = qb; qa.qEnd = qe;
-        qa.brec = c->recT.p; qa.bbox = c->boxTb.p; qa.cellStart = c->cellStart.p; qa.crec = c->crec.p;
-        qa.g = g; qa.dist = thickness; qa.emax = emax; qa.large = c->largeList.p; qa.nLargePtr = (const int*)c->histScratch.p + 48;
+        qa.brec = c->recT.p; qa.bbox = c->boxTb.p; qa.cellStart = c->cellStart.p; qa.rec0 = c->crec0.p; qa.rec1 = c->crec1.p;
+        qa.g = g; qa.dist = thickness; qa.lv = lv;
         IDP_TRY(run_query<2>(c, qa, c->candPT, &c->nCcdPT));
         aa.cand = c->candPT.p; aa.nCand = c->nCcdPT;
         if (c->nCcdPT > 0) IDP_LAUNCH(c, k_accd<0>, std::min(blocks_for(c->nCcdPT, 128), (unsigned)c->sm_count * 32), 128, 0, aa);
@@ -1455,13 +1471,13 @@ int ccd_step(idp_ctx* c, double thickness, double* alpha_inout, int keep_candida
     }
     {
         StageTimer tm(c, IDP_STAGE_CCD_EE);
-        EMax emax = {{0, 0, 0}};
+        Levels lv;
         shard_range(c, c->nBE, &qb, &qe);
-        IDP_TRY(build_cells_multi(c, c->boxEb.p, c->nBE, g, c->boxEb.p, qb, qe));
+        IDP_TRY(build_cells(c, c->boxEb.p, c->recE.p, c->nBE, g, latN, &lv, c->boxEb.p, qb, qe, true));
         QueryArgs qa;
         qa.qrec = c->recE.p; qa.qbox = c->boxEb.p; qa.qBegin = qb; qa.qEnd = qe;
-        qa.brec = c->recE.p; qa.bbox = c->boxEb.p; qa.cellStart = c->cellStart.p; qa.crec = c->crec.p;
-        qa.g = g; qa.dist = thickness; qa.emax = emax; qa.large = c->largeList.p; qa.nLargePtr = (const int*)c->histScratch.p + 48;
+        qa.brec = c->recE.p; qa.bbox = c->boxEb.p; qa.cellStart = c->cellStart.p; qa.rec0 = c->crec0.p; qa.rec1 = c->crec1.p;
+        qa.g = g; qa.dist = thickness; qa.lv = lv;
         IDP_TRY(run_query<3>(c, qa, c->candEE, &c->nCcdEE));
         aa.cand = c->candEE.p; aa.nCand = c->nCcdEE;
         if (c->nCcdEE > 0) {

@@ -113,6 +113,8 @@ int idp_get_hessian_csr(idp_ctx* ctx, int* ptr, int* col, double* val);
 /* device pointers (valid until the next idp_barrier_hessian / idp_barrier_all on this context) */
 int idp_hessian_csr_device(idp_ctx* ctx, const int** d_ptr, const int** d_col, const double** d_val, long* nnz);
 int idp_gradient_device(idp_ctx* ctx, const double** d_g_xyz);
+/* g_accum[v*stride + a] += the gradient of the last idp_barrier_gradient / idp_barrier_all (sharded: the all-reduced one) */
+int idp_get_gradient(idp_ctx* ctx, double* g_accum, int stride);
 
 /* ---- Compute_Intersection_Free_StepSize (FEM/IPC.h:1879-2244) ---------------------------------------------- */
 /* searchDir: nV rows x 3 doubles (std::vector<T>, stride 3 in the reference). alpha is in/out and includes the

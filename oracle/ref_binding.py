@@ -121,7 +121,7 @@ class ReferenceIPC:
         X, X0 = np.ascontiguousarray(m.X, np.float64), np.ascontiguousarray(m.X0, np.float64)
         rows = np.ascontiguousarray(rows, np.int32); w = np.ascontiguousarray(weights, np.float64)
         E = C.c_double(0.0); g = np.zeros((len(X), 3))
-        cap = 144 * len(rows) + 1
+        cap = 144 * len(rows) + 1 if want_h else 1
         tr = np.zeros(cap, np.int32); tc = np.zeros(cap, np.int32); tv = np.zeros(cap)
         nt = self.lib.refipc_barrier(len(X), _p(X), _p(X0), len(rows), _p(rows), _p(w), dHat2, kappa, thickness, int(project_spd), C.byref(E), _p(g),
                                      cap, _p(tr) if want_h else None, _p(tc) if want_h else None, _p(tv) if want_h else None)

@@ -49,6 +49,29 @@ def config5_mesh(nx, ny, extent):
     return m, d, h
 
 
+def count_vertex_pairs(rows, nV):
+    """Number of distinct ordered vertex pairs (vi, vj) that appear together in a row = block non-zeros of the Hessian."""
+    r = rows.astype(np.int64)
+    v = np.where(r < 0, -r - 1, r)             # decoded vertex ids; -1 (unused slot) decodes to 0 and is masked below
+    used = np.ones(r.shape, bool)
+    plain = r[:, 0] < 0                         # PT / PE / PP rows: slots holding -1 are unused (PE: slot 3, PP: slots 2, 3)
+    used[plain, 3] = r[plain, 3] >= 0
+    used[plain, 2] = r[plain, 2] >= 0
+    chunks = []
+    for c0 in range(0, len(r), 4000000):
+        vv, uu = v[c0:c0 + 4000000], used[c0:c0 + 4000000]
+        keys = []
+        for i in range(4):
+            for j in range(i, 4):
+                ok = uu[:, i] & uu[:, j]
+                lo = np.minimum(vv[ok, i], vv[ok, j]); hi = np.maximum(vv[ok, i], vv[ok, j])
+                keys.append(lo * nV + hi)
+        chunks.append(np.unique(np.concatenate(keys)))
+    allk = np.unique(np.concatenate(chunks))
+    diag = int(((allk // nV) == (allk % nV)).sum())
+    return 2 * (len(allk) - diag) + diag
+
+
 def static_and_ccd(name, m, d, dhat, out, log):
     from oracle import ref_binding
     from oracle.binding import Oracle
@@ -67,6 +90,17 @@ def static_and_ccd(name, m, d, dhat, out, log):
     rec["min_dist2"] = float(mn)
     rec["info_all"] = [float(info[0, 0]), float(info[0, 1])] if len(info) and (info == info[0]).all() else None
     log("%s reference min dist: %.17g, %.0f s" % (name, mn, time.time() - t0))
+    # barrier energy and gradient of the whole set through the reference's Compute_Barrier / _Gradient (kappa = 1e5, the
+    # bench's), and the size of the Hessian pattern (9 x number of distinct ordered vertex pairs that share a row)
+    t0 = time.time()
+    E, g, _ = ref.barrier(m, rows, info[:, 0], dhat * dhat, 1e5, want_h=False)
+    rec["barrier"] = {"kappa": 1e5, "E_reference": float(E), "g_l2": float(np.linalg.norm(g)), "g_l1": float(np.abs(g).sum()),
+                      "g_sample_index": [int(i) for i in np.linspace(0, m.nV - 1, 64).astype(np.int64)],
+                      "g_sample": [[float(x) for x in g[i]] for i in np.linspace(0, m.nV - 1, 64).astype(np.int64)]}
+    log("%s reference E = %.17g, |g| = %.17g, %.0f s" % (name, E, rec["barrier"]["g_l2"], time.time() - t0))
+    t0 = time.time()
+    rec["barrier"]["nnz"] = int(9 * count_vertex_pairs(rows, m.nV))
+    log("%s Hessian pattern nnz = %d, %.0f s" % (name, rec["barrier"]["nnz"], time.time() - t0))
     t0 = time.time()
     h = quiet()
     a = ref.ccd(m, d, 1.0, 0.0)
