@@ -410,27 +410,134 @@ __device__ __forceinline__ void reduce_sorted_bucket(const ReduceArgs& a, int v,
     if (tid == 0) a.uCount[v] = U;
     sync();
 }
-#define IDP_REDUCE_WARPS 4
-#define IDP_REDUCE_CAP 512 // bucket entries a warp sorts in shared memory
+#define IDP_REDUCE_WARPS 8
+#define IDP_REDUCE_CAP 512 // bucket entries a warp sorts in registers (16 per lane)
+// Warp-level bitonic sort of 32 E (key, payload) pairs held E per lane (element index = lane * E + r): the stages with
+// partner distance < E are compare-exchanges between registers of one lane, the others exchange with lane ^ (distance / E)
+// through shuffles. Fully unrolled: every register index is static.
+// branch-free selects (the compiler turned the 64-bit ternaries of the network into divergent branches)
+__device__ __forceinline__ unsigned long long selp64(bool p, unsigned long long a, unsigned long long b)
+{
+    unsigned long long r;
+    asm("{ .reg .pred q; setp.ne.u32 q, %3, 0; selp.b64 %0, %1, %2, q; }" : "=l"(r) : "l"(a), "l"(b), "r"((unsigned)p));
+    return r;
+}
+__device__ __forceinline__ unsigned selp32(bool p, unsigned a, unsigned b)
+{
+    unsigned r;
+    asm("{ .reg .pred q; setp.ne.u32 q, %3, 0; selp.b32 %0, %1, %2, q; }" : "=r"(r) : "r"(a), "r"(b), "r"((unsigned)p));
+    return r;
+}
+template <int E>
+__device__ __forceinline__ void warp_bitonic_sort(unsigned long long (&key)[E], unsigned (&pay)[E], int lane)
+{
+#pragma unroll
+    for (int k = 2; k <= 32 * E; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j < E) {
+#pragma unroll
+                for (int r = 0; r < E; ++r) {
+                    const int p = r ^ j;
+                    if (p > r) {
+                        const bool asc = k < E ? ((r & k) == 0) : ((lane & (k / E)) == 0); // direction of the block of k elements
+                        const bool sw = (key[r] > key[p]) == asc;
+                        const unsigned long long ka = key[r], kb = key[p];
+                        const unsigned pa = pay[r], pb = pay[p];
+                        key[r] = selp64(sw, kb, ka); key[p] = selp64(sw, ka, kb);
+                        pay[r] = selp32(sw, pb, pa); pay[p] = selp32(sw, pa, pb);
+                    }
+                }
+            }
+            else {
+                const int lj = j / E;
+                const bool lower = (lane & lj) == 0;
+                const bool asc = (lane & (k / E)) == 0; // k >= 2 j >= 2 E here
+                const bool keepMin = lower == asc;
+#pragma unroll
+                for (int r = 0; r < E; ++r) {
+                    const unsigned long long ok = __shfl_xor_sync(0xffffffffu, key[r], lj);
+                    const unsigned op = __shfl_xor_sync(0xffffffffu, pay[r], lj);
+                    const bool take = (ok < key[r]) == keepMin && ok != key[r];
+                    key[r] = selp64(take, ok, key[r]);
+                    pay[r] = selp32(take, op, pay[r]);
+                }
+            }
+        }
+    }
+}
+// one vertex: sort its bucket by (vhi, origin), find the unique upper neighbours, sum the duplicates in origin order
+template <int E>
+__device__ __forceinline__ void vertex_reduce_warp(const ReduceArgs& a, int v, int off, int n, int lane, unsigned short* sPay, unsigned short* sStart)
+{
+    unsigned long long key[E];
+    unsigned pay[E];
+#pragma unroll
+    for (int r = 0; r < E; ++r) {
+        const int e = lane * E + r;
+        key[r] = e < n ? a.bktKey[off + e] : ~0ull; // padding sorts to the end
+        pay[r] = (unsigned)e;
+    }
+    warp_bitonic_sort<E>(key, pay, lane);
+    // heads of the runs of equal vhi
+    const unsigned prevLast = __shfl_up_sync(0xffffffffu, (unsigned)(key[E - 1] >> 32), 1);
+    unsigned heads = 0;
+#pragma unroll
+    for (int r = 0; r < E; ++r) {
+        const int e = lane * E + r;
+        const unsigned vj = (unsigned)(key[r] >> 32), pv = r ? (unsigned)(key[r - 1] >> 32) : prevLast;
+        if (e < n && (e == 0 || vj != pv)) heads |= 1u << r;
+        if (e < n) sPay[e] = (unsigned short)pay[r];
+    }
+    int base = __popc(heads); // exclusive prefix of the head counts over the lanes
+    const int mine = base;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, base, o);
+        if (lane >= o) base += t;
+    }
+    const int U = __shfl_sync(0xffffffffu, base, 31);
+    base -= mine;
+#pragma unroll
+    for (int r = 0; r < E; ++r) {
+        if (heads & (1u << r)) {
+            const int u = base + __popc(heads & ((1u << r) - 1u));
+            const int vj = (int)(unsigned)(key[r] >> 32);
+            sStart[u] = (unsigned short)(lane * E + r);
+            a.uCol[off + u] = vj;
+            if (vj != v) atomicAdd(&a.lowerCount[vj], 1);
+        }
+    }
+    if (lane == 0) a.uCount[v] = U;
+    __syncwarp();
+    for (int t = lane; t < 9 * U; t += 32) {
+        const int u = t / 9, comp = t - 9 * u;
+        const int s0 = sStart[u], s1 = (u + 1 < U) ? (int)sStart[u + 1] : n;
+        const double* src = comp < 8 ? a.bktVal8 + 8 * (long)off + comp : a.bktVal1 + off;
+        const int stride = comp < 8 ? 8 : 1;
+        double sum = 0;
+        int p = s0;
+        for (; p + 4 <= s1; p += 4) { // four loads in flight; the additions stay in origin order
+            const double x0 = src[(long)stride * sPay[p]], x1 = src[(long)stride * sPay[p + 1]], x2 = src[(long)stride * sPay[p + 2]], x3 = src[(long)stride * sPay[p + 3]];
+            sum = (((sum + x0) + x1) + x2) + x3;
+        }
+        for (; p < s1; ++p) sum += src[(long)stride * sPay[p]];
+        a.uVal[9 * ((long)off + u) + comp] = sum;
+    }
+    __syncwarp();
+}
 __global__ void __launch_bounds__(32 * IDP_REDUCE_WARPS) k_vertex_reduce(ReduceArgs a)
 {
-    __shared__ unsigned long long sKey[IDP_REDUCE_WARPS][IDP_REDUCE_CAP];
-    __shared__ unsigned sPay[IDP_REDUCE_WARPS][IDP_REDUCE_CAP];
-    __shared__ unsigned sStart[IDP_REDUCE_WARPS][IDP_REDUCE_CAP];
-    __shared__ int sCnt[IDP_REDUCE_WARPS];
+    __shared__ unsigned short sPay[IDP_REDUCE_WARPS][IDP_REDUCE_CAP];
+    __shared__ unsigned short sStart[IDP_REDUCE_WARPS][IDP_REDUCE_CAP];
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    auto sync = [] { __syncwarp(); };
     for (int v = blockIdx.x * IDP_REDUCE_WARPS + wib; v < a.nV; v += gridDim.x * IDP_REDUCE_WARPS) {
         const int off = a.vtxOff[v], n = a.vtxOff[v + 1] - off;
         if (n == 0) { if (lane == 0) a.uCount[v] = 0; continue; }
-        if (n > IDP_REDUCE_CAP) {
-            if (lane == 0) { a.bigList[atomicAdd(a.bigCount, 1)] = v; a.uCount[v] = 0; }
-            continue;
-        }
-        for (int p = lane; p < n; p += 32) { sKey[wib][p] = a.bktKey[off + p]; sPay[wib][p] = (unsigned)p; }
-        __syncwarp();
-        bitonic_sort_kp(sKey[wib], sPay[wib], n, lane, 32, sync);
-        reduce_sorted_bucket(a, v, off, n, sKey[wib], sPay[wib], sStart[wib], lane, 32, &sCnt[wib], sync);
+        if (n <= 128) vertex_reduce_warp<4>(a, v, off, n, lane, sPay[wib], sStart[wib]);
+        else if (n <= 256) vertex_reduce_warp<8>(a, v, off, n, lane, sPay[wib], sStart[wib]);
+        else if (n <= IDP_REDUCE_CAP) vertex_reduce_warp<16>(a, v, off, n, lane, sPay[wib], sStart[wib]);
+        else if (lane == 0) { a.bigList[atomicAdd(a.bigCount, 1)] = v; a.uCount[v] = 0; }
     }
 }
 // oversized buckets: one CTA per vertex, the same network on global scratch (correct for any size; only pathological

@@ -347,3 +347,39 @@ def test_row_merge_fallback_for_large_vertex_counts(lib_built, orc, cases, monke
             assert np.array_equal(rows[dup], orows[(orows[:, 0] < 0) & (orows[:, 3] < 0)]), name
     finally:
         ctx.close()
+
+
+def test_hessian_assembly_bucket_sizes(lib_built, orc):
+    """The CSR assembly reduces the 3x3 blocks per lower vertex: buckets of <= 128 / 256 / 512 entries are sorted in
+    registers by one warp, larger ones by one CTA in global scratch. A 'star' of point-point and point-edge rows around a few
+    hub vertices drives every path (hub 0: ~4000 entries, hubs 1-3: 100-500) and is compared with the oracle's CSR; the
+    result must also be bit-identical from run to run (duplicates are summed in origin order, not in arrival order)."""
+    from idp_b200 import ContactContext
+    rng = np.random.default_rng(17)
+    nV = 3000
+    X = rng.uniform(-1, 1, (nV, 3))
+    X[:4] = [[0, 0, 0], [5, 0, 0], [0, 5, 0], [0, 0, 5]]
+    rows = []
+    for hub, cnt in ((0, 2000), (1, 230), (2, 120), (3, 50)):
+        partners = rng.choice(np.arange(4, nV), cnt, replace=False)
+        X[partners] = X[hub] + rng.normal(0, 1, (cnt, 3)) * 0.02 + 0.05 * rng.choice([-1, 1], (cnt, 3))
+        for k, b in enumerate(partners):
+            if k % 3 == 0 and k + 1 < cnt:
+                rows.append((-hub - 1, int(b), int(partners[k + 1]), -1 - (k % 2)))   # point-edge, multiplicity 1 or 2
+            else:
+                rows.append((-hub - 1, int(b), -1, -1 - (k % 3)))                      # point-point, multiplicity 1..3
+    rows = np.array(rows, np.int32)
+    dhat2 = 0.5 ** 2
+    c = ContactContext(0)
+    c.set_mesh(nV, np.arange(nV, dtype=np.int32), np.zeros((0, 2), np.int32), np.zeros((0, 3), np.int32))
+    c.set_rest_positions(X)
+    c.set_positions(X)
+    c.set_constraints(rows)
+    ptr, col, val = c.barrier_hessian(dhat2, KAPPA, project_spd=True)
+    ptr2, col2, val2 = c.barrier_hessian(dhat2, KAPPA, project_spd=True)
+    assert np.array_equal(ptr, ptr2) and np.array_equal(col, col2) and np.array_equal(val, val2)
+    om = orc.mesh(X, X, np.arange(nV, dtype=np.int32), np.zeros((0, 2), np.int32), np.zeros((0, 3), np.int32))
+    optr, ocol, oval = orc.barrier_hessian(om, rows, np.ones(len(rows)), dhat2, KAPPA, project_spd=True)["csr"]
+    assert np.array_equal(ptr, optr) and np.array_equal(col, ocol)
+    assert rel(val, oval) <= RTOL and np.abs(val - oval).max() <= RTOL * np.abs(oval).max()
+    c.close()
