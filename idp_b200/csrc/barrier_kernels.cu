@@ -286,7 +286,7 @@ int barrier_eval(idp_ctx* c, double dhat2, double kappa, double thickness, int w
         nBlocks = total; // only this rank's rows are counted
         IDP_CK(c, c->bktKey.reserve(std::max<long>(nBlocks, 1)));
         IDP_CK(c, c->bktVal8.reserve(8 * (size_t)std::max<long>(nBlocks, 1)));
-        IDP_CK(c, c->bktVal1.reserve(std::max<long>(nBlocks, 1)));
+        IDP_CK(c, c->bktVal1.reserve(std::max<long>(nBlocks, 1) + 2)); // + 2: the bulk copies read whole 16-byte pairs
         a.vtxOff = c->vtxOff.p; a.vtxCursor = c->vtxCursor.p; a.bktKey = c->bktKey.p; a.bktVal8 = c->bktVal8.p; a.bktVal1 = c->bktVal1.p;
         c->nBlocksUnique = 0;
         c->nnz = 0;
@@ -410,15 +410,22 @@ __device__ __forceinline__ void reduce_sorted_bucket(const ReduceArgs& a, int v,
     if (tid == 0) a.uCount[v] = U;
     sync();
 }
-#define IDP_REDUCE_WARPS 8
+#ifndef IDP_REDUCE_WARPS
+#define IDP_REDUCE_WARPS 4
+#endif
 #define IDP_REDUCE_CAP 512 // bucket entries a warp sorts in registers (16 per lane)
-// Warp-level bitonic sort of 32 E (key, payload) pairs held E per lane (element index = lane * E + r): the stages with
-// partner distance < E are compare-exchanges between registers of one lane, the others exchange with lane ^ (distance / E)
-// through shuffles. Fully unrolled: every register index is static.
-// branch-free selects (the compiler turned the 64-bit ternaries of the network into divergent branches)
+#ifndef IDP_REDUCE_STAGE
+#define IDP_REDUCE_STAGE 160 // bucket entries whose 3x3 values a warp stages in shared memory (72 B each)
+#endif
+// Warp-level bitonic sort of 32 E keys held E per lane (element index = lane * E + r). Stages with partner distance < E
+// are compare-exchanges between registers of one lane (static indices), the others exchange with lane ^ (distance / E)
+// through shuffles. Only the in-lane networks are unrolled; the merge levels and their cross-lane stages are rolled loops
+// with a run-time lane mask -- the fully unrolled network (three sizes of it) did not fit the instruction cache and the
+// kernel stalled on instruction fetch (ncu: no_instruction 8.5 of 14 cycles per issue).
+// PAY = false: the keys are unique and carry their own payload (packed slot), compare-exchange is a plain min / max.
 __device__ __forceinline__ unsigned long long selp64(bool p, unsigned long long a, unsigned long long b)
 {
-    unsigned long long r;
+    unsigned long long r; // branch-free (the compiler turned 64-bit ternaries into divergent branches)
     asm("{ .reg .pred q; setp.ne.u32 q, %3, 0; selp.b64 %0, %1, %2, q; }" : "=l"(r) : "l"(a), "l"(b), "r"((unsigned)p));
     return r;
 }
@@ -428,66 +435,116 @@ __device__ __forceinline__ unsigned selp32(bool p, unsigned a, unsigned b)
     asm("{ .reg .pred q; setp.ne.u32 q, %3, 0; selp.b32 %0, %1, %2, q; }" : "=r"(r) : "r"(a), "r"(b), "r"((unsigned)p));
     return r;
 }
-template <int E>
-__device__ __forceinline__ void warp_bitonic_sort(unsigned long long (&key)[E], unsigned (&pay)[E], int lane)
+template <int E, bool PAY>
+__device__ __forceinline__ void lane_stages(unsigned long long (&key)[E], unsigned (&pay)[E], int kFrom, bool ascLane)
 {
+    // the in-lane stages j = kFrom/2 .. 1 of one merge level; direction: static (r & k) inside the first levels (k < E),
+    // otherwise the lane's direction
 #pragma unroll
-    for (int k = 2; k <= 32 * E; k <<= 1) {
+    for (int j = E >> 1; j > 0; j >>= 1) {
+        if (j >= kFrom) continue;
 #pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            if (j < E) {
-#pragma unroll
-                for (int r = 0; r < E; ++r) {
-                    const int p = r ^ j;
-                    if (p > r) {
-                        const bool asc = k < E ? ((r & k) == 0) : ((lane & (k / E)) == 0); // direction of the block of k elements
-                        const bool sw = (key[r] > key[p]) == asc;
-                        const unsigned long long ka = key[r], kb = key[p];
-                        const unsigned pa = pay[r], pb = pay[p];
-                        key[r] = selp64(sw, kb, ka); key[p] = selp64(sw, ka, kb);
-                        pay[r] = selp32(sw, pb, pa); pay[p] = selp32(sw, pa, pb);
-                    }
-                }
-            }
-            else {
-                const int lj = j / E;
-                const bool lower = (lane & lj) == 0;
-                const bool asc = (lane & (k / E)) == 0; // k >= 2 j >= 2 E here
-                const bool keepMin = lower == asc;
-#pragma unroll
-                for (int r = 0; r < E; ++r) {
-                    const unsigned long long ok = __shfl_xor_sync(0xffffffffu, key[r], lj);
-                    const unsigned op = __shfl_xor_sync(0xffffffffu, pay[r], lj);
-                    const bool take = (ok < key[r]) == keepMin && ok != key[r];
-                    key[r] = selp64(take, ok, key[r]);
-                    pay[r] = selp32(take, op, pay[r]);
-                }
+        for (int r = 0; r < E; ++r) {
+            const int p = r ^ j;
+            if (p > r) {
+                const bool asc = kFrom < E ? ((r & kFrom) == 0) : ascLane;
+                const bool sw = (key[r] > key[p]) == asc;
+                const unsigned long long ka = key[r], kb = key[p];
+                key[r] = selp64(sw, kb, ka); key[p] = selp64(sw, ka, kb);
+                if (PAY) { const unsigned pa = pay[r], pb = pay[p]; pay[r] = selp32(sw, pb, pa); pay[p] = selp32(sw, pa, pb); }
             }
         }
     }
 }
-// one vertex: sort its bucket by (vhi, origin), find the unique upper neighbours, sum the duplicates in origin order
-template <int E>
-__device__ __forceinline__ void vertex_reduce_warp(const ReduceArgs& a, int v, int off, int n, int lane, unsigned short* sPay, unsigned short* sStart)
+template <int E, bool PAY>
+__device__ __forceinline__ void warp_bitonic_sort(unsigned long long (&key)[E], unsigned (&pay)[E], int lane)
 {
+#pragma unroll
+    for (int k = 2; k <= E; k <<= 1) lane_stages<E, PAY>(key, pay, k, (lane & 1) == 0); // levels inside a lane (k == E: by lane parity)
+#pragma unroll 1
+    for (int kk = 2; kk <= 32; kk <<= 1) { // levels of kk lanes = kk E elements
+        const bool asc = (lane & kk) == 0;
+#pragma unroll 1
+        for (int lj = kk >> 1; lj > 0; lj >>= 1) {
+            const bool keepMin = ((lane & lj) == 0) == asc;
+#pragma unroll
+            for (int r = 0; r < E; ++r) {
+                const unsigned long long ok = __shfl_xor_sync(0xffffffffu, key[r], lj);
+                const bool take = (ok < key[r]) == keepMin && ok != key[r];
+                if (PAY) { const unsigned op = __shfl_xor_sync(0xffffffffu, pay[r], lj); pay[r] = selp32(take, op, pay[r]); }
+                key[r] = selp64(take, ok, key[r]);
+            }
+        }
+        lane_stages<E, PAY>(key, pay, E, asc);
+    }
+}
+// ---- bulk-copy (TMA, 1-D) staging of a bucket's values: one elected lane arms the warp's mbarrier with the byte count and
+// issues cp.async.bulk for the 64-byte and the 8-byte parts; the copy runs while the warp sorts the keys in registers.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+                 "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}" ::"r"(smem_u32(bar)),
+                 "r"(parity)
+                 : "memory");
+}
+struct alignas(128) ReduceSmem { // one per warp
+    double val8[8 * IDP_REDUCE_STAGE];       // 64-byte parts, entry e at [8 e, 8 e + 8)
+    double val1[IDP_REDUCE_STAGE + 2];       // ninth components (the source is only 8-byte aligned: copied from the even slot below)
+    unsigned short pay[IDP_REDUCE_CAP];      // sorted position -> bucket slot
+    unsigned short start[IDP_REDUCE_CAP];    // unique block -> first sorted position
+    unsigned long long bar;
+};
+// one vertex: sort its bucket by (vhi, origin), find the unique upper neighbours, sum the duplicates in origin order
+// PACKED (nV <= 2^23): the sort key is (vhi : 23 | origin : 32 | slot : 9), unique, no payload registers.
+template <int E, bool PACKED>
+__device__ __forceinline__ void vertex_reduce_warp(const ReduceArgs& a, int v, int off, int n, int lane, ReduceSmem& sm, unsigned& phase)
+{
+    const bool staged = n <= IDP_REDUCE_STAGE;
+    const int off1 = off & ~1; // bulk copies need 16-byte aligned sources
+    if (staged && lane == 0) {
+        const unsigned b8 = 64u * (unsigned)n, b1 = 8u * (unsigned)(((off + n + 1) & ~1) - off1);
+        mbar_expect_tx(&sm.bar, b8 + b1);
+        bulk_g2s(sm.val8, a.bktVal8 + 8 * (long)off, b8, &sm.bar);
+        bulk_g2s(sm.val1, a.bktVal1 + off1, b1, &sm.bar);
+    }
     unsigned long long key[E];
     unsigned pay[E];
 #pragma unroll
     for (int r = 0; r < E; ++r) {
         const int e = lane * E + r;
-        key[r] = e < n ? a.bktKey[off + e] : ~0ull; // padding sorts to the end
+        unsigned long long k = ~0ull; // padding sorts to the end
+        if (e < n) {
+            k = a.bktKey[off + e];
+            if (PACKED) k = ((k >> 32) << 41) | ((k & 0xffffffffull) << 9) | (unsigned long long)e;
+        }
+        key[r] = k;
         pay[r] = (unsigned)e;
     }
-    warp_bitonic_sort<E>(key, pay, lane);
+    warp_bitonic_sort<E, !PACKED>(key, pay, lane);
     // heads of the runs of equal vhi
-    const unsigned prevLast = __shfl_up_sync(0xffffffffu, (unsigned)(key[E - 1] >> 32), 1);
+    constexpr int VSH = PACKED ? 41 : 32;
+    const unsigned prevLast = __shfl_up_sync(0xffffffffu, (unsigned)(key[E - 1] >> VSH), 1);
     unsigned heads = 0;
 #pragma unroll
     for (int r = 0; r < E; ++r) {
         const int e = lane * E + r;
-        const unsigned vj = (unsigned)(key[r] >> 32), pv = r ? (unsigned)(key[r - 1] >> 32) : prevLast;
+        const unsigned vj = (unsigned)(key[r] >> VSH), pv = r ? (unsigned)(key[r - 1] >> VSH) : prevLast;
         if (e < n && (e == 0 || vj != pv)) heads |= 1u << r;
-        if (e < n) sPay[e] = (unsigned short)pay[r];
+        if (e < n) sm.pay[e] = PACKED ? (unsigned short)((unsigned)key[r] & 511u) : (unsigned short)pay[r];
     }
     int base = __popc(heads); // exclusive prefix of the head counts over the lanes
     const int mine = base;
@@ -502,42 +559,74 @@ __device__ __forceinline__ void vertex_reduce_warp(const ReduceArgs& a, int v, i
     for (int r = 0; r < E; ++r) {
         if (heads & (1u << r)) {
             const int u = base + __popc(heads & ((1u << r) - 1u));
-            const int vj = (int)(unsigned)(key[r] >> 32);
-            sStart[u] = (unsigned short)(lane * E + r);
+            const int vj = (int)(unsigned)(key[r] >> VSH);
+            sm.start[u] = (unsigned short)(lane * E + r);
             a.uCol[off + u] = vj;
             if (vj != v) atomicAdd(&a.lowerCount[vj], 1);
         }
     }
     if (lane == 0) a.uCount[v] = U;
     __syncwarp();
-    for (int t = lane; t < 9 * U; t += 32) {
-        const int u = t / 9, comp = t - 9 * u;
-        const int s0 = sStart[u], s1 = (u + 1 < U) ? (int)sStart[u + 1] : n;
-        const double* src = comp < 8 ? a.bktVal8 + 8 * (long)off + comp : a.bktVal1 + off;
-        const int stride = comp < 8 ? 8 : 1;
-        double sum = 0;
-        int p = s0;
-        for (; p + 4 <= s1; p += 4) { // four loads in flight; the additions stay in origin order
-            const double x0 = src[(long)stride * sPay[p]], x1 = src[(long)stride * sPay[p + 1]], x2 = src[(long)stride * sPay[p + 2]], x3 = src[(long)stride * sPay[p + 3]];
-            sum = (((sum + x0) + x1) + x2) + x3;
+    if (staged) {
+        mbar_wait(&sm.bar, phase);
+        phase ^= 1u;
+        const double* s1p = sm.val1 + (off - off1);
+        for (int t = lane; t < 9 * U; t += 32) {
+            const int u = t / 9, comp = t - 9 * u;
+            const int s0 = sm.start[u], s1 = (u + 1 < U) ? (int)sm.start[u + 1] : n;
+            const double* src = comp < 8 ? sm.val8 + comp : s1p;
+            const int stride = comp < 8 ? 8 : 1;
+            double sum = 0;
+            int p = s0;
+            for (; p + 4 <= s1; p += 4) { // the additions stay in origin order
+                const double x0 = src[stride * sm.pay[p]], x1 = src[stride * sm.pay[p + 1]], x2 = src[stride * sm.pay[p + 2]], x3 = src[stride * sm.pay[p + 3]];
+                sum = (((sum + x0) + x1) + x2) + x3;
+            }
+            for (; p < s1; ++p) sum += src[stride * sm.pay[p]];
+            a.uVal[9 * ((long)off + u) + comp] = sum;
         }
-        for (; p < s1; ++p) sum += src[(long)stride * sPay[p]];
-        a.uVal[9 * ((long)off + u) + comp] = sum;
     }
-    __syncwarp();
+    else {
+        for (int t = lane; t < 9 * U; t += 32) {
+            const int u = t / 9, comp = t - 9 * u;
+            const int s0 = sm.start[u], s1 = (u + 1 < U) ? (int)sm.start[u + 1] : n;
+            const double* src = comp < 8 ? a.bktVal8 + 8 * (long)off + comp : a.bktVal1 + off;
+            const int stride = comp < 8 ? 8 : 1;
+            double sum = 0;
+            int p = s0;
+            for (; p + 4 <= s1; p += 4) { // four loads in flight; the additions stay in origin order
+                const double x0 = src[(long)stride * sm.pay[p]], x1 = src[(long)stride * sm.pay[p + 1]], x2 = src[(long)stride * sm.pay[p + 2]], x3 = src[(long)stride * sm.pay[p + 3]];
+                sum = (((sum + x0) + x1) + x2) + x3;
+            }
+            for (; p < s1; ++p) sum += src[(long)stride * sm.pay[p]];
+            a.uVal[9 * ((long)off + u) + comp] = sum;
+        }
+    }
+    __syncwarp(); // every lane is done with the staged values before the next bulk copy is issued
 }
+template <bool PACKED>
 __global__ void __launch_bounds__(32 * IDP_REDUCE_WARPS) k_vertex_reduce(ReduceArgs a)
 {
-    __shared__ unsigned short sPay[IDP_REDUCE_WARPS][IDP_REDUCE_CAP];
-    __shared__ unsigned short sStart[IDP_REDUCE_WARPS][IDP_REDUCE_CAP];
+    extern __shared__ __align__(128) unsigned char sRaw[];
+    ReduceSmem* smAll = reinterpret_cast<ReduceSmem*>(sRaw);
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    ReduceSmem& sm = smAll[wib];
+    if (lane == 0) {
+        mbar_init(&sm.bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    unsigned phase = 0;
     for (int v = blockIdx.x * IDP_REDUCE_WARPS + wib; v < a.nV; v += gridDim.x * IDP_REDUCE_WARPS) {
         const int off = a.vtxOff[v], n = a.vtxOff[v + 1] - off;
         if (n == 0) { if (lane == 0) a.uCount[v] = 0; continue; }
-        if (n <= 128) vertex_reduce_warp<4>(a, v, off, n, lane, sPay[wib], sStart[wib]);
-        else if (n <= 256) vertex_reduce_warp<8>(a, v, off, n, lane, sPay[wib], sStart[wib]);
-        else if (n <= IDP_REDUCE_CAP) vertex_reduce_warp<16>(a, v, off, n, lane, sPay[wib], sStart[wib]);
-        else if (lane == 0) { a.bigList[atomicAdd(a.bigCount, 1)] = v; a.uCount[v] = 0; }
+        if (n > IDP_REDUCE_CAP) { if (lane == 0) { a.bigList[atomicAdd(a.bigCount, 1)] = v; a.uCount[v] = 0; } }
+        else if (PACKED) {
+            if (n <= 128) vertex_reduce_warp<4, true>(a, v, off, n, lane, sm, phase);
+            else if (n <= 256) vertex_reduce_warp<8, true>(a, v, off, n, lane, sm, phase);
+            else vertex_reduce_warp<16, true>(a, v, off, n, lane, sm, phase);
+        }
+        else vertex_reduce_warp<16, false>(a, v, off, n, lane, sm, phase); // > 2^23 vertices: (key, payload) pairs, one size
     }
 }
 // oversized buckets: one CTA per vertex, the same network on global scratch (correct for any size; only pathological
@@ -667,7 +756,16 @@ int assemble_csr(idp_ctx* c)
     ra.vtxOff = c->vtxOff.p; ra.bktKey = c->bktKey.p; ra.bktVal8 = c->bktVal8.p; ra.bktVal1 = c->bktVal1.p; ra.nV = nV;
     ra.uCount = c->uCount.p; ra.uCol = c->uCol.p; ra.uVal = c->uVal.p; ra.lowerCount = c->lowerCount.p;
     ra.bigList = c->bigList.p; ra.bigCount = dBigCount; ra.bigKey = c->bigKey.p; ra.bigPay = c->bigPay.p; ra.bigStart = c->bigStart.p;
-    IDP_LAUNCH(c, k_vertex_reduce, std::min(blocks_for(nV, IDP_REDUCE_WARPS), (unsigned)c->sm_count * 64), 32 * IDP_REDUCE_WARPS, 0, ra);
+    const size_t reduceSmem = sizeof(ReduceSmem) * IDP_REDUCE_WARPS;
+    const unsigned reduceGrid = std::min(blocks_for(nV, IDP_REDUCE_WARPS), (unsigned)c->sm_count * 64);
+    if (nV <= (1 << 23) && !getenv("IDP_REDUCE_UNPACKED")) {
+        IDP_CK(c, cudaFuncSetAttribute(k_vertex_reduce<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)reduceSmem));
+        IDP_LAUNCH(c, k_vertex_reduce<true>, reduceGrid, 32 * IDP_REDUCE_WARPS, reduceSmem, ra);
+    }
+    else {
+        IDP_CK(c, cudaFuncSetAttribute(k_vertex_reduce<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)reduceSmem));
+        IDP_LAUNCH(c, k_vertex_reduce<false>, reduceGrid, 32 * IDP_REDUCE_WARPS, reduceSmem, ra);
+    }
     IDP_LAUNCH(c, k_vertex_reduce_big, (unsigned)c->sm_count * 2, 256, 0, ra);
     IDP_TRY(cub_scan_exclusive(c, c->uCount.p, c->vtxBlkStart.p, (long)nV + 1));
     int nSeg = 0;
