@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libidp_contact.so")
+LIB_PATH = os.environ.get("IDP_LIB_PATH") or os.path.join(_HERE, "libidp_contact.so")  # override: build-variant experiments only
 
 STATUS = {0: "IDP_OK", 1: "IDP_ERR_CUDA", 2: "IDP_ERR_INVALID", 3: "IDP_ERR_NONPOSITIVE_DISTANCE",
           4: "IDP_ERR_CCD_ZERO_STEP", 5: "IDP_ERR_UNSUPPORTED_PRIMITIVE", 6: "IDP_ERR_NCCL",

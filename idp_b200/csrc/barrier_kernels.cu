@@ -470,7 +470,7 @@ __device__ __forceinline__ void warp_bitonic_sort(unsigned long long (&key)[E], 
 #pragma unroll
             for (int r = 0; r < E; ++r) {
                 const unsigned long long ok = __shfl_xor_sync(0xffffffffu, key[r], lj);
-                const bool take = (ok < key[r]) == keepMin && ok != key[r];
+                const bool take = PAY ? ((ok < key[r]) == keepMin && ok != key[r]) : ((ok < key[r]) == keepMin);
                 if (PAY) { const unsigned op = __shfl_xor_sync(0xffffffffu, pay[r], lj); pay[r] = selp32(take, op, pay[r]); }
                 key[r] = selp64(take, ok, key[r]);
             }
@@ -508,6 +508,64 @@ struct alignas(128) ReduceSmem { // one per warp
     unsigned short start[IDP_REDUCE_CAP];    // unique block -> first sorted position
     unsigned long long bar;
 };
+struct SharedF64 { // explicit shared-window loads (a generic pointer would compile to LD instead of LDS)
+    unsigned base;
+    __device__ __forceinline__ double2 ld2(int i) const { double2 r; asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"(base + 8u * (unsigned)i)); return r; }
+    __device__ __forceinline__ double ld1(int i) const { double r; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(r) : "r"(base + 8u * (unsigned)i)); return r; }
+};
+struct GlobalF64 {
+    const double* base;
+    __device__ __forceinline__ double2 ld2(int i) const { return *reinterpret_cast<const double2*>(base + i); }
+    __device__ __forceinline__ double ld1(int i) const { return base[i]; }
+};
+// Sums of the duplicates in a fixed association of the sorted (= origin) order. Eight groups of four lanes; a lane adds
+// two components of the 64-byte part (16-byte loads) of every entry its group visits and the ninth component of every
+// fourth one. The first run (the diagonal block: every row at this vertex contributes) is strided over all eight groups
+// and combined by a butterfly; the other runs go to one group each. v8 / v1: the bucket's values (shared or global).
+template <class P8, class P1>
+__device__ __forceinline__ void bucket_sums(const ReduceSmem& sm, P8 v8, P1 v1, int U, int n, int lane, double* outp)
+{
+    const int grp = lane >> 2, sub = lane & 3, c2 = 2 * sub;
+    {
+        const int s1 = U > 1 ? (int)sm.start[1] : n; // run 0 = [0, s1)
+        double ax = 0, ay = 0, az = 0;
+        for (int p = grp; p < s1; p += 8) {
+            const int sl = sm.pay[p];
+            const double2 x = v8.ld2(8 * sl + c2);
+            ax += x.x; ay += x.y;
+            if (sub == 0) az += v1.ld1(sl);
+        }
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+            ax += __shfl_xor_sync(0xffffffffu, ax, o); ay += __shfl_xor_sync(0xffffffffu, ay, o); az += __shfl_xor_sync(0xffffffffu, az, o);
+        }
+        if (grp == 0) { outp[c2] = ax; outp[c2 + 1] = ay; if (sub == 0) outp[8] = az; }
+    }
+    for (int u0 = 1; u0 < U; u0 += 8) { // warp-uniform trip count: the shuffles below need all lanes
+        const int u = u0 + grp;
+        int s0 = 0, s1 = 0;
+        if (u < U) { s0 = sm.start[u]; s1 = (u + 1 < U) ? (int)sm.start[u + 1] : n; }
+        double ax = 0, ay = 0, az = 0;
+        int p = s0;
+        for (; p + 4 <= s1; p += 4) {
+            const int l0 = sm.pay[p], l1 = sm.pay[p + 1], l2 = sm.pay[p + 2], l3 = sm.pay[p + 3];
+            const double2 x0 = v8.ld2(8 * l0 + c2), x1 = v8.ld2(8 * l1 + c2);
+            const double2 x2 = v8.ld2(8 * l2 + c2), x3 = v8.ld2(8 * l3 + c2);
+            const double z = v1.ld1(sub == 0 ? l0 : (sub == 1 ? l1 : (sub == 2 ? l2 : l3)));
+            ax = (((ax + x0.x) + x1.x) + x2.x) + x3.x; ay = (((ay + x0.y) + x1.y) + x2.y) + x3.y;
+            az += z;
+        }
+        for (int q = 0; p < s1; ++p, ++q) {
+            const int sl = sm.pay[p];
+            const double2 x = v8.ld2(8 * sl + c2);
+            ax += x.x; ay += x.y;
+            if (sub == q) az += v1.ld1(sl);
+        }
+        az += __shfl_xor_sync(0xffffffffu, az, 1);
+        az += __shfl_xor_sync(0xffffffffu, az, 2);
+        if (u < U) { outp[9 * u + c2] = ax; outp[9 * u + c2 + 1] = ay; if (sub == 0) outp[9 * u + 8] = az; }
+    }
+}
 // one vertex: sort its bucket by (vhi, origin), find the unique upper neighbours, sum the duplicates in origin order
 // PACKED (nV <= 2^23): the sort key is (vhi : 23 | origin : 32 | slot : 9), unique, no payload registers.
 template <int E, bool PACKED>
@@ -567,41 +625,13 @@ __device__ __forceinline__ void vertex_reduce_warp(const ReduceArgs& a, int v, i
     }
     if (lane == 0) a.uCount[v] = U;
     __syncwarp();
+    double* outp = a.uVal + 9 * (long)off;
     if (staged) {
         mbar_wait(&sm.bar, phase);
         phase ^= 1u;
-        const double* s1p = sm.val1 + (off - off1);
-        for (int t = lane; t < 9 * U; t += 32) {
-            const int u = t / 9, comp = t - 9 * u;
-            const int s0 = sm.start[u], s1 = (u + 1 < U) ? (int)sm.start[u + 1] : n;
-            const double* src = comp < 8 ? sm.val8 + comp : s1p;
-            const int stride = comp < 8 ? 8 : 1;
-            double sum = 0;
-            int p = s0;
-            for (; p + 4 <= s1; p += 4) { // the additions stay in origin order
-                const double x0 = src[stride * sm.pay[p]], x1 = src[stride * sm.pay[p + 1]], x2 = src[stride * sm.pay[p + 2]], x3 = src[stride * sm.pay[p + 3]];
-                sum = (((sum + x0) + x1) + x2) + x3;
-            }
-            for (; p < s1; ++p) sum += src[stride * sm.pay[p]];
-            a.uVal[9 * ((long)off + u) + comp] = sum;
-        }
+        bucket_sums(sm, SharedF64{smem_u32(sm.val8)}, SharedF64{smem_u32(sm.val1 + (off - off1))}, U, n, lane, outp);
     }
-    else {
-        for (int t = lane; t < 9 * U; t += 32) {
-            const int u = t / 9, comp = t - 9 * u;
-            const int s0 = sm.start[u], s1 = (u + 1 < U) ? (int)sm.start[u + 1] : n;
-            const double* src = comp < 8 ? a.bktVal8 + 8 * (long)off + comp : a.bktVal1 + off;
-            const int stride = comp < 8 ? 8 : 1;
-            double sum = 0;
-            int p = s0;
-            for (; p + 4 <= s1; p += 4) { // four loads in flight; the additions stay in origin order
-                const double x0 = src[(long)stride * sm.pay[p]], x1 = src[(long)stride * sm.pay[p + 1]], x2 = src[(long)stride * sm.pay[p + 2]], x3 = src[(long)stride * sm.pay[p + 3]];
-                sum = (((sum + x0) + x1) + x2) + x3;
-            }
-            for (; p < s1; ++p) sum += src[(long)stride * sm.pay[p]];
-            a.uVal[9 * ((long)off + u) + comp] = sum;
-        }
-    }
+    else bucket_sums(sm, GlobalF64{a.bktVal8 + 8 * (long)off}, GlobalF64{a.bktVal1 + off}, U, n, lane, outp);
     __syncwarp(); // every lane is done with the staged values before the next bulk copy is issued
 }
 template <bool PACKED>
