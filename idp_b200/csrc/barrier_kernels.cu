@@ -75,8 +75,20 @@ __global__ void __launch_bounds__(256) k_row_kinds(const Row4* __restrict__ rows
     if (threadIdx.x < 8 && sh[threadIdx.x]) atomicAdd(&kindCount[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
 }
 
+// copies of the rows / weights in evaluation order (cached with the permutation): the barrier kernel reads them coalesced and
+// can fetch the next row while it works on the current one instead of chasing perm -> row -> positions
+__global__ void __launch_bounds__(256) k_gather_rows(const Row4* __restrict__ rows, const double* __restrict__ weights, const int* __restrict__ perm, long n,
+    Row4* __restrict__ rowsK, double* __restrict__ weightsK)
+{
+    for (long j = (long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (long)gridDim.x * blockDim.x) {
+        const int i = perm[j];
+        rowsK[j] = rows[i];
+        weightsK[j] = weights[i];
+    }
+}
+
 struct BarrierArgs {
-    const Row4* rows; const double* weights; const int* perm; long jBegin, jEnd; // rows perm[jBegin..jEnd): one path, sorted by kind
+    const Row4* rows; const double* weights; long jBegin, jEnd; // rows [jBegin, jEnd) of the kind-sorted copies: one path
     const double4* xp; const double4* x0p;
     double dHat2, kappa, xi2;
     int projectSPD;
@@ -95,7 +107,7 @@ struct BarrierArgs {
 struct BucketEmit {
     unsigned long long* key; double* val8; double* val1;
     int base[4]; int nv; const int* v; unsigned rowTag;
-    __device__ __forceinline__ void reserve(const int* vtxOff, int* cursor)
+    __device__ __forceinline__ void reserve(int* cursor)
     {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -104,7 +116,7 @@ struct BucketEmit {
                 int m = 1;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) m += (j < nv && v[j] > v[k]) ? 1 : 0;
-                base[k] = __ldg(vtxOff + v[k]) + atomicAdd(cursor + v[k], m);
+                base[k] = atomicAdd(cursor + v[k], m); // the cursors start at the bucket offsets: nothing depends on the result before the first block is stored
             }
         }
     }
@@ -138,14 +150,17 @@ struct BucketEmit {
 // (792 B): 2 blocks x 128 rows = 8 warps per SM at 255 registers (9 warps would need 96-thread blocks, but registers are
 // allocated per 4 warps, which caps them at 168 and spills 1.4 KB per row).
 template <int PATH> struct BarrierCfg { static constexpr int T = PATH == 0 ? IDP_BARRIER_T0 : 128; static constexpr int MINB = PATH == 0 ? IDP_BARRIER_B0 : (PATH == 1 ? 3 : 4); };
-template <int PATH, bool WANT_E, bool WANT_G, bool WANT_H>
+template <int PATH, bool WANT_E, bool WANT_G, bool WANT_H, bool PROJECT>
 __global__ void __launch_bounds__(BarrierCfg<PATH>::T, BarrierCfg<PATH>::MINB) k_barrier(BarrierArgs a)
 {
     extern __shared__ double sV[];
     double Eacc = 0;
-    for (long j = a.jBegin + (long)blockIdx.x * blockDim.x + threadIdx.x; j < a.jEnd; j += (long)gridDim.x * blockDim.x) {
-        const long i = a.perm[j];
-        const Row4 r = a.rows[i];
+    const long stride = (long)gridDim.x * blockDim.x;
+    long j = a.jBegin + (long)blockIdx.x * blockDim.x + threadIdx.x;
+    Row4 rNext = j < a.jEnd ? a.rows[j] : Row4{0, 0, 0, 0};
+    for (; j < a.jEnd; j += stride) {
+        const Row4 r = rNext;
+        if (j + stride < a.jEnd) rNext = a.rows[j + stride]; // in flight during this row's work
         const RowDec d = decode_row(r.a, r.b, r.c, r.d);
         V3 x[4], xr[4];
 #pragma unroll
@@ -158,9 +173,9 @@ __global__ void __launch_bounds__(BarrierCfg<PATH>::T, BarrierCfg<PATH>::MINB) k
         QlStore<9, BarrierCfg<PATH>::T> V9{sV + threadIdx.x};
         QlStore<6, BarrierCfg<PATH>::T> V6{sV + threadIdx.x};
         BucketEmit em;
-        em.key = a.bktKey; em.val8 = a.bktVal8; em.val1 = a.bktVal1; em.nv = d.nv; em.v = d.v; em.rowTag = (unsigned)i << 4;
-        if (WANT_H) em.reserve(a.vtxOff, a.vtxCursor);
-        const bool ok = row_eval<PATH>(d, x, xr, a.weights[i], a.dHat2, a.kappa, a.xi2, a.projectSPD != 0, WANT_H, V9, V6, out, em);
+        em.key = a.bktKey; em.val8 = a.bktVal8; em.val1 = a.bktVal1; em.nv = d.nv; em.v = d.v; em.rowTag = (unsigned)j << 4; // origin tag: any unique, reproducible id
+        if (WANT_H) em.reserve(a.vtxCursor);
+        const bool ok = row_eval<PATH>(d, x, xr, a.weights[j], a.dHat2, a.kappa, a.xi2, PROJECT, WANT_H, V9, V6, out, em);
         if (!ok) { atomicAdd(a.errDist, 1ull); continue; }
         if (WANT_H && out.eigFail) atomicAdd(a.errEig, 1ull);
         if (WANT_E) Eacc += out.E;
@@ -187,10 +202,15 @@ static int launch_barrier_path(idp_ctx* c, BarrierArgs a, unsigned grid, int sel
 {
     constexpr int T = BarrierCfg<PATH>::T;
     const size_t smem = PATH == 0 ? QlStore<9, T>::WORDS * sizeof(double) * T : (PATH == 1 ? QlStore<6, T>::WORDS * sizeof(double) * T : 0);
+#define IDP_BARRIER_CASE1(E, G, H, P)                                                                                     \
+    do {                                                                                                                  \
+        if (smem) IDP_CK(c, cudaFuncSetAttribute(k_barrier<PATH, E, G, H, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        IDP_LAUNCH(c, (k_barrier<PATH, E, G, H, P>), grid, T, smem, a);                                               \
+    } while (0)
 #define IDP_BARRIER_CASE(E, G, H)                                                                                         \
     do {                                                                                                                  \
-        if (smem) IDP_CK(c, cudaFuncSetAttribute(k_barrier<PATH, E, G, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        IDP_LAUNCH(c, (k_barrier<PATH, E, G, H>), grid, T, smem, a);                                                  \
+        if (H && a.projectSPD) IDP_BARRIER_CASE1(E, G, H, true);                                                          \
+        else IDP_BARRIER_CASE1(E, G, H, false);                                                                           \
     } while (0)
     switch (sel) {
     case 1: IDP_BARRIER_CASE(true, false, false); break;
@@ -203,6 +223,7 @@ static int launch_barrier_path(idp_ctx* c, BarrierArgs a, unsigned grid, int sel
     default: break;
     }
 #undef IDP_BARRIER_CASE
+#undef IDP_BARRIER_CASE1
     IDP_CK(c, cudaGetLastError());
     return IDP_OK;
 }
@@ -252,6 +273,10 @@ int barrier_eval(idp_ctx* c, double dhat2, double kappa, double thickness, int w
         IDP_CK(c, cudaMemcpyAsync(hk, dKind, sizeof(hk), cudaMemcpyDeviceToHost, c->stream));
         IDP_CK(c, cudaStreamSynchronize(c->stream));
         for (int k = 0; k < 8; ++k) c->kindCount[k] = hk[k];
+        const long nOwn = c->nRows - c->kindCount[7];
+        IDP_CK(c, c->rowsK.reserve(std::max<long>(nOwn, 1))); IDP_CK(c, c->weightsK.reserve(std::max<long>(nOwn, 1)));
+        if (nOwn > 0)
+            IDP_LAUNCH(c, k_gather_rows, std::min(blocks_for(nOwn, 256), (unsigned)c->sm_count * 16), 256, 0, c->rows.p, c->weights.p, c->rowPerm.p, nOwn, c->rowsK.p, c->weightsK.p);
         c->permValid = true;
     }
     const long nPath[3] = {c->kindCount[K_EE] + c->kindCount[K_EE_M] + c->kindCount[K_PE_M] + c->kindCount[K_PP_M] + c->kindCount[K_PT],
@@ -261,7 +286,7 @@ int barrier_eval(idp_ctx* c, double dhat2, double kappa, double thickness, int w
         return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "mollified rows need the rest positions (idp_set_rest_positions)", __FILE__, __LINE__);
     const unsigned grid = std::max(1u, std::min(blocks_for(std::max(nPath[0], std::max(nPath[1], nPath[2])), 128), (unsigned)c->sm_count * 16));
     BarrierArgs a;
-    a.rows = c->rows.p; a.weights = c->weights.p; a.perm = c->rowPerm.p; a.jBegin = 0; a.jEnd = 0;
+    a.rows = c->rowsK.p; a.weights = c->weightsK.p; a.jBegin = 0; a.jEnd = 0;
     a.xp = c->xp.p; a.x0p = c->x0p.p;
     a.dHat2 = dhat2 + 2 * std::sqrt(dhat2) * thickness; // IPC.h:757
     a.kappa = kappa; a.xi2 = thickness * thickness; a.projectSPD = project_spd;
@@ -277,12 +302,12 @@ int barrier_eval(idp_ctx* c, double dhat2, double kappa, double thickness, int w
         const size_t nV1 = (size_t)c->nV + 1;
         IDP_CK(c, c->vtxCnt.reserve(nV1)); IDP_CK(c, c->vtxOff.reserve(nV1)); IDP_CK(c, c->vtxCursor.reserve(nV1));
         IDP_CK(c, cudaMemsetAsync(c->vtxCnt.p, 0, nV1 * sizeof(int), c->stream));
-        IDP_CK(c, cudaMemsetAsync(c->vtxCursor.p, 0, nV1 * sizeof(int), c->stream));
         IDP_LAUNCH(c, k_vertex_block_counts, std::min(blocks_for(c->nRows, 256), (unsigned)c->sm_count * 16), 256, 0, c->rows.p, c->nRows, c->rank, ownRanks, ownerShift, c->vtxCnt.p);
         IDP_TRY(cub_scan_exclusive(c, c->vtxCnt.p, c->vtxOff.p, (long)nV1));
         int total = 0;
         IDP_CK(c, cudaMemcpyAsync(&total, c->vtxOff.p + c->nV, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         IDP_CK(c, cudaStreamSynchronize(c->stream));
+        IDP_CK(c, cudaMemcpyAsync(c->vtxCursor.p, c->vtxOff.p, nV1 * sizeof(int), cudaMemcpyDeviceToDevice, c->stream)); // cursors start at the bucket offsets
         nBlocks = total; // only this rank's rows are counted
         IDP_CK(c, c->bktKey.reserve(std::max<long>(nBlocks, 1)));
         IDP_CK(c, c->bktVal8.reserve(8 * (size_t)std::max<long>(nBlocks, 1)));

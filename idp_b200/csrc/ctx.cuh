@@ -156,6 +156,8 @@ struct idp_ctx {
     // evaluation order of this rank's rows: stable sort by row kind (uniform warps); rebuilt when the rows change
     idp::DBuf<unsigned char> rowKind, rowKindSorted;
     idp::DBuf<int> rowIota, rowPerm;
+    idp::DBuf<idp::Row4> rowsK;         // this rank's rows in evaluation (kind-sorted) order: k_barrier streams them
+    idp::DBuf<double> weightsK;
     long kindCount[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     bool permValid = false;
     // Hessian blocks bucketed by lower vertex (BucketEmit) and their per-vertex reduction (assemble_csr)

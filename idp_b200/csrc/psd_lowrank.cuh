@@ -256,48 +256,73 @@ IDP_HD bool make_pd_ql(double* a, ST& S) // false: the QL iteration cap was reac
         g = ST::d(cm) - dl + el * (g >= 0 ? rcp_nr2(g + r0) : -rcp_nr2(r0 - g));
         double s = 1.0, c = 1.0, p = 0.0;
         double cp = 1.0, sp = 0.0; // rotation whose column update is still pending
-        bool pend = false, underflow = false;
+        bool underflow = false;
 #ifdef IDP_QL_STATS
         ++g_ql_stats.trips; g_ql_stats.givens += m - l; if (g_ql_stats.n < 512) g_ql_stats.chase[g_ql_stats.n++] = m - l;
 #endif
+        // The body is straight-line code on purpose: the scalar recurrence (s, c, g, p) -> next rotation is one serial
+        // dependency chain (~12 FP64 operations + MUFU); the column rotation of the PREVIOUS step (9 independent rows) has to
+        // be issued inside its stalls. With `if (ok)` / `if (pend)` as branches the compiler emitted chain and rotation as
+        // separate blocks (BSSY/BSYNC) and nothing overlapped (ncu source view). Now: the rotation arithmetic is
+        // unconditional (the first step applies the identity: cp = 1, sp = 0 and z0 == zc), only its stores are predicated;
+        // the underflow guard feeds 1.0 into the chain and is handled after the fact. The scalars of the next step are
+        // fetched one step ahead (d_{i+1} of the next step is this step's d_i, not yet modified).
         double* ci = S.col(m - 1);
-        for (int i = m - 1; i >= l; --i, ci -= ST::STRIDE_V) {
-            // loads first: scalars of this step and the column needed by the pending rotation (columns i+1, i+2)
-            const double ei = ST::e(ci), di = ST::d(ci), di1 = ST::d(ci + ST::STRIDE_V);
-            double z0[N];
-            if (pend) {
+        double ei = ST::e(ci), di = ST::d(ci), di1 = ST::d(ci + ST::STRIDE_V);
+        double sn, cn, rr, pn, gg, bb, er; // results of the scalar recurrence of one step
+        bool ok;
+        auto recurrence = [&]() {
+            const double f = s * ei;
+            bb = c * ei;
+            const double r2 = f * f + g * g;
+            ok = r2 > 1e-290;
+            const double r2s = ok ? r2 : 1.0;
+            const double ir = rsqrt_h3(r2s);
+            er = r2s * ir;
+            sn = f * ir; cn = g * ir;
+            gg = di1 - p;
+            rr = (di - gg) * sn + 2.0 * cn * bb;
+            pn = sn * rr;
+        };
+        auto split_on_underflow = [&]() { // tqli's recovery: split here; the carried column is the current column i+1
+            ST::dset(ci + ST::STRIDE_V, di1 - p);
+            ST::eset(ci + ST::STRIDE_V, 0.0);
+#pragma unroll
+            for (int k = 0; k < N; ++k) ST::zset(ci + ST::STRIDE_V, k, zc[k]);
+            underflow = true;
+        };
+        auto commit = [&](double eiN, double diN) {
+            ST::eset(ci + ST::STRIDE_V, er);
+            ST::dset(ci + ST::STRIDE_V, gg + pn);
+            g = cn * rr - bb;
+            s = sn; c = cn; p = pn;
+            cp = cn; sp = sn;
+            di1 = di; ei = eiN; di = diN;
+        };
+        { // first step (i = m - 1): no rotation pending yet
+            const bool more = m - 1 > l;
+            const double eiN = more ? ST::e(ci - ST::STRIDE_V) : 0.0, diN = more ? ST::d(ci - ST::STRIDE_V) : 0.0;
+            recurrence();
+            if (!ok) split_on_underflow();
+            else commit(eiN, diN);
+            ci -= ST::STRIDE_V;
+        }
+        if (!underflow) {
+            for (int i = m - 2; i >= l; --i, ci -= ST::STRIDE_V) {
+                const bool more = i > l;
+                const double eiN = more ? ST::e(ci - ST::STRIDE_V) : 0.0, diN = more ? ST::d(ci - ST::STRIDE_V) : 0.0;
+                double z0[N];
 #pragma unroll
                 for (int k = 0; k < N; ++k) z0[k] = ST::z(ci + ST::STRIDE_V, k);
-            }
-            const double f = s * ei, b = c * ei;
-            const double r2 = f * f + g * g;
-            const bool ok = r2 > 1e-290;
-            if (ok) {
-                const double ir = rsqrt_h3(r2);
-                ST::eset(ci + ST::STRIDE_V, r2 * ir);
-                s = f * ir; c = g * ir;
-                g = di1 - p;
-                const double rr = (di - g) * s + 2.0 * c * b;
-                p = s * rr;
-                ST::dset(ci + ST::STRIDE_V, g + p);
-                g = c * rr - b;
-            }
-            if (pend) {
+                recurrence();
 #pragma unroll
-                for (int k = 0; k < N; ++k) {
+                for (int k = 0; k < N; ++k) { // rotation of the previous step: columns i+2 (stored) and i+1 (carried on)
                     ST::zset(ci + 2 * ST::STRIDE_V, k, sp * z0[k] + cp * zc[k]);
                     zc[k] = cp * z0[k] - sp * zc[k];
                 }
+                if (!ok) { split_on_underflow(); break; }
+                commit(eiN, diN);
             }
-            if (!ok) { // recover from underflow (tqli): split here; the carried column is the current column i+1
-                ST::dset(ci + ST::STRIDE_V, di1 - p);
-                ST::eset(ci + ST::STRIDE_V, 0.0);
-#pragma unroll
-                for (int k = 0; k < N; ++k) ST::zset(ci + ST::STRIDE_V, k, zc[k]);
-                underflow = true;
-                break;
-            }
-            cp = c; sp = s; pend = true;
         }
         ST::eset(S.col(m), 0.0);
         if (underflow) continue;

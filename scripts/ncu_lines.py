@@ -23,6 +23,7 @@ out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_ou
 rows = list(csv.reader(out.splitlines()))
 # the page holds one section per captured launch: take the first one (pass -k / -c to ncu to choose the kernel)
 sec = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+sec = sec[int(os.environ.get("NCU_SEC", "0")):]  # NCU_SEC=k: the k-th captured launch
 end = sec[1] if len(sec) > 1 else len(rows)
 print("kernel:", rows[sec[0]][1])
 hdr = rows[sec[0] + 1]; ix = {h: i for i, h in enumerate(hdr)}
