@@ -106,7 +106,7 @@ struct BarrierArgs {
 // bytes (the 64-byte part is written as two full 32-byte sectors).
 struct BucketEmit {
     unsigned long long* key; double* val8; double* val1;
-    int base[4]; int nv; const int* v; unsigned rowTag;
+    int base[4]; int nv; int v[4]; unsigned rowTag; // v / base are only indexed with compile-time constants (registers, not local memory)
     __device__ __forceinline__ void reserve(int* cursor)
     {
 #pragma unroll
@@ -121,15 +121,21 @@ struct BucketEmit {
         }
     }
     __device__ __forceinline__ bool wants(int i, int j) const { return i <= j; }
+    // i, j are compile-time constants at every call site (unrolled loops)
     __device__ __forceinline__ void operator()(int i, int j, const double* blk) const
     {
         const bool tr = v[i] > v[j];
-        const int a = tr ? j : i, b = tr ? i : j; // a: lower vertex, b: higher (a == b on the diagonal)
-        int rnk = 0;
+        const int va = tr ? v[j] : v[i], vb = tr ? v[i] : v[j]; // va: lower vertex, vb: higher (equal on the diagonal)
+        const int ba = tr ? base[j] : base[i];
+        int rnk = 0; // blocks of the row in bucket va are ordered by the stencil index of the higher vertex
 #pragma unroll
-        for (int m = 0; m < 4; ++m) rnk += (m < b && m < nv && (v[m] > v[a] || m == a)) ? 1 : 0;
-        const long s = (long)base[a] + rnk;
-        key[s] = ((unsigned long long)(unsigned)v[b] << 32) | (unsigned long long)(rowTag | (unsigned)(4 * i + j));
+        for (int m = 0; m < 4; ++m) {
+            const bool before = tr ? (m < i) : (m < j);
+            const bool isA = tr ? (m == j) : (m == i);
+            rnk += (before && m < nv && (v[m] > va || isA)) ? 1 : 0;
+        }
+        const long s = (long)ba + rnk;
+        key[s] = ((unsigned long long)(unsigned)vb << 32) | (unsigned long long)(rowTag | (unsigned)(4 * i + j));
         double t[9];
 #pragma unroll
         for (int p = 0; p < 3; ++p)
@@ -173,7 +179,7 @@ __global__ void __launch_bounds__(BarrierCfg<PATH>::T, BarrierCfg<PATH>::MINB) k
         QlStore<9, BarrierCfg<PATH>::T> V9{sV + threadIdx.x};
         QlStore<6, BarrierCfg<PATH>::T> V6{sV + threadIdx.x};
         BucketEmit em;
-        em.key = a.bktKey; em.val8 = a.bktVal8; em.val1 = a.bktVal1; em.nv = d.nv; em.v = d.v; em.rowTag = (unsigned)j << 4; // origin tag: any unique, reproducible id
+        em.key = a.bktKey; em.val8 = a.bktVal8; em.val1 = a.bktVal1; em.nv = d.nv; em.v[0] = d.v[0]; em.v[1] = d.v[1]; em.v[2] = d.v[2]; em.v[3] = d.v[3]; em.rowTag = (unsigned)j << 4; // origin tag: any unique, reproducible id
         if (WANT_H) em.reserve(a.vtxCursor);
         const bool ok = row_eval<PATH>(d, x, xr, a.weights[j], a.dHat2, a.kappa, a.xi2, PROJECT, WANT_H, V9, V6, out, em);
         if (!ok) { atomicAdd(a.errDist, 1ull); continue; }
