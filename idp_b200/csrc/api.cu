@@ -71,6 +71,9 @@ void idp_destroy(idp_ctx* c)
     if (c->h_counters) cudaFreeHost(c->h_counters);
     if (c->h_red) cudaFreeHost(c->h_red);
     if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->commStream) cudaStreamDestroy(c->commStream);
+    if (c->evFork) cudaEventDestroy(c->evFork);
+    if (c->evJoin) cudaEventDestroy(c->evJoin);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     for (int i = 0; i < 2 * IDP_EVENT_POOL; ++i) if (c->evPool[i]) cudaEventDestroy(c->evPool[i]);
@@ -105,6 +108,7 @@ int idp_set_mesh(idp_ctx* c, int nV, int nBN, const int* bnode, int nBE, const i
     IDP_CK(c, cudaSetDevice(c->device));
     c->nV = nV; c->nBN = nBN; c->nBE = nBE; c->nBT = nBT;
     c->have_x = c->have_x0 = c->have_dir = false;
+    c->meanEdgeVersion = -1; // new boundary edges
     c->nRows = 0; c->nCandPT = c->nCandEE = c->nCcdPT = c->nCcdEE = 0;
     c->permValid = false;
     IDP_CK(c, c->bnode.reserve(std::max(nBN, 1)));
@@ -300,6 +304,40 @@ int idp_barrier_all(idp_ctx* c, double dhat2, double kappa, double thickness, in
     if (!c) return IDP_ERR_INVALID;
     IDP_CK(c, cudaSetDevice(c->device));
     double E = 0;
+    if (comm_on(c) && c->nccl_comm) {
+        // Sharded over NCCL: the three reductions that follow the row kernel (status agreement, energy, 3 nV gradient) run on a
+        // second stream while this rank assembles its partial CSR -- they used to be serialised after it.
+        const int st = barrier_eval(c, dhat2, kappa, thickness, 1, 1, 1, project_spd, &E);
+        if (!c->commStream) {
+            IDP_CK(c, cudaStreamCreateWithFlags(&c->commStream, cudaStreamNonBlocking));
+            IDP_CK(c, cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming));
+            IDP_CK(c, cudaEventCreateWithFlags(&c->evJoin, cudaEventDisableTiming));
+        }
+        double* cell = (double*)(c->counters.p + CNT_STATUS); // [status (max), E (sum)]
+        double pack[2] = {(double)st, st == IDP_OK ? E : 0.0};
+        IDP_CK(c, cudaMemcpyAsync(cell, pack, sizeof(pack), cudaMemcpyHostToDevice, c->stream));
+        IDP_CK(c, cudaEventRecord(c->evFork, c->stream));
+        IDP_CK(c, cudaStreamWaitEvent(c->commStream, c->evFork, 0));
+        cudaStream_t mainStream = c->stream;
+        c->stream = c->commStream;
+        int cst = comm_allreduce_max(c, cell, 1);
+        if (cst == IDP_OK) cst = comm_allreduce_sum(c, cell + 1, 1);
+        if (cst == IDP_OK) cst = comm_allreduce_sum(c, c->gbuf.p, 3L * c->nV);
+        const cudaError_t ce = cudaEventRecord(c->evJoin, c->commStream);
+        c->stream = mainStream;
+        if (cst != IDP_OK) return cst;
+        IDP_CK(c, ce);
+        const int ast = st == IDP_OK ? assemble_csr(c) : IDP_OK;
+        IDP_CK(c, cudaStreamWaitEvent(c->stream, c->evJoin, 0));
+        IDP_CK(c, cudaMemcpyAsync(pack, cell, sizeof(pack), cudaMemcpyDeviceToHost, c->stream));
+        IDP_CK(c, cudaStreamSynchronize(c->stream));
+        if (st != IDP_OK) return st;
+        if ((int)pack[0] != IDP_OK) { c->err = "another rank of the sharded operator failed"; return (int)pack[0]; }
+        IDP_TRY(ast);
+        if (E_inout) *E_inout += pack[1];
+        if (nnz) *nnz = c->nnz;
+        return IDP_OK;
+    }
     IDP_TRY(comm_agree_status(c, barrier_eval(c, dhat2, kappa, thickness, 1, 1, 1, project_spd, &E)));
     IDP_TRY(assemble_csr(c));
     IDP_TRY(finish_energy(c, E, E_inout));

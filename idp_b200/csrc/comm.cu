@@ -164,6 +164,15 @@ int comm_allreduce_min(idp_ctx* c, double* dev, long n)
     if (r != 0) return fail(c, IDP_ERR_NCCL, "NCCL error: %s at %s:%d", g_nccl.errstr ? g_nccl.errstr(r) : "?", __FILE__, __LINE__);
     return IDP_OK;
 }
+int comm_allreduce_max(idp_ctx* c, double* dev, long n)
+{
+    if (c->local_group) return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "comm_allreduce_max: NCCL communicators only", __FILE__, __LINE__);
+    if (!c->nccl_comm) return IDP_OK;
+    CommTimer tm(c);
+    const int r = g_nccl.allreduce(dev, dev, (size_t)n, 8, 2 /*ncclMax*/, c->nccl_comm, c->stream);
+    if (r != 0) return fail(c, IDP_ERR_NCCL, "NCCL error: %s at %s:%d", g_nccl.errstr ? g_nccl.errstr(r) : "?", __FILE__, __LINE__);
+    return IDP_OK;
+}
 // max over ranks of a status code, so that every rank leaves an operator with the same verdict (a rank-local failure
 // must not strand its peers in the next collective; the reference exit(-1)s the whole process at these points)
 int comm_agree_status(idp_ctx* c, int status)

@@ -102,6 +102,8 @@ struct idp_ctx {
     int device = 0;
     cudaStream_t stream = 0;
     bool own_stream = false;
+    cudaStream_t commStream = nullptr;              // NCCL collectives that overlap local work (idp_barrier_all)
+    cudaEvent_t evFork = nullptr, evJoin = nullptr;
     std::string err;
     long launches = 0;      // kernels of this library launched since the last idp_reset_counters
     long lib_launches = 0;  // CUB device-wide primitives invoked (each expands to a few library kernels)
@@ -123,11 +125,13 @@ struct idp_ctx {
     idp::DBuf<double> xs, ys, zs;       // SoA positions (streaming kernels)
     idp::DBuf<double4> xp, x0p, dp;     // 32-byte packed positions / rest positions / search direction (gathers)
     bool have_x = false, have_x0 = false, have_dir = false;
+    long xVersion = 0, meanEdgeVersion = -1; // positions counter; mean boundary-edge length cached per positions (hash builds)
+    double meanEdgeCached = 0;
     // ---- broad-phase scratch ----
     idp::DBuf<idp::PrimRec> recN, recE, recT;
     idp::DBuf<idp::IBox> boxNq, boxEq, boxEb, boxTb; // query boxes (inflated) and insert boxes
     idp::DBuf<idp::IBox> vbox;                        // per-vertex lattice box (CCD)
-    idp::DBuf<int> cellStart, cellCursor, largeList, histScratch;
+    idp::DBuf<int> cellStart, cellCursor, largeList, histScratch, prepRegion;
     idp::DBuf<int4> crec0, crec1;       // cell-sorted filter records, SoA 2 x 16 B (see k_cells)
     idp::DBuf<int2> candPT, candEE;
     long nCandPT = 0, nCandEE = 0;
@@ -293,6 +297,7 @@ int cub_scan_exclusive(idp_ctx* c, const int* in, int* out, long n);
 inline bool comm_on(const idp_ctx* c) { return c->nranks > 1 && (c->nccl_comm || c->local_group); }
 int comm_allreduce_min(idp_ctx* c, double* dev, long n);
 int comm_allreduce_sum(idp_ctx* c, double* dev, long n);
+int comm_allreduce_max(idp_ctx* c, double* dev, long n);
 int comm_agree_status(idp_ctx* c, int status); // max over ranks of a status code (collective; identity when unsharded)
 int comm_allgather_i64(idp_ctx* c, long long* dev, long perRank); // in place: rank r's perRank values at dev + r*perRank
 int comm_gather_groups(idp_ctx* c, const void* local, size_t elemSize, void* globalOut); // local [A|B|U] -> global [A..|B..|U..]

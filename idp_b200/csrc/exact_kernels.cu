@@ -92,7 +92,7 @@ int upload_positions(idp_ctx* c, const double* host, int stride, int which)
     IDP_LAUNCH(c, k_scatter_positions, blocks_for(c->nV, 256), 256, 0, c->stage.p, stride, c->nV,
         which == 0 ? c->xs.p : nullptr, c->ys.p, c->zs.p, dst.p);
     IDP_CK(c, cudaGetLastError());
-    if (which == 0) c->have_x = true;
+    if (which == 0) { c->have_x = true; ++c->xVersion; }
     if (which == 1) c->have_x0 = true;
     return IDP_OK;
 }
@@ -197,7 +197,36 @@ struct PrepArgs {
     GridDesc g;
     double radius;      // static: inflated query radius r'; CCD: unused
     const IBox* vbox;   // CCD: per-vertex lattice boxes
+    // Sharded contexts prepare only what their queries can meet: primitives [ownB, ownE) are this rank's queries (always
+    // prepared, phase 0); the others (phase 1) are potential partners and are skipped -- insert box marked with the
+    // sentinel pad[0] = -1, no 64-byte record written -- unless their lattice box overlaps `region`, the lattice bounding
+    // box of this rank's query boxes (a candidate's insert box always overlaps the inflated query box).
+    int ownB = 0, ownE = 0, phase = 0;
+    const int* region = nullptr; // {lo[3], hi[3]} on the device; nullptr: no filter (single GPU)
 };
+__device__ __forceinline__ bool outside_region(const int* __restrict__ rg, const IBox& b)
+{
+    return b.hi[0] < rg[0] || b.hi[1] < rg[1] || b.hi[2] < rg[2] || b.lo[0] > rg[3] || b.lo[1] > rg[4] || b.lo[2] > rg[5];
+}
+// lattice bounding box of the query boxes [qb, qe)
+__global__ void k_lat_region(const IBox* __restrict__ qbox, int qb, int qe, int* __restrict__ region)
+{
+    int lo[3] = {2147483647, 2147483647, 2147483647}, hi[3] = {-2147483647, -2147483647, -2147483647};
+    for (int q = qb + blockIdx.x * blockDim.x + threadIdx.x; q < qe; q += gridDim.x * blockDim.x) {
+        const IBox b = qbox[q];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { lo[k] = min(lo[k], b.lo[k]); hi[k] = max(hi[k], b.hi[k]); }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        lo[k] = __reduce_min_sync(0xffffffffu, lo[k]);
+        hi[k] = __reduce_max_sync(0xffffffffu, hi[k]);
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { atomicMin(&region[k], lo[k]); atomicMax(&region[3 + k], hi[k]); }
+    }
+}
 __device__ __forceinline__ void box_from_aabb(const GridDesc& g, const V3& lo, const V3& hi, double r, IBox& b)
 {
     b.lo[0] = lat_index(lo.x - r, g.lo[0], g.inv); b.lo[1] = lat_index(lo.y - r, g.lo[1], g.inv); b.lo[2] = lat_index(lo.z - r, g.lo[2], g.inv);
@@ -233,7 +262,8 @@ __device__ __forceinline__ void box_union(IBox& o, const IBox& a, const IBox& b)
 // nodes: query records. static: box = idx(p -+ r'); CCD: box = vbox[v]
 __global__ void k_prep_nodes(PrepArgs a, int nBN, PrimRec* __restrict__ rec, IBox* __restrict__ qbox)
 {
-    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < nBN; s += gridDim.x * blockDim.x) {
+    (void)nBN; // nodes are only ever queries: this rank's range is all that is needed
+    for (int s = a.ownB + blockIdx.x * blockDim.x + threadIdx.x; s < a.ownE; s += gridDim.x * blockDim.x) {
         const int v = a.bnode[s];
         V3 lo, hi;
         swept(a, v, lo, hi);
@@ -248,23 +278,28 @@ __global__ void k_prep_nodes(PrepArgs a, int nBN, PrimRec* __restrict__ rec, IBo
 }
 __global__ void k_prep_edges(PrepArgs a, int nBE, PrimRec* __restrict__ rec, IBox* __restrict__ qbox, IBox* __restrict__ bbox)
 {
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nBE; e += gridDim.x * blockDim.x) {
+    // phase 0: [ownB, ownE); phase 1: the rest, filtered by the region
+    const int n = a.phase == 0 ? a.ownE - a.ownB : nBE - (a.ownE - a.ownB);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int e = a.phase == 0 ? a.ownB + i : (i < a.ownB ? i : i + (a.ownE - a.ownB));
         const int2 ab = a.bedge[e];
         V3 l0, h0, l1, h1;
         swept(a, ab.x, l0, h0);
         swept(a, ab.y, l1, h1);
         const V3 lo = min3(l0, l1), hi = max3(h0, h1);
+        IBox b;
+        if (a.vbox) box_union(b, a.vbox[ab.x], a.vbox[ab.y]);
+        else box_from_aabb(a.g, lo, hi, 0.0, b);
+        if (a.phase == 1 && a.region && outside_region(a.region, b)) {
+            b.pad[0] = -1;
+            bbox[e] = b;
+            continue;
+        }
+        bbox[e] = b; // query and insert boxes coincide for CCD
         PrimRec r;
         rec_set(r, lo, hi, ab.x, ab.y, -1, (a.dbc[ab.x] && a.dbc[ab.y]) ? 1 : 0);
         rec[e] = r;
-        IBox b;
-        if (a.vbox) {
-            box_union(b, a.vbox[ab.x], a.vbox[ab.y]);
-            bbox[e] = b; // query and insert boxes coincide for CCD
-        }
-        else {
-            box_from_aabb(a.g, lo, hi, 0.0, b);
-            bbox[e] = b;
+        if (!a.vbox && a.phase == 0) {
             box_from_aabb(a.g, lo, hi, a.radius, b);
             qbox[e] = b;
         }
@@ -279,9 +314,6 @@ __global__ void k_prep_tris(PrepArgs a, int nBT, PrimRec* __restrict__ rec, IBox
         swept(a, f.y, l1, h1);
         swept(a, f.z, l2, h2);
         const V3 lo = min3(min3(l0, l1), l2), hi = max3(max3(h0, h1), h2);
-        PrimRec r;
-        rec_set(r, lo, hi, f.x, f.y, f.z, (a.dbc[f.x] && a.dbc[f.y] && a.dbc[f.z]) ? 1 : 0);
-        rec[t] = r;
         IBox b;
         if (a.vbox) {
             IBox t01;
@@ -289,7 +321,15 @@ __global__ void k_prep_tris(PrepArgs a, int nBT, PrimRec* __restrict__ rec, IBox
             box_union(b, t01, a.vbox[f.z]);
         }
         else box_from_aabb(a.g, lo, hi, 0.0, b);
+        if (a.region && outside_region(a.region, b)) { // triangles are only ever partners
+            b.pad[0] = -1;
+            bbox[t] = b;
+            continue;
+        }
         bbox[t] = b;
+        PrimRec r;
+        rec_set(r, lo, hi, f.x, f.y, f.z, (a.dbc[f.x] && a.dbc[f.y] && a.dbc[f.z]) ? 1 : 0);
+        rec[t] = r;
     }
 }
 // CCD: per-vertex lattice box of the alpha-scaled, xi/2-inflated swept segment (SPATIAL_HASH.h:525-533)
@@ -368,7 +408,9 @@ __global__ void k_level_hist(const IBox* __restrict__ bbox, int nB, GridDesc g, 
     __syncthreads();
     for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nB; b += gridDim.x * blockDim.x) {
         int lo[3], hi[3];
-        cell_range(g, bbox[b], lo, hi);
+        const IBox bx = bbox[b];
+        if (bx.pad[0] < 0) continue; // not prepared on this shard (outside the query region)
+        cell_range(g, bx, lo, hi);
         const int l = level_of(lo, hi, 1), s = level_shift(l);
         atomicAdd(&sh[l], 1);
 #pragma unroll
@@ -416,7 +458,9 @@ __global__ void k_cells(const IBox* __restrict__ bbox, const PrimRec* __restrict
     for (int k = 0; k < 6; ++k) rg[k] = region[k];
     for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nB; b += gridDim.x * blockDim.x) {
         int lo[3], hi[3];
-        cell_range(g, bbox[b], lo, hi);
+        const IBox bx = bbox[b];
+        if (bx.pad[0] < 0) continue; // not prepared on this shard (outside the query region)
+        cell_range(g, bx, lo, hi);
         const int li = lv.slot[level_of(lo, hi, lv.useBin1)], l = lv.shift[li];
         // queries visit the anchors in [qlo - ext, qhi] (level cells): anchors outside the shard's region are never met
         bool skip = false;
@@ -953,6 +997,7 @@ static void choose_static_grid(const double lo[3], const double hi[3], double me
 static int mean_edge_length(idp_ctx* c, double* out)
 {
     if (c->nBE == 0) { *out = 0; return IDP_OK; }
+    if (c->meanEdgeVersion == c->xVersion) { *out = c->meanEdgeCached; return IDP_OK; } // same positions as the last call (constraint set -> CCD)
     const long need = (long)c->nBE + 2 * ((c->nBE + 2047) / 2048 + 1);
     IDP_CK(c, c->red.reserve(std::max<long>(need, 3L * c->nBN + 2 * ((3L * c->nBN + 2047) / 2048 + 1))));
     IDP_LAUNCH(c, k_edge_lengths, blocks_for(c->nBE, 256), 256, 0, c->bedge.p, c->nBE, c->xp.p, c->red.p);
@@ -960,6 +1005,8 @@ static int mean_edge_length(idp_ctx* c, double* out)
     const long nb = (c->nBE + 2047) / 2048 + 1;
     IDP_TRY(tree_sum_device(c, c->red.p, c->nBE, c->red.p + c->nBE, c->red.p + c->nBE + nb, &s));
     *out = s / c->nBE;
+    c->meanEdgeCached = *out;
+    c->meanEdgeVersion = c->xVersion;
     return IDP_OK;
 }
 
@@ -982,6 +1029,40 @@ static void shard_range(const idp_ctx* c, long n, int* b, int* e)
 {
     *b = (int)(n * c->rank / c->nranks);
     *e = (int)(n * (c->rank + 1) / c->nranks);
+}
+
+// Primitive records and lattice boxes for one hash build. Single GPU: everything. Sharded: this rank's query ranges, then
+// only the partners whose insert box overlaps the lattice bounding box of those queries (PrepArgs); the rest is marked
+// with the sentinel box and costs one 32-byte store instead of the 64 + 32 (+ 32) bytes of records and boxes.
+static int prep_primitives(idp_ctx* c, PrepArgs pa, bool ccd)
+{
+    int nb, ne, eb, ee;
+    shard_range(c, c->nBN, &nb, &ne);
+    shard_range(c, c->nBE, &eb, &ee);
+    const bool shard = c->nranks > 1;
+    int* reg = nullptr;
+    if (shard) {
+        IDP_CK(c, c->prepRegion.reserve(12));
+        static const int init[12] = {2147483647, 2147483647, 2147483647, -2147483647, -2147483647, -2147483647,
+            2147483647, 2147483647, 2147483647, -2147483647, -2147483647, -2147483647};
+        IDP_CK(c, cudaMemcpyAsync(c->prepRegion.p, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+        reg = c->prepRegion.p;
+    }
+    pa.phase = 0; pa.region = nullptr;
+    pa.ownB = nb; pa.ownE = ne;
+    if (ne > nb) IDP_LAUNCH(c, k_prep_nodes, blocks_for(ne - nb, 256), 256, 0, pa, c->nBN, c->recN.p, c->boxNq.p);
+    pa.ownB = eb; pa.ownE = ee;
+    if (ee > eb) IDP_LAUNCH(c, k_prep_edges, blocks_for(ee - eb, 256), 256, 0, pa, c->nBE, c->recE.p, c->boxEq.p, c->boxEb.p);
+    if (shard) {
+        if (ne > nb) IDP_LAUNCH(c, k_lat_region, std::min(blocks_for(ne - nb, 256), (unsigned)c->sm_count * 4), 256, 0, c->boxNq.p, nb, ne, reg);
+        if (ee > eb) IDP_LAUNCH(c, k_lat_region, std::min(blocks_for(ee - eb, 256), (unsigned)c->sm_count * 4), 256, 0, ccd ? c->boxEb.p : c->boxEq.p, eb, ee, reg + 6);
+        pa.phase = 1; pa.region = reg + 6;
+        if (c->nBE - (ee - eb) > 0) IDP_LAUNCH(c, k_prep_edges, blocks_for(c->nBE - (ee - eb), 256), 256, 0, pa, c->nBE, c->recE.p, c->boxEq.p, c->boxEb.p);
+        pa.region = reg;
+    }
+    if (c->nBT > 0) IDP_LAUNCH(c, k_prep_tris, blocks_for(c->nBT, 256), 256, 0, pa, c->nBT, c->recT.p, c->boxTb.p);
+    IDP_CK(c, cudaGetLastError());
+    return IDP_OK;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1020,10 +1101,7 @@ int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
         IDP_CK(c, c->recN.reserve(c->nBN)); IDP_CK(c, c->boxNq.reserve(c->nBN));
         IDP_CK(c, c->recE.reserve(c->nBE)); IDP_CK(c, c->boxEq.reserve(c->nBE)); IDP_CK(c, c->boxEb.reserve(c->nBE));
         IDP_CK(c, c->recT.reserve(c->nBT)); IDP_CK(c, c->boxTb.reserve(c->nBT));
-        IDP_LAUNCH(c, k_prep_nodes, blocks_for(c->nBN, 256), 256, 0, pa, c->nBN, c->recN.p, c->boxNq.p);
-        IDP_LAUNCH(c, k_prep_edges, blocks_for(c->nBE, 256), 256, 0, pa, c->nBE, c->recE.p, c->boxEq.p, c->boxEb.p);
-        IDP_LAUNCH(c, k_prep_tris, blocks_for(c->nBT, 256), 256, 0, pa, c->nBT, c->recT.p, c->boxTb.p);
-        IDP_CK(c, cudaGetLastError());
+        IDP_TRY(prep_primitives(c, pa, false));
     }
     unsigned long long* cnt = (unsigned long long*)c->counters.p;
     int qb, qe;
@@ -1390,6 +1468,10 @@ static void ccd_set_grid(const double lo[3], const double hi[3], double voxelSiz
     for (int d = 0; d < 3; ++d) g.n[d] = (n[d] + k) / k;
 }
 
+__global__ void k_poison_step_on_error(const unsigned long long* __restrict__ err, unsigned long long* __restrict__ alphaBits)
+{
+    if (*err) *alphaBits = 0ull;
+}
 int ccd_step(idp_ctx* c, double thickness, double* alpha_inout, int keep_candidates)
 {
     (void)keep_candidates;
@@ -1439,10 +1521,7 @@ int ccd_step(idp_ctx* c, double thickness, double* alpha_inout, int keep_candida
         IDP_CK(c, c->recN.reserve(c->nBN)); IDP_CK(c, c->boxNq.reserve(c->nBN));
         IDP_CK(c, c->recE.reserve(c->nBE)); IDP_CK(c, c->boxEq.reserve(c->nBE)); IDP_CK(c, c->boxEb.reserve(c->nBE));
         IDP_CK(c, c->recT.reserve(c->nBT)); IDP_CK(c, c->boxTb.reserve(c->nBT));
-        IDP_LAUNCH(c, k_prep_nodes, blocks_for(c->nBN, 256), 256, 0, pa, c->nBN, c->recN.p, c->boxNq.p);
-        IDP_LAUNCH(c, k_prep_edges, blocks_for(c->nBE, 256), 256, 0, pa, c->nBE, c->recE.p, c->boxEq.p, c->boxEb.p);
-        IDP_LAUNCH(c, k_prep_tris, blocks_for(c->nBT, 256), 256, 0, pa, c->nBT, c->recT.p, c->boxTb.p);
-        IDP_CK(c, cudaGetLastError());
+        IDP_TRY(prep_primitives(c, pa, true));
     }
     unsigned long long* cnt = (unsigned long long*)c->counters.p;
     {
@@ -1486,8 +1565,12 @@ int ccd_step(idp_ctx* c, double thickness, double* alpha_inout, int keep_candida
         }
         IDP_CK(c, cudaGetLastError());
     }
-    // positive doubles order like their bit patterns, so the device cell is a valid double for the min all-reduce
-    if (comm_on(c)) IDP_TRY(comm_allreduce_min(c, (double*)(cnt + CNT_ALPHA_BITS), 1));
+    // positive doubles order like their bit patterns, so the device cell is a valid double for the min all-reduce; a rank
+    // that hit the ACCD iteration cap zeroes its cell first, so the same reduction tells every rank (no second collective)
+    if (comm_on(c)) {
+        IDP_LAUNCH(c, k_poison_step_on_error, 1, 1, 0, cnt + CNT_ERR_CCD, cnt + CNT_ALPHA_BITS);
+        IDP_TRY(comm_allreduce_min(c, (double*)(cnt + CNT_ALPHA_BITS), 1));
+    }
     IDP_TRY(read_counters(c));
     c->ccd_iters = (long)c->h_counters[CNT_CCD_ITERS];
     double out;
@@ -1495,8 +1578,8 @@ int ccd_step(idp_ctx* c, double thickness, double* alpha_inout, int keep_candida
     // the PT and EE candidate buffers are invalidated for the static phase
     c->nCandPT = 0; c->nCandEE = 0;
     // every rank leaves with the same verdict (the step itself is already the global minimum)
-    const int st = comm_agree_status(c, c->h_counters[CNT_ERR_CCD] ? IDP_ERR_CCD_ITERATION_CAP : IDP_OK);
-    if (st != IDP_OK) return fail(c, st, "%s (%s:%d)", "additive CCD iteration cap reached", __FILE__, __LINE__);
+    const int st = (c->h_counters[CNT_ERR_CCD] || (comm_on(c) && c->h_counters[CNT_ALPHA_BITS] == 0)) ? IDP_ERR_CCD_ITERATION_CAP : IDP_OK;
+    if (st != IDP_OK) return fail(c, st, "%s (%s:%d)", "additive CCD iteration cap reached (on this or another rank)", __FILE__, __LINE__);
     *alpha_inout = out;
     if (out == 0 && alpha > 0) return fail(c, IDP_ERR_CCD_ZERO_STEP, "%s (%s:%d)", "CCD returned a zero step", __FILE__, __LINE__);
     return IDP_OK;
