@@ -29,7 +29,8 @@ EXPORTS = ["idp_create", "idp_destroy", "idp_last_error", "idp_set_stream", "idp
            "idp_barrier_hessian", "idp_barrier_all", "idp_get_hessian_csr", "idp_hessian_csr_device",
            "idp_gradient_device", "idp_get_gradient", "idp_ccd_step", "idp_set_search_direction", "idp_ccd_step_resident", "idp_min_dist2", "idp_comm_unique_id", "idp_comm_init",
            "idp_set_shard", "idp_kernel_launches", "idp_library_calls", "idp_reset_counters", "idp_stage_ms",
-           "idp_last_count", "idp_measure_fp64_tflops"]
+           "idp_last_count", "idp_measure_fp64_tflops", "idp_system_set_flow_term", "idp_system_set_mass", "idp_project_dbc",
+           "idp_solve_pcg", "idp_set_mesh_from_triangles", "idp_get_surface_primitives"]
 
 
 class IdpError(RuntimeError):
@@ -86,6 +87,12 @@ def load_library(path=LIB_PATH):
     L.idp_last_count.argtypes = [vp, i]
     L.idp_last_count.restype = l
     L.idp_measure_fp64_tflops.argtypes = [vp, C.POINTER(d)]
+    L.idp_system_set_flow_term.argtypes = [vp, i, vp, i, vp, d]
+    L.idp_system_set_mass.argtypes = [vp, vp]
+    L.idp_project_dbc.argtypes = [vp]
+    L.idp_solve_pcg.argtypes = [vp, vp, vp, d, i, C.POINTER(i), C.POINTER(d)]
+    L.idp_set_mesh_from_triangles.argtypes = [vp, i, i, vp, i, vp, i, vp]
+    L.idp_get_surface_primitives.argtypes = [vp, C.POINTER(i), vp, C.POINTER(i), vp, C.POINTER(i), vp, vp, vp, vp]
     return L
 
 
@@ -184,6 +191,48 @@ class ContactContext:
         out = np.empty((n.value, 2), np.int32)
         if n.value:
             self._ck(self.L.idp_get_candidates(self.h, which, C.byref(n), _p(out)))
+        return out
+
+    # ---- the rest of the Newton system (flow term, mass, Project_DBC, PCG, surface extraction) ----
+    def set_flow_term(self, elem, vol, h):
+        if elem is None or len(elem) == 0:
+            return self._ck(self.L.idp_system_set_flow_term(self.h, 0, None, 3, None, 0.0))
+        elem = np.ascontiguousarray(elem, np.int32)
+        vol = np.ascontiguousarray(vol, np.float64)
+        self._ck(self.L.idp_system_set_flow_term(self.h, len(elem), _p(elem), elem.shape[1], _p(vol), float(h)))
+
+    def set_mass(self, m):
+        m = None if m is None else np.ascontiguousarray(m, np.float64)
+        self._ck(self.L.idp_system_set_mass(self.h, _p(m)))
+
+    def project_dbc(self):
+        self._ck(self.L.idp_project_dbc(self.h))
+
+    def solve_pcg(self, rhs, rel_tol=1e-10, max_iter=10000):
+        rhs = np.ascontiguousarray(rhs, np.float64).reshape(-1)
+        sol = np.empty_like(rhs)
+        it = C.c_int(0)
+        res = C.c_double(0.0)
+        self._ck(self.L.idp_solve_pcg(self.h, _p(rhs), _p(sol), rel_tol, max_iter, C.byref(it), C.byref(res)))
+        return sol, it.value, res.value
+
+    def set_mesh_from_triangles(self, nV, tri, X=None, dbc=None):
+        tri = np.ascontiguousarray(tri, np.int32)
+        X = None if X is None else np.ascontiguousarray(X, np.float64)
+        dbc = None if dbc is None else np.ascontiguousarray(dbc, np.uint8)
+        self.nV = nV
+        self._ck(self.L.idp_set_mesh_from_triangles(self.h, nV, len(tri), _p(tri), tri.shape[1], _p(X), 0 if X is None else X.shape[1], _p(dbc)))
+
+    def get_surface_primitives(self, areas=False):
+        n = [C.c_int(0) for _ in range(3)]
+        self._ck(self.L.idp_get_surface_primitives(self.h, C.byref(n[0]), None, C.byref(n[1]), None, C.byref(n[2]), None, None, None, None))
+        nN, nE, nT = (k.value for k in n)
+        out = dict(bnode=np.empty(nN, np.int32), bedge=np.empty((nE, 2), np.int32), btri=np.empty((nT, 3), np.int32))
+        ar = dict(BNArea=np.empty(nN), BEArea=np.empty(nE), BTArea=np.empty(nT)) if areas else dict(BNArea=None, BEArea=None, BTArea=None)
+        self._ck(self.L.idp_get_surface_primitives(self.h, None, _p(out["bnode"]), None, _p(out["bedge"]), None, _p(out["btri"]),
+                                                   _p(ar["BNArea"]), _p(ar["BEArea"]), _p(ar["BTArea"])))
+        if areas:
+            out.update(ar)
         return out
 
     # ---- barrier ----

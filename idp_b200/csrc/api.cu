@@ -109,6 +109,7 @@ int idp_set_mesh(idp_ctx* c, int nV, int nBN, const int* bnode, int nBE, const i
     c->nV = nV; c->nBN = nBN; c->nBE = nBE; c->nBT = nBT;
     c->have_x = c->have_x0 = c->have_dir = false;
     c->meanEdgeVersion = -1; // new boundary edges
+    c->surfValid = false; c->nFlowElem = 0; c->haveMass = false;
     c->nRows = 0; c->nCandPT = c->nCandEE = c->nCcdPT = c->nCcdEE = 0;
     c->permValid = false;
     IDP_CK(c, c->bnode.reserve(std::max(nBN, 1)));
@@ -343,6 +344,85 @@ int idp_barrier_all(idp_ctx* c, double dhat2, double kappa, double thickness, in
     IDP_TRY(finish_energy(c, E, E_inout));
     IDP_TRY(finish_gradient(c, nullptr, 3));
     if (nnz) *nnz = c->nnz;
+    return IDP_OK;
+}
+// ---- the rest of the Newton system around the barrier Hessian -----------------------------------------
+int idp_system_set_flow_term(idp_ctx* c, int n_elem, const int* elem3, int stride, const double* vol, double h)
+{
+    if (!c || n_elem < 0 || (n_elem && (!elem3 || !vol || stride < 3))) return c ? fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "idp_system_set_flow_term: bad arguments", __FILE__, __LINE__) : IDP_ERR_INVALID;
+    IDP_CK(c, cudaSetDevice(c->device));
+    c->nFlowElem = 0;
+    if (n_elem == 0) return IDP_OK;
+    std::vector<int> e3(3 * (size_t)n_elem);
+    for (long e = 0; e < n_elem; ++e) {
+        const int a = elem3[(long)stride * e], b = elem3[(long)stride * e + 1], d = elem3[(long)stride * e + 2];
+        if (a < 0 || b < 0 || d < 0 || a >= c->nV || b >= c->nV || d >= c->nV || a == b || b == d || a == d)
+            return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "idp_system_set_flow_term: element with out-of-range or repeated vertices", __FILE__, __LINE__);
+        e3[3 * e] = a; e3[3 * e + 1] = b; e3[3 * e + 2] = d;
+    }
+    IDP_CK(c, c->flowElem.reserve(3 * (size_t)n_elem));
+    IDP_CK(c, c->flowVol.reserve(n_elem));
+    IDP_CK(c, cudaMemcpyAsync(c->flowElem.p, e3.data(), e3.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    IDP_CK(c, cudaMemcpyAsync(c->flowVol.p, vol, (size_t)n_elem * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    IDP_CK(c, cudaStreamSynchronize(c->stream));
+    c->nFlowElem = n_elem;
+    c->flowH = h;
+    return IDP_OK;
+}
+int idp_system_set_mass(idp_ctx* c, const double* m_per_vertex)
+{
+    if (!c) return IDP_ERR_INVALID;
+    IDP_CK(c, cudaSetDevice(c->device));
+    c->haveMass = false;
+    if (!m_per_vertex) return IDP_OK;
+    IDP_CK(c, c->massDiag.reserve(c->nV));
+    IDP_CK(c, cudaMemcpyAsync(c->massDiag.p, m_per_vertex, (size_t)c->nV * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    IDP_CK(c, cudaStreamSynchronize(c->stream));
+    c->haveMass = true;
+    return IDP_OK;
+}
+int idp_project_dbc(idp_ctx* c)
+{
+    if (!c) return IDP_ERR_INVALID;
+    IDP_CK(c, cudaSetDevice(c->device));
+    return project_dbc(c);
+}
+int idp_solve_pcg(idp_ctx* c, const double* rhs, double* sol, double rel_tol, int max_iter, int* iters, double* rel_residual)
+{
+    if (!c || !rhs || max_iter < 0 || !(rel_tol >= 0)) return c ? fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "idp_solve_pcg: bad arguments", __FILE__, __LINE__) : IDP_ERR_INVALID;
+    IDP_CK(c, cudaSetDevice(c->device));
+    return solve_pcg(c, rhs, sol, rel_tol, max_iter, iters, rel_residual);
+}
+int idp_set_mesh_from_triangles(idp_ctx* c, int nV, int nF, const int* tri, int stride, const double* x, int xstride, const uint8_t* dbc)
+{
+    if (!c || nV <= 0 || nF < 0 || (nF && (!tri || stride < 3)) || (x && xstride < 3))
+        return c ? fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "idp_set_mesh_from_triangles: bad arguments", __FILE__, __LINE__) : IDP_ERR_INVALID;
+    for (long i = 0; i < nF; ++i)
+        for (int k = 0; k < 3; ++k)
+            if (tri[(long)stride * i + k] < 0 || tri[(long)stride * i + k] >= nV) return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "idp_set_mesh_from_triangles: vertex index out of range", __FILE__, __LINE__);
+    IDP_CK(c, cudaSetDevice(c->device));
+    return extract_surface(c, nV, nF, tri, stride, x, xstride, dbc);
+}
+int idp_get_surface_primitives(idp_ctx* c, int* nBN, int* bnode, int* nBE, int* bedge2, int* nBT, int* btri3, double* BNArea, double* BEArea, double* BTArea)
+{
+    if (!c) return IDP_ERR_INVALID;
+    IDP_CK(c, cudaSetDevice(c->device));
+    if (nBN) *nBN = c->nBN;
+    if (nBE) *nBE = c->nBE;
+    if (nBT) *nBT = c->nBT;
+    if (bnode && c->nBN) IDP_CK(c, cudaMemcpyAsync(bnode, c->bnode.p, c->nBN * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (bedge2 && c->nBE) IDP_CK(c, cudaMemcpyAsync(bedge2, c->bedge.p, c->nBE * sizeof(int2), cudaMemcpyDeviceToHost, c->stream));
+    std::vector<int4> t4;
+    if (btri3 && c->nBT) {
+        t4.resize(c->nBT);
+        IDP_CK(c, cudaMemcpyAsync(t4.data(), c->btri.p, c->nBT * sizeof(int4), cudaMemcpyDeviceToHost, c->stream));
+    }
+    if ((BNArea || BEArea || BTArea) && !c->surfValid) return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "areas exist only after idp_set_mesh_from_triangles", __FILE__, __LINE__);
+    if (BNArea && c->nBN) IDP_CK(c, cudaMemcpyAsync(BNArea, c->surfNodeAreaC.p, c->nBN * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (BEArea && c->nBE) IDP_CK(c, cudaMemcpyAsync(BEArea, c->surfEdgeArea.p, c->nBE * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (BTArea && c->nBT) IDP_CK(c, cudaMemcpyAsync(BTArea, c->surfTriAreaH.p, c->nBT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    IDP_CK(c, cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i < t4.size(); ++i) { btri3[3 * i] = t4[i].x; btri3[3 * i + 1] = t4[i].y; btri3[3 * i + 2] = t4[i].z; }
     return IDP_OK;
 }
 int idp_get_hessian_csr(idp_ctx* c, int* ptr, int* col, double* val)

@@ -147,6 +147,71 @@ struct BucketEmit {
     }
 };
 
+// ---- the other Hessian terms of the flow Newton system, emitted into the same buckets --------------
+// Laplacian flow term (Shell/INC_POTENTIAL.h:323-339): per triangle element and axis d the reference appends the triplets
+// (v_i d, v_i d, 2 h vol / 6) and (v_i d, v_j d, -h vol / 6) for the two other vertices j -- i.e. the 3x3 blocks
+// (v_i, v_i) = (2 h vol / 6) I and (v_i, v_j) = (-h vol / 6) I; the symmetric assembly takes the upper blocks.
+// Lumped mass (`sysMtr += M`, INC_POTENTIAL.h:383-386; M diagonal, Shell/DISCRETE_SHELL.h:279-318): block (v, v) = m_v I.
+struct ExtraArgs {
+    const int* elem; const double* vol; int eBegin, eEnd; double h;
+    const double* mass; int vBegin, vEnd;
+    int* vtxCnt; int* vtxCursor; unsigned long long* bktKey; double* bktVal8; double* bktVal1;
+    unsigned tagBase;
+};
+__global__ void __launch_bounds__(256) k_extra_counts(ExtraArgs a)
+{
+    const int nE = a.eEnd - a.eBegin, nM = a.mass ? a.vEnd - a.vBegin : 0;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nE + nM; t += gridDim.x * blockDim.x) {
+        if (t < nE) {
+            const int e = a.eBegin + t;
+            const int v[3] = {a.elem[3 * e], a.elem[3 * e + 1], a.elem[3 * e + 2]};
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                int m = 1;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) m += v[j] > v[k] ? 1 : 0;
+                atomicAdd(&a.vtxCnt[v[k]], m);
+            }
+        }
+        else {
+            const int v = a.vBegin + (t - nE);
+            if (a.mass[v] != 0.0) atomicAdd(&a.vtxCnt[v], 1);
+        }
+    }
+}
+__global__ void __launch_bounds__(256) k_extra_emit(ExtraArgs a)
+{
+    const int nE = a.eEnd - a.eBegin, nM = a.mass ? a.vEnd - a.vBegin : 0;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nE + nM; t += gridDim.x * blockDim.x) {
+        BucketEmit em;
+        em.key = a.bktKey; em.val8 = a.bktVal8; em.val1 = a.bktVal1;
+        em.rowTag = (a.tagBase + (unsigned)t) << 4;
+        double blk[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        if (t < nE) {
+            const int e = a.eBegin + t;
+            em.nv = 3; em.v[0] = a.elem[3 * e]; em.v[1] = a.elem[3 * e + 1]; em.v[2] = a.elem[3 * e + 2]; em.v[3] = -1;
+            em.reserve(a.vtxCursor);
+            const double w = a.h * a.vol[e] / 6.0;
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = i; j < 3; ++j) {
+                    blk[0] = blk[4] = blk[8] = (i == j) ? 2.0 * w : -w;
+                    em(i, j, blk);
+                }
+        }
+        else {
+            const int v = a.vBegin + (t - nE);
+            const double m = a.mass[v];
+            if (m == 0.0) continue;
+            em.nv = 1; em.v[0] = v; em.v[1] = em.v[2] = em.v[3] = -1;
+            em.reserve(a.vtxCursor);
+            blk[0] = blk[4] = blk[8] = m;
+            em(0, 0, blk);
+        }
+    }
+}
+
 // One thread per constraint row. PATH 0: four-vertex kinds (PT, EE and the three mollified kinds; 9x9 QL with the work
 // store in shared memory), PATH 1: point-edge (6x6 QL), PATH 2: point-point (closed form).
 // Rows are visited through a permutation that groups them by kind (stable, so memory locality of the constraint order is
@@ -254,8 +319,9 @@ int barrier_eval(idp_ctx* c, double dhat2, double kappa, double thickness, int w
         IDP_CK(c, c->gbuf.reserve(3 * (size_t)c->nV));
         IDP_CK(c, cudaMemsetAsync(c->gbuf.p, 0, 3 * (size_t)c->nV * sizeof(double), c->stream));
     }
-    if (want_h) { c->nnz = 0; c->nBlocksUnique = 0; }
-    if (c->nRows == 0) return IDP_OK;
+    if (want_h) { c->nnz = 0; c->nBlocksUnique = 0; c->nBlocksEmitted = 0; }
+    const bool extraTerms = want_h && (c->nFlowElem > 0 || c->haveMass); // flow / mass blocks are assembled even without contact rows
+    if (c->nRows == 0 && !extraTerms) return IDP_OK;
     StageTimer tm(c, IDP_STAGE_BARRIER);
     IDP_CK(c, cudaMemsetAsync(c->counters.p + CNT_ERR_DIST, 0, sizeof(long long), c->stream));
     IDP_CK(c, cudaMemsetAsync(c->counters.p + CNT_ERR_EIG, 0, sizeof(long long), c->stream));
@@ -263,7 +329,8 @@ int barrier_eval(idp_ctx* c, double dhat2, double kappa, double thickness, int w
     const int ownRanks = c->rowsLocal ? 1 : c->nranks; // LOCAL-ROWS mode: every row in c->rows is this rank's
     int ownerShift = 8;
     while (ownerShift < 14 && (c->nV >> ownerShift) > 16 * c->nranks) ++ownerShift;
-    if (!c->permValid) {
+    if (c->nRows == 0) { for (int k = 0; k < 8; ++k) c->kindCount[k] = 0; }
+    else if (!c->permValid) {
         IDP_CK(c, c->rowKind.reserve(c->nRows)); IDP_CK(c, c->rowKindSorted.reserve(c->nRows));
         IDP_CK(c, c->rowIota.reserve(c->nRows)); IDP_CK(c, c->rowPerm.reserve(c->nRows));
         unsigned long long* dKind = (unsigned long long*)(c->counters.p + CNT_KINDS);
@@ -302,13 +369,25 @@ int barrier_eval(idp_ctx* c, double dhat2, double kappa, double thickness, int w
     a.errDist = (unsigned long long*)(c->counters.p + CNT_ERR_DIST);
     a.errEig = (unsigned long long*)(c->counters.p + CNT_ERR_EIG);
     a.vtxOff = nullptr; a.vtxCursor = nullptr; a.bktKey = nullptr; a.bktVal8 = nullptr; a.bktVal1 = nullptr;
-    long nBlocks = 0;
+    long nBlocks = 0, nExtra = 0;
+    ExtraArgs xaKeep = {};
     if (want_h) {
-        if (c->nRows >= (1L << 28)) return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "more than 2^28 constraint rows on one rank", __FILE__, __LINE__);
+        c->csrProjected = false;
+        if (c->nRows + (long)c->nFlowElem + c->nV >= (1L << 28)) return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "more than 2^28 constraint rows (+ elements + vertices) on one rank", __FILE__, __LINE__);
         const size_t nV1 = (size_t)c->nV + 1;
         IDP_CK(c, c->vtxCnt.reserve(nV1)); IDP_CK(c, c->vtxOff.reserve(nV1)); IDP_CK(c, c->vtxCursor.reserve(nV1));
         IDP_CK(c, cudaMemsetAsync(c->vtxCnt.p, 0, nV1 * sizeof(int), c->stream));
-        IDP_LAUNCH(c, k_vertex_block_counts, std::min(blocks_for(c->nRows, 256), (unsigned)c->sm_count * 16), 256, 0, c->rows.p, c->nRows, c->rank, ownRanks, ownerShift, c->vtxCnt.p);
+        if (c->nRows > 0)
+            IDP_LAUNCH(c, k_vertex_block_counts, std::min(blocks_for(c->nRows, 256), (unsigned)c->sm_count * 16), 256, 0, c->rows.p, c->nRows, c->rank, ownRanks, ownerShift, c->vtxCnt.p);
+        // the other terms of the system matrix (flow Laplacian, lumped mass) share the buckets; sharded by element / vertex range
+        ExtraArgs xa;
+        xa.elem = c->flowElem.p; xa.vol = c->flowVol.p; xa.h = c->flowH; xa.mass = c->haveMass ? c->massDiag.p : nullptr;
+        xa.eBegin = (int)((long)c->nFlowElem * c->rank / c->nranks); xa.eEnd = (int)((long)c->nFlowElem * (c->rank + 1) / c->nranks);
+        xa.vBegin = (int)((long)c->nV * c->rank / c->nranks); xa.vEnd = (int)((long)c->nV * (c->rank + 1) / c->nranks);
+        xa.vtxCnt = c->vtxCnt.p;
+        nExtra = (xa.eEnd - xa.eBegin) + (xa.mass ? xa.vEnd - xa.vBegin : 0);
+        if (nExtra > 0) IDP_LAUNCH(c, k_extra_counts, std::min(blocks_for(nExtra, 256), (unsigned)c->sm_count * 16), 256, 0, xa);
+        xaKeep = xa;
         IDP_TRY(cub_scan_exclusive(c, c->vtxCnt.p, c->vtxOff.p, (long)nV1));
         int total = 0;
         IDP_CK(c, cudaMemcpyAsync(&total, c->vtxOff.p + c->nV, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -338,6 +417,11 @@ int barrier_eval(idp_ctx* c, double dhat2, double kappa, double thickness, int w
         if (nPath[0] > 0) IDP_TRY(launch_barrier_path<0>(c, a0, g0, sel));
         if (nPath[1] > 0) IDP_TRY(launch_barrier_path<1>(c, a1, g1, sel));
         if (nPath[2] > 0) IDP_TRY(launch_barrier_path<2>(c, a2, g2, sel));
+    }
+    if (want_h && nExtra > 0) {
+        xaKeep.vtxCursor = c->vtxCursor.p; xaKeep.bktKey = c->bktKey.p; xaKeep.bktVal8 = c->bktVal8.p; xaKeep.bktVal1 = c->bktVal1.p;
+        xaKeep.tagBase = (unsigned)nMine;
+        IDP_LAUNCH(c, k_extra_emit, std::min(blocks_for(nExtra, 256), (unsigned)c->sm_count * 16), 256, 0, xaKeep);
     }
     if (nMine > 0 && want_e) IDP_LAUNCH(c, k_sum_partials, 1, 256, 0, c->red.p, 3 * (int)grid, c->red.p + 3 * (size_t)grid);
     long long nerr = 0, neig = 0;
@@ -795,7 +879,7 @@ int assemble_csr(idp_ctx* c)
 {
     StageTimer tm(c, IDP_STAGE_CSR);
     IDP_CK(c, c->csrPtr.reserve(3 * (size_t)c->nV + 1));
-    const long n = c->nRows ? c->nBlocksEmitted : 0;
+    const long n = c->nBlocksEmitted;
     if (n <= 0) {
         IDP_CK(c, cudaMemsetAsync(c->csrPtr.p, 0, (3 * (size_t)c->nV + 1) * sizeof(int), c->stream));
         c->nnz = 0; c->nBlocksUnique = 0;

@@ -177,6 +177,19 @@ struct idp_ctx {
     idp::DBuf<int> csrPtr, csrCol;
     idp::DBuf<double> csrVal;
     long nnz = 0, nBlocksUnique = 0;
+    // ---- the rest of the Newton system assembled into the same CSR (flow term, lumped mass) ----
+    idp::DBuf<int> flowElem;            // 3 vertex ids per triangle element
+    idp::DBuf<double> flowVol, massDiag;
+    int nFlowElem = 0;
+    double flowH = 0;
+    bool haveMass = false;
+    bool csrProjected = false;          // idp_project_dbc has been applied to the current CSR
+    // ---- device-side surface extraction (idp_set_mesh_from_triangles) ----
+    idp::DBuf<int> surfTri;
+    idp::DBuf<double> surfTriArea, surfTriAreaH, surfNodeArea, surfNodeAreaC, surfEdgeArea, surfEdgeArea2;
+    bool surfValid = false;
+    // ---- PCG (idp_solve_pcg) ----
+    idp::DBuf<double> pcgX, pcgR, pcgZ, pcgP, pcgAp, pcgInvDiag, pcgScal;
     // ---- CCD ----
     long ccd_iters = 0;
     long nCcdPT = 0, nCcdEE = 0;
@@ -289,6 +302,9 @@ int sorted_candidates(idp_ctx* c, int which, int2* host_out);
 int barrier_eval(idp_ctx* c, double dhat2, double kappa, double thickness, int want_e, int want_g, int want_h,
     int project_spd, double* E_out);
 int assemble_csr(idp_ctx* c);
+int project_dbc(idp_ctx* c);
+int solve_pcg(idp_ctx* c, const double* rhs, double* sol, double rel_tol, int max_iter, int* iters, double* rel_res);
+int extract_surface(idp_ctx* c, int nV, int nF, const int* tri, int stride, const double* x, int xstride, const unsigned char* dbc);
 int min_dist2(idp_ctx* c, double thickness, double* host_dist2, double* min_out);
 int ccd_step(idp_ctx* c, double thickness, double* alpha_inout, int keep_candidates);
 int cub_scan_exclusive(idp_ctx* c, const int* in, int* out, long n);

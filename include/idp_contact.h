@@ -116,6 +116,37 @@ int idp_gradient_device(idp_ctx* ctx, const double** d_g_xyz);
 /* g_accum[v*stride + a] += the gradient of the last idp_barrier_gradient / idp_barrier_all (sharded: the all-reduced one) */
 int idp_get_gradient(idp_ctx* ctx, double* g_accum, int stride);
 
+/* ---- the caller-side steps around the barrier Hessian, kept on the device -------------------- */
+/* Terms assembled into the SAME device CSR by every following idp_barrier_hessian / idp_barrier_all (they persist until
+ * replaced; n_elem = 0 / NULL removes a term; idp_set_mesh* clears both):
+ *   flow term (FEM/Shell/INC_POTENTIAL.h:323-339, the `flow` branch of Compute_IncPotential_Hessian): per triangle element
+ *     (`stride` ints per element, volume vol[e]) and axis d:  H[(v_i,d),(v_i,d)] += 2 h vol / 6 and
+ *     H[(v_i,d),(v_j,d)] -= h vol / 6 for the two other vertices j of the element;
+ *   lumped mass (`sysMtr.Get_Matrix() += M.Get_Matrix()`, INC_POTENTIAL.h:383-386, M from Shell/DISCRETE_SHELL.h:279-318):
+ *     H[(v,d),(v,d)] += m[v] for every vertex with m[v] != 0.
+ * With these the matrix leaving idp_barrier_hessian is what Construct_From_Triplet + `+= M` hand to Project_DBC (values;
+ * the pattern additionally keeps explicit zeros inside every 3x3 block). Sharded contexts split the elements / vertices
+ * by contiguous ranges like the query primitives. */
+int idp_system_set_flow_term(idp_ctx* ctx, int n_elem, const int* elem3, int stride, const double* vol, double h);
+int idp_system_set_mass(idp_ctx* ctx, const double* m_per_vertex);
+/* CSR_MATRIX::Project_DBC (Math/CSR_MATRIX.h:130-141) applied to the device CSR with the Dirichlet mask of idp_set_mesh:
+ * every stored entry whose row or column vertex is a Dirichlet node becomes (row == col). Single-GPU contexts. */
+int idp_project_dbc(idp_ctx* ctx);
+/* The role of Solve_Direct (Math/DIRECT_SOLVER.h:14-88: CHOLMOD / SimplicialLDLT on the host) without moving the matrix:
+ * conjugate gradients with a 3x3 block-Jacobi preconditioner on the device CSR, x0 = 0, stops when |r| <= rel_tol |rhs| or
+ * after max_iter iterations (iterative: the caller states the tolerance; *rel_residual reports what was reached).
+ * rhs / sol: 3 nV doubles on the host (sol may be NULL). The matrix must be symmetric positive definite (project_spd = 1,
+ * mass and / or Dirichlet rows present). Single-GPU contexts. */
+int idp_solve_pcg(idp_ctx* ctx, const double* rhs, double* sol, double rel_tol, int max_iter, int* iters, double* rel_residual);
+/* Find_Surface_Primitives_And_Compute_Area (Utils/MESHIO.h:768-834) on the device, once per mesh instead of once per time
+ * step on the host with a std::map (Shell/IMPLICIT_EULER.h:222-241): sets the context's mesh from the element list
+ * (`stride` ints per triangle) in the reference's ordering contract. x (nV rows, xstride doubles; may be NULL = topology
+ * only) provides the areas BNArea / BEArea / BTArea and the "zero summed area is not a boundary node" rule. */
+int idp_set_mesh_from_triangles(idp_ctx* ctx, int nV, int nF, const int* tri, int stride, const double* x, int xstride, const uint8_t* dbc);
+/* the primitives (and, after idp_set_mesh_from_triangles, the areas) the context holds; any pointer may be NULL */
+int idp_get_surface_primitives(idp_ctx* ctx, int* nBN, int* bnode, int* nBE, int* bedge2, int* nBT, int* btri3, double* BNArea, double* BEArea,
+    double* BTArea);
+
 /* ---- Compute_Intersection_Free_StepSize (FEM/IPC.h:1879-2244) ---------------------------------------------- */
 /* searchDir: nV rows x 3 doubles (std::vector<T>, stride 3 in the reference). alpha is in/out and includes the
  * span clamp of the CCD hash build (Grid/SPATIAL_HASH.h:466-482). */

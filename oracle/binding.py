@@ -16,7 +16,7 @@ _BUILD = os.path.join(_HERE, "_build")
 def build(force=False):
     """Compile the two oracle builds (parity: -ffp-contract=off; fast: the reference's -O3 -mfma flags)."""
     outs = [os.path.join(_BUILD, n) for n in ("liborc_parity.so", "liborc_fast.so")]
-    srcs = [os.path.join(_HERE, n) for n in ("capi.cpp", "orc_math.hpp", "orc_deriv.hpp", "orc_ipc.hpp", "Makefile")]
+    srcs = [os.path.join(_HERE, n) for n in ("capi.cpp", "orc_math.hpp", "orc_deriv.hpp", "orc_ipc.hpp", "orc_system.hpp", "Makefile")]
     stale = force or any(not os.path.exists(o) for o in outs) or \
         max(os.path.getmtime(s) for s in srcs) > min(os.path.getmtime(o) for o in outs)
     if stale:
@@ -149,6 +149,57 @@ class Oracle:
             self.lib.orc_hess_copy(h, None, None, None, _p(ptr), _p(col), _p(val))
             out["csr"] = (ptr, col, val)
         self.lib.orc_hess_free(h)
+        return out
+
+    def system_matrix(self, mesh, rows, weight, dHat2, kappa, thickness=0.0, project_spd=True, elem=None, vol=None, h=0.0, mass=None,
+                      project_dbc=False, want_triplets=False):
+        """[flow triplets][barrier triplets] -> CSR -> += M -> Project_DBC (orc_system.hpp); returns (ptr, col, val)."""
+        L = self.lib
+        L.orc_system_matrix.restype = C.c_void_p
+        L.orc_system_matrix.argtypes = [C.POINTER(OrcMesh), C.c_long, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int,
+                                        C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_int]
+        m, _keep = mesh
+        rows = _i32(rows).reshape(-1, 4)
+        weight = _f64(weight)
+        nE = 0 if elem is None else len(elem)
+        elem = None if elem is None else _i32(elem)
+        vol = None if vol is None else _f64(vol)
+        mass = None if mass is None else _f64(mass)
+        hnd = L.orc_system_matrix(C.byref(m), len(rows), _p(rows), _p(weight), dHat2, kappa, thickness, int(project_spd), nE, _p(elem), _p(vol), h,
+                                  _p(mass), int(project_dbc))
+        try:
+            if L.orc_hess_status(hnd) != 0:
+                raise RuntimeError("oracle system matrix: status %d" % L.orc_hess_status(hnd))
+            nnz = L.orc_hess_count(hnd, 1)
+            ptr = np.empty(3 * m.nV + 1, np.int32); col = np.empty(nnz, np.int32); val = np.empty(nnz, np.float64)
+            L.orc_hess_copy(hnd, None, None, None, _p(ptr), _p(col), _p(val))
+            if want_triplets:
+                nt = L.orc_hess_count(hnd, 0)
+                tr = np.empty(nt, np.int32); tc = np.empty(nt, np.int32); tv = np.empty(nt, np.float64)
+                L.orc_hess_copy(hnd, _p(tr), _p(tc), _p(tv), None, None, None)
+        finally:
+            L.orc_hess_free(hnd)
+        if want_triplets:
+            return ptr, col, val, (tr, tc, tv)
+        return ptr, col, val
+
+    def surface(self, nV, tri, X):
+        """Find_Surface_Primitives_And_Compute_Area restated with std::map (orc_system.hpp)."""
+        L = self.lib
+        L.orc_surface.restype = C.c_void_p
+        L.orc_surface.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_surface_count.restype = C.c_long
+        L.orc_surface_count.argtypes = [C.c_void_p, C.c_int]
+        L.orc_surface_copy.argtypes = [C.c_void_p] * 7
+        L.orc_surface_free.argtypes = [C.c_void_p]
+        tri = _i32(tri).reshape(-1, 3)
+        X = _f64(X).reshape(-1, 3)
+        hnd = L.orc_surface(nV, len(tri), _p(tri), _p(X))
+        nN, nE, nT = (L.orc_surface_count(hnd, k) for k in range(3))
+        out = dict(bnode=np.empty(nN, np.int32), bedge=np.empty((nE, 2), np.int32), btri=np.empty((nT, 3), np.int32),
+                   BNArea=np.empty(nN), BEArea=np.empty(nE), BTArea=np.empty(nT))
+        L.orc_surface_copy(hnd, _p(out["bnode"]), _p(out["bedge"]), _p(out["btri"]), _p(out["BNArea"]), _p(out["BEArea"]), _p(out["BTArea"]))
+        L.orc_surface_free(hnd)
         return out
 
     def row_EgH(self, mesh, row, weight, dHat2, kappa, thickness=0.0, project_spd=True):

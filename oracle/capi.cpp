@@ -1,6 +1,7 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (see orc_math.hpp header).
 // Flat C entry points for ctypes (oracle/binding.py). Not part of the product's C ABI.
 #include "orc_ipc.hpp"
+#include "orc_system.hpp"
 #include <chrono>
 
 using namespace orc;
@@ -81,6 +82,44 @@ void orc_hess_copy(void* h, int* tr, int* tc, double* tv, int* ptr, int* col, do
     if (val) std::copy(H->A.val.begin(), H->A.val.end(), val);
 }
 void orc_hess_free(void* h) { delete (HessHandle*)h; }
+
+// ---- system matrix around the barrier Hessian (orc_system.hpp) -------------------------------------------------
+// triplets = [flow term][barrier rows] -> Construct_From_Triplet -> += M -> Project_DBC (INC_POTENTIAL.h:321-394)
+void* orc_system_matrix(const OrcMesh* m, long n, const int* rows, const double* weight, double dHat2, double kappa,
+    double thickness, int projectSPD, int nElem, const int* elem3, const double* vol, double h, const double* mass, int projectDBC)
+{
+    auto* H = new HessHandle();
+    if (nElem > 0) flow_term_triplets(nElem, elem3, vol, h, H->T);
+    H->status = n > 0 ? compute_barrier_hessian(to_mesh(m), to_rows(n, rows), weight, dHat2, kappa, thickness, projectSPD != 0, H->T) : OK;
+    if (H->status == OK) {
+        csr_from_triplets(3 * m->nV, H->T, H->A);
+        if (mass) csr_add_mass(H->A, m->nV, mass);
+        if (projectDBC && m->dbc) project_dbc(H->A, m->dbc, 3);
+    }
+    return H;
+}
+void* orc_surface(int nV, int nF, const int* tri, const double* X)
+{
+    auto* S = new SurfacePrimitives();
+    find_surface_primitives(nV, nF, tri, X, *S);
+    return S;
+}
+long orc_surface_count(void* h, int which)
+{
+    auto* S = (SurfacePrimitives*)h;
+    return which == 0 ? (long)S->bnode.size() : (which == 1 ? (long)S->bedge.size() / 2 : (long)S->btri.size() / 3);
+}
+void orc_surface_copy(void* h, int* bnode, int* bedge, int* btri, double* BNArea, double* BEArea, double* BTArea)
+{
+    auto* S = (SurfacePrimitives*)h;
+    std::copy(S->bnode.begin(), S->bnode.end(), bnode);
+    std::copy(S->bedge.begin(), S->bedge.end(), bedge);
+    std::copy(S->btri.begin(), S->btri.end(), btri);
+    std::copy(S->BNArea.begin(), S->BNArea.end(), BNArea);
+    std::copy(S->BEArea.begin(), S->BEArea.end(), BEArea);
+    std::copy(S->BTArea.begin(), S->BTArea.end(), BTArea);
+}
+void orc_surface_free(void* h) { delete (SurfacePrimitives*)h; }
 
 // per-row local E / g / H (dense n x n, n = 3*nv) for one row; returns status, writes nv and stencil
 int orc_row_EgH(const OrcMesh* m, const int* row, double weight, double dHat2, double kappa, double thickness,

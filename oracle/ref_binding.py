@@ -9,6 +9,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(_HERE, "_ref", "libidp_ref.so")
 LIB_IPC = os.path.join(_HERE, "_ref", "libidp_ref_ipc.so")
+LIB_CSR = os.path.join(_HERE, "_ref", "libidp_ref_csr.so")
 
 
 def available():
@@ -17,6 +18,27 @@ def available():
 
 def ipc_available():
     return os.path.exists(LIB_IPC)
+
+
+def csr_available():
+    return os.path.exists(LIB_CSR)
+
+
+def ref_csr_system(n, tr, tc, tv, mdiag=None, dbc=None, dim=3):
+    """The reference's own Math/CSR_MATRIX.h (oracle/ref_shim/ref_csr_capi.cpp): Construct_From_Triplet -> += M ->
+    Project_DBC, the sequence of FEM/Shell/INC_POTENTIAL.h:382-394. mdiag: n scalars (0 = no entry), dbc: n/dim flags."""
+    L = C.CDLL(LIB_CSR)
+    L.ref_csr_system.restype = C.c_long
+    L.ref_csr_system.argtypes = [C.c_int, C.c_long] + [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 3 + [C.c_long]
+    tr = np.ascontiguousarray(tr, np.int32); tc = np.ascontiguousarray(tc, np.int32); tv = np.ascontiguousarray(tv, np.float64)
+    mdiag = None if mdiag is None else np.ascontiguousarray(mdiag, np.float64)
+    dbc = None if dbc is None else np.ascontiguousarray(dbc, np.uint8)
+    cap = len(tv) + n
+    ptr = np.empty(n + 1, np.int32); col = np.empty(cap, np.int32); val = np.empty(cap, np.float64)
+    nnz = L.ref_csr_system(n, len(tv), _p(tr), _p(tc), _p(tv), None if mdiag is None else _p(mdiag), None if dbc is None else _p(dbc), dim,
+                           _p(ptr), _p(col), _p(val), cap)
+    assert nnz >= 0
+    return ptr, col[:nnz].copy(), val[:nnz].copy()
 
 
 def build():

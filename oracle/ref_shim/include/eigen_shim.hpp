@@ -455,4 +455,76 @@ struct SelfAdjointEigenSolver<Matrix<T, N, N>> {
     const Matrix<T, N, N>& eigenvectors() const { return vec; }
 };
 
+// ---- Eigen::SparseMatrix<T, RowMajor>: the subset Math/CSR_MATRIX.h and `sysMtr += M` (INC_POTENTIAL.h:383-386) use --------
+// setFromTriplets follows Eigen 3.3's set_from_triplets: duplicates are summed in triplet order, inner indices end up
+// ascending, explicit zeros stay; operator+= is the sparse sum (union of the patterns).
+enum { ColMajor = 0, RowMajor = 1 };
+template <class T, int Options = ColMajor>
+class SparseMatrix {
+    int nr = 0, nc = 0;
+    std::vector<int> outer, inner;
+    std::vector<T> vals;
+public:
+    void resize(int r, int c) { nr = r; nc = c; outer.assign((size_t)r + 1, 0); inner.clear(); vals.clear(); }
+    void setZero() { std::fill(outer.begin(), outer.end(), 0); inner.clear(); vals.clear(); }
+    void reserve(size_t n) { inner.resize(n); vals.resize(n); }
+    void finalize() {}
+    int rows() const { return nr; }
+    int cols() const { return nc; }
+    long nonZeros() const { return (long)outer[nr]; }
+    int outerSize() const { return nr; }
+    T* valuePtr() { return vals.data(); }
+    int* innerIndexPtr() { return inner.data(); }
+    int* outerIndexPtr() { return outer.data(); }
+    template <class It>
+    void setFromTriplets(It begin, It end)
+    {
+        std::vector<std::vector<std::pair<int, T>>> perRow((size_t)nr);
+        for (It it = begin; it != end; ++it) perRow[it->row()].push_back({it->col(), it->value()});
+        inner.clear(); vals.clear();
+        outer.assign((size_t)nr + 1, 0);
+        for (int r = 0; r < nr; ++r) {
+            auto& e = perRow[r];
+            std::stable_sort(e.begin(), e.end(), [](const std::pair<int, T>& a, const std::pair<int, T>& b) { return a.first < b.first; });
+            for (size_t k = 0; k < e.size(); ++k) {
+                if (k && e[k].first == e[k - 1].first) vals.back() += e[k].second;
+                else { inner.push_back(e[k].first); vals.push_back(e[k].second); }
+            }
+            outer[r + 1] = (int)inner.size();
+        }
+    }
+    T& coeffRef(int i, int j)
+    {
+        for (int p = outer[i]; p < outer[i + 1]; ++p) if (inner[p] == j) return vals[p];
+        static T zero; zero = T(0); return zero; // (insertion is not needed by the compiled path)
+    }
+    SparseMatrix& operator+=(const SparseMatrix& o)
+    {
+        std::vector<int> no((size_t)nr + 1, 0), ni; std::vector<T> nv;
+        for (int r = 0; r < nr; ++r) {
+            int p = outer[r], q = o.outer[r];
+            while (p < outer[r + 1] || q < o.outer[r + 1]) {
+                const int cp = p < outer[r + 1] ? inner[p] : 2147483647, cq = q < o.outer[r + 1] ? o.inner[q] : 2147483647;
+                if (cp == cq) { ni.push_back(cp); nv.push_back(vals[p] + o.vals[q]); ++p; ++q; }
+                else if (cp < cq) { ni.push_back(cp); nv.push_back(vals[p]); ++p; }
+                else { ni.push_back(cq); nv.push_back(o.vals[q]); ++q; }
+            }
+            no[r + 1] = (int)ni.size();
+        }
+        outer.swap(no); inner.swap(ni); vals.swap(nv);
+        return *this;
+    }
+    class InnerIterator {
+        SparseMatrix& m; int k, p;
+    public:
+        InnerIterator(SparseMatrix& mat, int outerI) : m(mat), k(outerI), p(mat.outer[outerI]) {}
+        operator bool() const { return p < m.outer[k + 1]; }
+        InnerIterator& operator++() { ++p; return *this; }
+        int row() const { return k; }
+        int col() const { return m.inner[p]; }
+        const T& value() const { return m.vals[p]; }
+        T& valueRef() { return m.vals[p]; }
+    };
+};
+
 } // namespace Eigen

@@ -10,6 +10,7 @@ struct module {
 };
 using module_ = module;
 template <class... Ts> struct init {};
+enum class return_value_policy { automatic, reference, reference_internal, copy, move, take_ownership };
 struct is_operator {};
 struct self_t {};
 static const self_t self = self_t();
