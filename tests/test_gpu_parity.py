@@ -329,6 +329,32 @@ def test_b2_side_by_side_with_reference_types(lib_built, cases):
         assert m_new == m_ref and deq == 1.0
 
 
+def test_ipc_energy_plugin_routed_to_b200(lib_built, orc, cases):
+    """tests/host_shim/ipc_energy_plugin.cpp: the reference's own plugin class IPC_ENERGY<T,3,false> (FEM/Energy/IPC_ENERGY.h:11-58,
+    compiled unmodified from /root/reference) with its three barrier calls qualified B200::, driven through the
+    ABSTRACT_ENERGY virtual interface, against the reference's free functions on the same objects."""
+    import ctypes as C
+    import os
+    from conftest import ROOT
+    so = os.path.join(ROOT, "tests", "host_shim", "libipc_energy_plugin.so")
+    if not os.path.exists(so):
+        pytest.skip("libipc_energy_plugin.so is built where /root/reference exists (make -C tests/host_shim)")
+    drv = C.CDLL(so)
+    drv.ipc_energy_plugin.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_void_p]
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    for name, m, d, dhats in cases[:2]:
+        dh = dhats[-1]
+        rows, _info, _, _ = orc.constraint_set(omesh(orc, m), dh * dh)
+        rows = np.ascontiguousarray(rows, np.int32)
+        X = np.ascontiguousarray(m.X); X0 = np.ascontiguousarray(m.X0)
+        rep = np.zeros(8)
+        assert drv.ipc_energy_plugin(m.nV, P(X), P(X0), len(rows), P(rows), dh * dh, KAPPA, P(rep)) == 0
+        e_ref, e_new, gmax, gdiff, hmax, hdiff, n_ref, n_new = rep
+        assert len(rows) > 0 and abs(e_new - e_ref) <= RTOL * abs(e_ref - 0.5), (name, e_ref, e_new)   # added onto the caller's 0.5
+        assert gmax > 0 and gdiff <= RTOL * gmax, (name, gdiff, gmax)
+        assert n_new == n_ref > 0 and hdiff <= RTOL * hmax, (name, n_ref, n_new, hdiff, hmax)
+
+
 def test_row_merge_fallback_for_large_vertex_counts(lib_built, orc, cases, monkeypatch):
     """Meshes with more than 2^21 vertices cannot pack a PP/PE row into one 64-bit key; the 16-byte row merge sort they fall
     back to is forced here on a small mesh (IDP_FORCE_ROW_MERGE) and must give the identical constraint set."""
