@@ -5,6 +5,7 @@
 // maintainer would switch the five call sites, and the results are compared. Built only where /root/reference exists
 // (tests/host_shim/Makefile); the shared object travels to the GPU box.
 #include <FEM/IPC.h>
+#include <Math/CSR_MATRIX.h>
 #include "../../idp_b200/host/IPC_B200.h"
 #include <algorithm>
 #include <cmath>
@@ -111,5 +112,69 @@ extern "C" int b2_side_by_side(int nV, const double* x, const double* x0, int nB
     bool deq = dRef.size() == dNew.size();
     for (size_t i = 0; deq && i < dRef.size(); ++i) deq = dRef[i] == dNew[i];
     report[13] = mRef; report[14] = mNew; report[15] = deq ? 1.0 : 0.0;
+    return 0;
+}
+
+
+// The `flow` branch of Compute_IncPotential_Hessian (FEM/Shell/INC_POTENTIAL.h:321-394) side by side: the reference's
+// sequence -- flow triplets (:323-339, restated here: INC_POTENTIAL.h itself needs the whole shell stack), the reference's
+// Compute_Barrier_Hessian, the reference's CSR_MATRIX::Construct_From_Triplet, `+= M`, CSR_MATRIX::Project_DBC -- against
+// B200::Compute_IncPotential_Hessian_Flow, which assembles everything on the device and fills the same CSR_MATRIX type
+// through Construct_From_CSR. report: [nnzRef, nnzNew (stored), maxAbs, maxDiff, entries of Ref missing in New]
+extern "C" int b2_flow_system(int nV, const double* x, const double* x0, int nF, const int* tri, const double* vol, const double* mass,
+    const unsigned char* dbc, int nRows, const int* rows4, double h, double dHat2, double kappa, double* report)
+{
+    MESH_NODE<T, 3> X(nV);
+    MESH_NODE_ATTR<T, 3> attr(nV);
+    for (int i = 0; i < nV; ++i) {
+        X.Append(VECTOR<T, 3>(x[3 * i], x[3 * i + 1], x[3 * i + 2]));
+        attr.Append(VECTOR<T, 3>(x0[3 * i], x0[3 * i + 1], x0[3 * i + 2]), VECTOR<T, 3>(0.0), VECTOR<T, 3>(0.0), 0.0);
+    }
+    MESH_ELEM<2> Elem(nF);
+    for (int i = 0; i < nF; ++i) Elem.Append(VECTOR<int, 3>(tri[3 * i], tri[3 * i + 1], tri[3 * i + 2]));
+    std::vector<VECTOR<int, 4>> cs;
+    for (int i = 0; i < nRows; ++i) cs.emplace_back(rows4[4 * i], rows4[4 * i + 1], rows4[4 * i + 2], rows4[4 * i + 3]);
+    const std::vector<VECTOR<T, 2>> info(cs.size(), VECTOR<T, 2>(1, dHat2));
+    std::vector<bool> DBCb(nV, false);
+    for (int i = 0; i < nV; ++i) DBCb[i] = dbc[i] != 0;
+    T kap[3] = {kappa, kappa, kappa};
+    const int dim = 3;
+    // reference sequence
+    Trips triplets;
+    for (int id = 0; id < nF; ++id)
+        for (int i = 0; i < dim; ++i)
+            for (int d = 0; d < dim; ++d) {
+                triplets.emplace_back(tri[3 * id + i] * dim + d, tri[3 * id + (i + 1) % dim] * dim + d, -h * vol[id] / 6);
+                triplets.emplace_back(tri[3 * id + i] * dim + d, tri[3 * id + (i + 2) % dim] * dim + d, -h * vol[id] / 6);
+                triplets.emplace_back(tri[3 * id + i] * dim + d, tri[3 * id + i] * dim + d, 2 * h * vol[id] / 6);
+            }
+    Compute_Barrier_Hessian<T, 3, false>(X, attr, cs, info, dHat2, kap, T(0), true, triplets);
+    CSR_MATRIX<T> sysRef, M, sysNew;
+    sysRef.Construct_From_Triplet(nV * dim, nV * dim, triplets);
+    Trips mt;
+    for (int v = 0; v < nV; ++v)
+        if (mass[v] != 0.0) for (int d = 0; d < dim; ++d) mt.emplace_back(v * dim + d, v * dim + d, mass[v]);
+    M.Construct_From_Triplet(nV * dim, nV * dim, mt);
+    sysRef.Get_Matrix() += M.Get_Matrix();
+    sysRef.Project_DBC(DBCb, dim);
+    // device path
+    const std::vector<T> volv(vol, vol + nF), massv(mass, mass + nV);
+    B200::Compute_IncPotential_Hessian_Flow<T, 3>(Elem, volv, h, X, attr, cs, info, dHat2, kap, T(0), true, massv, DBCb, sysNew);
+    auto& A = sysRef.Get_Matrix();
+    auto& B = sysNew.Get_Matrix();
+    double amax = 0, dmax = 0, missing = 0;
+    for (int r = 0; r < nV * dim; ++r) {
+        int q = B.outerIndexPtr()[r];
+        for (int p = A.outerIndexPtr()[r]; p < A.outerIndexPtr()[r + 1]; ++p) {
+            const int c = A.innerIndexPtr()[p];
+            while (q < B.outerIndexPtr()[r + 1] && B.innerIndexPtr()[q] < c) { dmax = std::max(dmax, std::fabs(B.valuePtr()[q])); ++q; } // explicit zeros of the 3x3 blocks
+            const double a = A.valuePtr()[p];
+            amax = std::max(amax, std::fabs(a));
+            if (q < B.outerIndexPtr()[r + 1] && B.innerIndexPtr()[q] == c) { dmax = std::max(dmax, std::fabs(a - B.valuePtr()[q])); ++q; }
+            else if (a != 0.0) missing += 1;
+        }
+        for (; q < B.outerIndexPtr()[r + 1]; ++q) dmax = std::max(dmax, std::fabs(B.valuePtr()[q]));
+    }
+    report[0] = (double)A.nonZeros(); report[1] = (double)B.nonZeros(); report[2] = amax; report[3] = dmax; report[4] = missing;
     return 0;
 }

@@ -329,6 +329,39 @@ def test_b2_side_by_side_with_reference_types(lib_built, cases):
         assert m_new == m_ref and deq == 1.0
 
 
+def test_b2_flow_system_matrix_with_reference_types(lib_built, orc, cases):
+    """tests/host_shim/b2_side_by_side.cpp::b2_flow_system: the `flow` branch of Compute_IncPotential_Hessian
+    (Shell/INC_POTENTIAL.h:321-394) -- the reference's own Compute_Barrier_Hessian + CSR_MATRIX (Construct_From_Triplet,
+    += M, Project_DBC) against B200::Compute_IncPotential_Hessian_Flow (device assembly, Construct_From_CSR hand-over)."""
+    import ctypes as C
+    import os
+    from conftest import ROOT
+    so = os.path.join(ROOT, "tests", "host_shim", "libb2_side_by_side.so")
+    if not os.path.exists(so):
+        pytest.skip("libb2_side_by_side.so is built where /root/reference exists (make -C tests/host_shim)")
+    drv = C.CDLL(so)
+    if not hasattr(drv, "b2_flow_system"):
+        pytest.skip("stale libb2_side_by_side.so")
+    drv.b2_flow_system.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                   C.c_double, C.c_double, C.c_double, C.c_void_p]
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    for name, m, d, dhats in cases[:2]:
+        dh = dhats[-1]
+        rng = np.random.default_rng(8)
+        rows, _info, _, _ = orc.constraint_set(omesh(orc, m), dh * dh)
+        rows = np.ascontiguousarray(rows, np.int32)
+        F = np.ascontiguousarray(m.btri[:, :3], np.int32)
+        vol = rng.uniform(0.5, 2.0, len(F)) * 1e-4
+        mass = rng.uniform(0.1, 1.0, m.nV)
+        dbc = (rng.uniform(size=m.nV) < 0.06).astype(np.uint8)
+        X = np.ascontiguousarray(m.X); X0 = np.ascontiguousarray(m.X0)
+        rep = np.zeros(8)
+        assert drv.b2_flow_system(m.nV, P(X), P(X0), len(F), P(F), P(vol), P(mass), P(dbc), len(rows), P(rows), 0.01, dh * dh, KAPPA, P(rep)) == 0
+        nnz_ref, nnz_new, amax, dmax, missing = rep[:5]
+        assert nnz_ref > 0 and nnz_new >= nnz_ref and missing == 0, (name, rep[:5])
+        assert dmax <= RTOL * amax, (name, dmax, amax)
+
+
 def test_ipc_energy_plugin_routed_to_b200(lib_built, orc, cases):
     """tests/host_shim/ipc_energy_plugin.cpp: the reference's own plugin class IPC_ENERGY<T,3,false> (FEM/Energy/IPC_ENERGY.h:11-58,
     compiled unmodified from /root/reference) with its three barrier calls qualified B200::, driven through the
