@@ -36,7 +36,7 @@ if world > 1:
 ctx.set_surface_mesh(mesh)
 for sigma in (0.5 * h, 1.0 * h, 2.0 * h, 4.0 * h):
     ctx.set_search_direction(np.ascontiguousarray(d * sigma))
-    for a0 in (1.0, 0.25):
+    for a0 in (1.0, 0.5, 0.25, 0.1):  # the full alpha0 grid
         for xi in (0.0, 1e-4):
             for _ in range(2):
                 a = ctx.ccd_step_resident(a0, xi)  # warm-up (buffers sized)
