@@ -456,7 +456,9 @@ def main():
             if "rows" not in bufs or bufs["rows"].shape[0] < nl:
                 bufs["rows"] = torch.empty((int(nl * 1.1) + 16, 4), dtype=torch.int32).pin_memory()
                 bufs["info"] = torch.empty((int(nl * 1.1) + 16, 2), dtype=torch.float64).pin_memory()
-            ctx._ck(ctx.L.idp_get_constraints(ctx.h, bufs["rows"].numpy().ctypes.data, bufs["info"].numpy().ctypes.data))
+            # asynchronous hand-over (idp_*_begin / idp_transfers_end): the rows travel while the barrier terms are evaluated,
+            # the CSR while the line-search filter (CCD) and min-distance run; everything is complete before the step ends
+            ctx._ck(ctx.L.idp_get_constraints_begin(ctx.h, bufs["rows"].numpy().ctypes.data, bufs["info"].numpy().ctypes.data))
             E, nnz = ctx.barrier_all(dhat2, KAPPA)
             g_host.zero_()
             # gradient accumulate + CSR to the host (what the reference's Newton solve consumes)
@@ -465,10 +467,11 @@ def main():
                 bufs["ptr"] = torch.empty(3 * mesh.nV + 1, dtype=torch.int32).pin_memory()
                 bufs["col"] = torch.empty(int(nnz * 1.1) + 16, dtype=torch.int32).pin_memory()
                 bufs["val"] = torch.empty(int(nnz * 1.1) + 16, dtype=torch.float64).pin_memory()
-            ctx._ck(ctx.L.idp_get_hessian_csr(ctx.h, bufs["ptr"].numpy().ctypes.data, bufs["col"].numpy().ctypes.data,
-                                              bufs["val"].numpy().ctypes.data))
+            ctx._ck(ctx.L.idp_get_hessian_csr_begin(ctx.h, bufs["ptr"].numpy().ctypes.data, bufs["col"].numpy().ctypes.data,
+                                                    bufs["val"].numpy().ctypes.data))
             a = ctx.ccd_step(Dh.numpy(), 1.0)
             _, mn = ctx.min_dist2(want_all=False)
+            ctx._ck(ctx.L.idp_transfers_end(ctx.h))
             return n + ctx.count(3) + ctx.count(4), (n, nnz, E, a, mn, nl)
 
         for _ in range(2):
@@ -479,11 +482,14 @@ def main():
         h2d = 2 * mesh.nV * 3 * 8
         # bytes that cross PCIe per step on this rank: its rows (16 B; stencilInfo is filled on the host, weights are all one),
         # the gradient, the CSR (ptr, col, val) and the scalars
-        d2h = nl2 * 16 + mesh.nV * 3 * 8 + (3 * mesh.nV + 1) * 4 + nnz2 * 12 + 64
+        # CSR: values + one column vertex per 3x3 block + block-row starts (the scalar ptr / col arrays are expanded on the host)
+        d2h = nl2 * 16 + mesh.nV * 3 * 8 + (mesh.nV + 1) * 4 + nnz2 * 8 + (nnz2 // 9) * 4 + 64
         e2e = {"value": pairs_per_step * k2 / (wall2 * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": wall2 / k2, "steps": k2,
                "timed_region": "wall clock (max over ranks) around set_positions + constraint set + this rank's rows D2H + barrier E/g/H + g D2H + "
-                               "this rank's CSR D2H + search-direction H2D + CCD + min-dist, pinned host buffers; bytes are per rank"}
+                               "this rank's CSR D2H (compact block columns, expanded to Construct_From_CSR's ptr/col/val on the host) + search-direction H2D + "
+                               "CCD + min-dist, pinned host buffers, transfers overlapped with the following operator and completed "
+                               "(idp_transfers_end) inside the step; bytes are per rank"}
 
     # ---- parity of THIS run against the committed digests of the reference's own loops on the same mesh ----
     parity = None

@@ -30,7 +30,8 @@ EXPORTS = ["idp_create", "idp_destroy", "idp_last_error", "idp_set_stream", "idp
            "idp_gradient_device", "idp_get_gradient", "idp_ccd_step", "idp_set_search_direction", "idp_ccd_step_resident", "idp_min_dist2", "idp_comm_unique_id", "idp_comm_init",
            "idp_set_shard", "idp_kernel_launches", "idp_library_calls", "idp_reset_counters", "idp_stage_ms",
            "idp_last_count", "idp_measure_fp64_tflops", "idp_system_set_flow_term", "idp_system_set_mass", "idp_project_dbc",
-           "idp_solve_pcg", "idp_set_mesh_from_triangles", "idp_get_surface_primitives"]
+           "idp_solve_pcg", "idp_set_mesh_from_triangles", "idp_get_surface_primitives", "idp_get_constraints_begin",
+           "idp_get_hessian_csr_begin", "idp_transfers_end"]
 
 
 class IdpError(RuntimeError):
@@ -90,6 +91,9 @@ def load_library(path=LIB_PATH):
     L.idp_system_set_flow_term.argtypes = [vp, i, vp, i, vp, d]
     L.idp_system_set_mass.argtypes = [vp, vp]
     L.idp_project_dbc.argtypes = [vp]
+    L.idp_get_constraints_begin.argtypes = [vp, vp, vp]
+    L.idp_get_hessian_csr_begin.argtypes = [vp, vp, vp, vp]
+    L.idp_transfers_end.argtypes = [vp]
     L.idp_solve_pcg.argtypes = [vp, vp, vp, d, i, C.POINTER(i), C.POINTER(d)]
     L.idp_set_mesh_from_triangles.argtypes = [vp, i, i, vp, i, vp, i, vp]
     L.idp_get_surface_primitives.argtypes = [vp, C.POINTER(i), vp, C.POINTER(i), vp, C.POINTER(i), vp, vp, vp, vp]

@@ -1,6 +1,7 @@
 // extern "C" launcher layer of libidp_contact.so (include/idp_contact.h). Thin: argument checks, marshalling of
 // host buffers, and calls into the launchers of exact_kernels.cu / barrier_kernels.cu / comm.cu.
 #include "ctx.cuh"
+#include <chrono>
 #include <string.h>
 #include <thread>
 
@@ -68,9 +69,16 @@ void idp_destroy(idp_ctx* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     comm_destroy(c);
+    idp_transfers_end(c); // joins the host workers of pending transfers
     if (c->h_counters) cudaFreeHost(c->h_counters);
     if (c->h_red) cudaFreeHost(c->h_red);
     if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->copyStream) cudaStreamDestroy(c->copyStream);
+    if (c->evCopyFork) cudaEventDestroy(c->evCopyFork);
+    if (c->evRows) cudaEventDestroy(c->evRows);
+    if (c->evBlk) cudaEventDestroy(c->evBlk);
+    if (c->evVal) cudaEventDestroy(c->evVal);
+    if (c->h_blk) cudaFreeHost(c->h_blk);
     if (c->commStream) cudaStreamDestroy(c->commStream);
     if (c->evFork) cudaEventDestroy(c->evFork);
     if (c->evJoin) cudaEventDestroy(c->evJoin);
@@ -433,6 +441,138 @@ int idp_get_hessian_csr(idp_ctx* c, int* ptr, int* col, double* val)
     if (col && c->nnz) IDP_CK(c, cudaMemcpyAsync(col, c->csrCol.p, c->nnz * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     if (val && c->nnz) IDP_CK(c, cudaMemcpyAsync(val, c->csrVal.p, c->nnz * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     IDP_CK(c, cudaStreamSynchronize(c->stream));
+    return IDP_OK;
+}
+// ---- asynchronous result transfers ---------------------------------------------------------------------------------
+// The results a host-side Newton solve consumes are large (4 M triangles: 465 MB of rows, 4.8 GB of CSR). The *_begin
+// calls enqueue their device-to-host copies on a copy stream that only waits for what has been computed so far and
+// return; the caller goes on with the next operator (barrier evaluation while the rows travel, CCD and min-distance
+// while the CSR travels) and collects everything with idp_transfers_end. The CSR crosses PCIe in compact form -- values,
+// plus ONE column vertex per 3x3 block and the block-row starts (3.4 GB instead of 4.8) -- and the scalar (ptr, col) arrays
+// Construct_From_CSR takes are expanded by host threads while the values are still in flight.
+__global__ void __launch_bounds__(256) k_block_cols(const int* __restrict__ rowStart, const int* __restrict__ col, int nV, int* __restrict__ blkCol)
+{
+    const int lane = threadIdx.x & 31;
+    for (int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < nV; v += (gridDim.x * blockDim.x) >> 5) {
+        const int bs = rowStart[v], nb = rowStart[v + 1] - bs;
+        for (int s = lane; s < nb; s += 32) blkCol[bs + s] = col[9L * bs + 3 * s] / 3;
+    }
+}
+static int copy_stream_ready(idp_ctx* c)
+{
+    if (!c->copyStream) {
+        IDP_CK(c, cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
+        IDP_CK(c, cudaEventCreateWithFlags(&c->evCopyFork, cudaEventDisableTiming));
+        IDP_CK(c, cudaEventCreateWithFlags(&c->evRows, cudaEventDisableTiming));
+        IDP_CK(c, cudaEventCreateWithFlags(&c->evBlk, cudaEventDisableTiming));
+        IDP_CK(c, cudaEventCreateWithFlags(&c->evVal, cudaEventDisableTiming));
+    }
+    IDP_CK(c, cudaEventRecord(c->evCopyFork, c->stream));
+    IDP_CK(c, cudaStreamWaitEvent(c->copyStream, c->evCopyFork, 0));
+    return IDP_OK;
+}
+// a large copy is cut into pieces so that the small read-backs of the operators running meanwhile (counters, scalars) are not
+// queued behind gigabytes on the same copy engine
+static int copy_d2h_chunked(idp_ctx* c, void* dst, const void* src, size_t bytes)
+{
+    const size_t chunk = 32u << 20;
+    for (size_t o = 0; o < bytes; o += chunk)
+        IDP_CK(c, cudaMemcpyAsync((char*)dst + o, (const char*)src + o, std::min(chunk, bytes - o), cudaMemcpyDeviceToHost, c->copyStream));
+    return IDP_OK;
+}
+int idp_get_constraints_begin(idp_ctx* c, int* rows4, double* info2)
+{
+    if (!c) return IDP_ERR_INVALID;
+    IDP_CK(c, cudaSetDevice(c->device));
+    if (c->pendRows) return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "idp_get_constraints_begin: a transfer is already pending (idp_transfers_end)", __FILE__, __LINE__);
+    if (!c->weights_all_one && info2) { // caller-supplied weights: nothing to overlap, the plain getter does it
+        return idp_get_constraints(c, rows4, info2);
+    }
+    IDP_TRY(copy_stream_ready(c));
+    if (rows4 && c->nRows) IDP_TRY(copy_d2h_chunked(c, rows4, c->rows.p, c->nRows * sizeof(Row4)));
+    IDP_CK(c, cudaEventRecord(c->evRows, c->copyStream));
+    c->pendRows = true;
+    if (info2 && c->nRows) { // weights are all one (OIPC, IPC.h:656-660): stencilInfo is filled by host threads while the rows travel
+        const double dh2 = c->cs_dhat2;
+        const long n = c->nRows;
+        c->rowsWorker = new std::thread([=]() {
+            host_parallel(n, [=](long b, long e) { for (long i = b; i < e; ++i) { info2[2 * i] = 1.0; info2[2 * i + 1] = dh2; } });
+        });
+    }
+    return IDP_OK;
+}
+int idp_get_hessian_csr_begin(idp_ctx* c, int* ptr, int* col, double* val)
+{
+    if (!c || !ptr || !col || !val) return c ? fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "idp_get_hessian_csr_begin: ptr, col and val are required", __FILE__, __LINE__) : IDP_ERR_INVALID;
+    IDP_CK(c, cudaSetDevice(c->device));
+    if (c->pendCsr) return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "idp_get_hessian_csr_begin: a transfer is already pending (idp_transfers_end)", __FILE__, __LINE__);
+    if (c->nnz <= 0) return idp_get_hessian_csr(c, ptr, col, val);
+    IDP_TRY(copy_stream_ready(c));
+    const long nBlk = c->nBlocksUnique;
+    const size_t need = (size_t)c->nV + 1 + (size_t)nBlk;
+    if (need > c->h_blk_cap) {
+        if (c->h_blk) cudaFreeHost(c->h_blk);
+        c->h_blk = nullptr; c->h_blk_cap = 0;
+        IDP_CK(c, cudaMallocHost((void**)&c->h_blk, (need + need / 8) * sizeof(int)));
+        c->h_blk_cap = need + need / 8;
+    }
+    IDP_CK(c, c->blkCol.reserve(nBlk));
+    k_block_cols<<<std::min(blocks_for(32L * c->nV, 256), (unsigned)c->sm_count * 16), 256, 0, c->copyStream>>>(c->rowStart.p, c->csrCol.p, c->nV, c->blkCol.p);
+    ++c->launches;
+    IDP_CK(c, cudaMemcpyAsync(c->h_blk, c->rowStart.p, ((size_t)c->nV + 1) * sizeof(int), cudaMemcpyDeviceToHost, c->copyStream));
+    IDP_TRY(copy_d2h_chunked(c, c->h_blk + c->nV + 1, c->blkCol.p, (size_t)nBlk * sizeof(int)));
+    IDP_CK(c, cudaEventRecord(c->evBlk, c->copyStream));
+    IDP_TRY(copy_d2h_chunked(c, val, c->csrVal.p, c->nnz * sizeof(double)));
+    IDP_CK(c, cudaEventRecord(c->evVal, c->copyStream));
+    c->pendCsr = true;
+    // host threads expand (block-row starts, block columns) into the scalar ptr / col arrays while the values are in flight
+    const int* rs = c->h_blk;
+    const int* bc = c->h_blk + c->nV + 1;
+    const long nV = c->nV;
+    const int device = c->device;
+    cudaEvent_t evBlk = c->evBlk;
+    int* status = &c->workerStatus;
+    c->workerStatus = 0;
+    c->csrWorker = new std::thread([=]() {
+        if (cudaSetDevice(device) != cudaSuccess || cudaEventSynchronize(evBlk) != cudaSuccess) { *status = IDP_ERR_CUDA; return; }
+        host_parallel(nV, [=](long b, long e) {
+            for (long v = b; v < e; ++v) {
+                const long bs = rs[v], nb = rs[v + 1] - bs;
+                for (int a = 0; a < 3; ++a) {
+                    const long p0 = 9 * bs + (long)a * 3 * nb;
+                    ptr[3 * v + a] = (int)p0;
+                    int* o = col + p0;
+                    for (long s = 0; s < nb; ++s) { const int c3 = 3 * bc[bs + s]; o[3 * s] = c3; o[3 * s + 1] = c3 + 1; o[3 * s + 2] = c3 + 2; }
+                }
+            }
+        });
+        ptr[3 * nV] = 9 * rs[nV];
+    });
+    return IDP_OK;
+}
+int idp_transfers_end(idp_ctx* c)
+{
+    if (!c) return IDP_ERR_INVALID;
+    IDP_CK(c, cudaSetDevice(c->device));
+    const bool dbg = getenv("IDP_DEBUG") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
+    double t1 = t0, t2 = t0;
+    auto join = [](void*& w) { if (w) { std::thread* t = (std::thread*)w; t->join(); delete t; w = nullptr; } };
+    if (c->pendRows) {
+        c->pendRows = false;
+        join(c->rowsWorker);
+        IDP_CK(c, cudaEventSynchronize(c->evRows));
+    }
+    t1 = now();
+    if (c->pendCsr) {
+        c->pendCsr = false;
+        join(c->csrWorker);
+        t2 = now();
+        IDP_CK(c, cudaEventSynchronize(c->evVal));
+        if (c->workerStatus != IDP_OK) return fail(c, IDP_ERR_CUDA, "%s (%s:%d)", "idp_transfers_end: the CSR expansion thread failed", __FILE__, __LINE__);
+    }
+    if (dbg) fprintf(stderr, "[idp] transfers_end: rows %.1f ms, CSR expansion %.1f, wait values %.1f\n", t1 - t0, t2 - t1, now() - t2);
     return IDP_OK;
 }
 int idp_hessian_csr_device(idp_ctx* c, const int** d_ptr, const int** d_col, const double** d_val, long* nnz)

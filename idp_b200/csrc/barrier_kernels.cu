@@ -877,6 +877,7 @@ __global__ void k_lower_starts(const int* __restrict__ sortedCol, long nLower, i
 
 int assemble_csr(idp_ctx* c)
 {
+    if (c->pendCsr) IDP_CK(c, cudaStreamWaitEvent(c->stream, c->evVal, 0)); // a pending idp_get_hessian_csr_begin still reads the old CSR
     StageTimer tm(c, IDP_STAGE_CSR);
     IDP_CK(c, c->csrPtr.reserve(3 * (size_t)c->nV + 1));
     const long n = c->nBlocksEmitted;

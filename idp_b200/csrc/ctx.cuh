@@ -102,6 +102,16 @@ struct idp_ctx {
     int device = 0;
     cudaStream_t stream = 0;
     bool own_stream = false;
+    // ---- asynchronous result transfers (idp_get_*_begin / idp_transfers_end): a copy stream beside the compute stream ----
+    cudaStream_t copyStream = nullptr;
+    cudaEvent_t evCopyFork = nullptr, evRows = nullptr, evBlk = nullptr, evVal = nullptr;
+    bool pendRows = false, pendCsr = false;
+    int* pendRowsOut = nullptr; double* pendInfoOut = nullptr; long pendRowsN = 0;
+    int* pendPtr = nullptr; int* pendCol = nullptr; double* pendVal = nullptr;
+    int* h_blk = nullptr; size_t h_blk_cap = 0;     // pinned: rowStart (nV + 1) + block column vertices
+    void* rowsWorker = nullptr; void* csrWorker = nullptr; // std::thread*: host-side fill / expansion running beside the copies
+    int workerStatus = 0;
+    idp::DBuf<int> blkCol;
     cudaStream_t commStream = nullptr;              // NCCL collectives that overlap local work (idp_barrier_all)
     cudaEvent_t evFork = nullptr, evJoin = nullptr;
     std::string err;

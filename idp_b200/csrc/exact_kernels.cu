@@ -1070,6 +1070,7 @@ static int prep_primitives(idp_ctx* c, PrepArgs pa, bool ccd)
 // ------------------------------------------------------------------------------------------------------------
 int build_constraint_set(idp_ctx* c, double dhat2_in, double thickness)
 {
+    if (c->pendRows) IDP_CK(c, cudaStreamWaitEvent(c->stream, c->evRows, 0)); // a pending idp_get_constraints_begin still reads the old rows
     c->permValid = false;
     c->dist2Valid = false;
     if (!c->have_x) return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "positions not set", __FILE__, __LINE__);

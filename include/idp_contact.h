@@ -110,6 +110,15 @@ int idp_barrier_hessian(idp_ctx* ctx, double dhat2, double kappa, double thickne
 int idp_barrier_all(idp_ctx* ctx, double dhat2, double kappa, double thickness, int project_spd, double* E_inout, long* nnz);
 /* copy the CSR to the host: exactly the (ptr, col, val) arrays CSR_MATRIX::Construct_From_CSR takes (CSR_MATRIX.h:33-47) */
 int idp_get_hessian_csr(idp_ctx* ctx, int* ptr, int* col, double* val);
+/* Asynchronous variants for hosts that overlap the hand-over with the next operator (the Newton step goes on with the line
+ * search while the matrix travels): *_begin enqueues the device-to-host copies on a copy stream and returns; the output
+ * buffers must stay valid (and should be pinned) until idp_transfers_end has returned, which completes every pending
+ * transfer. The CSR crosses PCIe compactly (values + one column vertex per 3x3 block + block-row starts) and the scalar
+ * (ptr, col) arrays of Construct_From_CSR are expanded by host threads inside idp_transfers_end while the values are still
+ * in flight. Results are identical to the synchronous getters. */
+int idp_get_constraints_begin(idp_ctx* ctx, int* rows4, double* info2);
+int idp_get_hessian_csr_begin(idp_ctx* ctx, int* ptr, int* col, double* val);
+int idp_transfers_end(idp_ctx* ctx);
 /* device pointers (valid until the next idp_barrier_hessian / idp_barrier_all on this context) */
 int idp_hessian_csr_device(idp_ctx* ctx, const int** d_ptr, const int** d_col, const double** d_val, long* nnz);
 int idp_gradient_device(idp_ctx* ctx, const double** d_g_xyz);

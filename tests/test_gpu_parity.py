@@ -329,6 +329,33 @@ def test_b2_side_by_side_with_reference_types(lib_built, cases):
         assert m_new == m_ref and deq == 1.0
 
 
+def test_async_transfers_match_the_synchronous_getters(gpu_ctx, cases):
+    """idp_get_constraints_begin / idp_get_hessian_csr_begin + idp_transfers_end (copy stream, compact block-column CSR
+    expanded on the host) against idp_get_constraints / idp_get_hessian_csr, with other operators running in between."""
+    c = gpu_ctx
+    for name, m, d, dhats in cases[:2]:
+        c.set_surface_mesh(m)
+        dh = dhats[-1]
+        n = c.constraint_set(dh * dh)
+        rows, info = c.get_constraints()
+        rows2 = np.full_like(rows, -7); info2 = np.full_like(info, -7.0)
+        c._ck(c.L.idp_get_constraints_begin(c.h, rows2.ctypes.data, info2.ctypes.data))
+        E, nnz = c.barrier_all(dh * dh, KAPPA)            # runs while the rows travel
+        ptr = np.full(3 * m.nV + 1, -7, np.int32); col = np.full(nnz, -7, np.int32); val = np.full(nnz, -7.0)
+        c._ck(c.L.idp_get_hessian_csr_begin(c.h, ptr.ctypes.data, col.ctypes.data, val.ctypes.data))
+        a = c.ccd_step(d, 1.0)                             # runs while the CSR travels
+        c.min_dist2(want_all=False)
+        c._ck(c.L.idp_transfers_end(c.h))
+        assert np.array_equal(rows, rows2) and np.array_equal(info, info2), name
+        sptr, scol, sval = c.get_hessian_csr()
+        assert np.array_equal(ptr, sptr) and np.array_equal(col, scol) and np.array_equal(val, sval), name
+        # a second begin without end is refused; end with nothing pending is a no-op
+        c._ck(c.L.idp_transfers_end(c.h))
+        c._ck(c.L.idp_get_hessian_csr_begin(c.h, ptr.ctypes.data, col.ctypes.data, val.ctypes.data))
+        assert c.L.idp_get_hessian_csr_begin(c.h, ptr.ctypes.data, col.ctypes.data, val.ctypes.data) != 0
+        c._ck(c.L.idp_transfers_end(c.h))
+
+
 def test_b2_flow_system_matrix_with_reference_types(lib_built, orc, cases):
     """tests/host_shim/b2_side_by_side.cpp::b2_flow_system: the `flow` branch of Compute_IncPotential_Hessian
     (Shell/INC_POTENTIAL.h:321-394) -- the reference's own Compute_Barrier_Hessian + CSR_MATRIX (Construct_From_Triplet,
