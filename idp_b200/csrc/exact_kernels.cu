@@ -796,19 +796,28 @@ __device__ __forceinline__ unsigned long long dup_key(const Row4& r, int bits, l
     const unsigned long long p = (unsigned long long)(nV - 1 - (long long)(-r.a - 1)); // k0 = -p-1 ascending <=> p descending
     return (p << (2 * bits)) | ((unsigned long long)r.b << bits) | (unsigned long long)(r.c + 1);
 }
-__global__ void __launch_bounds__(256) k_classify_pt(ClassifyArgs a)
+__global__ void __launch_bounds__(256, 3) k_classify_pt(ClassifyArgs a)
 {
     const long stride = (long)gridDim.x * blockDim.x;
     const long nRound = (a.nCand + 31) / 32 * 32;
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nRound; i += stride) {
+    const long i0 = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int2 zero2 = make_int2(0, 0);
+    int2 c1 = i0 < a.nCand ? a.cand[i0] : zero2;
+    int2 c2 = i0 + stride < a.nCand ? a.cand[i0 + stride] : zero2;
+    int v1 = a.nCand ? a.bnode[c1.x] : 0;
+    int4 t1n = a.nCand ? a.btri[c1.y] : make_int4(0, 0, 0, 0);
+    for (long i = i0; i < nRound; i += stride) {
         bool direct = false, dup = false;
         Row4 r = {0, 0, 0, 0};
         long long ckey = 0;
+        const int2 c = c1;
+        const int vI = v1;
+        const int4 t = t1n;
+        c1 = c2;
+        v1 = a.bnode[c1.x]; t1n = a.btri[c1.y];
+        c2 = i + 2 * stride < a.nCand ? a.cand[i + 2 * stride] : zero2;
         if (i < a.nCand) {
-            const int2 c = a.cand[i];
             ckey = (long long)c.x * a.nPartner + c.y;
-            const int vI = a.bnode[c.x];
-            const int4 t = a.btri[c.y];
             const V3 p = ldv(a.xp, vI), t0 = ldv(a.xp, t.x), t1 = ldv(a.xp, t.y), t2 = ldv(a.xp, t.z);
             const int ty = pt_type(p, t0, t1, t2);
             const double d = dist2_pt_by_type(ty, p, t0, t1, t2);
@@ -833,18 +842,27 @@ __global__ void __launch_bounds__(256) k_classify_pt(ClassifyArgs a)
         if (dup && s >= 0) { if (a.dupBits) a.keysDup[s] = dup_key(r, a.dupBits, a.nV); else a.rowsDup[s] = r; }
     }
 }
-__global__ void __launch_bounds__(256) k_classify_ee(ClassifyArgs a)
+// The gathers of a candidate form a dependent chain candidate -> edge vertices -> positions; the first two links are
+// fetched one and two iterations ahead (the kernel was long-scoreboard bound at 16 warps/SM).
+__global__ void __launch_bounds__(256, 3) k_classify_ee(ClassifyArgs a)
 {
     const long stride = (long)gridDim.x * blockDim.x;
     const long nRound = (a.nCand + 31) / 32 * 32;
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nRound; i += stride) {
+    const long i0 = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int2 zero2 = make_int2(0, 0);
+    int2 c1 = i0 < a.nCand ? a.cand[i0] : zero2;                     // candidate of this iteration
+    int2 c2 = i0 + stride < a.nCand ? a.cand[i0 + stride] : zero2;   // ... of the next one
+    int2 ea1 = a.bedge[c1.x], eb1 = a.bedge[c1.y];
+    for (long i = i0; i < nRound; i += stride) {
         bool direct = false, dup = false;
         Row4 r = {0, 0, 0, 0};
         long long ckey = 0;
+        const int2 c = c1, ea = ea1, eb = eb1;
+        c1 = c2;
+        ea1 = a.bedge[c1.x]; eb1 = a.bedge[c1.y];
+        c2 = i + 2 * stride < a.nCand ? a.cand[i + 2 * stride] : zero2;
         if (i < a.nCand) {
-            const int2 c = a.cand[i];
             ckey = (long long)c.x * a.nPartner + c.y;
-            const int2 ea = a.bedge[c.x], eb = a.bedge[c.y];
             const V3 a0 = ldv(a.xp, ea.x), a1 = ldv(a.xp, ea.y), b0 = ldv(a.xp, eb.x), b1 = ldv(a.xp, eb.y);
             const int ty = ee_type(a0, a1, b0, b1);
             const double d = dist2_ee_by_type(ty, a0, a1, b0, b1);
@@ -1337,9 +1355,10 @@ int sorted_candidates(idp_ctx* c, int which, int2* host_out)
     IDP_CK(c, c->blkKeySorted.reserve(n));
     IDP_LAUNCH(c, k_pack_pairs, blocks_for(n, 256), 256, 0, src.p, n, c->blkKey.p);
     size_t bytes = 0;
-    IDP_CK(c, cub::DeviceRadixSort::SortKeys(nullptr, bytes, c->blkKey.p, c->blkKeySorted.p, (int)n, 0, 64, c->stream));
+    // 64-bit item count: the CCD-only stress config produces up to 7 G swept-AABB candidates (> 2^31)
+    IDP_CK(c, cub::DeviceRadixSort::SortKeys(nullptr, bytes, c->blkKey.p, c->blkKeySorted.p, (long long)n, 0, 64, c->stream));
     IDP_CK(c, c->cubTemp.reserve(bytes));
-    IDP_CK(c, cub::DeviceRadixSort::SortKeys(c->cubTemp.p, bytes, c->blkKey.p, c->blkKeySorted.p, (int)n, 0, 64, c->stream));
+    IDP_CK(c, cub::DeviceRadixSort::SortKeys(c->cubTemp.p, bytes, c->blkKey.p, c->blkKeySorted.p, (long long)n, 0, 64, c->stream));
     ++c->lib_launches;
     IDP_LAUNCH(c, k_unpack_pairs, blocks_for(n, 256), 256, 0, c->blkKeySorted.p, n, (int2*)c->blkKey.p);
     IDP_CK(c, cudaMemcpyAsync(host_out, c->blkKey.p, n * sizeof(int2), cudaMemcpyDeviceToHost, c->stream));
