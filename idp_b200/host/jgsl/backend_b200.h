@@ -1,0 +1,129 @@
+// The B200 backend of the flow time step (shell_flow.h): every operator is one call into the C ABI of libidp_contact.so
+// (include/idp_contact.h). The constraint set, the barrier rows, the system matrix (flow + mass + projected barrier
+// Hessians), Project_DBC and the linear solve never leave the device; the host sees scalars, the 3 nV gradient and the
+// 3 nV search direction. There is no CPU fallback: without a CUDA device idp_create fails and the step exits like the
+// reference does on a fatal condition (message + exit(-1)).
+#pragma once
+#include <cstdio>
+#include <cstdlib>
+
+#include "idp_contact.h"
+#include "shell_flow.h"
+
+namespace jgsl {
+
+class B200Backend : public ContactBackend {
+public:
+    double pcg_rel_tol = 1e-10; // Solve_Direct is a factorisation in the reference; the iterative solve states its tolerance
+    int pcg_max_iter = 20000;
+    long pcg_iters_total = 0, newton_solves = 0;
+
+    explicit B200Backend(int device = 0)
+    {
+        const int rc = idp_create(device, &ctx_);
+        if (rc != IDP_OK) {
+            printf("JGSL (B200): no usable CUDA device / libidp_contact context (status %d); this build has no CPU path\n", rc);
+            exit(-1);
+        }
+    }
+    ~B200Backend() override { if (ctx_) idp_destroy(ctx_); }
+    const char* name() const override { return "B200"; }
+    idp_ctx* context() const { return ctx_; }
+
+    void set_mesh(int nV, const std::vector<int>& tri3, const double* x, const std::vector<uint8_t>& dbc) override
+    {
+        // Find_Surface_Primitives_And_Compute_Area runs once per mesh content, not once per time step (IMPLICIT_EULER.h:222 "TODO: only once")
+        if (nV != nV_ || tri3 != tri_ || dbc != dbc_) {
+            check(idp_set_mesh_from_triangles(ctx_, nV, (int)(tri3.size() / 3), tri3.data(), 3, x, 3, dbc.data()));
+            nV_ = nV; tri_ = tri3; dbc_ = dbc;
+            termsSet_ = false;
+        }
+        fresh_ = false;
+    }
+    void set_rest_positions(const double* x0) override { check(idp_set_rest_positions(ctx_, x0, 3)); fresh_ = false; }
+    void set_system_terms(const std::vector<int>& elem3, const std::vector<double>& vol, double h, const std::vector<double>& mass) override
+    {
+        if (termsSet_ && elem3 == elem_ && vol == vol_ && h == h_ && mass == mass_) return;
+        check(idp_system_set_flow_term(ctx_, (int)(elem3.size() / 3), elem3.data(), 3, vol.data(), h));
+        check(idp_system_set_mass(ctx_, mass.data()));
+        elem_ = elem3; vol_ = vol; h_ = h; mass_ = mass;
+        termsSet_ = true;
+        fresh_ = false;
+    }
+    void set_positions(const double* x) override { check(idp_set_positions(ctx_, x, 3)); fresh_ = false; }
+    int constraint_set(double dHat2, double thickness) override
+    {
+        int n = 0;
+        check(idp_constraint_set(ctx_, dHat2, thickness, &n));
+        fresh_ = false;
+        return n;
+    }
+    void barrier_energy(double dHat2, double kappa, double thickness, double& E) override
+    {
+        check(idp_barrier_energy(ctx_, dHat2, kappa, thickness, &E));
+    }
+    void barrier_gradient(double dHat2, double kappa, double thickness, double* g) override
+    {
+        // one pass over the rows produces the gradient AND the assembled system matrix the solve of this iterate needs
+        long nnz = 0;
+        check(idp_barrier_all(ctx_, dHat2, kappa, thickness, 1, nullptr, &nnz));
+        check(idp_get_gradient(ctx_, g, 3));
+        fresh_ = true; freshKappa_ = kappa; freshDHat2_ = dHat2;
+    }
+    bool solve_newton_system(double dHat2, double kappa, double thickness, const double* rhs, double* sol) override
+    {
+        if (!(fresh_ && freshKappa_ == kappa && freshDHat2_ == dHat2)) {
+            long nnz = 0;
+            check(idp_barrier_hessian(ctx_, dHat2, kappa, thickness, 1, &nnz));
+        }
+        fresh_ = false; // Project_DBC rewrites the values in place
+        check(idp_project_dbc(ctx_));
+        int iters = 0;
+        double rel = 0;
+        check(idp_solve_pcg(ctx_, rhs, sol, pcg_rel_tol, pcg_max_iter, &iters, &rel));
+        pcg_iters_total += iters; ++newton_solves;
+        printf("linear solve (device PCG): %d iterations, relative residual %le\n", iters, rel);
+        return rel <= 1e3 * pcg_rel_tol && rel == rel;
+    }
+    double ccd(const double* dir, double thickness, double alpha) override
+    {
+        check(idp_ccd_step(ctx_, dir, 3, thickness, &alpha));
+        return alpha;
+    }
+    bool min_dist2(double thickness, std::vector<double>* dist2, double& minDist2) override
+    {
+        const long n = idp_last_count(ctx_, 0);
+        if (n <= 0) return false;
+        if (dist2) dist2->resize((size_t)n);
+        check(idp_min_dist2(ctx_, thickness, dist2 ? dist2->data() : nullptr, &minDist2));
+        return true;
+    }
+    void get_rows(std::vector<int>& rows4, std::vector<double>& info2) override
+    {
+        const long n = idp_last_count(ctx_, 0);
+        rows4.resize(4 * (size_t)n); info2.resize(2 * (size_t)n);
+        if (n) check(idp_get_constraints(ctx_, rows4.data(), info2.data()));
+    }
+    void set_rows(const std::vector<int>& rows4, const std::vector<double>& info2) override
+    {
+        check(idp_set_constraints(ctx_, (int)(rows4.size() / 4), rows4.data(), info2.data()));
+        fresh_ = false;
+    }
+
+private:
+    void check(int rc)
+    {
+        if (rc == IDP_OK) return;
+        printf("JGSL (B200): %s (status %d)\n", idp_last_error(ctx_), rc); // the reference prints and exits on its fatal conditions
+        exit(-1);
+    }
+    idp_ctx* ctx_ = nullptr;
+    int nV_ = -1;
+    std::vector<int> tri_, elem_;
+    std::vector<uint8_t> dbc_;
+    std::vector<double> vol_, mass_;
+    double h_ = 0, freshKappa_ = 0, freshDHat2_ = 0;
+    bool termsSet_ = false, fresh_ = false;
+};
+
+} // namespace jgsl

@@ -1,0 +1,56 @@
+"""Golden trace of BASELINE configs[0] (the paper's normal-flow example): the reference's UNCHANGED script
+Projects/FEMShell/12-14_normal_flow.py + Python/Drivers run from the writable mirror (scripts/make_ref_mirror.sh) on the
+`JGSL` module of this repository built with the REFERENCE's own CPU contact loops as its backend
+(tests/host_shim/jgsl_ref/JGSL.so: FEM/IPC.h + Grid/SPATIAL_HASH.h + Math/CSR_MATRIX.h compiled from /root/reference).
+Stores the input mesh, counter.txt (PN iterations and contact # per time step, Shell/IMPLICIT_EULER.h:857-864) and the
+final vertex positions. The B200 build of the same module must reproduce the trace (tests/test_gpu_jgsl_module.py).
+
+Run in the authoring container only (needs /root/reference):  python tests/golden/make_golden_normal_flow.py
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+MIRROR = os.path.join(ROOT, "baseline", "_ref", "IDP_mirror")
+CASES = [("bunny3K", "0.5", "-5e-3", "50"), ("hand", "0.5", "5e-3", "3")]  # batch.py:36-43 and :16-23
+
+
+def read_obj(path):
+    V, F = [], []
+    for line in open(path):
+        if line.startswith("v "):
+            V.append([float(t) for t in line.split()[1:4]])
+        elif line.startswith("f"):
+            F.append([int(t.split("/")[0]) - 1 for t in line.split()[1:4]])
+    return np.array(V, np.float64), np.array(F, np.int32)
+
+
+def main():
+    subprocess.check_call([os.path.join(ROOT, "scripts", "make_ref_mirror.sh")])
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "host_shim"), "jgsl_ref/JGSL.so"])
+    cwd = os.path.join(MIRROR, "Projects", "FEMShell")
+    subprocess.check_call(["chmod", "-R", "u+w", cwd])
+    out = {}
+    for mesh, smooth, mag, frames in CASES:
+        folder = os.path.join(cwd, "output", "12-14_normal_flow", "%s_%s_%s_%s" % (mesh, smooth, mag, frames))
+        subprocess.call(["rm", "-rf", folder])
+        env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "tests", "host_shim", "jgsl_ref"), OMP_NUM_THREADS="8")
+        subprocess.check_call([sys.executable, "12-14_normal_flow.py", mesh, smooth, mag, frames], cwd=cwd, env=env, stdout=subprocess.DEVNULL)
+        V, F = read_obj(os.path.join(cwd, "input", mesh + ".obj"))
+        Vend, _ = read_obj(os.path.join(folder, "shell%s.obj" % frames))
+        counter = np.array([[int(t) for t in l.split()] for l in open(os.path.join(folder, "counter.txt"))], np.int64)
+        out[mesh + "/V"] = V
+        out[mesh + "/F"] = F
+        out[mesh + "/args"] = np.array([smooth, mag, frames])
+        out[mesh + "/counter"] = counter
+        out[mesh + "/V_end"] = Vend
+        print(mesh, "steps", len(counter), "PN iterations", counter[:, 0].sum(), "last contact #", counter[-1, 1])
+    np.savez_compressed(os.path.join(HERE, "normal_flow_trace.npz"), **out)
+
+
+if __name__ == "__main__":
+    main()

