@@ -91,6 +91,10 @@ def load_library(path=LIB_PATH):
     L.idp_system_set_flow_term.argtypes = [vp, i, vp, i, vp, d]
     L.idp_system_set_mass.argtypes = [vp, vp]
     L.idp_project_dbc.argtypes = [vp]
+    L.idp_system_set_membrane.argtypes = [vp, i, vp, i, vp, vp, vp, vp, d]
+    L.idp_system_set_hinges.argtypes = [vp, i, vp, vp, d, d]
+    L.idp_elastic_energy.argtypes = [vp, C.POINTER(d)]
+    L.idp_elastic_gradient.argtypes = [vp, vp, i]
     L.idp_get_constraints_begin.argtypes = [vp, vp, vp]
     L.idp_get_hessian_csr_begin.argtypes = [vp, vp, vp, vp]
     L.idp_transfers_end.argtypes = [vp]
@@ -208,6 +212,34 @@ class ContactContext:
     def set_mass(self, m):
         m = None if m is None else np.ascontiguousarray(m, np.float64)
         self._ck(self.L.idp_system_set_mass(self.h, _p(m)))
+
+    def set_membrane(self, elem, ib, vol, lam, mu, h):
+        """Membrane triangles: rest first fundamental form ib = (IB00, IB01, IB11), vol, lambda, mu per element; weight h^2."""
+        if elem is None or len(elem) == 0:
+            return self._ck(self.L.idp_system_set_membrane(self.h, 0, None, 3, None, None, None, None, 0.0))
+        elem = np.ascontiguousarray(elem, np.int32)
+        n = len(elem)
+        ib = np.ascontiguousarray(ib, np.float64).reshape(n, 3)
+        vol, lam, mu = (np.ascontiguousarray(np.broadcast_to(a, n), np.float64) for a in (vol, lam, mu))
+        self._ck(self.L.idp_system_set_membrane(self.h, n, _p(elem), elem.shape[1], _p(ib), _p(vol), _p(lam), _p(mu), float(h)))
+
+    def set_hinges(self, stencil, info, k, h):
+        """Bending hinges: stencil (v0; v1, v2; v3), info = (rest angle, rest edge length, rest height); energy h^2 k (..)^2 e/h."""
+        if stencil is None or len(stencil) == 0:
+            return self._ck(self.L.idp_system_set_hinges(self.h, 0, None, None, 0.0, 0.0))
+        stencil = np.ascontiguousarray(stencil, np.int32).reshape(-1, 4)
+        info = np.ascontiguousarray(info, np.float64).reshape(-1, 3)
+        self._ck(self.L.idp_system_set_hinges(self.h, len(stencil), _p(stencil), _p(info), float(k), float(h)))
+
+    def elastic_energy(self, E0=0.0):
+        E = C.c_double(E0)
+        self._ck(self.L.idp_elastic_energy(self.h, C.byref(E)))
+        return E.value
+
+    def elastic_gradient(self, g_accum=None):
+        g = np.zeros((self.nV, 3), np.float64) if g_accum is None else g_accum
+        self._ck(self.L.idp_elastic_gradient(self.h, _p(g), g.shape[1]))
+        return g
 
     def project_dbc(self):
         self._ck(self.L.idp_project_dbc(self.h))

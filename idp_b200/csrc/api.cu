@@ -117,7 +117,7 @@ int idp_set_mesh(idp_ctx* c, int nV, int nBN, const int* bnode, int nBE, const i
     c->nV = nV; c->nBN = nBN; c->nBE = nBE; c->nBT = nBT;
     c->have_x = c->have_x0 = c->have_dir = false;
     c->meanEdgeVersion = -1; // new boundary edges
-    c->surfValid = false; c->nFlowElem = 0; c->haveMass = false;
+    c->surfValid = false; c->nFlowElem = 0; c->haveMass = false; c->nMem = 0; c->nHinge = 0;
     c->nRows = 0; c->nCandPT = c->nCandEE = c->nCcdPT = c->nCcdEE = 0;
     c->permValid = false;
     IDP_CK(c, c->bnode.reserve(std::max(nBN, 1)));
@@ -389,6 +389,81 @@ int idp_system_set_mass(idp_ctx* c, const double* m_per_vertex)
     c->haveMass = true;
     return IDP_OK;
 }
+// ---- elastic terms of the shell system (elastic_kernels.cu) ------------------------------------------
+int idp_system_set_membrane(idp_ctx* c, int n_elem, const int* elem3, int stride, const double* ib3, const double* vol, const double* lambda,
+    const double* mu, double h)
+{
+    if (!c || n_elem < 0 || (n_elem && (!elem3 || !ib3 || !vol || !lambda || !mu || stride < 3)))
+        return c ? fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "idp_system_set_membrane: bad arguments", __FILE__, __LINE__) : IDP_ERR_INVALID;
+    IDP_CK(c, cudaSetDevice(c->device));
+    c->nMem = 0;
+    if (n_elem == 0) return IDP_OK;
+    std::vector<int> e3(3 * (size_t)n_elem);
+    std::vector<double> coef((size_t)n_elem);
+    for (long e = 0; e < n_elem; ++e) {
+        const int a = elem3[(long)stride * e], b = elem3[(long)stride * e + 1], d = elem3[(long)stride * e + 2];
+        if (a < 0 || b < 0 || d < 0 || a >= c->nV || b >= c->nV || d >= c->nV || a == b || b == d || a == d)
+            return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "idp_system_set_membrane: element with out-of-range or repeated vertices", __FILE__, __LINE__);
+        e3[3 * e] = a; e3[3 * e + 1] = b; e3[3 * e + 2] = d;
+        coef[e] = h * h * vol[e];
+    }
+    IDP_CK(c, c->memElem.reserve(3 * (size_t)n_elem)); IDP_CK(c, c->memIB.reserve(3 * (size_t)n_elem));
+    IDP_CK(c, c->memCoef.reserve(n_elem)); IDP_CK(c, c->memLambda.reserve(n_elem)); IDP_CK(c, c->memMu.reserve(n_elem));
+    IDP_CK(c, cudaMemcpyAsync(c->memElem.p, e3.data(), e3.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    IDP_CK(c, cudaMemcpyAsync(c->memIB.p, ib3, 3 * (size_t)n_elem * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    IDP_CK(c, cudaMemcpyAsync(c->memCoef.p, coef.data(), (size_t)n_elem * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    IDP_CK(c, cudaMemcpyAsync(c->memLambda.p, lambda, (size_t)n_elem * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    IDP_CK(c, cudaMemcpyAsync(c->memMu.p, mu, (size_t)n_elem * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    IDP_CK(c, cudaStreamSynchronize(c->stream));
+    c->nMem = n_elem;
+    return IDP_OK;
+}
+int idp_system_set_hinges(idp_ctx* c, int n_hinge, const int* stencil4, const double* info3, double k, double h)
+{
+    if (!c || n_hinge < 0 || (n_hinge && (!stencil4 || !info3)))
+        return c ? fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "idp_system_set_hinges: bad arguments", __FILE__, __LINE__) : IDP_ERR_INVALID;
+    IDP_CK(c, cudaSetDevice(c->device));
+    c->nHinge = 0;
+    if (n_hinge == 0) return IDP_OK;
+    for (long e = 0; e < n_hinge; ++e) {
+        const int* v = stencil4 + 4 * e;
+        for (int i = 0; i < 4; ++i) {
+            if (v[i] < 0 || v[i] >= c->nV) return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "idp_system_set_hinges: vertex index out of range", __FILE__, __LINE__);
+            for (int j = 0; j < i; ++j)
+                if (v[i] == v[j]) return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "idp_system_set_hinges: repeated vertex in a hinge stencil", __FILE__, __LINE__);
+        }
+        if (!(info3[3 * e + 2] != 0.0)) return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "idp_system_set_hinges: zero rest height", __FILE__, __LINE__);
+    }
+    IDP_CK(c, c->hingeV.reserve(4 * (size_t)n_hinge)); IDP_CK(c, c->hingeInfo.reserve(3 * (size_t)n_hinge));
+    IDP_CK(c, cudaMemcpyAsync(c->hingeV.p, stencil4, 4 * (size_t)n_hinge * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    IDP_CK(c, cudaMemcpyAsync(c->hingeInfo.p, info3, 3 * (size_t)n_hinge * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    IDP_CK(c, cudaStreamSynchronize(c->stream));
+    c->nHinge = n_hinge;
+    c->hingeKh2 = h * h * k;
+    return IDP_OK;
+}
+int idp_elastic_energy(idp_ctx* c, double* E_inout)
+{
+    if (!c || !E_inout) return IDP_ERR_INVALID;
+    IDP_CK(c, cudaSetDevice(c->device));
+    double E = 0;
+    IDP_TRY(elastic_energy_gradient(c, 1, 0, &E));
+    *E_inout += E;
+    return IDP_OK;
+}
+int idp_elastic_gradient(idp_ctx* c, double* g_accum, int stride)
+{
+    if (!c || (g_accum && stride < 3)) return IDP_ERR_INVALID;
+    IDP_CK(c, cudaSetDevice(c->device));
+    IDP_TRY(elastic_energy_gradient(c, 0, 1, nullptr));
+    if (!g_accum) return IDP_OK;
+    std::vector<double> g(3 * (size_t)c->nV);
+    IDP_CK(c, cudaMemcpyAsync(g.data(), c->elasticG.p, g.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    IDP_CK(c, cudaStreamSynchronize(c->stream));
+    for (long v = 0; v < c->nV; ++v)
+        for (int a = 0; a < 3; ++a) g_accum[(long)stride * v + a] += g[3 * v + a];
+    return IDP_OK;
+}
 int idp_project_dbc(idp_ctx* c)
 {
     if (!c) return IDP_ERR_INVALID;
@@ -409,6 +484,7 @@ int idp_set_mesh_from_triangles(idp_ctx* c, int nV, int nF, const int* tri, int 
         for (int k = 0; k < 3; ++k)
             if (tri[(long)stride * i + k] < 0 || tri[(long)stride * i + k] >= nV) return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "idp_set_mesh_from_triangles: vertex index out of range", __FILE__, __LINE__);
     IDP_CK(c, cudaSetDevice(c->device));
+    c->nFlowElem = 0; c->haveMass = false; c->nMem = 0; c->nHinge = 0; // a new mesh drops the terms of the previous one
     return extract_surface(c, nV, nF, tri, stride, x, xstride, dbc);
 }
 int idp_get_surface_primitives(idp_ctx* c, int* nBN, int* bnode, int* nBE, int* bedge2, int* nBT, int* btri3, double* BNArea, double* BEArea, double* BTArea)

@@ -8,6 +8,7 @@
 #include "ctx.cuh"
 #include "pair_deriv.cuh"
 #include "psd_lowrank.cuh"
+#include "bucket_emit.cuh"
 #include <cub/cub.cuh>
 
 #ifndef IDP_BARRIER_T0
@@ -97,54 +98,6 @@ struct BarrierArgs {
     const int* vtxOff; int* vtxCursor; unsigned long long* bktKey; double* bktVal8; double* bktVal1; // Hessian block buckets
     unsigned long long* errDist;
     unsigned long long* errEig;
-};
-
-// Hessian sink: block (i,j), i <= j, of a row goes to the bucket of its lower vertex vlo = min(v[i], v[j]) (stored transposed
-// when v[i] > v[j]). A row reserves its slots in the (up to four) buckets with one atomic each; inside the reservation the
-// blocks are ordered by the stencil index of the higher vertex. Bucket entry: key (vhi << 32 | row << 4 | 4 i + j) -- the
-// low word is a deterministic origin tag that fixes the summation order of duplicates -- and the 3x3 values split 64 + 8
-// bytes (the 64-byte part is written as two full 32-byte sectors).
-struct BucketEmit {
-    unsigned long long* key; double* val8; double* val1;
-    int base[4]; int nv; int v[4]; unsigned rowTag; // v / base are only indexed with compile-time constants (registers, not local memory)
-    __device__ __forceinline__ void reserve(int* cursor)
-    {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            base[k] = 0;
-            if (k < nv) {
-                int m = 1;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) m += (j < nv && v[j] > v[k]) ? 1 : 0;
-                base[k] = atomicAdd(cursor + v[k], m); // the cursors start at the bucket offsets: nothing depends on the result before the first block is stored
-            }
-        }
-    }
-    __device__ __forceinline__ bool wants(int i, int j) const { return i <= j; }
-    // i, j are compile-time constants at every call site (unrolled loops)
-    __device__ __forceinline__ void operator()(int i, int j, const double* blk) const
-    {
-        const bool tr = v[i] > v[j];
-        const int va = tr ? v[j] : v[i], vb = tr ? v[i] : v[j]; // va: lower vertex, vb: higher (equal on the diagonal)
-        const int ba = tr ? base[j] : base[i];
-        int rnk = 0; // blocks of the row in bucket va are ordered by the stencil index of the higher vertex
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-            const bool before = tr ? (m < i) : (m < j);
-            const bool isA = tr ? (m == j) : (m == i);
-            rnk += (before && m < nv && (v[m] > va || isA)) ? 1 : 0;
-        }
-        const long s = (long)ba + rnk;
-        key[s] = ((unsigned long long)(unsigned)vb << 32) | (unsigned long long)(rowTag | (unsigned)(4 * i + j));
-        double t[9];
-#pragma unroll
-        for (int p = 0; p < 3; ++p)
-#pragma unroll
-            for (int q = 0; q < 3; ++q) t[3 * p + q] = tr ? blk[3 * q + p] : blk[3 * p + q];
-        double2* d8 = reinterpret_cast<double2*>(val8 + 8 * s);
-        d8[0] = make_double2(t[0], t[1]); d8[1] = make_double2(t[2], t[3]); d8[2] = make_double2(t[4], t[5]); d8[3] = make_double2(t[6], t[7]);
-        val1[s] = t[8];
-    }
 };
 
 // ---- the other Hessian terms of the flow Newton system, emitted into the same buckets --------------
@@ -320,7 +273,7 @@ int barrier_eval(idp_ctx* c, double dhat2, double kappa, double thickness, int w
         IDP_CK(c, cudaMemsetAsync(c->gbuf.p, 0, 3 * (size_t)c->nV * sizeof(double), c->stream));
     }
     if (want_h) { c->nnz = 0; c->nBlocksUnique = 0; c->nBlocksEmitted = 0; }
-    const bool extraTerms = want_h && (c->nFlowElem > 0 || c->haveMass); // flow / mass blocks are assembled even without contact rows
+    const bool extraTerms = want_h && (c->nFlowElem > 0 || c->haveMass || c->nMem > 0 || c->nHinge > 0); // the other terms are assembled even without contact rows
     if (c->nRows == 0 && !extraTerms) return IDP_OK;
     StageTimer tm(c, IDP_STAGE_BARRIER);
     IDP_CK(c, cudaMemsetAsync(c->counters.p + CNT_ERR_DIST, 0, sizeof(long long), c->stream));
@@ -369,11 +322,11 @@ int barrier_eval(idp_ctx* c, double dhat2, double kappa, double thickness, int w
     a.errDist = (unsigned long long*)(c->counters.p + CNT_ERR_DIST);
     a.errEig = (unsigned long long*)(c->counters.p + CNT_ERR_EIG);
     a.vtxOff = nullptr; a.vtxCursor = nullptr; a.bktKey = nullptr; a.bktVal8 = nullptr; a.bktVal1 = nullptr;
-    long nBlocks = 0, nExtra = 0;
+    long nBlocks = 0, nExtra = 0, nElastic = 0;
     ExtraArgs xaKeep = {};
     if (want_h) {
         c->csrProjected = false;
-        if (c->nRows + (long)c->nFlowElem + c->nV >= (1L << 28)) return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "more than 2^28 constraint rows (+ elements + vertices) on one rank", __FILE__, __LINE__);
+        if (c->nRows + (long)c->nFlowElem + c->nV + c->nMem + c->nHinge >= (1L << 28)) return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "more than 2^28 constraint rows (+ elements + vertices) on one rank", __FILE__, __LINE__);
         const size_t nV1 = (size_t)c->nV + 1;
         IDP_CK(c, c->vtxCnt.reserve(nV1)); IDP_CK(c, c->vtxOff.reserve(nV1)); IDP_CK(c, c->vtxCursor.reserve(nV1));
         IDP_CK(c, cudaMemsetAsync(c->vtxCnt.p, 0, nV1 * sizeof(int), c->stream));
@@ -388,6 +341,8 @@ int barrier_eval(idp_ctx* c, double dhat2, double kappa, double thickness, int w
         nExtra = (xa.eEnd - xa.eBegin) + (xa.mass ? xa.vEnd - xa.vBegin : 0);
         if (nExtra > 0) IDP_LAUNCH(c, k_extra_counts, std::min(blocks_for(nExtra, 256), (unsigned)c->sm_count * 16), 256, 0, xa);
         xaKeep = xa;
+        // membrane triangles and bending hinges (elastic_kernels.cu)
+        if (c->nMem > 0 || c->nHinge > 0) IDP_TRY(elastic_block_counts(c, c->vtxCnt.p, &nElastic));
         IDP_TRY(cub_scan_exclusive(c, c->vtxCnt.p, c->vtxOff.p, (long)nV1));
         int total = 0;
         IDP_CK(c, cudaMemcpyAsync(&total, c->vtxOff.p + c->nV, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -423,6 +378,7 @@ int barrier_eval(idp_ctx* c, double dhat2, double kappa, double thickness, int w
         xaKeep.tagBase = (unsigned)nMine;
         IDP_LAUNCH(c, k_extra_emit, std::min(blocks_for(nExtra, 256), (unsigned)c->sm_count * 16), 256, 0, xaKeep);
     }
+    if (want_h && nElastic > 0) IDP_TRY(elastic_emit_blocks(c, project_spd, (unsigned)(nMine + nExtra), c->vtxCursor.p, c->bktKey.p, c->bktVal8.p, c->bktVal1.p));
     if (nMine > 0 && want_e) IDP_LAUNCH(c, k_sum_partials, 1, 256, 0, c->red.p, 3 * (int)grid, c->red.p + 3 * (size_t)grid);
     long long nerr = 0, neig = 0;
     IDP_CK(c, cudaMemcpyAsync(&nerr, c->counters.p + CNT_ERR_DIST, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));

@@ -194,6 +194,12 @@ struct idp_ctx {
     double flowH = 0;
     bool haveMass = false;
     bool csrProjected = false;          // idp_project_dbc has been applied to the current CSR
+    // ---- elastic terms of the shell system (membrane triangles, bending hinges; elastic_kernels.cu) ----
+    idp::DBuf<int> memElem, hingeV;      // 3 / 4 vertex ids per element
+    idp::DBuf<double> memIB, memCoef, memLambda, memMu, hingeInfo; // IB (3 per triangle), h^2 vol, Lame parameters; (thetabar, ebar, hbar)
+    idp::DBuf<double> elasticG;         // gradient of the elastic terms (3 nV)
+    int nMem = 0, nHinge = 0;
+    double hingeKh2 = 0;                // h^2 k
     // ---- device-side surface extraction (idp_set_mesh_from_triangles) ----
     idp::DBuf<int> surfTri;
     idp::DBuf<double> surfTriArea, surfTriAreaH, surfNodeArea, surfNodeAreaC, surfEdgeArea, surfEdgeArea2;
@@ -313,6 +319,10 @@ int barrier_eval(idp_ctx* c, double dhat2, double kappa, double thickness, int w
     int project_spd, double* E_out);
 int assemble_csr(idp_ctx* c);
 int project_dbc(idp_ctx* c);
+// elastic terms: bucket counts / Hessian blocks for the assembly in barrier_eval, energy + gradient on request
+int elastic_block_counts(idp_ctx* c, int* vtxCnt, long* nElements);
+int elastic_emit_blocks(idp_ctx* c, int project_spd, unsigned tagBase, int* vtxCursor, unsigned long long* bktKey, double* bktVal8, double* bktVal1);
+int elastic_energy_gradient(idp_ctx* c, int want_e, int want_g, double* E_out);
 int solve_pcg(idp_ctx* c, const double* rhs, double* sol, double rel_tol, int max_iter, int* iters, double* rel_res);
 int extract_surface(idp_ctx* c, int nV, int nF, const int* tri, int stride, const double* x, int xstride, const unsigned char* dbc);
 int min_dist2(idp_ctx* c, double thickness, double* host_dist2, double* min_out);

@@ -138,6 +138,22 @@ int idp_get_gradient(idp_ctx* ctx, double* g_accum, int stride);
  * by contiguous ranges like the query primitives. */
 int idp_system_set_flow_term(idp_ctx* ctx, int n_elem, const int* elem3, int stride, const double* vol, double h);
 int idp_system_set_mass(idp_ctx* ctx, const double* m_per_vertex);
+/* Elastic terms of the discrete-shell system (FEM/Shell/INC_POTENTIAL.h:75-96, 213-232, 340-352: the non-flow branch), assembled
+ * into the same device CSR as the barrier rows by every following idp_barrier_hessian / idp_barrier_all, each element's
+ * Hessian projected to PSD when project_spd is set (makePD, Math/UTILS.h:9-27); they persist until replaced (n = 0 removes a
+ * term; idp_set_mesh* clears them). Elements whose vertices are all Dirichlet nodes (mask of idp_set_mesh*) are skipped.
+ *   membrane (FEM/Shell/MEMBRANE.h:8-315, neo-Hookean on the first fundamental form): per triangle (`stride` ints) the REST
+ *     first fundamental form ib3 = (IB00, IB01, IB11) (elemAttr IB, not inverted), vol, lambda, mu (elasticityAttr), weight h^2;
+ *   hinges (FEM/Shell/BENDING.h:52-80,176-213,438-497, KL = false): per hinge the stencil (v0; v1, v2; v3) of edgeStencil and
+ *     info3 = (rest angle, rest edge length, rest height) of edgeInfo (Shell/DISCRETE_SHELL.h:169-211); k = bendingStiffMult *
+ *     E t^3 / (24 (1 - nu^2)); energy h^2 k (theta - thetabar)^2 ebar / hbar. */
+int idp_system_set_membrane(idp_ctx* ctx, int n_elem, const int* elem3, int stride, const double* ib3, const double* vol, const double* lambda,
+    const double* mu, double h);
+int idp_system_set_hinges(idp_ctx* ctx, int n_hinge, const int* stencil4, const double* info3, double k, double h);
+/* Compute_Membrane_Energy + Compute_Bending_Energy (adds to *E_inout) and the matching gradients (g_accum[v*stride + a] +=;
+ * g_accum may be NULL) at the current positions. The barrier operators above stay barrier-only. */
+int idp_elastic_energy(idp_ctx* ctx, double* E_inout);
+int idp_elastic_gradient(idp_ctx* ctx, double* g_accum, int stride);
 /* CSR_MATRIX::Project_DBC (Math/CSR_MATRIX.h:130-141) applied to the device CSR with the Dirichlet mask of idp_set_mesh:
  * every stored entry whose row or column vertex is a Dirichlet node becomes (row == col). Single-GPU contexts. */
 int idp_project_dbc(idp_ctx* ctx);

@@ -202,6 +202,37 @@ class Oracle:
         L.orc_surface_free(hnd)
         return out
 
+    def membrane_batch(self, X, elem, ib, coef, lam, mu, dbc=None, project_spd=True, want_h=True):
+        """Membrane E / g / H per triangle (orc_elastic.hpp; MEMBRANE.h:8-315): returns E[e], g (nV x 3), H (nE x 9 x 9), active[e]."""
+        L = self.lib
+        L.orc_membrane_batch.argtypes = [C.c_int] + [C.c_void_p] * 7 + [C.c_int] + [C.c_void_p] * 4
+        X = _f64(X).reshape(-1, 3); elem = _i32(elem).reshape(-1, 3); ib = _f64(ib).reshape(-1, 3)
+        n = len(elem)
+        coef, lam, mu = (_f64(np.broadcast_to(a, n)) for a in (coef, lam, mu))
+        dbc = None if dbc is None else np.ascontiguousarray(dbc, np.uint8)
+        E = np.zeros(n); g = np.zeros_like(X); H = np.zeros((n, 9, 9)) if want_h else None; act = np.zeros(n, np.uint8)
+        L.orc_membrane_batch(n, _p(elem), _p(X), _p(ib), _p(coef), _p(lam), _p(mu), None if dbc is None else _p(dbc), int(project_spd), _p(E), _p(g),
+                             None if H is None else _p(H), _p(act))
+        return E, g, H, act
+
+    def hinge_batch(self, X, stencil, info, kh2, dbc=None, project_spd=True, want_h=True):
+        """Hinge bending E / g / H (orc_elastic.hpp; BENDING.h KL=false): info = (thetabar, ebar, hbar) per hinge, kh2 = h^2 k."""
+        L = self.lib
+        L.orc_hinge_batch.argtypes = [C.c_int] + [C.c_void_p] * 3 + [C.c_double, C.c_void_p, C.c_int] + [C.c_void_p] * 4
+        X = _f64(X).reshape(-1, 3); stencil = _i32(stencil).reshape(-1, 4); info = _f64(info).reshape(-1, 3)
+        n = len(stencil)
+        dbc = None if dbc is None else np.ascontiguousarray(dbc, np.uint8)
+        E = np.zeros(n); g = np.zeros_like(X); H = np.zeros((n, 12, 12)) if want_h else None; act = np.zeros(n, np.uint8)
+        L.orc_hinge_batch(n, _p(stencil), _p(X), _p(info), float(kh2), None if dbc is None else _p(dbc), int(project_spd), _p(E), _p(g),
+                          None if H is None else _p(H), _p(act))
+        return E, g, H, act
+
+    def dihedral_angle(self, x12):
+        self.lib.orc_dihedral_angle.restype = C.c_double
+        self.lib.orc_dihedral_angle.argtypes = [C.c_void_p]
+        x12 = _f64(x12)
+        return self.lib.orc_dihedral_angle(_p(x12))
+
     def row_EgH(self, mesh, row, weight, dHat2, kappa, thickness=0.0, project_spd=True):
         m, _keep = mesh
         row = _i32(row)

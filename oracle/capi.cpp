@@ -2,6 +2,7 @@
 // Flat C entry points for ctypes (oracle/binding.py). Not part of the product's C ABI.
 #include "orc_ipc.hpp"
 #include "orc_system.hpp"
+#include "orc_elastic.hpp"
 #include <chrono>
 
 using namespace orc;
@@ -82,6 +83,53 @@ void orc_hess_copy(void* h, int* tr, int* tc, double* tv, int* ptr, int* col, do
     if (val) std::copy(H->A.val.begin(), H->A.val.end(), val);
 }
 void orc_hess_free(void* h) { delete (HessHandle*)h; }
+
+// ---- elastic terms of the shell system (orc_elastic.hpp) ---------------------------------------------------------
+// Per element: E[e], g (accumulated into g3nV), H (81 / 144 doubles per element, row major, zero for skipped elements),
+// active[e] = 0 where the reference skips the element (all vertices Dirichlet, MEMBRANE.h:25 / BENDING.h:56-60; det IB == 0).
+void orc_membrane_batch(int nElem, const int* elem3, const double* X, const double* ib3, const double* coef, const double* lambda, const double* mu,
+    const uint8_t* dbc, int projectSPD, double* E, double* g3nV, double* H81, uint8_t* active)
+{
+#pragma omp parallel for
+    for (int e = 0; e < nElem; ++e) {
+        const int* t = elem3 + 3 * e;
+        active[e] = 0; E[e] = 0;
+        if (H81) std::memset(H81 + 81 * (size_t)e, 0, 81 * sizeof(double));
+        if (dbc && dbc[t[0]] && dbc[t[1]] && dbc[t[2]]) continue;
+        const V3 x[3] = {ld3(X + 3 * t[0]), ld3(X + 3 * t[1]), ld3(X + 3 * t[2])};
+        double g[9];
+        if (!membrane_EgH(x, ib3 + 3 * e, coef[e], lambda[e], mu[e], projectSPD != 0, E + e, g, H81 ? H81 + 81 * (size_t)e : nullptr)) continue;
+        active[e] = 1;
+        if (g3nV)
+            for (int k = 0; k < 3; ++k)
+                for (int d = 0; d < 3; ++d) {
+#pragma omp atomic
+                    g3nV[3 * t[k] + d] += g[3 * k + d];
+                }
+    }
+}
+void orc_hinge_batch(int nHinge, const int* stencil4, const double* X, const double* info3, double kh2, const uint8_t* dbc, int projectSPD,
+    double* E, double* g3nV, double* H144, uint8_t* active)
+{
+#pragma omp parallel for
+    for (int e = 0; e < nHinge; ++e) {
+        const int* t = stencil4 + 4 * e;
+        active[e] = 0; E[e] = 0;
+        if (H144) std::memset(H144 + 144 * (size_t)e, 0, 144 * sizeof(double));
+        if (dbc && dbc[t[0]] && dbc[t[1]] && dbc[t[2]] && dbc[t[3]]) continue;
+        const V3 x[4] = {ld3(X + 3 * t[0]), ld3(X + 3 * t[1]), ld3(X + 3 * t[2]), ld3(X + 3 * t[3])};
+        double g[12];
+        E[e] = hinge_EgH(x, info3[3 * e], kh2 * info3[3 * e + 1] / info3[3 * e + 2], projectSPD != 0, g, H144 ? H144 + 144 * (size_t)e : nullptr);
+        active[e] = 1;
+        if (g3nV)
+            for (int k = 0; k < 4; ++k)
+                for (int d = 0; d < 3; ++d) {
+#pragma omp atomic
+                    g3nV[3 * t[k] + d] += g[3 * k + d];
+                }
+    }
+}
+double orc_dihedral_angle(const double* x12) { return dihedral_angle(ld3(x12), ld3(x12 + 3), ld3(x12 + 6), ld3(x12 + 9)); }
 
 // ---- system matrix around the barrier Hessian (orc_system.hpp) -------------------------------------------------
 // triplets = [flow term][barrier rows] -> Construct_From_Triplet -> += M -> Project_DBC (INC_POTENTIAL.h:321-394)

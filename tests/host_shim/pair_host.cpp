@@ -3,6 +3,7 @@
 // fallback of the product: nothing in idp_b200/ links or loads it.
 #include "../../idp_b200/csrc/pair_deriv.cuh"
 #include "../../idp_b200/csrc/psd_lowrank.cuh"
+#include "../../idp_b200/csrc/shell_elastic.cuh"
 using namespace idp;
 static V3 l3(const double* p) { return mk3(p[0], p[1], p[2]); }
 extern "C" {
@@ -57,6 +58,31 @@ int hs_make_pd(int n, const double* A, double* out)
     }
     else return -1;
     return ok ? 0 : 1;
+}
+// shell_elastic.cuh on the host: one hinge (x: 4 x 3) / one membrane triangle (x: 3 x 3); dense H (12x12 / 9x9, row major)
+int hs_hinge_EgH(const double* x, double thetabar, double coef, int projectSPD, double* E, double* g, double* H)
+{
+    double work[QlStore<9, 1>::WORDS];
+    QlStore<9, 1> V9{work};
+    const V3 xv[4] = {l3(x), l3(x + 3), l3(x + 6), l3(x + 9)};
+    ElasticOut out;
+    DenseEmit em{H, 12};
+    hinge_eval(xv, thetabar, coef, projectSPD != 0, true, true, V9, out, em);
+    *E = out.E;
+    for (int i = 0; i < 12; ++i) g[i] = out.g[i];
+    return out.eigFail ? 1 : 0;
+}
+int hs_membrane_EgH(const double* x, const double* ib3, double coef, double lambda, double mu, int projectSPD, double* E, double* g, double* H)
+{
+    double work[QlStore<6, 1>::WORDS];
+    QlStore<6, 1> V6{work};
+    const V3 xv[3] = {l3(x), l3(x + 3), l3(x + 6)};
+    ElasticOut out;
+    DenseEmit em{H, 9};
+    if (!membrane_eval(xv, ib3, coef, lambda, mu, projectSPD != 0, true, true, V6, out, em)) return 2;
+    *E = out.E;
+    for (int i = 0; i < 9; ++i) g[i] = out.g[i];
+    return out.eigFail ? 1 : 0;
 }
 #ifdef IDP_QL_STATS
 // development aid (scripts/ql_stats.py): chase lengths of the QL trips of the last 9x9 projection

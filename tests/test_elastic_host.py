@@ -1,0 +1,119 @@
+"""CPU tests of the elastic terms: the product's device header idp_b200/csrc/shell_elastic.cuh compiled
+for the host (test-only harness, tests/host_shim/pair_host.cpp) against the oracle (oracle/orc_elastic.hpp: the reference's
+energy definitions differentiated by second-order jets, cyclic-Jacobi makePD) and against finite differences."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+@pytest.fixture(scope="module")
+def hs():
+    src = os.path.join(ROOT, "tests", "host_shim", "pair_host.cpp")
+    out = os.path.join(ROOT, "tests", "host_shim", "libpair_host.so")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", out, src])
+    L = C.CDLL(out)
+    L.hs_hinge_EgH.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.hs_membrane_EgH.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    return L
+
+
+def _hinge(hs, x, thetabar, coef, proj):
+    E = np.zeros(1); g = np.zeros(12); H = np.zeros((12, 12))
+    assert hs.hs_hinge_EgH(_p(x), thetabar, coef, int(proj), _p(E), _p(g), _p(H)) == 0
+    return E[0], g, H
+
+
+def _membrane(hs, x, ib, coef, lam, mu, proj):
+    E = np.zeros(1); g = np.zeros(9); H = np.zeros((9, 9))
+    rc = hs.hs_membrane_EgH(_p(x), _p(ib), coef, lam, mu, int(proj), _p(E), _p(g), _p(H))
+    return rc, E[0], g, H
+
+
+def _rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def _random_hinges(rng, n):
+    out = []
+    for _ in range(n):
+        e0, e1 = rng.normal(size=3), rng.normal(size=3)
+        ax = e1 - e0
+        t = np.cross(ax, rng.normal(size=3)); t /= np.linalg.norm(t)
+        ang = rng.uniform(-3.0, 3.0) if rng.random() < 0.8 else rng.choice([1e-7, -1e-6, 3.1, -3.1])
+        k = ax / np.linalg.norm(ax)
+        t2 = t * np.cos(ang) + np.cross(k, t) * np.sin(ang)
+        m = 0.5 * (e0 + e1)
+        x0 = m + rng.uniform(0.3, 2.0) * t + rng.uniform(-0.4, 0.4) * ax
+        x3 = m - rng.uniform(0.3, 2.0) * t2 + rng.uniform(-0.4, 0.4) * ax
+        out.append(np.concatenate([x0, e0, e1, x3]) * rng.choice([1e-2, 1.0, 30.0]))
+    return out
+
+
+def test_hinge_matches_oracle_jets(orc, hs):
+    rng = np.random.default_rng(5)
+    for x in _random_hinges(rng, 200):
+        thetabar, coef = rng.uniform(-1, 1), 10.0 ** rng.uniform(-4, 3)
+        info = np.array([[thetabar, 2.0, 0.5]])
+        for proj in (False, True):
+            E, g, H = _hinge(hs, x, thetabar, coef, proj)
+            oE, og, oH, act = orc.hinge_batch(x.reshape(4, 3), np.arange(4), info, coef * 0.5 / 2.0, project_spd=proj)
+            assert act[0] == 1
+            assert abs(E - oE[0]) <= 1e-10 * abs(oE[0]) + 1e-300
+            assert _rel(g, og.ravel()) <= 1e-10
+            assert _rel(H, oH[0]) <= 1e-10, (proj, _rel(H, oH[0]))
+            assert np.allclose(H, H.T, rtol=0, atol=1e-13 * np.abs(H).max())
+            if proj:
+                assert np.linalg.eigvalsh(H).min() >= -1e-12 * np.abs(H).max()
+        # translation invariance and the sign convention of the angle
+        assert np.abs(g.reshape(4, 3).sum(0)).max() <= 1e-12 * np.abs(g).max()
+
+
+def test_hinge_angle_sign_and_finite_differences(orc, hs):
+    x = np.array([0.0, 1, 0.3, 0, 0, 0, 1, 0, 0, 0.2, -1, 0.4])  # x0 ; x1, x2 ; x3
+    th = orc.dihedral_angle(x)
+    n1 = np.cross(x[3:6] - x[0:3], x[6:9] - x[0:3]); n2 = np.cross(x[6:9] - x[9:12], x[3:6] - x[9:12])
+    c = n1 @ n2 / np.linalg.norm(n1) / np.linalg.norm(n2)
+    assert abs(abs(th) - np.arccos(c)) < 1e-15 and th != 0
+    E0, g, H = _hinge(hs, x, 0.1, 2.0, False)
+    assert abs(E0 - 2.0 * (th - 0.1) ** 2) <= 1e-14
+    eps = 1e-6
+    for i in range(12):
+        xp, xm = x.copy(), x.copy(); xp[i] += eps; xm[i] -= eps
+        Ep, gp, _ = _hinge(hs, xp, 0.1, 2.0, False); Em, gm, _ = _hinge(hs, xm, 0.1, 2.0, False)
+        assert abs((Ep - Em) / (2 * eps) - g[i]) <= 1e-7 * max(1.0, abs(g[i]))
+        assert np.abs((gp - gm) / (2 * eps) - H[i]).max() <= 1e-6 * max(1.0, np.abs(H).max())
+
+
+def test_membrane_matches_oracle_jets(orc, hs):
+    rng = np.random.default_rng(7)
+    for it in range(300):
+        X0 = rng.normal(size=(3, 3)) * rng.choice([1e-2, 1.0, 10.0])
+        e1, e2 = X0[1] - X0[0], X0[2] - X0[0]
+        ib = np.array([e1 @ e1, e1 @ e2, e2 @ e2])
+        x = X0 + rng.normal(size=(3, 3)) * 0.3 * np.sqrt(ib[0])   # stretched, sheared or compressed, never inverted in 2-D terms
+        lam, mu, coef = 10.0 ** rng.uniform(-1, 4), 10.0 ** rng.uniform(-1, 4), 10.0 ** rng.uniform(-6, 0)
+        for proj in (False, True):
+            rc, E, g, H = _membrane(hs, x.ravel().copy(), ib, coef, lam, mu, proj)
+            assert rc == 0
+            oE, og, oH, act = orc.membrane_batch(x, np.arange(3), ib, coef, lam, mu, project_spd=proj)
+            assert act[0] == 1
+            assert abs(E - oE[0]) <= 1e-10 * max(abs(oE[0]), coef * mu * 1e-3)
+            assert _rel(g, og.ravel()) <= 1e-10
+            assert _rel(H, oH[0]) <= 1e-10, (it, proj, _rel(H, oH[0]))
+            if proj:
+                assert np.linalg.eigvalsh(H).min() >= -1e-12 * np.abs(H).max()
+        assert np.abs(g.reshape(3, 3).sum(0)).max() <= 1e-12 * np.abs(g).max()
+    # rest state: zero energy and gradient; degenerate rest triangle: skipped
+    rc, E, g, H = _membrane(hs, X0.ravel().copy(), ib, 1.0, 3.0, 2.0, True)
+    assert rc == 0 and abs(E) < 1e-13 and np.abs(g).max() < 1e-10 * np.sqrt(ib[0])
+    rc, *_ = _membrane(hs, X0.ravel().copy(), np.array([1.0, 2.0, 4.0]), 1.0, 3.0, 2.0, True)
+    assert rc == 2
