@@ -91,6 +91,7 @@ def load_library(path=LIB_PATH):
     L.idp_system_set_flow_term.argtypes = [vp, i, vp, i, vp, d]
     L.idp_system_set_mass.argtypes = [vp, vp]
     L.idp_project_dbc.argtypes = [vp]
+    L.idp_project_dbc_mask.argtypes = [vp, vp]
     L.idp_system_set_membrane.argtypes = [vp, i, vp, i, vp, vp, vp, vp, d]
     L.idp_system_set_hinges.argtypes = [vp, i, vp, vp, d, d]
     L.idp_elastic_energy.argtypes = [vp, C.POINTER(d)]
@@ -241,8 +242,11 @@ class ContactContext:
         self._ck(self.L.idp_elastic_gradient(self.h, _p(g), g.shape[1]))
         return g
 
-    def project_dbc(self):
-        self._ck(self.L.idp_project_dbc(self.h))
+    def project_dbc(self, mask=None):
+        if mask is None:
+            return self._ck(self.L.idp_project_dbc(self.h))
+        mask = np.ascontiguousarray(mask, np.uint8)
+        self._ck(self.L.idp_project_dbc_mask(self.h, _p(mask)))
 
     def solve_pcg(self, rhs, rel_tol=1e-10, max_iter=10000):
         rhs = np.ascontiguousarray(rhs, np.float64).reshape(-1)

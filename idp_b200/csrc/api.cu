@@ -470,6 +470,12 @@ int idp_project_dbc(idp_ctx* c)
     IDP_CK(c, cudaSetDevice(c->device));
     return project_dbc(c);
 }
+int idp_project_dbc_mask(idp_ctx* c, const uint8_t* mask)
+{
+    if (!c) return IDP_ERR_INVALID;
+    IDP_CK(c, cudaSetDevice(c->device));
+    return project_dbc(c, mask);
+}
 int idp_solve_pcg(idp_ctx* c, const double* rhs, double* sol, double rel_tol, int max_iter, int* iters, double* rel_residual)
 {
     if (!c || !rhs || max_iter < 0 || !(rel_tol >= 0)) return c ? fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "idp_solve_pcg: bad arguments", __FILE__, __LINE__) : IDP_ERR_INVALID;

@@ -129,7 +129,7 @@ struct idp_ctx {
     idp::DBuf<int> bnode;
     idp::DBuf<int2> bedge;
     idp::DBuf<int4> btri;
-    idp::DBuf<unsigned char> dbc;
+    idp::DBuf<unsigned char> dbc, projMask;
     // ---- per-iterate state ----
     idp::DBuf<double> stage;            // upload staging (AoS)
     idp::DBuf<double> xs, ys, zs;       // SoA positions (streaming kernels)
@@ -318,7 +318,7 @@ int sorted_candidates(idp_ctx* c, int which, int2* host_out);
 int barrier_eval(idp_ctx* c, double dhat2, double kappa, double thickness, int want_e, int want_g, int want_h,
     int project_spd, double* E_out);
 int assemble_csr(idp_ctx* c);
-int project_dbc(idp_ctx* c);
+int project_dbc(idp_ctx* c, const unsigned char* host_mask = nullptr);
 // elastic terms: bucket counts / Hessian blocks for the assembly in barrier_eval, energy + gradient on request
 int elastic_block_counts(idp_ctx* c, int* vtxCnt, long* nElements);
 int elastic_emit_blocks(idp_ctx* c, int project_spd, unsigned tagBase, int* vtxCursor, unsigned long long* bktKey, double* bktVal8, double* bktVal1);

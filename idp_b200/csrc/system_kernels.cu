@@ -25,11 +25,18 @@ __global__ void __launch_bounds__(256) k_project_dbc(const int* __restrict__ ptr
         }
     }
 }
-int project_dbc(idp_ctx* c)
+int project_dbc(idp_ctx* c, const unsigned char* host_mask)
 {
     if (c->nnz <= 0) return IDP_OK;
     if (c->nranks > 1) return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "idp_project_dbc: the per-rank CSRs are partial sums; project after summing them (single-GPU contexts only)", __FILE__, __LINE__);
-    IDP_LAUNCH(c, k_project_dbc, std::min(blocks_for(32L * 3 * c->nV, 256), (unsigned)c->sm_count * 32), 256, 0, c->csrPtr.p, c->csrCol.p, c->csrVal.p, c->dbc.p, 3 * c->nV);
+    const unsigned char* mask = c->dbc.p;
+    if (host_mask) { // a caller-supplied mask (the nodes that stay fixed while the augmented-Lagrangian Dirichlet penalty is active)
+        IDP_CK(c, c->projMask.reserve(c->nV));
+        IDP_CK(c, cudaMemcpyAsync(c->projMask.p, host_mask, c->nV, cudaMemcpyHostToDevice, c->stream));
+        mask = c->projMask.p;
+    }
+    IDP_LAUNCH(c, k_project_dbc, std::min(blocks_for(32L * 3 * c->nV, 256), (unsigned)c->sm_count * 32), 256, 0, c->csrPtr.p, c->csrCol.p, c->csrVal.p, mask, 3 * c->nV);
+    if (host_mask) IDP_CK(c, cudaStreamSynchronize(c->stream)); // the host buffer may go away
     IDP_CK(c, cudaGetLastError());
     c->csrProjected = true;
     return IDP_OK;

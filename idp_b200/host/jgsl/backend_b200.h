@@ -36,7 +36,7 @@ public:
         if (nV != nV_ || tri3 != tri_ || dbc != dbc_) {
             check(idp_set_mesh_from_triangles(ctx_, nV, (int)(tri3.size() / 3), tri3.data(), 3, x, 3, dbc.data()));
             nV_ = nV; tri_ = tri3; dbc_ = dbc;
-            termsSet_ = false;
+            termsSet_ = false; elasticSet_ = false;
         }
         fresh_ = false;
     }
@@ -50,6 +50,20 @@ public:
         termsSet_ = true;
         fresh_ = false;
     }
+    void set_elastic_terms(const std::vector<int>& elem3, const std::vector<double>& ib3, const std::vector<double>& vol, const std::vector<double>& lambda,
+        const std::vector<double>& mu, const std::vector<int>& stencil4, const std::vector<double>& info3, double k, double h) override
+    {
+        if (elasticSet_ && elem3 == mElem_ && ib3 == mIB_ && vol == mVol_ && lambda == mLam_ && mu == mMu_ && stencil4 == hSt_ && info3 == hInfo_ && k == hK_ &&
+            h == eH_)
+            return;
+        check(idp_system_set_membrane(ctx_, (int)(elem3.size() / 3), elem3.data(), 3, ib3.data(), vol.data(), lambda.data(), mu.data(), h));
+        check(idp_system_set_hinges(ctx_, (int)(stencil4.size() / 4), stencil4.data(), info3.data(), k, h));
+        mElem_ = elem3; mIB_ = ib3; mVol_ = vol; mLam_ = lambda; mMu_ = mu; hSt_ = stencil4; hInfo_ = info3; hK_ = k; eH_ = h;
+        elasticSet_ = true;
+        fresh_ = false;
+    }
+    void elastic_energy(double& E) override { check(idp_elastic_energy(ctx_, &E)); }
+    void elastic_gradient(double* g) override { check(idp_elastic_gradient(ctx_, g, 3)); }
     void set_positions(const double* x) override { check(idp_set_positions(ctx_, x, 3)); fresh_ = false; }
     int constraint_set(double dHat2, double thickness) override
     {
@@ -70,14 +84,14 @@ public:
         check(idp_get_gradient(ctx_, g, 3));
         fresh_ = true; freshKappa_ = kappa; freshDHat2_ = dHat2;
     }
-    bool solve_newton_system(double dHat2, double kappa, double thickness, const double* rhs, double* sol) override
+    bool solve_newton_system(double dHat2, double kappa, double thickness, const std::vector<uint8_t>* projMask, const double* rhs, double* sol) override
     {
         if (!(fresh_ && freshKappa_ == kappa && freshDHat2_ == dHat2)) {
             long nnz = 0;
             check(idp_barrier_hessian(ctx_, dHat2, kappa, thickness, 1, &nnz));
         }
         fresh_ = false; // Project_DBC rewrites the values in place
-        check(idp_project_dbc(ctx_));
+        check(idp_project_dbc_mask(ctx_, projMask ? projMask->data() : nullptr));
         int iters = 0;
         double rel = 0;
         check(idp_solve_pcg(ctx_, rhs, sol, pcg_rel_tol, pcg_max_iter, &iters, &rel));
@@ -119,7 +133,10 @@ private:
     }
     idp_ctx* ctx_ = nullptr;
     int nV_ = -1;
-    std::vector<int> tri_, elem_;
+    std::vector<int> tri_, elem_, mElem_, hSt_;
+    std::vector<double> mIB_, mVol_, mLam_, mMu_, hInfo_;
+    double hK_ = 0, eH_ = 0;
+    bool elasticSet_ = false;
     std::vector<uint8_t> dbc_;
     std::vector<double> vol_, mass_;
     double h_ = 0, freshKappa_ = 0, freshDHat2_ = 0;

@@ -1,13 +1,14 @@
 // Python module `JGSL` (pybind11) hosting the device-resident contact path: the subset of the reference's module surface
-// (Library/EXPORTER.cpp:17-36) that Projects/FEMShell/12-14_normal_flow.py ->
-// Python/Drivers/{SimulationBase,FEMDiscreteShellBase}.py touches, with the same names, argument order and side effects, so
+// (Library/EXPORTER.cpp:17-36) that Projects/FEMShell/12-14_normal_flow.py and 16_fix_char_seq.py ->
+// Python/Drivers/{SimulationBase,FEMDiscreteShellBase}.py touch, with the same names, argument order and side effects, so
 // that those scripts run unchanged with this module on their import path:
 //   module level   Kokkos_Initialize, Set_Parameter / Get_Parameter, TIMER_FLUSH, Scalar*/Vector*/Matrix*, StdVector*,
 //                  StdMapPairiToi, CSR_MATRIX_D, FIXED_COROTATED_{2,3}.Create
 //   Storage.*      the storages the drivers construct
-//   MeshIO.*       Append_Attribute, Read_TriMesh_Obj, Write_TriMesh_Obj
-//   FEM.*          Boundary_Dirichlet;  FEM.DiscreteShell.*  Add_Shell, Initialize_Shell_Hinge_EIPC, Initialize_OIPC,
-//                  Update_Normal_Flow_Neumann, Advance_One_Step_IE_Flow  (DISCRETE_SHELL.h:1087-1126)
+//   MeshIO.*       Append_Attribute, Read_TriMesh_Obj, Write_TriMesh_Obj, Load_Velocity_X0, Zero_Velocity
+//   FEM.*          Boundary_Dirichlet, Init/Step/Turn/Reset/Load_Dirichlet;  FEM.DiscreteShell.*  Add_Shell,
+//                  Initialize_Shell_Hinge_EIPC, Initialize_OIPC, Update_Normal_Flow_Neumann, Advance_One_Step_IE_Flow,
+//                  Advance_One_Step_IE_Hinge  (DISCRETE_SHELL.h:1087-1126)
 // Everything else of the reference's module raises NotImplementedError by name (B200_NOT_BUILT) instead of being absent
 // silently. The time step itself is shell_flow.h on the backend selected at compile time: backend_b200.h (the product) or,
 // for the test-only trace checker built under tests/host_shim/, the reference's own CPU loops.
@@ -225,8 +226,20 @@ PYBIND11_MODULE(JGSL, m)
     io.def("Append_Attribute", [](const TriStorage& src, TriStorage& dst) { dst.rows.insert(dst.rows.end(), src.rows.begin(), src.rows.end()); });
     io.def("Read_TriMesh_Obj", &read_trimesh_obj, "read triangle mesh from obj file");
     io.def("Write_TriMesh_Obj", &write_trimesh_obj, "write triangle mesh to obj file");
+    // Load_Velocity_X0 (Utils/MESHIO.h:986-1004): velocities that carry the current nodes to frame `lastFrame` within h
+    io.def("Load_Velocity_X0", [](const std::string& folder, int lastFrame, double h, NodeStorage& Xcur, NodeAttrStorage& nodeAttr) {
+        NodeStorage X1;
+        TriStorage E1;
+        read_trimesh_obj(folder + "/" + std::to_string(lastFrame) + ".obj", X1, E1);
+        if (Xcur.size() != nodeAttr.size() || X1.size() != nodeAttr.size()) {
+            printf("node count does not match!\n");
+            exit(-1);
+        }
+        for (int i = 0; i < Xcur.size(); ++i) std::get<1>(nodeAttr.rows[i]) = (std::get<0>(X1.rows[i]) - std::get<0>(Xcur.rows[i])) / h;
+    });
+    io.def("Zero_Velocity", [](NodeAttrStorage& nodeAttr) { for (auto& r : nodeAttr.rows) std::get<1>(r) = Vec<double, 3>(); }); // :1006-1014
     for (const char* n : {"Transform_Points", "Read_SegMesh_Seg", "Write_SegMesh_Obj", "Read_TetMesh_Vtk", "Find_Surface_TriMesh",
-             "Write_Surface_TriMesh_Obj", "Zero_Velocity", "Load_Velocity", "Load_Velocity_X0"})
+             "Write_Surface_TriMesh_Obj", "Load_Velocity"})
         not_built(io, n);
 
     // ---- FEM.* (FEM/BOUNDARY_CONDITION.h:268-291) and FEM.DiscreteShell.* (FEM/Shell/DISCRETE_SHELL.h:1087-1126) ---------------------
@@ -253,30 +266,37 @@ PYBIND11_MODULE(JGSL, m)
     sh.def("Initialize_OIPC", &initialize_oipc, py::arg("E"), py::arg("nu"), py::arg("thickness"), py::arg("h"), py::arg("M"), py::arg("kappa"),
         py::arg("stiffMult") = 1.0);
     sh.def("Update_Normal_Flow_Neumann", &update_normal_flow_neumann);
-    sh.def("Advance_One_Step_IE_Flow",
-        [](TriStorage& Elem, const StdVectorVector2i& seg, DbcStorage& DBC, const EdgeToTri& edge2tri, const StdVectorVector4i& edgeStencil,
-            const StdVectorVector3d& edgeInfo, double thickness, double bendingStiffMult, const Vec<double, 4>& fiberStiffMult,
-            const Vec<double, 3>& fiberLimit, Vec<double, 2>& s, Vec<double, 2>& sHat, Vec<double, 2>& kappa_s, const StdVectorXd& b, double h,
-            double NewtonTol, bool withCollision, double dHat2, Vec<double, 3>& kappaVec, double mu, double epsv2, int fricIterAmt,
-            const StdVectorXi& compNodeRange, const StdVectorXd& muComp, bool staticSolve, NodeStorage& X, NodeAttrStorage& nodeAttr, CsrMatrix& M,
-            ElemAttrStorage& elemAttr, Fcr2Storage& elasticityAttr, Storage<Vec<int, 4>>& tet, Storage<Mat<double, 3>, Mat<double, 3>>& tetAttr,
-            Fcr3Storage& tetElasticityAttr, const StdVectorVector2i& rod, const StdVectorVector3d& rodInfo, const StdVectorVector3i& rodHinge,
-            const StdVectorVector3d& rodHingeInfo, const StdVectorVector3i& stitchInfo, const StdVectorXd& stitchRatio, double k_stitch,
-            const StdVectorXi& particle, const std::string& outputFolder) {
-            (void)edge2tri; (void)edgeStencil; (void)edgeInfo; (void)bendingStiffMult; (void)fiberLimit; (void)s; (void)sHat; (void)epsv2;
-            (void)fricIterAmt; (void)compNodeRange; (void)tetAttr; (void)tetElasticityAttr; (void)rodInfo; (void)rodHinge; (void)rodHingeInfo;
-            (void)stitchRatio; (void)k_stitch;
-            if (muComp.size() && muComp.size() == compNodeRange.size() * compNodeRange.size()) mu = 1; // friction requested per component
+    // Advance_One_Step_IE_Discrete_Shell<double, 3, KL=false, elasticIPC=false, flow> (DISCRETE_SHELL.h:1110, 1113): 42 positional arguments
+    auto step = [](bool flow) {
+        return [flow](TriStorage& Elem, const StdVectorVector2i& seg, DbcStorage& DBC, const EdgeToTri& edge2tri, const StdVectorVector4i& edgeStencil,
+                   const StdVectorVector3d& edgeInfo, double thickness, double bendingStiffMult, const Vec<double, 4>& fiberStiffMult,
+                   const Vec<double, 3>& fiberLimit, Vec<double, 2>& s, Vec<double, 2>& sHat, Vec<double, 2>& kappa_s, const StdVectorXd& b, double h,
+                   double NewtonTol, bool withCollision, double dHat2, Vec<double, 3>& kappaVec, double mu, double epsv2, int fricIterAmt,
+                   const StdVectorXi& compNodeRange, const StdVectorXd& muComp, bool staticSolve, NodeStorage& X, NodeAttrStorage& nodeAttr, CsrMatrix& M,
+                   ElemAttrStorage& elemAttr, Fcr2Storage& elasticityAttr, Storage<Vec<int, 4>>& tet, Storage<Mat<double, 3>, Mat<double, 3>>& tetAttr,
+                   Fcr3Storage& tetElasticityAttr, const StdVectorVector2i& rod, const StdVectorVector3d& rodInfo, const StdVectorVector3i& rodHinge,
+                   const StdVectorVector3d& rodHingeInfo, const StdVectorVector3i& stitchInfo, const StdVectorXd& stitchRatio, double k_stitch,
+                   const StdVectorXi& particle, const std::string& outputFolder) {
+            (void)edge2tri; (void)fiberLimit; (void)s; (void)sHat; (void)epsv2; (void)fricIterAmt; (void)tetAttr; (void)tetElasticityAttr; (void)rodInfo;
+            (void)rodHinge; (void)rodHingeInfo; (void)stitchRatio; (void)k_stitch;
+            ShellStepInputs in;
+            in.flow = flow; in.thickness = thickness; in.bendingStiffMult = bendingStiffMult; in.h = h; in.NewtonTol = NewtonTol; in.dHat2 = dHat2;
+            in.mu = (muComp.size() && muComp.size() == compNodeRange.size() * compNodeRange.size()) ? 1.0 : mu; // per-component friction requested
+            in.withCollision = withCollision; in.staticSolve = staticSolve;
+            in.nTet = tet.size(); in.nRod = (int)rod.size(); in.nStitch = (int)stitchInfo.size(); in.nParticle = (int)particle.size();
+            in.outputFolder = outputFolder;
             JGSL_BACKEND_CLASS& be = backend();
-            const int it = advance_one_step_ie_flow(be, Elem, seg, DBC, thickness, fiberStiffMult, kappa_s, b, h, NewtonTol, withCollision, dHat2,
-                kappaVec, mu, staticSolve, X, nodeAttr, M, elemAttr, elasticityAttr, tet.size(), (int)rod.size(), (int)stitchInfo.size(),
-                (int)particle.size(), outputFolder);
+            const int it = advance_one_step_ie(be, in, Elem, seg, DBC, edgeStencil, edgeInfo, fiberStiffMult, kappa_s, b, kappaVec, X, nodeAttr, M, elemAttr,
+                elasticityAttr);
             fflush(stdout);
             return it;
-        });
+        };
+    };
+    sh.def("Advance_One_Step_IE_Flow", step(true));
+    sh.def("Advance_One_Step_IE_Hinge", step(false));
     for (const char* n : {"Add_Garment", "Make_Rod", "Make_Rod_Net", "Add_Discrete_Particles", "Initialize_Shell", "Initialize_Garment",
              "Initialize_Shell_Hinge", "Update_Material_With_Tex_Shell", "Initialize_Shell_EIPC", "Initialize_Discrete_Rod",
-             "Initialize_Discrete_Particle", "Initialize_EIPC", "Initialize_OIPC_VM", "Advance_One_Step_IE", "Advance_One_Step_IE_Hinge",
+             "Initialize_Discrete_Particle", "Initialize_EIPC", "Initialize_OIPC_VM", "Advance_One_Step_IE",
              "Advance_One_Step_IE_EIPC", "Advance_One_Step_IE_Hinge_EIPC", "Advance_One_Step_SIE", "Advance_One_Step_SIE_Hinge",
              "Advance_One_Step_SIE_EIPC", "Advance_One_Step_SIE_Hinge_EIPC", "Construct_Surface_Mesh", "Compute_Stretch_From_File",
              "XZ_As_Texture", "Adjust_Material"})

@@ -1,9 +1,9 @@
-// Host Newton driver of the discrete-shell "flow" time step around the device-resident contact path.
+// Host Newton driver of the discrete-shell time step around the device-resident contact path.
 //
-// What the reference does in Library/FEM/Shell/IMPLICIT_EULER.h:151-891 (Advance_One_Step_IE_Discrete_Shell<double,3,false,
-// false,flow=true>, exported as FEM.DiscreteShell.Advance_One_Step_IE_Flow, DISCRETE_SHELL.h:1113) with Line_Search
-// (:9-149) and the `flow` branches of Compute_IncPotential / _Gradient / _Hessian (INC_POTENTIAL.h:53-73,191-211,323-394),
-// restated here on top of a small backend interface: every contact operator, the system-matrix assembly, Project_DBC and
+// What the reference does in Library/FEM/Shell/IMPLICIT_EULER.h:151-891 (Advance_One_Step_IE_Discrete_Shell<double,3,KL=false,
+// elasticIPC=false,flow>, exported as FEM.DiscreteShell.Advance_One_Step_IE_Flow / _IE_Hinge, DISCRETE_SHELL.h:1110,1113) with
+// Line_Search (:9-149) and Compute_IncPotential / _Gradient / _Hessian (INC_POTENTIAL.h:14-394: the `flow` branch, or membrane +
+// hinge bending + inertia), restated here on top of a small backend interface: every contact operator, the system-matrix assembly, Project_DBC and
 // the linear solve are ONE backend call each, so that the B200 backend (backend_b200.h) keeps them on the device and the
 // host only runs the O(nV) vector algebra and the control flow. Same printed lines, same files (residual.txt, counter.txt,
 // stretch.txt, Hessian_info.txt), same error behaviour (message + exit(-1)).
@@ -36,12 +36,19 @@ struct ContactBackend {
     virtual void set_rest_positions(const double* x0) = 0;
     // the constant terms of the system matrix: Laplacian flow blocks (INC_POTENTIAL.h:323-339), lumped mass (:383-386)
     virtual void set_system_terms(const std::vector<int>& elem3, const std::vector<double>& vol, double h, const std::vector<double>& mass) = 0;
+    // elastic terms of the non-flow step: membrane triangles (MEMBRANE.h) and bending hinges (BENDING.h, KL = false); empty = none
+    virtual void set_elastic_terms(const std::vector<int>& elem3, const std::vector<double>& ib3, const std::vector<double>& vol,
+        const std::vector<double>& lambda, const std::vector<double>& mu, const std::vector<int>& stencil4, const std::vector<double>& info3, double k,
+        double h) = 0;
+    virtual void elastic_energy(double& E) = 0;   // adds Compute_Membrane_Energy + Compute_Bending_Energy
+    virtual void elastic_gradient(double* g) = 0; // adds
     virtual void set_positions(const double* x) = 0;
     virtual int constraint_set(double dHat2, double thickness) = 0;                      // Compute_Constraint_Set, returns #rows
     virtual void barrier_energy(double dHat2, double kappa, double thickness, double& E) = 0;          // adds
     virtual void barrier_gradient(double dHat2, double kappa, double thickness, double* g) = 0;        // adds
     // Compute_IncPotential_Hessian (flow) + Solve_Direct: assemble flow + mass + projected barrier Hessians, Project_DBC, solve
-    virtual bool solve_newton_system(double dHat2, double kappa, double thickness, const double* rhs, double* sol) = 0;
+    // projMask: the vertices Project_DBC fixes (null: the Dirichlet mask of set_mesh)
+    virtual bool solve_newton_system(double dHat2, double kappa, double thickness, const std::vector<uint8_t>* projMask, const double* rhs, double* sol) = 0;
     virtual double ccd(const double* dir, double thickness, double alpha) = 0;          // Compute_Intersection_Free_StepSize
     virtual bool min_dist2(double thickness, std::vector<double>* dist2, double& minDist2) = 0; // false: no rows
     virtual void get_rows(std::vector<int>& rows4, std::vector<double>& info2) = 0;
@@ -347,13 +354,20 @@ inline void max_and_avg_stretch(const TriStorage& Elem, const std::vector<bool>&
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
-// The incremental potential of the flow step without the barrier term (INC_POTENTIAL.h:53-73 + 131-144 and :191-211 +
-// 250-268): E = -h/2 x^T L x + 1/2 (x - xtilde)^T M (x - xtilde), L assembled per triangle with weight vol/6.
-struct FlowPotential {
+// The incremental potential without the barrier term (INC_POTENTIAL.h:14-150 energy, :152-276 gradient):
+//   flow:   -h/2 x^T L x, L assembled per triangle with weight vol/6 (host, O(nF))             (:53-73, 191-211)
+//   else:   membrane + hinge bending (backend: on the device for the B200 build)                (:75-96, 213-232)
+//   both:   + 1/2 (x - xtilde)^T M (x - xtilde), M lumped                                       (:131-144, 250-268)
+//   + the augmented-Lagrangian Dirichlet penalty 1/2 k sum m_v |x_v - target_v|^2 while it is active (DIRICHLET.h:25-71)
+struct StepPotential {
+    bool flow = false;
+    ContactBackend* be = nullptr;
     const TriStorage* Elem = nullptr;
     const Fcr2Storage* fcr = nullptr;
     const std::vector<double>* massDiag = nullptr; // 3 nV
-    double h = 0;
+    const DbcStorage* DBC = nullptr;
+    const NodeAttrStorage* nodeAttr = nullptr;
+    double h = 0, DBCStiff = 0;
     std::vector<double> Lx;
 
     void laplacian(const std::vector<double>& x)
@@ -368,11 +382,27 @@ struct FlowPotential {
             }
         }
     }
+    double dbc_dist2(const std::vector<double>& x, bool massWeighted) const
+    {
+        double s = 0;
+        for (const auto& r : DBC->rows) {
+            const Vec<double, 4>& dI = std::get<0>(r);
+            const int v = (int)dI[0];
+            double p = 0;
+            for (int d = 0; d < 3; ++d) p += (dI[d + 1] - x[3 * (size_t)v + d]) * (dI[d + 1] - x[3 * (size_t)v + d]);
+            s += massWeighted ? p * std::get<3>(nodeAttr->rows[v]) : p;
+        }
+        return s;
+    }
+    // the backend must hold x as its current positions when flow == false
     double energy(const std::vector<double>& x, const std::vector<double>& xtilde)
     {
-        laplacian(x);
         double E = 0;
-        for (size_t i = 0; i < x.size(); ++i) E += -h * 0.5 * x[i] * Lx[i];
+        if (flow) {
+            laplacian(x);
+            for (size_t i = 0; i < x.size(); ++i) E += -h * 0.5 * x[i] * Lx[i];
+        }
+        else be->elastic_energy(E);
         double I = 0;
         for (size_t i = 0; i < x.size(); ++i) {
             const double dx = x[i] - xtilde[i];
@@ -382,21 +412,28 @@ struct FlowPotential {
     }
     void gradient(const std::vector<double>& x, const std::vector<double>& xtilde, std::vector<double>& g)
     {
-        laplacian(x);
-        g.resize(x.size());
-        for (size_t i = 0; i < x.size(); ++i) g[i] = -h * Lx[i] + (*massDiag)[i] * (x[i] - xtilde[i]);
+        g.assign(x.size(), 0.0);
+        if (flow) {
+            laplacian(x);
+            for (size_t i = 0; i < x.size(); ++i) g[i] = -h * Lx[i];
+        }
+        else be->elastic_gradient(g.data());
+        for (size_t i = 0; i < x.size(); ++i) g[i] += (*massDiag)[i] * (x[i] - xtilde[i]);
+    }
+    void add_dbc_energy(const std::vector<double>& x, double& E) const
+    {
+        if (DBCStiff) E += 0.5 * DBCStiff * dbc_dist2(x, true);
     }
 };
 
-struct FlowStepState { // what Line_Search shares with the Newton loop
+struct StepState { // what Line_Search shares with the Newton loop
     std::vector<double> x, xtilde, sol, rhs, g;
     int nRows = 0;
     double Eprev = 0;
 };
 
-// Line_Search<..., flow=true> (IMPLICIT_EULER.h:9-149) for the configuration the flow drivers use (no inextensibility, no
-// fibers, no tets, mu = 0, hard Dirichlet constraints)
-inline void flow_line_search(ContactBackend& be, FlowPotential& pot, FlowStepState& s, bool withCollision, double dHat2, double kappa, double thickness,
+// Line_Search (IMPLICIT_EULER.h:9-149) for the configurations hosted here (no inextensibility, no fibers, no tets, mu = 0)
+inline void step_line_search(ContactBackend& be, StepPotential& pot, StepState& s, bool withCollision, double dHat2, double kappa, double thickness,
     double& alpha, double& feasibleAlpha)
 {
     const std::vector<double> xprev = s.x;
@@ -409,9 +446,9 @@ inline void flow_line_search(ContactBackend& be, FlowPotential& pot, FlowStepSta
     double E;
     do {
         for (size_t i = 0; i < s.x.size(); ++i) s.x[i] = xprev[i] + alpha * s.sol[i];
+        be.set_positions(s.x.data());
         E = pot.energy(s.x, s.xtilde);
         if (withCollision) {
-            be.set_positions(s.x.data());
             s.nRows = be.constraint_set(dHat2, thickness);
             if (s.nRows) {
                 double minDist2 = 0;
@@ -425,6 +462,7 @@ inline void flow_line_search(ContactBackend& be, FlowPotential& pot, FlowStepSta
             }
             be.barrier_energy(dHat2, kappa, thickness, E);
         }
+        pot.add_dbc_energy(s.x, E);
         alpha /= 2.0;
         printf("E %le, Eprev %le, alpha %le, valid %d\n", E, s.Eprev, alpha * 2, 1);
     } while (E > s.Eprev);
@@ -432,33 +470,41 @@ inline void flow_line_search(ContactBackend& be, FlowPotential& pot, FlowStepSta
     s.Eprev = E;
 }
 
-struct FlowStepOptions {
-    bool verbose = true;
+struct ShellStepInputs { // the arguments of Advance_One_Step_IE_Discrete_Shell the hosted variants read (IMPLICIT_EULER.h:151-187)
+    bool flow = false;
+    double thickness = 0, bendingStiffMult = 0, h = 0, NewtonTol = 1e-3, dHat2 = 0, mu = 0;
+    bool withCollision = false, staticSolve = false;
+    int nTet = 0, nRod = 0, nStitch = 0, nParticle = 0;
+    std::string outputFolder;
 };
 
-// Advance_One_Step_IE_Discrete_Shell<double, 3, KL=false, elasticIPC=false, flow=true> (IMPLICIT_EULER.h:151-891).
+// Advance_One_Step_IE_Discrete_Shell<double, 3, KL=false, elasticIPC=false, flow> (IMPLICIT_EULER.h:151-891).
 // Unsupported inputs are rejected like the contact path rejects them (message + exit(-1)): segments, rods, particles, tets,
-// stitches, friction, strain limiting, fibers, static solves, moving Dirichlet targets.
-inline int advance_one_step_ie_flow(ContactBackend& be, TriStorage& Elem, const std::vector<Vec<int, 2>>& seg, DbcStorage& DBC, double thickness,
-    const Vec<double, 4>& fiberStiffMult, const Vec<double, 2>& kappa_s, const std::vector<double>& b, double h, double NewtonTol, bool withCollision,
-    double dHat2, Vec<double, 3>& kappaVec, double mu, bool staticSolve, NodeStorage& X, NodeAttrStorage& nodeAttr, CsrMatrix& M,
-    ElemAttrStorage& elemAttr, Fcr2Storage& elasticityAttr, int nTet, int nRod, int nStitch, int nParticle, const std::string& outputFolder)
+// stitches, friction, strain limiting, fibers, static solves.
+inline int advance_one_step_ie(ContactBackend& be, const ShellStepInputs& in, TriStorage& Elem, const std::vector<Vec<int, 2>>& seg, DbcStorage& DBC,
+    const std::vector<Vec<int, 4>>& edgeStencil, const std::vector<Vec<double, 3>>& edgeInfo, const Vec<double, 4>& fiberStiffMult,
+    const Vec<double, 2>& kappa_s, const std::vector<double>& b, Vec<double, 3>& kappaVec, NodeStorage& X, NodeAttrStorage& nodeAttr, CsrMatrix& M,
+    ElemAttrStorage& elemAttr, Fcr2Storage& elasticityAttr)
 {
-    if (!seg.empty() || nTet || nRod || nStitch || nParticle || mu > 0 || kappa_s[0] > 0 || fiberStiffMult[0] > 0 || staticSolve) {
-        printf("Advance_One_Step_IE_Flow (%s): segments / rods / particles / tets / stitches / friction / strain limiting / fibers / static "
-               "solves are outside the device-resident flow step\n", be.name());
+    const bool flow = in.flow, withCollision = in.withCollision;
+    const double h = in.h, thickness = in.thickness, dHat2 = in.dHat2, NewtonTol = in.NewtonTol;
+    const std::string& outputFolder = in.outputFolder;
+    if (!seg.empty() || in.nTet || in.nRod || in.nStitch || in.nParticle || in.mu > 0 || kappa_s[0] > 0 || fiberStiffMult[0] > 0 || fiberStiffMult[1] > 0 ||
+        in.staticSolve) {
+        printf("Advance_One_Step_IE (%s): segments / rods / particles / tets / stitches / friction / strain limiting / fibers / static "
+               "solves are outside the device-resident shell step\n", be.name());
         exit(-1);
     }
     const int nV = X.size();
     const size_t n3 = 3 * (size_t)nV;
     double kappa[3] = {kappaVec[0], kappaVec[1], kappaVec[2]};
 
-    FlowStepState s;
+    StepState s;
     s.x.resize(n3);
     for (int v = 0; v < nV; ++v) for (int d = 0; d < 3; ++d) s.x[3 * (size_t)v + d] = std::get<0>(X.rows[v])[d];
     const std::vector<double> xn = s.x;
 
-    // Xtilde = Xn + h v + h^2 M^-1 b with v zeroed by the flow variant (:196-217); M is the lumped (diagonal) mass
+    // Xtilde = Xn + h v + h^2 M^-1 b, v zeroed by the flow variant (:196-217); M is the lumped (diagonal) mass
     std::vector<double> massDiag(n3);
     for (size_t i = 0; i < n3; ++i) {
         massDiag[i] = M.coeff((int)i, (int)i);
@@ -469,23 +515,25 @@ inline int advance_one_step_ie_flow(ContactBackend& be, TriStorage& Elem, const 
     }
     s.xtilde = xn;
     for (int v = 0; v < nV; ++v) {
-        std::get<1>(nodeAttr.rows[v]) = Vec<double, 3>();
-        for (int d = 0; d < 3; ++d) s.xtilde[3 * (size_t)v + d] += h * h * (b[3 * (size_t)v + d] / massDiag[3 * (size_t)v + d]);
+        if (flow) std::get<1>(nodeAttr.rows[v]) = Vec<double, 3>();
+        const Vec<double, 3>& vel = std::get<1>(nodeAttr.rows[v]);
+        for (int d = 0; d < 3; ++d) s.xtilde[3 * (size_t)v + d] += h * vel[d] + h * h * (b[3 * (size_t)v + d] / massDiag[3 * (size_t)v + d]);
     }
     std::cout << "Xn and Xtilde prepared" << std::endl;
 
-    // Dirichlet data (:291-316, 383-398): mask, displacement to the targets
-    std::vector<uint8_t> dbcMask((size_t)nV, 0);
+    // Dirichlet data (:291-316): mask, displacement to the targets, nodes whose target is where they are
+    std::vector<uint8_t> dbcMask((size_t)nV, 0), dbcFixed((size_t)nV, 0);
     std::vector<bool> DBCb((size_t)nV, false);
     std::vector<double> DBCDisp(n3, 0.0);
-    bool moving = false;
     for (const auto& r : DBC.rows) {
         const Vec<double, 4>& dI = std::get<0>(r);
         const int v = (int)dI[0];
+        bool still = true;
         for (int d = 0; d < 3; ++d) {
             DBCDisp[3 * (size_t)v + d] = dI[d + 1] - s.x[3 * (size_t)v + d];
-            moving = moving || DBCDisp[3 * (size_t)v + d] != 0;
+            still = still && !DBCDisp[3 * (size_t)v + d];
         }
+        dbcFixed[v] = still ? 1 : 0;
         dbcMask[v] = 1;
         DBCb[v] = true;
     }
@@ -503,7 +551,30 @@ inline int advance_one_step_ie_flow(ContactBackend& be, TriStorage& Elem, const 
     be.set_rest_positions(x0.data());
     std::vector<double> massVertex((size_t)nV);
     for (int v = 0; v < nV; ++v) massVertex[v] = massDiag[3 * (size_t)v];
-    be.set_system_terms(tri3, vol, h, massVertex);
+    const std::vector<int> noElem;
+    const std::vector<double> noVol;
+    be.set_system_terms(flow ? tri3 : noElem, flow ? vol : noVol, h, massVertex);
+    if (!flow) {
+        std::vector<double> ib3(3 * (size_t)Elem.size()), lam((size_t)Elem.size()), mu((size_t)Elem.size());
+        for (int e = 0; e < Elem.size(); ++e) {
+            const Mat<double, 2>& IB = std::get<0>(elemAttr.rows[e]);
+            ib3[3 * (size_t)e] = IB(0, 0); ib3[3 * (size_t)e + 1] = IB(0, 1); ib3[3 * (size_t)e + 2] = IB(1, 1);
+            lam[e] = std::get<2>(elasticityAttr.rows[e]); mu[e] = std::get<3>(elasticityAttr.rows[e]);
+        }
+        std::vector<int> st;
+        std::vector<double> info;
+        double k = 0;
+        if (in.bendingStiffMult && elemAttr.size()) { // BENDING.h:53-54
+            k = in.bendingStiffMult * std::get<1>(elemAttr.rows[0])(0, 0);
+            st.resize(4 * edgeStencil.size()); info.resize(3 * edgeStencil.size());
+            for (size_t e = 0; e < edgeStencil.size(); ++e) {
+                for (int i = 0; i < 4; ++i) st[4 * e + i] = edgeStencil[e][i];
+                for (int i = 0; i < 3; ++i) info[3 * e + i] = edgeInfo[e][i];
+            }
+        }
+        be.set_elastic_terms(tri3, ib3, vol, lam, mu, st, info, k, h);
+    }
+    else be.set_elastic_terms(noElem, noVol, noVol, noVol, noVol, noElem, noVol, 0.0, h);
     be.set_positions(s.x.data());
     std::cout << "surface primitives found" << std::endl;
 
@@ -512,6 +583,9 @@ inline int advance_one_step_ie_flow(ContactBackend& be, TriStorage& Elem, const 
         DBCAlpha = be.ccd(DBCDisp.data(), thickness, DBCAlpha);
         printf("DBCAlpha under contact: %le\n", DBCAlpha);
     }
+    StepPotential pot;
+    pot.flow = flow; pot.be = &be; pot.Elem = &Elem; pot.fcr = &elasticityAttr; pot.massDiag = &massDiag; pot.DBC = &DBC; pot.nodeAttr = &nodeAttr; pot.h = h;
+    double DBCPenaltyXn = 0;
     if (DBCAlpha == 1) {
         for (const auto& r : DBC.rows) {
             const Vec<double, 4>& dI = std::get<0>(r);
@@ -519,15 +593,26 @@ inline int advance_one_step_ie_flow(ContactBackend& be, TriStorage& Elem, const 
         }
         printf("DBC handled\n");
     }
-    else {
+    else { // the targets cannot be reached without intersection: augmented-Lagrangian penalty (:413-417, DIRICHLET.h)
         printf("moved DBC by %le, turn on Augmented Lagrangian\n", DBCAlpha);
-        printf("Advance_One_Step_IE_Flow (%s): the augmented-Lagrangian Dirichlet path is outside the device-resident flow step\n", be.name());
-        exit(-1);
+        pot.DBCStiff = 1e6;
+        DBCPenaltyXn = pot.dbc_dist2(xn, false);
     }
-    (void)moving;
+    // the matrix terms that depend on the penalty: diagonal k m_v on the Dirichlet nodes (DIRICHLET.h:73-94) and the
+    // projection mask (all Dirichlet nodes, or only those that do not move while the penalty is active; INC_POTENTIAL.h:387-394)
+    auto set_penalty_terms = [&]() {
+        std::vector<double> mv = massVertex;
+        if (pot.DBCStiff) for (int v = 0; v < nV; ++v) if (dbcMask[v]) mv[v] += pot.DBCStiff * std::get<3>(nodeAttr.rows[v]);
+        be.set_system_terms(flow ? tri3 : noElem, flow ? vol : noVol, h, mv);
+    };
+    if (pot.DBCStiff) set_penalty_terms();
 
-    FlowPotential pot;
-    pot.Elem = &Elem; pot.fcr = &elasticityAttr; pot.massDiag = &massDiag; pot.h = h;
+    auto total_energy = [&]() { // Compute_IncPotential (+ Compute_DBC_Energy) at the backend's current positions
+        double E = pot.energy(s.x, s.xtilde);
+        if (withCollision) be.barrier_energy(dHat2, kappa[0], thickness, E);
+        pot.add_dbc_energy(s.x, E);
+        return E;
+    };
 
     int PNIter = 0;
     double L2Norm = 0;
@@ -537,10 +622,9 @@ inline int advance_one_step_ie_flow(ContactBackend& be, TriStorage& Elem, const 
     printf("computing initial energy\n");
     be.set_positions(s.x.data());
     if (withCollision) s.nRows = be.constraint_set(dHat2, thickness);
-    s.Eprev = pot.energy(s.x, s.xtilde);
-    if (withCollision) be.barrier_energy(dHat2, kappa[0], thickness, s.Eprev);
+    s.Eprev = total_energy();
     printf("entering Newton loop\n");
-    std::deque<double> resRecord;
+    std::deque<double> resRecord, MDBCProgress;
     s.rhs.resize(n3);
     s.sol.resize(n3);
     const int nFree = nV - DBC.size();
@@ -548,9 +632,21 @@ inline int advance_one_step_ie_flow(ContactBackend& be, TriStorage& Elem, const 
         // gradient (:459-491)
         pot.gradient(s.x, s.xtilde, s.g);
         if (withCollision) be.barrier_gradient(dHat2, kappa[0], thickness, s.g.data());
-        for (int v = 0; v < nV; ++v)
-            if (DBCb[v]) s.g[3 * (size_t)v] = s.g[3 * (size_t)v + 1] = s.g[3 * (size_t)v + 2] = 0;
-        std::cout << "project rhs for Dirichlet boundary condition " << DBC.size() << std::endl;
+        if (pot.DBCStiff) {
+            for (const auto& r : DBC.rows) {
+                const Vec<double, 4>& dI = std::get<0>(r);
+                const int v = (int)dI[0];
+                const double km = pot.DBCStiff * std::get<3>(nodeAttr.rows[v]);
+                for (int d = 0; d < 3; ++d) s.g[3 * (size_t)v + d] += km * (s.x[3 * (size_t)v + d] - dI[d + 1]);
+            }
+            for (int v = 0; v < nV; ++v)
+                if (dbcFixed[v]) s.g[3 * (size_t)v] = s.g[3 * (size_t)v + 1] = s.g[3 * (size_t)v + 2] = 0;
+        }
+        else {
+            for (int v = 0; v < nV; ++v)
+                if (DBCb[v]) s.g[3 * (size_t)v] = s.g[3 * (size_t)v + 1] = s.g[3 * (size_t)v + 2] = 0;
+            std::cout << "project rhs for Dirichlet boundary condition " << DBC.size() << std::endl;
+        }
         for (size_t i = 0; i < n3; ++i) s.rhs[i] = -s.g[i];
 
         // Hessian + search direction (:493-556)
@@ -558,7 +654,7 @@ inline int advance_one_step_ie_flow(ContactBackend& be, TriStorage& Elem, const 
             printf("use gradient descent\n");
             s.sol = s.rhs;
         }
-        else if (!be.solve_newton_system(dHat2, kappa[0], thickness, s.rhs.data(), s.sol.data())) {
+        else if (!be.solve_newton_system(dHat2, kappa[0], thickness, pot.DBCStiff ? &dbcFixed : nullptr, s.rhs.data(), s.sol.data())) {
             FILE* out = fopen((outputFolder + "/Hessian_info.txt").c_str(), "a+");
             if (out) { fprintf(out, "Hessian not SPD in PNIter%d\n", PNIter); fclose(out); }
             useGD = true;
@@ -567,7 +663,7 @@ inline int advance_one_step_ie_flow(ContactBackend& be, TriStorage& Elem, const 
         }
 
         double alpha, feasibleAlpha;
-        flow_line_search(be, pot, s, withCollision, dHat2, kappa[0], thickness, alpha, feasibleAlpha);
+        step_line_search(be, pot, s, withCollision, dHat2, kappa[0], thickness, alpha, feasibleAlpha);
 
         // kappa adaptation (:568-598): only rows that were closer than 1e-18 can trigger it, so the previous rows are
         // re-evaluated only when such a row exists (same outcome, no hand-over otherwise)
@@ -585,8 +681,7 @@ inline int advance_one_step_ie_flow(ContactBackend& be, TriStorage& Elem, const 
             if (updateKappa && kappa[0] < kappa[1]) {
                 kappa[0] *= 2;
                 kappaVec[0] *= 2;
-                s.Eprev = pot.energy(s.x, s.xtilde);
-                if (withCollision) be.barrier_energy(dHat2, kappa[0], thickness, s.Eprev);
+                s.Eprev = total_energy();
             }
         }
         rowsPrev.clear(); infoPrev.clear(); dist2Prev.clear();
@@ -633,7 +728,30 @@ inline int advance_one_step_ie_flow(ContactBackend& be, TriStorage& Elem, const 
         }
         else useGD = false;
 
-        if (!withCollision || s.nRows == 0) break; // the flow variant leaves after one iteration without contact (:850-854)
+        // progress of the penalised Dirichlet nodes towards their targets (:701-760)
+        if (pot.DBCStiff) {
+            const double progress = 1 - std::sqrt(pot.dbc_dist2(s.x, false) / DBCPenaltyXn);
+            printf("MDBC progress: %le, DBCStiff %le\n", progress, pot.DBCStiff);
+            MDBCProgress.push_back(progress);
+            if (MDBCProgress.size() > 4) MDBCProgress.pop_front();
+            if (progress < 0.99) {
+                if (L2Norm < NewtonTol * 10 && pot.DBCStiff < 1e8) {
+                    pot.DBCStiff *= 2;
+                    set_penalty_terms();
+                    s.Eprev = total_energy();
+                    printf("updated DBCStiff to %le\n", pot.DBCStiff);
+                }
+                L2Norm = NewtonTol * 10; // ensures not exit Newton loop
+            }
+            else {
+                pot.DBCStiff = 0;
+                set_penalty_terms();
+                s.Eprev = total_energy();
+                printf("DBC moved to target, turn off Augmented Lagrangian\n");
+            }
+        }
+
+        if (flow && (!withCollision || s.nRows == 0)) break; // the flow variant leaves after one iteration without contact (:850-854)
     } while (resRecord.size() < 3 || L2Norm > NewtonTol);
 
     FILE* out = fopen((outputFolder + "/counter.txt").c_str(), "a+");

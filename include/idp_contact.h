@@ -157,6 +157,9 @@ int idp_elastic_gradient(idp_ctx* ctx, double* g_accum, int stride);
 /* CSR_MATRIX::Project_DBC (Math/CSR_MATRIX.h:130-141) applied to the device CSR with the Dirichlet mask of idp_set_mesh:
  * every stored entry whose row or column vertex is a Dirichlet node becomes (row == col). Single-GPU contexts. */
 int idp_project_dbc(idp_ctx* ctx);
+/* the same with a caller-supplied vertex mask (nV bytes; NULL = the mask of idp_set_mesh*): Compute_IncPotential_Hessian projects
+ * only the Dirichlet nodes that do not move (DBCb_fixed) while the augmented-Lagrangian penalty is active (INC_POTENTIAL.h:387-394) */
+int idp_project_dbc_mask(idp_ctx* ctx, const uint8_t* mask);
 /* The role of Solve_Direct (Math/DIRECT_SOLVER.h:14-88: CHOLMOD / SimplicialLDLT on the host) without moving the matrix:
  * conjugate gradients with a 3x3 block-Jacobi preconditioner on the device CSR, x0 = 0, stops when |r| <= rel_tol |rhs| or
  * after max_iter iterations (iterative: the caller states the tolerance; *rel_residual reports what was reached).

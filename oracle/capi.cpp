@@ -90,6 +90,7 @@ void orc_hess_free(void* h) { delete (HessHandle*)h; }
 void orc_membrane_batch(int nElem, const int* elem3, const double* X, const double* ib3, const double* coef, const double* lambda, const double* mu,
     const uint8_t* dbc, int projectSPD, double* E, double* g3nV, double* H81, uint8_t* active)
 {
+    std::vector<double> ge(g3nV ? 9 * (size_t)nElem : 0, 0.0);
 #pragma omp parallel for
     for (int e = 0; e < nElem; ++e) {
         const int* t = elem3 + 3 * e;
@@ -100,17 +101,18 @@ void orc_membrane_batch(int nElem, const int* elem3, const double* X, const doub
         double g[9];
         if (!membrane_EgH(x, ib3 + 3 * e, coef[e], lambda[e], mu[e], projectSPD != 0, E + e, g, H81 ? H81 + 81 * (size_t)e : nullptr)) continue;
         active[e] = 1;
-        if (g3nV)
-            for (int k = 0; k < 3; ++k)
-                for (int d = 0; d < 3; ++d) {
-#pragma omp atomic
-                    g3nV[3 * t[k] + d] += g[3 * k + d];
-                }
+        if (g3nV) std::memcpy(&ge[9 * (size_t)e], g, sizeof(g));
     }
+    if (g3nV) // serial scatter in element order (the reference's loop is serial, MEMBRANE.h:71): reproducible sums
+        for (int e = 0; e < nElem; ++e)
+            if (active[e])
+                for (int k = 0; k < 3; ++k)
+                    for (int d = 0; d < 3; ++d) g3nV[3 * elem3[3 * e + k] + d] += ge[9 * (size_t)e + 3 * k + d];
 }
 void orc_hinge_batch(int nHinge, const int* stencil4, const double* X, const double* info3, double kh2, const uint8_t* dbc, int projectSPD,
     double* E, double* g3nV, double* H144, uint8_t* active)
 {
+    std::vector<double> ge(g3nV ? 12 * (size_t)nHinge : 0, 0.0);
 #pragma omp parallel for
     for (int e = 0; e < nHinge; ++e) {
         const int* t = stencil4 + 4 * e;
@@ -121,13 +123,13 @@ void orc_hinge_batch(int nHinge, const int* stencil4, const double* X, const dou
         double g[12];
         E[e] = hinge_EgH(x, info3[3 * e], kh2 * info3[3 * e + 1] / info3[3 * e + 2], projectSPD != 0, g, H144 ? H144 + 144 * (size_t)e : nullptr);
         active[e] = 1;
-        if (g3nV)
-            for (int k = 0; k < 4; ++k)
-                for (int d = 0; d < 3; ++d) {
-#pragma omp atomic
-                    g3nV[3 * t[k] + d] += g[3 * k + d];
-                }
+        if (g3nV) std::memcpy(&ge[12 * (size_t)e], g, sizeof(g));
     }
+    if (g3nV)
+        for (int e = 0; e < nHinge; ++e)
+            if (active[e])
+                for (int k = 0; k < 4; ++k)
+                    for (int d = 0; d < 3; ++d) g3nV[3 * stencil4[4 * e + k] + d] += ge[12 * (size_t)e + 3 * k + d];
 }
 double orc_dihedral_angle(const double* x12) { return dihedral_angle(ld3(x12), ld3(x12 + 3), ld3(x12 + 6), ld3(x12 + 9)); }
 

@@ -13,4 +13,11 @@ cp -r "$REF/Python/Drivers" "$DST/Python/"
 for m in bunny3K hand cat feline wm2_15k; do
   [ -f "$REF/Projects/FEMShell/input/$m.obj" ] && cp "$REF/Projects/FEMShell/input/$m.obj" "$DST/Projects/FEMShell/input/"
 done
+# config 2 (16_fix_char_seq.py): rest mannequin + the first target frames of the Rumba sequence
+for seq in Rumba_Dancing_unfixed; do
+  mkdir -p "$DST/Projects/FEMShell/input/$seq"
+  for f in $(seq 0 ${MIRROR_FRAMES:-6}); do
+    [ -f "$REF/Projects/FEMShell/input/$seq/$f.obj" ] && cp "$REF/Projects/FEMShell/input/$seq/$f.obj" "$DST/Projects/FEMShell/input/$seq/"
+  done
+done
 echo "mirror at $DST"

@@ -5,7 +5,12 @@ Projects/FEMShell/12-14_normal_flow.py + Python/Drivers run from the writable mi
 Stores the input mesh, counter.txt (PN iterations and contact # per time step, Shell/IMPLICIT_EULER.h:857-864) and the
 final vertex positions. The B200 build of the same module must reproduce the trace (tests/test_gpu_jgsl_module.py).
 
-Run in the authoring container only (needs /root/reference):  python tests/golden/make_golden_normal_flow.py
+The same for BASELINE configs[1] (the animation-fix example, Projects/FEMShell/16_fix_char_seq.py, unchanged): membrane + hinge
+bending + inertia + barrier on wm2_15k following the first frames of Rumba_Dancing_unfixed -> fix_char_seq_trace.npz (the
+script asks for 180 frames; the mirror holds the first 6 targets, so the run ends -- like the reference would -- when frame 7
+cannot be read; the 6 completed steps are the trace).
+
+Run in the authoring container only (needs /root/reference):  python tests/golden/make_golden_normal_flow.py [flow|seq]
 """
 import os
 import subprocess
@@ -29,11 +34,31 @@ def read_obj(path):
     return np.array(V, np.float64), np.array(F, np.int32)
 
 
+def fix_char_seq(cwd, env, n_frames=6):
+    folder = os.path.join(cwd, "output", "16_fix_char_seq")
+    subprocess.call(["rm", "-rf", folder])
+    subprocess.call([sys.executable, "16_fix_char_seq.py"], cwd=cwd, env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    counter = np.array([[int(t) for t in l.split()] for l in open(os.path.join(folder, "counter.txt"))], np.int64)
+    assert len(counter) == n_frames, counter
+    V, F = read_obj(os.path.join(cwd, "input", "wm2_15k.obj"))
+    out = {"rest/V": V, "rest/F": F, "counter": counter, "V_end": read_obj(os.path.join(folder, "shell%d.obj" % n_frames))[0],
+           "V_start": read_obj(os.path.join(folder, "shell0.obj"))[0]}
+    for f in range(1, n_frames + 1):
+        out["frame%d/V" % f] = read_obj(os.path.join(cwd, "input", "Rumba_Dancing_unfixed", "%d.obj" % f))[0]
+    print("fix_char_seq steps", len(counter), "PN iterations", counter[:, 0].sum(), "contact #", counter[:, 1].tolist())
+    np.savez_compressed(os.path.join(HERE, "fix_char_seq_trace.npz"), **out)
+
+
 def main():
     subprocess.check_call([os.path.join(ROOT, "scripts", "make_ref_mirror.sh")])
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "host_shim"), "jgsl_ref/JGSL.so"])
     cwd = os.path.join(MIRROR, "Projects", "FEMShell")
     subprocess.check_call(["chmod", "-R", "u+w", cwd])
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which in ("seq", "all"):
+        fix_char_seq(cwd, dict(os.environ, PYTHONPATH=os.path.join(ROOT, "tests", "host_shim", "jgsl_ref"), OMP_NUM_THREADS="8"))
+    if which == "seq":
+        return
     out = {}
     for mesh, smooth, mag, frames in CASES:
         folder = os.path.join(cwd, "output", "12-14_normal_flow", "%s_%s_%s_%s" % (mesh, smooth, mag, frames))

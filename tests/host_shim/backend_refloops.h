@@ -20,6 +20,11 @@ long refipc_barrier(int nV, const double* x, const double* x0, int n, const int*
 double refipc_ccd(int nV, const double* x, int nBN, const int* bn, int nBE, const int* be, int nBT, const int* bt, const unsigned char* dbc,
     const double* dir, double thickness, double step);
 double refipc_min_dist2(int nV, const double* x, int n, const int* rows4, double thickness, double* dist2);
+// the oracle's restatement of the elastic terms (oracle/orc_elastic.hpp; the reference's MEMBRANE.h / BENDING.h cannot be compiled here)
+void orc_membrane_batch(int nElem, const int* elem3, const double* X, const double* ib3, const double* coef, const double* lambda, const double* mu,
+    const unsigned char* dbc, int projectSPD, double* E, double* g3nV, double* H81, unsigned char* active);
+void orc_hinge_batch(int nHinge, const int* stencil4, const double* X, const double* info3, double kh2, const unsigned char* dbc, int projectSPD,
+    double* E, double* g3nV, double* H144, unsigned char* active);
 long ref_csr_system(int n, long nT, const int* r, const int* c, const double* v, const double* mdiag, const unsigned char* dbc, int dim,
     int* ptr, int* col, double* val, long cap);
 }
@@ -62,6 +67,34 @@ public:
     {
         elem_ = elem3; vol_ = vol; h_ = h; mass_ = mass;
     }
+    void set_elastic_terms(const std::vector<int>& elem3, const std::vector<double>& ib3, const std::vector<double>& vol, const std::vector<double>& lambda,
+        const std::vector<double>& mu, const std::vector<int>& stencil4, const std::vector<double>& info3, double k, double h) override
+    {
+        mElem_ = elem3; mIB_ = ib3; mLam_ = lambda; mMu_ = mu; hSt_ = stencil4; hInfo_ = info3; hKh2_ = h * h * k;
+        mCoef_.resize(vol.size());
+        for (size_t e = 0; e < vol.size(); ++e) mCoef_[e] = h * h * vol[e];
+    }
+    void elastic(double* Esum, double* g, std::vector<double>* H81, std::vector<double>* H144, std::vector<unsigned char>* actM, std::vector<unsigned char>* actH)
+    {
+        const int nM = (int)mElem_.size() / 3, nH = (int)hSt_.size() / 4;
+        std::vector<double> E((size_t)std::max(nM, nH) + 1);
+        std::vector<unsigned char> am((size_t)nM + 1), ah((size_t)nH + 1);
+        if (H81) H81->assign(81 * (size_t)nM, 0.0);
+        if (H144) H144->assign(144 * (size_t)nH, 0.0);
+        if (nM) {
+            orc_membrane_batch(nM, mElem_.data(), x_.data(), mIB_.data(), mCoef_.data(), mLam_.data(), mMu_.data(), dbc_.data(), 1, E.data(), g, H81 ? H81->data() : nullptr,
+                am.data());
+            if (Esum) for (int e = 0; e < nM; ++e) *Esum += E[e];
+        }
+        if (nH) {
+            orc_hinge_batch(nH, hSt_.data(), x_.data(), hInfo_.data(), hKh2_, dbc_.data(), 1, E.data(), g, H144 ? H144->data() : nullptr, ah.data());
+            if (Esum) for (int e = 0; e < nH; ++e) *Esum += E[e];
+        }
+        if (actM) *actM = am;
+        if (actH) *actH = ah;
+    }
+    void elastic_energy(double& E) override { elastic(&E, nullptr, nullptr, nullptr, nullptr, nullptr); }
+    void elastic_gradient(double* g) override { elastic(nullptr, g, nullptr, nullptr, nullptr, nullptr); }
     void set_positions(const double* x) override { x_.assign(x, x + 3 * (size_t)nV_); }
     int constraint_set(double dHat2, double thickness) override
     {
@@ -91,7 +124,7 @@ public:
         refipc_barrier(nV_, x_.data(), x0_.data(), (int)w.size(), rows_.data(), w.data(), dHat2, kappa, thickness, 0, nullptr, g, 0, nullptr, nullptr,
             nullptr);
     }
-    bool solve_newton_system(double dHat2, double kappa, double thickness, const double* rhs, double* sol) override
+    bool solve_newton_system(double dHat2, double kappa, double thickness, const std::vector<uint8_t>* projMask, const double* rhs, double* sol) override
     {
         // triplets in the reference's order: flow term (INC_POTENTIAL.h:323-339), then the barrier Hessians
         std::vector<int> tr, tc;
@@ -104,6 +137,25 @@ public:
                     tr.push_back(a); tc.push_back(q); tv.push_back(-h_ * vol_[e] / 6);
                     tr.push_back(a); tc.push_back(a); tv.push_back(2 * h_ * vol_[e] / 6);
                 }
+        if (!mElem_.empty() || !hSt_.empty()) { // membrane, then hinges (INC_POTENTIAL.h:344-352), dense per element like the reference's triplets
+            std::vector<double> H81, H144;
+            std::vector<unsigned char> am, ah;
+            elastic(nullptr, nullptr, &H81, &H144, &am, &ah);
+            for (size_t e = 0; e < mElem_.size() / 3; ++e) {
+                if (!am[e]) continue;
+                for (int i = 0; i < 9; ++i)
+                    for (int j = 0; j < 9; ++j) {
+                        tr.push_back(mElem_[3 * e + i / 3] * 3 + i % 3); tc.push_back(mElem_[3 * e + j / 3] * 3 + j % 3); tv.push_back(H81[81 * e + 9 * i + j]);
+                    }
+            }
+            for (size_t e = 0; e < hSt_.size() / 4; ++e) {
+                if (!ah[e]) continue;
+                for (int i = 0; i < 12; ++i)
+                    for (int j = 0; j < 12; ++j) {
+                        tr.push_back(hSt_[4 * e + i / 3] * 3 + i % 3); tc.push_back(hSt_[4 * e + j / 3] * 3 + j % 3); tv.push_back(H144[144 * e + 12 * i + j]);
+                    }
+            }
+        }
         if (!rows_.empty()) {
             std::vector<double> w = weights();
             const long cap = 144 * (long)w.size();
@@ -120,7 +172,7 @@ public:
         const long cap = (long)tv.size() + n;
         std::vector<int> ptr((size_t)n + 1), col((size_t)cap);
         std::vector<double> val((size_t)cap);
-        const long nnz = ref_csr_system(n, (long)tv.size(), tr.data(), tc.data(), tv.data(), md.data(), dbc_.data(), 3, ptr.data(), col.data(), val.data(), cap);
+        const long nnz = ref_csr_system(n, (long)tv.size(), tr.data(), tc.data(), tv.data(), md.data(), projMask ? projMask->data() : dbc_.data(), 3, ptr.data(), col.data(), val.data(), cap);
         if (nnz < 0) return false;
         // Jacobi-preconditioned conjugate gradients
         std::vector<double> dinv((size_t)n), r(rhs, rhs + n), z((size_t)n), p((size_t)n), Ap((size_t)n);
@@ -191,7 +243,9 @@ private:
     }
     int nV_ = 0;
     double h_ = 0;
-    std::vector<int> bnode_, bedge_, btri_, elem_, rows_;
+    std::vector<int> bnode_, bedge_, btri_, elem_, rows_, mElem_, hSt_;
+    std::vector<double> mIB_, mCoef_, mLam_, mMu_, hInfo_;
+    double hKh2_ = 0;
     std::vector<uint8_t> dbc_;
     std::vector<double> x_, x0_, vol_, mass_, info_;
 };

@@ -11,6 +11,8 @@ REFLOOPS_DIR = os.path.join(ROOT, "tests", "host_shim", "jgsl_ref")
 DRIVER = os.path.join(ROOT, "tests", "jgsl_driver", "normal_flow.py")
 MIRROR = os.path.join(ROOT, "baseline", "_ref", "IDP_mirror", "Projects", "FEMShell")
 TRACE = os.path.join(ROOT, "tests", "golden", "normal_flow_trace.npz")
+SEQ_TRACE = os.path.join(ROOT, "tests", "golden", "fix_char_seq_trace.npz")
+SEQ_DRIVER = os.path.join(ROOT, "tests", "jgsl_driver", "fix_char_seq.py")
 
 
 def build_product():
@@ -50,6 +52,36 @@ def run_own_driver(module_dir, mesh_obj, smooth, mag, frames, out, threads="8", 
         rc = subprocess.call([sys.executable, DRIVER, mesh_obj, str(smooth), str(mag), str(frames), out], env=env, stdout=lf, stderr=subprocess.STDOUT,
                              timeout=timeout)
     return rc, log
+
+
+def write_sequence(folder, z):
+    """rest mesh + target frames of the animation-fix fixture as the files the example reads"""
+    os.makedirs(os.path.join(folder, "seq"), exist_ok=True)
+    write_obj(os.path.join(folder, "rest.obj"), z["rest/V"], z["rest/F"])
+    n = len(z["counter"])
+    for f in range(1, n + 1):
+        write_obj(os.path.join(folder, "seq", "%d.obj" % f), z["frame%d/V" % f], z["rest/F"])
+    return os.path.join(folder, "rest.obj"), os.path.join(folder, "seq"), n
+
+
+def run_own_seq_driver(module_dir, rest_obj, seq, frames, out, threads="8", timeout=3000):
+    env = dict(os.environ, PYTHONPATH=module_dir, OMP_NUM_THREADS=threads)
+    os.makedirs(out, exist_ok=True)
+    log = os.path.join(out, "log.txt")
+    with open(log, "w") as lf:
+        rc = subprocess.call([sys.executable, SEQ_DRIVER, rest_obj, seq, str(frames), out], env=env, stdout=lf, stderr=subprocess.STDOUT, timeout=timeout)
+    return rc, log
+
+
+def run_reference_seq_script(module_dir, threads="8", timeout=3000):
+    """The reference's UNCHANGED Projects/FEMShell/16_fix_char_seq.py from the mirror. It asks for 180 frames; the mirror holds the
+    first targets only, so the process ends when a frame cannot be read (as the reference's would): the return code is not
+    checked, the completed steps are."""
+    folder = os.path.join(MIRROR, "output", "16_fix_char_seq")
+    subprocess.call(["rm", "-rf", folder])
+    env = dict(os.environ, PYTHONPATH=module_dir, OMP_NUM_THREADS=threads)
+    subprocess.call([sys.executable, "16_fix_char_seq.py"], cwd=MIRROR, env=env, stdout=subprocess.DEVNULL, stderr=subprocess.STDOUT, timeout=timeout)
+    return folder
 
 
 def run_reference_script(module_dir, mesh, smooth, mag, frames, threads="8", timeout=3000):

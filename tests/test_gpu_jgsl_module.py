@@ -10,8 +10,8 @@ import numpy as np
 import pytest
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-from jgsl_common import (MIRROR, PRODUCT_DIR, TRACE, build_product, compare_trace, read_counter, read_obj, run_own_driver, run_reference_script,  # noqa: E402
-                         write_obj)
+from jgsl_common import (MIRROR, PRODUCT_DIR, SEQ_TRACE, TRACE, build_product, compare_trace, read_counter, read_obj, run_own_driver,  # noqa: E402
+                         run_own_seq_driver, run_reference_script, run_reference_seq_script, write_obj, write_sequence)
 
 pytestmark = pytest.mark.gpu
 
@@ -61,3 +61,42 @@ def test_reference_scripts_run_unchanged_on_b200_module():
     compare_trace(read_counter(os.path.join(folder, "counter.txt")), z["hand/counter"], 3)
     Vend, _ = read_obj(os.path.join(folder, "shell%s.obj" % frames))
     _check_end_state(Vend, z, "hand", 0.01)
+
+
+def _check_seq(counter, Vend, z):
+    """Animation-fix example against the reference-loop trace: same number of steps, contact counts within 1 %, PN iterations
+    per step within 2 (the first step is the long one), end state within 1 % (median) / 10 % (99th percentile) of the motion."""
+    g = z["counter"]
+    assert counter.shape == g.shape, (counter.tolist(), g.tolist())
+    assert np.all(np.abs(counter[:, 1] - g[:, 1]) <= 0.01 * g[:, 1]), (counter[:, 1].tolist(), g[:, 1].tolist())
+    assert np.all(np.abs(counter[:, 0] - g[:, 0]) <= 2), (counter[:, 0].tolist(), g[:, 0].tolist())
+    moved = np.median(np.linalg.norm(z["V_end"] - z["V_start"], axis=1))
+    dev = np.linalg.norm(Vend - z["V_end"], axis=1)
+    assert moved > 0 and np.median(dev) <= 0.01 * moved and np.quantile(dev, 0.99) <= 0.10 * moved, (np.median(dev), np.quantile(dev, 0.99), moved)
+
+
+@pytest.mark.skipif(not os.path.exists(SEQ_TRACE), reason="fix_char_seq fixture absent")
+def test_b200_module_animation_fix_example(tmp_path):
+    """BASELINE configs[1]: wm2_15k (12,811 vertices / 25,472 triangles) following Rumba_Dancing_unfixed, dHat = 1e-2: membrane +
+    hinge bending + inertia + barrier, every term assembled and solved on the device."""
+    build_product()
+    z = np.load(SEQ_TRACE)
+    rest, seq, n = write_sequence(str(tmp_path), z)
+    out = str(tmp_path / "out")
+    rc, log = run_own_seq_driver(PRODUCT_DIR, rest, seq, n, out)
+    text = open(log).read()
+    assert rc == 0, text[-3000:]
+    assert "(B200 backend)" in text and "linear solve (device PCG)" in text
+    _check_seq(read_counter(os.path.join(out, "counter.txt")), read_obj(os.path.join(out, "shell%d.obj" % n))[0], z)
+    mins = [float(l.split()[2].rstrip(",")) for l in text.splitlines() if l.startswith("minDist2 =")]
+    assert mins and min(mins) > 0
+
+
+@pytest.mark.skipif(not (os.path.isdir(os.path.join(MIRROR, "input", "Rumba_Dancing_unfixed")) and os.path.exists(SEQ_TRACE)),
+                    reason="mirror of the reference's unchanged scripts / sequence absent (scripts/make_ref_mirror.sh)")
+def test_reference_animation_fix_script_runs_unchanged_on_b200_module():
+    build_product()
+    z = np.load(SEQ_TRACE)
+    folder = run_reference_seq_script(PRODUCT_DIR)
+    n = len(z["counter"])
+    _check_seq(read_counter(os.path.join(folder, "counter.txt")), read_obj(os.path.join(folder, "shell%d.obj" % n))[0], z)

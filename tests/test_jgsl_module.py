@@ -33,7 +33,7 @@ def test_module_surface(J):
     for name in ["V2dStorage", "V3dStorage", "V4dStorage", "V2iStorage", "V3iStorage", "V4iStorage", "SiStorage", "SdStorage", "V3dV3dV3dSdStorage",
                  "M2dM2dSdStorage", "M3dM3dSdStorage", "V2iV3dV3dV3dSdStorage"]:
         getattr(J.Storage, name)()
-    for name in ["Add_Shell", "Initialize_Shell_Hinge_EIPC", "Initialize_OIPC", "Update_Normal_Flow_Neumann", "Advance_One_Step_IE_Flow"]:
+    for name in ["Add_Shell", "Initialize_Shell_Hinge_EIPC", "Initialize_OIPC", "Update_Normal_Flow_Neumann", "Advance_One_Step_IE_Flow", "Advance_One_Step_IE_Hinge"]:
         assert hasattr(J.FEM.DiscreteShell, name), name
     for name in ["Boundary_Dirichlet", "Init_Dirichlet", "Step_Dirichlet", "Turn_Dirichlet", "Reset_Dirichlet", "Load_Dirichlet"]:
         assert hasattr(J.FEM, name), name
@@ -42,7 +42,7 @@ def test_module_surface(J):
     J.Set_Parameter("Terminate", False)
     assert J.Get_Parameter("Terminate", True) is False and J.Get_Parameter("missing", 7) == 7
     with pytest.raises(NotImplementedError):  # outside the hosted path: named, not silently absent
-        J.FEM.DiscreteShell.Advance_One_Step_IE_Hinge()
+        J.FEM.DiscreteShell.Advance_One_Step_SIE_Hinge()
 
 
 def _setup(J, tmp_path, V, F, h=0.5):
