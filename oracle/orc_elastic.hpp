@@ -8,7 +8,7 @@
 // is the oracle's cyclic-Jacobi makePD (Math/UTILS.h:9-27). Parity status: UNPINNED against compiled reference code (the
 // reference headers of these terms pull in the whole shell stack: Cabana storages, meta, the SVD routine); the dihedral
 // angle, its gradient and Hessian ARE pinned by the reference's own Math/DIHEDRAL_ANGLE.h compiled in oracle/_ref
-// (tests/test_elastic_oracle.py) where that build exists.
+// (tests/test_elastic_host.py::test_oracle_hinge_is_pinned_by_the_reference_dihedral_code) where that build exists.
 #pragma once
 #include "orc_deriv.hpp"
 #include <cmath>

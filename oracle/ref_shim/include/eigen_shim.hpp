@@ -99,6 +99,7 @@ struct Matrix {
         return redux_sum(t, 0, R * C);
     }
     T norm() const { return std::sqrt(squaredNorm()); }
+    Matrix normalized() const { Matrix r = *this; const T n = norm(); for (int i = 0; i < R * C; ++i) r.d[i] = d[i] / n; return r; }
     T prod() const { T p = d[0]; for (int i = 1; i < R * C; ++i) p *= d[i]; return p; }
     // Gaussian elimination with full pivoting (3x3 use in dead code of FEM/IPC.h; not result relevant)
     struct FullPivLU {
@@ -174,6 +175,7 @@ struct Matrix {
         template <class O> BlockRef& operator+=(const O& o) { const Matrix<T, BR, BC> v = o; for (int i = 0; i < BR; ++i) for (int j = 0; j < BC; ++j) m(i0 + i, j0 + j) += v(i, j); return *this; }
         template <class O> BlockRef& operator=(const O& o) { const Matrix<T, BR, BC> v = o; for (int i = 0; i < BR; ++i) for (int j = 0; j < BC; ++j) m(i0 + i, j0 + j) = v(i, j); return *this; }
         Matrix<T, BC, BR> transpose() const { return ((Matrix<T, BR, BC>)*this).transpose(); }
+        void setZero() { for (int i = 0; i < BR; ++i) for (int j = 0; j < BC; ++j) m(i0 + i, j0 + j) = T(0); }
     };
     template <int BR, int BC> BlockRef<BR, BC> block(int i, int j) { return BlockRef<BR, BC>{*this, i, j}; }
     struct DiagRef {

@@ -5,6 +5,7 @@
 #include <Math/Distance/EDGE_EDGE_MOLLIFIER.h>
 #include <Math/BARRIER.h>
 #include <Math/UTILS.h>
+#include <Math/DIHEDRAL_ANGLE.h>         // the hinge angle, its gradient and Hessian (used by FEM/Shell/BENDING.h)
 
 using namespace JGSL;
 typedef Eigen::Matrix<double, 3, 1> V3d;
@@ -66,6 +67,21 @@ int ref_aabb(int kind, const double* x, const double* d, double dist)
     case 1: return Edge_Edge_CD_Broadphase(l3(x), l3(x + 3), l3(x + 6), l3(x + 9), dist);
     case 2: return Point_Triangle_CCD_Broadphase(l3(x), l3(x + 3), l3(x + 6), l3(x + 9), l3(d), l3(d + 3), l3(d + 6), l3(d + 9), dist);
     default: return Edge_Edge_CCD_Broadphase(l3(x), l3(x + 3), l3(x + 6), l3(x + 9), l3(d), l3(d + 3), l3(d + 6), l3(d + 9), dist);
+    }
+}
+// Compute_Dihedral_Angle / _Gradient / _Hessian (Math/DIHEDRAL_ANGLE.h:9-24, 176-205, 1191-1298) in the argument order
+// FEM/Shell/BENDING.h calls them with: the hinge stencil (x0; x1, x2; x3). g: 12, H: 12 x 12 row major.
+void ref_dihedral(const double* x, double* theta, double* g, double* H)
+{
+    Eigen::Matrix<double, 3, 1> v0(x[0], x[1], x[2]), v1(x[3], x[4], x[5]), v2(x[6], x[7], x[8]), v3(x[9], x[10], x[11]);
+    JGSL::Compute_Dihedral_Angle(v0, v1, v2, v3, *theta);
+    Eigen::Matrix<double, 12, 1> grad;
+    JGSL::Compute_Dihedral_Angle_Gradient(v0, v1, v2, v3, grad);
+    Eigen::Matrix<double, 12, 12> Hs;
+    JGSL::Compute_Dihedral_Angle_Hessian(v0, v1, v2, v3, Hs);
+    for (int i = 0; i < 12; ++i) {
+        g[i] = grad[i];
+        for (int j = 0; j < 12; ++j) H[i * 12 + j] = Hs(i, j);
     }
 }
 }

@@ -117,3 +117,27 @@ def test_membrane_matches_oracle_jets(orc, hs):
     assert rc == 0 and abs(E) < 1e-13 and np.abs(g).max() < 1e-10 * np.sqrt(ib[0])
     rc, *_ = _membrane(hs, X0.ravel().copy(), np.array([1.0, 2.0, 4.0]), 1.0, 3.0, 2.0, True)
     assert rc == 2
+
+
+def test_oracle_hinge_is_pinned_by_the_reference_dihedral_code(orc):
+    """oracle/orc_elastic.hpp (jets of an atan2 formulation) against the REFERENCE's own Math/DIHEDRAL_ANGLE.h compiled in
+    oracle/_ref/libidp_ref.so: angle bit for bit, gradient and Hessian of W = c (theta - thetabar)^2 built from the
+    reference's closed forms (BENDING.h:196-200, 470-477) within 1e-10."""
+    lib = os.path.join(ROOT, "oracle", "_ref", "libidp_ref.so")
+    if not os.path.exists(lib):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    L = C.CDLL(lib)
+    if not hasattr(L, "ref_dihedral"):
+        pytest.skip("oracle/_ref predates ref_dihedral")
+    L.ref_dihedral.argtypes = [C.c_void_p] * 4
+    rng = np.random.default_rng(17)
+    for x in _random_hinges(rng, 300):
+        th = np.zeros(1); g = np.zeros(12); H = np.zeros((12, 12))
+        L.ref_dihedral(_p(x), _p(th), _p(g), _p(H))
+        assert orc.dihedral_angle(x) == th[0]
+        thetabar, c = rng.uniform(-1, 1), 10.0 ** rng.uniform(-3, 3)
+        oE, og, oH, _ = orc.hinge_batch(x.reshape(4, 3), np.arange(4), np.array([[thetabar, 2.0, 0.5]]), c * 0.5 / 2.0, project_spd=False)
+        d = th[0] - thetabar
+        assert abs(oE[0] - c * d * d) <= 1e-12 * c * d * d
+        assert _rel(og.ravel(), 2 * c * d * g) <= 1e-10
+        assert _rel(oH[0], 2 * c * (d * H + np.outer(g, g))) <= 1e-10
