@@ -31,7 +31,8 @@ EXPORTS = ["idp_create", "idp_destroy", "idp_last_error", "idp_set_stream", "idp
            "idp_set_shard", "idp_kernel_launches", "idp_library_calls", "idp_reset_counters", "idp_stage_ms",
            "idp_last_count", "idp_measure_fp64_tflops", "idp_system_set_flow_term", "idp_system_set_mass", "idp_project_dbc",
            "idp_solve_pcg", "idp_set_mesh_from_triangles", "idp_get_surface_primitives", "idp_get_constraints_begin",
-           "idp_get_hessian_csr_begin", "idp_transfers_end"]
+           "idp_get_hessian_csr_begin", "idp_transfers_end", "idp_system_set_membrane", "idp_system_set_hinges", "idp_elastic_energy",
+           "idp_elastic_gradient", "idp_project_dbc_mask"]
 
 
 class IdpError(RuntimeError):
