@@ -17,6 +17,7 @@
 #include <pybind11/stl.h>
 #include <pybind11/stl_bind.h>
 
+#include <chrono>
 #include <memory>
 #include <variant>
 
@@ -161,7 +162,10 @@ PYBIND11_MODULE(JGSL, m)
     m.def("Get_Parameter", &get_param<double>);
     m.def("Get_Parameter", &get_param<std::string>);
     m.def("TIMER_FLUSH", [](int frame, int frameNum, double t, double frameDt) {
-        printf("[frame %d/%d] %.6g of %.6g", frame, frameNum, t, frameDt);
+        static auto last = std::chrono::steady_clock::now();
+        const auto now = std::chrono::steady_clock::now();
+        printf("[frame %d/%d] %.6g of %.6g, %.3f s since the previous flush", frame, frameNum, t, frameDt, std::chrono::duration<double>(now - last).count());
+        last = now;
         if (backend_slot()) printf("  (%s backend)", backend_slot()->name());
         printf("\n");
         fflush(stdout);
