@@ -32,7 +32,8 @@ EXPORTS = ["idp_create", "idp_destroy", "idp_last_error", "idp_set_stream", "idp
            "idp_last_count", "idp_measure_fp64_tflops", "idp_system_set_flow_term", "idp_system_set_mass", "idp_project_dbc",
            "idp_solve_pcg", "idp_set_mesh_from_triangles", "idp_get_surface_primitives", "idp_get_constraints_begin",
            "idp_get_hessian_csr_begin", "idp_transfers_end", "idp_system_set_membrane", "idp_system_set_hinges", "idp_elastic_energy",
-           "idp_elastic_gradient", "idp_project_dbc_mask"]
+           "idp_elastic_gradient", "idp_project_dbc_mask", "idp_friction_update", "idp_friction_set", "idp_friction_energy",
+           "idp_friction_gradient", "idp_get_friction"]
 
 
 class IdpError(RuntimeError):
@@ -93,6 +94,11 @@ def load_library(path=LIB_PATH):
     L.idp_system_set_mass.argtypes = [vp, vp]
     L.idp_project_dbc.argtypes = [vp]
     L.idp_project_dbc_mask.argtypes = [vp, vp]
+    L.idp_friction_update.argtypes = [vp, d, d, d, C.POINTER(l)]
+    L.idp_friction_set.argtypes = [vp, vp, i, d, d]
+    L.idp_friction_energy.argtypes = [vp, C.POINTER(d)]
+    L.idp_friction_gradient.argtypes = [vp, vp, i]
+    L.idp_get_friction.argtypes = [vp, C.POINTER(l), vp, vp, vp, vp]
     L.idp_system_set_membrane.argtypes = [vp, i, vp, i, vp, vp, vp, vp, d]
     L.idp_system_set_hinges.argtypes = [vp, i, vp, vp, d, d]
     L.idp_elastic_energy.argtypes = [vp, C.POINTER(d)]
@@ -242,6 +248,34 @@ class ContactContext:
         g = np.zeros((self.nV, 3), np.float64) if g_accum is None else g_accum
         self._ck(self.L.idp_elastic_gradient(self.h, _p(g), g.shape[1]))
         return g
+
+    def friction_update(self, dhat2, kappa, thickness=0.0):
+        n = C.c_long(0)
+        self._ck(self.L.idp_friction_update(self.h, dhat2, kappa, thickness, C.byref(n)))
+        return n.value
+
+    def friction_set(self, Xn, epsv2_h2, mu):
+        Xn = None if Xn is None else np.ascontiguousarray(Xn, np.float64)
+        self._ck(self.L.idp_friction_set(self.h, _p(Xn), 3 if Xn is None else Xn.shape[1], float(epsv2_h2), float(mu)))
+
+    def friction_energy(self, E0=0.0):
+        E = C.c_double(E0)
+        self._ck(self.L.idp_friction_energy(self.h, C.byref(E)))
+        return E.value
+
+    def friction_gradient(self, g_accum=None):
+        g = np.zeros((self.nV, 3), np.float64) if g_accum is None else g_accum
+        self._ck(self.L.idp_friction_gradient(self.h, _p(g), g.shape[1]))
+        return g
+
+    def get_friction(self):
+        n = C.c_long(0)
+        self._ck(self.L.idp_get_friction(self.h, C.byref(n), None, None, None, None))
+        n = n.value
+        rows = np.zeros((n, 4), np.int32); cp = np.zeros((n, 2)); basis = np.zeros((n, 6)); nf = np.zeros(n)
+        if n:
+            self._ck(self.L.idp_get_friction(self.h, None, _p(rows), _p(cp), _p(basis), _p(nf)))
+        return rows, cp, basis, nf
 
     def project_dbc(self, mask=None):
         if mask is None:

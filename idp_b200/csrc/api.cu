@@ -117,7 +117,7 @@ int idp_set_mesh(idp_ctx* c, int nV, int nBN, const int* bnode, int nBE, const i
     c->nV = nV; c->nBN = nBN; c->nBE = nBE; c->nBT = nBT;
     c->have_x = c->have_x0 = c->have_dir = false;
     c->meanEdgeVersion = -1; // new boundary edges
-    c->surfValid = false; c->nFlowElem = 0; c->haveMass = false; c->nMem = 0; c->nHinge = 0;
+    c->surfValid = false; c->nFlowElem = 0; c->haveMass = false; c->nMem = 0; c->nHinge = 0; c->nFric = 0; c->nFricActive = 0; c->have_xn = false;
     c->nRows = 0; c->nCandPT = c->nCandEE = c->nCcdPT = c->nCcdEE = 0;
     c->permValid = false;
     IDP_CK(c, c->bnode.reserve(std::max(nBN, 1)));
@@ -464,6 +464,57 @@ int idp_elastic_gradient(idp_ctx* c, double* g_accum, int stride)
         for (int a = 0; a < 3; ++a) g_accum[(long)stride * v + a] += g[3 * v + a];
     return IDP_OK;
 }
+// ---- lagged friction (friction_kernels.cu) -----------------------------------------------------------
+int idp_friction_update(idp_ctx* c, double dhat2, double kappa, double thickness, long* n_friction_rows)
+{
+    if (!c) return IDP_ERR_INVALID;
+    IDP_CK(c, cudaSetDevice(c->device));
+    IDP_TRY(friction_update(c, dhat2, kappa, thickness));
+    if (n_friction_rows) *n_friction_rows = c->nFricActive;
+    return IDP_OK;
+}
+int idp_friction_set(idp_ctx* c, const double* xn, int stride, double epsv2_h2, double mu)
+{
+    if (!c || !(mu >= 0) || (mu > 0 && (!xn || !(epsv2_h2 > 0)))) return c ? fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "idp_friction_set: bad arguments", __FILE__, __LINE__) : IDP_ERR_INVALID;
+    IDP_CK(c, cudaSetDevice(c->device));
+    c->fricMu = mu;
+    c->fricEpsvh = mu > 0 ? std::sqrt(epsv2_h2) : 0.0;
+    if (xn) {
+        IDP_TRY(upload_positions(c, xn, stride, 3));
+        c->have_xn = true;
+    }
+    return IDP_OK;
+}
+int idp_friction_energy(idp_ctx* c, double* E_inout)
+{
+    if (!c || !E_inout) return IDP_ERR_INVALID;
+    IDP_CK(c, cudaSetDevice(c->device));
+    double E = 0;
+    IDP_TRY(friction_energy_gradient(c, 1, 0, &E));
+    *E_inout += E;
+    return IDP_OK;
+}
+int idp_friction_gradient(idp_ctx* c, double* g_accum, int stride)
+{
+    if (!c || (g_accum && stride < 3)) return IDP_ERR_INVALID;
+    IDP_CK(c, cudaSetDevice(c->device));
+    IDP_TRY(friction_energy_gradient(c, 0, 1, nullptr));
+    if (!g_accum) return IDP_OK;
+    std::vector<double> g(3 * (size_t)c->nV);
+    IDP_CK(c, cudaMemcpyAsync(g.data(), c->fricG.p, g.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    IDP_CK(c, cudaStreamSynchronize(c->stream));
+    for (long v = 0; v < c->nV; ++v)
+        for (int a = 0; a < 3; ++a) g_accum[(long)stride * v + a] += g[3 * v + a];
+    return IDP_OK;
+}
+int idp_get_friction(idp_ctx* c, long* n_rows, int* rows4, double* closest2, double* basis6, double* normal_force)
+{
+    if (!c) return IDP_ERR_INVALID;
+    IDP_CK(c, cudaSetDevice(c->device));
+    if (n_rows) *n_rows = c->nFricActive;
+    if (!rows4 && !closest2 && !basis6 && !normal_force) return IDP_OK;
+    return friction_copy_rows(c, rows4, closest2, basis6, normal_force);
+}
 int idp_project_dbc(idp_ctx* c)
 {
     if (!c) return IDP_ERR_INVALID;
@@ -490,7 +541,7 @@ int idp_set_mesh_from_triangles(idp_ctx* c, int nV, int nF, const int* tri, int 
         for (int k = 0; k < 3; ++k)
             if (tri[(long)stride * i + k] < 0 || tri[(long)stride * i + k] >= nV) return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "idp_set_mesh_from_triangles: vertex index out of range", __FILE__, __LINE__);
     IDP_CK(c, cudaSetDevice(c->device));
-    c->nFlowElem = 0; c->haveMass = false; c->nMem = 0; c->nHinge = 0; // a new mesh drops the terms of the previous one
+    c->nFlowElem = 0; c->haveMass = false; c->nMem = 0; c->nHinge = 0; c->nFric = 0; c->nFricActive = 0; c->have_xn = false; // a new mesh drops the terms of the previous one
     return extract_surface(c, nV, nF, tri, stride, x, xstride, dbc);
 }
 int idp_get_surface_primitives(idp_ctx* c, int* nBN, int* bnode, int* nBE, int* bedge2, int* nBT, int* btri3, double* BNArea, double* BEArea, double* BTArea)

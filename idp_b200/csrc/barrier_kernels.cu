@@ -273,7 +273,7 @@ int barrier_eval(idp_ctx* c, double dhat2, double kappa, double thickness, int w
         IDP_CK(c, cudaMemsetAsync(c->gbuf.p, 0, 3 * (size_t)c->nV * sizeof(double), c->stream));
     }
     if (want_h) { c->nnz = 0; c->nBlocksUnique = 0; c->nBlocksEmitted = 0; }
-    const bool extraTerms = want_h && (c->nFlowElem > 0 || c->haveMass || c->nMem > 0 || c->nHinge > 0); // the other terms are assembled even without contact rows
+    const bool extraTerms = want_h && (c->nFlowElem > 0 || c->haveMass || c->nMem > 0 || c->nHinge > 0 || (c->nFricActive > 0 && c->fricMu > 0 && c->have_xn)); // the other terms are assembled even without contact rows
     if (c->nRows == 0 && !extraTerms) return IDP_OK;
     StageTimer tm(c, IDP_STAGE_BARRIER);
     IDP_CK(c, cudaMemsetAsync(c->counters.p + CNT_ERR_DIST, 0, sizeof(long long), c->stream));
@@ -322,11 +322,11 @@ int barrier_eval(idp_ctx* c, double dhat2, double kappa, double thickness, int w
     a.errDist = (unsigned long long*)(c->counters.p + CNT_ERR_DIST);
     a.errEig = (unsigned long long*)(c->counters.p + CNT_ERR_EIG);
     a.vtxOff = nullptr; a.vtxCursor = nullptr; a.bktKey = nullptr; a.bktVal8 = nullptr; a.bktVal1 = nullptr;
-    long nBlocks = 0, nExtra = 0, nElastic = 0;
+    long nBlocks = 0, nExtra = 0, nElastic = 0, nFricRows = 0;
     ExtraArgs xaKeep = {};
     if (want_h) {
         c->csrProjected = false;
-        if (c->nRows + (long)c->nFlowElem + c->nV + c->nMem + c->nHinge >= (1L << 28)) return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "more than 2^28 constraint rows (+ elements + vertices) on one rank", __FILE__, __LINE__);
+        if (c->nRows + (long)c->nFlowElem + c->nV + c->nMem + c->nHinge + c->nFric >= (1L << 28)) return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "more than 2^28 constraint rows (+ elements + vertices) on one rank", __FILE__, __LINE__);
         const size_t nV1 = (size_t)c->nV + 1;
         IDP_CK(c, c->vtxCnt.reserve(nV1)); IDP_CK(c, c->vtxOff.reserve(nV1)); IDP_CK(c, c->vtxCursor.reserve(nV1));
         IDP_CK(c, cudaMemsetAsync(c->vtxCnt.p, 0, nV1 * sizeof(int), c->stream));
@@ -343,6 +343,7 @@ int barrier_eval(idp_ctx* c, double dhat2, double kappa, double thickness, int w
         xaKeep = xa;
         // membrane triangles and bending hinges (elastic_kernels.cu)
         if (c->nMem > 0 || c->nHinge > 0) IDP_TRY(elastic_block_counts(c, c->vtxCnt.p, &nElastic));
+        IDP_TRY(friction_block_counts(c, c->vtxCnt.p, &nFricRows)); // lagged friction rows (friction_kernels.cu)
         IDP_TRY(cub_scan_exclusive(c, c->vtxCnt.p, c->vtxOff.p, (long)nV1));
         int total = 0;
         IDP_CK(c, cudaMemcpyAsync(&total, c->vtxOff.p + c->nV, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -379,6 +380,7 @@ int barrier_eval(idp_ctx* c, double dhat2, double kappa, double thickness, int w
         IDP_LAUNCH(c, k_extra_emit, std::min(blocks_for(nExtra, 256), (unsigned)c->sm_count * 16), 256, 0, xaKeep);
     }
     if (want_h && nElastic > 0) IDP_TRY(elastic_emit_blocks(c, project_spd, (unsigned)(nMine + nExtra), c->vtxCursor.p, c->bktKey.p, c->bktVal8.p, c->bktVal1.p));
+    if (want_h && nFricRows > 0) IDP_TRY(friction_emit_blocks(c, (unsigned)(nMine + nExtra + nElastic), c->vtxCursor.p, c->bktKey.p, c->bktVal8.p, c->bktVal1.p));
     if (nMine > 0 && want_e) IDP_LAUNCH(c, k_sum_partials, 1, 256, 0, c->red.p, 3 * (int)grid, c->red.p + 3 * (size_t)grid);
     long long nerr = 0, neig = 0;
     IDP_CK(c, cudaMemcpyAsync(&nerr, c->counters.p + CNT_ERR_DIST, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));

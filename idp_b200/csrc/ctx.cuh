@@ -133,7 +133,7 @@ struct idp_ctx {
     // ---- per-iterate state ----
     idp::DBuf<double> stage;            // upload staging (AoS)
     idp::DBuf<double> xs, ys, zs;       // SoA positions (streaming kernels)
-    idp::DBuf<double4> xp, x0p, dp;     // 32-byte packed positions / rest positions / search direction (gathers)
+    idp::DBuf<double4> xp, x0p, dp, xnp; // 32-byte packed positions / rest positions / search direction / step-start positions (gathers)
     bool have_x = false, have_x0 = false, have_dir = false;
     long xVersion = 0, meanEdgeVersion = -1; // positions counter; mean boundary-edge length cached per positions (hash builds)
     double meanEdgeCached = 0;
@@ -200,6 +200,12 @@ struct idp_ctx {
     idp::DBuf<double> elasticG;         // gradient of the elastic terms (3 nV)
     int nMem = 0, nHinge = 0;
     double hingeKh2 = 0;                // h^2 k
+    // ---- lagged friction (friction_kernels.cu): rows frozen by idp_friction_update ----
+    idp::DBuf<unsigned char> fricRows;  // FricRow records (friction.cuh)
+    idp::DBuf<double> fricG;            // friction gradient (3 nV)
+    long nFric = 0, nFricActive = 0;
+    double fricMu = 0, fricEpsvh = 0;
+    bool have_xn = false;
     // ---- device-side surface extraction (idp_set_mesh_from_triangles) ----
     idp::DBuf<int> surfTri;
     idp::DBuf<double> surfTriArea, surfTriAreaH, surfNodeArea, surfNodeAreaC, surfEdgeArea, surfEdgeArea2;
@@ -312,7 +318,7 @@ struct KernelTimer : ScopeTimer {
 };
 
 // ---- host-side launchers implemented in the .cu files ----
-int upload_positions(idp_ctx* c, const double* host_xyz, int stride, int which); // which: 0 X, 1 X0, 2 dir
+int upload_positions(idp_ctx* c, const double* host_xyz, int stride, int which); // which: 0 X, 1 X0, 2 dir, 3 Xn (friction)
 int build_constraint_set(idp_ctx* c, double dhat2, double thickness);
 int sorted_candidates(idp_ctx* c, int which, int2* host_out);
 int barrier_eval(idp_ctx* c, double dhat2, double kappa, double thickness, int want_e, int want_g, int want_h,
@@ -323,6 +329,12 @@ int project_dbc(idp_ctx* c, const unsigned char* host_mask = nullptr);
 int elastic_block_counts(idp_ctx* c, int* vtxCnt, long* nElements);
 int elastic_emit_blocks(idp_ctx* c, int project_spd, unsigned tagBase, int* vtxCursor, unsigned long long* bktKey, double* bktVal8, double* bktVal1);
 int elastic_energy_gradient(idp_ctx* c, int want_e, int want_g, double* E_out);
+// lagged friction: basis from the current rows / positions; bucket counts / Hessian blocks for the assembly; E and g
+int friction_update(idp_ctx* c, double dhat2, double kappa, double thickness);
+int friction_block_counts(idp_ctx* c, int* vtxCnt, long* nRows);
+int friction_emit_blocks(idp_ctx* c, unsigned tagBase, int* vtxCursor, unsigned long long* bktKey, double* bktVal8, double* bktVal1);
+int friction_energy_gradient(idp_ctx* c, int want_e, int want_g, double* E_out);
+int friction_copy_rows(idp_ctx* c, int* rows4, double* closest2, double* basis6, double* normalForce);
 int solve_pcg(idp_ctx* c, const double* rhs, double* sol, double rel_tol, int max_iter, int* iters, double* rel_res);
 int extract_surface(idp_ctx* c, int nV, int nF, const int* tri, int stride, const double* x, int xstride, const unsigned char* dbc);
 int min_dist2(idp_ctx* c, double thickness, double* host_dist2, double* min_out);

@@ -82,7 +82,7 @@ int upload_positions(idp_ctx* c, const double* host, int stride, int which)
     const size_t n = (size_t)c->nV * stride;
     IDP_CK(c, c->stage.reserve(n));
     IDP_CK(c, cudaMemcpyAsync(c->stage.p, host, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    DBuf<double4>& dst = which == 0 ? c->xp : (which == 1 ? c->x0p : c->dp);
+    DBuf<double4>& dst = which == 0 ? c->xp : (which == 1 ? c->x0p : (which == 2 ? c->dp : c->xnp));
     IDP_CK(c, dst.reserve(c->nV));
     if (which == 0) {
         IDP_CK(c, c->xs.reserve(c->nV));

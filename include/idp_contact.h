@@ -154,6 +154,23 @@ int idp_system_set_hinges(idp_ctx* ctx, int n_hinge, const int* stencil4, const 
  * g_accum may be NULL) at the current positions. The barrier operators above stay barrier-only. */
 int idp_elastic_energy(idp_ctx* ctx, double* E_inout);
 int idp_elastic_gradient(idp_ctx* ctx, double* g_accum, int stride);
+/* Lagged friction (FEM/FRICTION.h:17-662), reusing the constraint rows:
+ *   idp_friction_update  = Compute_Friction_Basis (:17-124): freezes the non-mollified rows of the CURRENT constraint set at the
+ *     current positions with their closest-point weights, tangent bases and normal forces -b'(d) 2 sqrt(d) (lagged until the
+ *     next update); *n_friction_rows = how many rows carry friction;
+ *   idp_friction_set     = the Xn / epsv2*h*h / mu arguments of Compute_Friction_Potential / _Gradient / _Hessian (:172-662);
+ *     mu = 0 switches the term off;
+ *   idp_friction_energy / _gradient add mu * sum lambda f0(|u|) and its gradient at the current positions; the Hessian blocks
+ *     (inner 2x2 matrix is PSD by construction, so no projection is needed) are assembled into the same device CSR by every
+ *     following idp_barrier_hessian / idp_barrier_all (INC_POTENTIAL.h:375-377);
+ *   idp_get_friction copies the frozen rows in the reference's layout (rows, closest-point parameters (2), tangent basis
+ *     (3x2 column major), normal force); any pointer may be NULL.
+ * Per-component friction coefficients (Compute_Friction_Coef, :126-170) are not built. idp_set_mesh* clears the rows. */
+int idp_friction_update(idp_ctx* ctx, double dhat2, double kappa, double thickness, long* n_friction_rows);
+int idp_friction_set(idp_ctx* ctx, const double* xn, int stride, double epsv2_h2, double mu);
+int idp_friction_energy(idp_ctx* ctx, double* E_inout);
+int idp_friction_gradient(idp_ctx* ctx, double* g_accum, int stride);
+int idp_get_friction(idp_ctx* ctx, long* n_rows, int* rows4, double* closest2, double* basis6, double* normal_force);
 /* CSR_MATRIX::Project_DBC (Math/CSR_MATRIX.h:130-141) applied to the device CSR with the Dirichlet mask of idp_set_mesh:
  * every stored entry whose row or column vertex is a Dirichlet node becomes (row == col). Single-GPU contexts. */
 int idp_project_dbc(idp_ctx* ctx);

@@ -125,6 +125,10 @@ class ReferenceIPC:
                                  C.c_double, C.c_double]
         L.refipc_min_dist2.restype = C.c_double
         L.refipc_min_dist2.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_void_p]
+        if hasattr(L, "refipc_friction"):
+            L.refipc_friction.restype = C.c_long
+            L.refipc_friction.argtypes = ([C.c_int] + [C.c_void_p] * 3 + [C.c_int, C.c_void_p, C.c_void_p] + [C.c_double] * 5 + [C.c_int] +
+                                          [C.c_void_p] * 7 + [C.c_long] + [C.c_void_p] * 3)
 
     @staticmethod
     def _mesh(m):
@@ -159,3 +163,23 @@ class ReferenceIPC:
         d = np.zeros(len(rows))
         mn = self.lib.refipc_min_dist2(len(X), _p(X), len(rows), _p(rows), thickness, _p(d))
         return d, mn
+
+    def friction(self, Xb, rows, dHat2, kappa, X=None, Xn=None, epsv2_h2=1e-6, mu=0.3, thickness=0.0, project_spd=True, weights=None):
+        """The reference's own FEM/FRICTION.h: Compute_Friction_Basis at Xb (returned as rows / closest points / bases / normal
+        forces) and, with X and Xn, potential, gradient and Hessian triplets."""
+        Xb = np.ascontiguousarray(Xb, np.float64); rows = np.ascontiguousarray(rows, np.int32)
+        n = len(rows)
+        w = np.ones(n) if weights is None else np.ascontiguousarray(weights, np.float64)
+        nf = C.c_int(0)
+        frows = np.zeros((n, 4), np.int32); cp = np.zeros((n, 2)); basis = np.zeros((n, 6)); lam = np.zeros(n)
+        E = C.c_double(0.0); g = np.zeros_like(Xb)
+        ev = X is not None
+        if ev:
+            X = np.ascontiguousarray(X, np.float64); Xn = np.ascontiguousarray(Xn, np.float64)
+        cap = 144 * n + 1
+        tr = np.zeros(cap, np.int32); tc = np.zeros(cap, np.int32); tv = np.zeros(cap)
+        nt = self.lib.refipc_friction(len(Xb), _p(Xb), _p(X) if ev else None, _p(Xn) if ev else None, n, _p(rows), _p(w), dHat2, kappa, thickness,
+                                      epsv2_h2, mu, int(project_spd), C.byref(nf), _p(frows), _p(cp), _p(basis), _p(lam), C.byref(E), _p(g), cap,
+                                      _p(tr), _p(tc), _p(tv))
+        k = nf.value
+        return dict(rows=frows[:k], closest=cp[:k], basis=basis[:k], normal_force=lam[:k], E=E.value, g=g, triplets=(tr[:nt], tc[:nt], tv[:nt]))

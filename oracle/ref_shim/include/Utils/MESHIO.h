@@ -45,6 +45,20 @@ struct BASE_STORAGE {
         for (int i = 0; i < size; ++i) f(i, Get_Unchecked(i));
     }
     template <class F> void Each(F f) { for (int i = 0; i < size; ++i) f(i, Get_Unchecked(i)); }
+    void deep_copy_to(BASE_STORAGE& o) const { o.rows = rows; o.size = size; }
+    // Join(other).Par_Each(f): f(id, tuple of references to this row's fields followed by the other storage's)
+    template <class... Us> struct JOINED {
+        BASE_STORAGE& a; BASE_STORAGE<Us...>& b;
+        template <class F> void Par_Each(F f)
+        {
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 64)
+#endif
+            for (int i = 0; i < a.size; ++i) f(i, std::tuple_cat(a.Get_Unchecked(i), b.Get_Unchecked(i)));
+        }
+        template <class F> void Each(F f) { for (int i = 0; i < a.size; ++i) f(i, std::tuple_cat(a.Get_Unchecked(i), b.Get_Unchecked(i))); }
+    };
+    template <class... Us> JOINED<Us...> Join(BASE_STORAGE<Us...>& o) { return JOINED<Us...>{*this, o}; }
 private:
     template <std::size_t... I> static std::tuple<Ts&...> ref_tuple(std::tuple<Ts...>& t, std::index_sequence<I...>) { return std::tuple<Ts&...>(std::get<I>(t)...); }
 };

@@ -48,6 +48,8 @@ struct Matrix {
     template <int R2, int C2, class = typename std::enable_if<(R2 == C && C2 == R && R != C)>::type>
     Matrix(const Array<T, R2, C2>& a) { for (int i = 0; i < R * C; ++i) d[i] = a.d[i]; }
     static Matrix Zero() { Matrix m; m.setZero(); return m; }
+    static Matrix UnitX() { Matrix m; m.setZero(); m.d[0] = T(1); return m; }
+    static Matrix UnitY() { Matrix m; m.setZero(); m.d[1] = T(1); return m; }
     T& operator()(int i, int j) { return d[i + j * R]; }
     const T& operator()(int i, int j) const { return d[i + j * R]; }
     T& operator()(int i) { return d[i]; }
@@ -167,6 +169,7 @@ struct Matrix {
         operator Matrix<T, N, 1>() const { Matrix<T, N, 1> r; for (int i = 0; i < N; ++i) r.d[i] = m.d[s + i]; return r; }
         SegRef& operator=(const Matrix<T, N, 1>& r) { for (int i = 0; i < N; ++i) m.d[s + i] = r.d[i]; return *this; }
         Matrix<T, N, 1> operator-() const { return -((Matrix<T, N, 1>)*this); }
+        friend Matrix<T, N, 1> operator*(T a, const SegRef& r) { Matrix<T, N, 1> o; for (int i = 0; i < N; ++i) o.d[i] = a * r.m.d[r.s + i]; return o; }
     };
     template <int N> SegRef<N> segment(int s) { return SegRef<N>{*this, s}; }
     template <int BR, int BC> struct BlockRef {
@@ -182,6 +185,8 @@ struct Matrix {
         Matrix& m;
         void setConstant(T v) { for (int i = 0; i < (R < C ? R : C); ++i) m(i, i) = v; }
         T& operator[](int i) { return m(i, i); }
+        struct ArrRef { Matrix& m; ArrRef& operator+=(T v) { for (int i = 0; i < (R < C ? R : C); ++i) m(i, i) += v; return *this; } };
+        ArrRef array() { return ArrRef{m}; }
     };
     DiagRef diagonal() { return DiagRef{*this}; }
 

@@ -3,6 +3,7 @@
 // Cabana, the repo's Eigen subset, an inert pybind11) and exposes the six operators
 // <double, 3, shell=false, elasticIPC=false> to ctypes. No reference source is copied into this repository.
 #include <FEM/IPC.h>
+#include <FEM/FRICTION.h>
 
 using namespace JGSL;
 typedef double T;
@@ -111,6 +112,49 @@ double refipc_min_dist2(int nV, const double* x, int n, const int* rows4, double
     Compute_Min_Dist2<T, 3, false>(s.X, cs, thickness, d, mn);
     for (size_t i = 0; i < d.size(); ++i) dist2[i] = d[i];
     return mn;
+}
+
+// Lagged friction (FEM/FRICTION.h:17-662): Compute_Friction_Basis at xb with the contact rows, then potential / gradient /
+// Hessian triplets at x relative to xn. Outputs: the friction rows (the non-mollified contact rows, in order), closest-point
+// parameters (2 per row), tangent bases (6 per row, column major 3x2), normal forces; E (added), g (nV x 3, added), triplets.
+long refipc_friction(int nV, const double* xb, const double* x, const double* xn, int n, const int* rows4, const double* w, double dHat2, double kappa,
+    double thickness, double epsvh2, double mu, int projectSPD, int* nFric, int* fricRows4, double* closest2, double* basis6, double* normalForce,
+    double* E, double* g, long cap, int* trow, int* tcol, double* tval)
+{
+    Scene sb(nV, xb, nullptr, 0, nullptr, 0, nullptr, 0, nullptr, nullptr);
+    std::vector<VECTOR<int, 4>> cs, fcs;
+    std::vector<VECTOR<T, 2>> info;
+    to_rows(rows4, w, n, dHat2, cs, info);
+    std::vector<Eigen::Matrix<T, 2, 1>> cp;
+    std::vector<Eigen::Matrix<T, 3, 2>> tb;
+    std::vector<T> nf;
+    T kap[3] = {kappa, kappa, kappa};
+    Compute_Friction_Basis<T, 3, false>(sb.X, cs, info, fcs, cp, tb, nf, dHat2, kap, thickness);
+    *nFric = (int)fcs.size();
+    for (size_t i = 0; i < fcs.size(); ++i) {
+        for (int k = 0; k < 4; ++k) fricRows4[4 * i + k] = fcs[i][k];
+        closest2[2 * i] = cp[i][0]; closest2[2 * i + 1] = cp[i][1];
+        for (int c = 0; c < 2; ++c) for (int r = 0; r < 3; ++r) basis6[6 * i + 3 * c + r] = tb[i](r, c);
+        normalForce[i] = nf[i];
+    }
+    if (!x) return 0;
+    Scene s(nV, x, nullptr, 0, nullptr, 0, nullptr, 0, nullptr, nullptr), sn(nV, xn, nullptr, 0, nullptr, 0, nullptr, 0, nullptr, nullptr);
+    if (E) Compute_Friction_Potential<T, 3>(s.X, sn.X, fcs, cp, tb, nf, epsvh2, mu, *E);
+    if (g) {
+        Compute_Friction_Gradient<T, 3>(s.X, sn.X, fcs, cp, tb, nf, epsvh2, mu, s.nodeAttr);
+        for (int i = 0; i < nV; ++i) {
+            const VECTOR<T, 3>& gi = std::get<FIELDS<MESH_NODE_ATTR<T, 3>>::g>(s.nodeAttr.Get_Unchecked(i));
+            for (int k = 0; k < 3; ++k) g[3 * i + k] += gi[k];
+        }
+    }
+    long nt = 0;
+    if (trow) {
+        std::vector<Eigen::Triplet<T>> trip;
+        Compute_Friction_Hessian<T, 3>(s.X, sn.X, fcs, cp, tb, nf, epsvh2, mu, projectSPD != 0, trip);
+        nt = (long)trip.size();
+        for (long i = 0; i < nt && i < cap; ++i) { trow[i] = trip[i].row(); tcol[i] = trip[i].col(); tval[i] = trip[i].value(); }
+    }
+    return nt;
 }
 
 } // extern "C"

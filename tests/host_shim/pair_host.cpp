@@ -4,6 +4,7 @@
 #include "../../idp_b200/csrc/pair_deriv.cuh"
 #include "../../idp_b200/csrc/psd_lowrank.cuh"
 #include "../../idp_b200/csrc/shell_elastic.cuh"
+#include "../../idp_b200/csrc/friction.cuh"
 using namespace idp;
 static V3 l3(const double* p) { return mk3(p[0], p[1], p[2]); }
 extern "C" {
@@ -83,6 +84,38 @@ int hs_membrane_EgH(const double* x, const double* ib3, double coef, double lamb
     *E = out.E;
     for (int i = 0; i < 9; ++i) g[i] = out.g[i];
     return out.eigFail ? 1 : 0;
+}
+// friction.cuh on the host: basis of n contact rows at Xb, then E (added), g (nV x 3, added) and the dense per-row Hessians
+// (n x 12 x 12 over the row's stencil order, zero padded) at X relative to Xn. Outputs per row: nv, v[4], w[4], basis (6), lam.
+void hs_friction(int n, const int* rows4, const double* Xb, const double* X, const double* Xn, double dHat2, double kappa, double xi, double epsvh,
+    double mu, int* nv, int* verts, double* w, double* basis, double* lam, double* cp, double* E, double* g, double* H)
+{
+    for (int i = 0; i < n; ++i) {
+        const RowDec d = decode_row(rows4[4 * i], rows4[4 * i + 1], rows4[4 * i + 2], rows4[4 * i + 3]);
+        V3 xb[4];
+        for (int k = 0; k < 4; ++k) xb[k] = l3(Xb + 3 * (long)d.v[k]);
+        FricRow f;
+        friction_basis(d, xb, 1.0, dHat2 + 2 * sqrt(dHat2) * xi, kappa, xi * xi, f);
+        nv[i] = f.nv; lam[i] = f.lam;
+        for (int k = 0; k < 4; ++k) { verts[4 * i + k] = f.v[k]; w[4 * i + k] = f.w[k]; }
+        for (int a = 0; a < 3; ++a) { basis[6 * i + a] = f.t0[a]; basis[6 * i + 3 + a] = f.t1[a]; }
+        cp[2 * i] = f.cp[0]; cp[2 * i + 1] = f.cp[1];
+        if (!X || f.nv == 0) continue;
+        V3 dx[4];
+        for (int k = 0; k < 4; ++k) {
+            dx[k] = mk3(0, 0, 0);
+            if (k < f.nv) dx[k] = (f.pp_abs && k == 1) ? l3(X + 3 * (long)f.v[k]) : l3(X + 3 * (long)f.v[k]) - l3(Xn + 3 * (long)f.v[k]);
+        }
+        *E += friction_energy(f, dx, epsvh, mu);
+        double g3[3], B[9];
+        friction_gradient(f, dx, epsvh, mu, g3);
+        friction_hessian_core(f, dx, epsvh, mu, B);
+        for (int k = 0; k < f.nv; ++k) for (int a = 0; a < 3; ++a) g[3 * (long)f.v[k] + a] += f.w[k] * g3[a];
+        for (int p = 0; p < f.nv; ++p)
+            for (int q = 0; q < f.nv; ++q)
+                for (int a = 0; a < 3; ++a)
+                    for (int b = 0; b < 3; ++b) H[144 * (long)i + (3 * p + a) * 12 + 3 * q + b] = f.w[p] * f.w[q] * B[3 * a + b];
+    }
 }
 #ifdef IDP_QL_STATS
 // development aid (scripts/ql_stats.py): chase lengths of the QL trips of the last 9x9 projection

@@ -1,0 +1,117 @@
+"""Lagged friction: the product's device header idp_b200/csrc/friction.cuh compiled for the host (CPU
+test) and the CUDA path through the C ABI (GPU test) against the REFERENCE's own FEM/FRICTION.h compiled in
+oracle/_ref/libidp_ref_ipc.so (Compute_Friction_Basis / _Potential / _Gradient / _Hessian). Bars: friction rows identical,
+closest points / bases / normal forces / E / g / H within 1e-10 relative."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from conftest import make_cases  # noqa: E402
+from oracle import ref_binding  # noqa: E402
+
+KAPPA, MU, EPSV2H2 = 1e5, 0.4, 1e-4 * 0.01 ** 2 * 25.0
+needs_ref = pytest.mark.skipif(not (ref_binding.ipc_available() and hasattr(C.CDLL(ref_binding.LIB_IPC), "refipc_friction")),
+                               reason="oracle/_ref with the reference's FRICTION.h is not built (needs /root/reference)")
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _scene(orc, case, k):
+    """contact rows of a test mesh (oracle), a step-start state Xn and an iterate X that slides tangentially"""
+    name, m, d, dhats = case
+    dh2 = dhats[-1] ** 2
+    om = orc.mesh(m.X, m.X0, m.bnode, m.bedge, m.btri, m.dbc)
+    rows, info, _, _ = orc.constraint_set(om, dh2)
+    rng = np.random.default_rng(100 + k)
+    scale = np.sqrt(EPSV2H2)
+    Xn = m.X - rng.normal(0, 3.0 * scale, m.X.shape)           # displacements on both sides of the eps_v h clamp
+    X = m.X + rng.normal(0, 0.3 * scale, m.X.shape)
+    some = rng.uniform(size=len(X)) < 0.2
+    X[some] = Xn[some]                                          # vertices that did not move at all
+    return m, rows, dh2, Xn, X
+
+
+@needs_ref
+def test_friction_header_on_host_matches_reference(orc):
+    src = os.path.join(ROOT, "tests", "host_shim", "pair_host.cpp")
+    out = os.path.join(ROOT, "tests", "host_shim", "libpair_host.so")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", out, src])
+    hs = C.CDLL(out)
+    hs.hs_friction.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.c_double] * 5 + [C.c_void_p] * 9
+    ref = ref_binding.ReferenceIPC()
+    for k, case in enumerate(make_cases()):
+        m, rows, dh2, Xn, X = _scene(orc, case, k)
+        n = len(rows)
+        assert n > 0
+        r = ref.friction(m.X, rows, dh2, KAPPA, X=X, Xn=Xn, epsv2_h2=EPSV2H2, mu=MU)
+        nv = np.zeros(n, np.int32); verts = np.zeros((n, 4), np.int32); w = np.zeros((n, 4)); basis = np.zeros((n, 6)); lam = np.zeros(n)
+        cp = np.zeros((n, 2)); E = np.zeros(1); g = np.zeros_like(X); H = np.zeros((n, 12, 12))
+        rows_c = np.ascontiguousarray(rows, np.int32); Xb = np.ascontiguousarray(m.X)
+        hs.hs_friction(n, _p(rows_c), _p(Xb), _p(X), _p(Xn), dh2, KAPPA, 0.0, np.sqrt(EPSV2H2), MU, _p(nv), _p(verts), _p(w), _p(basis), _p(lam), _p(cp),
+                       _p(E), _p(g), _p(H))
+        act = nv > 0
+        assert act.sum() == len(r["rows"]) and np.array_equal(rows_c[act], r["rows"])       # the non-mollified rows, in order
+        mult = np.where(rows_c[act][:, 3] < -1, -rows_c[act][:, 3], 1)
+        assert np.allclose(lam[act] / mult, r["normal_force"], rtol=1e-12, atol=0)
+        assert np.allclose(basis[act], r["basis"], rtol=0, atol=1e-12)
+        four = nv[act] == 4
+        assert np.allclose(cp[act][four], r["closest"][four], rtol=1e-10, atol=1e-12)
+        assert abs(E[0] - r["E"]) <= 1e-10 * abs(r["E"])
+        assert np.abs(g - r["g"]).max() <= 1e-10 * np.abs(r["g"]).max()
+        dof = (3 * verts[:, :, None] + np.arange(3)[None, None, :]).reshape(n, 12)
+        rr = np.repeat(dof[:, :, None], 12, axis=2); cc = np.repeat(dof[:, None, :], 12, axis=1)
+        keep = np.abs(H) > 0
+        A = sp.coo_matrix((H[keep], (rr[keep], cc[keep])), shape=(3 * len(X),) * 2).tocsr()
+        tr, tc, tv = r["triplets"]
+        B = sp.coo_matrix((tv, (tr, tc)), shape=A.shape).tocsr()
+        assert spla.norm(A - B) <= 1e-10 * spla.norm(B), (case[0], spla.norm(A - B) / spla.norm(B))
+        assert spla.norm(B) > 0
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_friction_on_the_device_matches_reference(lib_built, orc):
+    from idp_b200 import ContactContext
+    ref = ref_binding.ReferenceIPC()
+    for k, case in enumerate(make_cases()):
+        m, rows, dh2, Xn, X = _scene(orc, case, k)
+        n3 = 3 * m.nV
+        c = ContactContext(0)
+        try:
+            c.set_surface_mesh(m)
+            assert c.constraint_set(dh2) == len(rows)
+            grows, _ = c.get_constraints()
+            nfr = c.friction_update(dh2, KAPPA)                      # Compute_Friction_Basis at the current positions
+            r = ref.friction(m.X, grows, dh2, KAPPA, X=X, Xn=Xn, epsv2_h2=EPSV2H2, mu=MU)
+            assert nfr == len(r["rows"])
+            frows, cp, basis, nf = c.get_friction()
+            assert np.array_equal(frows, r["rows"])
+            assert np.allclose(nf, r["normal_force"], rtol=1e-12, atol=0) and np.allclose(basis, r["basis"], rtol=0, atol=1e-12)
+            c.friction_set(Xn, EPSV2H2, MU)
+            c.set_positions(X)
+            E = c.friction_energy(E0=0.5)
+            assert abs(E - 0.5 - r["E"]) <= 1e-10 * abs(r["E"])
+            g = c.friction_gradient()
+            assert np.abs(g - r["g"]).max() <= 1e-10 * np.abs(r["g"]).max()
+            # the friction blocks ride along with the barrier Hessian: H(mu) - H(0) = the reference's friction triplets
+            c.set_constraints(grows)
+            p1, c1, v1 = c.barrier_hessian(dh2, KAPPA, project_spd=True)
+            c.friction_set(None, 0.0, 0.0)
+            p0, c0, v0 = c.barrier_hessian(dh2, KAPPA, project_spd=True)
+            A = sp.csr_matrix((v1, c1, p1), shape=(n3, n3)) - sp.csr_matrix((v0, c0, p0), shape=(n3, n3))
+            tr, tc, tv = r["triplets"]
+            B = sp.coo_matrix((tv, (tr, tc)), shape=(n3, n3)).tocsr()
+            assert spla.norm(A - B) <= 1e-9 * spla.norm(B), (case[0], spla.norm(A - B) / spla.norm(B))
+            assert c.friction_energy() == 0.0                        # mu = 0 switches the term off
+        finally:
+            c.close()
