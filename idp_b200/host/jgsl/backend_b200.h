@@ -99,6 +99,16 @@ public:
         printf("linear solve (device PCG): %d iterations, relative residual %le\n", iters, rel);
         return rel <= 1e3 * pcg_rel_tol && rel == rel;
     }
+    long friction_update(double dHat2, double kappa, double thickness) override
+    {
+        long n = 0;
+        check(idp_friction_update(ctx_, dHat2, kappa, thickness, &n));
+        fresh_ = false;
+        return n;
+    }
+    void friction_set(const double* xn, double epsv2h2, double mu) override { check(idp_friction_set(ctx_, xn, 3, epsv2h2, mu)); fresh_ = false; }
+    void friction_energy(double& E) override { check(idp_friction_energy(ctx_, &E)); }
+    void friction_gradient(double* g) override { check(idp_friction_gradient(ctx_, g, 3)); }
     double ccd(const double* dir, double thickness, double alpha) override
     {
         check(idp_ccd_step(ctx_, dir, 3, thickness, &alpha));

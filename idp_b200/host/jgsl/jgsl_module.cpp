@@ -281,11 +281,12 @@ PYBIND11_MODULE(JGSL, m)
                    Fcr3Storage& tetElasticityAttr, const StdVectorVector2i& rod, const StdVectorVector3d& rodInfo, const StdVectorVector3i& rodHinge,
                    const StdVectorVector3d& rodHingeInfo, const StdVectorVector3i& stitchInfo, const StdVectorXd& stitchRatio, double k_stitch,
                    const StdVectorXi& particle, const std::string& outputFolder) {
-            (void)edge2tri; (void)fiberLimit; (void)s; (void)sHat; (void)epsv2; (void)fricIterAmt; (void)tetAttr; (void)tetElasticityAttr; (void)rodInfo;
+            (void)edge2tri; (void)fiberLimit; (void)s; (void)sHat; (void)tetAttr; (void)tetElasticityAttr; (void)rodInfo;
             (void)rodHinge; (void)rodHingeInfo; (void)stitchRatio; (void)k_stitch;
             ShellStepInputs in;
             in.flow = flow; in.thickness = thickness; in.bendingStiffMult = bendingStiffMult; in.h = h; in.NewtonTol = NewtonTol; in.dHat2 = dHat2;
-            in.mu = (muComp.size() && muComp.size() == compNodeRange.size() * compNodeRange.size()) ? 1.0 : mu; // per-component friction requested
+            in.mu = mu; in.epsv2 = epsv2; in.fricIterAmt = fricIterAmt;
+            in.muPerComponent = muComp.size() && muComp.size() == compNodeRange.size() * compNodeRange.size();
             in.withCollision = withCollision; in.staticSolve = staticSolve;
             in.nTet = tet.size(); in.nRod = (int)rod.size(); in.nStitch = (int)stitchInfo.size(); in.nParticle = (int)particle.size();
             in.outputFolder = outputFolder;

@@ -49,6 +49,12 @@ struct ContactBackend {
     // Compute_IncPotential_Hessian (flow) + Solve_Direct: assemble flow + mass + projected barrier Hessians, Project_DBC, solve
     // projMask: the vertices Project_DBC fixes (null: the Dirichlet mask of set_mesh)
     virtual bool solve_newton_system(double dHat2, double kappa, double thickness, const std::vector<uint8_t>* projMask, const double* rhs, double* sol) = 0;
+    // lagged friction (FEM/FRICTION.h): freeze the current rows at the current positions; E / g at the current positions relative
+    // to xn; the Hessian blocks are part of solve_newton_system while mu > 0
+    virtual long friction_update(double dHat2, double kappa, double thickness) = 0;     // Compute_Friction_Basis, returns #friction rows
+    virtual void friction_set(const double* xn, double epsv2h2, double mu) = 0;
+    virtual void friction_energy(double& E) = 0;   // adds
+    virtual void friction_gradient(double* g) = 0; // adds
     virtual double ccd(const double* dir, double thickness, double alpha) = 0;          // Compute_Intersection_Free_StepSize
     virtual bool min_dist2(double thickness, std::vector<double>* dist2, double& minDist2) = 0; // false: no rows
     virtual void get_rows(std::vector<int>& rows4, std::vector<double>& info2) = 0;
@@ -368,6 +374,7 @@ struct StepPotential {
     const DbcStorage* DBC = nullptr;
     const NodeAttrStorage* nodeAttr = nullptr;
     double h = 0, DBCStiff = 0;
+    bool friction = false; // mu > 0 and contact on: Compute_Friction_Potential joins every energy evaluation
     std::vector<double> Lx;
 
     void laplacian(const std::vector<double>& x)
@@ -461,6 +468,7 @@ inline void step_line_search(ContactBackend& be, StepPotential& pot, StepState& 
                 }
             }
             be.barrier_energy(dHat2, kappa, thickness, E);
+            if (pot.friction) be.friction_energy(E);
         }
         pot.add_dbc_energy(s.x, E);
         alpha /= 2.0;
@@ -472,7 +480,9 @@ inline void step_line_search(ContactBackend& be, StepPotential& pot, StepState& 
 
 struct ShellStepInputs { // the arguments of Advance_One_Step_IE_Discrete_Shell the hosted variants read (IMPLICIT_EULER.h:151-187)
     bool flow = false;
-    double thickness = 0, bendingStiffMult = 0, h = 0, NewtonTol = 1e-3, dHat2 = 0, mu = 0;
+    double thickness = 0, bendingStiffMult = 0, h = 0, NewtonTol = 1e-3, dHat2 = 0, mu = 0, epsv2 = 0;
+    int fricIterAmt = 1;
+    bool muPerComponent = false; // Compute_Friction_Coef (per-component coefficients) is not hosted
     bool withCollision = false, staticSolve = false;
     int nTet = 0, nRod = 0, nStitch = 0, nParticle = 0;
     std::string outputFolder;
@@ -480,7 +490,7 @@ struct ShellStepInputs { // the arguments of Advance_One_Step_IE_Discrete_Shell 
 
 // Advance_One_Step_IE_Discrete_Shell<double, 3, KL=false, elasticIPC=false, flow> (IMPLICIT_EULER.h:151-891).
 // Unsupported inputs are rejected like the contact path rejects them (message + exit(-1)): segments, rods, particles, tets,
-// stitches, friction, strain limiting, fibers, static solves.
+// stitches, per-component friction coefficients, strain limiting, fibers, static solves.
 inline int advance_one_step_ie(ContactBackend& be, const ShellStepInputs& in, TriStorage& Elem, const std::vector<Vec<int, 2>>& seg, DbcStorage& DBC,
     const std::vector<Vec<int, 4>>& edgeStencil, const std::vector<Vec<double, 3>>& edgeInfo, const Vec<double, 4>& fiberStiffMult,
     const Vec<double, 2>& kappa_s, const std::vector<double>& b, Vec<double, 3>& kappaVec, NodeStorage& X, NodeAttrStorage& nodeAttr, CsrMatrix& M,
@@ -489,9 +499,9 @@ inline int advance_one_step_ie(ContactBackend& be, const ShellStepInputs& in, Tr
     const bool flow = in.flow, withCollision = in.withCollision;
     const double h = in.h, thickness = in.thickness, dHat2 = in.dHat2, NewtonTol = in.NewtonTol;
     const std::string& outputFolder = in.outputFolder;
-    if (!seg.empty() || in.nTet || in.nRod || in.nStitch || in.nParticle || in.mu > 0 || kappa_s[0] > 0 || fiberStiffMult[0] > 0 || fiberStiffMult[1] > 0 ||
-        in.staticSolve) {
-        printf("Advance_One_Step_IE (%s): segments / rods / particles / tets / stitches / friction / strain limiting / fibers / static "
+    if (!seg.empty() || in.nTet || in.nRod || in.nStitch || in.nParticle || in.muPerComponent || kappa_s[0] > 0 || fiberStiffMult[0] > 0 ||
+        fiberStiffMult[1] > 0 || in.staticSolve) {
+        printf("Advance_One_Step_IE (%s): segments / rods / particles / tets / stitches / per-component friction / strain limiting / fibers / static "
                "solves are outside the device-resident shell step\n", be.name());
         exit(-1);
     }
@@ -610,28 +620,15 @@ inline int advance_one_step_ie(ContactBackend& be, const ShellStepInputs& in, Tr
     auto total_energy = [&]() { // Compute_IncPotential (+ Compute_DBC_Energy) at the backend's current positions
         double E = pot.energy(s.x, s.xtilde);
         if (withCollision) be.barrier_energy(dHat2, kappa[0], thickness, E);
+        if (pot.friction) be.friction_energy(E);
         pot.add_dbc_energy(s.x, E);
         return E;
     };
-
-    int PNIter = 0;
-    double L2Norm = 0;
-    bool useGD = false;
-    std::vector<int> rowsPrev;
-    std::vector<double> infoPrev, dist2Prev;
-    printf("computing initial energy\n");
-    be.set_positions(s.x.data());
-    if (withCollision) s.nRows = be.constraint_set(dHat2, thickness);
-    s.Eprev = total_energy();
-    printf("entering Newton loop\n");
-    std::deque<double> resRecord, MDBCProgress;
-    s.rhs.resize(n3);
-    s.sol.resize(n3);
-    const int nFree = nV - DBC.size();
-    do {
-        // gradient (:459-491)
+    // gradient of the same potential with the Dirichlet handling of :459-482, rhs = -g
+    auto gradient_and_rhs = [&]() {
         pot.gradient(s.x, s.xtilde, s.g);
         if (withCollision) be.barrier_gradient(dHat2, kappa[0], thickness, s.g.data());
+        if (pot.friction) be.friction_gradient(s.g.data());
         if (pot.DBCStiff) {
             for (const auto& r : DBC.rows) {
                 const Vec<double, 4>& dI = std::get<0>(r);
@@ -648,6 +645,31 @@ inline int advance_one_step_ie(ContactBackend& be, const ShellStepInputs& in, Tr
             std::cout << "project rhs for Dirichlet boundary condition " << DBC.size() << std::endl;
         }
         for (size_t i = 0; i < n3; ++i) s.rhs[i] = -s.g[i];
+    };
+
+    int PNIter = 0;
+    double L2Norm = 0;
+    bool useGD = false;
+    std::vector<int> rowsPrev;
+    std::vector<double> infoPrev, dist2Prev;
+    printf("computing initial energy\n");
+    be.set_positions(s.x.data());
+    if (withCollision) s.nRows = be.constraint_set(dHat2, thickness);
+    pot.friction = withCollision && in.mu > 0;
+    if (pot.friction) { // lagged friction: basis and normal forces from the state the step starts in (:432-439)
+        be.friction_set(xn.data(), in.epsv2 * h * h, in.mu);
+        be.friction_update(dHat2, kappa[0], thickness);
+    }
+    else be.friction_set(nullptr, 0.0, 0.0);
+    s.rhs.resize(n3);
+    s.sol.resize(n3);
+    s.Eprev = total_energy();
+    printf("entering Newton loop\n");
+    std::deque<double> resRecord, MDBCProgress;
+    int fricIterI = 0;
+    const int nFree = nV - DBC.size();
+    do {
+        gradient_and_rhs(); // :459-491
 
         // Hessian + search direction (:493-556)
         if (useGD) {
@@ -748,6 +770,25 @@ inline int advance_one_step_ie(ContactBackend& be, const ShellStepInputs& in, Tr
                 set_penalty_terms();
                 s.Eprev = total_energy();
                 printf("DBC moved to target, turn off Augmented Lagrangian\n");
+            }
+        }
+
+        // converged with the lagged friction forces: refresh them and check the residual again (:762-848)
+        if (resRecord.size() == 3 && L2Norm <= NewtonTol) {
+            ++fricIterI;
+            if ((fricIterI < in.fricIterAmt || in.fricIterAmt <= 0) && pot.friction) {
+                be.friction_update(dHat2, kappa[0], thickness);
+                gradient_and_rhs();
+                if (!be.solve_newton_system(dHat2, kappa[0], thickness, pot.DBCStiff ? &dbcFixed : nullptr, s.rhs.data(), s.sol.data())) {
+                    FILE* fo = fopen((outputFolder + "/Hessian_info.txt").c_str(), "a+");
+                    if (fo) { fprintf(fo, "Hessian not SPD in PNIter%d\n", PNIter); fclose(fo); }
+                    exit(-1);
+                }
+                L2Norm = 0.0;
+                for (size_t i = 0; i < n3; ++i) L2Norm += s.sol[i] * s.sol[i];
+                L2Norm = std::sqrt(L2Norm / nFree) / h;
+                printf("friction updated Newton res = %le, tol = %le\n", L2Norm, NewtonTol);
+                if (L2Norm > NewtonTol) s.Eprev = total_energy();
             }
         }
 

@@ -74,6 +74,21 @@ def main():
         out[mesh + "/counter"] = counter
         out[mesh + "/V_end"] = Vend
         print(mesh, "steps", len(counter), "PN iterations", counter[:, 0].sum(), "last contact #", counter[-1, 1])
+    # friction (mu = 0.3, two friction iterations): the paper scripts leave sim.mu at 0, so this case is driven by the repository's own
+    # caller (tests/jgsl_driver/normal_flow.py, the same module calls with mu / fricIterAmt passed through) on the same checker build
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from jgsl_common import REFLOOPS_DIR, read_counter, run_own_driver, write_obj
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        obj = os.path.join(tmp, "hand.obj")
+        write_obj(obj, out["hand/V"], out["hand/F"])
+        rc, log = run_own_driver(REFLOOPS_DIR, obj, "0.5", "5e-3", "3", os.path.join(tmp, "out"), mu=0.3, fric_iter=2)
+        assert rc == 0, open(log).read()[-2000:]
+        out["hand_friction/args"] = np.array(["0.5", "5e-3", "3", "0.3", "2"])
+        out["hand_friction/counter"] = read_counter(os.path.join(tmp, "out", "counter.txt"))
+        out["hand_friction/V_end"] = read_obj(os.path.join(tmp, "out", "shell3.obj"))[0]
+        out["hand_friction/friction_updates"] = np.array(open(log).read().count("friction updated Newton res"))
+        print("hand with friction", out["hand_friction/counter"].tolist(), "friction updates", int(out["hand_friction/friction_updates"]))
     np.savez_compressed(os.path.join(HERE, "normal_flow_trace.npz"), **out)
 
 

@@ -25,6 +25,9 @@ void orc_membrane_batch(int nElem, const int* elem3, const double* X, const doub
     const unsigned char* dbc, int projectSPD, double* E, double* g3nV, double* H81, unsigned char* active);
 void orc_hinge_batch(int nHinge, const int* stencil4, const double* X, const double* info3, double kh2, const unsigned char* dbc, int projectSPD,
     double* E, double* g3nV, double* H144, unsigned char* active);
+long refipc_friction(int nV, const double* xb, const double* x, const double* xn, int n, const int* rows4, const double* w, double dHat2, double kappa,
+    double thickness, double epsvh2, double mu, int projectSPD, int* nFric, int* fricRows4, double* closest2, double* basis6, double* normalForce,
+    double* E, double* g, long cap, int* trow, int* tcol, double* tval);
 long ref_csr_system(int n, long nT, const int* r, const int* c, const double* v, const double* mdiag, const unsigned char* dbc, int dim,
     int* ptr, int* col, double* val, long cap);
 }
@@ -166,6 +169,12 @@ public:
             tr.insert(tr.end(), br.begin(), br.begin() + nt); tc.insert(tc.end(), bc.begin(), bc.begin() + nt);
             tv.insert(tv.end(), bv.begin(), bv.begin() + nt);
         }
+        if (fMu_ > 0 && !fRows_.empty()) { // friction Hessian (INC_POTENTIAL.h:375-377)
+            std::vector<int> fr, fc;
+            std::vector<double> fv;
+            friction_call(nullptr, nullptr, &fr, &fc, &fv);
+            tr.insert(tr.end(), fr.begin(), fr.end()); tc.insert(tc.end(), fc.begin(), fc.end()); tv.insert(tv.end(), fv.begin(), fv.end());
+        }
         const int n = 3 * nV_;
         std::vector<double> md((size_t)n);
         for (int v = 0; v < nV_; ++v) md[3 * v] = md[3 * v + 1] = md[3 * v + 2] = mass_[v];
@@ -217,6 +226,36 @@ public:
         printf("linear solve (host PCG): %d iterations, relative residual %le\n", it, std::sqrt(rr / bnorm));
         return true;
     }
+    // the reference's own FEM/FRICTION.h: the basis is recomputed from the frozen state on every call (same values)
+    long friction_update(double dHat2, double kappa, double thickness) override
+    {
+        fRows_ = rows_; fInfo_ = info_; fXb_ = x_; fDHat2_ = dHat2; fKappa_ = kappa; fXi_ = thickness;
+        return friction_call(nullptr, nullptr, nullptr, nullptr, nullptr);
+    }
+    void friction_set(const double* xn, double epsv2h2, double mu) override
+    {
+        fMu_ = mu; fEps_ = epsv2h2;
+        if (xn) fXn_.assign(xn, xn + 3 * (size_t)nV_);
+    }
+    long friction_call(double* E, double* g, std::vector<int>* tr, std::vector<int>* tc, std::vector<double>* tv)
+    {
+        const int n = (int)fRows_.size() / 4;
+        if (!n) return 0;
+        std::vector<double> w((size_t)n);
+        for (int i = 0; i < n; ++i) w[i] = fInfo_[2 * i];
+        std::vector<int> fr(4 * (size_t)n);
+        std::vector<double> cp(2 * (size_t)n), bs(6 * (size_t)n), lam((size_t)n);
+        int nf = 0;
+        const bool ev = (E || g || tr) && fMu_ > 0;
+        const long cap = tr ? 144 * (long)n : 0;
+        if (tr) { tr->resize((size_t)cap); tc->resize((size_t)cap); tv->resize((size_t)cap); }
+        const long nt = refipc_friction(nV_, fXb_.data(), ev ? x_.data() : nullptr, ev ? fXn_.data() : nullptr, n, fRows_.data(), w.data(), fDHat2_, fKappa_, fXi_, fEps_,
+            fMu_, 1, &nf, fr.data(), cp.data(), bs.data(), lam.data(), E, g, cap, tr ? tr->data() : nullptr, tr ? tc->data() : nullptr, tr ? tv->data() : nullptr);
+        if (tr) { tr->resize((size_t)nt); tc->resize((size_t)nt); tv->resize((size_t)nt); }
+        return nf;
+    }
+    void friction_energy(double& E) override { if (fMu_ > 0) friction_call(&E, nullptr, nullptr, nullptr, nullptr); }
+    void friction_gradient(double* g) override { if (fMu_ > 0) friction_call(nullptr, g, nullptr, nullptr, nullptr); }
     double ccd(const double* dir, double thickness, double alpha) override
     {
         return refipc_ccd(nV_, x_.data(), (int)bnode_.size(), bnode_.data(), (int)bedge_.size() / 2, bedge_.data(), (int)btri_.size() / 3, btri_.data(),
@@ -246,6 +285,9 @@ private:
     std::vector<int> bnode_, bedge_, btri_, elem_, rows_, mElem_, hSt_;
     std::vector<double> mIB_, mCoef_, mLam_, mMu_, hInfo_;
     double hKh2_ = 0;
+    std::vector<int> fRows_;
+    std::vector<double> fInfo_, fXb_, fXn_;
+    double fDHat2_ = 0, fKappa_ = 0, fXi_ = 0, fMu_ = 0, fEps_ = 0;
     std::vector<uint8_t> dbc_;
     std::vector<double> x_, x0_, vol_, mass_, info_;
 };

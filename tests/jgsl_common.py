@@ -43,14 +43,14 @@ def read_counter(path):
     return np.array([[int(t) for t in l.split()] for l in open(path)], np.int64)
 
 
-def run_own_driver(module_dir, mesh_obj, smooth, mag, frames, out, threads="8", timeout=3000):
+def run_own_driver(module_dir, mesh_obj, smooth, mag, frames, out, threads="8", timeout=3000, mu=None, fric_iter=None):
     """tests/jgsl_driver/normal_flow.py in a fresh interpreter with `module_dir` first on the import path."""
     env = dict(os.environ, PYTHONPATH=module_dir, OMP_NUM_THREADS=threads)
     log = os.path.join(out, "log.txt")
     os.makedirs(out, exist_ok=True)
     with open(log, "w") as lf:
-        rc = subprocess.call([sys.executable, DRIVER, mesh_obj, str(smooth), str(mag), str(frames), out], env=env, stdout=lf, stderr=subprocess.STDOUT,
-                             timeout=timeout)
+        rc = subprocess.call([sys.executable, DRIVER, mesh_obj, str(smooth), str(mag), str(frames), out] + ([str(mu)] if mu is not None else []) + ([str(fric_iter)] if fric_iter is not None else []), env=env,
+                             stdout=lf, stderr=subprocess.STDOUT, timeout=timeout)
     return rc, log
 
 

@@ -4,7 +4,7 @@ Python/Drivers/FEMDiscreteShellBase.py:143-147,190-204,238-242,266-273,333-341,3
 same order with the same arguments, so the GPU box (where /root/reference does not exist) can drive the module without the
 reference's scripts. Where the mirror of the unchanged scripts is present the tests run those as well.
 
-usage: python normal_flow.py <mesh.obj> <smoothIntensity> <normalFlowMag> <frames> <output folder>
+usage: python normal_flow.py <mesh.obj> <smoothIntensity> <normalFlowMag> <frames> <output folder> [mu] [fricIterAmt]   (the drivers' sim.mu / sim.fricIterAmt, defaults 0 / 1)
 """
 import os
 import sys
@@ -12,7 +12,7 @@ import sys
 from JGSL import *  # noqa: F401,F403  (whichever build of the module is first on the import path)
 
 
-def run(mesh_path, smooth, mag, frames, out):
+def run(mesh_path, smooth, mag, frames, out, mu=0.0, fric_iter=1):
     os.makedirs(out, exist_ok=True)
     if not out.endswith("/"):
         out += "/"
@@ -47,7 +47,7 @@ def run(mesh_path, smooth, mag, frames, out):
         FEM.DiscreteShell.Update_Normal_Flow_Neumann(X, Elem, massMatrix, mag, bodyForce)
         total += FEM.DiscreteShell.Advance_One_Step_IE_Flow(
             Elem, segs, DBC, edge2tri, edgeStencil, edgeInfo, 0, 0, Vector4d(0, 0, 0, 0), Vector3d(0, 0, 0), Vector2d(1.01, 0), Vector2d(1, 1),
-            Vector2d(0, 0), bodyForce, dt, 1e-3, True, dHat2, kappa, 0, 1e-6, 1, compNodeRange, muComp, False, X, nodeAttr, massMatrix, elemAttr,
+            Vector2d(0, 0), bodyForce, dt, 1e-3, True, dHat2, kappa, mu, 1e-6, fric_iter, compNodeRange, muComp, False, X, nodeAttr, massMatrix, elemAttr,
             elasticity, tet, tetAttr, tetElasticity, rod, rodInfo, rodHinge, rodHingeInfo, stitchInfo, stitchRatio, 10, particle, out)
         print("Total PN iteration count: ", total, "\n")
         TIMER_FLUSH(f, frames, dt, dt)
@@ -58,4 +58,5 @@ def run(mesh_path, smooth, mag, frames, out):
 
 
 if __name__ == "__main__":
-    run(sys.argv[1], float(sys.argv[2]), float(sys.argv[3]), int(sys.argv[4]), sys.argv[5])
+    run(sys.argv[1], float(sys.argv[2]), float(sys.argv[3]), int(sys.argv[4]), sys.argv[5], float(sys.argv[6]) if len(sys.argv) > 6 else 0.0,
+        int(sys.argv[7]) if len(sys.argv) > 7 else 1)
