@@ -211,7 +211,7 @@ struct idp_ctx {
     idp::DBuf<double> surfTriArea, surfTriAreaH, surfNodeArea, surfNodeAreaC, surfEdgeArea, surfEdgeArea2;
     bool surfValid = false;
     // ---- PCG (idp_solve_pcg) ----
-    idp::DBuf<double> pcgX, pcgR, pcgZ, pcgP, pcgAp, pcgInvDiag, pcgScal;
+    idp::DBuf<double> pcgX, pcgR, pcgZ, pcgP, pcgP2, pcgAp, pcgInvDiag, pcgScal;
     // ---- CCD ----
     long ccd_iters = 0;
     long nCcdPT = 0, nCcdEE = 0;

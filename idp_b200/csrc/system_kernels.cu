@@ -5,6 +5,7 @@
 //   * Find_Surface_Primitives_And_Compute_Area  Utils/MESHIO.h:768-834 (std::map ordering contract, areas)
 // FP64 + int32; everything here is bound by HBM bandwidth (SpMV: 12 bytes per stored scalar).
 #include "ctx.cuh"
+#include <cooperative_groups.h>
 #include <cub/cub.cuh>
 
 namespace idp {
@@ -46,28 +47,34 @@ int project_dbc(idp_ctx* c, const unsigned char* host_mask)
 // Block-Jacobi PCG on the scalar CSR. The matrix comes from assemble_csr, so the three scalar rows of a vertex have the
 // same block columns (3 nb entries each, stored back to back): one warp takes a block row, streams the three value rows
 // and the column indices coalesced and gathers x.
-// Scalars (rho = r.z, p.Ap, r.r) never visit the host inside the loop: every kernel leaves per-block partial sums in a
-// fixed slot array and the consumer kernels add them up in slot order themselves (deterministic, no atomics, no extra
-// launches); the host reads the residual every IDP_PCG_CHECK iterations.
+// Scalars (rho = r.z, p.Ap, r.r) never visit the host inside the loop: every phase leaves per-block partial sums in a
+// fixed slot array and the consumers add them up in slot order themselves (deterministic, no atomics); the host reads the
+// iteration count and the residual once, after the solve.
 // ------------------------------------------------------------------------------------------------------------
 #define IDP_PCG_BLOCKS 1184 // 148 SMs x 8
 #define IDP_PCG_CHECK 10
 struct PcgScal { double part[3][IDP_PCG_BLOCKS]; }; // 0: p.Ap, 1: r.z (new), 2: r.r
-__device__ __forceinline__ double sum_partials(const double* __restrict__ p)
+// every thread of every block adds the same values in the same order (strided per-thread sums, xor-butterfly inside the warp,
+// the eight warp sums in warp order): identical result in all threads and blocks, no atomics
+__device__ __forceinline__ void sum_partials2(const double* __restrict__ p0, const double* __restrict__ p1, int n, double& s0, double& s1)
 {
-    // every thread of the block adds the same values in the same order: identical result in all threads and blocks
-    __shared__ double sred[256];
-    double s = 0;
-    for (int i = threadIdx.x; i < IDP_PCG_BLOCKS; i += blockDim.x) s += p[i];
-    sred[threadIdx.x] = s;
+    __shared__ double sred[2][8];
+    double a = 0, b = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { a += p0[i]; b += p1[i]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+    if ((threadIdx.x & 31) == 0) { sred[0][threadIdx.x >> 5] = a; sred[1][threadIdx.x >> 5] = b; }
     __syncthreads();
-    for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
-        if ((int)threadIdx.x < o) sred[threadIdx.x] += sred[threadIdx.x + o];
-        __syncthreads();
-    }
-    const double t = sred[0];
+    a = 0; b = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += sred[0][w]; b += sred[1][w]; }
     __syncthreads();
-    return t;
+    s0 = a; s1 = b;
+}
+__device__ __forceinline__ double sum_partials(const double* __restrict__ p, int n = IDP_PCG_BLOCKS)
+{
+    double a, b;
+    sum_partials2(p, p, n, a, b);
+    return a;
 }
 __device__ __forceinline__ void block_partial(double v, double* __restrict__ slot)
 {
@@ -109,7 +116,7 @@ __global__ void __launch_bounds__(256) k_pcg_inv_diag(const int* __restrict__ pt
         }
     }
 }
-// r = b (x0 = 0), z = M^-1 r, p = z; partial sums of r.z and r.r
+// r = b (x0 = 0), z = M^-1 r, p = 0; partial sums of r.z and r.r
 __global__ void __launch_bounds__(256) k_pcg_init(const double* __restrict__ b, const double* __restrict__ inv, int nV, double* __restrict__ x,
     double* __restrict__ r, double* __restrict__ z, double* __restrict__ p, PcgScal* __restrict__ sc)
 {
@@ -121,73 +128,103 @@ __global__ void __launch_bounds__(256) k_pcg_init(const double* __restrict__ b, 
         x[3 * v] = 0; x[3 * v + 1] = 0; x[3 * v + 2] = 0;
         r[3 * v] = r0; r[3 * v + 1] = r1; r[3 * v + 2] = r2;
         z[3 * v] = z0; z[3 * v + 1] = z1; z[3 * v + 2] = z2;
-        p[3 * v] = z0; p[3 * v + 1] = z1; p[3 * v + 2] = z2;
+        p[3 * v] = 0; p[3 * v + 1] = 0; p[3 * v + 2] = 0; // the first direction is formed as z + 0 * p by the iteration kernel
         rz += r0 * z0 + r1 * z1 + r2 * z2;
         rr += r0 * r0 + r1 * r1 + r2 * r2;
     }
     block_partial(rz, &sc->part[1][blockIdx.x]);
     block_partial(rr, &sc->part[2][blockIdx.x]);
 }
-// Ap = A p (one warp per block row) and the partial sums of p.Ap
-__global__ void __launch_bounds__(256) k_pcg_spmv(const int* __restrict__ ptr, const int* __restrict__ col, const double* __restrict__ val, int nV,
-    const double* __restrict__ p, double* __restrict__ Ap, PcgScal* __restrict__ sc)
-{
-    const int lane = threadIdx.x & 31;
-    double acc = 0;
-    for (int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < nV; v += (gridDim.x * blockDim.x) >> 5) {
-        double s[3] = {0, 0, 0};
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            const int p0 = ptr[3 * v + i], p1 = ptr[3 * v + i + 1];
-            for (int q = p0 + lane; q < p1; q += 32) s[i] += val[q] * __ldg(p + col[q]);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            s[0] += __shfl_xor_sync(0xffffffffu, s[0], o); s[1] += __shfl_xor_sync(0xffffffffu, s[1], o); s[2] += __shfl_xor_sync(0xffffffffu, s[2], o);
-        }
-        if (lane == 0) {
-            Ap[3 * v] = s[0]; Ap[3 * v + 1] = s[1]; Ap[3 * v + 2] = s[2];
-            acc += p[3 * v] * s[0] + p[3 * v + 1] * s[1] + p[3 * v + 2] * s[2];
-        }
-    }
-    block_partial(acc, &sc->part[0][blockIdx.x]);
-}
-// alpha = rho / p.Ap; x += alpha p; r -= alpha Ap; z = M^-1 r; partial sums of the new r.z and r.r (into `next`)
-__global__ void __launch_bounds__(256) k_pcg_update(const PcgScal* __restrict__ cur, PcgScal* __restrict__ next, const double* __restrict__ inv, int nV,
-    const double* __restrict__ p, const double* __restrict__ Ap, double* __restrict__ x, double* __restrict__ r, double* __restrict__ z)
-{
-    const double rho = sum_partials(cur->part[1]), pAp = sum_partials(cur->part[0]);
-    const double alpha = pAp != 0 ? rho / pAp : 0.0;
-    double rz = 0, rr = 0;
-    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < nV; v += gridDim.x * blockDim.x) {
-        double rv[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            x[3 * v + k] += alpha * p[3 * v + k];
-            rv[k] = r[3 * v + k] - alpha * Ap[3 * v + k];
-            r[3 * v + k] = rv[k];
-        }
-        const double* m = inv + 9 * (long)v;
-        const double z0 = m[0] * rv[0] + m[1] * rv[1] + m[2] * rv[2], z1 = m[3] * rv[0] + m[4] * rv[1] + m[5] * rv[2], z2 = m[6] * rv[0] + m[7] * rv[1] + m[8] * rv[2];
-        z[3 * v] = z0; z[3 * v + 1] = z1; z[3 * v + 2] = z2;
-        rz += rv[0] * z0 + rv[1] * z1 + rv[2] * z2;
-        rr += rv[0] * rv[0] + rv[1] * rv[1] + rv[2] * rv[2];
-    }
-    block_partial(rz, &next->part[1][blockIdx.x]);
-    block_partial(rr, &next->part[2][blockIdx.x]);
-}
-// beta = rho_new / rho_old; p = z + beta p
-__global__ void __launch_bounds__(256) k_pcg_direction(const PcgScal* __restrict__ cur, const PcgScal* __restrict__ next, int n, const double* __restrict__ z,
-    double* __restrict__ p)
-{
-    const double rhoOld = sum_partials(cur->part[1]), rhoNew = sum_partials(next->part[1]);
-    const double beta = rhoOld != 0 ? rhoNew / rhoOld : 0.0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = z[i] + beta * p[i];
-}
 __global__ void __launch_bounds__(256) k_pcg_read_rr(const PcgScal* __restrict__ sc, double* __restrict__ out)
 {
     const double rr = sum_partials(sc->part[2]);
     if (threadIdx.x == 0) *out = rr;
+}
+
+// The whole iteration in ONE cooperative launch (one resident grid, three grid-wide barriers per iteration, convergence tested on
+// the device after every iteration). The first version launched three kernels per iteration and read the residual every ten
+// iterations: for the small systems of the paper examples (10^4 unknowns, ~250 iterations per Newton step) that was pure launch
+// latency -- 24 us per iteration, 75 % of the whole normal-flow run. Phases: (1) Ap = A p, one warp per block row streaming the
+// three value rows and the column indices coalesced, partial p.Ap; (2) alpha, x += alpha p, r -= alpha Ap, z = M^-1 r, partials of
+// r.z and r.r; the next direction p = z + beta p is formed inside phase (1) of the following iteration (two barriers per iteration, not three).
+// Partials per block, summed in slot order by every block (deterministic).
+struct PcgPersistentArgs {
+    const int* ptr; const int* col; const double* val; const double* inv; int nV;
+    double* x; double* r; double* z; double* p0; double* p1; double* Ap; PcgScal* sc;
+    double target; int maxIter; int* itersOut; double* rrOut;
+};
+__global__ void __launch_bounds__(256) k_pcg_persistent(PcgPersistentArgs a)
+{
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    const int nb = gridDim.x, lane = threadIdx.x & 31;
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+    int cur = 0;
+    double rho, rr;
+    sum_partials2(a.sc[0].part[1], a.sc[0].part[2], nb, rho, rr);
+    double beta = 0.0;           // p = z + beta p_old; the first direction is z itself (p_old = 0 from k_pcg_init)
+    double* po = a.p0; double* pn = a.p1;
+    int it = 0;
+    while (it < a.maxIter && rr > a.target) {
+        { // new direction and A p in one pass: the gathers form p[col] = z[col] + beta p_old[col] themselves (same fma as the owner's
+          // write), so no grid-wide barrier is needed between the direction update and the product
+            double acc = 0;
+            for (int v = gtid >> 5; v < a.nV; v += gsize >> 5) {
+                double s[3] = {0, 0, 0};
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const int q0 = a.ptr[3 * v + i], q1 = a.ptr[3 * v + i + 1];
+                    for (int q = q0 + lane; q < q1; q += 32) {
+                        const int cI = a.col[q];
+                        s[i] += a.val[q] * fma(beta, po[cI], a.z[cI]);
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    s[0] += __shfl_xor_sync(0xffffffffu, s[0], o); s[1] += __shfl_xor_sync(0xffffffffu, s[1], o); s[2] += __shfl_xor_sync(0xffffffffu, s[2], o);
+                }
+                if (lane == 0) {
+                    double pv[3];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) { pv[k] = fma(beta, po[3 * v + k], a.z[3 * v + k]); pn[3 * v + k] = pv[k]; a.Ap[3 * v + k] = s[k]; }
+                    acc += pv[0] * s[0] + pv[1] * s[1] + pv[2] * s[2];
+                }
+            }
+            block_partial(acc, &a.sc[cur].part[0][blockIdx.x]);
+        }
+        grid.sync();
+        { // x += alpha p; r -= alpha Ap; z = M^-1 r; partials of the new r.z and r.r
+            const double pAp = sum_partials(a.sc[cur].part[0], nb);
+            const double alpha = pAp != 0 ? rho / pAp : 0.0;
+            double rz = 0, r2 = 0;
+            for (int v = gtid; v < a.nV; v += gsize) {
+                double rv[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    a.x[3 * v + k] += alpha * pn[3 * v + k];
+                    rv[k] = a.r[3 * v + k] - alpha * a.Ap[3 * v + k];
+                    a.r[3 * v + k] = rv[k];
+                }
+                const double* m = a.inv + 9 * (long)v;
+                const double z0 = m[0] * rv[0] + m[1] * rv[1] + m[2] * rv[2], z1 = m[3] * rv[0] + m[4] * rv[1] + m[5] * rv[2], z2 = m[6] * rv[0] + m[7] * rv[1] + m[8] * rv[2];
+                a.z[3 * v] = z0; a.z[3 * v + 1] = z1; a.z[3 * v + 2] = z2;
+                rz += rv[0] * z0 + rv[1] * z1 + rv[2] * z2;
+                r2 += rv[0] * rv[0] + rv[1] * rv[1] + rv[2] * rv[2];
+            }
+            block_partial(rz, &a.sc[cur ^ 1].part[1][blockIdx.x]);
+            block_partial(r2, &a.sc[cur ^ 1].part[2][blockIdx.x]);
+        }
+        grid.sync();
+        double rhoNew;
+        sum_partials2(a.sc[cur ^ 1].part[1], a.sc[cur ^ 1].part[2], nb, rhoNew, rr);
+        beta = rho != 0 ? rhoNew / rho : 0.0;
+        rho = rhoNew;
+        double* t = po; po = pn; pn = t;
+        cur ^= 1;
+        ++it;
+        if (!(rr == rr)) break; // breakdown: reported by the host
+    }
+    if (gtid == 0) { *a.itersOut = it; *a.rrOut = rr; }
 }
 
 int solve_pcg(idp_ctx* c, const double* rhs, double* sol, double rel_tol, int max_iter, int* iters, double* rel_res)
@@ -196,34 +233,41 @@ int solve_pcg(idp_ctx* c, const double* rhs, double* sol, double rel_tol, int ma
     if (c->nnz <= 0) return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "idp_solve_pcg: no system matrix (call idp_barrier_hessian / idp_barrier_all first)", __FILE__, __LINE__);
     const int nV = c->nV;
     const size_t n = 3 * (size_t)nV;
-    IDP_CK(c, c->pcgX.reserve(n)); IDP_CK(c, c->pcgR.reserve(n)); IDP_CK(c, c->pcgZ.reserve(n)); IDP_CK(c, c->pcgP.reserve(n)); IDP_CK(c, c->pcgAp.reserve(n));
+    IDP_CK(c, c->pcgX.reserve(n)); IDP_CK(c, c->pcgR.reserve(n)); IDP_CK(c, c->pcgZ.reserve(n)); IDP_CK(c, c->pcgP.reserve(n)); IDP_CK(c, c->pcgP2.reserve(n)); IDP_CK(c, c->pcgAp.reserve(n));
     IDP_CK(c, c->pcgInvDiag.reserve(9 * (size_t)nV));
-    IDP_CK(c, c->pcgScal.reserve(2 * sizeof(PcgScal) / sizeof(double) + 8));
+    IDP_CK(c, c->pcgScal.reserve(2 * sizeof(PcgScal) / sizeof(double) + 8)); // + the (rr, iterations) read-back slots
     PcgScal* sc[2] = {(PcgScal*)c->pcgScal.p, (PcgScal*)c->pcgScal.p + 1};
     double* dRR = c->pcgScal.p + 2 * sizeof(PcgScal) / sizeof(double);
     // rhs: host -> pcgAp (scratch) -> r
     IDP_CK(c, cudaMemcpyAsync(c->pcgAp.p, rhs, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     IDP_CK(c, cudaMemsetAsync(c->pcgScal.p, 0, 2 * sizeof(PcgScal), c->stream));
     IDP_LAUNCH(c, k_pcg_inv_diag, blocks_for(nV, 256), 256, 0, c->csrPtr.p, c->csrCol.p, c->csrVal.p, nV, c->pcgInvDiag.p);
-    IDP_LAUNCH(c, k_pcg_init, IDP_PCG_BLOCKS, 256, 0, c->pcgAp.p, c->pcgInvDiag.p, nV, c->pcgX.p, c->pcgR.p, c->pcgZ.p, c->pcgP.p, sc[0]);
+    // one resident grid for the whole solve: as many blocks as the problem can use, at most what fits on the device at once
+    int perSm = 0;
+    IDP_CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_pcg_persistent, 256, 0));
+    // at least ~4 block rows per warp: a grid-wide barrier costs more the more blocks take part, and small systems are all latency
+    const int grid = std::max(1, std::min(std::min(perSm * c->sm_count, IDP_PCG_BLOCKS), (int)blocks_for(8L * nV, 256)));
+    IDP_LAUNCH(c, k_pcg_init, grid, 256, 0, c->pcgAp.p, c->pcgInvDiag.p, nV, c->pcgX.p, c->pcgR.p, c->pcgZ.p, c->pcgP.p, sc[0]);
     IDP_LAUNCH(c, k_pcg_read_rr, 1, 256, 0, sc[0], dRR);
     double rr0 = 0;
     IDP_CK(c, cudaMemcpyAsync(&rr0, dRR, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     IDP_CK(c, cudaStreamSynchronize(c->stream));
-    int it = 0, cur = 0;
+    int it = 0;
     double rr = rr0;
-    const double target = rel_tol * rel_tol * rr0;
-    while (it < max_iter && rr > target && rr0 > 0) {
-        const int burst = std::min(IDP_PCG_CHECK, max_iter - it);
-        for (int k = 0; k < burst; ++k, cur ^= 1) {
-            IDP_LAUNCH(c, k_pcg_spmv, IDP_PCG_BLOCKS, 256, 0, c->csrPtr.p, c->csrCol.p, c->csrVal.p, nV, c->pcgP.p, c->pcgAp.p, sc[cur]);
-            IDP_LAUNCH(c, k_pcg_update, IDP_PCG_BLOCKS, 256, 0, sc[cur], sc[cur ^ 1], c->pcgInvDiag.p, nV, c->pcgP.p, c->pcgAp.p, c->pcgX.p, c->pcgR.p, c->pcgZ.p);
-            IDP_LAUNCH(c, k_pcg_direction, IDP_PCG_BLOCKS, 256, 0, sc[cur], sc[cur ^ 1], (int)n, c->pcgZ.p, c->pcgP.p);
-        }
-        it += burst;
-        IDP_LAUNCH(c, k_pcg_read_rr, 1, 256, 0, sc[cur], dRR);
-        IDP_CK(c, cudaMemcpyAsync(&rr, dRR, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (rr0 > 0 && max_iter > 0) {
+        PcgPersistentArgs pa;
+        pa.ptr = c->csrPtr.p; pa.col = c->csrCol.p; pa.val = c->csrVal.p; pa.inv = c->pcgInvDiag.p; pa.nV = nV;
+        pa.x = c->pcgX.p; pa.r = c->pcgR.p; pa.z = c->pcgZ.p; pa.p0 = c->pcgP.p; pa.p1 = c->pcgP2.p; pa.Ap = c->pcgAp.p; pa.sc = sc[0];
+        pa.target = rel_tol * rel_tol * rr0; pa.maxIter = max_iter;
+        pa.itersOut = (int*)(dRR + 1); pa.rrOut = dRR;
+        void* kargs[] = {&pa};
+        IDP_CK(c, cudaLaunchCooperativeKernel((const void*)k_pcg_persistent, dim3(grid), dim3(256), kargs, 0, c->stream));
+        ++c->launches;
+        double out[2] = {0, 0};
+        IDP_CK(c, cudaMemcpyAsync(out, dRR, sizeof(out), cudaMemcpyDeviceToHost, c->stream));
         IDP_CK(c, cudaStreamSynchronize(c->stream));
+        rr = out[0];
+        std::memcpy(&it, &out[1], sizeof(int));
         if (!(rr == rr)) return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "idp_solve_pcg: the iteration broke down (matrix not positive definite?)", __FILE__, __LINE__);
     }
     IDP_CK(c, cudaGetLastError());
