@@ -469,3 +469,52 @@ def test_hessian_assembly_bucket_sizes(lib_built, orc):
     assert np.array_equal(ptr, optr) and np.array_equal(col, ocol)
     assert rel(val, oval) <= RTOL and np.abs(val - oval).max() <= RTOL * np.abs(oval).max()
     c.close()
+
+
+def test_config2_geometry_matches_reference_loops(lib_built, orc):
+    """BASELINE configs[1] geometry (wm2_15k, 12,811 vertices / 25,472 triangles, dHat = 1e-2; tests/golden/fix_char_seq_trace.npz): the
+    contact-rich, intersection-free state the animation-fix example reaches after six frames of Rumba_Dancing_unfixed (46.7 K rows),
+    search direction = towards the (self-intersecting) target frame. The hot-path operators on the paper's own mesh against the
+    reference's loops (oracle/_ref) where that build exists, else against the oracle: constraint set bit-exact, E / g 1e-10,
+    min-dist bit-exact, CCD conservative and within 1e-6."""
+    import os
+    from idp_b200 import ContactContext, meshgen
+    from oracle import ref_binding
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fix_char_seq_trace.npz")
+    if not os.path.exists(path):
+        pytest.skip("fix_char_seq fixture absent")
+    z = np.load(path)
+    F = z["rest/F"]
+    X, Xnext = z["V_end"], z["frame6/V"]
+    m = meshgen.SurfaceMesh(X, F, X0=z["frame6/V"])
+    dh2 = 1e-4
+    c = ContactContext(0)
+    try:
+        c.set_surface_mesh(m)
+        n = c.constraint_set(dh2)
+        rows, info = c.get_constraints()
+        assert n > 10000
+        if ref_binding.ipc_available():
+            ref = ref_binding.ReferenceIPC()
+            rrows, rinfo = ref.constraint_set(m, dh2)
+            rE, rg, _ = ref.barrier(m, rows, info[:, 0], dh2, KAPPA, want_h=False)
+            rd, rmin = ref.min_dist2(m, rows)
+            ralpha = ref.ccd(m, Xnext - X, 1.0)
+        else:
+            om = orc.mesh(m.X, m.X0, m.bnode, m.bedge, m.btri, m.dbc)
+            rrows, rinfo, _, _ = orc.constraint_set(om, dh2)
+            _, rE = orc.barrier(om, rows, info[:, 0], dh2, KAPPA)
+            rg = orc.barrier_gradient(om, rows, info[:, 0], dh2, KAPPA)[1]
+            rd, rmin = orc.min_dist2(om, rows)
+            ralpha = orc.ccd(om, Xnext - X, 1.0)["step"]
+        assert n == len(rrows) and np.array_equal(lexsorted(rows), lexsorted(rrows))
+        E = c.barrier_energy(dh2, KAPPA)
+        g = c.barrier_gradient(dh2, KAPPA)
+        assert abs(E - rE) <= RTOL * abs(rE)
+        assert np.abs(g - rg).max() <= RTOL * np.abs(rg).max()
+        d, mn = c.min_dist2()
+        assert np.array_equal(d, rd) and mn == rmin
+        alpha = c.ccd_step(Xnext - X, 1.0)
+        assert alpha <= ralpha and abs(alpha - ralpha) <= 1e-6 * ralpha, (alpha, ralpha)
+    finally:
+        c.close()
