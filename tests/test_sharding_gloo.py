@@ -21,7 +21,7 @@ def _worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from idp_b200.sharding import row_owner, shard_range
+    from sharding_np import row_owner, shard_range
     from oracle.binding import Oracle
     orc = Oracle()
     name, m, d, dhats = make_cases()[1]
@@ -70,7 +70,7 @@ def test_sharded_reductions_world2():
 
 
 def test_row_owner_decodes_every_row_kind():
-    from idp_b200.sharding import owner_shift, row_owner, row_vertices
+    from sharding_np import owner_shift, row_owner, row_vertices
     rows = np.array([[5, 6, 7, 8], [5, 6, -8, 9], [5, 7, 8, -10], [5, 7, -9, -10],
                      [-4, 10, 11, 12], [-4, 10, 11, -2], [-4, 10, -1, -3]], np.int32)
     v = row_vertices(rows)
@@ -81,7 +81,7 @@ def test_row_owner_decodes_every_row_kind():
 
 
 def test_shard_range_tiles_exactly():
-    from idp_b200.sharding import shard_range
+    from sharding_np import shard_range
     for n in (0, 1, 7, 1000, 2008008, 6000011):
         for P in (1, 2, 3, 4, 8):
             edges = [shard_range(n, r, P) for r in range(P)]
