@@ -170,14 +170,23 @@ __global__ void __launch_bounds__(256) k_pcg_persistent(PcgPersistentArgs a)
           // write), so no grid-wide barrier is needed between the direction update and the product
             double acc = 0;
             for (int v = gtid >> 5; v < a.nV; v += gsize >> 5) {
+                // the three scalar rows of a block row have the same columns (assemble_csr stores them back to back, 3 nb entries
+                // each): one column load and one gathered direction value serve all three rows
                 double s[3] = {0, 0, 0};
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    const int q0 = a.ptr[3 * v + i], q1 = a.ptr[3 * v + i + 1];
-                    for (int q = q0 + lane; q < q1; q += 32) {
-                        const int cI = a.col[q];
-                        s[i] += a.val[q] * fma(beta, po[cI], a.z[cI]);
-                    }
+                const int q0 = a.ptr[3 * v], len = a.ptr[3 * v + 1] - q0;
+                const double* v0 = a.val + q0; const double* v1 = v0 + len; const double* v2 = v1 + len;
+                int k = lane;
+                for (; k + 32 < len; k += 64) { // two entries per lane and trip: eight independent loads in flight before the first use
+                    const int cA = a.col[q0 + k], cB = a.col[q0 + k + 32];
+                    const double a0 = v0[k], a1 = v1[k], a2 = v2[k], b0 = v0[k + 32], b1 = v1[k + 32], b2 = v2[k + 32];
+                    const double pA = fma(beta, po[cA], a.z[cA]), pB = fma(beta, po[cB], a.z[cB]);
+                    s[0] += a0 * pA; s[1] += a1 * pA; s[2] += a2 * pA;
+                    s[0] += b0 * pB; s[1] += b1 * pB; s[2] += b2 * pB;
+                }
+                if (k < len) {
+                    const int cI = a.col[q0 + k];
+                    const double pv = fma(beta, po[cI], a.z[cI]);
+                    s[0] += v0[k] * pv; s[1] += v1[k] * pv; s[2] += v2[k] * pv;
                 }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
