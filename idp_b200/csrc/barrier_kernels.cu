@@ -777,41 +777,44 @@ __global__ void k_csr_ptr(const int* __restrict__ rowStart, int nV, int* __restr
         ptr[3 * (long)v + 2] = 9 * s + 6 * nb;
     }
 }
-// upper (and diagonal) blocks: one thread per (unique block, component)
-__global__ void __launch_bounds__(288) k_write_upper(const double* __restrict__ uVal, const int* __restrict__ usrc, const int* __restrict__ urow,
-    const int* __restrict__ ucol, int nSeg, const int* __restrict__ vtxBlkStart, const int* __restrict__ rowStart, const int* __restrict__ lowerCount,
-    int* __restrict__ col, double* __restrict__ val)
+// One warp per block row writes its three scalar rows: entry k of a row is component b = k % 3 of block slot k / 3, the first
+// lowerCount[v] slots being the mirrored blocks (`order` lists the strictly-upper unique blocks stably sorted by their column
+// vertex, so the members of one block row appear with ascending row vertex = ascending column in the mirror; lstart[v] = first
+// entry of row v; stored transposed), the rest the diagonal + upper blocks in bucket order. Consecutive lanes write consecutive
+// positions of all three rows (the first version ran one thread per (block, component): 24-byte pieces scattered over the rows,
+// seven index loads per scalar).
+__global__ void __launch_bounds__(256) k_write_rows(const double* __restrict__ uVal, const int* __restrict__ usrc, const int* __restrict__ urow,
+    const int* __restrict__ ucol, const int* __restrict__ vtxBlkStart, const int* __restrict__ rowStart, const int* __restrict__ lowerCount,
+    const int* __restrict__ order, const int* __restrict__ lstart, int nV, int* __restrict__ col, double* __restrict__ val)
 {
-    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long seg = t / 9;
-    const int comp = (int)(t - seg * 9);
-    if (seg >= nSeg) return;
-    const int vi = urow[seg], vj = ucol[seg];
-    const int bs = rowStart[vi], nb = rowStart[vi + 1] - bs;
-    const int slot = lowerCount[vi] + (int)(seg - vtxBlkStart[vi]);
-    const int a = comp / 3, b = comp - 3 * a;
-    const long pos = 9L * bs + (long)a * 3 * nb + 3L * slot + b;
-    col[pos] = 3 * vj + b;
-    val[pos] = uVal[9L * usrc[seg] + comp];
-}
-// mirrored blocks: `order` lists the strictly-upper unique blocks stably sorted by their column vertex, so the members
-// of one block row appear with ascending row vertex = ascending column in the mirror. lstart[v] = first entry of row v.
-__global__ void __launch_bounds__(288) k_write_lower(const double* __restrict__ uVal, const int* __restrict__ usrc, const int* __restrict__ urow,
-    const int* __restrict__ order, const int* __restrict__ sortedCol, long nLower, const int* __restrict__ lstart, const int* __restrict__ rowStart,
-    int* __restrict__ col, double* __restrict__ val)
-{
-    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long e = t / 9;
-    const int comp = (int)(t - e * 9);
-    if (e >= nLower) return;
-    const int seg = order[e];
-    const int row = sortedCol[e], cv = urow[seg]; // mirror: row vertex = original column, column vertex = original row
-    const int bs = rowStart[row], nb = rowStart[row + 1] - bs;
-    const int slot = (int)(e - lstart[row]);
-    const int a = comp / 3, b = comp - 3 * a;
-    const long pos = 9L * bs + (long)a * 3 * nb + 3L * slot + b;
-    col[pos] = 3 * cv + b;
-    val[pos] = uVal[9L * usrc[seg] + 3 * b + a]; // transposed block
+    const int lane = threadIdx.x & 31;
+    for (int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < nV; v += (gridDim.x * blockDim.x) >> 5) {
+        const int bs = rowStart[v], nb = rowStart[v + 1] - bs, nl = lowerCount[v], ub = vtxBlkStart[v], le = lstart[v];
+        const long base = 9L * bs;
+        for (int k = lane; k < 3 * nb; k += 32) {
+            const int slot = k / 3, b = k - 3 * slot;
+            int cv;
+            const double* blk;
+            int s0, s1, s2; // offsets of component (a, b) for a = 0, 1, 2 inside the 9-value block
+            if (slot < nl) {
+                const int seg = order[le + slot];
+                cv = urow[seg];
+                blk = uVal + 9L * usrc[seg];
+                s0 = 3 * b; s1 = 3 * b + 1; s2 = 3 * b + 2; // transposed
+            }
+            else {
+                const int seg = ub + (slot - nl);
+                cv = ucol[seg];
+                blk = uVal + 9L * usrc[seg];
+                s0 = b; s1 = 3 + b; s2 = 6 + b;
+            }
+            const double x0 = blk[s0], x1 = blk[s1], x2 = blk[s2];
+            const int c3 = 3 * cv + b;
+            const long p0 = base + k, p1 = p0 + 3L * nb, p2 = p1 + 3L * nb;
+            col[p0] = c3; col[p1] = c3; col[p2] = c3;
+            val[p0] = x0; val[p1] = x1; val[p2] = x2;
+        }
+    }
 }
 __global__ void k_lower_keys(const int* __restrict__ urow, const int* __restrict__ ucol, int nSeg, int* __restrict__ keyOut, int* __restrict__ segOut)
 {
@@ -900,11 +903,8 @@ int assemble_csr(idp_ctx* c)
     IDP_LAUNCH(c, k_lower_starts, blocks_for(nV + 1, 256), 256, 0, c->lkeySorted.p, nLower, nV, c->lstart.p);
     IDP_LAUNCH(c, k_csr_ptr, blocks_for(nV + 1, 256), 256, 0, c->rowStart.p, nV, c->csrPtr.p);
     if (nSeg > 0)
-        IDP_LAUNCH(c, k_write_upper, blocks_for(9L * nSeg, 288), 288, 0, c->uVal.p, c->usrc.p, c->urow.p, c->ucol.p, nSeg, c->vtxBlkStart.p, c->rowStart.p,
-            c->lowerCount.p, c->csrCol.p, c->csrVal.p);
-    if (nLower > 0)
-        IDP_LAUNCH(c, k_write_lower, blocks_for(9L * nLower, 288), 288, 0, c->uVal.p, c->usrc.p, c->urow.p, c->lsegSorted.p, c->lkeySorted.p, nLower, c->lstart.p,
-            c->rowStart.p, c->csrCol.p, c->csrVal.p);
+        IDP_LAUNCH(c, k_write_rows, std::min(blocks_for(32L * nV, 256), (unsigned)c->sm_count * 32), 256, 0, c->uVal.p, c->usrc.p, c->urow.p, c->ucol.p, c->vtxBlkStart.p,
+            c->rowStart.p, c->lowerCount.p, c->lsegSorted.p, c->lstart.p, nV, c->csrCol.p, c->csrVal.p);
     IDP_CK(c, cudaGetLastError());
     IDP_CK(c, cudaStreamSynchronize(c->stream));
     return IDP_OK;
