@@ -233,6 +233,29 @@ class Oracle:
         x12 = _f64(x12)
         return self.lib.orc_dihedral_angle(_p(x12))
 
+    def friction(self, Xb, rows, dHat2, kappa, X=None, Xn=None, epsv2_h2=1e-6, mu=0.3, thickness=0.0, project_spd=True, weights=None):
+        """Lagged friction (orc_friction.hpp; FEM/FRICTION.h): basis at Xb, then E / g / triplets at X relative to Xn. Same
+        return layout as oracle.ref_binding.ReferenceIPC.friction."""
+        L = self.lib
+        L.orc_friction.restype = C.c_long
+        L.orc_friction.argtypes = ([C.c_int] + [C.c_void_p] * 3 + [C.c_long, C.c_void_p, C.c_void_p] + [C.c_double] * 5 + [C.c_int] + [C.c_void_p] * 7 +
+                                   [C.c_long] + [C.c_void_p] * 3)
+        Xb = _f64(Xb).reshape(-1, 3); rows = _i32(rows).reshape(-1, 4)
+        n = len(rows)
+        w = np.ones(n) if weights is None else _f64(weights)
+        nf = C.c_int(0)
+        frows = np.zeros((n, 4), np.int32); cp = np.zeros((n, 2)); basis = np.zeros((n, 6)); lam = np.zeros(n)
+        E = C.c_double(0.0); g = np.zeros_like(Xb)
+        ev = X is not None
+        if ev:
+            X = _f64(X).reshape(-1, 3); Xn = _f64(Xn).reshape(-1, 3)
+        cap = 144 * n + 1
+        tr = np.zeros(cap, np.int32); tc = np.zeros(cap, np.int32); tv = np.zeros(cap)
+        nt = L.orc_friction(len(Xb), _p(Xb), _p(X) if ev else None, _p(Xn) if ev else None, n, _p(rows), _p(w), dHat2, kappa, thickness, epsv2_h2, mu,
+                            int(project_spd), C.byref(nf), _p(frows), _p(cp), _p(basis), _p(lam), C.byref(E), _p(g), cap, _p(tr), _p(tc), _p(tv))
+        k = nf.value
+        return dict(rows=frows[:k], closest=cp[:k], basis=basis[:k], normal_force=lam[:k], E=E.value, g=g, triplets=(tr[:nt], tc[:nt], tv[:nt]))
+
     def row_EgH(self, mesh, row, weight, dHat2, kappa, thickness=0.0, project_spd=True):
         m, _keep = mesh
         row = _i32(row)

@@ -3,6 +3,7 @@
 #include "orc_ipc.hpp"
 #include "orc_system.hpp"
 #include "orc_elastic.hpp"
+#include "orc_friction.hpp"
 #include <chrono>
 
 using namespace orc;
@@ -132,6 +133,32 @@ void orc_hinge_batch(int nHinge, const int* stencil4, const double* X, const dou
                     for (int d = 0; d < 3; ++d) g3nV[3 * stencil4[4 * e + k] + d] += ge[12 * (size_t)e + 3 * k + d];
 }
 double orc_dihedral_angle(const double* x12) { return dihedral_angle(ld3(x12), ld3(x12 + 3), ld3(x12 + 6), ld3(x12 + 9)); }
+
+// ---- lagged friction (orc_friction.hpp) ---------------------------------------------------------------------------
+// basis at Xb from the contact rows (outputs like the reference's containers: rows, closest (2), basis (3x2 column major), normal
+// force), then E (added) / g (added) / triplets at X relative to Xn when X is given. Returns the triplet count (<= cap written).
+long orc_friction(int nV, const double* Xb, const double* X, const double* Xn, long n, const int* rows4, const double* weight, double dHat2, double kappa,
+    double thickness, double epsvh2, double mu, int projectSPD, int* nFric, int* fricRows4, double* closest2, double* basis6, double* normalForce,
+    double* E, double* g, long cap, int* tr, int* tc, double* tv)
+{
+    (void)nV;
+    std::vector<FrictionRow> fr;
+    friction_basis(Xb, to_rows(n, rows4), weight, dHat2, kappa, thickness, fr);
+    *nFric = (int)fr.size();
+    for (size_t i = 0; i < fr.size(); ++i) {
+        for (int k = 0; k < 4; ++k) fricRows4[4 * i + k] = fr[i].row[k];
+        closest2[2 * i] = fr[i].cp[0]; closest2[2 * i + 1] = fr[i].cp[1];
+        basis6[6 * i] = fr[i].t0.x; basis6[6 * i + 1] = fr[i].t0.y; basis6[6 * i + 2] = fr[i].t0.z;
+        basis6[6 * i + 3] = fr[i].t1.x; basis6[6 * i + 4] = fr[i].t1.y; basis6[6 * i + 5] = fr[i].t1.z;
+        normalForce[i] = fr[i].lam;
+    }
+    if (!X) return 0;
+    Triplets T;
+    friction_eval(X, Xn, fr, epsvh2, mu, projectSPD != 0, E, g, tr ? &T : nullptr);
+    const long nt = (long)T.v.size();
+    for (long i = 0; i < nt && i < cap; ++i) { tr[i] = T.r[i]; tc[i] = T.c[i]; tv[i] = T.v[i]; }
+    return nt;
+}
 
 // ---- system matrix around the barrier Hessian (orc_system.hpp) -------------------------------------------------
 // triplets = [flow term][barrier rows] -> Construct_From_Triplet -> += M -> Project_DBC (INC_POTENTIAL.h:321-394)

@@ -1,7 +1,8 @@
 """Lagged friction: the product's device header idp_b200/csrc/friction.cuh compiled for the host (CPU
 test) and the CUDA path through the C ABI (GPU test) against the REFERENCE's own FEM/FRICTION.h compiled in
-oracle/_ref/libidp_ref_ipc.so (Compute_Friction_Basis / _Potential / _Gradient / _Hessian). Bars: friction rows identical,
-closest points / bases / normal forces / E / g / H within 1e-10 relative."""
+oracle/_ref/libidp_ref_ipc.so (Compute_Friction_Basis / _Potential / _Gradient / _Hessian) -- or, where that build is absent,
+against the oracle restatement oracle/orc_friction.hpp, which is itself pinned by the reference build here. Bars: friction rows
+identical, closest points / bases / normal forces / E / g / H within 1e-10 relative."""
 import ctypes as C
 import os
 import subprocess
@@ -18,8 +19,13 @@ from conftest import make_cases  # noqa: E402
 from oracle import ref_binding  # noqa: E402
 
 KAPPA, MU, EPSV2H2 = 1e5, 0.4, 1e-4 * 0.01 ** 2 * 25.0
-needs_ref = pytest.mark.skipif(not (ref_binding.ipc_available() and hasattr(C.CDLL(ref_binding.LIB_IPC), "refipc_friction")),
-                               reason="oracle/_ref with the reference's FRICTION.h is not built (needs /root/reference)")
+HAVE_REF = ref_binding.ipc_available() and hasattr(C.CDLL(ref_binding.LIB_IPC), "refipc_friction")
+needs_ref = pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref with the reference's FRICTION.h is not built (needs /root/reference)")
+
+
+def _checker(orc):
+    """the reference's own friction code where it is built, else its restatement"""
+    return ref_binding.ReferenceIPC() if HAVE_REF else orc
 
 
 def _p(a):
@@ -42,13 +48,32 @@ def _scene(orc, case, k):
 
 
 @needs_ref
+def test_oracle_friction_matches_reference(orc):
+    """oracle/orc_friction.hpp against the reference's FRICTION.h: rows and normal forces bit for bit, the rest 1e-12."""
+    ref = ref_binding.ReferenceIPC()
+    for k, case in enumerate(make_cases()):
+        m, rows, dh2, Xn, X = _scene(orc, case, k)
+        r = ref.friction(m.X, rows, dh2, KAPPA, X=X, Xn=Xn, epsv2_h2=EPSV2H2, mu=MU)
+        o = orc.friction(m.X, rows, dh2, KAPPA, X=X, Xn=Xn, epsv2_h2=EPSV2H2, mu=MU)
+        assert np.array_equal(o["rows"], r["rows"]) and np.array_equal(o["normal_force"], r["normal_force"])
+        four = (r["rows"][:, 0] >= 0) | (r["rows"][:, 3] >= 0)                         # EE / PT: two parameters
+        pe = (r["rows"][:, 0] < 0) & (r["rows"][:, 2] >= 0) & (r["rows"][:, 3] < 0)        # PE: one (the reference leaves the other unset)
+        assert np.array_equal(o["closest"][four], r["closest"][four]) and np.array_equal(o["closest"][pe, 0], r["closest"][pe, 0])
+        assert np.allclose(o["basis"], r["basis"], rtol=0, atol=1e-15)
+        assert abs(o["E"] - r["E"]) <= 1e-13 * abs(r["E"]) and np.abs(o["g"] - r["g"]).max() <= 1e-12 * np.abs(r["g"]).max()
+        n3 = 3 * len(X)
+        A = sp.coo_matrix((o["triplets"][2], (o["triplets"][0], o["triplets"][1])), shape=(n3, n3)).tocsr()
+        B = sp.coo_matrix((r["triplets"][2], (r["triplets"][0], r["triplets"][1])), shape=(n3, n3)).tocsr()
+        assert len(o["triplets"][2]) == len(r["triplets"][2]) and spla.norm(A - B) <= 1e-12 * spla.norm(B)
+
+
 def test_friction_header_on_host_matches_reference(orc):
     src = os.path.join(ROOT, "tests", "host_shim", "pair_host.cpp")
     out = os.path.join(ROOT, "tests", "host_shim", "libpair_host.so")
     subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", out, src])
     hs = C.CDLL(out)
     hs.hs_friction.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.c_double] * 5 + [C.c_void_p] * 9
-    ref = ref_binding.ReferenceIPC()
+    ref = _checker(orc)
     for k, case in enumerate(make_cases()):
         m, rows, dh2, Xn, X = _scene(orc, case, k)
         n = len(rows)
@@ -78,11 +103,10 @@ def test_friction_header_on_host_matches_reference(orc):
         assert spla.norm(B) > 0
 
 
-@needs_ref
 @pytest.mark.gpu
 def test_friction_on_the_device_matches_reference(lib_built, orc):
     from idp_b200 import ContactContext
-    ref = ref_binding.ReferenceIPC()
+    ref = _checker(orc)
     for k, case in enumerate(make_cases()):
         m, rows, dh2, Xn, X = _scene(orc, case, k)
         n3 = 3 * m.nV
