@@ -167,6 +167,12 @@ inline double initialize_shell_hinge(double rho0, double E, double nu, double th
     NodeAttrStorage& nodeAttr, CsrMatrix& M, const Vec<double, 3>& gravity, std::vector<double>& b, ElemAttrStorage& elemAttr,
     Fcr2Storage& elasticityAttr, Vec<double, 3>& kappa)
 {
+    for (const auto& r : Elem.rows)
+        for (int k = 0; k < 3; ++k)
+            if (std::get<0>(r)[k] < 0 || std::get<0>(r)[k] >= X.size()) { // e.g. the rest shape of the next frame could not be read
+                printf("Initialize_Shell: element vertex %d outside the %d nodes given (mesh file missing?)\n", std::get<0>(r)[k], X.size());
+                exit(-1);
+            }
     auto P = [&](int v) -> const Vec<double, 3>& { return std::get<0>(X.rows[v]); };
     TriStorage kept;
     for (const auto& r : Elem.rows) {
