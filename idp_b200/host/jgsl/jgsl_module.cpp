@@ -266,7 +266,19 @@ PYBIND11_MODULE(JGSL, m)
 
     py::module_ sh = fem.def_submodule("DiscreteShell", "discrete shell simulation hosted on the B200 contact path");
     sh.def("Add_Shell", &add_shell);
-    sh.def("Initialize_Shell_Hinge_EIPC", &initialize_shell_hinge);
+    auto init_hinge = [](bool eipc) {
+        return [eipc](double rho0, double E, double nu, double thickness, double h, double dHat2, NodeStorage& X, TriStorage& Elem, StdVectorVector2i& seg,
+                   EdgeToTri& edge2tri, StdVectorVector4i& edgeStencil, StdVectorVector3d& edgeInfo, NodeAttrStorage& nodeAttr, CsrMatrix& M,
+                   const Vec<double, 3>& gravity, StdVectorXd& b, ElemAttrStorage& elemAttr, Fcr2Storage& elasticityAttr, Vec<double, 3>& kappa) {
+            return initialize_shell_hinge(rho0, E, nu, thickness, h, dHat2, X, Elem, seg, edge2tri, edgeStencil, edgeInfo, nodeAttr, M, gravity, b, elemAttr,
+                elasticityAttr, kappa, eipc);
+        };
+    };
+    sh.def("Initialize_Shell_Hinge_EIPC", init_hinge(true));  // Initialize_Discrete_Shell<double, 3, KL=false, elasticIPC=true>
+    sh.def("Initialize_Shell_Hinge", init_hinge(false));      // ... elasticIPC=false
+    sh.def("Initialize_EIPC", &initialize_eipc, py::arg("E"), py::arg("nu"), py::arg("thickness"), py::arg("h"), py::arg("M"), py::arg("kappa"),
+        py::arg("stiffMult") = 1.0);
+    sh.def("Initialize_OIPC_VM", &initialize_oipc_vm, py::arg("dHat2"), py::arg("nodeAttr"), py::arg("kappa"), py::arg("stiffMult") = 1.0);
     sh.def("Initialize_OIPC", &initialize_oipc, py::arg("E"), py::arg("nu"), py::arg("thickness"), py::arg("h"), py::arg("M"), py::arg("kappa"),
         py::arg("stiffMult") = 1.0);
     sh.def("Update_Normal_Flow_Neumann", &update_normal_flow_neumann);
@@ -300,8 +312,8 @@ PYBIND11_MODULE(JGSL, m)
     sh.def("Advance_One_Step_IE_Flow", step(true));
     sh.def("Advance_One_Step_IE_Hinge", step(false));
     for (const char* n : {"Add_Garment", "Make_Rod", "Make_Rod_Net", "Add_Discrete_Particles", "Initialize_Shell", "Initialize_Garment",
-             "Initialize_Shell_Hinge", "Update_Material_With_Tex_Shell", "Initialize_Shell_EIPC", "Initialize_Discrete_Rod",
-             "Initialize_Discrete_Particle", "Initialize_EIPC", "Initialize_OIPC_VM", "Advance_One_Step_IE",
+             "Update_Material_With_Tex_Shell", "Initialize_Shell_EIPC", "Initialize_Discrete_Rod",
+             "Initialize_Discrete_Particle", "Advance_One_Step_IE",
              "Advance_One_Step_IE_EIPC", "Advance_One_Step_IE_Hinge_EIPC", "Advance_One_Step_SIE", "Advance_One_Step_SIE_Hinge",
              "Advance_One_Step_SIE_EIPC", "Advance_One_Step_SIE_Hinge_EIPC", "Construct_Surface_Mesh", "Compute_Stretch_From_File",
              "XZ_As_Texture", "Adjust_Material"})

@@ -165,7 +165,7 @@ inline double dihedral_angle(const Vec<double, 3>& v0, const Vec<double, 3>& v1,
 inline double initialize_shell_hinge(double rho0, double E, double nu, double thickness, double h, double dHat2, NodeStorage& X, TriStorage& Elem,
     std::vector<Vec<int, 2>>& seg, EdgeToTri& edge2tri, std::vector<Vec<int, 4>>& edgeStencil, std::vector<Vec<double, 3>>& edgeInfo,
     NodeAttrStorage& nodeAttr, CsrMatrix& M, const Vec<double, 3>& gravity, std::vector<double>& b, ElemAttrStorage& elemAttr,
-    Fcr2Storage& elasticityAttr, Vec<double, 3>& kappa)
+    Fcr2Storage& elasticityAttr, Vec<double, 3>& kappa, bool elasticIPC = true)
 {
     for (const auto& r : Elem.rows)
         for (int k = 0; k < 3; ++k)
@@ -272,8 +272,10 @@ inline double initialize_shell_hinge(double rho0, double E, double nu, double th
         k = E * std::pow(thickness, 3) / (24 * (1.0 - nu * nu));
         std::cout << "hinge k = " << k << std::endl;
     }
-    kappa[0] = h * h * mu; kappa[1] = h * h * lambda; kappa[2] = nu; // elasticIPC = true (:343-349)
-    dHat2 = thickness * thickness;
+    if (elasticIPC) { // :343-349; the non-EIPC instantiation leaves kappa and dHat2 alone
+        kappa[0] = h * h * mu; kappa[1] = h * h * lambda; kappa[2] = nu;
+        dHat2 = thickness * thickness;
+    }
     std::cout << "shell initialized" << std::endl;
     return dHat2;
 }
@@ -293,6 +295,27 @@ inline double initialize_oipc(double E, double nu, double thickness, double h, C
     const double dHat2 = thickness * thickness;
     const double Hb = barrier_hessian_scalar(1.0e-16, dHat2, 1.0);
     kappa[0] = stiffMult * 1.0e11 * M.diagonal_mean() * 3 / (4.0e-16 * Hb);
+    kappa[1] = 100 * kappa[0];
+    printf("original IPC kappa = %le\n", kappa[0]);
+    return dHat2;
+}
+
+// Initialize_EIPC<double, elasticIPC=true> (DISCRETE_SHELL.h:555-564; exported as Initialize_EIPC)
+inline double initialize_eipc(double E, double nu, double thickness, double h, CsrMatrix& M, Vec<double, 3>& kappa, double stiffMult)
+{
+    (void)M; (void)stiffMult;
+    const double lambda = E * nu / (1.0 - nu * nu), mu = E / (2.0 * (1.0 + nu));
+    kappa[0] = h * h * mu; kappa[1] = h * h * lambda; kappa[2] = nu;
+    return thickness * thickness;
+}
+
+// Initialize_OIPC_VecM (DISCRETE_SHELL.h:579-600; exported as Initialize_OIPC_VM): the kappa heuristic from the mean nodal mass
+inline double initialize_oipc_vm(double dHat2, NodeAttrStorage& nodeAttr, Vec<double, 3>& kappa, double stiffMult)
+{
+    double avg = 0;
+    for (const auto& r : nodeAttr.rows) avg += std::get<3>(r);
+    avg /= nodeAttr.size();
+    kappa[0] = stiffMult * 1.0e11 * avg / (4.0e-16 * barrier_hessian_scalar(1.0e-16, dHat2, 1.0));
     kappa[1] = 100 * kappa[0];
     printf("original IPC kappa = %le\n", kappa[0]);
     return dHat2;
