@@ -33,7 +33,7 @@ EXPORTS = ["idp_create", "idp_destroy", "idp_last_error", "idp_set_stream", "idp
            "idp_solve_pcg", "idp_set_mesh_from_triangles", "idp_get_surface_primitives", "idp_get_constraints_begin",
            "idp_get_hessian_csr_begin", "idp_transfers_end", "idp_system_set_membrane", "idp_system_set_hinges", "idp_elastic_energy",
            "idp_elastic_gradient", "idp_project_dbc_mask", "idp_friction_update", "idp_friction_set", "idp_friction_energy",
-           "idp_friction_gradient", "idp_get_friction"]
+           "idp_friction_gradient", "idp_get_friction", "idp_friction_set_components"]
 
 
 class IdpError(RuntimeError):
@@ -97,6 +97,7 @@ def load_library(path=LIB_PATH):
     L.idp_friction_update.argtypes = [vp, d, d, d, C.POINTER(l)]
     L.idp_friction_set.argtypes = [vp, vp, i, d, d]
     L.idp_friction_energy.argtypes = [vp, C.POINTER(d)]
+    L.idp_friction_set_components.argtypes = [vp, i, vp, vp]
     L.idp_friction_gradient.argtypes = [vp, vp, i]
     L.idp_get_friction.argtypes = [vp, C.POINTER(l), vp, vp, vp, vp]
     L.idp_system_set_membrane.argtypes = [vp, i, vp, i, vp, vp, vp, vp, d]
@@ -257,6 +258,13 @@ class ContactContext:
     def friction_set(self, Xn, epsv2_h2, mu):
         Xn = None if Xn is None else np.ascontiguousarray(Xn, np.float64)
         self._ck(self.L.idp_friction_set(self.h, _p(Xn), 3 if Xn is None else Xn.shape[1], float(epsv2_h2), float(mu)))
+
+    def friction_set_components(self, comp_node_range, mu_comp):
+        if comp_node_range is None or len(comp_node_range) == 0:
+            return self._ck(self.L.idp_friction_set_components(self.h, 0, None, None))
+        r = np.ascontiguousarray(comp_node_range, np.int32)
+        m = np.ascontiguousarray(mu_comp, np.float64).reshape(len(r), len(r))
+        self._ck(self.L.idp_friction_set_components(self.h, len(r), _p(r), _p(m)))
 
     def friction_energy(self, E0=0.0):
         E = C.c_double(E0)

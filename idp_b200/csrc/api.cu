@@ -485,6 +485,19 @@ int idp_friction_set(idp_ctx* c, const double* xn, int stride, double epsv2_h2, 
     }
     return IDP_OK;
 }
+int idp_friction_set_components(idp_ctx* c, int n_comp, const int* comp_node_range, const double* mu_comp)
+{
+    if (!c || n_comp < 0 || (n_comp && (!comp_node_range || !mu_comp))) return c ? fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "idp_friction_set_components: bad arguments", __FILE__, __LINE__) : IDP_ERR_INVALID;
+    IDP_CK(c, cudaSetDevice(c->device));
+    c->nFricComp = 0;
+    if (n_comp == 0) return IDP_OK;
+    IDP_CK(c, c->fricCompRange.reserve(n_comp)); IDP_CK(c, c->fricMuComp.reserve((size_t)n_comp * n_comp));
+    IDP_CK(c, cudaMemcpyAsync(c->fricCompRange.p, comp_node_range, (size_t)n_comp * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    IDP_CK(c, cudaMemcpyAsync(c->fricMuComp.p, mu_comp, (size_t)n_comp * n_comp * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    IDP_CK(c, cudaStreamSynchronize(c->stream));
+    c->nFricComp = n_comp;
+    return IDP_OK;
+}
 int idp_friction_energy(idp_ctx* c, double* E_inout)
 {
     if (!c || !E_inout) return IDP_ERR_INVALID;

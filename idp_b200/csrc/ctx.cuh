@@ -204,6 +204,9 @@ struct idp_ctx {
     idp::DBuf<unsigned char> fricRows;  // FricRow records (friction.cuh)
     idp::DBuf<double> fricG;            // friction gradient (3 nV)
     long nFric = 0, nFricActive = 0;
+    idp::DBuf<int> fricCompRange;       // Compute_Friction_Coef: component c holds the vertices below fricCompRange[c] (and above the previous bound)
+    idp::DBuf<double> fricMuComp;       // nComp x nComp coefficients
+    int nFricComp = 0;
     double fricMu = 0, fricEpsvh = 0;
     bool have_xn = false;
     // ---- device-side surface extraction (idp_set_mesh_from_triangles) ----

@@ -36,6 +36,22 @@ __global__ void __launch_bounds__(256) k_friction_basis(const Row4* __restrict__
     if (threadIdx.x == 0 && s) atomicAdd(nActive, (unsigned long long)s);
 }
 
+// Compute_Friction_Coef (FRICTION.h:126-170): the normal force of a row is scaled by the coefficient of the two components its
+// first and its opposite primitive belong to (vertex v is in the first component whose upper bound exceeds it); mu becomes 1
+__global__ void __launch_bounds__(256) k_friction_coef(FricRow* __restrict__ rows, long n, const int* __restrict__ compRange, const double* __restrict__ muComp,
+    int nComp, unsigned long long* __restrict__ bad)
+{
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        FricRow& f = rows[i];
+        if (f.nv == 0) continue;
+        const int va = f.v[0], vb = f.kind == K_EE ? f.v[2] : f.v[1];
+        int ca = -1, cb = -1;
+        for (int c = nComp - 1; c >= 0; --c) { if (va < compRange[c]) ca = c; if (vb < compRange[c]) cb = c; }
+        if (ca < 0 || cb < 0) { atomicAdd(bad, 1ull); continue; } // "can't find node compI"
+        f.lam *= muComp[ca + cb * nComp];
+    }
+}
+
 struct FrictionArgs {
     const FricRow* rows; long rBegin, rEnd;
     const double4* xp; const double4* xnp;
@@ -141,6 +157,15 @@ int friction_update(idp_ctx* c, double dhat2, double kappa, double thickness)
     IDP_CK(c, cudaStreamSynchronize(c->stream));
     c->nFric = c->nRows;
     c->nFricActive = (long)n;
+    if (c->nFricComp > 0 && n > 0) {
+        IDP_CK(c, cudaMemsetAsync(cnt, 0, sizeof(long long), c->stream));
+        IDP_LAUNCH(c, k_friction_coef, std::min(blocks_for(c->nRows, 256), (unsigned)c->sm_count * 16), 256, 0, (FricRow*)c->fricRows.p, c->nRows, c->fricCompRange.p,
+            c->fricMuComp.p, c->nFricComp, cnt);
+        long long bad = 0;
+        IDP_CK(c, cudaMemcpyAsync(&bad, cnt, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+        IDP_CK(c, cudaStreamSynchronize(c->stream));
+        if (bad) return fail(c, IDP_ERR_INVALID, "%s (%s:%d)", "idp_friction_update: a vertex lies beyond the last component bound (can't find node compI)", __FILE__, __LINE__);
+    }
     return IDP_OK;
 }
 

@@ -128,6 +128,10 @@ public:
         return n;
     }
     void friction_set(const double* xn, double epsv2h2, double mu) override { check(idp_friction_set(ctx_, xn, 3, epsv2h2, mu)); fresh_ = false; }
+    void friction_set_components(const std::vector<int>& compNodeRange, const std::vector<double>& muComp) override
+    {
+        check(idp_friction_set_components(ctx_, (int)compNodeRange.size(), compNodeRange.data(), muComp.data()));
+    }
     void friction_energy(double& E) override { Scope t(*this, OP_FRIC); check(idp_friction_energy(ctx_, &E)); }
     void friction_gradient(double* g) override { Scope t(*this, OP_FRIC); check(idp_friction_gradient(ctx_, g, 3)); }
     double ccd(const double* dir, double thickness, double alpha) override

@@ -298,7 +298,7 @@ PYBIND11_MODULE(JGSL, m)
             ShellStepInputs in;
             in.flow = flow; in.thickness = thickness; in.bendingStiffMult = bendingStiffMult; in.h = h; in.NewtonTol = NewtonTol; in.dHat2 = dHat2;
             in.mu = mu; in.epsv2 = epsv2; in.fricIterAmt = fricIterAmt;
-            in.muPerComponent = muComp.size() && muComp.size() == compNodeRange.size() * compNodeRange.size();
+            in.compNodeRange = compNodeRange; in.muComp = muComp;
             in.withCollision = withCollision; in.staticSolve = staticSolve;
             in.nTet = tet.size(); in.nRod = (int)rod.size(); in.nStitch = (int)stitchInfo.size(); in.nParticle = (int)particle.size();
             in.outputFolder = outputFolder;

@@ -53,6 +53,8 @@ struct ContactBackend {
     // to xn; the Hessian blocks are part of solve_newton_system while mu > 0
     virtual long friction_update(double dHat2, double kappa, double thickness) = 0;     // Compute_Friction_Basis, returns #friction rows
     virtual void friction_set(const double* xn, double epsv2h2, double mu) = 0;
+    // Compute_Friction_Coef: per-component coefficients applied to the normal forces at every friction_update (empty: off)
+    virtual void friction_set_components(const std::vector<int>& compNodeRange, const std::vector<double>& muComp) = 0;
     virtual void friction_energy(double& E) = 0;   // adds
     virtual void friction_gradient(double* g) = 0; // adds
     virtual double ccd(const double* dir, double thickness, double alpha) = 0;          // Compute_Intersection_Free_StepSize
@@ -511,7 +513,8 @@ struct ShellStepInputs { // the arguments of Advance_One_Step_IE_Discrete_Shell 
     bool flow = false;
     double thickness = 0, bendingStiffMult = 0, h = 0, NewtonTol = 1e-3, dHat2 = 0, mu = 0, epsv2 = 0;
     int fricIterAmt = 1;
-    bool muPerComponent = false; // Compute_Friction_Coef (per-component coefficients) is not hosted
+    std::vector<int> compNodeRange; // Compute_Friction_Coef: used when muComp holds one coefficient per pair of components
+    std::vector<double> muComp;
     bool withCollision = false, staticSolve = false;
     int nTet = 0, nRod = 0, nStitch = 0, nParticle = 0;
     std::string outputFolder;
@@ -519,7 +522,7 @@ struct ShellStepInputs { // the arguments of Advance_One_Step_IE_Discrete_Shell 
 
 // Advance_One_Step_IE_Discrete_Shell<double, 3, KL=false, elasticIPC=false, flow> (IMPLICIT_EULER.h:151-891).
 // Unsupported inputs are rejected like the contact path rejects them (message + exit(-1)): segments, rods, particles, tets,
-// stitches, per-component friction coefficients, strain limiting, fibers, static solves.
+// stitches, strain limiting, fibers, static solves.
 inline int advance_one_step_ie(ContactBackend& be, const ShellStepInputs& in, TriStorage& Elem, const std::vector<Vec<int, 2>>& seg, DbcStorage& DBC,
     const std::vector<Vec<int, 4>>& edgeStencil, const std::vector<Vec<double, 3>>& edgeInfo, const Vec<double, 4>& fiberStiffMult,
     const Vec<double, 2>& kappa_s, const std::vector<double>& b, Vec<double, 3>& kappaVec, NodeStorage& X, NodeAttrStorage& nodeAttr, CsrMatrix& M,
@@ -528,9 +531,9 @@ inline int advance_one_step_ie(ContactBackend& be, const ShellStepInputs& in, Tr
     const bool flow = in.flow, withCollision = in.withCollision;
     const double h = in.h, thickness = in.thickness, dHat2 = in.dHat2, NewtonTol = in.NewtonTol;
     const std::string& outputFolder = in.outputFolder;
-    if (!seg.empty() || in.nTet || in.nRod || in.nStitch || in.nParticle || in.muPerComponent || kappa_s[0] > 0 || fiberStiffMult[0] > 0 ||
-        fiberStiffMult[1] > 0 || in.staticSolve) {
-        printf("Advance_One_Step_IE (%s): segments / rods / particles / tets / stitches / per-component friction / strain limiting / fibers / static "
+    if (!seg.empty() || in.nTet || in.nRod || in.nStitch || in.nParticle || kappa_s[0] > 0 || fiberStiffMult[0] > 0 || fiberStiffMult[1] > 0 ||
+        in.staticSolve) {
+        printf("Advance_One_Step_IE (%s): segments / rods / particles / tets / stitches / strain limiting / fibers / static "
                "solves are outside the device-resident shell step\n", be.name());
         exit(-1);
     }
@@ -684,9 +687,13 @@ inline int advance_one_step_ie(ContactBackend& be, const ShellStepInputs& in, Tr
     printf("computing initial energy\n");
     be.set_positions(s.x.data());
     if (withCollision) s.nRows = be.constraint_set(dHat2, thickness);
-    pot.friction = withCollision && in.mu > 0;
+    // per-component coefficients (Compute_Friction_Coef) are in force when muComp is an nComp x nComp table; mu is then 1 (:435-438)
+    const bool perComp = !in.muComp.empty() && in.muComp.size() == in.compNodeRange.size() * in.compNodeRange.size();
+    const double muEff = perComp ? 1.0 : in.mu;
+    pot.friction = withCollision && muEff > 0;
     if (pot.friction) { // lagged friction: basis and normal forces from the state the step starts in (:432-439)
-        be.friction_set(xn.data(), in.epsv2 * h * h, in.mu);
+        be.friction_set_components(perComp ? in.compNodeRange : std::vector<int>(), perComp ? in.muComp : std::vector<double>());
+        be.friction_set(xn.data(), in.epsv2 * h * h, muEff);
         be.friction_update(dHat2, kappa[0], thickness);
     }
     else be.friction_set(nullptr, 0.0, 0.0);

@@ -165,9 +165,13 @@ int idp_elastic_gradient(idp_ctx* ctx, double* g_accum, int stride);
  *     following idp_barrier_hessian / idp_barrier_all (INC_POTENTIAL.h:375-377);
  *   idp_get_friction copies the frozen rows in the reference's layout (rows, closest-point parameters (2), tangent basis
  *     (3x2 column major), normal force); any pointer may be NULL.
- * Per-component friction coefficients (Compute_Friction_Coef, :126-170) are not built. idp_set_mesh* clears the rows. */
+ *   idp_friction_set_components = the compNodeRange / muComp arguments of Compute_Friction_Coef (:126-170): with n_comp > 0 every
+ *     following idp_friction_update scales the normal force of a row by mu_comp[c0 + c1 * n_comp], c0 / c1 the components of its
+ *     first and of its opposite primitive (vertex v belongs to the first component with v < comp_node_range[c]); the caller then
+ *     passes mu = 1 like the reference does. n_comp = 0 switches it off. idp_set_mesh* clears the rows. */
 int idp_friction_update(idp_ctx* ctx, double dhat2, double kappa, double thickness, long* n_friction_rows);
 int idp_friction_set(idp_ctx* ctx, const double* xn, int stride, double epsv2_h2, double mu);
+int idp_friction_set_components(idp_ctx* ctx, int n_comp, const int* comp_node_range, const double* mu_comp);
 int idp_friction_energy(idp_ctx* ctx, double* E_inout);
 int idp_friction_gradient(idp_ctx* ctx, double* g_accum, int stride);
 int idp_get_friction(idp_ctx* ctx, long* n_rows, int* rows4, double* closest2, double* basis6, double* normal_force);

@@ -160,6 +160,21 @@ long orc_friction(int nV, const double* Xb, const double* X, const double* Xn, l
     return nt;
 }
 
+// Compute_Friction_Coef on friction rows (as returned by orc_friction) and their normal forces, in place; 0 on success
+int orc_friction_coef(int n, const int* fricRows4, int nComp, const int* compNodeRange, const double* muComp, double* normalForce)
+{
+    std::vector<FrictionRow> fr((size_t)n);
+    for (int i = 0; i < n; ++i) {
+        FrictionRow& f = fr[i];
+        for (int k = 0; k < 4; ++k) f.row[k] = fricRows4[4 * i + k];
+        f.v[0] = f.row[0] >= 0 ? f.row[0] : -f.row[0] - 1; f.v[1] = f.row[1]; f.v[2] = f.row[2]; f.v[3] = f.row[3];
+        f.lam = normalForce[i];
+    }
+    if (!friction_coef(fr, std::vector<int>(compNodeRange, compNodeRange + nComp), std::vector<double>(muComp, muComp + (size_t)nComp * nComp))) return 1;
+    for (int i = 0; i < n; ++i) normalForce[i] = fr[i].lam;
+    return 0;
+}
+
 // ---- system matrix around the barrier Hessian (orc_system.hpp) -------------------------------------------------
 // triplets = [flow term][barrier rows] -> Construct_From_Triplet -> += M -> Project_DBC (INC_POTENTIAL.h:321-394)
 void* orc_system_matrix(const OrcMesh* m, long n, const int* rows, const double* weight, double dHat2, double kappa,

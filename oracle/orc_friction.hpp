@@ -73,6 +73,18 @@ static inline void friction_basis(const double* X, const std::vector<Row>& rows,
     }
 }
 
+// Compute_Friction_Coef (FRICTION.h:114-170): normal force x coefficient of the (first primitive, opposite primitive) components
+static inline bool friction_coef(std::vector<FrictionRow>& rows, const std::vector<int>& compNodeRange, const std::vector<double>& muComp)
+{
+    auto comp = [&](int v) { for (size_t c = 0; c < compNodeRange.size(); ++c) if (v < compNodeRange[c]) return (int)c; return -1; };
+    for (FrictionRow& f : rows) {
+        const int c0 = comp(f.v[0]), c1 = comp(f.row[0] >= 0 ? f.v[2] : f.v[1]);
+        if (c0 < 0 || c1 < 0) return false; // "can't find node compI"
+        f.lam *= muComp[c0 + c1 * compNodeRange.size()];
+    }
+    return true;
+}
+
 // stencil weights of the relative displacement (FRICTION_UTILS.h: *_RelDX / *_TT)
 static inline void friction_weights(const FrictionRow& f, double w[4])
 {

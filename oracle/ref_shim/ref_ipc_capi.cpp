@@ -157,4 +157,17 @@ long refipc_friction(int nV, const double* xb, const double* x, const double* xn
     return nt;
 }
 
+// Compute_Friction_Coef (FRICTION.h:126-170) on friction rows and their normal forces (scaled in place); returns the mu it sets (1)
+double refipc_friction_coef(int n, const int* fricRows4, int nComp, const int* compNodeRange, const double* muComp, double* normalForce)
+{
+    std::vector<VECTOR<int, 4>> fcs;
+    for (int i = 0; i < n; ++i) fcs.emplace_back(fricRows4[4 * i], fricRows4[4 * i + 1], fricRows4[4 * i + 2], fricRows4[4 * i + 3]);
+    std::vector<int> range(compNodeRange, compNodeRange + nComp);
+    std::vector<T> mc(muComp, muComp + (size_t)nComp * nComp), nf(normalForce, normalForce + n);
+    T mu = 0;
+    Compute_Friction_Coef<T, 3>(fcs, range, mc, nf, mu);
+    for (int i = 0; i < n; ++i) normalForce[i] = nf[i];
+    return mu;
+}
+
 } // extern "C"

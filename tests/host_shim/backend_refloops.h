@@ -254,6 +254,14 @@ public:
         if (tr) { tr->resize((size_t)nt); tc->resize((size_t)nt); tv->resize((size_t)nt); }
         return nf;
     }
+    void friction_set_components(const std::vector<int>& compNodeRange, const std::vector<double>& muComp) override
+    {
+        if (!compNodeRange.empty()) { // the stateless reference entry point evaluates with unit coefficients only
+            printf("reference-loops backend: per-component friction coefficients are checked at the operator level (tests/test_friction.py)\n");
+            exit(-1);
+        }
+        (void)muComp;
+    }
     void friction_energy(double& E) override { if (fMu_ > 0) friction_call(&E, nullptr, nullptr, nullptr, nullptr); }
     void friction_gradient(double* g) override { if (fMu_ > 0) friction_call(nullptr, g, nullptr, nullptr, nullptr); }
     double ccd(const double* dir, double thickness, double alpha) override

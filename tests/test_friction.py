@@ -139,3 +139,61 @@ def test_friction_on_the_device_matches_reference(lib_built, orc):
             assert c.friction_energy() == 0.0                        # mu = 0 switches the term off
         finally:
             c.close()
+
+
+@needs_ref
+def test_friction_components_oracle_matches_reference(orc):
+    """Compute_Friction_Coef: oracle/orc_friction.hpp against the reference's own function."""
+    ref = ref_binding.ReferenceIPC()
+    L, O = ref.lib, orc.lib
+    L.refipc_friction_coef.restype = C.c_double
+    L.refipc_friction_coef.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    O.orc_friction_coef.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    m, rows, dh2, Xn, X = _scene(orc, make_cases()[0], 0)
+    r = ref.friction(m.X, rows, dh2, KAPPA)
+    rng_ = np.array([m.nV // 3, 2 * m.nV // 3, m.nV], np.int32)
+    muc = np.array([0.1, 0.2, 0.3, 0.2, 0.4, 0.5, 0.3, 0.5, 0.6])
+    a, b = r["normal_force"].copy(), r["normal_force"].copy()
+    fr = np.ascontiguousarray(r["rows"], np.int32)
+    assert L.refipc_friction_coef(len(fr), _p(fr), 3, _p(rng_), _p(muc), _p(a)) == 1.0
+    assert O.orc_friction_coef(len(fr), _p(fr), 3, _p(rng_), _p(muc), _p(b)) == 0
+    assert np.array_equal(a, b) and not np.array_equal(a, r["normal_force"])
+
+
+@pytest.mark.gpu
+def test_friction_components_on_the_device(lib_built, orc):
+    """idp_friction_set_components: the frozen normal forces carry the per-component coefficient (checked against the reference's
+    Compute_Friction_Coef where built, else the oracle's)."""
+    from idp_b200 import ContactContext
+    m, rows, dh2, Xn, X = _scene(orc, make_cases()[0], 0)
+    rng_ = np.array([m.nV // 3, 2 * m.nV // 3, m.nV], np.int32)
+    muc = np.array([0.1, 0.2, 0.3, 0.2, 0.4, 0.5, 0.3, 0.5, 0.6])
+    c = ContactContext(0)
+    try:
+        c.set_surface_mesh(m)
+        c.constraint_set(dh2)
+        c.friction_update(dh2, KAPPA)
+        frows, _, _, nf0 = c.get_friction()
+        c.friction_set_components(rng_, muc)
+        c.friction_update(dh2, KAPPA)
+        frows1, _, _, nf1 = c.get_friction()
+        assert np.array_equal(frows, frows1)
+        want = nf0.copy()
+        fr = np.ascontiguousarray(frows, np.int32)
+        if HAVE_REF:
+            L = ref_binding.ReferenceIPC().lib
+            L.refipc_friction_coef.restype = C.c_double
+            L.refipc_friction_coef.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+            L.refipc_friction_coef(len(fr), _p(fr), 3, _p(rng_), _p(muc), _p(want))
+        else:
+            orc.lib.orc_friction_coef.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+            assert orc.lib.orc_friction_coef(len(fr), _p(fr), 3, _p(rng_), _p(muc), _p(want)) == 0
+        assert np.allclose(nf1, want, rtol=1e-14, atol=0) and not np.allclose(nf1, nf0)
+        c.friction_set_components(None, None)
+        c.friction_update(dh2, KAPPA)
+        assert np.array_equal(c.get_friction()[3], nf0)
+        with pytest.raises(Exception):  # a vertex beyond the last bound: the reference prints "can't find node compI" and exits
+            c.friction_set_components(np.array([m.nV // 2], np.int32), np.array([0.3]))
+            c.friction_update(dh2, KAPPA)
+    finally:
+        c.close()
