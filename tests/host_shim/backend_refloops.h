@@ -36,6 +36,8 @@ namespace jgsl {
 
 class RefLoopsBackend : public ContactBackend {
 public:
+    double pcg_rel_tol = 1e-12; // same knobs as the B200 backend (the module sets them); this backend always solves to 1e-12
+    int pcg_max_iter = 100000;
     explicit RefLoopsBackend(int) {}
     const char* name() const override { return "reference-loops"; }
 
