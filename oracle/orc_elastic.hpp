@@ -5,10 +5,11 @@
 //                    dihedral angle Library/Math/DIHEDRAL_ANGLE.h:9-24
 // The ENERGIES are written as the reference defines them; gradients and Hessians are obtained from those expressions by
 // second-order forward-mode jets (orc_deriv.hpp), independently of the closed forms the CUDA path uses; the PSD projection
-// is the oracle's cyclic-Jacobi makePD (Math/UTILS.h:9-27). Parity status: UNPINNED against compiled reference code (the
-// reference headers of these terms pull in the whole shell stack: Cabana storages, meta, the SVD routine); the dihedral
-// angle, its gradient and Hessian ARE pinned by the reference's own Math/DIHEDRAL_ANGLE.h compiled in oracle/_ref
-// (tests/test_elastic_host.py::test_oracle_hinge_is_pinned_by_the_reference_dihedral_code) where that build exists.
+// is the oracle's cyclic-Jacobi makePD (Math/UTILS.h:9-27). Parity status: PINNED by the reference's own code compiled in
+// oracle/_ref (tests/test_elastic_host.py): FEM/Shell/MEMBRANE.h and BENDING.h (KL = false) in libidp_ref_shell.so -- energy,
+// gradient and PSD-projected Hessian triplets of a deformed mesh with a Dirichlet mask within 1e-10 -- and Math/DIHEDRAL_ANGLE.h
+// in libidp_ref.so (angle bit for bit, gradient / Hessian 1e-10). Those builds use the repository's Eigen stand-in (no Eigen
+// in this image), like every other reference build here.
 #pragma once
 #include "orc_deriv.hpp"
 #include <cmath>

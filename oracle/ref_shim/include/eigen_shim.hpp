@@ -48,6 +48,7 @@ struct Matrix {
     template <int R2, int C2, class = typename std::enable_if<(R2 == C && C2 == R && R != C)>::type>
     Matrix(const Array<T, R2, C2>& a) { for (int i = 0; i < R * C; ++i) d[i] = a.d[i]; }
     static Matrix Zero() { Matrix m; m.setZero(); return m; }
+    static Matrix Identity() { Matrix m; m.setZero(); for (int i = 0; i < (R < C ? R : C); ++i) m(i, i) = T(1); return m; }
     static Matrix UnitX() { Matrix m; m.setZero(); m.d[0] = T(1); return m; }
     static Matrix UnitY() { Matrix m; m.setZero(); m.d[1] = T(1); return m; }
     T& operator()(int i, int j) { return d[i + j * R]; }
@@ -147,7 +148,14 @@ struct Matrix {
         template <int R2, int C2> Matrix<T, 1, C> cross(const Matrix<T, R2, C2>& o) const { return ((Matrix<T, 1, C>)*this).cross(o); }
         Matrix<T, 1, C> cross(const RowRef& o) const { return ((Matrix<T, 1, C>)*this).cross((Matrix<T, 1, C>)o); }
         Matrix<T, C, 1> transpose() const { return ((Matrix<T, 1, C>)*this).transpose(); }
+        Matrix<T, 1, C> operator-() const { return -((Matrix<T, 1, C>)*this); }
     };
+    // comma initialiser, rows at a time (m << row0, row1, ...)
+    struct RowComma {
+        Matrix& m; int i;
+        RowComma& operator,(const Matrix<T, 1, C>& r) { for (int j = 0; j < C; ++j) m(i, j) = r.d[j]; ++i; return *this; }
+    };
+    RowComma operator<<(const Matrix<T, 1, C>& r) { RowComma c{*this, 0}; c, r; return c; }
     struct ColRef {
         Matrix& m; int j;
         operator Matrix<T, R, 1>() const { Matrix<T, R, 1> r; for (int i = 0; i < R; ++i) r.d[i] = m(i, j); return r; }
@@ -176,6 +184,7 @@ struct Matrix {
         Matrix& m; int i0, j0;
         operator Matrix<T, BR, BC>() const { Matrix<T, BR, BC> r; for (int i = 0; i < BR; ++i) for (int j = 0; j < BC; ++j) r(i, j) = m(i0 + i, j0 + j); return r; }
         template <class O> BlockRef& operator+=(const O& o) { const Matrix<T, BR, BC> v = o; for (int i = 0; i < BR; ++i) for (int j = 0; j < BC; ++j) m(i0 + i, j0 + j) += v(i, j); return *this; }
+        template <class O> BlockRef& operator-=(const O& o) { const Matrix<T, BR, BC> v = o; for (int i = 0; i < BR; ++i) for (int j = 0; j < BC; ++j) m(i0 + i, j0 + j) -= v(i, j); return *this; }
         template <class O> BlockRef& operator=(const O& o) { const Matrix<T, BR, BC> v = o; for (int i = 0; i < BR; ++i) for (int j = 0; j < BC; ++j) m(i0 + i, j0 + j) = v(i, j); return *this; }
         Matrix<T, BC, BR> transpose() const { return ((Matrix<T, BR, BC>)*this).transpose(); }
         void setZero() { for (int i = 0; i < BR; ++i) for (int j = 0; j < BC; ++j) m(i0 + i, j0 + j) = T(0); }

@@ -1,7 +1,8 @@
 """Golden trace of BASELINE configs[0] (the paper's normal-flow example): the reference's UNCHANGED script
 Projects/FEMShell/12-14_normal_flow.py + Python/Drivers run from the writable mirror (scripts/make_ref_mirror.sh) on the
 `JGSL` module of this repository built with the REFERENCE's own CPU contact loops as its backend
-(tests/host_shim/jgsl_ref/JGSL.so: FEM/IPC.h + Grid/SPATIAL_HASH.h + Math/CSR_MATRIX.h compiled from /root/reference).
+(tests/host_shim/jgsl_ref/JGSL.so: FEM/IPC.h + Grid/SPATIAL_HASH.h + Math/CSR_MATRIX.h + FEM/Shell/MEMBRANE.h + BENDING.h +
+FEM/FRICTION.h compiled from /root/reference).
 Stores the input mesh, counter.txt (PN iterations and contact # per time step, Shell/IMPLICIT_EULER.h:857-864) and the
 final vertex positions. The B200 build of the same module must reproduce the trace (tests/test_gpu_jgsl_module.py).
 

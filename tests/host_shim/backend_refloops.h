@@ -1,6 +1,7 @@
 // TEST INFRASTRUCTURE (never shipped, never linked into idp_b200/): the same flow time step (idp_b200/host/jgsl/shell_flow.h)
 // with every contact operator served by the REFERENCE's own CPU loops -- FEM/IPC.h + Grid/SPATIAL_HASH.h compiled in
-// oracle/_ref/libidp_ref_ipc.so -- and the system matrix built by the reference's own Math/CSR_MATRIX.h
+// oracle/_ref/libidp_ref_ipc.so --, the membrane / hinge terms by the reference's own FEM/Shell/MEMBRANE.h and BENDING.h
+// (oracle/_ref/libidp_ref_shell.so), friction by its FEM/FRICTION.h, and the system matrix built by the reference's own Math/CSR_MATRIX.h
 // (oracle/_ref/libidp_ref_csr.so: Construct_From_Triplet, += M, Project_DBC). Used to produce the per-step
 // "PN iterations / contact #" trace (counter.txt, Shell/IMPLICIT_EULER.h:857-864) that the B200 build of the module must
 // reproduce. The linear solve is a host Jacobi-preconditioned CG to 1e-12 (CHOLMOD is not in this image).
@@ -20,11 +21,11 @@ long refipc_barrier(int nV, const double* x, const double* x0, int n, const int*
 double refipc_ccd(int nV, const double* x, int nBN, const int* bn, int nBE, const int* be, int nBT, const int* bt, const unsigned char* dbc,
     const double* dir, double thickness, double step);
 double refipc_min_dist2(int nV, const double* x, int n, const int* rows4, double thickness, double* dist2);
-// the oracle's restatement of the elastic terms (oracle/orc_elastic.hpp; the reference's MEMBRANE.h / BENDING.h cannot be compiled here)
-void orc_membrane_batch(int nElem, const int* elem3, const double* X, const double* ib3, const double* coef, const double* lambda, const double* mu,
-    const unsigned char* dbc, int projectSPD, double* E, double* g3nV, double* H81, unsigned char* active);
-void orc_hinge_batch(int nHinge, const int* stencil4, const double* X, const double* info3, double kh2, const unsigned char* dbc, int projectSPD,
-    double* E, double* g3nV, double* H144, unsigned char* active);
+// the reference's own shell energy terms (FEM/Shell/MEMBRANE.h, BENDING.h with KL = false; oracle/_ref/libidp_ref_shell.so)
+long refshell_membrane(int nV, const double* x, int nE, const int* elem3, const double* ib3, const double* vol, const double* lambda, const double* mu,
+    const unsigned char* dbc, double h, int projectSPD, double* E, double* g, long cap, int* tr, int* tc, double* tv);
+long refshell_hinges(int nV, const double* x, int nH, const int* stencil4, const double* info3, double k, double bendingStiffMult, const unsigned char* dbc,
+    double h, int projectSPD, double* E, double* g, long cap, int* tr, int* tc, double* tv);
 long refipc_friction(int nV, const double* xb, const double* x, const double* xn, int n, const int* rows4, const double* w, double dHat2, double kappa,
     double thickness, double epsvh2, double mu, int projectSPD, int* nFric, int* fricRows4, double* closest2, double* basis6, double* normalForce,
     double* E, double* g, long cap, int* trow, int* tcol, double* tval);
@@ -75,31 +76,28 @@ public:
     void set_elastic_terms(const std::vector<int>& elem3, const std::vector<double>& ib3, const std::vector<double>& vol, const std::vector<double>& lambda,
         const std::vector<double>& mu, const std::vector<int>& stencil4, const std::vector<double>& info3, double k, double h) override
     {
-        mElem_ = elem3; mIB_ = ib3; mLam_ = lambda; mMu_ = mu; hSt_ = stencil4; hInfo_ = info3; hKh2_ = h * h * k;
-        mCoef_.resize(vol.size());
-        for (size_t e = 0; e < vol.size(); ++e) mCoef_[e] = h * h * vol[e];
+        mElem_ = elem3; mIB_ = ib3; mVol_ = vol; mLam_ = lambda; mMu_ = mu; hSt_ = stencil4; hInfo_ = info3; hK_ = k; eH_ = h;
     }
-    void elastic(double* Esum, double* g, std::vector<double>* H81, std::vector<double>* H144, std::vector<unsigned char>* actM, std::vector<unsigned char>* actH)
+    // Compute_Membrane_* then Compute_Bending_* of the reference itself: E (added), g (added), triplets (appended)
+    void elastic(double* E, double* g, std::vector<int>* tr, std::vector<int>* tc, std::vector<double>* tv)
     {
         const int nM = (int)mElem_.size() / 3, nH = (int)hSt_.size() / 4;
-        std::vector<double> E((size_t)std::max(nM, nH) + 1);
-        std::vector<unsigned char> am((size_t)nM + 1), ah((size_t)nH + 1);
-        if (H81) H81->assign(81 * (size_t)nM, 0.0);
-        if (H144) H144->assign(144 * (size_t)nH, 0.0);
-        if (nM) {
-            orc_membrane_batch(nM, mElem_.data(), x_.data(), mIB_.data(), mCoef_.data(), mLam_.data(), mMu_.data(), dbc_.data(), 1, E.data(), g, H81 ? H81->data() : nullptr,
-                am.data());
-            if (Esum) for (int e = 0; e < nM; ++e) *Esum += E[e];
+        for (int part = 0; part < 2; ++part) {
+            const long cap = tr ? (part == 0 ? 81L * nM : 144L * nH) : 0;
+            if ((part == 0 ? nM : nH) == 0) continue;
+            std::vector<int> r((size_t)cap), c((size_t)cap);
+            std::vector<double> v((size_t)cap);
+            long nt;
+            if (part == 0)
+                nt = refshell_membrane(nV_, x_.data(), nM, mElem_.data(), mIB_.data(), mVol_.data(), mLam_.data(), mMu_.data(), dbc_.data(), eH_, 1, E, g, cap,
+                    tr ? r.data() : nullptr, c.data(), v.data());
+            else
+                nt = refshell_hinges(nV_, x_.data(), nH, hSt_.data(), hInfo_.data(), hK_, 1.0, dbc_.data(), eH_, 1, E, g, cap, tr ? r.data() : nullptr, c.data(), v.data());
+            if (tr) { tr->insert(tr->end(), r.begin(), r.begin() + nt); tc->insert(tc->end(), c.begin(), c.begin() + nt); tv->insert(tv->end(), v.begin(), v.begin() + nt); }
         }
-        if (nH) {
-            orc_hinge_batch(nH, hSt_.data(), x_.data(), hInfo_.data(), hKh2_, dbc_.data(), 1, E.data(), g, H144 ? H144->data() : nullptr, ah.data());
-            if (Esum) for (int e = 0; e < nH; ++e) *Esum += E[e];
-        }
-        if (actM) *actM = am;
-        if (actH) *actH = ah;
     }
-    void elastic_energy(double& E) override { elastic(&E, nullptr, nullptr, nullptr, nullptr, nullptr); }
-    void elastic_gradient(double* g) override { elastic(nullptr, g, nullptr, nullptr, nullptr, nullptr); }
+    void elastic_energy(double& E) override { elastic(&E, nullptr, nullptr, nullptr, nullptr); }
+    void elastic_gradient(double* g) override { elastic(nullptr, g, nullptr, nullptr, nullptr); }
     void set_positions(const double* x) override { x_.assign(x, x + 3 * (size_t)nV_); }
     int constraint_set(double dHat2, double thickness) override
     {
@@ -142,25 +140,7 @@ public:
                     tr.push_back(a); tc.push_back(q); tv.push_back(-h_ * vol_[e] / 6);
                     tr.push_back(a); tc.push_back(a); tv.push_back(2 * h_ * vol_[e] / 6);
                 }
-        if (!mElem_.empty() || !hSt_.empty()) { // membrane, then hinges (INC_POTENTIAL.h:344-352), dense per element like the reference's triplets
-            std::vector<double> H81, H144;
-            std::vector<unsigned char> am, ah;
-            elastic(nullptr, nullptr, &H81, &H144, &am, &ah);
-            for (size_t e = 0; e < mElem_.size() / 3; ++e) {
-                if (!am[e]) continue;
-                for (int i = 0; i < 9; ++i)
-                    for (int j = 0; j < 9; ++j) {
-                        tr.push_back(mElem_[3 * e + i / 3] * 3 + i % 3); tc.push_back(mElem_[3 * e + j / 3] * 3 + j % 3); tv.push_back(H81[81 * e + 9 * i + j]);
-                    }
-            }
-            for (size_t e = 0; e < hSt_.size() / 4; ++e) {
-                if (!ah[e]) continue;
-                for (int i = 0; i < 12; ++i)
-                    for (int j = 0; j < 12; ++j) {
-                        tr.push_back(hSt_[4 * e + i / 3] * 3 + i % 3); tc.push_back(hSt_[4 * e + j / 3] * 3 + j % 3); tv.push_back(H144[144 * e + 12 * i + j]);
-                    }
-            }
-        }
+        if (!mElem_.empty() || !hSt_.empty()) elastic(nullptr, nullptr, &tr, &tc, &tv); // membrane, then hinges (INC_POTENTIAL.h:344-352)
         if (!rows_.empty()) {
             std::vector<double> w = weights();
             const long cap = 144 * (long)w.size();
@@ -293,8 +273,8 @@ private:
     int nV_ = 0;
     double h_ = 0;
     std::vector<int> bnode_, bedge_, btri_, elem_, rows_, mElem_, hSt_;
-    std::vector<double> mIB_, mCoef_, mLam_, mMu_, hInfo_;
-    double hKh2_ = 0;
+    std::vector<double> mIB_, mVol_, mLam_, mMu_, hInfo_;
+    double hK_ = 0, eH_ = 0;
     std::vector<int> fRows_;
     std::vector<double> fInfo_, fXb_, fXn_;
     double fDHat2_ = 0, fKappa_ = 0, fXi_ = 0, fMu_ = 0, fEps_ = 0;

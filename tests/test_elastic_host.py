@@ -141,3 +141,75 @@ def test_oracle_hinge_is_pinned_by_the_reference_dihedral_code(orc):
         assert abs(oE[0] - c * d * d) <= 1e-12 * c * d * d
         assert _rel(og.ravel(), 2 * c * d * g) <= 1e-10
         assert _rel(oH[0], 2 * c * (d * H + np.outer(g, g))) <= 1e-10
+
+
+def _ref_shell():
+    lib = os.path.join(ROOT, "oracle", "_ref", "libidp_ref_shell.so")
+    if not os.path.exists(lib):
+        pytest.skip("oracle/_ref/libidp_ref_shell.so not built (needs /root/reference)")
+    L = C.CDLL(lib)
+    L.refshell_membrane.restype = C.c_long
+    L.refshell_membrane.argtypes = [C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 6 + [C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_long] + [C.c_void_p] * 3
+    L.refshell_hinges.restype = C.c_long
+    L.refshell_hinges.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_double, C.c_int, C.c_void_p,
+                                  C.c_void_p, C.c_long] + [C.c_void_p] * 3
+    return L
+
+
+def _blocks_to_csr(H, verts, n):
+    import scipy.sparse as sp
+    k = verts.shape[1]
+    dof = (3 * verts[:, :, None] + np.arange(3)[None, None, :]).reshape(len(verts), 3 * k)
+    r = np.repeat(dof[:, :, None], 3 * k, axis=2).ravel()
+    c = np.repeat(dof[:, None, :], 3 * k, axis=1).ravel()
+    return sp.coo_matrix((H.ravel(), (r, c)), shape=(n, n)).tocsr()
+
+
+def test_oracle_elastic_terms_are_pinned_by_the_reference_shell_headers(orc):
+    """oracle/orc_elastic.hpp against the REFERENCE's own FEM/Shell/MEMBRANE.h and BENDING.h (KL = false) compiled in
+    oracle/_ref/libidp_ref_shell.so: Compute_Membrane_* / Compute_Bending_* energy, gradient and PSD-projected Hessian triplets on a
+    deformed mesh with a Dirichlet mask (all-Dirichlet elements skipped by both), 1e-10."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import make_cases
+    from shell_np import first_fundamental_forms, hinges
+    L = _ref_shell()
+    name, m, _d, _ = make_cases()[1]
+    rng = np.random.default_rng(23)
+    F = np.ascontiguousarray(m.btri[:, :3], np.int32)
+    X0 = np.ascontiguousarray(m.X0)
+    ib = np.ascontiguousarray(first_fundamental_forms(X0, F))
+    X = np.ascontiguousarray(X0 + rng.normal(0, 0.03 * np.sqrt(ib[:, 0].mean()), X0.shape))
+    dbc = (rng.uniform(size=m.nV) < 0.15).astype(np.uint8)
+    area = 0.5 * np.linalg.norm(np.cross(X0[F[:, 1]] - X0[F[:, 0]], X0[F[:, 2]] - X0[F[:, 0]]), axis=1)
+    vol = np.ascontiguousarray(area * 1e-2)
+    lam = np.full(len(F), 1e4 * 0.4 / (1 - 0.16)); mu = np.full(len(F), 1e4 / 2.8)
+    h, n3 = 0.04, 3 * m.nV
+    for proj in (0, 1):
+        E = C.c_double(0.0); g = np.zeros_like(X); cap = 81 * len(F)
+        tr = np.zeros(cap, np.int32); tc = np.zeros(cap, np.int32); tv = np.zeros(cap)
+        nt = L.refshell_membrane(m.nV, _p(X), len(F), _p(F), _p(ib), _p(vol), _p(lam), _p(mu), _p(dbc), h, proj, C.byref(E), _p(g), cap, _p(tr), _p(tc), _p(tv))
+        oE, og, oH, act = orc.membrane_batch(X, F, ib, h * h * vol, lam, mu, dbc=dbc, project_spd=bool(proj))
+        assert 0 < act.sum() < len(F) and nt == 81 * act.sum()
+        assert abs(E.value - oE.sum()) <= 1e-10 * np.abs(oE).sum()
+        assert np.abs(g - og).max() <= 1e-10 * np.abs(og).max()
+        A = sp.coo_matrix((tv[:nt], (tr[:nt], tc[:nt])), shape=(n3, n3)).tocsr()
+        B = _blocks_to_csr(oH, F, n3)
+        assert spla.norm(A - B) <= 1e-10 * spla.norm(B), ("membrane", proj, spla.norm(A - B) / spla.norm(B))
+    st, info = hinges(X0, F)
+    info[:, 0] += rng.normal(0, 0.05, len(info))
+    st = np.ascontiguousarray(st); info = np.ascontiguousarray(info)
+    k = 1e4 * 1e-6 / (24 * (1 - 0.16))
+    for proj in (0, 1):
+        E = C.c_double(0.0); g = np.zeros_like(X); cap = 144 * len(st)
+        tr = np.zeros(cap, np.int32); tc = np.zeros(cap, np.int32); tv = np.zeros(cap)
+        nt = L.refshell_hinges(m.nV, _p(X), len(st), _p(st), _p(info), k, 1.0, _p(dbc), h, proj, C.byref(E), _p(g), cap, _p(tr), _p(tc), _p(tv))
+        oE, og, oH, act = orc.hinge_batch(X, st, info, h * h * k, dbc=dbc, project_spd=bool(proj))
+        assert nt == 144 * act.sum()
+        assert abs(E.value - oE.sum()) <= 1e-10 * np.abs(oE).sum()
+        assert np.abs(g - og).max() <= 1e-10 * np.abs(og).max()
+        A = sp.coo_matrix((tv[:nt], (tr[:nt], tc[:nt])), shape=(n3, n3)).tocsr()
+        B = _blocks_to_csr(oH, st, n3)
+        assert spla.norm(A - B) <= 1e-10 * spla.norm(B), ("hinge", proj, spla.norm(A - B) / spla.norm(B))
