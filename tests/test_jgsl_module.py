@@ -10,7 +10,8 @@ import sys
 import numpy as np
 import pytest
 
-from jgsl_common import (DRIVER, PRODUCT_DIR, REFLOOPS_DIR, TRACE, build_product, compare_trace, read_counter, read_obj, run_own_driver, write_obj)
+from jgsl_common import (DRIVER, PRODUCT_DIR, REFLOOPS_DIR, SEQ_TRACE, TRACE, build_product, compare_trace, read_counter, read_obj, run_own_driver,
+                         run_own_seq_driver, write_obj, write_sequence)
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
@@ -137,3 +138,15 @@ def test_own_driver_reproduces_reference_script_trace(tmp_path):
     assert np.array_equal(read_counter(str(tmp_path / "out" / "counter.txt")), z["hand/counter"])
     Vend, _ = read_obj(str(tmp_path / "out" / ("shell%s.obj" % frames)))
     assert np.array_equal(Vend, z["hand/V_end"])
+
+
+@pytest.mark.skipif(not (os.path.exists(os.path.join(REFLOOPS_DIR, "JGSL.so")) and os.path.exists(SEQ_TRACE)),
+                    reason="reference-loops checker build / fixture absent (needs /root/reference)")
+def test_own_seq_driver_reproduces_reference_script_trace(tmp_path):
+    """Animation-fix example (membrane + hinge bending + barrier): the golden counter.txt came from the reference's unchanged
+    16_fix_char_seq.py; the repository's own caller on the same all-reference checker build gives the same first two steps."""
+    z = np.load(SEQ_TRACE)
+    rest, seq, _n = write_sequence(str(tmp_path), z)
+    rc, log = run_own_seq_driver(REFLOOPS_DIR, rest, seq, 2, str(tmp_path / "out"))
+    assert rc == 0, open(log).read()[-2000:]
+    assert np.array_equal(read_counter(str(tmp_path / "out" / "counter.txt")), z["counter"][:2])
