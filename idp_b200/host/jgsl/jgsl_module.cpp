@@ -27,6 +27,9 @@
 #endif
 #include JGSL_BACKEND_HEADER
 #include "dirichlet.h"
+#ifdef JGSL_STEP_HOOK_HEADER
+#include JGSL_STEP_HOOK_HEADER // test builds may take over a whole time step (tests/host_shim/ref_driver_hook.h); never set for the product
+#endif
 
 namespace py = pybind11;
 using namespace jgsl;
@@ -302,6 +305,12 @@ PYBIND11_MODULE(JGSL, m)
             in.withCollision = withCollision; in.staticSolve = staticSolve;
             in.nTet = tet.size(); in.nRod = (int)rod.size(); in.nStitch = (int)stitchInfo.size(); in.nParticle = (int)particle.size();
             in.outputFolder = outputFolder;
+#ifdef JGSL_STEP_HOOK
+            {
+                int hooked = 0;
+                if (JGSL_STEP_HOOK(in, Elem, DBC, edgeStencil, edgeInfo, b, kappaVec, X, nodeAttr, elemAttr, elasticityAttr, &hooked)) { fflush(stdout); return hooked; }
+            }
+#endif
             JGSL_BACKEND_CLASS& be = backend();
             // the linear solve is iterative where the reference factorises: its stopping rule is a parameter of this build
             // (Set_Parameter("B200.pcg_rel_tol", 1e-10), Set_Parameter("B200.pcg_max_iter", 20000))

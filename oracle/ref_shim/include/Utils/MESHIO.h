@@ -46,6 +46,8 @@ struct BASE_STORAGE {
     }
     template <class F> void Each(F f) { for (int i = 0; i < size; ++i) f(i, Get_Unchecked(i)); }
     void deep_copy_to(BASE_STORAGE& o) const { o.rows = rows; o.size = size; }
+    template <std::size_t I, class V> void Fill(const V& v) { for (auto& r : rows) std::get<I>(r) = v; }
+    int Insert(int i, const Ts&... v) { if (i >= size) { rows.resize((std::size_t)i + 1); size = i + 1; } rows[i] = std::tuple<Ts...>(v...); return i; }
     // Join(other).Par_Each(f): f(id, tuple of references to this row's fields followed by the other storage's)
     template <class... Us> struct JOINED {
         BASE_STORAGE& a; BASE_STORAGE<Us...>& b;

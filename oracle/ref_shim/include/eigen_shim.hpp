@@ -188,6 +188,8 @@ struct Matrix {
         template <class O> BlockRef& operator=(const O& o) { const Matrix<T, BR, BC> v = o; for (int i = 0; i < BR; ++i) for (int j = 0; j < BC; ++j) m(i0 + i, j0 + j) = v(i, j); return *this; }
         Matrix<T, BC, BR> transpose() const { return ((Matrix<T, BR, BC>)*this).transpose(); }
         void setZero() { for (int i = 0; i < BR; ++i) for (int j = 0; j < BC; ++j) m(i0 + i, j0 + j) = T(0); }
+        struct BlockDiag { Matrix& m; int i0, j0; void setConstant(T v) { for (int i = 0; i < (BR < BC ? BR : BC); ++i) m(i0 + i, j0 + i) = v; } };
+        BlockDiag diagonal() { return BlockDiag{m, i0, j0}; }
     };
     template <int BR, int BC> BlockRef<BR, BC> block(int i, int j) { return BlockRef<BR, BC>{*this, i, j}; }
     struct DiagRef {
@@ -287,6 +289,20 @@ struct Matrix<T, Dynamic, C> {
     int nr = 0;
     Matrix() {}
     Matrix(long rows, long cols) : d((size_t)rows * cols), nr((int)rows) { (void)cols; }
+    explicit Matrix(long rows) : d((size_t)rows * C), nr((int)rows) {} // VectorXd v(n)
+    static Matrix Zero(long rows) { Matrix m(rows); std::fill(m.d.begin(), m.d.end(), T(0)); return m; }
+    long size() const { return (long)d.size(); }
+    T* data() { return d.data(); }
+    const T* data() const { return d.data(); }
+    template <int N> struct SegRef {
+        Matrix& m; int s;
+        template <class O> SegRef& operator+=(const O& o) { const Matrix<T, N, 1> v = o; for (int i = 0; i < N; ++i) m.d[s + i] += v.d[i]; return *this; }
+        operator Matrix<T, N, 1>() const { Matrix<T, N, 1> r; for (int i = 0; i < N; ++i) r.d[i] = m.d[s + i]; return r; }
+    };
+    template <int N> SegRef<N> segment(int s) { return SegRef<N>{*this, s}; }
+    T dot(const Matrix& o) const { T s = T(0); for (size_t i = 0; i < d.size(); ++i) s += d[i] * o.d[i]; return s; }
+    T squaredNorm() const { return dot(*this); }
+    Matrix operator-(const Matrix& o) const { Matrix r = *this; for (size_t i = 0; i < d.size(); ++i) r.d[i] -= o.d[i]; return r; }
     T& operator()(int i, int j) { return d[i + (size_t)j * nr]; }
     const T& operator()(int i, int j) const { return d[i + (size_t)j * nr]; }
     T& operator[](int i) { return d[i]; }
@@ -334,6 +350,8 @@ struct Triplet {
 
 typedef Matrix<double, 1, 3> RowVector3d;
 typedef Matrix<double, 3, 1> Vector3d;
+typedef Matrix<double, Dynamic, 1> VectorXd;
+inline void setNbThreads(int) {}
 typedef Matrix<double, 3, 3> Matrix3d;
 
 template <class T, int N>
@@ -530,6 +548,13 @@ public:
         outer.swap(no); inner.swap(ni); vals.swap(nv);
         return *this;
     }
+    Matrix<T, Dynamic, 1> operator*(const Matrix<T, Dynamic, 1>& x) const // row-major product (CSR_MATRIX keeps RowMajor matrices)
+    {
+        Matrix<T, Dynamic, 1> y = Matrix<T, Dynamic, 1>::Zero(nr);
+        for (int r = 0; r < nr; ++r) { T s = T(0); for (int p = outer[r]; p < outer[r + 1]; ++p) s += vals[p] * x[inner[p]]; y[r] = s; }
+        return y;
+    }
+    T coeff(int i, int j) const { for (int p = outer[i]; p < outer[i + 1]; ++p) if (inner[p] == j) return vals[p]; return T(0); }
     class InnerIterator {
         SparseMatrix& m; int k, p;
     public:

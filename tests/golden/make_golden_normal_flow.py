@@ -3,8 +3,11 @@ Projects/FEMShell/12-14_normal_flow.py + Python/Drivers run from the writable mi
 `JGSL` module of this repository built with the REFERENCE's own CPU contact loops as its backend
 (tests/host_shim/jgsl_ref/JGSL.so: FEM/IPC.h + Grid/SPATIAL_HASH.h + Math/CSR_MATRIX.h + FEM/Shell/MEMBRANE.h + BENDING.h +
 FEM/FRICTION.h compiled from /root/reference).
-Stores the input mesh, counter.txt (PN iterations and contact # per time step, Shell/IMPLICIT_EULER.h:857-864) and the
-final vertex positions. The B200 build of the same module must reproduce the trace (tests/test_gpu_jgsl_module.py).
+With JGSL_REF_DRIVER=1 that build hands every time step to the REFERENCE's own Newton driver (tests/host_shim/libref_driver.so:
+Advance_One_Step_IE_Discrete_Shell + Line_Search of FEM/Shell/IMPLICIT_EULER.h, Compute_IncPotential* of INC_POTENTIAL.h), so the
+traces stored here are produced by the reference's scripts, driver and operators; only the storages, Eigen, the linear solver and
+the module's set-up functions are this repository's. Stores the input mesh, counter.txt (PN iterations and contact # per time
+step, Shell/IMPLICIT_EULER.h:857-864) and the final vertex positions. The B200 build of the same module must reproduce the trace (tests/test_gpu_jgsl_module.py).
 
 The same for BASELINE configs[1] (the animation-fix example, Projects/FEMShell/16_fix_char_seq.py, unchanged): membrane + hinge
 bending + inertia + barrier on wm2_15k following the first frames of Rumba_Dancing_unfixed -> fix_char_seq_trace.npz (the
@@ -57,14 +60,14 @@ def main():
     subprocess.check_call(["chmod", "-R", "u+w", cwd])
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     if which in ("seq", "all"):
-        fix_char_seq(cwd, dict(os.environ, PYTHONPATH=os.path.join(ROOT, "tests", "host_shim", "jgsl_ref"), OMP_NUM_THREADS="8"))
+        fix_char_seq(cwd, dict(os.environ, PYTHONPATH=os.path.join(ROOT, "tests", "host_shim", "jgsl_ref"), OMP_NUM_THREADS="8", JGSL_REF_DRIVER="1"))
     if which == "seq":
         return
     out = {}
     for mesh, smooth, mag, frames in CASES:
         folder = os.path.join(cwd, "output", "12-14_normal_flow", "%s_%s_%s_%s" % (mesh, smooth, mag, frames))
         subprocess.call(["rm", "-rf", folder])
-        env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "tests", "host_shim", "jgsl_ref"), OMP_NUM_THREADS="8")
+        env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "tests", "host_shim", "jgsl_ref"), OMP_NUM_THREADS="8", JGSL_REF_DRIVER="1")
         subprocess.check_call([sys.executable, "12-14_normal_flow.py", mesh, smooth, mag, frames], cwd=cwd, env=env, stdout=subprocess.DEVNULL)
         V, F = read_obj(os.path.join(cwd, "input", mesh + ".obj"))
         Vend, _ = read_obj(os.path.join(folder, "shell%s.obj" % frames))
@@ -83,6 +86,7 @@ def main():
     with tempfile.TemporaryDirectory() as tmp:
         obj = os.path.join(tmp, "hand.obj")
         write_obj(obj, out["hand/V"], out["hand/F"])
+        os.environ["JGSL_REF_DRIVER"] = "1"
         rc, log = run_own_driver(REFLOOPS_DIR, obj, "0.5", "5e-3", "3", os.path.join(tmp, "out"), mu=0.3, fric_iter=2)
         assert rc == 0, open(log).read()[-2000:]
         out["hand_friction/args"] = np.array(["0.5", "5e-3", "3", "0.3", "2"])

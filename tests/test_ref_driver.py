@@ -1,0 +1,58 @@
+"""The restated Newton driver (idp_b200/host/jgsl/shell_flow.h) against the REFERENCE's own driver.
+
+tests/host_shim/libref_driver.so is the reference's `Advance_One_Step_IE_Discrete_Shell` (FEM/Shell/IMPLICIT_EULER.h:151-891, with
+Line_Search, Compute_IncPotential / _Gradient / _Hessian of INC_POTENTIAL.h and every operator header they include) compiled in
+place from /root/reference against the stand-ins of oracle/ref_shim/include. The checker build of the module
+(tests/host_shim/jgsl_ref/JGSL.so) hands each time step to it when JGSL_REF_DRIVER is set; the golden traces in tests/golden were
+generated that way (tests/golden/make_golden_normal_flow.py). With the variable unset, the same build runs the restated driver on
+the same reference operators: both must give the same counter.txt (PN iterations and contact # per step) and end state.
+No GPU and no product code is involved here; this pins the host logic the B200 module shares with the checker build.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from jgsl_common import REFLOOPS_DIR, ROOT, TRACE, read_counter, read_obj, run_own_driver, write_obj
+
+HAVE = os.path.exists(os.path.join(REFLOOPS_DIR, "JGSL.so")) and os.path.exists(os.path.join(ROOT, "tests", "host_shim", "libref_driver.so"))
+pytestmark = pytest.mark.skipif(not HAVE, reason="reference driver / checker build absent (needs /root/reference)")
+
+
+def _run(tmp_path, name, ref_driver, mu=None, fric_iter=None):
+    z = np.load(TRACE)
+    obj = str(tmp_path / "hand.obj")
+    write_obj(obj, z["hand/V"], z["hand/F"])
+    smooth, mag, frames = z["hand/args"]
+    out = str(tmp_path / name)
+    old = os.environ.pop("JGSL_REF_DRIVER", None)
+    try:
+        if ref_driver:
+            os.environ["JGSL_REF_DRIVER"] = "1"
+        rc, log = run_own_driver(REFLOOPS_DIR, obj, smooth, mag, frames, out, mu=mu, fric_iter=fric_iter)
+    finally:
+        os.environ.pop("JGSL_REF_DRIVER", None)
+        if old is not None:
+            os.environ["JGSL_REF_DRIVER"] = old
+    assert rc == 0, open(log).read()[-2000:]
+    Vend, _ = read_obj(os.path.join(out, "shell%s.obj" % frames))
+    return read_counter(os.path.join(out, "counter.txt")), Vend, open(log).read()
+
+
+def test_reference_driver_reproduces_the_golden_trace(tmp_path):
+    """the golden really is the reference driver's output (regenerating it here gives the same bits)"""
+    z = np.load(TRACE)
+    counter, Vend, _ = _run(tmp_path, "ref", True)
+    assert np.array_equal(counter, z["hand/counter"]), (counter.tolist(), z["hand/counter"].tolist())
+    assert np.array_equal(Vend, z["hand/V_end"])
+
+
+def test_restated_driver_matches_reference_driver_with_friction(tmp_path):
+    """lagged friction (mu = 0.3, two friction iterations per step): restated driver == reference driver, row by row"""
+    z = np.load(TRACE)
+    mu, it = 0.3, 2
+    c_ref, V_ref, _ = _run(tmp_path, "ref", True, mu=mu, fric_iter=it)
+    c_own, V_own, _ = _run(tmp_path, "own", False, mu=mu, fric_iter=it)
+    assert np.array_equal(c_ref, z["hand_friction/counter"]), (c_ref.tolist(), z["hand_friction/counter"].tolist())
+    assert np.array_equal(c_own, c_ref), (c_own.tolist(), c_ref.tolist())
+    assert np.array_equal(V_own, V_ref) and np.array_equal(V_ref, z["hand_friction/V_end"])
