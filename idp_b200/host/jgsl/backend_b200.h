@@ -15,8 +15,8 @@ namespace jgsl {
 
 class B200Backend : public ContactBackend {
 public:
-    double pcg_rel_tol = 1e-10; // Solve_Direct is a factorisation in the reference; the iterative solve states its tolerance
-    int pcg_max_iter = 20000;
+    double pcg_rel_tol = 1e-12; // Solve_Direct is a factorisation in the reference: an ill-conditioned flow (batch.py's cat) follows it from the first step only below 1e-10
+    int pcg_max_iter = 200000; // the reference factorises, so the cap only bounds a broken system: ill-conditioned flows (batch.py's cat) need > 20,000
     long pcg_iters_total = 0, newton_solves = 0;
 
     explicit B200Backend(int device = 0)

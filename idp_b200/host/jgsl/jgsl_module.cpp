@@ -313,9 +313,9 @@ PYBIND11_MODULE(JGSL, m)
 #endif
             JGSL_BACKEND_CLASS& be = backend();
             // the linear solve is iterative where the reference factorises: its stopping rule is a parameter of this build
-            // (Set_Parameter("B200.pcg_rel_tol", 1e-10), Set_Parameter("B200.pcg_max_iter", 20000))
-            be.pcg_rel_tol = get_param<double>("B200.pcg_rel_tol", 1e-10);
-            be.pcg_max_iter = get_param<int>("B200.pcg_max_iter", 20000);
+            // (Set_Parameter("B200.pcg_rel_tol", 1e-12), Set_Parameter("B200.pcg_max_iter", 200000))
+            be.pcg_rel_tol = get_param<double>("B200.pcg_rel_tol", 1e-12);
+            be.pcg_max_iter = get_param<int>("B200.pcg_max_iter", 200000);
             const int it = advance_one_step_ie(be, in, Elem, seg, DBC, edgeStencil, edgeInfo, fiberStiffMult, kappa_s, b, kappaVec, X, nodeAttr, M, elemAttr,
                 elasticityAttr);
             fflush(stdout);

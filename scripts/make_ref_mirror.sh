@@ -10,7 +10,7 @@ DST=$HERE/baseline/_ref/IDP_mirror
 mkdir -p "$DST/Projects/FEMShell/input" "$DST/Python"
 cp "$REF"/Projects/FEMShell/*.py "$DST/Projects/FEMShell/"
 cp -r "$REF/Python/Drivers" "$DST/Python/"
-for m in bunny3K hand cat feline wm2_15k; do
+for m in bunny3K hand cat feline font_Tao wm2_15k; do
   [ -f "$REF/Projects/FEMShell/input/$m.obj" ] && cp "$REF/Projects/FEMShell/input/$m.obj" "$DST/Projects/FEMShell/input/"
 done
 # config 2 (16_fix_char_seq.py): rest mannequin + the first target frames of the Rumba sequence
@@ -19,5 +19,10 @@ for seq in Rumba_Dancing_unfixed; do
   for f in $(seq 0 ${MIRROR_FRAMES:-6}); do
     [ -f "$REF/Projects/FEMShell/input/$seq/$f.obj" ] && cp "$REF/Projects/FEMShell/input/$seq/$f.obj" "$DST/Projects/FEMShell/input/$seq/"
   done
+done
+# batch.py's second sequence: three target frames
+mkdir -p "$DST/Projects/FEMShell/input/Kick_unfixed"
+for f in 0 1 2 3; do
+  [ -f "$REF/Projects/FEMShell/input/Kick_unfixed/$f.obj" ] && cp "$REF/Projects/FEMShell/input/Kick_unfixed/$f.obj" "$DST/Projects/FEMShell/input/Kick_unfixed/"
 done
 echo "mirror at $DST"

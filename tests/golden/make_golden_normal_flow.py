@@ -14,7 +14,7 @@ bending + inertia + barrier on wm2_15k following the first frames of Rumba_Danci
 script asks for 180 frames; the mirror holds the first 6 targets, so the run ends -- like the reference would -- when frame 7
 cannot be read; the 6 completed steps are the trace).
 
-Run in the authoring container only (needs /root/reference):  python tests/golden/make_golden_normal_flow.py [flow|seq]
+Run in the authoring container only (needs /root/reference):  python tests/golden/make_golden_normal_flow.py [flow|seq|batch]
 """
 import os
 import subprocess
@@ -26,6 +26,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 MIRROR = os.path.join(ROOT, "baseline", "_ref", "IDP_mirror")
 CASES = [("bunny3K", "0.5", "-5e-3", "50"), ("hand", "0.5", "5e-3", "3")]  # batch.py:36-43 and :16-23
+# further lines of batch.py (:7-14 cat, :56-63 font_Tao, :46-53 feline, :97-101 second sequence) -> batch_lines_trace.npz
+BATCH_CASES = [("cat", "0.5", "5e-3", "10"), ("font_Tao", "0.5", "5e-3", "10"), ("feline", "1", "-5e-3", "50")]
 
 
 def read_obj(path):
@@ -38,19 +40,40 @@ def read_obj(path):
     return np.array(V, np.float64), np.array(F, np.int32)
 
 
-def fix_char_seq(cwd, env, n_frames=6):
-    folder = os.path.join(cwd, "output", "16_fix_char_seq")
+def fix_char_seq(cwd, env, n_frames=6, seq="Rumba_Dancing_unfixed", save=True):
+    # the script's output folder carries its arguments; without arguments it runs the Rumba sequence
+    args = [] if seq == "Rumba_Dancing_unfixed" else [seq]
+    folder = os.path.join(cwd, "output", "16_fix_char_seq", *args)
     subprocess.call(["rm", "-rf", folder])
-    subprocess.call([sys.executable, "16_fix_char_seq.py"], cwd=cwd, env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    subprocess.call([sys.executable, "16_fix_char_seq.py"] + args, cwd=cwd, env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     counter = np.array([[int(t) for t in l.split()] for l in open(os.path.join(folder, "counter.txt"))], np.int64)
     assert len(counter) == n_frames, counter
     V, F = read_obj(os.path.join(cwd, "input", "wm2_15k.obj"))
     out = {"rest/V": V, "rest/F": F, "counter": counter, "V_end": read_obj(os.path.join(folder, "shell%d.obj" % n_frames))[0],
            "V_start": read_obj(os.path.join(folder, "shell0.obj"))[0]}
     for f in range(1, n_frames + 1):
-        out["frame%d/V" % f] = read_obj(os.path.join(cwd, "input", "Rumba_Dancing_unfixed", "%d.obj" % f))[0]
-    print("fix_char_seq steps", len(counter), "PN iterations", counter[:, 0].sum(), "contact #", counter[:, 1].tolist())
-    np.savez_compressed(os.path.join(HERE, "fix_char_seq_trace.npz"), **out)
+        out["frame%d/V" % f] = read_obj(os.path.join(cwd, "input", seq, "%d.obj" % f))[0]
+    print("fix_char_seq", seq, "steps", len(counter), "PN iterations", counter[:, 0].sum(), "contact #", counter[:, 1].tolist())
+    if save:
+        np.savez_compressed(os.path.join(HERE, "fix_char_seq_trace.npz"), **out)
+    return out
+
+
+def normal_flow_case(cwd, out, mesh, smooth, mag, frames):
+    folder = os.path.join(cwd, "output", "12-14_normal_flow", "%s_%s_%s_%s" % (mesh, smooth, mag, frames))
+    if not (os.environ.get("GOLDEN_REUSE") and os.path.exists(os.path.join(folder, "shell%s.obj" % frames))):  # GOLDEN_REUSE=1: keep finished runs
+        subprocess.call(["rm", "-rf", folder])
+        env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "tests", "host_shim", "jgsl_ref"), OMP_NUM_THREADS="8", JGSL_REF_DRIVER="1")
+        subprocess.check_call([sys.executable, "12-14_normal_flow.py", mesh, smooth, mag, frames], cwd=cwd, env=env, stdout=subprocess.DEVNULL)
+    V, F = read_obj(os.path.join(cwd, "input", mesh + ".obj"))
+    Vend, _ = read_obj(os.path.join(folder, "shell%s.obj" % frames))
+    counter = np.array([[int(t) for t in l.split()] for l in open(os.path.join(folder, "counter.txt"))], np.int64)
+    out[mesh + "/V"] = V
+    out[mesh + "/F"] = F
+    out[mesh + "/args"] = np.array([smooth, mag, frames])
+    out[mesh + "/counter"] = counter
+    out[mesh + "/V_end"] = Vend
+    print(mesh, "steps", len(counter), "PN iterations", counter[:, 0].sum(), "last contact #", counter[-1, 1], flush=True)
 
 
 def main():
@@ -63,21 +86,20 @@ def main():
         fix_char_seq(cwd, dict(os.environ, PYTHONPATH=os.path.join(ROOT, "tests", "host_shim", "jgsl_ref"), OMP_NUM_THREADS="8", JGSL_REF_DRIVER="1"))
     if which == "seq":
         return
+    if which == "batch":
+        out = {}
+        for case in BATCH_CASES:
+            normal_flow_case(cwd, out, *case)
+        kick = fix_char_seq(cwd, dict(os.environ, PYTHONPATH=os.path.join(ROOT, "tests", "host_shim", "jgsl_ref"), OMP_NUM_THREADS="8", JGSL_REF_DRIVER="1"),
+                            n_frames=3, seq="Kick_unfixed", save=False)
+        for k, v in kick.items():
+            if not k.startswith("rest/"):  # the rest mannequin is in fix_char_seq_trace.npz already
+                out["kick/" + k] = v
+        np.savez_compressed(os.path.join(HERE, "batch_lines_trace.npz"), **out)
+        return
     out = {}
     for mesh, smooth, mag, frames in CASES:
-        folder = os.path.join(cwd, "output", "12-14_normal_flow", "%s_%s_%s_%s" % (mesh, smooth, mag, frames))
-        subprocess.call(["rm", "-rf", folder])
-        env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "tests", "host_shim", "jgsl_ref"), OMP_NUM_THREADS="8", JGSL_REF_DRIVER="1")
-        subprocess.check_call([sys.executable, "12-14_normal_flow.py", mesh, smooth, mag, frames], cwd=cwd, env=env, stdout=subprocess.DEVNULL)
-        V, F = read_obj(os.path.join(cwd, "input", mesh + ".obj"))
-        Vend, _ = read_obj(os.path.join(folder, "shell%s.obj" % frames))
-        counter = np.array([[int(t) for t in l.split()] for l in open(os.path.join(folder, "counter.txt"))], np.int64)
-        out[mesh + "/V"] = V
-        out[mesh + "/F"] = F
-        out[mesh + "/args"] = np.array([smooth, mag, frames])
-        out[mesh + "/counter"] = counter
-        out[mesh + "/V_end"] = Vend
-        print(mesh, "steps", len(counter), "PN iterations", counter[:, 0].sum(), "last contact #", counter[-1, 1])
+        normal_flow_case(cwd, out, mesh, smooth, mag, frames)
     # friction (mu = 0.3, two friction iterations): the paper scripts leave sim.mu at 0, so this case is driven by the repository's own
     # caller (tests/jgsl_driver/normal_flow.py, the same module calls with mu / fricIterAmt passed through) on the same checker build
     sys.path.insert(0, os.path.join(ROOT, "tests"))

@@ -18,6 +18,8 @@ def run(mesh_path, smooth, mag, frames, out, mu=0.0, fric_iter=1):
         out += "/"
     Kokkos_Initialize()
     Set_Parameter("Basic.log_folder", out)
+    if os.environ.get("IDP_PCG_REL_TOL"):  # experiments on the stopping rule of the device solve (the default is used otherwise)
+        Set_Parameter("B200.pcg_rel_tol", float(os.environ["IDP_PCG_REL_TOL"]))
     X, X0, Elem = Storage.V3dStorage(), Storage.V3dStorage(), Storage.V3iStorage()
     nodeAttr, massMatrix = Storage.V3dV3dV3dSdStorage(), CSR_MATRIX_D()
     elemAttr, elasticity = Storage.M2dM2dSdStorage(), FIXED_COROTATED_2.Create()
