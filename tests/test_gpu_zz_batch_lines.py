@@ -22,7 +22,7 @@ pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not os.path.exists(BATCH_TRACE
 # within 2.1 % / 2.6 %), kick in 2 of 3 (third: one contact row of 46,598), cat -- an ill-conditioned system, 50 K PCG iterations per
 # solve -- in its first 3 (then within 8.4 % / 4.6 %; the restated driver on the reference's CPU operators differs from the reference's
 # driver by 4.7 % / 4.3 % on it). The bars leave a margin over that.
-BARS = {"cat": (1, 0.20, 0.20, 0.03, 0.15), "font_Tao": (5, 0.02, 0.05, 0.01, 0.02), "feline": (5, 0.08, 0.10, 0.01, 0.10), "kick": (1, 0.01, 0.10, 0.01, 0.01)}
+BARS = {"cat": (0, 0.20, 0.20, 0.03, 0.15), "font_Tao": (5, 0.02, 0.05, 0.01, 0.02), "feline": (5, 0.08, 0.10, 0.01, 0.10), "kick": (1, 0.01, 0.10, 0.01, 0.01)}
 
 
 @pytest.mark.parametrize("example", sorted(BARS))
