@@ -117,9 +117,23 @@ double refipc_min_dist2(int nV, const double* x, int n, const int* rows4, double
 // Lagged friction (FEM/FRICTION.h:17-662): Compute_Friction_Basis at xb with the contact rows, then potential / gradient /
 // Hessian triplets at x relative to xn. Outputs: the friction rows (the non-mollified contact rows, in order), closest-point
 // parameters (2 per row), tangent bases (6 per row, column major 3x2), normal forces; E (added), g (nV x 3, added), triplets.
+long refipc_friction_comp(int nV, const double* xb, const double* x, const double* xn, int n, const int* rows4, const double* w, double dHat2, double kappa,
+    double thickness, double epsvh2, double mu, int projectSPD, int* nFric, int* fricRows4, double* closest2, double* basis6, double* normalForce,
+    double* E, double* g, long cap, int* trow, int* tcol, double* tval, int nComp, const int* compNodeRange, const double* muComp);
+
 long refipc_friction(int nV, const double* xb, const double* x, const double* xn, int n, const int* rows4, const double* w, double dHat2, double kappa,
     double thickness, double epsvh2, double mu, int projectSPD, int* nFric, int* fricRows4, double* closest2, double* basis6, double* normalForce,
     double* E, double* g, long cap, int* trow, int* tcol, double* tval)
+{
+    return refipc_friction_comp(nV, xb, x, xn, n, rows4, w, dHat2, kappa, thickness, epsvh2, mu, projectSPD, nFric, fricRows4, closest2, basis6, normalForce, E, g,
+        cap, trow, tcol, tval, 0, nullptr, nullptr);
+}
+
+// the same with per-component coefficients: Compute_Friction_Coef (FRICTION.h:126-170) scales the normal forces right after the basis,
+// as the time step does (Shell/IMPLICIT_EULER.h:435-438); it sets mu to 1
+long refipc_friction_comp(int nV, const double* xb, const double* x, const double* xn, int n, const int* rows4, const double* w, double dHat2, double kappa,
+    double thickness, double epsvh2, double mu, int projectSPD, int* nFric, int* fricRows4, double* closest2, double* basis6, double* normalForce,
+    double* E, double* g, long cap, int* trow, int* tcol, double* tval, int nComp, const int* compNodeRange, const double* muComp)
 {
     Scene sb(nV, xb, nullptr, 0, nullptr, 0, nullptr, 0, nullptr, nullptr);
     std::vector<VECTOR<int, 4>> cs, fcs;
@@ -130,6 +144,11 @@ long refipc_friction(int nV, const double* xb, const double* x, const double* xn
     std::vector<T> nf;
     T kap[3] = {kappa, kappa, kappa};
     Compute_Friction_Basis<T, 3, false>(sb.X, cs, info, fcs, cp, tb, nf, dHat2, kap, thickness);
+    if (nComp > 0) {
+        std::vector<int> range(compNodeRange, compNodeRange + nComp);
+        std::vector<T> mc(muComp, muComp + (size_t)nComp * nComp);
+        Compute_Friction_Coef<T, 3>(fcs, range, mc, nf, mu);
+    }
     *nFric = (int)fcs.size();
     for (size_t i = 0; i < fcs.size(); ++i) {
         for (int k = 0; k < 4; ++k) fricRows4[4 * i + k] = fcs[i][k];

@@ -14,7 +14,7 @@ bending + inertia + barrier on wm2_15k following the first frames of Rumba_Danci
 script asks for 180 frames; the mirror holds the first 6 targets, so the run ends -- like the reference would -- when frame 7
 cannot be read; the 6 completed steps are the trace).
 
-Run in the authoring container only (needs /root/reference):  python tests/golden/make_golden_normal_flow.py [flow|seq|batch]
+Run in the authoring container only (needs /root/reference):  python tests/golden/make_golden_normal_flow.py [flow|seq|batch|components]
 """
 import os
 import subprocess
@@ -76,6 +76,33 @@ def normal_flow_case(cwd, out, mesh, smooth, mag, frames):
     print(mesh, "steps", len(counter), "PN iterations", counter[:, 0].sum(), "last contact #", counter[-1, 1], flush=True)
 
 
+def two_shells_friction():
+    """Lagged friction with one coefficient per pair of components (muComp, Shell/IMPLICIT_EULER.h:435-438): two nested geodesic
+    spheres (2,004 vertices), the outer one with inward normals so that the flow presses them together; mu = 0.1 inside a
+    component, 0.6 between the two; the reference's driver and operators through tests/jgsl_driver/two_shells.py."""
+    import tempfile
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from idp_b200 import meshgen
+    from jgsl_common import REFLOOPS_DIR, read_counter, write_obj
+    mesh, _ = meshgen.nested_icospheres(nu=10, gap=5e-3, jitter=1e-4)
+    F = np.ascontiguousarray(mesh.btri[:, :3], np.int32)
+    n1, half = mesh.nV // 2, len(F) // 2
+    out = {"inner/V": mesh.X[:n1], "inner/F": F[:half], "outer/V": mesh.X[n1:], "outer/F": np.ascontiguousarray(F[half:, ::-1] - n1),
+           "args": np.array(["0.5", "4e-3", "4", "0.1", "0.6", "2"])}  # smooth, magnitude, frames, mu same / cross component, friction iterations
+    with tempfile.TemporaryDirectory() as tmp:
+        for k in ("inner", "outer"):
+            write_obj(os.path.join(tmp, k + ".obj"), out[k + "/V"], out[k + "/F"])
+        env = dict(os.environ, PYTHONPATH=REFLOOPS_DIR, OMP_NUM_THREADS="8", JGSL_REF_DRIVER="1")
+        log = subprocess.check_output([sys.executable, os.path.join(ROOT, "tests", "jgsl_driver", "two_shells.py"), os.path.join(tmp, "inner.obj"),
+                                       os.path.join(tmp, "outer.obj")] + list(out["args"][:3]) + [os.path.join(tmp, "out")] + list(out["args"][3:]), env=env).decode()
+        out["counter"] = read_counter(os.path.join(tmp, "out", "counter.txt"))
+        out["V_end"] = read_obj(os.path.join(tmp, "out", "shell4.obj"))[0]
+        out["friction_updates"] = np.array(log.count("friction updated Newton res"))
+    print("two shells with per-component friction", out["counter"].tolist(), "friction updates", int(out["friction_updates"]))
+    np.savez_compressed(os.path.join(HERE, "two_shells_friction_trace.npz"), **out)
+
+
 def main():
     subprocess.check_call([os.path.join(ROOT, "scripts", "make_ref_mirror.sh")])
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "host_shim"), "jgsl_ref/JGSL.so"])
@@ -85,6 +112,9 @@ def main():
     if which in ("seq", "all"):
         fix_char_seq(cwd, dict(os.environ, PYTHONPATH=os.path.join(ROOT, "tests", "host_shim", "jgsl_ref"), OMP_NUM_THREADS="8", JGSL_REF_DRIVER="1"))
     if which == "seq":
+        return
+    if which == "components":
+        two_shells_friction()
         return
     if which == "batch":
         out = {}

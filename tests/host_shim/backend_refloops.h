@@ -29,6 +29,9 @@ long refshell_hinges(int nV, const double* x, int nH, const int* stencil4, const
 long refipc_friction(int nV, const double* xb, const double* x, const double* xn, int n, const int* rows4, const double* w, double dHat2, double kappa,
     double thickness, double epsvh2, double mu, int projectSPD, int* nFric, int* fricRows4, double* closest2, double* basis6, double* normalForce,
     double* E, double* g, long cap, int* trow, int* tcol, double* tval);
+long refipc_friction_comp(int nV, const double* xb, const double* x, const double* xn, int n, const int* rows4, const double* w, double dHat2, double kappa,
+    double thickness, double epsvh2, double mu, int projectSPD, int* nFric, int* fricRows4, double* closest2, double* basis6, double* normalForce,
+    double* E, double* g, long cap, int* trow, int* tcol, double* tval, int nComp, const int* compNodeRange, const double* muComp);
 long ref_csr_system(int n, long nT, const int* r, const int* c, const double* v, const double* mdiag, const unsigned char* dbc, int dim,
     int* ptr, int* col, double* val, long cap);
 }
@@ -231,18 +234,15 @@ public:
         const bool ev = (E || g || tr) && fMu_ > 0;
         const long cap = tr ? 144 * (long)n : 0;
         if (tr) { tr->resize((size_t)cap); tc->resize((size_t)cap); tv->resize((size_t)cap); }
-        const long nt = refipc_friction(nV_, fXb_.data(), ev ? x_.data() : nullptr, ev ? fXn_.data() : nullptr, n, fRows_.data(), w.data(), fDHat2_, fKappa_, fXi_, fEps_,
-            fMu_, 1, &nf, fr.data(), cp.data(), bs.data(), lam.data(), E, g, cap, tr ? tr->data() : nullptr, tr ? tc->data() : nullptr, tr ? tv->data() : nullptr);
+        const long nt = refipc_friction_comp(nV_, fXb_.data(), ev ? x_.data() : nullptr, ev ? fXn_.data() : nullptr, n, fRows_.data(), w.data(), fDHat2_, fKappa_, fXi_, fEps_,
+            fMu_, 1, &nf, fr.data(), cp.data(), bs.data(), lam.data(), E, g, cap, tr ? tr->data() : nullptr, tr ? tc->data() : nullptr, tr ? tv->data() : nullptr,
+            (int)fComp_.size(), fComp_.data(), fMuComp_.data());
         if (tr) { tr->resize((size_t)nt); tc->resize((size_t)nt); tv->resize((size_t)nt); }
         return nf;
     }
     void friction_set_components(const std::vector<int>& compNodeRange, const std::vector<double>& muComp) override
     {
-        if (!compNodeRange.empty()) { // the stateless reference entry point evaluates with unit coefficients only
-            printf("reference-loops backend: per-component friction coefficients are checked at the operator level (tests/test_friction.py)\n");
-            exit(-1);
-        }
-        (void)muComp;
+        fComp_ = compNodeRange; fMuComp_ = muComp; // Compute_Friction_Coef runs right after the basis inside refipc_friction_comp
     }
     void friction_energy(double& E) override { if (fMu_ > 0) friction_call(&E, nullptr, nullptr, nullptr, nullptr); }
     void friction_gradient(double* g) override { if (fMu_ > 0) friction_call(nullptr, g, nullptr, nullptr, nullptr); }
@@ -276,7 +276,8 @@ private:
     std::vector<double> mIB_, mVol_, mLam_, mMu_, hInfo_;
     double hK_ = 0, eH_ = 0;
     std::vector<int> fRows_;
-    std::vector<double> fInfo_, fXb_, fXn_;
+    std::vector<double> fInfo_, fXb_, fXn_, fMuComp_;
+    std::vector<int> fComp_;
     double fDHat2_ = 0, fKappa_ = 0, fXi_ = 0, fMu_ = 0, fEps_ = 0;
     std::vector<uint8_t> dbc_;
     std::vector<double> x_, x0_, vol_, mass_, info_;

@@ -13,6 +13,8 @@ MIRROR = os.path.join(ROOT, "baseline", "_ref", "IDP_mirror", "Projects", "FEMSh
 TRACE = os.path.join(ROOT, "tests", "golden", "normal_flow_trace.npz")
 SEQ_TRACE = os.path.join(ROOT, "tests", "golden", "fix_char_seq_trace.npz")
 SEQ_DRIVER = os.path.join(ROOT, "tests", "jgsl_driver", "fix_char_seq.py")
+TWO_SHELLS_DRIVER = os.path.join(ROOT, "tests", "jgsl_driver", "two_shells.py")
+TWO_SHELLS_TRACE = os.path.join(ROOT, "tests", "golden", "two_shells_friction_trace.npz")
 
 
 def build_product():
@@ -52,6 +54,26 @@ def run_own_driver(module_dir, mesh_obj, smooth, mag, frames, out, threads="8", 
         rc = subprocess.call([sys.executable, DRIVER, mesh_obj, str(smooth), str(mag), str(frames), out] + ([str(mu)] if mu is not None else []) + ([str(fric_iter)] if fric_iter is not None else []), env=env,
                              stdout=lf, stderr=subprocess.STDOUT, timeout=timeout)
     return rc, log
+
+
+def run_two_shells(module_dir, folder, z, out, threads="8", timeout=3000, ref_driver=False):
+    """tests/jgsl_driver/two_shells.py on the fixture z (tests/golden/two_shells_friction_trace.npz) -> (rc, log text, counter, end positions)"""
+    os.makedirs(out, exist_ok=True)
+    for k in ("inner", "outer"):
+        write_obj(os.path.join(folder, k + ".obj"), z[k + "/V"], z[k + "/F"])
+    a = [str(t) for t in z["args"]]
+    env = dict(os.environ, PYTHONPATH=module_dir, OMP_NUM_THREADS=threads)
+    env.pop("JGSL_REF_DRIVER", None)
+    if ref_driver:
+        env["JGSL_REF_DRIVER"] = "1"
+    log = os.path.join(out, "log.txt")
+    with open(log, "w") as lf:
+        rc = subprocess.call([sys.executable, TWO_SHELLS_DRIVER, os.path.join(folder, "inner.obj"), os.path.join(folder, "outer.obj")] + a[:3] + [out] + a[3:],
+                             env=env, stdout=lf, stderr=subprocess.STDOUT, timeout=timeout)
+    text = open(log).read()
+    if rc != 0:
+        return rc, text, None, None
+    return rc, text, read_counter(os.path.join(out, "counter.txt")), read_obj(os.path.join(out, "shell%s.obj" % a[2]))[0]
 
 
 def write_sequence(folder, z):

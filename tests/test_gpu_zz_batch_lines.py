@@ -7,13 +7,14 @@ compared exactly and the rest within a few percent; every run stays intersection
 import os
 import sys
 
+import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "scripts"))
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from jgsl_batch_lines import BATCH_TRACE, run_example  # noqa: E402
-from jgsl_common import build_product  # noqa: E402
+from jgsl_common import PRODUCT_DIR, TWO_SHELLS_TRACE, build_product, run_two_shells  # noqa: E402
 
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not os.path.exists(BATCH_TRACE), reason="batch_lines_trace.npz absent")]
 
@@ -37,3 +38,25 @@ def test_b200_module_batch_line(tmp_path, example):
     assert abs(r["pn_iterations"] - r["golden_pn_iterations"]) <= rel_iters * r["golden_pn_iterations"], r
     assert r["median_dev_over_moved"] <= med and r["p99_dev_over_moved"] <= p99, r
     assert r["min_minDist2"] is not None and r["min_minDist2"] > 0, r
+
+
+@pytest.mark.skipif(not os.path.exists(TWO_SHELLS_TRACE), reason="two_shells_friction_trace.npz absent")
+def test_b200_module_component_friction(tmp_path):
+    """Two shells pressed together by the flow, lagged friction with the muComp table (0.1 inside a component, 0.6 across): the device
+    path (idp_friction_set_components) against the trace of the reference's own driver and FRICTION.h. 18 K contact rows from the
+    second step on; bars as for the single-component friction test."""
+    build_product()
+    z = np.load(TWO_SHELLS_TRACE)
+    rc, text, counter, Vend = run_two_shells(PRODUCT_DIR, str(tmp_path), z, str(tmp_path / "out"))
+    assert rc == 0, text[-3000:]
+    assert "(B200 backend)" in text and "linear solve (device PCG)" in text
+    g = z["counter"]
+    assert counter.shape == g.shape and np.array_equal(counter[:2], g[:2]), (counter.tolist(), g.tolist())
+    assert np.all(np.abs(counter[:, 1] - g[:, 1]) <= 0.03 * np.maximum(g[:, 1], 50)) and np.all(np.abs(counter[:, 0] - g[:, 0]) <= 3), (counter.tolist(), g.tolist())
+    assert text.count("friction updated Newton res") >= 1
+    V0 = np.concatenate([z["inner/V"], z["outer/V"]])
+    moved = np.median(np.linalg.norm(z["V_end"] - V0, axis=1))
+    dev = np.linalg.norm(Vend - z["V_end"], axis=1)
+    assert np.median(dev) <= 0.01 * moved and np.quantile(dev, 0.99) <= 0.05 * moved, (np.median(dev), np.quantile(dev, 0.99), moved)
+    mins = [float(l.split()[2].rstrip(",")) for l in text.splitlines() if l.startswith("minDist2 =")]
+    assert mins and min(mins) > 0

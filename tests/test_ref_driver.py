@@ -13,7 +13,7 @@ import os
 import numpy as np
 import pytest
 
-from jgsl_common import REFLOOPS_DIR, ROOT, TRACE, read_counter, read_obj, run_own_driver, write_obj
+from jgsl_common import REFLOOPS_DIR, ROOT, TRACE, TWO_SHELLS_TRACE, read_counter, read_obj, run_own_driver, run_two_shells, write_obj
 
 HAVE = os.path.exists(os.path.join(REFLOOPS_DIR, "JGSL.so")) and os.path.exists(os.path.join(ROOT, "tests", "host_shim", "libref_driver.so"))
 pytestmark = pytest.mark.skipif(not HAVE, reason="reference driver / checker build absent (needs /root/reference)")
@@ -56,3 +56,15 @@ def test_restated_driver_matches_reference_driver_with_friction(tmp_path):
     assert np.array_equal(c_ref, z["hand_friction/counter"]), (c_ref.tolist(), z["hand_friction/counter"].tolist())
     assert np.array_equal(c_own, c_ref), (c_own.tolist(), c_ref.tolist())
     assert np.array_equal(V_own, V_ref) and np.array_equal(V_ref, z["hand_friction/V_end"])
+
+
+def test_restated_driver_matches_reference_driver_with_component_friction(tmp_path):
+    """two components, one friction coefficient per pair of components (muComp table -> Compute_Friction_Coef, mu = 1,
+    IMPLICIT_EULER.h:435-438): the golden is the reference driver's run; the restated driver on the reference's FRICTION.h gives the
+    same rows, and the end state to the digits the obj files carry"""
+    z = np.load(TWO_SHELLS_TRACE)
+    rc, text, counter, Vend = run_two_shells(REFLOOPS_DIR, str(tmp_path), z, str(tmp_path / "own"))
+    assert rc == 0, text[-2000:]
+    assert np.array_equal(counter, z["counter"]), (counter.tolist(), z["counter"].tolist())
+    assert text.count("friction updated Newton res") == int(z["friction_updates"]) > 0
+    assert np.abs(Vend - z["V_end"]).max() <= 1e-10
