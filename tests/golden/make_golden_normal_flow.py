@@ -14,7 +14,7 @@ bending + inertia + barrier on wm2_15k following the first frames of Rumba_Danci
 script asks for 180 frames; the mirror holds the first 6 targets, so the run ends -- like the reference would -- when frame 7
 cannot be read; the 6 completed steps are the trace).
 
-Run in the authoring container only (needs /root/reference):  python tests/golden/make_golden_normal_flow.py [flow|seq|batch|components]
+Run in the authoring container only (needs /root/reference):  python tests/golden/make_golden_normal_flow.py [flow|seq|batch|components|cloth]
 """
 import os
 import subprocess
@@ -103,6 +103,33 @@ def two_shells_friction():
     np.savez_compressed(os.path.join(HERE, "two_shells_friction_trace.npz"), **out)
 
 
+def cloth_on_ball():
+    """A 441-vertex cloth falling under gravity onto a 252-vertex ball that is a moving Dirichlet body, friction 0.3, 12 steps of
+    Advance_One_Step_IE_Hinge through the reference's unchanged Python/Drivers (tests/jgsl_driver/cloth_on_ball.py) and the
+    reference's own Newton driver and operators."""
+    import tempfile
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from idp_b200 import meshgen
+    from jgsl_common import REFLOOPS_DIR, run_cloth_on_ball
+    n = 20
+    g = np.linspace(-0.5, 0.5, n + 1)
+    xx, zz = np.meshgrid(g, g, indexing="ij")
+    V = np.stack([xx.ravel(), 0.30 + 1e-3 * np.random.default_rng(5).standard_normal(xx.size), zz.ravel()], 1)
+    idx = np.arange((n + 1) ** 2).reshape(n + 1, n + 1)
+    t1 = np.stack([idx[:-1, :-1], idx[:-1, 1:], idx[1:, :-1]], -1).reshape(-1, 3)
+    t2 = np.stack([idx[1:, 1:], idx[1:, :-1], idx[:-1, 1:]], -1).reshape(-1, 3)
+    Vb, Fb = meshgen.icosphere(5, 0.25)
+    out = {"cloth/V": V, "cloth/F": np.concatenate([t1, t2]).astype(np.int32), "ball/V": Vb, "ball/F": np.ascontiguousarray(Fb[:, :3], np.int32),
+           "args": np.array(["12", "0.3"])}  # frames, mu
+    with tempfile.TemporaryDirectory() as tmp:
+        rc, text, counter, Vend = run_cloth_on_ball(REFLOOPS_DIR, tmp, out, ref_driver=True)
+        assert rc == 0, text[-2000:]
+    out["counter"], out["V_end"], out["friction_updates"] = counter, Vend, np.array(text.count("friction updated Newton res"))
+    print("cloth on ball", counter.tolist(), "friction updates", int(out["friction_updates"]))
+    np.savez_compressed(os.path.join(HERE, "cloth_on_ball_trace.npz"), **out)
+
+
 def main():
     subprocess.check_call([os.path.join(ROOT, "scripts", "make_ref_mirror.sh")])
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "host_shim"), "jgsl_ref/JGSL.so"])
@@ -115,6 +142,9 @@ def main():
         return
     if which == "components":
         two_shells_friction()
+        return
+    if which == "cloth":
+        cloth_on_ball()
         return
     if which == "batch":
         out = {}

@@ -13,6 +13,9 @@ MIRROR = os.path.join(ROOT, "baseline", "_ref", "IDP_mirror", "Projects", "FEMSh
 TRACE = os.path.join(ROOT, "tests", "golden", "normal_flow_trace.npz")
 SEQ_TRACE = os.path.join(ROOT, "tests", "golden", "fix_char_seq_trace.npz")
 SEQ_DRIVER = os.path.join(ROOT, "tests", "jgsl_driver", "fix_char_seq.py")
+CLOTH_DRIVER = os.path.join(ROOT, "tests", "jgsl_driver", "cloth_on_ball.py")
+CLOTH_TRACE = os.path.join(ROOT, "tests", "golden", "cloth_on_ball_trace.npz")
+MIRROR_PYTHON = os.path.join(ROOT, "baseline", "_ref", "IDP_mirror", "Python")
 TWO_SHELLS_DRIVER = os.path.join(ROOT, "tests", "jgsl_driver", "two_shells.py")
 TWO_SHELLS_TRACE = os.path.join(ROOT, "tests", "golden", "two_shells_friction_trace.npz")
 
@@ -74,6 +77,28 @@ def run_two_shells(module_dir, folder, z, out, threads="8", timeout=3000, ref_dr
     if rc != 0:
         return rc, text, None, None
     return rc, text, read_counter(os.path.join(out, "counter.txt")), read_obj(os.path.join(out, "shell%s.obj" % a[2]))[0]
+
+
+def run_cloth_on_ball(module_dir, folder, z, threads="8", timeout=3000, ref_driver=False):
+    """tests/jgsl_driver/cloth_on_ball.py (the reference's unchanged Python/Drivers from the mirror) on the fixture z, working
+    directory `folder` -> (rc, log text, counter, end positions)"""
+    os.makedirs(folder, exist_ok=True)
+    for k in ("cloth", "ball"):
+        write_obj(os.path.join(folder, k + ".obj"), z[k + "/V"], z[k + "/F"])
+    frames, mu = [str(t) for t in z["args"]]
+    env = dict(os.environ, PYTHONPATH=module_dir, OMP_NUM_THREADS=threads)
+    env.pop("JGSL_REF_DRIVER", None)
+    if ref_driver:
+        env["JGSL_REF_DRIVER"] = "1"
+    log = os.path.join(folder, "log.txt")
+    with open(log, "w") as lf:
+        rc = subprocess.call([sys.executable, CLOTH_DRIVER, MIRROR_PYTHON, os.path.join(folder, "cloth.obj"), os.path.join(folder, "ball.obj"), frames, mu],
+                             cwd=folder, env=env, stdout=lf, stderr=subprocess.STDOUT, timeout=timeout)
+    text = open(log).read()
+    out = os.path.join(folder, "output", "cloth_on_ball", "run")
+    if rc != 0:
+        return rc, text, None, None
+    return rc, text, read_counter(os.path.join(out, "counter.txt")), read_obj(os.path.join(out, "shell%s.obj" % frames))[0]
 
 
 def write_sequence(folder, z):

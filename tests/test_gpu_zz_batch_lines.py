@@ -3,7 +3,8 @@
 animation-fix sequence (16_fix_char_seq.py Kick_unfixed) -- against tests/golden/batch_lines_trace.npz, the traces of the
 reference's unchanged scripts on the reference's own Newton driver and CPU operators (tests/golden/make_golden_normal_flow.py
 batch). Same kind of bar as tests/test_gpu_jgsl_module.py: the flow is chaotic in the last bits, so the leading steps are
-compared exactly and the rest within a few percent; every run stays intersection free."""
+compared exactly and the rest within a few percent; every run stays intersection free. Two further scenes whose goldens come from the
+reference's own driver: per-component friction (two shells, muComp table) and a cloth falling onto a moving Dirichlet ball."""
 import os
 import sys
 
@@ -14,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "scripts"))
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from jgsl_batch_lines import BATCH_TRACE, run_example  # noqa: E402
-from jgsl_common import PRODUCT_DIR, TWO_SHELLS_TRACE, build_product, run_two_shells  # noqa: E402
+from jgsl_common import CLOTH_TRACE, MIRROR_PYTHON, PRODUCT_DIR, TWO_SHELLS_TRACE, build_product, run_cloth_on_ball, run_two_shells  # noqa: E402
 
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not os.path.exists(BATCH_TRACE), reason="batch_lines_trace.npz absent")]
 
@@ -57,6 +58,29 @@ def test_b200_module_component_friction(tmp_path):
     V0 = np.concatenate([z["inner/V"], z["outer/V"]])
     moved = np.median(np.linalg.norm(z["V_end"] - V0, axis=1))
     dev = np.linalg.norm(Vend - z["V_end"], axis=1)
+    assert np.median(dev) <= 0.01 * moved and np.quantile(dev, 0.99) <= 0.05 * moved, (np.median(dev), np.quantile(dev, 0.99), moved)
+    mins = [float(l.split()[2].rstrip(",")) for l in text.splitlines() if l.startswith("minDist2 =")]
+    assert mins and min(mins) > 0
+
+
+@pytest.mark.skipif(not (os.path.exists(CLOTH_TRACE) and os.path.isdir(MIRROR_PYTHON)), reason="fixture / mirror of the reference's Python/Drivers absent")
+def test_b200_module_cloth_on_ball(tmp_path):
+    """The hinge time step beyond the paper scripts (gravity, a moving Dirichlet body, friction 0.3; the reference's unchanged
+    Python/Drivers): B200 module against the trace of the reference's own driver and operators. A small, well-conditioned scene:
+    contact counts and PN iterations per step equal or next to equal."""
+    build_product()
+    z = np.load(CLOTH_TRACE)
+    rc, text, counter, Vend = run_cloth_on_ball(PRODUCT_DIR, str(tmp_path), z)
+    assert rc == 0, text[-3000:]
+    assert "(B200 backend)" in text and "linear solve (device PCG)" in text
+    g = z["counter"]
+    assert counter.shape == g.shape and np.array_equal(counter[:6], g[:6]), (counter.tolist(), g.tolist())
+    assert np.all(np.abs(counter[:, 1] - g[:, 1]) <= np.maximum(3, 0.05 * g[:, 1])) and np.all(np.abs(counter[:, 0] - g[:, 0]) <= 3), (counter.tolist(), g.tolist())
+    n_cloth = len(z["cloth/V"])
+    V0 = np.concatenate([z["cloth/V"], z["ball/V"]])
+    moved = np.median(np.linalg.norm(z["V_end"] - V0, axis=1))
+    dev = np.linalg.norm(Vend - z["V_end"], axis=1)
+    assert np.abs(Vend[n_cloth:] - z["V_end"][n_cloth:]).max() <= 1e-12  # the scripted ball
     assert np.median(dev) <= 0.01 * moved and np.quantile(dev, 0.99) <= 0.05 * moved, (np.median(dev), np.quantile(dev, 0.99), moved)
     mins = [float(l.split()[2].rstrip(",")) for l in text.splitlines() if l.startswith("minDist2 =")]
     assert mins and min(mins) > 0

@@ -13,7 +13,8 @@ import os
 import numpy as np
 import pytest
 
-from jgsl_common import REFLOOPS_DIR, ROOT, TRACE, TWO_SHELLS_TRACE, read_counter, read_obj, run_own_driver, run_two_shells, write_obj
+from jgsl_common import (CLOTH_TRACE, MIRROR_PYTHON, REFLOOPS_DIR, ROOT, TRACE, TWO_SHELLS_TRACE, read_counter, read_obj, run_cloth_on_ball, run_own_driver,
+                         run_two_shells, write_obj)
 
 HAVE = os.path.exists(os.path.join(REFLOOPS_DIR, "JGSL.so")) and os.path.exists(os.path.join(ROOT, "tests", "host_shim", "libref_driver.so"))
 pytestmark = pytest.mark.skipif(not HAVE, reason="reference driver / checker build absent (needs /root/reference)")
@@ -68,3 +69,16 @@ def test_restated_driver_matches_reference_driver_with_component_friction(tmp_pa
     assert np.array_equal(counter, z["counter"]), (counter.tolist(), z["counter"].tolist())
     assert text.count("friction updated Newton res") == int(z["friction_updates"]) > 0
     assert np.abs(Vend - z["V_end"]).max() <= 1e-10
+
+
+@pytest.mark.skipif(not os.path.isdir(MIRROR_PYTHON), reason="mirror of the reference's Python/Drivers absent (scripts/make_ref_mirror.sh)")
+def test_restated_driver_matches_reference_driver_on_cloth_on_ball(tmp_path):
+    """Advance_One_Step_IE_Hinge beyond the paper scripts: gravity, a Dirichlet subset moving with a velocity (Step_Dirichlet every
+    step, the ball), membrane + bending + inertia, friction in the elastic step; scene driven by the reference's unchanged
+    Python/Drivers. The golden is the reference driver's run: the restated driver gives the same rows and the same end state bits."""
+    z = np.load(CLOTH_TRACE)
+    rc, text, counter, Vend = run_cloth_on_ball(REFLOOPS_DIR, str(tmp_path), z)
+    assert rc == 0, text[-2000:]
+    assert np.array_equal(counter, z["counter"]), (counter.tolist(), z["counter"].tolist())
+    assert counter[-1, 1] > 0 and text.count("friction updated Newton res") == int(z["friction_updates"])
+    assert np.array_equal(Vend, z["V_end"])
