@@ -9,11 +9,14 @@ the same reference operators: both must give the same counter.txt (PN iterations
 No GPU and no product code is involved here; this pins the host logic the B200 module shares with the checker build.
 """
 import os
+import re
+import subprocess
+import sys
 
 import numpy as np
 import pytest
 
-from jgsl_common import (CLOTH_TRACE, MIRROR_PYTHON, REFLOOPS_DIR, ROOT, TRACE, TWO_SHELLS_TRACE, read_counter, read_obj, run_cloth_on_ball, run_own_driver,
+from jgsl_common import (CLOTH_DRIVER, CLOTH_TRACE, MIRROR_PYTHON, REFLOOPS_DIR, ROOT, TRACE, TWO_SHELLS_TRACE, read_counter, read_obj, run_cloth_on_ball, run_own_driver,
                          run_two_shells, write_obj)
 
 HAVE = os.path.exists(os.path.join(REFLOOPS_DIR, "JGSL.so")) and os.path.exists(os.path.join(ROOT, "tests", "host_shim", "libref_driver.so"))
@@ -82,3 +85,54 @@ def test_restated_driver_matches_reference_driver_on_cloth_on_ball(tmp_path):
     assert np.array_equal(counter, z["counter"]), (counter.tolist(), z["counter"].tolist())
     assert counter[-1, 1] > 0 and text.count("friction updated Newton res") == int(z["friction_updates"])
     assert np.array_equal(Vend, z["V_end"])
+
+
+def _squeeze_log(folder, z, ref_driver, seconds):
+    """cloth_on_ball.py with the fixed plate above the cloth, stopped after `seconds` (the squeezed step does not end)"""
+    os.makedirs(folder, exist_ok=True)
+    for k in ("cloth", "ball"):
+        write_obj(os.path.join(folder, k + ".obj"), z[k + "/V"], z[k + "/F"])
+    n = 6
+    g = np.linspace(-0.3, 0.3, n + 1)
+    xx, zz = np.meshgrid(g, g, indexing="ij")
+    idx = np.arange((n + 1) ** 2).reshape(n + 1, n + 1)
+    F = np.concatenate([np.stack([idx[:-1, :-1], idx[:-1, 1:], idx[1:, :-1]], -1).reshape(-1, 3), np.stack([idx[1:, 1:], idx[1:, :-1], idx[:-1, 1:]], -1).reshape(-1, 3)])
+    write_obj(os.path.join(folder, "plate.obj"), np.stack([xx.ravel(), np.full(xx.size, 0.33), zz.ravel()], 1), F)
+    env = dict(os.environ, PYTHONPATH=REFLOOPS_DIR, OMP_NUM_THREADS="8")
+    env.pop("JGSL_REF_DRIVER", None)
+    if ref_driver:
+        env["JGSL_REF_DRIVER"] = "1"
+    log = os.path.join(folder, "log.txt")
+    with open(log, "w") as lf:
+        try:
+            subprocess.run([sys.executable, CLOTH_DRIVER, MIRROR_PYTHON, os.path.join(folder, "cloth.obj"), os.path.join(folder, "ball.obj"), "22", "0.0",
+                            os.path.join(folder, "plate.obj")], cwd=folder, env=env, stdout=lf, stderr=subprocess.STDOUT, timeout=seconds)
+        except subprocess.TimeoutExpired:
+            pass
+    text = open(log, errors="replace").read()
+    kappa = re.findall(r"minDist2 = [0-9.e+-]+, kappa = ([0-9.e+-]+)", text)
+    return kappa, re.findall(r"updated DBCStiff to ([0-9.e+-]+)", text), re.findall(r"PNIter(\d+): Newton res = ([0-9.]+)e", text)
+
+
+@pytest.mark.skipif(not os.path.isdir(MIRROR_PYTHON), reason="mirror of the reference's Python/Drivers absent (scripts/make_ref_mirror.sh)")
+def test_restated_driver_matches_reference_driver_when_squeezed(tmp_path):
+    """The barrier-stiffness rule (kappa doubles when a row closer than 1e-9 gets closer, IMPLICIT_EULER.h:568-598) and the
+    augmented-Lagrangian Dirichlet path (DBCStiff doubling) only show under extreme compression: the rising ball squeezes the cloth
+    against a fixed plate. The squeezed step never converges (in the reference either), so both drivers run for a fixed time and the
+    common prefix of their Newton iterations is compared: same kappa at every iteration, same stiffness updates."""
+    z = np.load(CLOTH_TRACE)
+    k_ref, d_ref, it_ref = _squeeze_log(str(tmp_path / "ref"), z, True, 18)
+    k_own, d_own, it_own = _squeeze_log(str(tmp_path / "own"), z, False, 18)
+    n = min(len(k_ref), len(k_own))
+    if n < 135:
+        pytest.skip("machine too slow to reach the squeezed step in the time given (%d Newton iterations)" % n)
+    assert k_ref[:n] == k_own[:n]
+    changes = [i for i in range(1, n) if k_own[i] != k_own[i - 1]]
+    assert len(changes) >= 3, changes  # the rule fired, at the same iterations in both (the sequences are equal)
+    m = min(len(d_ref), len(d_own))
+    assert m >= 1 and d_ref[:m] == d_own[:m]
+    # Newton iteration indices and the leading digits of the residuals agree over the prefix (the last printed digit may differ:
+    # distances of 1e-9 are differences of O(1) coordinates)
+    m = min(len(it_ref), len(it_own), 3 * n // 4)
+    assert [a[0] for a in it_ref[:m]] == [a[0] for a in it_own[:m]]
+    assert all(abs(float(a[1]) - float(b[1])) <= 2e-3 * max(1.0, float(a[1])) for a, b in zip(it_ref[:m], it_own[:m]))
